@@ -1,0 +1,208 @@
+/*
+ * pvsg.h -- C ABI of libpvsg_sm100.so, the B200 (sm_100a) backend of the OpenPVSG
+ * inference hot path (Mask2Former / Mask2Former-VPS forward + relation head).
+ *
+ * Conventions:
+ *   - plain device pointers + explicit sizes; no torch types; fp32 unless stated;
+ *   - feature maps are TOKEN-MAJOR (NHWC): [B, H, W, C] == [B*H*W, C], C contiguous;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocates, never synchronises, keeps no global state -> CUDA-graph capturable;
+ *   - returns PVSG_OK (0) or a negative error code (see pvsg_error_string); a failed
+ *     argument check launches nothing.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * OpenPVSG tree; "L0" = inside mmcv-full 1.4.0 / mmdet 2.25.0, reached from the cited
+ * reference call site).
+ */
+#ifndef PVSG_H_
+#define PVSG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVSG_VERSION 100
+#define PVSG_OK 0
+#define PVSG_ERR_INVALID_ARG (-1)
+#define PVSG_ERR_UNSUPPORTED (-2)
+#define PVSG_ERR_LAUNCH (-3)
+#define PVSG_ERR_NO_DEVICE (-4)
+
+#define PVSG_ACT_NONE 0
+#define PVSG_ACT_RELU 1
+
+int pvsg_version(void);
+const char* pvsg_error_string(int code);
+/* SM count / compute capability of `device`; PVSG_ERR_NO_DEVICE when no CUDA device. */
+int pvsg_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- dense layers --- */
+
+/* C[b] = act(A[b] (+A2[b]) . W[b]^T + bias + R[b]);  A [M,K] (row stride lda), W [N,K]
+ * (row stride ldw), C [M,N] (ldc), R [M,N] (ldr) optional, A2 same layout as A, optional.
+ * `batch` problems with element strides sA/sW/sC (sA also applies to A2, sC to R).
+ * Replaces torch nn.Linear / F.linear at: mask2former_head.py:376-380 (cls_embed,
+ * mask_embed), L0 FFN / value_proj / sampling_offsets / attention_weights / output_proj /
+ * in_proj / out_proj (configs/mask2former_vps/mask2former_video_r50_base.py:36-88), and
+ * models/relation_head/{base.py:46-48, transformer.py:28-32}. */
+int pvsg_linear(const float* A, const float* A2, const float* W, const float* bias,
+                const float* R, float* C, int64_t M, int64_t N, int64_t K,
+                int64_t lda, int64_t ldw, int64_t ldc, int64_t ldr, int act,
+                int64_t batch, int64_t sA, int64_t sW, int64_t sC, void* stream);
+
+/* y = act(conv2d(x, w) + bias + residual), NHWC, implicit GEMM (no im2col buffer).
+ * x [B,H,W,Cin]; w [Cout,R,S,Cin] (BN already folded in by the host); y/residual
+ * [B,OH,OW,Cout], OH = (H + 2*pad - R)/stride + 1.
+ * Replaces the cuDNN convs of L0 ResNet / ConvModule reached from
+ * models/mask2former_vps/mask2former.py:130 and mask2former_video_head.py:382. */
+int pvsg_conv2d_nhwc(const float* x, const float* w, const float* bias, const float* residual,
+                     float* y, int B, int H, int W, int Cin, int Cout, int R, int S,
+                     int stride, int pad, int act, void* stream);
+
+/* 3x3 stride-2 pad-1 max pooling, NHWC (L0 ResNet stem). */
+int pvsg_maxpool3x3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream);
+
+/* layout converters between the reference's NCHW tensors and token-major. */
+int pvsg_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int pvsg_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, void* stream);
+
+/* y[r,:] = LayerNorm(x[r,:]) * gamma + beta, eps inside sqrt; C in {128,256,512,1024}.
+ * (torch nn.LayerNorm: L0 norms / post_norm mask2former_head.py:375; relation
+ * transformer.py:26,44.) */
+int pvsg_layernorm(const float* x, const float* gamma, const float* beta, float* y,
+                   int64_t rows, int C, float eps, void* stream);
+
+/* GroupNorm over token-major x [B,HW,C] (L0 ConvModule norm GN(32)); stats = workspace
+ * of 2*B*groups doubles (zeroed by the call). y = act(GN(x)). */
+int pvsg_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* y,
+                        double* stats, int B, int64_t HW, int C, int groups, float eps,
+                        int act, void* stream);
+
+/* y[r,:] = x[r,:] + v[:]  (level_embed add, mask2former_head.py:424-426). */
+int pvsg_add_rowvec(const float* x, const float* v, float* y, int64_t rows, int C, void* stream);
+
+/* Bilinear resize, align_corners=False, token-major: dst [B,OH,OW,C] (= or +=) resize(src
+ * [B,IH,IW,C]).  (F.interpolate at L0 pixel-decoder FPN step, and the source-side
+ * pooling that the attn-mask downsample of mask2former_head.py:383-387 reduces to.) */
+int pvsg_bilinear_resize_nhwc(const float* src, float* dst, int B, int IH, int IW, int OH,
+                              int OW, int C, int accumulate, void* stream);
+
+/* Sine positional encoding, token-major out [T*H*W, 2*num_feats] (+ add_vec[2*num_feats]
+ * if non-null).  dim_t [num_feats] / dim_t_z [2*num_feats] are the temperature tables
+ * (host-computed exactly as the reference does).  T = 0 -> 2-D encoding (L0
+ * SinePositionalEncoding); T >= 1 -> models/mask2former_vps/position_encoding.py:55-99. */
+int pvsg_sine_pe(float* out, const float* dim_t, const float* dim_t_z, const float* add_vec,
+                 int T, int H, int W, int num_feats, float scale, float eps, void* stream);
+
+/* ------------------------------------------------- multi-scale deformable attn --- */
+
+/* mmcv MultiScaleDeformableAttnFunction.forward (L0; selected by cfg
+ * mask2former_video_r50_base.py:38-47).  value [B,N,H,D]; spatial_shapes [L,2] (h,w) and
+ * level_start_index [L] are HOST int64 arrays; sampling_locations [B,Nq,H,L,P,2] in
+ * [0,1] (x,y); attention_weights [B,Nq,H,L,P]; out [B,Nq,H*D].  D must be 32. */
+int pvsg_msda_forward(const float* value, const int64_t* spatial_shapes,
+                      const int64_t* level_start_index, const float* sampling_locations,
+                      const float* attention_weights, float* out, int B, int64_t N,
+                      int64_t Nq, int H, int D, int L, int P, void* stream);
+
+/* Fused variant: takes the RAW projections proj [B,Nq,H*L*P*3] = [offsets (H,L,P,2) |
+ * attention logits (H,L,P)] and reference points ref [Nq,2] (x,y in [0,1], shared by all
+ * levels) and does softmax over L*P, location arithmetic, bilinear sampling and the
+ * weighted sum in one kernel (mmcv MultiScaleDeformableAttention.forward minus its
+ * Linear layers). */
+int pvsg_msda_fused_forward(const float* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const float* proj,
+                            const float* ref, float* out, int B, int64_t N, int64_t Nq,
+                            int H, int D, int L, int P, void* stream);
+
+/* ------------------------------------------------------------------ attention --- */
+
+/* out = softmax(scale * Q K^T + mask) V per (batch, head); token strides in floats:
+ * element (b, i, h, d) of Q is Q[b*q_bs + i*q_ts + h*D + d] (same for K, V, out).
+ * mask: optional uint8 [B,Lq,Lk], non-zero = blocked, shared by all heads
+ * (mask2former_head.py:388-391 repeats it per head); row_open: optional int32 [B,Lq]
+ * = number of un-blocked keys of that row -- rows with 0 attend to everything
+ * (mask2former_head.py:453-454).  ws: workspace of pvsg_attention_workspace_bytes.
+ * D in {32, 128}.  Replaces nn.MultiheadAttention core (L0 MultiheadAttention reached
+ * from mask2former_head.py:457-468) and the encoder self-attention of
+ * models/relation_head/base.py:32-37, transformer.py:20-25. */
+int64_t pvsg_attention_workspace_bytes(int B, int H, int Lq, int Lk, int D);
+int pvsg_attention(const float* Q, const float* K, const float* V, const uint8_t* mask,
+                   const int32_t* row_open, float* out, void* ws, int B, int H, int Lq,
+                   int Lk, int D, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts,
+                   int64_t v_bs, int64_t v_ts, int64_t o_bs, int64_t o_ts, float scale,
+                   void* stream);
+
+/* ------------------------------------------------------------ mask logits ------- */
+
+/* The per-frame query x pixel contraction einsum('bqc,bchw->bqhw')
+ * (mask2former_head.py:382, mask2former_video_head.py:344) on token-major features:
+ * logits[b,q,p] = sum_c embed[b,q,c] * feat[b,p,c].
+ *   logits    : optional fp32 [B,Q,P] output;
+ *   attn_mask : optional uint8 [B,Q,P] = (logit < 0)  -- i.e. sigmoid < 0.5,
+ *               mask2former_head.py:391 -- with row_open[b,q] = #(logit >= 0)
+ *               (int32, zeroed by the call).
+ * For the attention mask of the NEXT decoder layer pass feat = the mask features
+ * bilinearly resized to that layer's (h_l, w_l) (pvsg_bilinear_resize_nhwc): the
+ * align_corners=False downsample is linear, so it commutes with the contraction. */
+int pvsg_mask_logits(const float* embed, const float* feat, float* logits, uint8_t* attn_mask,
+                     int32_t* row_open, int B, int Q, int64_t P, int C, void* stream);
+
+/* --------------------------------------------------------- panoptic fusion ------ */
+
+/* Fused replacement of: final x4 bilinear upsample (mask2former_head.py:674-679 /
+ * mask2former_video_head.py:662-667) + crop + optional rescale + sigmoid + score-weighted
+ * argmax + per-segment area tests + id assignment
+ * (mask2former_fusion_head.py:96-171, :373-383).  The upsampled logits never exist in
+ * memory and there is no host round trip.
+ *   cls_logits [Q,NC+1]; mask_logits [Q,h,w] (low-res, un-upsampled);
+ *   (in_h,in_w) = batch_input_shape, (img_h,img_w) = img_shape crop, (out_h,out_w) =
+ *   ori_shape if rescale else img_shape;
+ *   pan_out  int32 [out_h,out_w] (void = NC);
+ *   seg_info int32 [1 + 4*Q]: [0] = n_kept, then per kept query k (query order):
+ *            (query index, class, seg_id or -1 if dropped, final area);
+ *   work     int32 [4*Q] scratch (areas); scores float [Q] scratch;
+ *   pix_ws   uint16 [out_h*out_w] scratch (winner index + ">= 0.5" bit per pixel). */
+int pvsg_panoptic_fuse(const float* cls_logits, const float* mask_logits, int Q, int NC,
+                       int num_things, int h, int w, int in_h, int in_w, int img_h, int img_w,
+                       int out_h, int out_w, float object_mask_thr, double iou_thr,
+                       int filter_low_score, int instance_offset, int32_t* pan_out,
+                       int32_t* seg_info, int32_t* work, float* scores, uint16_t* pix_ws,
+                       void* stream);
+
+/* Instance branch (mask2former_fusion_head.py:192-242) for `n` candidate queries already
+ * selected by the caller's top-k: for each candidate the binary mask (upsampled logit > 0)
+ * statistics at output resolution: stats float [n,2] = (sum of sigmoid over the mask, pixel
+ * count); boxes int32 [n,4] = mask2bbox (x_min, y_min, x_max+1, y_max+1), zeros when empty;
+ * masks_out (optional) uint8 [n,out_h,out_w]. */
+int pvsg_instance_masks(const float* mask_logits, const int32_t* query_idx, int n, int h, int w,
+                        int in_h, int in_w, int img_h, int img_w, int out_h, int out_w,
+                        float* stats, int32_t* boxes, uint8_t* masks_out, void* stream);
+
+/* ------------------------------------------------------------ relation head ----- */
+
+/* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */
+int pvsg_max_over_time(const float* x, float* y, int N, int T, int C, void* stream);
+
+/* PairProposalNetwork.forward (base.py:49-62), factorised: U = sub_tok W1[:, :F]^T + b1 and
+ * V = obj_tok W1[:, F:]^T are precomputed [N,Hd] (two pvsg_linear calls);
+ * pair[i,j] = b2 + sum_h w2[h] * relu(U[i,h] + V[j,h]) for i != j, 0 on the diagonal. */
+int pvsg_pair_proposal(const float* U, const float* V, const float* w2, const float* b2,
+                       float* pair, int N, int Hd, void* stream);
+
+/* pick_top_pairs_eval (test_utils.py:4-22): diagonal -> -inf, the min(N*N, k) largest
+ * entries in descending order (ties: lower flat index first); pairs int32 [k,2] = (s,o),
+ * diagonal hits removed; n_out int32 [1]. N*N <= 65536*4. */
+int pvsg_top_pairs(const float* pair, int N, int k, int32_t* pairs, int32_t* n_out, void* stream);
+
+/* concatenate_sub_obj (train_utils.py:67-81) + PositionalEncoding add (transformer.py:77-81):
+ * out[p,t,:] = [sub[s_p,t,:], obj[o_p,t,:]] + pe[t,:] (pe optional, [T,2F]). */
+int pvsg_gather_pairs(const float* sub, const float* obj, const int32_t* pairs, const float* pe,
+                      float* out, int P, int T, int F, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVSG_H_ */

@@ -1,0 +1,365 @@
+// fp32 SIMT GEMM / implicit-GEMM convolution (round-1 baseline engine).
+//
+//   C[M,N] = act(A[M,K] (+A2) . W[N,K]^T + bias + R)
+//
+// One kernel template serves nn.Linear, the mask-logit contraction (with a sign-mask
+// epilogue) and NHWC convolutions (the A tile is gathered on the fly from the input
+// feature map: no im2col buffer).  Tiles BM x BN x 16, register micro-tile (4*MI) x (4*NI),
+// double-buffered shared memory with register prefetch, float4 global loads.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BK = 16;
+
+struct GemmParams {
+    const float* A;
+    const float* A2;
+    const float* W;
+    const float* bias;
+    const float* R;
+    float* C;
+    uint8_t* mask;      // sign-mask epilogue output (same indexing as C), or null
+    int32_t* row_open;  // per-row count of (value >= 0), with mask
+    int64_t M, N, K, lda, ldw, ldc, ldr;
+    int64_t sA, sW, sC;
+    int act;
+    // convolution geometry (CONV only)
+    int H, Wd, Cin, OH, OW, S, stride, pad;
+};
+
+template <int BM, int BN, int MI, int NI, bool VEC, bool CONV>
+__global__ void __launch_bounds__((BM / (4 * MI)) * (BN / (4 * NI)), (BM * BN >= 128 * 128) ? 2 : 4)
+gemm_kernel(GemmParams p) {
+    constexpr int TX = BN / (4 * NI);
+    constexpr int TY = BM / (4 * MI);
+    constexpr int T = TX * TY;
+    constexpr int LDA_S = BM + 4;
+    constexpr int LDB_S = BN + 4;
+    __shared__ __align__(16) float As[2][BK][LDA_S];
+    __shared__ __align__(16) float Bs[2][BK][LDB_S];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int64_t m0 = (int64_t)blockIdx.y * BM;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int64_t bz = blockIdx.z;
+    const float* A = p.A + bz * p.sA;
+    const float* A2 = p.A2 ? p.A2 + bz * p.sA : nullptr;
+    const float* W = p.W + bz * p.sW;
+
+    // ---- global -> register staging -------------------------------------------------
+    constexpr int LA = VEC ? (BM * 4 + T - 1) / T : (BM * BK + T - 1) / T;
+    constexpr int LB = VEC ? (BN * 4 + T - 1) / T : (BN * BK + T - 1) / T;
+    float4 ra[VEC ? LA : 1];
+    float4 rb[VEC ? LB : 1];
+    float sa[VEC ? 1 : LA];
+    float sb[VEC ? 1 : LB];
+    // conv: per staged row, the top-left input coordinate and batch base
+    int cv_ih0[(VEC && CONV) ? LA : 1], cv_iw0[(VEC && CONV) ? LA : 1];
+    int64_t cv_base[(VEC && CONV) ? LA : 1];
+    if (VEC && CONV) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            int idx = tid + i * T;
+            int64_t m = m0 + (idx >> 2);
+            if (m < p.M && idx < BM * 4) {
+                int ow = (int)(m % p.OW);
+                int64_t t = m / p.OW;
+                int oh = (int)(t % p.OH);
+                int64_t b = t / p.OH;
+                cv_ih0[i] = oh * p.stride - p.pad;
+                cv_iw0[i] = ow * p.stride - p.pad;
+                cv_base[i] = b * p.H * p.Wd * (int64_t)p.Cin;
+            } else {
+                cv_ih0[i] = -(1 << 28);
+                cv_iw0[i] = 0;
+                cv_base[i] = 0;
+            }
+        }
+    }
+
+    auto load_tile = [&](int64_t k0) {
+        if (VEC) {
+            int r = 0, s = 0, c0 = 0;
+            if (CONV) {
+                int rs = (int)(k0 / p.Cin);
+                c0 = (int)(k0 - (int64_t)rs * p.Cin);
+                r = rs / p.S;
+                s = rs - r * p.S;
+            }
+#pragma unroll
+            for (int i = 0; i < LA; ++i) {
+                int idx = tid + i * T;
+                int row = idx >> 2, kq = idx & 3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < BM * 4) {
+                    if (CONV) {
+                        int ih = cv_ih0[i] + r, iw = cv_iw0[i] + s;
+                        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) {
+                            v = __ldg(reinterpret_cast<const float4*>(
+                                A + cv_base[i] + ((int64_t)ih * p.Wd + iw) * p.Cin + c0 + kq * 4));
+                        }
+                    } else {
+                        int64_t m = m0 + row, k = k0 + kq * 4;
+                        if (m < p.M && k < p.K) {
+                            v = __ldg(reinterpret_cast<const float4*>(A + m * p.lda + k));
+                            if (A2) {
+                                float4 u = __ldg(reinterpret_cast<const float4*>(A2 + m * p.lda + k));
+                                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                            }
+                        }
+                    }
+                }
+                ra[i] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+                int idx = tid + i * T;
+                int row = idx >> 2, kq = idx & 3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                int64_t n = n0 + row, k = k0 + kq * 4;
+                if (idx < BN * 4 && n < p.N && k < p.K)
+                    v = __ldg(reinterpret_cast<const float4*>(W + n * p.ldw + k));
+                rb[i] = v;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < LA; ++i) {
+                int idx = tid + i * T;
+                int row = idx / BK, kk = idx % BK;
+                int64_t m = m0 + row, k = k0 + kk;
+                float v = 0.f;
+                if (idx < BM * BK && m < p.M && k < p.K) {
+                    if (CONV) {
+                        int c = (int)(k % p.Cin);
+                        int rs = (int)(k / p.Cin);
+                        int r = rs / p.S, s = rs - r * p.S;
+                        int ow = (int)(m % p.OW);
+                        int64_t t = m / p.OW;
+                        int oh = (int)(t % p.OH);
+                        int64_t b = t / p.OH;
+                        int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + s;
+                        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd)
+                            v = __ldg(A + ((b * p.H + ih) * p.Wd + iw) * (int64_t)p.Cin + c);
+                    } else {
+                        v = __ldg(A + m * p.lda + k);
+                        if (A2) v += __ldg(A2 + m * p.lda + k);
+                    }
+                }
+                sa[i] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+                int idx = tid + i * T;
+                int row = idx / BK, kk = idx % BK;
+                int64_t n = n0 + row, k = k0 + kk;
+                sb[i] = (idx < BN * BK && n < p.N && k < p.K) ? __ldg(W + n * p.ldw + k) : 0.f;
+            }
+        }
+    };
+    auto store_tile = [&](int buf) {
+        if (VEC) {
+#pragma unroll
+            for (int i = 0; i < LA; ++i) {
+                int idx = tid + i * T;
+                if (idx < BM * 4) {
+                    int row = idx >> 2, kq = (idx & 3) * 4;
+                    As[buf][kq + 0][row] = ra[i].x;
+                    As[buf][kq + 1][row] = ra[i].y;
+                    As[buf][kq + 2][row] = ra[i].z;
+                    As[buf][kq + 3][row] = ra[i].w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+                int idx = tid + i * T;
+                if (idx < BN * 4) {
+                    int row = idx >> 2, kq = (idx & 3) * 4;
+                    Bs[buf][kq + 0][row] = rb[i].x;
+                    Bs[buf][kq + 1][row] = rb[i].y;
+                    Bs[buf][kq + 2][row] = rb[i].z;
+                    Bs[buf][kq + 3][row] = rb[i].w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < LA; ++i) {
+                int idx = tid + i * T;
+                if (idx < BM * BK) As[buf][idx % BK][idx / BK] = sa[i];
+            }
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+                int idx = tid + i * T;
+                if (idx < BN * BK) Bs[buf][idx % BK][idx / BK] = sb[i];
+            }
+        }
+    };
+
+    float acc[4 * MI][4 * NI];
+#pragma unroll
+    for (int i = 0; i < 4 * MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4 * NI; ++j) acc[i][j] = 0.f;
+
+    const int64_t nk = (p.K + BK - 1) / BK;
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int64_t kt = 0; kt < nk; ++kt) {
+        const int buf = (int)(kt & 1);
+        if (kt + 1 < nk) load_tile((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4 * MI], b[4 * NI];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                float4 v = *reinterpret_cast<const float4*>(&As[buf][k][mi * (BM / MI) + ty * 4]);
+                a[mi * 4 + 0] = v.x; a[mi * 4 + 1] = v.y; a[mi * 4 + 2] = v.z; a[mi * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) {
+                float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][ni * (BN / NI) + tx * 4]);
+                b[ni * 4 + 0] = v.x; b[ni * 4 + 1] = v.y; b[ni * 4 + 2] = v.z; b[ni * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4 * MI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4 * NI; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) store_tile(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue ---------------------------------------------------------------------
+    float* C = p.C ? p.C + bz * p.sC : nullptr;
+    const float* R = p.R ? p.R + bz * p.sC : nullptr;
+    uint8_t* mask = p.mask ? p.mask + bz * p.sC : nullptr;
+    const bool vec_out = ((p.N & 3) == 0) && ((p.ldc & 3) == 0) && (!R || (p.ldr & 3) == 0);
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t m = m0 + mi * (BM / MI) + ty * 4 + i;
+            if (m >= p.M) continue;
+            int open = 0;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) {
+                const int64_t n = n0 + ni * (BN / NI) + tx * 4;
+                if (n >= p.N) continue;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = acc[mi * 4 + i][ni * 4 + j];
+                    if (p.bias && n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                }
+                if (R) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < p.N) v[j] += __ldg(R + m * p.ldr + n + j);
+                }
+                if (p.act == PVSG_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (C) {
+                    if (vec_out) {
+                        *reinterpret_cast<float4*>(C + m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (n + j < p.N) C[m * p.ldc + n + j] = v[j];
+                    }
+                }
+                if (mask) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (n + j < p.N) {
+                            bool blocked = v[j] < 0.f;
+                            mask[m * p.ldc + n + j] = blocked ? 1 : 0;
+                            open += blocked ? 0 : 1;
+                        }
+                    }
+                }
+            }
+            if (mask && p.row_open && open) atomicAdd(p.row_open + bz * p.M + m, open);
+        }
+    }
+}
+
+template <int BM, int BN, int MI, int NI, bool VEC, bool CONV>
+int launch(const GemmParams& p, int64_t batch, cudaStream_t st) {
+    constexpr int T = (BM / (4 * MI)) * (BN / (4 * NI));
+    dim3 grid((unsigned)((p.N + BN - 1) / BN), (unsigned)((p.M + BM - 1) / BM), (unsigned)batch);
+    if (grid.y > 65535 || grid.z > 65535) return PVSG_ERR_UNSUPPORTED;
+    gemm_kernel<BM, BN, MI, NI, VEC, CONV><<<grid, T, 0, st>>>(p);
+    return pvsg_launch_status();
+}
+
+template <bool VEC, bool CONV>
+int dispatch(const GemmParams& p, int64_t batch, cudaStream_t st) {
+    // Big tile when it fills the machine; small tile for the decoder's M = 100 GEMMs.
+    const int64_t big_ctas = ((p.M + 127) / 128) * ((p.N + 127) / 128) * batch;
+    if (p.M > 64 && p.N > 64 && big_ctas >= 120) return launch<128, 128, 2, 2, VEC, CONV>(p, batch, st);
+    if (p.N <= 32) return launch<64, 32, 1, 1, VEC, CONV>(p, batch, st);
+    return launch<32, 64, 1, 1, VEC, CONV>(p, batch, st);
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int pvsg_linear(const float* A, const float* A2, const float* W, const float* bias,
+                           const float* R, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldw, int64_t ldc, int64_t ldr, int act, int64_t batch,
+                           int64_t sA, int64_t sW, int64_t sC, void* stream) {
+    PVSG_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0 && batch > 0);
+    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N));
+    PVSG_CHECK_ARG(act == PVSG_ACT_NONE || act == PVSG_ACT_RELU);
+    GemmParams p{};
+    p.A = A; p.A2 = A2; p.W = W; p.bias = bias; p.R = R; p.C = C;
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.ldr = ldr;
+    p.sA = sA; p.sW = sW; p.sC = sC; p.act = act;
+    const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldw % 4 == 0) && (sA % 4 == 0) &&
+                     (sW % 4 == 0) && aligned16(A) && aligned16(W) && (!A2 || aligned16(A2));
+    return vec ? dispatch<true, false>(p, batch, as_stream(stream))
+               : dispatch<false, false>(p, batch, as_stream(stream));
+}
+
+extern "C" int pvsg_mask_logits(const float* embed, const float* feat, float* logits,
+                                uint8_t* attn_mask, int32_t* row_open, int B, int Q, int64_t P,
+                                int C, void* stream) {
+    PVSG_CHECK_ARG(embed && feat && (logits || attn_mask) && B > 0 && Q > 0 && P > 0 && C > 0);
+    PVSG_CHECK_ARG(C % 4 == 0 && aligned16(embed) && aligned16(feat));
+    cudaStream_t st = as_stream(stream);
+    if (attn_mask && row_open) {
+        if (cudaMemsetAsync(row_open, 0, sizeof(int32_t) * (size_t)B * Q, st) != cudaSuccess)
+            return PVSG_ERR_LAUNCH;
+    }
+    GemmParams p{};
+    p.A = embed; p.W = feat; p.C = logits; p.mask = attn_mask; p.row_open = row_open;
+    p.M = Q; p.N = P; p.K = C; p.lda = C; p.ldw = C; p.ldc = P; p.ldr = 0;
+    p.sA = (int64_t)Q * C; p.sW = P * C; p.sC = (int64_t)Q * P; p.act = PVSG_ACT_NONE;
+    return dispatch<true, false>(p, B, st);
+}
+
+extern "C" int pvsg_conv2d_nhwc(const float* x, const float* w, const float* bias,
+                                const float* residual, float* y, int B, int H, int W, int Cin,
+                                int Cout, int R, int S, int stride, int pad, int act, void* stream) {
+    PVSG_CHECK_ARG(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0);
+    PVSG_CHECK_ARG(stride > 0 && pad >= 0);
+    PVSG_CHECK_ARG(act == PVSG_ACT_NONE || act == PVSG_ACT_RELU);
+    const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+    PVSG_CHECK_ARG(OH > 0 && OW > 0);
+    GemmParams p{};
+    p.A = x; p.W = w; p.bias = bias; p.R = residual; p.C = y;
+    p.M = (int64_t)B * OH * OW; p.N = Cout; p.K = (int64_t)R * S * Cin;
+    p.lda = p.K; p.ldw = p.K; p.ldc = Cout; p.ldr = Cout; p.act = act;
+    p.H = H; p.Wd = W; p.Cin = Cin; p.OH = OH; p.OW = OW; p.S = S; p.stride = stride; p.pad = pad;
+    if (R == 1 && S == 1 && stride == 1 && pad == 0 && Cin % 4 == 0 && aligned16(x) && aligned16(w)) {
+        p.lda = Cin;  // a 1x1 stride-1 conv is a plain GEMM over tokens
+        return dispatch<true, false>(p, 1, as_stream(stream));
+    }
+    if (Cin % BK == 0 && aligned16(x) && aligned16(w)) return dispatch<true, true>(p, 1, as_stream(stream));
+    return dispatch<false, true>(p, 1, as_stream(stream));
+}

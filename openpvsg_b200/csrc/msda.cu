@@ -1,0 +1,158 @@
+// Multi-scale deformable attention (sampling + aggregation), D = 32 channels per head.
+//
+// One warp owns one (query, head).  The warp is split in 4 groups of 8 lanes; a group
+// covers the 32 channels with one float4 per lane (one 128-byte line per bilinear corner)
+// and walks the samples s = g, g+4, g+8, ... of the L*P samples; the four partial sums
+// are combined with two warp shuffles.  In the fused variant the warp also does the
+// softmax over the L*P attention logits and the location arithmetic from the raw
+// projections, so sampling_locations / attention_weights never exist in memory.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_LEVELS = 8;
+
+struct MsdaLevels {
+    int h[MAX_LEVELS];
+    int w[MAX_LEVELS];
+    int64_t start[MAX_LEVELS];
+};
+
+// Bilinear sample of value[b, start + (y, x), head, 4*q4 .. 4*q4+3] with zero padding,
+// pixel coordinates (x, y) already in the align_corners=False frame (loc * size - 0.5).
+__device__ __forceinline__ void sample_acc(const float4* __restrict__ vbase, int hgt, int wid, int64_t pix_stride,
+                                           float x, float y, float aw, float4& acc) {
+    // mmcv's CUDA op: skip samples entirely outside (-1, size)
+    if (!(y > -1.f && x > -1.f && y < (float)hgt && x < (float)wid)) return;
+    const int y0 = (int)floorf(y), x0 = (int)floorf(x);
+    const float ly = y - (float)y0, lx = x - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const bool y0v = y0 >= 0, y1v = y0 + 1 <= hgt - 1, x0v = x0 >= 0, x1v = x0 + 1 <= wid - 1;
+    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+    if (y0v && x0v) v00 = __ldg(vbase + ((int64_t)y0 * wid + x0) * pix_stride);
+    if (y0v && x1v) v01 = __ldg(vbase + ((int64_t)y0 * wid + x0 + 1) * pix_stride);
+    if (y1v && x0v) v10 = __ldg(vbase + ((int64_t)(y0 + 1) * wid + x0) * pix_stride);
+    if (y1v && x1v) v11 = __ldg(vbase + ((int64_t)(y0 + 1) * wid + x0 + 1) * pix_stride);
+    const float w00 = hy * hx * aw, w01 = hy * lx * aw, w10 = ly * hx * aw, w11 = ly * lx * aw;
+    acc.x += w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+    acc.y += w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+    acc.z += w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+    acc.w += w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
+                                                   const float* __restrict__ loc_or_proj,
+                                                   const float* __restrict__ aw_or_ref, float* __restrict__ out,
+                                                   int64_t N, int64_t Nq, int H, int L, int P, int64_t total) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, q4 = lane & 7;
+    const int LP = L * P;
+    // work item = (b, query, head); consecutive warps of a CTA take consecutive QUERIES of one
+    // head so that their sampling neighbourhoods overlap in L1.
+    const int wpb = blockDim.x >> 5;
+    const int64_t qblocks = (Nq + wpb - 1) / wpb;
+    for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+        const int64_t qb = blk % qblocks;
+        const int64_t t = blk / qblocks;
+        const int head = (int)(t % H);
+        const int64_t b = t / H;
+        const int64_t nq = qb * wpb + (threadIdx.x >> 5);
+        if (nq >= Nq) continue;
+        const int64_t pix_stride = (int64_t)H * 8;  // float4 per pixel (H heads * 32 ch / 4)
+        const float4* vb = reinterpret_cast<const float4*>(value) + (b * N * H + head) * 8 + q4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FUSED) {
+            // proj row: [H*LP*2 offsets | H*LP logits]
+            const float* prow = loc_or_proj + (b * Nq + nq) * (int64_t)(H * LP * 3);
+            const float* offp = prow + (int64_t)head * LP * 2;
+            const float* lgp = prow + (int64_t)H * LP * 2 + (int64_t)head * LP;
+            const float lg = lane < LP ? __ldg(lgp + lane) : -INFINITY;
+            const float mx = warp_max(lg);
+            const float e = lane < LP ? __expf(lg - mx) : 0.f;
+            const float wgt = e / warp_sum(e);
+            const float o0 = lane < LP ? __ldg(offp + 2 * lane) : 0.f;      // x offset of sample `lane`
+            const float o1 = lane < LP ? __ldg(offp + 2 * lane + 1) : 0.f;  // y offset
+            const float rx = __ldg(aw_or_ref + nq * 2), ry = __ldg(aw_or_ref + nq * 2 + 1);
+            for (int s0 = 0; s0 < LP; s0 += 4) {  // trip count is warp-uniform (full-mask shuffles)
+                const int s = min(s0 + g, LP - 1);
+                float aw = __shfl_sync(0xffffffffu, wgt, s);
+                const float ox = __shfl_sync(0xffffffffu, o0, s);
+                const float oy = __shfl_sync(0xffffffffu, o1, s);
+                if (s0 + g >= LP) aw = 0.f;
+                const int l = s / P;
+                const int hgt = lv.h[l], wid = lv.w[l];
+                // loc = ref + off / (w, h); pixel = loc * size - 0.5
+                const float x = (rx + ox / (float)wid) * (float)wid - 0.5f;
+                const float y = (ry + oy / (float)hgt) * (float)hgt - 0.5f;
+                sample_acc(vb + lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, aw, acc);
+            }
+        } else {
+            const float* locp = loc_or_proj + ((b * Nq + nq) * H + head) * (int64_t)LP * 2;
+            const float* awp = aw_or_ref + ((b * Nq + nq) * H + head) * (int64_t)LP;
+            for (int s = g; s < LP; s += 4) {
+                const int l = s / P;
+                const int hgt = lv.h[l], wid = lv.w[l];
+                const float x = __ldg(locp + 2 * s) * (float)wid - 0.5f;
+                const float y = __ldg(locp + 2 * s + 1) * (float)hgt - 0.5f;
+                sample_acc(vb + lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, __ldg(awp + s), acc);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (g == 0) reinterpret_cast<float4*>(out)[((b * Nq + nq) * H + head) * 8 + q4] = acc;
+    }
+}
+
+int fill_levels(MsdaLevels& lv, const int64_t* spatial_shapes, const int64_t* level_start_index, int L,
+                int64_t N) {
+    if (L <= 0 || L > MAX_LEVELS) return PVSG_ERR_UNSUPPORTED;
+    int64_t tot = 0;
+    for (int l = 0; l < L; ++l) {
+        lv.h[l] = (int)spatial_shapes[2 * l];
+        lv.w[l] = (int)spatial_shapes[2 * l + 1];
+        lv.start[l] = level_start_index[l];
+        if (lv.h[l] <= 0 || lv.w[l] <= 0 || lv.start[l] != tot) return PVSG_ERR_INVALID_ARG;
+        tot += (int64_t)lv.h[l] * lv.w[l];
+    }
+    return tot == N ? PVSG_OK : PVSG_ERR_INVALID_ARG;
+}
+
+template <bool FUSED>
+int launch(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+           const float* a, const float* b2, float* out, int B, int64_t N, int64_t Nq, int H, int D, int L,
+           int P, void* stream) {
+    PVSG_CHECK_ARG(value && spatial_shapes && level_start_index && a && b2 && out);
+    PVSG_CHECK_ARG(B > 0 && N > 0 && Nq > 0 && H > 0 && P > 0);
+    if (D != 32 || L * P > 32) return PVSG_ERR_UNSUPPORTED;
+    MsdaLevels lv{};
+    int rc = fill_levels(lv, spatial_shapes, level_start_index, L, N);
+    if (rc != PVSG_OK) return rc;
+    const int wpb = 8;
+    const int64_t total = (int64_t)B * H * ((Nq + wpb - 1) / wpb);
+    const unsigned grid = (unsigned)imin64(total, 148 * 64);
+    msda_kernel<FUSED><<<grid, wpb * 32, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P, total);
+    return pvsg_launch_status();
+}
+
+}  // namespace
+
+extern "C" int pvsg_msda_forward(const float* value, const int64_t* spatial_shapes,
+                                 const int64_t* level_start_index, const float* sampling_locations,
+                                 const float* attention_weights, float* out, int B, int64_t N, int64_t Nq,
+                                 int H, int D, int L, int P, void* stream) {
+    return launch<false>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                         out, B, N, Nq, H, D, L, P, stream);
+}
+
+extern "C" int pvsg_msda_fused_forward(const float* value, const int64_t* spatial_shapes,
+                                       const int64_t* level_start_index, const float* proj,
+                                       const float* ref, float* out, int B, int64_t N, int64_t Nq, int H,
+                                       int D, int L, int P, void* stream) {
+    return launch<true>(value, spatial_shapes, level_start_index, proj, ref, out, B, N, Nq, H, D, L, P, stream);
+}

@@ -1,0 +1,296 @@
+// Fused panoptic / instance post-processing (MaskFormerFusionHeadCustom, reference
+// models/mask2former/mask2former_fusion_head.py:96-242, :325-404) working directly on the
+// low-resolution mask logits: the x4 bilinear upsample, crop, optional rescale, sigmoid,
+// score-weighted argmax and the per-segment area tests all happen in registers.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NONE = 0x7fff;
+
+struct UpGeom {
+    int h, w;            // low-res logits
+    int in_h, in_w;      // batch_input_shape (upsample target)
+    int img_h, img_w;    // crop
+    int out_h, out_w;    // final size
+    float sh, sw;        // h / in_h, w / in_w
+    float rh, rw;        // img_h / out_h, img_w / out_w (rescale stage)
+    int rescale;         // out != img
+};
+
+// logits upsampled to (in_h, in_w) at integer pixel (y, x): same operation order as ATen's
+// upsample_bilinear2d: (a*wx0 + b*wx1)*wy0 + (c*wx0 + d*wx1)*wy1.
+__device__ __forceinline__ float up_logit(const float* __restrict__ lg, const UpGeom& g, int y, int x) {
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    bilinear_coord(y, g.sh, g.h, y0, y1, wy0, wy1);
+    bilinear_coord(x, g.sw, g.w, x0, x1, wx0, wx1);
+    const float a = __ldg(lg + y0 * g.w + x0), b = __ldg(lg + y0 * g.w + x1);
+    const float c = __ldg(lg + y1 * g.w + x0), d = __ldg(lg + y1 * g.w + x1);
+    return (a * wx0 + b * wx1) * wy0 + (c * wx0 + d * wx1) * wy1;
+}
+
+// value of the final (cropped, optionally rescaled) logit map at output pixel (oy, ox)
+__device__ __forceinline__ float final_logit(const float* __restrict__ lg, const UpGeom& g, int oy, int ox) {
+    if (!g.rescale) return up_logit(lg, g, oy, ox);
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    bilinear_coord(oy, g.rh, g.img_h, y0, y1, wy0, wy1);
+    bilinear_coord(ox, g.rw, g.img_w, x0, x1, wx0, wx1);
+    const float a = up_logit(lg, g, y0, x0), b = up_logit(lg, g, y0, x1);
+    const float c = up_logit(lg, g, y1, x0), d = up_logit(lg, g, y1, x1);
+    return (a * wx0 + b * wx1) * wy0 + (c * wx0 + d * wx1) * wy1;
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+// Step 1 (one CTA): per-query softmax max / argmax, keep test, compaction in query order.
+__global__ void __launch_bounds__(128) pan_select_kernel(const float* __restrict__ cls, int Q, int NC, float thr,
+                                                         int32_t* __restrict__ seg_info, int32_t* __restrict__ work,
+                                                         float* __restrict__ scores) {
+    __shared__ int keep[1024];
+    __shared__ float sc[1024];
+    __shared__ int lb[1024];
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        const float* row = cls + (int64_t)q * (NC + 1);
+        float mx = -INFINITY;
+        int arg = 0;
+        for (int c = 0; c <= NC; ++c) {
+            const float v = row[c];
+            if (v > mx) { mx = v; arg = c; }
+        }
+        float sum = 0.f;
+        for (int c = 0; c <= NC; ++c) sum += expf(row[c] - mx);
+        const float score = 1.f / sum;  // softmax value of the arg-max class
+        sc[q] = score;
+        lb[q] = arg;
+        keep[q] = (arg != NC && score > thr) ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int q = 0; q < Q; ++q) {
+            if (keep[q]) {
+                seg_info[1 + 4 * n + 0] = q;
+                seg_info[1 + 4 * n + 1] = lb[q];
+                seg_info[1 + 4 * n + 2] = -1;
+                seg_info[1 + 4 * n + 3] = 0;
+                scores[n] = sc[q];
+                ++n;
+            }
+        }
+        seg_info[0] = n;
+        for (int i = 0; i < 4 * Q; ++i) work[i] = 0;
+    }
+}
+
+// Step 2: one thread per output pixel.  work[0..Q) = mask_area (argmax == k), work[Q..2Q) =
+// original_area (sigmoid >= 0.5), work[2Q..3Q) = final area (argmax == k and sigmoid >= 0.5).
+__global__ void __launch_bounds__(256) pan_pixel_kernel(const float* __restrict__ mask_logits, UpGeom g, int Q,
+                                                        const int32_t* __restrict__ seg_info,
+                                                        const float* __restrict__ scores, int32_t* __restrict__ work,
+                                                        uint16_t* __restrict__ pix) {
+    extern __shared__ int sh_cnt[];  // [3 * n_kept]
+    const int n = seg_info[0];
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    const int64_t npix = (int64_t)g.out_h * g.out_w;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < npix;
+    const int oy = valid ? (int)(p / g.out_w) : 0, ox = valid ? (int)(p % g.out_w) : 0;
+    const int lane = threadIdx.x & 31;
+    float best = -INFINITY;
+    int bestk = NONE;
+    bool best_hi = false;
+    const int64_t lstride = (int64_t)g.h * g.w;
+    for (int k = 0; k < n; ++k) {
+        const int q = seg_info[1 + 4 * k];
+        float sig = 0.f;
+        bool hi = false;
+        if (valid) {
+            sig = sigmoidf_(final_logit(mask_logits + q * lstride, g, oy, ox));
+            hi = sig >= 0.5f;
+            const float prob = scores[k] * sig;
+            if (prob > best) { best = prob; bestk = k; best_hi = hi; }  // first max wins (torch argmax)
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hi);
+        if (lane == 0 && bal) atomicAdd(&sh_cnt[n + k], __popc(bal));
+    }
+    // histogram of winners, warp-aggregated
+    {
+        const unsigned peers = __match_any_sync(0xffffffffu, bestk);
+        const unsigned hi_peers = __ballot_sync(0xffffffffu, best_hi) & peers;
+        if (valid && bestk != NONE && lane == (__ffs(peers) - 1)) {
+            atomicAdd(&sh_cnt[bestk], __popc(peers));
+            if (hi_peers) atomicAdd(&sh_cnt[2 * n + bestk], __popc(hi_peers));
+        }
+    }
+    if (valid) pix[p] = (uint16_t)(bestk | (best_hi ? 0x8000 : 0));
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
+        const int v = sh_cnt[i];
+        if (v) atomicAdd(&work[(i / n) * Q + (i % n)], v);
+    }
+}
+
+// Step 3 (one thread): the sequential accept / id-assignment loop,
+// mask2former_fusion_head.py:140-169.
+__global__ void pan_decide_kernel(int Q, int num_things, double iou_thr, int filter_low_score, int instance_offset,
+                                  int32_t* __restrict__ seg_info, const int32_t* __restrict__ work) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = seg_info[0];
+    int instance_id = 1;
+    for (int k = 0; k < n; ++k) {
+        const int cls = seg_info[1 + 4 * k + 1];
+        const int mask_area = work[k], original_area = work[Q + k];
+        const int final_area = filter_low_score ? work[2 * Q + k] : mask_area;
+        int seg = -1;
+        if (mask_area > 0 && original_area > 0) {
+            if (!((double)mask_area / (double)original_area < iou_thr) && final_area > 0) {
+                if (cls < num_things) {
+                    seg = cls + instance_id * instance_offset;
+                    ++instance_id;
+                } else {
+                    seg = cls;
+                }
+            }
+        }
+        seg_info[1 + 4 * k + 2] = seg;
+        seg_info[1 + 4 * k + 3] = seg >= 0 ? final_area : 0;
+    }
+}
+
+// Step 4: winner index -> segment id.
+__global__ void __launch_bounds__(256) pan_write_kernel(const uint16_t* __restrict__ pix,
+                                                        const int32_t* __restrict__ seg_info, int NC,
+                                                        int filter_low_score, int32_t* __restrict__ pan, int64_t npix) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const int v = pix[p];
+        const int k = v & NONE;
+        int id = NC;
+        if (k != NONE && (!filter_low_score || (v & 0x8000))) {
+            const int seg = seg_info[1 + 4 * k + 2];
+            if (seg >= 0) id = seg;
+        }
+        pan[p] = id;
+    }
+}
+
+__global__ void ins_init_kernel(float* stats, int32_t* boxes, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        stats[2 * i] = 0.f;
+        stats[2 * i + 1] = 0.f;
+        boxes[4 * i] = INT_MAX;
+        boxes[4 * i + 1] = INT_MAX;
+        boxes[4 * i + 2] = -1;
+        boxes[4 * i + 3] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(256) ins_pixel_kernel(const float* __restrict__ mask_logits,
+                                                        const int32_t* __restrict__ query_idx, UpGeom g,
+                                                        float* __restrict__ stats, int32_t* __restrict__ boxes,
+                                                        uint8_t* __restrict__ masks_out) {
+    const int i = blockIdx.y;
+    const int q = query_idx[i];
+    const int64_t npix = (int64_t)g.out_h * g.out_w;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < npix;
+    const int oy = valid ? (int)(p / g.out_w) : 0, ox = valid ? (int)(p % g.out_w) : 0;
+    float s = 0.f;
+    int cnt = 0, xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
+    if (valid) {
+        const float v = final_logit(mask_logits + (int64_t)q * g.h * g.w, g, oy, ox);
+        const bool on = v > 0.f;
+        if (on) {
+            s = sigmoidf_(v);
+            cnt = 1;
+            xmin = xmax = ox;
+            ymin = ymax = oy;
+        }
+        if (masks_out) masks_out[(int64_t)i * npix + p] = on ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&stats[2 * i], s);
+        atomicAdd(&stats[2 * i + 1], (float)cnt);
+        atomicMin(&boxes[4 * i], xmin);
+        atomicMin(&boxes[4 * i + 1], ymin);
+        atomicMax(&boxes[4 * i + 2], xmax);
+        atomicMax(&boxes[4 * i + 3], ymax);
+    }
+}
+
+__global__ void ins_finish_kernel(int32_t* boxes, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        if (boxes[4 * i + 2] < 0) {
+            boxes[4 * i] = boxes[4 * i + 1] = boxes[4 * i + 2] = boxes[4 * i + 3] = 0;
+        } else {
+            boxes[4 * i + 2] += 1;
+            boxes[4 * i + 3] += 1;
+        }
+    }
+}
+
+int make_geom(UpGeom& g, int h, int w, int in_h, int in_w, int img_h, int img_w, int out_h, int out_w) {
+    if (h <= 0 || w <= 0 || in_h <= 0 || in_w <= 0 || img_h <= 0 || img_w <= 0 || out_h <= 0 || out_w <= 0)
+        return PVSG_ERR_INVALID_ARG;
+    if (img_h > in_h || img_w > in_w) return PVSG_ERR_INVALID_ARG;
+    g.h = h; g.w = w; g.in_h = in_h; g.in_w = in_w; g.img_h = img_h; g.img_w = img_w;
+    g.out_h = out_h; g.out_w = out_w;
+    g.sh = (float)h / (float)in_h; g.sw = (float)w / (float)in_w;
+    g.rh = (float)img_h / (float)out_h; g.rw = (float)img_w / (float)out_w;
+    g.rescale = (out_h != img_h || out_w != img_w) ? 1 : 0;
+    return PVSG_OK;
+}
+
+}  // namespace
+
+extern "C" int pvsg_panoptic_fuse(const float* cls_logits, const float* mask_logits, int Q, int NC,
+                                  int num_things, int h, int w, int in_h, int in_w, int img_h, int img_w,
+                                  int out_h, int out_w, float object_mask_thr, double iou_thr,
+                                  int filter_low_score, int instance_offset, int32_t* pan_out,
+                                  int32_t* seg_info, int32_t* work, float* scores, uint16_t* pix_ws,
+                                  void* stream) {
+    PVSG_CHECK_ARG(cls_logits && mask_logits && pan_out && seg_info && work && scores && pix_ws);
+    PVSG_CHECK_ARG(Q > 0 && Q <= 1024 && NC > 0 && num_things >= 0 && num_things <= NC);
+    UpGeom g{};
+    int rc = make_geom(g, h, w, in_h, in_w, img_h, img_w, out_h, out_w);
+    if (rc != PVSG_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int64_t npix = (int64_t)out_h * out_w;
+    pan_select_kernel<<<1, 128, 0, st>>>(cls_logits, Q, NC, object_mask_thr, seg_info, work, scores);
+    pan_pixel_kernel<<<(unsigned)((npix + 255) / 256), 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info,
+                                                                                       scores, work, pix_ws);
+    pan_decide_kernel<<<1, 32, 0, st>>>(Q, num_things, iou_thr, filter_low_score, instance_offset, seg_info, work);
+    pan_write_kernel<<<(unsigned)imin64((npix + 255) / 256, 148 * 16), 256, 0, st>>>(
+        pix_ws, seg_info, NC, filter_low_score, pan_out, npix);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_instance_masks(const float* mask_logits, const int32_t* query_idx, int n, int h, int w,
+                                   int in_h, int in_w, int img_h, int img_w, int out_h, int out_w,
+                                   float* stats, int32_t* boxes, uint8_t* masks_out, void* stream) {
+    PVSG_CHECK_ARG(mask_logits && query_idx && stats && boxes && n > 0 && n <= 65535);
+    UpGeom g{};
+    int rc = make_geom(g, h, w, in_h, in_w, img_h, img_w, out_h, out_w);
+    if (rc != PVSG_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int64_t npix = (int64_t)out_h * out_w;
+    ins_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, boxes, n);
+    dim3 grid((unsigned)((npix + 255) / 256), (unsigned)n);
+    ins_pixel_kernel<<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
+    ins_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(boxes, n);
+    return pvsg_launch_status();
+}

@@ -1,0 +1,91 @@
+"""ctypes binding of libpvsg_sm100.so (the C ABI declared in include/pvsg.h).
+
+The library is built in-tree by ``build()`` (``make`` in openpvsg_b200/csrc, nvcc
+-gencode arch=compute_100a,code=sm_100a).  There is NO fallback: if the shared object is
+missing or a call returns an error code, a ``PvsgError`` is raised.
+"""
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libpvsg_sm100.so')
+CSRC = os.path.join(HERE, 'csrc')
+
+P = c_void_p
+I = c_int
+L = c_int64
+F = c_float
+D = c_double
+
+# name -> (restype, argtypes); mirrors include/pvsg.h one to one
+SIGNATURES = {
+    'pvsg_version': (I, []),
+    'pvsg_error_string': (c_char_p, [I]),
+    'pvsg_device_info': (I, [I, P, P, P]),
+    'pvsg_linear': (I, [P, P, P, P, P, P, L, L, L, L, L, L, L, I, L, L, L, L, P]),
+    'pvsg_conv2d_nhwc': (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
+    'pvsg_maxpool3x3s2_nhwc': (I, [P, P, I, I, I, I, P]),
+    'pvsg_nchw_to_nhwc': (I, [P, P, I, I, I, I, P]),
+    'pvsg_nhwc_to_nchw': (I, [P, P, I, I, I, I, P]),
+    'pvsg_layernorm': (I, [P, P, P, P, L, I, F, P]),
+    'pvsg_groupnorm_nhwc': (I, [P, P, P, P, P, I, L, I, I, F, I, P]),
+    'pvsg_add_rowvec': (I, [P, P, P, L, I, P]),
+    'pvsg_bilinear_resize_nhwc': (I, [P, P, I, I, I, I, I, I, I, P]),
+    'pvsg_sine_pe': (I, [P, P, P, P, I, I, I, I, F, F, P]),
+    'pvsg_msda_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
+    'pvsg_msda_fused_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
+    'pvsg_attention_workspace_bytes': (L, [I, I, I, I, I]),
+    'pvsg_attention': (I, [P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
+    'pvsg_mask_logits': (I, [P, P, P, P, P, I, I, L, I, P]),
+    'pvsg_panoptic_fuse': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),
+    'pvsg_instance_masks': (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, P, P]),
+    'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
+    'pvsg_pair_proposal': (I, [P, P, P, P, P, I, I, P]),
+    'pvsg_top_pairs': (I, [P, I, I, P, P, P]),
+    'pvsg_gather_pairs': (I, [P, P, P, P, P, I, I, I, P]),
+}
+
+
+class PvsgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into openpvsg_b200/libpvsg_sm100.so."""
+    res = subprocess.run(['make', '-j8', '-C', CSRC], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise PvsgError('building libpvsg_sm100.so failed')
+    return LIB_PATH
+
+
+def load():
+    """dlopen the library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PvsgError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                        '(there is no CPU / PyTorch fallback for the pvsg kernels)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pvsg_version() != 100:
+        raise PvsgError('libpvsg_sm100.so version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().pvsg_error_string(code).decode()
+        raise PvsgError(f'{what} failed: {msg} ({code})')

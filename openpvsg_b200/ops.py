@@ -1,0 +1,348 @@
+"""torch-tensor front end of the C ABI (include/pvsg.h).
+
+PyTorch is used here for device memory and streams only: every function checks its
+tensors (CUDA, fp32, layout), passes raw pointers + sizes + the current stream to
+libpvsg_sm100.so and returns the output tensor.  No torch arithmetic happens here and
+there is no fallback path -- a missing library or a failed call raises ``PvsgError``.
+All calls are stream-ordered and allocation-free on the native side, so a whole forward
+can be captured with ``torch.cuda.graph``.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _l
+
+ACT_NONE, ACT_RELU = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name='tensor'):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise _l.PvsgError(f'{name}: expected a CUDA float32 tensor, got {t.device} {t.dtype}')
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t, name):
+    """View `t` as [rows, C] with unit inner stride; returns (tensor, rows, C, row_stride)."""
+    _f32(t, name)
+    if t.dim() != 2:
+        if not t.is_contiguous():
+            raise _l.PvsgError(f'{name}: non-2D tensors must be contiguous')
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1:
+        raise _l.PvsgError(f'{name}: inner stride must be 1')
+    return t, t.shape[0], t.shape[1], t.stride(0)
+
+
+def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, out=None):
+    """act((x + add_input) @ weight.T + bias + residual); x [..., K], weight [N, K] (row slices ok)."""
+    lib = _l.load()
+    lead = x.shape[:-1]
+    x2, M, K, lda = _rows(x, 'x')
+    w2, N, Kw, ldw = _rows(weight, 'weight')
+    if Kw != K:
+        raise _l.PvsgError(f'linear: K mismatch {K} vs {Kw}')
+    a2 = None
+    if add_input is not None:
+        a2, M2, K2, lda2 = _rows(add_input, 'add_input')
+        if (M2, K2, lda2) != (M, K, lda):
+            raise _l.PvsgError('linear: add_input must match x layout')
+    created = out is None
+    if created:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    o2, Mo, No, ldc = _rows(out, 'out')
+    if (Mo, No) != (M, N):
+        raise _l.PvsgError('linear: bad out shape')
+    r2, ldr = None, 0
+    if residual is not None:
+        r2, Mr, Nr, ldr = _rows(residual, 'residual')
+        if (Mr, Nr) != (M, N):
+            raise _l.PvsgError('linear: bad residual shape')
+    if bias is not None and (_f32(bias, 'bias').numel() != N or not bias.is_contiguous()):
+        raise _l.PvsgError('linear: bad bias')
+    _l.check(lib.pvsg_linear(_ptr(x2), _ptr(a2), _ptr(w2), _ptr(bias), _ptr(r2), _ptr(o2), M, N, K, lda, ldw,
+                             ldc, ldr, act, 1, 0, 0, 0, _stream()), 'pvsg_linear')
+    return out.reshape(*lead, N) if created else out
+
+
+def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NONE, out=None):
+    """x [B,H,W,Cin] token-major, weight [Cout,R,S,Cin] -> [B,OH,OW,Cout]."""
+    lib = _l.load()
+    _f32(x, 'x'), _f32(weight, 'weight')
+    if not (x.is_contiguous() and weight.is_contiguous() and x.dim() == 4 and weight.dim() == 4):
+        raise _l.PvsgError('conv2d_nhwc: contiguous 4-D tensors required')
+    B, H, W, Cin = x.shape
+    Cout, R, S, Cw = weight.shape
+    if Cw != Cin:
+        raise _l.PvsgError('conv2d_nhwc: channel mismatch')
+    OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    if out is None:
+        out = torch.empty(B, OH, OW, Cout, device=x.device, dtype=torch.float32)
+    if residual is not None and (tuple(residual.shape) != (B, OH, OW, Cout) or not residual.is_contiguous()):
+        raise _l.PvsgError('conv2d_nhwc: bad residual')
+    _l.check(lib.pvsg_conv2d_nhwc(_ptr(x), _ptr(weight), _ptr(_f32(bias)), _ptr(_f32(residual)), _ptr(out), B, H,
+                                  W, Cin, Cout, R, S, stride, pad, act, _stream()), 'pvsg_conv2d_nhwc')
+    return out
+
+
+def maxpool3x3s2_nhwc(x):
+    lib = _l.load()
+    B, H, W, C = _f32(x).shape
+    out = torch.empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_maxpool3x3s2_nhwc(_ptr(x.contiguous()), _ptr(out), B, H, W, C, _stream()), 'pvsg_maxpool')
+    return out
+
+
+def nchw_to_nhwc(x):
+    lib = _l.load()
+    B, C, H, W = _f32(x).shape
+    out = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_nchw_to_nhwc(_ptr(x.contiguous()), _ptr(out), B, C, H, W, _stream()), 'pvsg_nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x):
+    lib = _l.load()
+    B, H, W, C = _f32(x).shape
+    out = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_nhwc_to_nchw(_ptr(x.contiguous()), _ptr(out), B, C, H, W, _stream()), 'pvsg_nhwc_to_nchw')
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    lib = _l.load()
+    _f32(x)
+    if not x.is_contiguous():
+        raise _l.PvsgError('layernorm: contiguous input required')
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(lib.pvsg_layernorm(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), x.numel() // C, C, eps,
+                                _stream()), 'pvsg_layernorm')
+    return out
+
+
+def groupnorm_nhwc(x, gamma, beta, groups=32, eps=1e-5, act=ACT_NONE, out=None):
+    """x [B, H, W, C] (or [B, HW, C]) token-major."""
+    lib = _l.load()
+    _f32(x)
+    if not x.is_contiguous():
+        raise _l.PvsgError('groupnorm: contiguous input required')
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    if out is None:
+        out = torch.empty_like(x)
+    stats = torch.empty(B * groups * 2, device=x.device, dtype=torch.float64)
+    _l.check(lib.pvsg_groupnorm_nhwc(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), _ptr(stats), B, HW,
+                                     C, groups, eps, act, _stream()), 'pvsg_groupnorm_nhwc')
+    return out
+
+
+def add_rowvec(x, v, out=None):
+    lib = _l.load()
+    _f32(x), _f32(v)
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(lib.pvsg_add_rowvec(_ptr(x.contiguous()), _ptr(v.contiguous()), _ptr(out), x.numel() // C, C,
+                                 _stream()), 'pvsg_add_rowvec')
+    return out
+
+
+def bilinear_resize_nhwc(src, out_hw, out=None, accumulate=False):
+    """F.interpolate(mode='bilinear', align_corners=False) on token-major [B,H,W,C]."""
+    lib = _l.load()
+    B, IH, IW, C = _f32(src).shape
+    OH, OW = out_hw
+    if out is None:
+        if accumulate:
+            raise _l.PvsgError('bilinear_resize: accumulate needs out')
+        out = torch.empty(B, OH, OW, C, device=src.device, dtype=torch.float32)
+    _l.check(lib.pvsg_bilinear_resize_nhwc(_ptr(src.contiguous()), _ptr(out), B, IH, IW, OH, OW, C,
+                                           1 if accumulate else 0, _stream()), 'pvsg_bilinear_resize_nhwc')
+    return out
+
+
+def sine_pe(h, w, device, t=0, num_feats=128, temperature=10000, scale=6.283185307179586, eps=1e-6,
+            add_vec=None):
+    """Token-major sine positional encoding [max(t,1)*h*w, 2*num_feats]."""
+    lib = _l.load()
+    # temperature tables exactly as the reference builds them (position_encoding.py:84-88)
+    dim_t = torch.arange(num_feats, dtype=torch.float32)
+    dim_t = (temperature ** (2 * (dim_t // 2) / num_feats)).to(device)
+    dim_t_z = torch.arange(num_feats * 2, dtype=torch.float32)
+    dim_t_z = (temperature ** (2 * (dim_t_z // 2) / (num_feats * 2))).to(device)
+    out = torch.empty(max(t, 1) * h * w, 2 * num_feats, device=device, dtype=torch.float32)
+    _l.check(lib.pvsg_sine_pe(_ptr(out), _ptr(dim_t), _ptr(dim_t_z), _ptr(_f32(add_vec)), t, h, w, num_feats,
+                              scale, eps, _stream()), 'pvsg_sine_pe')
+    return out
+
+
+def _levels(spatial_shapes):
+    shapes = [(int(h), int(w)) for h, w in spatial_shapes]
+    L = len(shapes)
+    ss = (ctypes.c_int64 * (2 * L))(*[v for hw in shapes for v in hw])
+    starts, acc = [], 0
+    for h, w in shapes:
+        starts.append(acc)
+        acc += h * w
+    ls = (ctypes.c_int64 * L)(*starts)
+    return ss, ls, L, acc
+
+
+def msda_forward(value, spatial_shapes, sampling_locations, attention_weights):
+    """mmcv MultiScaleDeformableAttnFunction.forward: value [B,N,H,D], sampling_locations
+    [B,Nq,H,L,P,2], attention_weights [B,Nq,H,L,P] -> [B,Nq,H*D]."""
+    lib = _l.load()
+    B, N, H, D = _f32(value).shape
+    _, Nq, _, L, P, _ = _f32(sampling_locations).shape
+    ss, ls, L2, tot = _levels(spatial_shapes)
+    if L2 != L or tot != N:
+        raise _l.PvsgError('msda_forward: spatial_shapes do not match value')
+    out = torch.empty(B, Nq, H * D, device=value.device, dtype=torch.float32)
+    _l.check(lib.pvsg_msda_forward(_ptr(value.contiguous()), ss, ls, _ptr(sampling_locations.contiguous()),
+                                   _ptr(_f32(attention_weights).contiguous()), _ptr(out), B, N, Nq, H, D, L, P,
+                                   _stream()), 'pvsg_msda_forward')
+    return out
+
+
+def msda_fused_forward(value, spatial_shapes, proj, ref, num_heads=8, num_points=4):
+    """value [B,N,H*D]; proj [B,Nq,H*L*P*3] raw (offsets | logits); ref [Nq,2]."""
+    lib = _l.load()
+    B, N, C = _f32(value).shape
+    ss, ls, L, tot = _levels(spatial_shapes)
+    Nq = proj.shape[1]
+    D = C // num_heads
+    if tot != N or _f32(proj).shape[2] != num_heads * L * num_points * 3 or tuple(_f32(ref).shape) != (Nq, 2):
+        raise _l.PvsgError('msda_fused_forward: shape mismatch')
+    out = torch.empty(B, Nq, C, device=value.device, dtype=torch.float32)
+    _l.check(lib.pvsg_msda_fused_forward(_ptr(value.contiguous()), ss, ls, _ptr(proj.contiguous()),
+                                         _ptr(ref.contiguous()), _ptr(out), B, N, Nq, num_heads, D, L,
+                                         num_points, _stream()), 'pvsg_msda_fused_forward')
+    return out
+
+
+def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None):
+    """q [B,Lq,E], k/v [B,Lk,E] (any batch / token strides, unit inner stride) -> [B,Lq,E].
+    mask uint8 [B,Lq,Lk] (non-zero = blocked), row_open int32 [B,Lq]."""
+    lib = _l.load()
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _f32(t, n)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise _l.PvsgError(f'attention: {n} must be [B,L,E] with unit inner stride')
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    D = E // num_heads
+    if scale is None:
+        scale = float(D) ** -0.5
+    if out is None:
+        out = torch.empty(B, Lq, E, device=q.device, dtype=torch.float32)
+    if mask is not None and not (mask.dtype == torch.uint8 and mask.is_contiguous() and
+                                 tuple(mask.shape) == (B, Lq, Lk)):
+        raise _l.PvsgError('attention: mask must be contiguous uint8 [B,Lq,Lk]')
+    if row_open is not None and not (row_open.dtype == torch.int32 and row_open.is_contiguous()):
+        raise _l.PvsgError('attention: row_open must be contiguous int32')
+    nbytes = lib.pvsg_attention_workspace_bytes(B, num_heads, Lq, Lk, D)
+    ws = torch.empty(nbytes, device=q.device, dtype=torch.uint8)
+    _l.check(lib.pvsg_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(row_open), _ptr(out), _ptr(ws), B,
+                                num_heads, Lq, Lk, D, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
+                                v.stride(0), v.stride(1), out.stride(0), out.stride(1), scale, _stream()),
+             'pvsg_attention')
+    return out
+
+
+def mask_logits(embed, feat, want_logits=True, want_mask=False):
+    """embed [B,Q,C], feat [B,P,C] token-major -> logits [B,Q,P] and/or (mask uint8, row_open int32)."""
+    lib = _l.load()
+    B, Q, C = _f32(embed).shape
+    P = _f32(feat).shape[1]
+    logits = torch.empty(B, Q, P, device=embed.device, dtype=torch.float32) if want_logits else None
+    mask = torch.empty(B, Q, P, device=embed.device, dtype=torch.uint8) if want_mask else None
+    row_open = torch.empty(B, Q, device=embed.device, dtype=torch.int32) if want_mask else None
+    _l.check(lib.pvsg_mask_logits(_ptr(embed.contiguous()), _ptr(feat.contiguous()), _ptr(logits), _ptr(mask),
+                                  _ptr(row_open), B, Q, P, C, _stream()), 'pvsg_mask_logits')
+    return logits, mask, row_open
+
+
+def panoptic_fuse(cls_logits, mask_logits_lr, in_hw, img_hw, out_hw, num_things, num_classes,
+                  object_mask_thr=0.8, iou_thr=0.8, filter_low_score=True, instance_offset=1000):
+    """cls_logits [Q,NC+1], mask_logits_lr [Q,h,w] -> (pan int32 [out_h,out_w], seg_info int32 [1+4Q])."""
+    lib = _l.load()
+    Q = _f32(cls_logits).shape[0]
+    _, h, w = _f32(mask_logits_lr).shape
+    dev = cls_logits.device
+    pan = torch.empty(out_hw[0], out_hw[1], device=dev, dtype=torch.int32)
+    seg_info = torch.empty(1 + 4 * Q, device=dev, dtype=torch.int32)
+    work = torch.empty(4 * Q, device=dev, dtype=torch.int32)
+    scores = torch.empty(Q, device=dev, dtype=torch.float32)
+    pix = torch.empty(out_hw[0] * out_hw[1], device=dev, dtype=torch.int16)
+    _l.check(lib.pvsg_panoptic_fuse(_ptr(cls_logits.contiguous()), _ptr(mask_logits_lr.contiguous()), Q,
+                                    num_classes, num_things, h, w, in_hw[0], in_hw[1], img_hw[0], img_hw[1],
+                                    out_hw[0], out_hw[1], object_mask_thr, iou_thr, 1 if filter_low_score else 0,
+                                    instance_offset, _ptr(pan), _ptr(seg_info), _ptr(work), _ptr(scores),
+                                    _ptr(pix), _stream()), 'pvsg_panoptic_fuse')
+    return pan, seg_info
+
+
+def instance_masks(mask_logits_lr, query_idx, in_hw, img_hw, out_hw, want_masks=True):
+    lib = _l.load()
+    _, h, w = _f32(mask_logits_lr).shape
+    n = query_idx.numel()
+    dev = mask_logits_lr.device
+    stats = torch.empty(n, 2, device=dev, dtype=torch.float32)
+    boxes = torch.empty(n, 4, device=dev, dtype=torch.int32)
+    masks = torch.empty(n, out_hw[0], out_hw[1], device=dev, dtype=torch.uint8) if want_masks else None
+    if n == 0:
+        return stats, boxes, masks
+    _l.check(lib.pvsg_instance_masks(_ptr(mask_logits_lr.contiguous()), _ptr(query_idx.to(torch.int32).contiguous()),
+                                     n, h, w, in_hw[0], in_hw[1], img_hw[0], img_hw[1], out_hw[0], out_hw[1],
+                                     _ptr(stats), _ptr(boxes), _ptr(masks), _stream()), 'pvsg_instance_masks')
+    return stats, boxes, masks
+
+
+def max_over_time(x):
+    lib = _l.load()
+    N, T, C = _f32(x).shape
+    out = torch.empty(N, C, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_max_over_time(_ptr(x.contiguous()), _ptr(out), N, T, C, _stream()), 'pvsg_max_over_time')
+    return out
+
+
+def pair_proposal(U, V, w2, b2):
+    lib = _l.load()
+    N, Hd = _f32(U).shape
+    out = torch.empty(N, N, device=U.device, dtype=torch.float32)
+    _l.check(lib.pvsg_pair_proposal(_ptr(U.contiguous()), _ptr(_f32(V).contiguous()), _ptr(_f32(w2).contiguous()),
+                                    _ptr(_f32(b2)), _ptr(out), N, Hd, _stream()), 'pvsg_pair_proposal')
+    return out
+
+
+def top_pairs(pair, k):
+    lib = _l.load()
+    N = _f32(pair).shape[0]
+    pairs = torch.zeros(max(1, min(k, N * N)), 2, device=pair.device, dtype=torch.int32)
+    n_out = torch.zeros(1, device=pair.device, dtype=torch.int32)
+    _l.check(lib.pvsg_top_pairs(_ptr(pair.contiguous()), N, k, _ptr(pairs), _ptr(n_out), _stream()),
+             'pvsg_top_pairs')
+    return pairs, n_out
+
+
+def gather_pairs(sub, obj, pairs, pe=None):
+    """sub/obj [N,T,F], pairs int32 [P,2] -> [P,T,2F] (+ pe[:T])."""
+    lib = _l.load()
+    N, T, Fd = _f32(sub).shape
+    Pn = pairs.shape[0]
+    out = torch.empty(Pn, T, 2 * Fd, device=sub.device, dtype=torch.float32)
+    _l.check(lib.pvsg_gather_pairs(_ptr(sub.contiguous()), _ptr(_f32(obj).contiguous()), _ptr(pairs.contiguous()),
+                                   _ptr(_f32(pe)), _ptr(out), Pn, T, Fd, _stream()), 'pvsg_gather_pairs')
+    return out
