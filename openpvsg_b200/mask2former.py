@@ -1,0 +1,991 @@
+"""B200 backend of the OpenPVSG Mask2Former / Mask2Former-VPS inference path.
+
+Same registry names, constructor arguments, ``forward`` / ``simple_test`` signatures and
+``state_dict`` key layout as the reference (and the mmdet 2.25 / mmcv 1.4 modules its
+configs name), so a config ``type=`` string or an existing checkpoint resolves to these
+classes unchanged -- but every tensor operation is a call into libpvsg_sm100.so
+(openpvsg_b200/ops.py).  Inference only: training methods raise NotImplementedError.
+
+Internal layout is token-major (NHWC).  Tensors crossing the reference's interfaces keep
+their reference SHAPES ([B,C,H,W] feature maps, [B,Q,h,w] mask logits); feature maps are
+handed around as channels_last views so no transposition is needed between modules.
+
+Reference files: models/mask2former/{mask2former,mask2former_head,mask2former_fusion_head}.py,
+models/mask2former_vps/{mask2former,mask2former_video_head,position_encoding}.py; L0 modules
+per SURVEY.md appendix A.
+"""
+import copy
+from collections import defaultdict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .registry import (ATTENTION, BACKBONES, DETECTORS, FEEDFORWARD_NETWORK, HEADS, PLUGIN_LAYERS,
+                       POSITIONAL_ENCODING, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, ConfigDict,
+                       build_backbone, build_head, build_plugin_layer, build_positional_encoding,
+                       build_transformer_layer_sequence, to_cfg)
+
+INSTANCE_OFFSET = 1000
+
+
+def _tokens(x):
+    """[B,C,H,W] tensor (any memory format) -> token-major [B,H,W,C] contiguous."""
+    if x.dim() != 4:
+        raise ValueError('expected a [B,C,H,W] tensor')
+    t = x.permute(0, 2, 3, 1)
+    return t if t.is_contiguous() else ops.nchw_to_nhwc(x.contiguous())
+
+
+def _as_nchw(t):
+    """token-major [B,H,W,C] -> logical [B,C,H,W] (channels_last view, no copy)."""
+    return t.permute(0, 3, 1, 2)
+
+
+class _Prepared(nn.Module):
+    """Modules cache kernel-layout copies of their parameters; loading a checkpoint or
+    moving the module invalidates the cache."""
+
+    def __init__(self):
+        super().__init__()
+        self._prep = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._prep = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *a, **k):
+        self._prep = None
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError('openpvsg_b200 implements the inference path only '
+                                      '(SURVEY.md 8f rank 4: training forward/backward is a "next" row)')
+        return super().train(False)
+
+
+# ======================================================================================
+# backbone: mmdet ResNet (L0, A1)
+# ======================================================================================
+class _Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.stride = stride
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride, bias=False),
+                                            nn.BatchNorm2d(planes * 4))
+        else:
+            self.downsample = None
+
+
+def _fold(conv, bn):
+    """conv (no bias) + eval-mode BN -> ([Cout,R,S,Cin] weight, bias), fp32."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = (conv.weight * scale[:, None, None, None]).permute(0, 2, 3, 1).contiguous()
+    b = (bn.bias - bn.running_mean * scale).contiguous()
+    return w, b
+
+
+@BACKBONES.register_module()
+class ResNet(_Prepared):
+    """mmdet ``ResNet`` (depth 50/101, style='pytorch', norm_eval) -- torchvision key names.
+    cfg: configs/mask2former_vps/mask2former_video_r50_base.py:7-16."""
+    arch = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+
+    def __init__(self, depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=-1, norm_cfg=None,
+                 norm_eval=True, style='pytorch', init_cfg=None, **kwargs):
+        super().__init__()
+        if depth not in self.arch or style != 'pytorch' or num_stages != 4:
+            raise NotImplementedError('ResNet: only depth 50/101, style="pytorch", 4 stages')
+        self.out_indices = tuple(out_indices)
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inpl = 64
+        for i, (n, planes) in enumerate(zip(self.arch[depth], (64, 128, 256, 512))):
+            blocks = []
+            for b in range(n):
+                stride = 2 if (b == 0 and i > 0) else 1
+                blocks.append(_Bottleneck(inpl, planes, stride, b == 0))
+                inpl = planes * 4
+            setattr(self, f'layer{i + 1}', nn.Sequential(*blocks))
+        self.eval()
+
+    def init_weights(self):
+        pass
+
+    @torch.no_grad()
+    def _prepare(self):
+        p = {'stem': _fold(self.conv1, self.bn1), 'blocks': []}
+        for i in range(4):
+            for blk in getattr(self, f'layer{i + 1}'):
+                d = dict(c1=_fold(blk.conv1, blk.bn1), c2=_fold(blk.conv2, blk.bn2), c3=_fold(blk.conv3, blk.bn3),
+                         stride=blk.stride, stage=i)
+                d['ds'] = _fold(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                p['blocks'].append(d)
+        self._prep = p
+
+    @torch.no_grad()
+    def forward(self, x):
+        if self._prep is None:
+            self._prepare()
+        p = self._prep
+        x = _tokens(x)
+        x = ops.conv2d_nhwc(x, *p['stem'], stride=2, pad=3, act=ops.ACT_RELU)
+        x = ops.maxpool3x3s2_nhwc(x)
+        outs = []
+        nblk = len(p['blocks'])
+        for j, d in enumerate(p['blocks']):
+            idt = x
+            o = ops.conv2d_nhwc(x, *d['c1'], act=ops.ACT_RELU)
+            o = ops.conv2d_nhwc(o, *d['c2'], stride=d['stride'], pad=1, act=ops.ACT_RELU)
+            if d['ds'] is not None:
+                idt = ops.conv2d_nhwc(x, *d['ds'], stride=d['stride'])
+            x = ops.conv2d_nhwc(o, *d['c3'], residual=idt, act=ops.ACT_RELU)
+            if j + 1 == nblk or p['blocks'][j + 1]['stage'] != d['stage']:
+                if d['stage'] in self.out_indices:
+                    outs.append(_as_nchw(x))
+        return tuple(outs)
+
+
+# ======================================================================================
+# positional encodings
+# ======================================================================================
+@POSITIONAL_ENCODING.register_module()
+class SinePositionalEncoding(nn.Module):
+    """mmdet SinePositionalEncoding (L0, A4).  ``forward(mask)`` takes the all-valid bool mask
+    [B,h,w] the reference passes (mask2former_head.py:428-432) and returns [B,2F,h,w]."""
+
+    def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * 3.141592653589793, eps=1e-6,
+                 offset=0., init_cfg=None):
+        super().__init__()
+        if not normalize or offset != 0.:
+            raise NotImplementedError('SinePositionalEncoding: normalize=True, offset=0 only')
+        self.num_feats, self.temperature, self.scale, self.eps = num_feats, temperature, scale, eps
+
+    def tokens(self, h, w, device, t=0, add_vec=None):
+        return ops.sine_pe(h, w, device, t=t, num_feats=self.num_feats, temperature=self.temperature,
+                           scale=self.scale, eps=self.eps, add_vec=add_vec)
+
+    def forward(self, mask):
+        b, h, w = mask.shape
+        pe = self.tokens(h, w, mask.device).view(1, h, w, -1)
+        return _as_nchw(pe).expand(b, -1, -1, -1)
+
+
+@POSITIONAL_ENCODING.register_module()
+class SinePositionalEncoding3D(SinePositionalEncoding):
+    """models/mask2former_vps/position_encoding.py:9-109; mask [B,T,h,w] -> [B,T,2F,h,w]."""
+
+    def forward(self, mask):
+        assert mask.dim() == 4
+        b, t, h, w = mask.shape
+        pe = self.tokens(h, w, mask.device, t=t).view(1, t, h, w, -1)
+        return pe.permute(0, 1, 4, 2, 3).expand(b, -1, -1, -1, -1)
+
+
+# ======================================================================================
+# pixel decoder (L0, A2/A3)
+# ======================================================================================
+@ATTENTION.register_module()
+class MultiScaleDeformableAttention(_Prepared):
+    """mmcv MultiScaleDeformableAttention (cfg mask2former_video_r50_base.py:38-47).
+
+    ``forward`` keeps mmcv's signature on seq-first tensors; the pixel decoder calls
+    ``forward_tokens`` (batch-first token-major, fused projections + fused sampling kernel).
+    """
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64, dropout=0.1,
+                 batch_first=False, norm_cfg=None, init_cfg=None):
+        super().__init__()
+        if embed_dims // num_heads != 32:
+            raise NotImplementedError('MultiScaleDeformableAttention kernel: 32 channels per head')
+        self.embed_dims, self.num_heads, self.num_levels, self.num_points = embed_dims, num_heads, num_levels, num_points
+        self.batch_first = batch_first
+        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+
+    @torch.no_grad()
+    def _prepare(self):
+        self._prep = dict(
+            w=torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0).contiguous(),
+            b=torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0).contiguous())
+
+    @torch.no_grad()
+    def forward_tokens(self, x, pos, ref, spatial_shapes):
+        """x, pos [B,N,C]; ref [N,2] -> output_proj(msda) + x."""
+        if self._prep is None:
+            self._prepare()
+        proj = ops.linear(x, self._prep['w'], self._prep['b'], add_input=pos)
+        value = ops.linear(x, self.value_proj.weight, self.value_proj.bias)
+        samp = ops.msda_fused_forward(value, spatial_shapes, proj, ref, self.num_heads, self.num_points)
+        return ops.linear(samp, self.output_proj.weight, self.output_proj.bias, residual=x)
+
+    @torch.no_grad()
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
+                reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        """mmcv signature (seq-first unless batch_first).  reference_points [B,Nq,L,2]."""
+        if value is None:
+            value = query
+        if identity is None:
+            identity = query
+        if key_padding_mask is not None and bool(key_padding_mask.any()):
+            raise NotImplementedError('key_padding_mask with masked positions')
+        q = query if query_pos is None else None
+        if not self.batch_first:
+            query, value, identity = (t.permute(1, 0, 2).contiguous() for t in (query, value, identity))
+            if query_pos is not None:
+                query_pos = query_pos.permute(1, 0, 2).contiguous()
+        B, Nq, C = query.shape
+        shapes = [(int(h), int(w)) for h, w in spatial_shapes.tolist()] if torch.is_tensor(spatial_shapes) \
+            else list(spatial_shapes)
+        H, L, P = self.num_heads, self.num_levels, self.num_points
+        v = ops.linear(value, self.value_proj.weight, self.value_proj.bias)
+        off = ops.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias, add_input=query_pos)
+        aw = ops.linear(query, self.attention_weights.weight, self.attention_weights.bias, add_input=query_pos)
+        # general reference points (per level): use the unfused op with explicit locations
+        norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32, device=query.device)
+        loc = reference_points[:, :, None, :, None, :] + off.view(B, Nq, H, L, P, 2) / norm[None, None, None, :, None, :]
+        aw = aw.view(B, Nq, H, L * P).softmax(-1).view(B, Nq, H, L, P)
+        out = ops.msda_forward(v.view(B, -1, H, C // H), shapes, loc.contiguous(), aw.contiguous())
+        out = ops.linear(out, self.output_proj.weight, self.output_proj.bias, residual=identity)
+        del q
+        return out if self.batch_first else out.permute(1, 0, 2)
+
+
+@FEEDFORWARD_NETWORK.register_module()
+class FFN(nn.Module):
+    """mmcv FFN: keys ``layers.0.0`` (Linear+act) and ``layers.1`` (Linear); add_identity."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2, act_cfg=None, ffn_drop=0.,
+                 dropout_layer=None, add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        if num_fcs != 2:
+            raise NotImplementedError('FFN: num_fcs=2 only')
+        self.add_identity = add_identity
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True),
+                                                  nn.Dropout(ffn_drop)),
+                                    nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
+
+    @torch.no_grad()
+    def forward(self, x, identity=None):
+        h = ops.linear(x, self.layers[0][0].weight, self.layers[0][0].bias, act=ops.ACT_RELU)
+        res = (x if identity is None else identity) if self.add_identity else None
+        return ops.linear(h, self.layers[1].weight, self.layers[1].bias, residual=res)
+
+
+class _Norm(nn.LayerNorm):
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.layernorm(x if x.is_contiguous() else x.contiguous(), self.weight, self.bias, self.eps)
+
+
+@TRANSFORMER_LAYER.register_module()
+class BaseTransformerLayer(nn.Module):
+    """mmcv BaseTransformerLayer restricted to the encoder form used by the pixel decoder:
+    operation_order = ('self_attn', 'norm', 'ffn', 'norm') with MultiScaleDeformableAttention."""
+
+    def __init__(self, attn_cfgs=None, ffn_cfgs=None, operation_order=None, norm_cfg=None, init_cfg=None,
+                 batch_first=False, **kwargs):
+        super().__init__()
+        if tuple(operation_order) != ('self_attn', 'norm', 'ffn', 'norm'):
+            raise NotImplementedError(f'BaseTransformerLayer: unsupported operation_order {operation_order}')
+        attn_cfgs = to_cfg(attn_cfgs)
+        self.attentions = nn.ModuleList([ATTENTION.build(attn_cfgs)])
+        self.embed_dims = self.attentions[0].embed_dims
+        ffn = dict(to_cfg(ffn_cfgs))
+        ffn.pop('type', None)
+        ffn.setdefault('embed_dims', self.embed_dims)
+        self.ffns = nn.ModuleList([FFN(**ffn)])
+        self.norms = nn.ModuleList([_Norm(self.embed_dims), _Norm(self.embed_dims)])
+
+    @torch.no_grad()
+    def forward_tokens(self, x, pos, ref, spatial_shapes):
+        x = self.attentions[0].forward_tokens(x, pos, ref, spatial_shapes)
+        x = self.norms[0](x)
+        x = self.ffns[0](x)
+        return self.norms[1](x)
+
+
+@TRANSFORMER_LAYER_SEQUENCE.register_module()
+class DetrTransformerEncoder(nn.Module):
+    def __init__(self, transformerlayers=None, num_layers=6, post_norm_cfg=None, init_cfg=None, **kwargs):
+        super().__init__()
+        cfg = dict(to_cfg(transformerlayers))
+        cfg.pop('type', None)
+        self.layers = nn.ModuleList([BaseTransformerLayer(**copy.deepcopy(cfg)) for _ in range(num_layers)])
+        self.embed_dims = self.layers[0].embed_dims
+
+
+class _ConvModule(nn.Module):
+    """mmcv ConvModule: conv -> GN -> act, keys ``conv`` / ``gn``."""
+
+    def __init__(self, cin, cout, k, padding=0, bias=False, act=False, groups=32):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=bias)
+        self.gn = nn.GroupNorm(groups, cout)
+        self.act = act
+        self.pad = padding
+        self._w = None
+
+    @torch.no_grad()
+    def forward_tokens(self, x):
+        if self._w is None or self._w.device != self.conv.weight.device:
+            self._w = self.conv.weight.permute(0, 2, 3, 1).contiguous()
+        y = ops.conv2d_nhwc(x, self._w, self.conv.bias, pad=self.pad)
+        return y
+
+    def norm_tokens(self, y):
+        return ops.groupnorm_nhwc(y, self.gn.weight, self.gn.bias, self.gn.num_groups, self.gn.eps,
+                                  ops.ACT_RELU if self.act else ops.ACT_NONE)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._w = None
+        return super()._load_from_state_dict(*a, **k)
+
+
+@PLUGIN_LAYERS.register_module()
+class MSDeformAttnPixelDecoder(_Prepared):
+    """mmdet MSDeformAttnPixelDecoder (cfg mask2former_video_r50_base.py:27-59)."""
+
+    def __init__(self, in_channels=(256, 512, 1024, 2048), strides=(4, 8, 16, 32), feat_channels=256,
+                 out_channels=256, num_outs=3, norm_cfg=None, act_cfg=None, encoder=None,
+                 positional_encoding=None, init_cfg=None):
+        super().__init__()
+        self.strides = list(strides)
+        self.num_input_levels = len(in_channels)
+        enc = to_cfg(encoder)
+        self.num_encoder_levels = enc.transformerlayers.attn_cfgs.num_levels
+        self.num_outs = num_outs
+        groups = (norm_cfg or {}).get('num_groups', 32)
+        self.input_convs = nn.ModuleList([
+            _ConvModule(in_channels[i], feat_channels, 1, bias=True, groups=groups)
+            for i in range(self.num_input_levels - 1, self.num_input_levels - self.num_encoder_levels - 1, -1)])
+        self.encoder = TRANSFORMER_LAYER_SEQUENCE.build(enc)
+        self.postional_encoding = build_positional_encoding(positional_encoding)  # (sic) mmdet attribute name
+        self.level_encoding = nn.Embedding(self.num_encoder_levels, feat_channels)
+        self.lateral_convs = nn.ModuleList()
+        self.output_convs = nn.ModuleList()
+        for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
+            self.lateral_convs.append(_ConvModule(in_channels[i], feat_channels, 1, groups=groups))
+            self.output_convs.append(_ConvModule(feat_channels, feat_channels, 3, padding=1, act=True, groups=groups))
+        self.mask_feature = nn.Conv2d(feat_channels, out_channels, 1)
+        self._shape_cache = {}
+
+    def init_weights(self):
+        pass
+
+    @torch.no_grad()
+    def _shape_consts(self, shapes, device):
+        """level positional encodings + reference points; depend on the shapes only."""
+        key = (tuple(shapes), str(device))
+        if key not in self._shape_cache or self._prep is None:
+            pos, refs = [], []
+            for i, (h, w) in enumerate(shapes):
+                pos.append(self.postional_encoding.tokens(h, w, device, add_vec=self.level_encoding.weight[i].contiguous()))
+                ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
+                                        indexing='ij')
+                refs.append(torch.stack(((xs.flatten() + 0.5) / w, (ys.flatten() + 0.5) / h), -1))
+            self._shape_cache = {key: (torch.cat(pos, 0).contiguous(), torch.cat(refs, 0).to(device).contiguous())}
+            self._prep = True
+        return self._shape_cache[key]
+
+    @torch.no_grad()
+    def forward(self, feats):
+        """feats: 4 maps [B,C,H,W] (C2..C5) -> (mask_feature [B,C,h4,w4], [m32, m16, m8])."""
+        B = feats[0].shape[0]
+        toks, shapes = [], []
+        for i in range(self.num_encoder_levels):
+            f = _tokens(feats[self.num_input_levels - i - 1])
+            cm = self.input_convs[i]
+            y = cm.norm_tokens(cm.forward_tokens(f))
+            shapes.append((y.shape[1], y.shape[2]))
+            toks.append(y.view(B, -1, y.shape[-1]))
+        x = torch.cat(toks, 1)  # pure data movement (torch.cat = cudaMemcpy-class op)
+        pos, ref = self._shape_consts(shapes, x.device)
+        posb = pos[None].expand(B, -1, -1).contiguous() if B > 1 else pos[None]
+        for layer in self.encoder.layers:
+            x = layer.forward_tokens(x, posb, ref, shapes)
+        outs, start = [], 0
+        for (h, w) in shapes:
+            outs.append(x[:, start:start + h * w].reshape(B, h, w, -1))
+            start += h * w
+        for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
+            j = self.num_input_levels - self.num_encoder_levels - 1 - i
+            lat = self.lateral_convs[j]
+            cur = lat.norm_tokens(lat.forward_tokens(_tokens(feats[i])))
+            ops.bilinear_resize_nhwc(outs[-1].contiguous(), cur.shape[1:3], out=cur, accumulate=True)
+            oc = self.output_convs[j]
+            outs.append(oc.norm_tokens(oc.forward_tokens(cur)))
+        wmf = self.mask_feature.weight.view(self.mask_feature.out_channels, -1)
+        mf = ops.linear(outs[-1], wmf, self.mask_feature.bias)
+        return _as_nchw(mf), [_as_nchw(o) for o in outs[:self.num_outs]]
+
+
+# ======================================================================================
+# transformer decoder (L0, A5)
+# ======================================================================================
+@ATTENTION.register_module()
+class MultiheadAttention(nn.Module):
+    """mmcv MultiheadAttention wrapper: parameters live in ``attn`` (torch nn.MultiheadAttention
+    key names); forward = identity + MHA(q + query_pos, k + key_pos, v)."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0., dropout_layer=None, batch_first=False,
+                 init_cfg=None, **kwargs):
+        super().__init__()
+        if batch_first:
+            raise NotImplementedError('MultiheadAttention: batch_first=False only (as in the reference cfg)')
+        self.embed_dims, self.num_heads = embed_dims, num_heads
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop)
+
+    @torch.no_grad()
+    def forward_tokens(self, query, query_pos, kproj=None, vproj=None, mask=None, row_open=None):
+        """batch-first tokens.  query/query_pos [B,Q,E].  Cross attention passes the
+        precomputed key / value projections [B,Lk,E]; self attention passes none."""
+        E = self.embed_dims
+        w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
+        if kproj is None:  # self attention: q, k from query + pos; v from query
+            qk = ops.linear(query, w[:2 * E], b[:2 * E], add_input=query_pos)
+            v = ops.linear(query, w[2 * E:], b[2 * E:])
+            q, k = qk[..., :E], qk[..., E:]
+        else:
+            q = ops.linear(query, w[:E], b[:E], add_input=query_pos)
+            k, v = kproj, vproj
+        o = ops.attention(q, k, v, self.num_heads, mask=mask, row_open=row_open)
+        return ops.linear(o, self.attn.out_proj.weight, self.attn.out_proj.bias, residual=query)
+
+    @torch.no_grad()
+    def project_kv(self, key, key_pos, value):
+        E = self.embed_dims
+        w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
+        return (ops.linear(key, w[E:2 * E], b[E:2 * E], add_input=key_pos),
+                ops.linear(value, w[2 * E:], b[2 * E:]))
+
+    @torch.no_grad()
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
+                key_padding_mask=None, **kwargs):
+        """mmcv signature, seq-first [L,B,E]; attn_mask bool [B*H,Lq,Lk] (True = blocked) or None."""
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        if key_padding_mask is not None and bool(key_padding_mask.any()):
+            raise NotImplementedError('key_padding_mask with masked positions')
+        bf = lambda t: None if t is None else t.permute(1, 0, 2).contiguous()  # noqa: E731
+        q, k, v, qp, kp = bf(query), bf(key), bf(value), bf(query_pos), bf(key_pos)
+        mask = row_open = None
+        if attn_mask is not None:
+            B = q.shape[0]
+            m = attn_mask.view(B, self.num_heads, *attn_mask.shape[1:])
+            if not bool((m == m[:, :1]).all()):
+                raise NotImplementedError('per-head attention masks')
+            mask = m[:, 0].to(torch.uint8).contiguous()
+            row_open = None  # an explicit mask is used as given
+        kproj, vproj = self.project_kv(k, kp, v)
+        out = self.forward_tokens(q, qp, kproj, vproj, mask, row_open)
+        if identity is not None:
+            out = out - q + bf(identity)
+        return out.permute(1, 0, 2)
+
+
+@TRANSFORMER_LAYER.register_module()
+class DetrTransformerDecoderLayer(nn.Module):
+    """mmdet DetrTransformerDecoderLayer, operation_order
+    ('cross_attn','norm','self_attn','norm','ffn','norm') -- mask2former_video_r50_base.py:63-88."""
+
+    def __init__(self, attn_cfgs=None, ffn_cfgs=None, feedforward_channels=None, operation_order=None,
+                 norm_cfg=None, init_cfg=None, **kwargs):
+        super().__init__()
+        if tuple(operation_order) != ('cross_attn', 'norm', 'self_attn', 'norm', 'ffn', 'norm'):
+            raise NotImplementedError(f'DetrTransformerDecoderLayer: unsupported operation_order {operation_order}')
+        a = dict(to_cfg(attn_cfgs))
+        a.pop('type', None)
+        self.attentions = nn.ModuleList([MultiheadAttention(**a), MultiheadAttention(**a)])
+        self.embed_dims = self.attentions[0].embed_dims
+        f = dict(to_cfg(ffn_cfgs or {}))
+        f.pop('type', None)
+        f.setdefault('embed_dims', self.embed_dims)
+        if feedforward_channels is not None:
+            f['feedforward_channels'] = feedforward_channels
+        self.ffns = nn.ModuleList([FFN(**f)])
+        self.norms = nn.ModuleList([_Norm(self.embed_dims) for _ in range(3)])
+
+    @torch.no_grad()
+    def forward_tokens(self, query, query_pos, kproj, vproj, mask, row_open):
+        x = self.attentions[0].forward_tokens(query, query_pos, kproj, vproj, mask, row_open)
+        x = self.norms[0](x)
+        x = self.attentions[1].forward_tokens(x, query_pos)
+        x = self.norms[1](x)
+        x = self.ffns[0](x)
+        return self.norms[2](x)
+
+    @torch.no_grad()
+    def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        """mmcv BaseTransformerLayer signature (seq-first), as called at mask2former_head.py:457-468."""
+        attn_masks = attn_masks or [None, None]
+        x = self.attentions[0](query, key, value, None, query_pos=query_pos, key_pos=key_pos,
+                               attn_mask=attn_masks[0], key_padding_mask=key_padding_mask)
+        x = self.norms[0](x.contiguous())
+        x = self.attentions[1](x, x, x, None, query_pos=query_pos, key_pos=query_pos, attn_mask=attn_masks[1],
+                               key_padding_mask=query_key_padding_mask)
+        x = self.norms[1](x.contiguous())
+        x = self.ffns[0](x)
+        return self.norms[2](x)
+
+
+@TRANSFORMER_LAYER_SEQUENCE.register_module()
+class DetrTransformerDecoder(nn.Module):
+    def __init__(self, transformerlayers=None, num_layers=9, return_intermediate=False, post_norm_cfg=None,
+                 init_cfg=None, **kwargs):
+        super().__init__()
+        cfg = dict(to_cfg(transformerlayers))
+        cfg.pop('type', None)
+        self.layers = nn.ModuleList([DetrTransformerDecoderLayer(**copy.deepcopy(cfg)) for _ in range(num_layers)])
+        self.embed_dims = self.layers[0].embed_dims
+        self.post_norm = _Norm(self.embed_dims)
+        self.return_intermediate = return_intermediate
+
+
+# ======================================================================================
+# heads
+# ======================================================================================
+class _Mask2FormerHeadBase(_Prepared):
+    """Shared implementation of Mask2FormerHeadCustom (models/mask2former/mask2former_head.py)
+    and Mask2FormerVideoHead (models/mask2former_vps/mask2former_video_head.py)."""
+    video = False
+
+    def __init__(self, in_channels, feat_channels, out_channels, num_things_classes=80, num_stuff_classes=53,
+                 num_queries=100, num_transformer_feat_level=3, pixel_decoder=None,
+                 enforce_decoder_input_project=False, transformer_decoder=None, positional_encoding=None,
+                 loss_cls=None, loss_mask=None, loss_dice=None, train_cfg=None, test_cfg=None, init_cfg=None,
+                 **kwargs):
+        super().__init__()
+        transformer_decoder = to_cfg(transformer_decoder)
+        pixel_decoder = to_cfg(pixel_decoder)
+        self.num_things_classes = num_things_classes
+        self.num_stuff_classes = num_stuff_classes
+        self.num_classes = num_things_classes + num_stuff_classes
+        self.num_queries = num_queries
+        self.num_transformer_feat_level = num_transformer_feat_level
+        self.num_heads = transformer_decoder.transformerlayers.attn_cfgs.num_heads
+        self.num_transformer_decoder_layers = transformer_decoder.num_layers
+        assert pixel_decoder.encoder.transformerlayers.attn_cfgs.num_levels == num_transformer_feat_level
+        pixel_decoder_ = copy.deepcopy(pixel_decoder)
+        pixel_decoder_.update(in_channels=in_channels, feat_channels=feat_channels, out_channels=out_channels)
+        self.pixel_decoder = build_plugin_layer(pixel_decoder_)[1]
+        self.transformer_decoder = build_transformer_layer_sequence(transformer_decoder)
+        self.decoder_embed_dims = self.transformer_decoder.embed_dims
+        if self.decoder_embed_dims != feat_channels or enforce_decoder_input_project:
+            raise NotImplementedError('decoder_input_projs other than Identity')
+        self.decoder_input_projs = nn.ModuleList([nn.Identity() for _ in range(num_transformer_feat_level)])
+        self.decoder_positional_encoding = build_positional_encoding(positional_encoding)
+        self.query_embed = nn.Embedding(num_queries, feat_channels)
+        self.query_feat = nn.Embedding(num_queries, feat_channels)
+        self.level_embed = nn.Embedding(num_transformer_feat_level, feat_channels)
+        self.cls_embed = nn.Linear(feat_channels, self.num_classes + 1)
+        self.mask_embed = nn.Sequential(nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+                                        nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+                                        nn.Linear(feat_channels, out_channels))
+        self.test_cfg, self.train_cfg = test_cfg, train_cfg
+        self._pe_cache = {}
+
+    def init_weights(self):
+        pass
+
+    def forward_train(self, *a, **k):
+        raise NotImplementedError('training is out of scope of the B200 inference backend')
+
+    loss = forward_train
+
+    # ---- per-layer prediction heads (mask2former_head.py:355-395 / video :337-359) ----
+    @torch.no_grad()
+    def _embeds(self, query):
+        """query [B,Q,C] -> (cls_pred [B,Q,NC+1], mask_embed [B,Q,C])."""
+        x = self.transformer_decoder.post_norm(query)
+        cls_pred = ops.linear(x, self.cls_embed.weight, self.cls_embed.bias)
+        me = ops.linear(x, self.mask_embed[0].weight, self.mask_embed[0].bias, act=ops.ACT_RELU)
+        me = ops.linear(me, self.mask_embed[2].weight, self.mask_embed[2].bias, act=ops.ACT_RELU)
+        me = ops.linear(me, self.mask_embed[4].weight, self.mask_embed[4].bias)
+        return cls_pred, me
+
+    @torch.no_grad()
+    def _decoder_pe(self, shape_thw, device):
+        key = (shape_thw, str(device))
+        if key not in self._pe_cache:
+            t, h, w = shape_thw
+            self._pe_cache[key] = self.decoder_positional_encoding.tokens(h, w, device, t=t if self.video else 0)
+        return self._pe_cache[key]
+
+    @torch.no_grad()
+    def _run(self, feats, num_frames, want_all, force_masks=None):
+        """Core forward on token-major tensors.
+
+        Returns dict(cls [B,Q,NC+1] list, mask_lr [B,T,Q,h,w] list (all layers only when
+        want_all), query [B,Q,C]).  Work elision (SURVEY.md 7 "exact-parity work elision"):
+        intermediate layers only need the sign of the bilinearly down-sampled logits, which is
+        the sign of embed . (down-sampled mask features), so the full-resolution contraction
+        runs for the last layer only unless ``want_all``.
+        """
+        mask_features, memories = self.pixel_decoder(feats)
+        BT = mask_features.shape[0]
+        T = num_frames
+        B = BT // T
+        assert B * T == BT  # mask2former_video_head.py:384
+        mf = _tokens(mask_features)                       # [BT,h4,w4,C]
+        _, h4, w4, C = mf.shape
+        mf_flat = mf.view(B, T * h4 * w4, C)
+        lvl_shapes = [tuple(m.shape[-2:]) for m in memories]
+        # attention-mask features: mask features resized to each decoder level (linear, so it
+        # commutes with the contraction -- see include/pvsg.h pvsg_mask_logits)
+        pooled = [ops.bilinear_resize_nhwc(mf, s).view(B, -1, C) for s in lvl_shapes]
+        dec_in, dec_pe = [], []
+        for i, m in enumerate(memories):
+            tok = _tokens(m)                              # [BT,h,w,C]
+            h, w = lvl_shapes[i]
+            dec_in.append(ops.add_rowvec(tok, self.level_embed.weight[i].contiguous()).view(B, T * h * w, C))
+            pe = self._decoder_pe((T, h, w), tok.device)
+            dec_pe.append(pe[None].expand(B, -1, -1).contiguous() if B > 1 else pe[None])
+        Q = self.num_queries
+        query = self.query_feat.weight[None].expand(B, -1, -1).contiguous()
+        qpos = self.query_embed.weight[None].expand(B, -1, -1).contiguous()
+        layers = self.transformer_decoder.layers
+        nl = self.num_transformer_decoder_layers
+        # K / V projections of every (layer, level) pair: independent of the queries
+        cls_list, mask_list = [], []
+        cls_pred, me = self._embeds(query)
+        cls_list.append(cls_pred)
+        if want_all:
+            mask_list.append(ops.mask_logits(me, mf_flat, True, False)[0].view(B, Q, T, h4, w4).transpose(1, 2))
+        _, mask, row_open = ops.mask_logits(me, pooled[0], False, True)
+        if force_masks is not None:  # tests: teacher-force the discrete masks (see tests/test_models_gpu.py)
+            mask, row_open = self._forced(force_masks[0])
+        for i in range(nl):
+            lvl = i % self.num_transformer_feat_level
+            kproj, vproj = layers[i].attentions[0].project_kv(dec_in[lvl], dec_pe[lvl], dec_in[lvl])
+            query = layers[i].forward_tokens(query, qpos, kproj, vproj, mask, row_open)
+            cls_pred, me = self._embeds(query)
+            cls_list.append(cls_pred)
+            last = i == nl - 1
+            if want_all or last:
+                mask_list.append(ops.mask_logits(me, mf_flat, True, False)[0].view(B, Q, T, h4, w4).transpose(1, 2))
+            if not last:
+                _, mask, row_open = ops.mask_logits(me, pooled[(i + 1) % self.num_transformer_feat_level], False, True)
+                if force_masks is not None:
+                    mask, row_open = self._forced(force_masks[i + 1])
+        return dict(cls=cls_list, masks=mask_list, query=query)
+
+    @staticmethod
+    def _forced(mask):
+        mask = mask.to(torch.uint8).contiguous()
+        return mask, (mask == 0).sum(-1).to(torch.int32).contiguous()
+
+    @torch.no_grad()
+    def _upsample(self, mask_lr, size):
+        """[N,Q,h,w] low-res logits -> [N,Q,H,W] (F.interpolate bilinear, align_corners=False)."""
+        N, Q, h, w = mask_lr.shape
+        # a [N*Q, h, w] plane stack is token-major with C = 1: resize through the C=4 kernel by
+        # moving Q into the channel axis
+        t = ops.nchw_to_nhwc(mask_lr.contiguous())                    # [N,h,w,Q]
+        up = ops.bilinear_resize_nhwc(t, size)                        # Q = 100 -> multiple of 4
+        return ops.nhwc_to_nchw(up)
+
+
+@HEADS.register_module()
+class Mask2FormerHeadCustom(_Mask2FormerHeadBase):
+    """models/mask2former/mask2former_head.py:20 (image panoptic head)."""
+    video = False
+
+    @torch.no_grad()
+    def forward(self, feats, img_metas, return_query=False):
+        """mask2former_head.py:397-479: returns (cls_pred_list, mask_pred_list[, query_feat])."""
+        r = self._run(feats, 1, want_all=True)
+        masks = [m[:, 0] for m in r['masks']]
+        qf = r['query'].transpose(0, 1)  # [Q,B,C]
+        return (r['cls'], masks, qf) if return_query else (r['cls'], masks)
+
+    @torch.no_grad()
+    def simple_test_with_query(self, feats, img_metas, upsample=True, **kwargs):
+        """mask2former_head.py:650-681.  upsample=False (used by the detector's fused path)
+        returns the low-resolution logits instead of the 4x bilinear upsample."""
+        r = self._run(feats, 1, want_all=False)
+        mask = r['masks'][-1][:, 0]
+        if upsample:
+            mask = self._upsample(mask, tuple(img_metas[0]['batch_input_shape']))
+        return r['cls'][-1], mask, r['query'].transpose(0, 1).unsqueeze(0)
+
+    def simple_test(self, feats, img_metas, **kwargs):
+        c, m, _ = self.simple_test_with_query(feats, img_metas, **kwargs)
+        return c, m
+
+
+@HEADS.register_module()
+class Mask2FormerVideoHead(_Mask2FormerHeadBase):
+    """models/mask2former_vps/mask2former_video_head.py:20 (video head; (b, t) batch axis)."""
+    video = True
+
+    @torch.no_grad()
+    def forward(self, feats, img_metas, return_query=False):
+        """mask2former_video_head.py:361-462; img_metas = list over batch of lists over frames."""
+        T = len(img_metas[0])
+        r = self._run(feats, T, want_all=True)
+        qf = r['query'].transpose(0, 1)
+        return (r['cls'], r['masks'], qf) if return_query else (r['cls'], r['masks'])
+
+    @torch.no_grad()
+    def simple_test_with_query(self, feats, img_metas, upsample=True, **kwargs):
+        """mask2former_video_head.py:637-669 -> (cls [B,Q,NC+1], masks [B,T,Q,H,W], query [Q,B,C])."""
+        T = len(img_metas[0])
+        r = self._run(feats, T, want_all=False)
+        mask = r['masks'][-1]
+        if upsample:
+            B = mask.shape[0]
+            mask = self._upsample(mask.flatten(0, 1), tuple(img_metas[0][0]['batch_input_shape']))
+            mask = mask.unflatten(0, (B, T))
+        return r['cls'][-1], mask, r['query'].transpose(0, 1)
+
+
+# ======================================================================================
+# fusion head (models/mask2former/mask2former_fusion_head.py)
+# ======================================================================================
+@HEADS.register_module()
+class MaskFormerFusionHeadCustom(nn.Module):
+    def __init__(self, num_things_classes=80, num_stuff_classes=53, test_cfg=None, loss_panoptic=None,
+                 init_cfg=None, **kwargs):
+        super().__init__()
+        self.num_things_classes = num_things_classes
+        self.num_stuff_classes = num_stuff_classes
+        self.num_classes = num_things_classes + num_stuff_classes
+        self.test_cfg = dict(test_cfg or {})
+
+    def forward_train(self, **kwargs):
+        return dict()
+
+    @torch.no_grad()
+    def _panoptic(self, mask_cls, mask_lr, in_hw, img_hw, out_hw):
+        return ops.panoptic_fuse(mask_cls, mask_lr, in_hw, img_hw, out_hw, self.num_things_classes, self.num_classes,
+                                 float(self.test_cfg.get('object_mask_thr', 0.8)),
+                                 float(self.test_cfg.get('iou_thr', 0.8)),
+                                 bool(self.test_cfg.get('filter_low_score', False)), INSTANCE_OFFSET)
+
+    @staticmethod
+    def _query_dict(seg_info, query_feat):
+        """seg_info (host int32 array) -> {seg_id: [feat]} in the reference's insertion order."""
+        n = int(seg_info[0])
+        rows = seg_info[1:1 + 4 * n].reshape(n, 4)
+        d = defaultdict(list)
+        for q, _cls, seg, _area in rows:
+            if seg >= 0:
+                d[int(seg)].append(query_feat[int(q)])
+        return d
+
+    @torch.no_grad()
+    def panoptic_postprocess_with_query(self, mask_cls, mask_pred, query_feats):
+        """mask2former_fusion_head.py:96-171 on full-resolution logits [Q,H,W]."""
+        H, W = mask_pred.shape[-2:]
+        pan, info = self._panoptic(mask_cls, mask_pred, (H, W), (H, W), (H, W))
+        return pan, self._query_dict(info.cpu().numpy(), query_feats)
+
+    @torch.no_grad()
+    def instance_postprocess(self, mask_cls, mask_lr, in_hw=None, img_hw=None, out_hw=None, want_masks=True):
+        """mask2former_fusion_head.py:192-242.  Class-score top-k runs on the tiny [Q, NC]
+        score matrix on the host side of the stream (torch.topk, 12.6k values); all per-pixel
+        work (binary masks, mask scores, boxes) is pvsg_instance_masks."""
+        max_per_image = self.test_cfg.get('max_per_image', 100)
+        H, W = mask_lr.shape[-2:]
+        in_hw, img_hw, out_hw = in_hw or (H, W), img_hw or (H, W), out_hw or (H, W)
+        scores = torch.softmax(mask_cls, dim=-1)[:, :-1]
+        scores_per_image, top_indices = scores.flatten(0, 1).topk(max_per_image, sorted=False)
+        labels_per_image = top_indices % self.num_classes
+        query_indices = top_indices // self.num_classes
+        is_thing = labels_per_image < self.num_things_classes
+        scores_per_image, labels_per_image = scores_per_image[is_thing], labels_per_image[is_thing]
+        query_indices = query_indices[is_thing]
+        stats, boxes, masks = ops.instance_masks(mask_lr, query_indices.to(torch.int32), in_hw, img_hw, out_hw,
+                                                 want_masks)
+        mask_scores = stats[:, 0] / (stats[:, 1] + 1e-6)
+        det_scores = scores_per_image * mask_scores
+        bboxes = torch.cat([boxes.float(), det_scores[:, None]], dim=-1)
+        return labels_per_image, bboxes, (masks.bool() if masks is not None else None)
+
+    @torch.no_grad()
+    def simple_test_with_query(self, mask_cls_results, mask_pred_results, query_feats, img_metas, rescale=False,
+                               lowres=False, **kwargs):
+        """mask2former_fusion_head.py:325-404.  With ``lowres=True`` mask_pred_results are the
+        un-upsampled logits and the x4 upsample is fused into the post-processing kernels."""
+        panoptic_on = self.test_cfg.get('panoptic_on', True)
+        semantic_on = self.test_cfg.get('semantic_on', False)
+        instance_on = self.test_cfg.get('instance_on', False)
+        assert not semantic_on, 'segmantic segmentation results are not supported yet.'
+        results = []
+        for mask_cls, mask_pred, qf, meta in zip(mask_cls_results, mask_pred_results, query_feats, img_metas):
+            img_hw = tuple(meta['img_shape'][:2])
+            in_hw = tuple(meta['batch_input_shape']) if lowres else tuple(mask_pred.shape[-2:])
+            out_hw = tuple(meta['ori_shape'][:2]) if rescale else img_hw
+            result = dict()
+            if panoptic_on:
+                pan, info = self._panoptic(mask_cls, mask_pred, in_hw, img_hw, out_hw)
+                result['pan_results'] = pan
+                result['query_feats'] = self._query_dict(info.cpu().numpy(), qf)
+            if instance_on:
+                result['ins_results'] = self.instance_postprocess(mask_cls, mask_pred, in_hw, img_hw, out_hw)
+            results.append(result)
+        return results
+
+
+HEADS.register_module(name='MaskFormerFusionHead', module=MaskFormerFusionHeadCustom)
+
+
+def bbox2result(bboxes, labels, num_classes):
+    """mmdet.core.bbox2result (L0)."""
+    if bboxes.shape[0] == 0:
+        return [np.zeros((0, bboxes.shape[1]), dtype=np.float32) for _ in range(num_classes)]
+    bboxes = bboxes.detach().cpu().numpy()
+    labels = labels.detach().cpu().numpy()
+    return [bboxes[labels == i, :] for i in range(num_classes)]
+
+
+# ======================================================================================
+# detectors
+# ======================================================================================
+class _DetectorBase(nn.Module):
+    def __init__(self, backbone, neck=None, panoptic_head=None, panoptic_fusion_head=None, train_cfg=None,
+                 test_cfg=None, init_cfg=None, **kwargs):
+        super().__init__()
+        if neck is not None:
+            raise NotImplementedError('neck')
+        self.backbone = build_backbone(backbone)
+        ph = copy.deepcopy(to_cfg(panoptic_head))
+        ph.update(train_cfg=train_cfg, test_cfg=test_cfg)
+        self.panoptic_head = build_head(ph)
+        pf = copy.deepcopy(to_cfg(panoptic_fusion_head))
+        pf.update(test_cfg=test_cfg)
+        self.panoptic_fusion_head = build_head(pf)
+        self.num_things_classes = self.panoptic_head.num_things_classes
+        self.num_stuff_classes = self.panoptic_head.num_stuff_classes
+        self.num_classes = self.panoptic_head.num_classes
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.eval()
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError('inference backend only')
+        return super().train(False)
+
+    def extract_feat(self, img):
+        return self.backbone(img)
+
+    def forward_train(self, *a, **k):
+        raise NotImplementedError('training is out of scope of the B200 inference backend')
+
+    def aug_test(self, imgs, img_metas, **kwargs):
+        raise NotImplementedError  # as the reference: mask2former.py:193-194
+
+    def forward(self, img=None, img_metas=None, return_loss=False, **kwargs):
+        """mmdet BaseDetector.forward."""
+        if return_loss:
+            return self.forward_train(img, img_metas, **kwargs)
+        return self.forward_test(img, img_metas, **kwargs)
+
+
+@DETECTORS.register_module()
+class Mask2FormerCustom(_DetectorBase):
+    """models/mask2former/mask2former.py:14 (image panoptic segmentation)."""
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """mmdet BaseDetector.forward_test (single augmentation): adds batch_input_shape."""
+        img, metas = (imgs[0], img_metas[0]) if isinstance(imgs, (list, tuple)) else (imgs, img_metas)
+        for m in metas:
+            m['batch_input_shape'] = tuple(img.shape[-2:])
+        return self.simple_test(img, metas, **kwargs)
+
+    @torch.no_grad()
+    def simple_test(self, imgs, img_metas, **kwargs):
+        """mask2former.py:121-191."""
+        feats = self.extract_feat(imgs)
+        mask_cls, mask_lr, query_feats = self.panoptic_head.simple_test_with_query(feats, img_metas, upsample=False)
+        results = self.panoptic_fusion_head.simple_test_with_query(mask_cls, mask_lr, query_feats, img_metas,
+                                                                   lowres=True, **kwargs)
+        for r in results:
+            if 'pan_results' in r:
+                r['pan_results'] = r['pan_results'].cpu().numpy()
+            if 'query_feats' in r:
+                r['query_feats'] = {k: [x.cpu().numpy() for x in v] for k, v in r['query_feats'].items()}
+            if 'ins_results' in r:
+                labels, bboxes, masks = r['ins_results']
+                bbox_results = bbox2result(bboxes, labels, self.num_things_classes)
+                mask_results = [[] for _ in range(self.num_things_classes)]
+                masks_np = masks.cpu().numpy()
+                for j, label in enumerate(labels.tolist()):
+                    mask_results[label].append(masks_np[j])
+                r['ins_results'] = bbox_results, mask_results
+        if self.num_stuff_classes == 0:
+            results = [res['ins_results'] for res in results]
+        return results
+
+
+@DETECTORS.register_module()
+class Mask2FormerVideoCustom(_DetectorBase):
+    """models/mask2former_vps/mask2former.py:33 (video panoptic segmentation)."""
+
+    def __init__(self, *args, dataset='kitti-step', **kwargs):
+        super().__init__(*args, **kwargs)
+        self.dataset = dataset
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """mask2former.py:225-240."""
+        for img, img_meta in zip(imgs, img_metas):
+            for m in img_meta:
+                m['batch_input_shape'] = tuple(img.size()[-2:])
+        for ref_img, ref_img_meta in zip(kwargs['ref_img'], kwargs['ref_img_metas']):
+            for frame_meta in ref_img_meta:
+                frame_meta['batch_input_shape'] = tuple(ref_img.size()[-2:])
+        kwargs['ref_img'] = kwargs['ref_img'][0] if isinstance(kwargs['ref_img'], (list, tuple)) else kwargs['ref_img']
+        return self.simple_test(img=imgs, img_metas=img_metas, **kwargs)
+
+    @torch.no_grad()
+    def simple_test(self, img, img_metas, ref_img, ref_img_metas, **kwargs):
+        """mask2former.py:125-223 for the shipped configuration (clip length 1 per sample)."""
+        bs, num_frame, three, h, w = ref_img.size()
+        if num_frame != 1:
+            # frames >= 2 call self.match_from_embds, which the reference class does not define
+            # (mask2former.py:155) -- same failure mode here.
+            raise AttributeError("'Mask2FormerVideoCustom' object has no attribute 'match_from_embds'")
+        video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
+        results = [[] for _ in range(bs)]
+        for i in range(bs):
+            feats = [f[i:i + 1] for f in video_x]
+            mask_cls, mask_lr, query = self.panoptic_head.simple_test_with_query(feats, [ref_img_metas[i]],
+                                                                                 upsample=False)
+            out_logits = mask_cls                      # [1,Q,NC+1]
+            out_embds = query.permute(1, 0, 2)         # [1,Q,C]
+            for frame_id in range(num_frame):
+                res = self.panoptic_fusion_head.simple_test_with_query(
+                    out_logits, mask_lr[:, frame_id], out_embds, [ref_img_metas[i][frame_id]], lowres=True,
+                    **kwargs)[0]
+                res['pan_results'] = res['pan_results'].cpu().numpy()
+                if 'ins_results' in res:
+                    labels, bboxes, masks = res['ins_results']
+                    ids = torch.arange(len(bboxes), dtype=bboxes.dtype, device=bboxes.device)[:, None] + 1
+                    bboxes = torch.cat([ids, bboxes], dim=1)
+                    inds = torch.argsort(bboxes[:, -1], descending=True)[:10]
+                    labels, bboxes, masks = labels[inds], bboxes[inds], masks[inds]
+                    bbox_results = bbox2result(bboxes, labels, self.num_things_classes)
+                    mask_results = [[] for _ in range(self.num_things_classes)]
+                    masks_np = masks.cpu().numpy()
+                    for j, label in enumerate(labels.tolist()):
+                        mask_results[label].append(masks_np[j])
+                    res['ins_results'] = bbox_results, mask_results
+                results[i].append(res)
+        return results

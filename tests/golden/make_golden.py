@@ -381,10 +381,45 @@ def golden_m2f():
     print('detector.npz VPS segments', vkeys, 'IPS segments', ikeys)
 
 
+def golden_full_frames():
+    """ORACLE-derived (not reference-derived) fixtures at the BASELINE full sizes: the CPU oracle
+    takes ~10-40 s per frame at these sizes, so its outputs are stored once here instead of
+    being recomputed on the GPU box.  The oracle itself is pinned by the vectors above."""
+    sd = syn.mask2former_state_dict(seed=3)
+    for name, (H, W) in (('frame_480x640', (480, 640)), ('frame_720x1280', (720, 1280))):
+        img = syn.synthetic_frame(17, H, W)[None]
+        meta = syn.frame_meta(H, W)
+        with torch.no_grad():
+            feats = om.resnet50(sd, img)
+            cls, masks, query, ex = om.head_forward(sd, feats, video=True, num_frames=1, return_all=True)
+            res = om.vps_simple_test(sd, img[None], [[meta]], instance_on=False)[0][0]
+        keys = sorted(res['query_feats'].keys())
+        near = [int((torch.nn.functional.interpolate(masks[i].flatten(0, 1), tuple(ex['memories'][i % 3].shape[-2:]),
+                                                     mode='bilinear', align_corners=False).abs() < 1e-4).sum())
+                for i in range(9)]
+        np.savez_compressed(
+            f'{HERE}/{name}.npz', weights_seed=3, frame_seed=17, H=H, W=W, in_checksum=checksum(img),
+            c5_sample=feats[3][0, ::16, ::3, ::3].numpy(), c2_sample=feats[0][0, ::16, ::9, ::9].numpy(),
+            mask_feature_sample=ex['mask_features'][0, 0, ::8, ::6, ::6].numpy(),
+            cls_all=torch.stack([c[0] for c in cls]).numpy(), query=query.numpy(),
+            mask_last_sample=masks[-1][0, 0, :, ::4, ::4].numpy(),
+            mask_mid_sample=masks[4][0, 0, :, ::8, ::8].numpy(),
+            attn_masks=np.concatenate([np.packbits(a[0].numpy().reshape(-1)) for a in ex['attn_masks']]),
+            attn_shapes=np.array([list(a[0].shape) for a in ex['attn_masks']]),
+            near_zero_mask_logits=np.array(near),
+            pan=res['pan_results'], keys=np.array(keys),
+            qfeats=np.stack([np.asarray(res['query_feats'][k][0]) for k in keys]) if keys else np.zeros((0, 256)))
+        print(name, 'segments', keys, 'near-zero mask logits per layer', near)
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == 'frames':
+        golden_full_frames()
+        sys.exit(0)
     golden_relation()
     golden_m2f()
+    golden_full_frames()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
