@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mask2Former-VPS (R50) inference frames/s on synthetic 720p clips.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+A step = one pass of the hot path over one clip shard: `--frames` (default 100) synthetic
+720p frames per GPU (BASELINE.json configs[1]; weak scaling: the clip has N x 100 frames,
+contiguous blocks per rank), each frame through backbone -> pixel decoder (6 x MSDeformAttn)
+-> 9 masked-attention decoder layers -> fused panoptic + instance post-processing, then the
+tube-linking exchange (all-gather over NCCL when N > 1).
+
+`value`  : frames/s with the frames already resident in HBM (results still read back).
+`e2e`    : frames/s through the public detector API (model(return_loss=False, rescale=True,
+           img=..., ref_img=...)) from PINNED HOST frames: H2D of every frame and D2H of every
+           result inside the timed region.
+`roofline`: the dominant kernel family (the fp32 GEMM / implicit-GEMM conv engine), achieved
+           TFLOP/s on algorithmic FLOPs measured live with CUDA events on an instrumented
+           frame, against the measured bf16 tensor peak of MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle (a port of the reference algorithm; the reference itself needs
+           mmcv/mmdet, which cannot be installed offline) timed on the host cores on a bounded
+           sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W = 720, 1280
+METRIC = 'Mask2Former-VPS R50 inference frames/sec @720p'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d['bf16_tflops_sustained'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def make_frames(n_distinct, rank):
+    from openpvsg_b200 import synthetic as syn
+    return [syn.synthetic_frame(1000 * rank + i, H, W) for i in range(n_distinct)]
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_oracle_fps(n_frames, warmup=1):
+    from openpvsg_b200 import synthetic as syn
+    from oracle import m2f as om
+    torch.set_num_threads(os.cpu_count())
+    sd = syn.mask2former_state_dict(seed=0)
+    meta = syn.frame_meta(H, W)
+    frames = [syn.synthetic_frame(i, H, W) for i in range(max(1, min(n_frames, 2)))]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + n_frames):
+            t0 = time.perf_counter()
+            om.vps_simple_test(sd, frames[i % len(frames)][None, None], [[meta]], rescale=True)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return n_frames / sum(times), times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fps, times = cpu_oracle_fps(args.steps, warmup=min(args.warmup, 1))
+    cores = os.cpu_count()
+    line = dict(metric=METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * float(np.mean(times)), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload='Mask2Former R50 inference, synthetic 720p clip (BASELINE configs[1])',
+                            frames_per_step=1, note='CPU oracle port of the reference algorithm; mmcv/mmdet '
+                            'are not installable offline so the reference itself cannot run'),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port',
+                                  sample=f'{args.steps} frame(s) @720p, 1 frame per step, torch CPU fp32, {cores} threads'),
+                e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# instrumented frame: per-kernel-family time / flops with CUDA events
+# --------------------------------------------------------------------------------------
+def kernel_breakdown(det, img, meta):
+    from openpvsg_b200 import ops
+    fam = {}
+    events = []
+
+    def wrap(name, family, flops_fn=None, bytes_fn=None):
+        orig = getattr(ops, name)
+
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(*a, **k)
+            e1.record()
+            events.append((family, e0, e1, flops_fn(a, k, out) if flops_fn else 0.0,
+                           bytes_fn(a, k, out) if bytes_fn else 0.0))
+            return out
+        setattr(ops, name, f)
+        return orig
+
+    def lin_flops(a, k, out):
+        x, w = a[0], a[1]
+        return 2.0 * (x.numel() // x.shape[-1]) * w.shape[0] * w.shape[1]
+
+    def conv_flops(a, k, out):
+        w = a[1]
+        return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+
+    def ml_flops(a, k, out):
+        e, f = a[0], a[1]
+        return 2.0 * e.shape[0] * e.shape[1] * e.shape[2] * f.shape[1]
+
+    def msda_bytes(a, k, out):
+        v, proj = a[0], a[2]
+        return 4.0 * (v.numel() + proj.numel() + out.numel())
+
+    saved = {n: wrap(n, f, fl, by) for n, f, fl, by in (
+        ('linear', 'gemm', lin_flops, None), ('conv2d_nhwc', 'gemm', conv_flops, None),
+        ('mask_logits', 'gemm', ml_flops, None), ('msda_fused_forward', 'msda', None, msda_bytes),
+        ('attention', 'attention', None, None), ('layernorm', 'norm', None, None),
+        ('groupnorm_nhwc', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
+        ('instance_masks', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
+        ('maxpool3x3s2_nhwc', 'resize', None, None), ('add_rowvec', 'norm', None, None))}
+    try:
+        runners = det._runners
+        det._runners = None  # eager path so that every launch is bracketed by events
+        det.simple_test(None, None, ref_img=img[None, None], ref_img_metas=[[meta]], rescale=True)
+        events.clear()
+        det.simple_test(None, None, ref_img=img[None, None], ref_img_metas=[[meta]], rescale=True)
+        torch.cuda.synchronize()
+    finally:
+        det._runners = runners
+        for n, o in saved.items():
+            setattr(ops, n, o)
+    for family, e0, e1, fl, by in events:
+        d = fam.setdefault(family, dict(ms=0.0, gflop=0.0, gbyte=0.0, launches=0))
+        d['ms'] += e0.elapsed_time(e1)
+        d['gflop'] += fl / 1e9
+        d['gbyte'] += by / 1e9
+        d['launches'] += 1
+    return fam
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--frames', type=int, default=100, help='frames per GPU per step')
+    ap.add_argument('--distinct', type=int, default=8, help='distinct synthetic frames cycled through')
+    ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    import openpvsg_b200 as pv
+    from openpvsg_b200 import configs, engine, lib, synthetic as syn, tubes
+    peaks = load_peaks()
+    det = pv.build_detector(configs.mask2former_r50(True))
+    det.load_state_dict(syn.mask2former_state_dict(seed=0))
+    det.to(dev)
+    engine.enable_cuda_graph(det)
+    meta = syn.frame_meta(H, W)
+    host = [f.pin_memory() for f in make_frames(args.distinct, rank)]
+    resident = [f.to(dev) for f in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_step(frames, api):
+        """One clip shard: every frame through the detector, then tube linking."""
+        entries = []
+        for i in range(args.frames):
+            x = frames[i % len(frames)]
+            if api:  # public API from pinned host memory
+                xd = x.to(dev, non_blocking=True)[None]
+                res = det(return_loss=False, rescale=True, img=[xd], img_metas=[[dict(meta)]], ref_img=[xd[None]],
+                          ref_img_metas=[[dict(meta)]])[0][0]
+            else:
+                res = det.simple_test(None, None, ref_img=x[None, None], ref_img_metas=[[meta]], rescale=True)[0][0]
+            ids = list(res['query_feats'].keys())
+            entries.append((ids, [res['query_feats'][k][0] for k in ids]))
+        ids_feats = [(ids, torch.stack(f).cpu().numpy() if f else np.zeros((0, 256), np.float32)) for ids, f in entries]
+        return tubes.gather_and_link(ids_feats, args.frames * world, device=dev if world > 1 else 'cpu')
+
+    def timed(frames, api, steps, warmup):
+        for _ in range(warmup):
+            run_step(frames, api)
+        barrier()
+        n0 = lib.launch_count[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            linker = run_step(frames, api)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, linker, lib.launch_count[0] - n0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, linker, _ = timed(resident, False, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(host, True, args.steps, 1)
+    runner = next(iter(det._runners.values()))
+    launches = runner.launches_per_frame * args.frames * args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_frames = args.frames * world * args.steps
+    value = total_frames / (ms_dev * 1e-3)
+    e2e = total_frames / (ms_e2e * 1e-3)
+    fam = kernel_breakdown(det, resident[0], meta)
+    tot_ms = sum(d['ms'] for d in fam.values())
+    g = fam.get('gemm', dict(ms=1.0, gflop=0.0, launches=1))
+    achieved_tf = g['gflop'] / g['ms']  # GFLOP / ms == TFLOP/s
+    roofline = dict(kernel='gemm_kernel (fp32 SIMT GEMM / implicit-GEMM conv engine)', bound='tensor',
+                    achieved=round(achieved_tf, 2), peak=peaks['tf_sustained'], unit='TFLOP/s',
+                    frac=round(achieved_tf / peaks['tf_sustained'], 4), traffic=None,
+                    peak_source=peaks['source'] + ', sustained bf16 figure (kernel timed inside a long step)',
+                    launches_per_frame=g['launches'], gflop_per_frame=round(g['gflop'], 1),
+                    share_of_frame=round(g['ms'] / tot_ms, 3))
+    m = fam.get('msda')
+    kernels = {k: dict(ms_per_frame=round(d['ms'], 3), share=round(d['ms'] / tot_ms, 3), launches=d['launches'])
+               for k, d in fam.items()}
+    if m:
+        kernels['msda']['achieved_GBps'] = round(m['gbyte'] / (m['ms'] * 1e-3), 1)
+        kernels['msda']['frac_hbm'] = round(m['gbyte'] / (m['ms'] * 1e-3) / peaks['hbm_gbs'], 4)
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, times = cpu_oracle_fps(args.cpu_frames)
+        cpu = dict(value=fps, unit='frames/s', cores=os.cpu_count(), kind='port',
+                   sample=f'{args.cpu_frames} frames @720p through the CPU oracle (torch CPU fp32, '
+                          f'{os.cpu_count()} threads), 1 warm-up frame')
+    in_bytes = 3 * 736 * 1280 * 4
+    out_bytes = H * W * 4 + (1 + 400) * 4 + 10 * H * W + 100 * 256 * 4
+    line = dict(metric=METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 3), higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='Mask2Former-VPS R50 inference, synthetic 720p clip, 100 frames per GPU '
+                                     '(BASELINE configs[1]); random-init weights of the reference architecture',
+                            frames_per_gpu_per_step=args.frames, distinct_frames=args.distinct,
+                            resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
+                            l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',
+                            cuda_graph=True, tubes=len(linker.object_list)),
+                e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames,
+                         d2h_bytes_per_step=out_bytes * args.frames, ms_per_step=round(ms_e2e / args.steps, 3)),
+                gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -85,7 +85,13 @@ def load():
     return lib
 
 
+# kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)
+KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3}
+launch_count = [0]
+
+
 def check(code, what):
+    launch_count[0] += KERNELS_PER_CALL.get(what, 1)
     if code != 0:
         msg = load().pvsg_error_string(code).decode()
         raise PvsgError(f'{what} failed: {msg} ({code})')

@@ -802,22 +802,31 @@ class MaskFormerFusionHeadCustom(nn.Module):
         """mask2former_fusion_head.py:192-242.  Class-score top-k runs on the tiny [Q, NC]
         score matrix on the host side of the stream (torch.topk, 12.6k values); all per-pixel
         work (binary masks, mask scores, boxes) is pvsg_instance_masks."""
-        max_per_image = self.test_cfg.get('max_per_image', 100)
         H, W = mask_lr.shape[-2:]
         in_hw, img_hw, out_hw = in_hw or (H, W), img_hw or (H, W), out_hw or (H, W)
+        return self._instance_finish(self._instance_device(mask_cls, mask_lr, in_hw, img_hw, out_hw, want_masks))
+
+    @torch.no_grad()
+    def _instance_device(self, mask_cls, mask_lr, in_hw, img_hw, out_hw, want_masks=True):
+        """Static-shape device part (CUDA-graph capturable): all ``max_per_image`` candidates are
+        evaluated, stuff candidates are dropped afterwards by ``_instance_finish``."""
+        max_per_image = self.test_cfg.get('max_per_image', 100)
         scores = torch.softmax(mask_cls, dim=-1)[:, :-1]
         scores_per_image, top_indices = scores.flatten(0, 1).topk(max_per_image, sorted=False)
         labels_per_image = top_indices % self.num_classes
-        query_indices = top_indices // self.num_classes
-        is_thing = labels_per_image < self.num_things_classes
-        scores_per_image, labels_per_image = scores_per_image[is_thing], labels_per_image[is_thing]
-        query_indices = query_indices[is_thing]
-        stats, boxes, masks = ops.instance_masks(mask_lr, query_indices.to(torch.int32), in_hw, img_hw, out_hw,
-                                                 want_masks)
+        query_indices = (top_indices // self.num_classes).to(torch.int32)
+        stats, boxes, masks = ops.instance_masks(mask_lr, query_indices, in_hw, img_hw, out_hw, want_masks)
+        return dict(scores=scores_per_image, labels=labels_per_image, stats=stats, boxes=boxes, masks=masks)
+
+    @torch.no_grad()
+    def _instance_finish(self, d):
+        is_thing = d['labels'] < self.num_things_classes
+        stats = d['stats'][is_thing]
         mask_scores = stats[:, 0] / (stats[:, 1] + 1e-6)
-        det_scores = scores_per_image * mask_scores
-        bboxes = torch.cat([boxes.float(), det_scores[:, None]], dim=-1)
-        return labels_per_image, bboxes, (masks.bool() if masks is not None else None)
+        det_scores = d['scores'][is_thing] * mask_scores
+        bboxes = torch.cat([d['boxes'][is_thing].float(), det_scores[:, None]], dim=-1)
+        masks = d['masks'][is_thing].bool() if d['masks'] is not None else None
+        return d['labels'][is_thing], bboxes, masks
 
     @torch.no_grad()
     def simple_test_with_query(self, mask_cls_results, mask_pred_results, query_feats, img_metas, rescale=False,
@@ -962,6 +971,12 @@ class Mask2FormerVideoCustom(_DetectorBase):
             # frames >= 2 call self.match_from_embds, which the reference class does not define
             # (mask2former.py:155) -- same failure mode here.
             raise AttributeError("'Mask2FormerVideoCustom' object has no attribute 'match_from_embds'")
+        if getattr(self, '_runners', None) is not None and bs == 1:
+            # CUDA-graph replay of the same kernels (openpvsg_b200/engine.py)
+            from .engine import get_runner
+            runner = get_runner(self, ref_img_metas[0][0], kwargs.get('rescale', False))
+            runner.run(ref_img)
+            return [[runner.results()]]
         video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
         results = [[] for _ in range(bs)]
         for i in range(bs):

@@ -1,0 +1,166 @@
+"""Tube linking of per-frame VPS results (reference models/mask2former_vps/utils.py:20-89
+``concat_seq``) and its multi-GPU form.
+
+Frames of a clip are independent work items, so a clip is sharded over ranks in contiguous
+blocks; the only exchange of the whole path is here: an all-gather of the kept
+(segment id, query feature) entries of every frame.  Masks are never gathered -- each rank
+RLE-encodes the frames it owns.  Wire formats follow the reference:
+``masks.txt`` lines ``frame id cid h w rle`` (models/unitrack/utils/io.py:14-37) and the
+per-tube feature lists of ``query_feats.pickle`` (utils.py:75-89).
+"""
+import numpy as np
+import torch
+
+
+# -------------------------------------------------------------------------- RLE -------
+def rle_counts(mask):
+    """COCO RLE run lengths of a [H,W] binary mask (column-major, first run counts zeros)."""
+    flat = np.asarray(mask, dtype=np.uint8).reshape(-1, order='F')
+    if flat.size == 0:
+        return [0]
+    change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    bounds = np.concatenate(([0], change, [flat.size]))
+    runs = np.diff(bounds).tolist()
+    return runs if flat[0] == 0 else [0] + runs
+
+
+def rle_string(counts):
+    """pycocotools ``rleToString``: 5 bits per char + continuation bit, deltas from the 3rd run."""
+    out = []
+    for i, x in enumerate(counts):
+        x = int(x)
+        if i > 2:
+            x -= int(counts[i - 2])
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(chr(c + 48))
+    return ''.join(out)
+
+
+def rle_decode(string, h, w):
+    """Inverse of rle_string + rle_counts (pycocotools ``rleFrString`` + decode)."""
+    counts, p, m = [], 0, 0
+    while p < len(string):
+        x, k, more = 0, 0, True
+        while more:
+            c = ord(string[p]) - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if m > 2:
+            x += counts[m - 2]
+        counts.append(x)
+        m += 1
+    flat = np.zeros(h * w, np.uint8)
+    pos, val = 0, 0
+    for c in counts:
+        flat[pos:pos + c] = val
+        pos += c
+        val ^= 1
+    return flat.reshape((h, w), order='F')
+
+
+# ------------------------------------------------------------------- tube linking -----
+class TubeLinker:
+    """Incremental ``concat_seq``: tube id = 1 + order of first appearance of a panoptic id."""
+
+    def __init__(self):
+        self.object_list = []
+        self.feat_tubes = {}
+        self.rows = []          # (frame (1-based), tube id, class id, h, w, rle string)
+        self.num_frames = 0
+
+    def add_frame(self, seg_ids, feats, pan=None):
+        """seg_ids: iterable of panoptic ids kept in this frame (reference dict order);
+        feats: matching [n,256] array; pan: optional int32 [H,W] map (-> masks.txt rows)."""
+        frame_id = self.num_frames
+        for ins_id, feat in zip(seg_ids, feats):
+            ins_id = int(ins_id)
+            if ins_id not in self.object_list:
+                self.object_list.append(ins_id)
+                self.feat_tubes[len(self.object_list)] = {}
+            tid = self.object_list.index(ins_id) + 1
+            self.feat_tubes[tid][frame_id] = dict(query_feat=np.array(feat, dtype=np.float32, copy=True).reshape(-1),
+                                                  cls_id=int(ins_id % 1000))
+            if pan is not None:
+                mask = (pan == ins_id)
+                self.rows.append((frame_id + 1, tid, int(ins_id % 1000), mask.shape[0], mask.shape[1],
+                                  rle_string(rle_counts(mask))))
+        self.num_frames += 1
+
+    def tube_features(self, feature_dim=256):
+        """[N_tubes, T, 256] with zero rows for absent frames -- the relation head's input
+        (utils/relation_matching.py:431-442, datasets/datasets/pvsg_relation.py:47-53)."""
+        out = np.zeros((len(self.object_list), self.num_frames, feature_dim), np.float32)
+        for tid, frames in self.feat_tubes.items():
+            for f, d in frames.items():
+                out[tid - 1, f] = d['query_feat']
+        return out
+
+    def masks_txt(self):
+        return ''.join(f'{fr} {tid} {cid} {h} {w} {rle}\n' for fr, tid, cid, h, w, rle in self.rows)
+
+
+def concat_seq(outputs):
+    """outputs: list over frames of [result dict] (what single_gpu_test collects).  Returns the
+    TubeLinker holding masks.txt rows and the per-tube query features."""
+    linker = TubeLinker()
+    for output in outputs:
+        output = output[0]
+        ids = list(output['query_feats'].keys())
+        feats = [np.asarray(torch.as_tensor(output['query_feats'][k][0]).cpu()) for k in ids]
+        linker.add_frame(ids, feats, output.get('pan_results'))
+    return linker
+
+
+# ------------------------------------------------------------------ multi-GPU ---------
+def shard_frames(num_frames, world_size, rank):
+    """Contiguous block of ceil(T / G) frames per rank."""
+    per = (num_frames + world_size - 1) // world_size
+    lo = min(rank * per, num_frames)
+    return lo, min(lo + per, num_frames)
+
+
+def pack_frames(frame_entries, max_frames, max_segments, feature_dim=256, device='cpu'):
+    """frame_entries: list over local frames of (seg_ids list, feats [n,256]).  Fixed-size tensors
+    for the all-gather: ids int32 [max_frames, max_segments] (-1 = empty), feats fp32."""
+    ids = torch.full((max_frames, max_segments), -1, dtype=torch.int32)
+    feats = torch.zeros(max_frames, max_segments, feature_dim)
+    for f, (sid, ft) in enumerate(frame_entries):
+        n = len(sid)
+        if n:
+            ids[f, :n] = torch.as_tensor(list(sid), dtype=torch.int32)
+            feats[f, :n] = torch.as_tensor(np.asarray(ft, np.float32).reshape(n, -1))
+    return ids.to(device), feats.to(device)
+
+
+def gather_and_link(frame_entries, num_frames, max_segments=100, device='cpu'):
+    """All-gather the per-frame kept entries of every rank (NCCL when the tensors are on the
+    GPU, gloo on CPU) and link tubes over the whole clip.  Every rank returns the same
+    TubeLinker (without masks.txt rows: masks stay on the rank that owns the frame)."""
+    import torch.distributed as dist
+    ws = dist.get_world_size() if dist.is_initialized() else 1
+    per = (num_frames + ws - 1) // ws
+    ids, feats = pack_frames(frame_entries, per, max_segments, device=device)
+    if ws > 1:
+        all_ids = [torch.empty_like(ids) for _ in range(ws)]
+        all_feats = [torch.empty_like(feats) for _ in range(ws)]
+        dist.all_gather(all_ids, ids)
+        dist.all_gather(all_feats, feats)
+    else:
+        all_ids, all_feats = [ids], [feats]
+    ids = torch.cat(all_ids, 0)[:num_frames].cpu().numpy()
+    feats = torch.cat(all_feats, 0)[:num_frames].cpu().numpy()
+    linker = TubeLinker()
+    for f in range(num_frames):
+        keep = ids[f] >= 0
+        linker.add_frame(ids[f][keep].tolist(), feats[f][keep])
+    return linker

@@ -1,0 +1,105 @@
+"""CPU: tube linking / wire formats / frame sharding, incl. the N > 1 path over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from openpvsg_b200 import tubes
+from oracle import m2f as om
+
+
+def _fake_outputs(num_frames=7, seed=0, h=12, w=9):
+    rng = np.random.default_rng(seed)
+    outs = []
+    for f in range(num_frames):
+        pan = np.full((h, w), 126, np.int32)
+        ids = []
+        for sid in (1005, 117, 2005, 3040):
+            if rng.random() < 0.6:
+                y, x = rng.integers(0, h - 3), rng.integers(0, w - 3)
+                pan[y:y + 3, x:x + 3] = sid
+                ids.append(sid)
+        ids = [i for i in ids if (pan == i).any()]
+        outs.append([dict(pan_results=pan, query_feats={i: [torch.full((256,), float(i + f))] for i in ids})])
+    return outs
+
+
+def test_rle_roundtrip_and_oracle():
+    rng = np.random.default_rng(1)
+    for shape in ((1, 1), (5, 7), (33, 21), (64, 64)):
+        for p in (0.0, 0.1, 0.5, 1.0):
+            m = (rng.random(shape) < p).astype(np.uint8)
+            counts = tubes.rle_counts(m)
+            assert counts == om.rle_encode(m)
+            assert sum(counts) == m.size
+            s = tubes.rle_string(counts)
+            assert s == om.rle_to_string(counts)
+            assert np.array_equal(tubes.rle_decode(s, *shape), m)
+    # long runs need multi-character codes
+    m = np.zeros((300, 300), np.uint8)
+    m[100:200, 50:250] = 1
+    assert np.array_equal(tubes.rle_decode(tubes.rle_string(tubes.rle_counts(m)), 300, 300), m)
+
+
+def test_concat_seq_matches_oracle():
+    outs = _fake_outputs()
+    linker = tubes.concat_seq(outs)
+    rows, feat_tubes = om.concat_seq(outs)
+    assert linker.rows == rows
+    assert sorted(linker.feat_tubes) == sorted(feat_tubes)
+    for tid in feat_tubes:
+        assert sorted(linker.feat_tubes[tid]) == sorted(feat_tubes[tid])
+        for f in feat_tubes[tid]:
+            assert np.array_equal(linker.feat_tubes[tid][f]['query_feat'], feat_tubes[tid][f]['query_feat'])
+            assert linker.feat_tubes[tid][f]['cls_id'] == feat_tubes[tid][f]['cls_id']
+    txt = linker.masks_txt().splitlines()
+    assert len(txt) == len(rows) and txt[0].split(' ')[:5] == [str(v) for v in rows[0][:5]]
+    feats = linker.tube_features()
+    assert feats.shape == (len(linker.object_list), len(outs), 256)
+    # empty clip / frames with nothing detected
+    assert tubes.concat_seq([[dict(pan_results=np.full((4, 4), 126, np.int32), query_feats={})]]).rows == []
+
+
+def test_shard_frames():
+    for T, G in ((100, 1), (300, 8), (380, 8), (5, 8), (0, 2)):
+        blocks = [tubes.shard_frames(T, G, r) for r in range(G)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == T
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert max(b[1] - b[0] for b in blocks) == (T + G - 1) // G if T else True
+
+
+def _worker(rank, world, port, outs, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = tubes.shard_frames(len(outs), world, rank)
+    entries = []
+    for o in outs[lo:hi]:
+        ids = list(o[0]['query_feats'].keys())
+        entries.append((ids, [o[0]['query_feats'][k][0].numpy() for k in ids]))
+    linker = tubes.gather_and_link(entries, len(outs))
+    q.put((rank, linker.object_list, linker.tube_features()))
+    dist.destroy_process_group()
+
+
+def test_gather_and_link_world2_gloo():
+    outs = _fake_outputs(num_frames=9, seed=3)
+    ref = tubes.concat_seq(outs)
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, outs, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, object_list, feats in got:
+        assert object_list == ref.object_list
+        assert np.array_equal(feats, ref.tube_features())
