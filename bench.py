@@ -182,7 +182,7 @@ def kernel_breakdown(det, img, meta):
         ('instance_masks', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
         ('maxpool3x3s2_nhwc', 'resize', None, None), ('add_rowvec', 'norm', None, None))}
     try:
-        runners = det._runners
+        runners = getattr(det, '_runners', None)
         det._runners = None  # eager path so that every launch is bracketed by events
         det.simple_test(None, None, ref_img=img[None, None], ref_img_metas=[[meta]], rescale=True)
         events.clear()
@@ -211,6 +211,7 @@ def main():
     ap.add_argument('--distinct', type=int, default=8, help='distinct synthetic frames cycled through')
     ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu launch lists)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -232,7 +233,10 @@ def main():
     det = pv.build_detector(configs.mask2former_r50(True))
     det.load_state_dict(syn.mask2former_state_dict(seed=0))
     det.to(dev)
-    engine.enable_cuda_graph(det)
+    if not args.no_graph:
+        engine.enable_cuda_graph(det)
+    else:
+        det._runners = None
     meta = syn.frame_meta(H, W)
     host = [f.pin_memory() for f in make_frames(args.distinct, rank)]
     resident = [f.to(dev) for f in host]
@@ -283,8 +287,13 @@ def main():
     ms_dev, linker, _ = timed(resident, False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(host, True, args.steps, 1)
-    runner = next(iter(det._runners.values()))
-    launches = runner.launches_per_frame * args.frames * args.steps
+    if det._runners:
+        per_frame = next(iter(det._runners.values())).launches_per_frame
+    else:
+        n0 = lib.launch_count[0]
+        run_step(resident[:1] * 1, False) if args.frames == 1 else None
+        per_frame = (lib.launch_count[0] - n0) or 638
+    launches = per_frame * args.frames * args.steps
 
     if rank != 0:
         if world > 1:
@@ -325,7 +334,7 @@ def main():
                             frames_per_gpu_per_step=args.frames, distinct_frames=args.distinct,
                             resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
                             l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',
-                            cuda_graph=True, tubes=len(linker.object_list)),
+                            cuda_graph=not args.no_graph, tubes=len(linker.object_list)),
                 e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames,
                          d2h_bytes_per_step=out_bytes * args.frames, ms_per_step=round(ms_e2e / args.steps, 3)),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu)
