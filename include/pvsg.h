@@ -61,6 +61,32 @@ int pvsg_conv2d_nhwc(const float* x, const float* w, const float* bias, const fl
                      float* y, int B, int H, int W, int Cin, int Cout, int R, int S,
                      int stride, int pad, int act, void* stream);
 
+/* ---- tcgen05 engine (same contractions on the 5th-gen tensor cores, fp32-grade) ----
+ * Operands are "split-bf16": an fp32 tensor x is carried as two bf16 planes of the same
+ * shape, hi = bf16(x), lo = bf16(x - hi) (4 bytes / element, like fp32); one product is
+ * hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM (error ~2^-17 relative per product).
+ * TMA (cp.async.bulk.tensor, 128B swizzle) feeds tcgen05.mma kind::f16 from shared memory. */
+
+/* hi/lo planes of x (+ x2 if non-null); n elements, n % 4 == 0. */
+int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* lo, int64_t n, void* stream);
+
+/* pvsg_linear on split operands.  A [M,K] planes (row stride lda), W [N,K] planes (ldw);
+ * outputs (any subset): C fp32, (C_hi, C_lo) split planes, or mask/row_open = the sign-mask
+ * epilogue of pvsg_mask_logits; all with row stride ldc.  K % 64 == 0, lda/ldw % 8 == 0.
+ * Returns PVSG_ERR_UNSUPPORTED for shapes it does not cover (caller uses pvsg_linear). */
+int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
+                   const void* W_lo, int64_t ldw, const float* bias, const float* R, int64_t ldr,
+                   float* C, void* C_hi, void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc,
+                   int64_t M, int64_t N, int64_t K, int act, void* stream);
+
+/* pvsg_conv2d_nhwc (stride 1) on split operands: x planes [B,H,W,Cin], w planes
+ * [Cout,R,S,Cin]; im2col-free -- a 4-D TMA box over the NHWC planes is shifted per filter
+ * tap and out-of-bounds zero fill provides the padding.  Cin % 64 == 0. */
+int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                   const float* bias, const float* residual, float* y, void* y_hi, void* y_lo,
+                   int B, int H, int W, int Cin, int Cout, int R, int S, int pad, int act,
+                   void* stream);
+
 /* 3x3 stride-2 pad-1 max pooling, NHWC (L0 ResNet stem). */
 int pvsg_maxpool3x3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream);
 

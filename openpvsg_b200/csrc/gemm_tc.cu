@@ -1,0 +1,475 @@
+// tcgen05 GEMM / implicit-GEMM convolution engine with fp32-grade accuracy ("split-bf16").
+//
+//   C[M,N] = act(A[M,K] . W[N,K]^T + bias + R)
+//
+// Every fp32 operand x is carried as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)), the
+// same 4 bytes per element as fp32.  One logical product is three tensor-core MMAs
+// accumulated in the same TMEM tile:  hi.hi + hi.lo + lo.hi  (the dropped lo.lo term and
+// the residual of the split are ~2^-17 relative, i.e. fp32 re-association level).
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B swizzle) of A_hi, A_lo, W_hi, W_lo
+//              k-blocks of 64 into a 3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma
+//              (kind::f16, bf16 x bf16 -> fp32, M = 128, N = BN, K = 16) x 3 x 4 per stage,
+//              tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> bias / residual /
+//              ReLU -> fp32 and/or split-bf16 stores
+// Convolutions use a 4-D tensor map over the NHWC planes: the M tile is an 8 x 16 patch of
+// output pixels and every filter tap is the same TMA box shifted by (r - pad, s - pad); TMA's
+// out-of-bounds zero fill is the convolution's zero padding.  No im2col buffer exists.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;             // bf16 elements = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 192;
+constexpr int PATCH_H = 8, PATCH_W = 16;   // conv M tile = 8 x 16 output pixels
+
+struct TcParams {
+    const float* bias;
+    const float* R;
+    float* C;
+    __nv_bfloat16* C_hi;
+    __nv_bfloat16* C_lo;
+    uint8_t* mask;
+    int32_t* row_open;
+    int64_t M, N, ldc, ldr;
+    int num_kb;
+    int act;
+    // conv mode
+    int conv, OH, OW, cin_kb, S, pad, tiles_h, tiles_w;
+};
+
+// ------------------------------------------------------------------ PTX wrappers -------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);       // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
+    using S = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* acc_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    // tile coordinates
+    int64_t m0 = 0;
+    int tb = 0, oh0 = 0, ow0 = 0;
+    if (p.conv) {
+        int t = blockIdx.y;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        tb = t / p.tiles_h;
+        oh0 = th * PATCH_H;
+        ow0 = tw * PATCH_W;
+    } else {
+        m0 = (int64_t)blockIdx.y * BM;
+    }
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * S::STAGE_BYTES;
+                mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                if (p.conv) {
+                    const int rs = kb / p.cin_kb, cb = kb - rs * p.cin_kb;
+                    const int r = rs / p.S, sx = rs - r * p.S;
+                    const int iy = oh0 + r - p.pad, ix = ow0 + sx - p.pad;
+                    tma_load_4d(&tmA_hi, &full[s], st, cb * BK, ix, iy, tb);
+                    tma_load_4d(&tmA_lo, &full[s], st + S::A_BYTES, cb * BK, ix, iy, tb);
+                } else {
+                    tma_load_2d(&tmA_hi, &full[s], st, kb * BK, (int)m0);
+                    tma_load_2d(&tmA_lo, &full[s], st + S::A_BYTES, kb * BK, (int)m0);
+                }
+                tma_load_2d(&tmB_hi, &full[s], st + 2 * S::A_BYTES, kb * BK, n0);
+                tma_load_2d(&tmB_lo, &full[s], st + 2 * S::A_BYTES + S::B_BYTES, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint32_t off = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle row
+                    const uint64_t dah = umma_desc(a_hi + off), dal = umma_desc(a_lo + off);
+                    const uint64_t dbh = umma_desc(b_hi + off), dbl = umma_desc(b_lo + off);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0);   // small terms first
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty[s]);          // stage reusable once these MMAs retire
+            }
+            umma_commit(acc_full);               // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row_in_tile = q * 32 + lane;
+        int64_t out_row;
+        bool row_ok;
+        if (p.conv) {
+            const int oh = oh0 + row_in_tile / PATCH_W, ow = ow0 + row_in_tile % PATCH_W;
+            row_ok = oh < p.OH && ow < p.OW;
+            out_row = ((int64_t)tb * p.OH + oh) * p.OW + ow;
+        } else {
+            out_row = m0 + row_in_tile;
+            row_ok = out_row < p.M;
+        }
+        int open = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int64_t n = (int64_t)n0 + c0;
+            if (!row_ok || n >= p.N) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            const bool full_chunk = n + 32 <= p.N;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
+            }
+            if (p.R) {
+                const float* rr = p.R + out_row * p.ldr + n;
+                if (full_chunk && (p.ldr & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(rr) + j);
+                        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n + j < p.N) f[j] += __ldg(rr + j);
+                }
+            }
+            if (p.act == PVSG_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.C) {
+                float* cc = p.C + out_row * p.ldc + n;
+                if (full_chunk && (p.ldc & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(cc)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n + j < p.N) cc[j] = f[j];
+                }
+            }
+            if (p.C_hi) {
+                __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
+                __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
+                if (full_chunk && (p.ldc & 7) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = f[8 * j + 2 * e], x1 = f[8 * j + 2 * e + 1];
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        if (n + j < p.N) {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
+                            ch[j] = h;
+                            cl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
+                        }
+                    }
+                }
+            }
+            if (p.mask) {
+                uint8_t* mm = p.mask + out_row * p.ldc + n;
+                for (int j = 0; j < 32; ++j) {
+                    if (n + j < p.N) {
+                        const bool blocked = f[j] < 0.f;
+                        mm[j] = blocked ? 1 : 0;
+                        open += blocked ? 0 : 1;
+                    }
+                }
+            }
+        }
+        if (p.mask && p.row_open && row_ok && open) atomicAdd(p.row_open + out_row, open);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// fp32 -> (hi, lo) bf16 planes, optionally of x + x2
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                    int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        if (x2) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(x2) + i);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        const float a[4] = {v.x, v.y, v.z, v.w};
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat16 hh = __float2bfloat16_rn(a[e]);
+            h[e] = __bfloat16_as_ushort(hh);
+            l[e] = __bfloat16_as_ushort(__float2bfloat16_rn(a[e] - __bfloat162float(hh)));
+        }
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+        reinterpret_cast<uint2*>(lo)[i] = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+    }
+}
+
+// ------------------------------------------------------------------ host side ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D map over a row-major [rows, cols] bf16 matrix with row pitch ld (elements); box = [box_rows, 64]
+bool make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 4-D map over NHWC bf16 [B, H, W, C]; box = [1, 8, 16, 64]
+bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)PATCH_W, (cuuint32_t)PATCH_H, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+              const TcParams& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL) !=
+            cudaSuccess)
+            return PVSG_ERR_LAUNCH;
+        configured = true;
+    }
+    gemm_tc_kernel<BN><<<grid, NTHREADS, Smem<BN>::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    return pvsg_launch_status();
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* lo, int64_t n, void* stream) {
+    PVSG_CHECK_ARG(x && hi && lo && n > 0 && n % 4 == 0 && al16(x) && (!x2 || al16(x2)));
+    const int64_t n4 = n / 4;
+    split_kernel<<<(unsigned)imin64((n4 + 255) / 256, 148 * 16), 256, 0, as_stream(stream)>>>(
+        x, x2, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n4);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo,
+                              int64_t ldw, const float* bias, const float* R, int64_t ldr, float* C, void* C_hi,
+                              void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc, int64_t M, int64_t N,
+                              int64_t K, int act, void* stream) {
+    PVSG_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && (C || C_hi || mask) && M > 0 && N > 0 && K > 0);
+    PVSG_CHECK_ARG((C_hi == nullptr) == (C_lo == nullptr));
+    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N));
+    if (K % BK != 0 || lda % 8 != 0 || ldw % 8 != 0 || !al16(A_hi) || !al16(A_lo) || !al16(W_hi) || !al16(W_lo))
+        return PVSG_ERR_UNSUPPORTED;
+    if (M > 0x7fffffffLL || (M + BM - 1) / BM > 65535) return PVSG_ERR_UNSUPPORTED;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const int BN = 128;
+    if (!make_map_2d(&ta_hi, A_hi, M, K, lda, BM) || !make_map_2d(&ta_lo, A_lo, M, K, lda, BM) ||
+        !make_map_2d(&tb_hi, W_hi, N, K, ldw, BN) || !make_map_2d(&tb_lo, W_lo, N, K, ldw, BN))
+        return PVSG_ERR_LAUNCH;
+    TcParams p{};
+    p.bias = bias; p.R = R; p.C = C;
+    p.C_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
+    p.mask = mask; p.row_open = row_open;
+    p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+    return launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, as_stream(stream));
+}
+
+extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                              const float* bias, const float* residual, float* y, void* y_hi, void* y_lo, int B,
+                              int H, int W, int Cin, int Cout, int R, int S, int pad, int act, void* stream) {
+    PVSG_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && (y || y_hi) && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+    PVSG_CHECK_ARG((y_hi == nullptr) == (y_lo == nullptr) && R > 0 && S > 0 && pad >= 0);
+    if (Cin % BK != 0 || !al16(x_hi) || !al16(x_lo) || !al16(w_hi) || !al16(w_lo)) return PVSG_ERR_UNSUPPORTED;
+    const int OH = H + 2 * pad - R + 1, OW = W + 2 * pad - S + 1;   // stride 1
+    PVSG_CHECK_ARG(OH > 0 && OW > 0);
+    const int64_t K = (int64_t)R * S * Cin;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const int BN = 128;
+    if (!make_map_4d(&ta_hi, x_hi, B, H, W, Cin) || !make_map_4d(&ta_lo, x_lo, B, H, W, Cin) ||
+        !make_map_2d(&tb_hi, w_hi, Cout, K, K, BN) || !make_map_2d(&tb_lo, w_lo, Cout, K, K, BN))
+        return PVSG_ERR_LAUNCH;
+    TcParams p{};
+    p.bias = bias; p.R = residual; p.C = y;
+    p.C_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
+    p.M = (int64_t)B * OH * OW; p.N = Cout; p.ldc = Cout; p.ldr = Cout; p.act = act;
+    p.num_kb = (int)(K / BK); p.conv = 1; p.OH = OH; p.OW = OW; p.cin_kb = Cin / BK; p.S = S; p.pad = pad;
+    p.tiles_h = (OH + PATCH_H - 1) / PATCH_H; p.tiles_w = (OW + PATCH_W - 1) / PATCH_W;
+    const int64_t tiles = (int64_t)B * p.tiles_h * p.tiles_w;
+    if (tiles > 65535) return PVSG_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((Cout + BN - 1) / BN), (unsigned)tiles);
+    return launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, as_stream(stream));
+}

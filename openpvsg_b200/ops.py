@@ -8,6 +8,7 @@ All calls are stream-ordered and allocation-free on the native side, so a whole 
 can be captured with ``torch.cuda.graph``.
 """
 import ctypes
+import os
 
 import torch
 
@@ -44,6 +45,50 @@ def _rows(t, name):
     return t, t.shape[0], t.shape[1], t.stride(0)
 
 
+# ----------------------------------------------------------------------------------------
+# engine selection: 'tc' = tcgen05 split-bf16 GEMM/conv (csrc/gemm_tc.cu) where the shape is
+# covered, SIMT fp32 (csrc/gemm.cu) otherwise; 'simt' = SIMT everywhere.  Both are this
+# library's CUDA kernels -- this is not a fallback to another backend.
+# ----------------------------------------------------------------------------------------
+ENGINE = [os.environ.get('PVSG_ENGINE', 'tc')]
+_wplanes = {}
+
+
+def set_engine(name):
+    if name not in ('tc', 'simt'):
+        raise ValueError(name)
+    ENGINE[0] = name
+
+
+def split_bf16(x, add=None):
+    """fp32 tensor -> (hi, lo) bf16 planes of the same shape (of x + add when given)."""
+    lib = _l.load()
+    _f32(x, 'x')
+    if not x.is_contiguous() or (add is not None and not (add.is_contiguous() and add.shape == x.shape)):
+        raise _l.PvsgError('split_bf16: contiguous tensors of equal shape required')
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _l.check(lib.pvsg_split_bf16(_ptr(x), _ptr(_f32(add)), _ptr(hi), _ptr(lo), x.numel(), _stream()),
+             'pvsg_split_bf16')
+    return hi, lo
+
+
+def _weight_planes(w):
+    """Cached split planes of a (possibly sliced) weight matrix, keyed by storage identity."""
+    key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), w._version)
+    hit = _wplanes.get(key)
+    if hit is None:
+        if len(_wplanes) > 4096:
+            _wplanes.clear()
+        hit = split_bf16(w.contiguous())
+        _wplanes[key] = hit
+    return hit
+
+
+def _tc_ok(K, lda):
+    return ENGINE[0] == 'tc' and K % 64 == 0 and lda % 8 == 0
+
+
 def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, out=None):
     """act((x + add_input) @ weight.T + bias + residual); x [..., K], weight [N, K] (row slices ok)."""
     lib = _l.load()
@@ -52,6 +97,8 @@ def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, ou
     w2, N, Kw, ldw = _rows(weight, 'weight')
     if Kw != K:
         raise _l.PvsgError(f'linear: K mismatch {K} vs {Kw}')
+    if _tc_ok(K, K) and x2.is_contiguous() and (add_input is None or add_input.is_contiguous()):
+        return _linear_tc(lib, x, x2, w2, bias, add_input, residual, act, out, lead, M, N, K)
     a2 = None
     if add_input is not None:
         a2, M2, K2, lda2 = _rows(add_input, 'add_input')
@@ -75,9 +122,46 @@ def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, ou
     return out.reshape(*lead, N) if created else out
 
 
+def _linear_tc(lib, x, x2, w2, bias, add_input, residual, act, out, lead, M, N, K):
+    a_hi, a_lo = split_bf16(x2, None if add_input is None else add_input.reshape(M, K))
+    w_hi, w_lo = _weight_planes(w2)
+    created = out is None
+    if created:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    o2, Mo, No, ldc = _rows(out, 'out')
+    if (Mo, No) != (M, N):
+        raise _l.PvsgError('linear: bad out shape')
+    r2, ldr = None, 0
+    if residual is not None:
+        r2, Mr, Nr, ldr = _rows(residual, 'residual')
+        if (Mr, Nr) != (M, N):
+            raise _l.PvsgError('linear: bad residual shape')
+    if bias is not None and (_f32(bias, 'bias').numel() != N or not bias.is_contiguous()):
+        raise _l.PvsgError('linear: bad bias')
+    _l.check(lib.pvsg_linear_tc(_ptr(a_hi), _ptr(a_lo), K, _ptr(w_hi), _ptr(w_lo), K, _ptr(bias), _ptr(r2), ldr,
+                                _ptr(o2), None, None, None, None, ldc, M, N, K, act, _stream()), 'pvsg_linear_tc')
+    return out.reshape(*lead, N) if created else out
+
+
 def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NONE, out=None):
     """x [B,H,W,Cin] token-major, weight [Cout,R,S,Cin] -> [B,OH,OW,Cout]."""
     lib = _l.load()
+    if (ENGINE[0] == 'tc' and stride == 1 and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
+            and weight.is_contiguous() and out is None):
+        B, H, W, Cin = x.shape
+        Cout, R, S, _ = weight.shape
+        if R == 1 and S == 1 and pad == 0:
+            return linear(x, weight.view(Cout, Cin), bias, residual=residual, act=act)
+        x_hi, x_lo = split_bf16(x)
+        w_hi, w_lo = _weight_planes(weight)
+        OH, OW = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+        y = torch.empty(B, OH, OW, Cout, device=x.device, dtype=torch.float32)
+        if residual is not None and (tuple(residual.shape) != tuple(y.shape) or not residual.is_contiguous()):
+            raise _l.PvsgError('conv2d_nhwc: bad residual')
+        _l.check(lib.pvsg_conv2d_tc(_ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(_f32(bias)),
+                                    _ptr(_f32(residual)), _ptr(y), None, None, B, H, W, Cin, Cout, R, S, pad, act,
+                                    _stream()), 'pvsg_conv2d_tc')
+        return y
     _f32(x, 'x'), _f32(weight, 'weight')
     if not (x.is_contiguous() and weight.is_contiguous() and x.dim() == 4 and weight.dim() == 4):
         raise _l.PvsgError('conv2d_nhwc: contiguous 4-D tensors required')

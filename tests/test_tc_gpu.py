@@ -1,0 +1,79 @@
+"""GPU: the tcgen05 split-bf16 GEMM / conv engine vs float64 references.
+
+The engine must be fp32-grade: max error relative to the row/column norms stays at the level of
+fp32 re-association (a single-pass bf16 GEMM would sit near 4e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from openpvsg_b200 import ops as _ops
+    _ops.set_engine('tc')
+    yield _ops
+    _ops.set_engine('tc')
+
+
+def randn(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_split_planes(ops):
+    x = randn(1, 1000, 64) * 3
+    hi, lo = ops.split_bf16(x.cuda())
+    rec = hi.float().cpu() + lo.float().cpu()
+    assert ((rec - x).abs() <= x.abs() * 2.0 ** -16 + 1e-30).all()
+    hi2, lo2 = ops.split_bf16(x.cuda(), x.cuda())
+    assert torch.equal(hi2.cpu(), (2 * x).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (100, 256, 256), (19320, 288, 256), (333, 1024, 256),
+                                   (100, 127, 256), (58880, 100, 256), (100, 256, 2048), (257, 57, 128),
+                                   (920, 2048, 512)])
+def test_linear_tc(ops, M, N, K):
+    x, w, b = randn(1, M, K), randn(2, N, K) / K ** 0.5, randn(3, N)
+    res = randn(4, M, N)
+    y = ops.linear(x.cuda(), w.cuda(), b.cuda(), residual=res.cuda(), act=ops.ACT_RELU)
+    ref = F.relu(F.linear(x.double(), w.double(), b.double()) + res.double())
+    err = (y.cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+    # agrees with the SIMT fp32 engine to re-association level
+    ops.set_engine('simt')
+    y2 = ops.linear(x.cuda(), w.cuda(), b.cuda(), residual=res.cuda(), act=ops.ACT_RELU)
+    ops.set_engine('tc')
+    assert (y - y2).abs().max().item() < 1e-4
+
+
+def test_linear_tc_add_input_and_slices(ops):
+    M, K = 100, 256
+    x, pos = randn(1, M, K), randn(2, M, K)
+    w, b = randn(4, 768, K) / 16, randn(5, 768)
+    y = ops.linear(x.cuda(), w.cuda()[256:512], b.cuda()[256:512], add_input=pos.cuda())
+    ref = F.linear((x + pos).double(), w[256:512].double(), b[256:512].double())
+    assert (y.cpu().double() - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
+    buf = torch.zeros(M, 768, device='cuda')
+    ops.linear(x.cuda(), w.cuda()[:512], b.cuda()[:512], out=buf[:, :512])
+    ref1 = F.linear(x.double(), w[:512].double(), b[:512].double())
+    assert (buf[:, :512].cpu().double() - ref1).abs().max().item() < 3e-5 * ref1.abs().max().item()
+
+
+@pytest.mark.parametrize('cin,cout,k,pad,hw,B', [(64, 64, 3, 1, (46, 80), 2), (256, 256, 3, 1, (23, 40), 1),
+                                                 (128, 128, 3, 1, (92, 160), 1), (64, 256, 1, 0, (45, 77), 2),
+                                                 (512, 512, 3, 1, (23, 40), 1), (64, 64, 3, 1, (184, 320), 1)])
+def test_conv_tc(ops, cin, cout, k, pad, hw, B):
+    x = randn(1, B, cin, *hw)
+    w = randn(2, cout, cin, k, k) / (cin * k * k) ** 0.5
+    b = randn(3, cout)
+    ref = F.conv2d(x.double(), w.double(), b.double(), 1, pad)
+    res = randn(4, *ref.shape)
+    y = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().cuda(), w.permute(0, 2, 3, 1).contiguous().cuda(),
+                        b.cuda(), residual=res.permute(0, 2, 3, 1).contiguous().cuda(), stride=1, pad=pad,
+                        act=ops.ACT_RELU)
+    ref = F.relu(ref + res.double())
+    err = (y.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
