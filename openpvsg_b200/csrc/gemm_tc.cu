@@ -7,14 +7,17 @@
 // accumulated in the same TMEM tile:  hi.hi + hi.lo + lo.hi  (the dropped lo.lo term and
 // the residual of the split are ~2^-17 relative, i.e. fp32 re-association level).
 //
-// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+// Persistent kernel, one CTA per SM, 192 threads, tiles of 128 x 128 handed out round-robin:
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B swizzle) of A_hi, A_lo, W_hi, W_lo
-//              k-blocks of 64 into a 3-stage shared-memory ring, mbarrier complete_tx
+//              k-blocks of 64 into a 3-stage shared-memory ring (mbarrier complete_tx); runs
+//              ahead across tile boundaries
 //   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma
-//              (kind::f16, bf16 x bf16 -> fp32, M = 128, N = BN, K = 16) x 3 x 4 per stage,
-//              tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> bias / residual /
-//              ReLU -> fp32 and/or split-bf16 stores
+//              (kind::f16, bf16 x bf16 -> fp32, M = 128, N = 128, K = 16) x 3 x 4 per stage into
+//              one of TWO TMEM accumulators; tcgen05.commit releases the stage / publishes
+//              the accumulator
+//   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory
+//              transpose -> coalesced bias / residual / ReLU / fp32, split-bf16 or sign-mask
+//              stores; overlaps the next tile's main loop through the second accumulator
 // Convolutions use a 4-D tensor map over the NHWC planes: the M tile is an 8 x 16 patch of
 // output pixels and every filter tap is the same TMA box shifted by (r - pad, s - pad); TMA's
 // out-of-bounds zero fill is the convolution's zero padding.  No im2col buffer exists.
@@ -26,10 +29,18 @@
 namespace {
 
 constexpr int BM = 128;
+constexpr int BN = 128;
 constexpr int BK = 64;             // bf16 elements = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
 constexpr int PATCH_H = 8, PATCH_W = 16;   // conv M tile = 8 x 16 output pixels
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_BYTES = BN * BK * 2;        // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int EPI_LD = 33;                  // padded row of the per-warp transpose buffer
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int TMEM_COLS = 2 * BN;
 
 struct TcParams {
     const float* bias;
@@ -42,6 +53,7 @@ struct TcParams {
     int64_t M, N, ldc, ldr;
     int num_kb;
     int act;
+    int tiles_m, tiles_n;
     // conv mode
     int conv, OH, OW, cin_kb, S, pad, tiles_h, tiles_w;
 };
@@ -54,6 +66,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -116,53 +131,64 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN>
-struct Smem {
-    static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+struct Tile {
+    int64_t m0;       // linear mode: first row
+    int n0;
+    int tb, oh0, ow0; // conv mode
 };
 
-template <int BN>
+__device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
+    Tile tl;
+    const int nt = t % p.tiles_n;
+    int mt = t / p.tiles_n;
+    tl.n0 = nt * BN;
+    tl.m0 = (int64_t)mt * BM;
+    tl.tb = tl.oh0 = tl.ow0 = 0;
+    if (p.conv) {
+        const int tw = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        tl.tb = mt / p.tiles_h;
+        tl.oh0 = th * PATCH_H;
+        tl.ow0 = tw * PATCH_W;
+    }
+    return tl;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
-    using S = Smem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + STAGES;
-    uint64_t* acc_full = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+    uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    // tile coordinates
-    int64_t m0 = 0;
-    int tb = 0, oh0 = 0, ow0 = 0;
-    if (p.conv) {
-        int t = blockIdx.y;
-        const int tw = t % p.tiles_w;
-        t /= p.tiles_w;
-        const int th = t % p.tiles_h;
-        tb = t / p.tiles_h;
-        oh0 = th * PATCH_H;
-        ow0 = tw * PATCH_W;
-    } else {
-        m0 = (int64_t)blockIdx.y * BM;
-    }
+    const int num_tiles = p.tiles_m * p.tiles_n;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: BN fp32 columns x 128 lanes
+    if (warp == 1) {   // TMEM: two 128-column fp32 accumulators x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BN) : "memory");
+                     "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -171,162 +197,211 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------------
         if (lane == 0) {
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * S::STAGE_BYTES;
-                mbar_expect_tx(&full[s], S::STAGE_BYTES);
-                if (p.conv) {
-                    const int rs = kb / p.cin_kb, cb = kb - rs * p.cin_kb;
-                    const int r = rs / p.S, sx = rs - r * p.S;
-                    const int iy = oh0 + r - p.pad, ix = ow0 + sx - p.pad;
-                    tma_load_4d(&tmA_hi, &full[s], st, cb * BK, ix, iy, tb);
-                    tma_load_4d(&tmA_lo, &full[s], st + S::A_BYTES, cb * BK, ix, iy, tb);
-                } else {
-                    tma_load_2d(&tmA_hi, &full[s], st, kb * BK, (int)m0);
-                    tma_load_2d(&tmA_lo, &full[s], st + S::A_BYTES, kb * BK, (int)m0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const Tile tl = decode_tile(p, t);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    if (p.conv) {
+                        const int rs = kb / p.cin_kb, cb = kb - rs * p.cin_kb;
+                        const int r = rs / p.S, sx = rs - r * p.S;
+                        const int iy = tl.oh0 + r - p.pad, ix = tl.ow0 + sx - p.pad;
+                        tma_load_4d(&tmA_hi, &full[s], st, cb * BK, ix, iy, tl.tb);
+                        tma_load_4d(&tmA_lo, &full[s], st + A_BYTES, cb * BK, ix, iy, tl.tb);
+                    } else {
+                        tma_load_2d(&tmA_hi, &full[s], st, kb * BK, (int)tl.m0);
+                        tma_load_2d(&tmA_lo, &full[s], st + A_BYTES, kb * BK, (int)tl.m0);
+                    }
+                    tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
+                    tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
                 }
-                tma_load_2d(&tmB_hi, &full[s], st + 2 * S::A_BYTES, kb * BK, n0);
-                tma_load_2d(&tmB_lo, &full[s], st + 2 * S::A_BYTES + S::B_BYTES, kb * BK, n0);
             }
         }
     } else if (warp == 1) {
+        // ------------------------------ MMA issuer --------------------------------------
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + S::A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
-                const uint32_t b_lo = b_hi + S::B_BYTES;
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                    const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint32_t off = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle row
-                    const uint64_t dah = umma_desc(a_hi + off), dal = umma_desc(a_lo + off);
-                    const uint64_t dbh = umma_desc(b_hi + off), dbl = umma_desc(b_lo + off);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0);   // small terms first
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
-                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t off = k * 32;  // 16 bf16 = 32 bytes along K inside the swizzle row
+                        const uint64_t dah = umma_desc(a_hi + off), dal = umma_desc(a_lo + off);
+                        const uint64_t dbh = umma_desc(b_hi + off), dbl = umma_desc(b_lo + off);
+                        umma_bf16(tmem_d, dal, dbh, idesc, (kb | k) != 0);   // small terms first
+                        umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                        umma_bf16(tmem_d, dah, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);          // stage reusable once these MMAs retire
                 }
-                umma_commit(&empty[s]);          // stage reusable once these MMAs retire
+                umma_commit(&acc_full[buf]);         // accumulator complete
             }
-            umma_commit(acc_full);               // accumulator complete
         }
     } else {
         // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        // thread = one accumulator row; 32 columns per tcgen05.ld; 128-bit global accesses
         const int q = warp & 3;
-        mbar_wait(acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row_in_tile = q * 32 + lane;
-        int64_t out_row;
-        bool row_ok;
-        if (p.conv) {
-            const int oh = oh0 + row_in_tile / PATCH_W, ow = ow0 + row_in_tile % PATCH_W;
-            row_ok = oh < p.OH && ow < p.OW;
-            out_row = ((int64_t)tb * p.OH + oh) * p.OW + ow;
-        } else {
-            out_row = m0 + row_in_tile;
-            row_ok = out_row < p.M;
-        }
-        int open = 0;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+            const Tile tl = decode_tile(p, t);
+            const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
+            mbar_wait(&acc_full[buf], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row_in_tile = q * 32 + lane;
+            int64_t out_row;
+            bool row_ok;
+            if (p.conv) {
+                const int oh = tl.oh0 + row_in_tile / PATCH_W, ow = tl.ow0 + row_in_tile % PATCH_W;
+                row_ok = oh < p.OH && ow < p.OW;
+                out_row = ((int64_t)tl.tb * p.OH + oh) * p.OW + ow;
+            } else {
+                out_row = tl.m0 + row_in_tile;
+                row_ok = out_row < p.M;
+            }
+            int open = 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int64_t n = (int64_t)n0 + c0;
-            if (!row_ok || n >= p.N) continue;
-            float f[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int64_t n = (int64_t)tl.n0 + c0;
+                if (n >= p.N) break;                                  // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (!row_ok) continue;
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            const bool full_chunk = n + 32 <= p.N;
-            if (p.bias) {
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                const bool full_chunk = n + 32 <= p.N;
+                if (p.bias) {
+                    if (full_chunk && ((n & 3) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
-            }
-            if (p.R) {
-                const float* rr = p.R + out_row * p.ldr + n;
-                if (full_chunk && (p.ldr & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(rr) + j);
-                        f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n + j < p.N) f[j] += __ldg(rr + j);
-                }
-            }
-            if (p.act == PVSG_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (p.C) {
-                float* cc = p.C + out_row * p.ldc + n;
-                if (full_chunk && (p.ldc & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        reinterpret_cast<float4*>(cc)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n + j < p.N) cc[j] = f[j];
-                }
-            }
-            if (p.C_hi) {
-                __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
-                __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
-                if (full_chunk && (p.ldc & 7) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t hw[4], lw[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float x0 = f[8 * j + 2 * e], x1 = f[8 * j + 2 * e + 1];
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
                         }
-                        reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
                     }
-                } else {
-                    for (int j = 0; j < 32; ++j) {
-                        if (n + j < p.N) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-                            ch[j] = h;
-                            cl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
+                }
+                if (p.R) {
+                    const float* rr = p.R + out_row * p.ldr + n;
+                    if (full_chunk && (p.ldr & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t4 = __ldg(reinterpret_cast<const float4*>(rr) + j);
+                            f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < p.N) f[j] += __ldg(rr + j);
+                    }
+                }
+                if (p.act == PVSG_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.C) {
+                    float* cc = p.C + out_row * p.ldc + n;
+                    if (full_chunk && (p.ldc & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4*>(cc)[j] =
+                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < p.N) cc[j] = f[j];
+                    }
+                }
+                if (p.C_hi) {
+                    __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
+                    __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
+                    if (full_chunk && (p.ldc & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float x0 = f[8 * j + 2 * e], x1 = f[8 * j + 2 * e + 1];
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            }
+                            reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j) {
+                            if (n + j < p.N) {
+                                const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
+                                ch[j] = h;
+                                cl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
+                            }
+                        }
+                    }
+                }
+                if (p.mask) {
+                    uint8_t* mm = p.mask + out_row * p.ldc + n;
+                    if (full_chunk && (p.ldc & 15) == 0) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            w[j] = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const bool blocked = f[4 * j + e] < 0.f;
+                                w[j] |= (blocked ? 1u : 0u) << (8 * e);
+                                open += blocked ? 0 : 1;
+                            }
+                        }
+                        reinterpret_cast<uint4*>(mm)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        reinterpret_cast<uint4*>(mm)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    } else {
+                        for (int j = 0; j < 32; ++j) {
+                            if (n + j < p.N) {
+                                const bool blocked = f[j] < 0.f;
+                                mm[j] = blocked ? 1 : 0;
+                                open += blocked ? 0 : 1;
+                            }
                         }
                     }
                 }
             }
-            if (p.mask) {
-                uint8_t* mm = p.mask + out_row * p.ldc + n;
-                for (int j = 0; j < 32; ++j) {
-                    if (n + j < p.N) {
-                        const bool blocked = f[j] < 0.f;
-                        mm[j] = blocked ? 1 : 0;
-                        open += blocked ? 0 : 1;
-                    }
-                }
-            }
+            if (p.mask && p.row_open && row_ok && open) atomicAdd(p.row_open + out_row, open);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (p.mask && p.row_open && row_ok && open) atomicAdd(p.row_open + out_row, open);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
     }
 }
 
@@ -372,6 +447,17 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 // 2-D map over a row-major [rows, cols] bf16 matrix with row pitch ld (elements); box = [box_rows, 64]
 bool make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
@@ -398,17 +484,18 @@ bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-              const TcParams& p, dim3 grid, cudaStream_t st) {
+              const TcParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL) !=
+        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) !=
             cudaSuccess)
             return PVSG_ERR_LAUNCH;
         configured = true;
     }
-    gemm_tc_kernel<BN><<<grid, NTHREADS, Smem<BN>::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    const unsigned grid = (unsigned)imin64(tiles, sm_count());
+    gemm_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
     return pvsg_launch_status();
 }
 
@@ -433,9 +520,9 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N));
     if (K % BK != 0 || lda % 8 != 0 || ldw % 8 != 0 || !al16(A_hi) || !al16(A_lo) || !al16(W_hi) || !al16(W_lo))
         return PVSG_ERR_UNSUPPORTED;
-    if (M > 0x7fffffffLL || (M + BM - 1) / BM > 65535) return PVSG_ERR_UNSUPPORTED;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || ((M + BM - 1) / BM) * ((N + BN - 1) / BN) > 0x7fffffffLL)
+        return PVSG_ERR_UNSUPPORTED;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    const int BN = 128;
     if (!make_map_2d(&ta_hi, A_hi, M, K, lda, BM) || !make_map_2d(&ta_lo, A_lo, M, K, lda, BM) ||
         !make_map_2d(&tb_hi, W_hi, N, K, ldw, BN) || !make_map_2d(&tb_lo, W_lo, N, K, ldw, BN))
         return PVSG_ERR_LAUNCH;
@@ -444,8 +531,8 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
-    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-    return launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, as_stream(stream));
+    p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
+    return launch_tc(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
 }
 
 extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
@@ -458,7 +545,6 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
     PVSG_CHECK_ARG(OH > 0 && OW > 0);
     const int64_t K = (int64_t)R * S * Cin;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    const int BN = 128;
     if (!make_map_4d(&ta_hi, x_hi, B, H, W, Cin) || !make_map_4d(&ta_lo, x_lo, B, H, W, Cin) ||
         !make_map_2d(&tb_hi, w_hi, Cout, K, K, BN) || !make_map_2d(&tb_lo, w_lo, Cout, K, K, BN))
         return PVSG_ERR_LAUNCH;
@@ -468,8 +554,8 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
     p.M = (int64_t)B * OH * OW; p.N = Cout; p.ldc = Cout; p.ldr = Cout; p.act = act;
     p.num_kb = (int)(K / BK); p.conv = 1; p.OH = OH; p.OW = OW; p.cin_kb = Cin / BK; p.S = S; p.pad = pad;
     p.tiles_h = (OH + PATCH_H - 1) / PATCH_H; p.tiles_w = (OW + PATCH_W - 1) / PATCH_W;
-    const int64_t tiles = (int64_t)B * p.tiles_h * p.tiles_w;
-    if (tiles > 65535) return PVSG_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)((Cout + BN - 1) / BN), (unsigned)tiles);
-    return launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, as_stream(stream));
+    const int64_t tiles_m = (int64_t)B * p.tiles_h * p.tiles_w;
+    if (tiles_m * ((Cout + BN - 1) / BN) > 0x7fffffffLL) return PVSG_ERR_UNSUPPORTED;
+    p.tiles_m = (int)tiles_m; p.tiles_n = (Cout + BN - 1) / BN;
+    return launch_tc(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
 }

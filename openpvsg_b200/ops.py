@@ -74,14 +74,22 @@ def split_bf16(x, add=None):
 
 
 def _weight_planes(w):
-    """Cached split planes of a (possibly sliced) weight matrix, keyed by storage identity."""
-    key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), w._version)
-    hit = _wplanes.get(key)
+    """Cached split planes of a (possibly sliced) weight matrix.  The cache lives ON the base
+    tensor object (the nn.Parameter / prepared weight), so it dies with it and can never be hit
+    by a different tensor that happens to reuse the same address; in-place updates
+    (load_state_dict) bump the version counter and invalidate it."""
+    base = w._base if w._base is not None else w
+    cache = base.__dict__.get('_pvsg_planes')
+    if cache is None:
+        cache = {}
+        base._pvsg_planes = cache
+    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), base._version)
+    hit = cache.get(key)
     if hit is None:
-        if len(_wplanes) > 4096:
-            _wplanes.clear()
+        for k in [k for k in cache if k[3] != base._version]:
+            del cache[k]
         hit = split_bf16(w.contiguous())
-        _wplanes[key] = hit
+        cache[key] = hit
     return hit
 
 

@@ -24,10 +24,13 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 
 
 def short(name):
-    m = re.search(r'([A-Za-z_][A-Za-z0-9_]*)\s*(<[^(]*)?\(', name)
-    base = m.group(1) if m else name
-    t = re.search(r'<([^(]*)>\s*\(', name)
-    return base + ('<' + t.group(1) + '>' if t and len(t.group(1)) < 40 else '')
+    s = re.sub(r'^void\s+', '', name.strip())
+    s = s.replace('<unnamed>::', '').replace('(anonymous namespace)::', '')
+    m = re.match(r'([A-Za-z_][A-Za-z0-9_:]*)', s)
+    base = m.group(1) if m else s[:40]
+    t = re.match(r'[A-Za-z_][A-Za-z0-9_:]*<(.*?)>\(', s)
+    targs = re.sub(r'\((int|bool)\)', '', t.group(1)) if t else ''
+    return base + (f'<{targs}>' if targs and len(targs) < 40 else '')
 
 
 def launches(path, out, note=''):
