@@ -1,17 +1,32 @@
 """CUDA-graph frame runner for the VPS detector.
 
 A frame's device work (backbone -> pixel decoder -> 9 decoder layers -> fused panoptic /
-instance post-processing, ~450 kernel launches) has static shapes, no host round trip
+instance post-processing, ~500 kernel launches) has static shapes, no host round trip
 and allocates only through torch's caching allocator, so it is captured once per input
 shape into one CUDA graph and replayed per frame: the launch-bound decoder stops paying
-Python + launch latency.  Host-side work per frame is one H2D copy into the static input
-buffer, one graph launch, and the D2H copies of the results.
+Python + launch latency.
+
+Per frame the host does: one H2D copy into the static input buffer, one graph launch,
+asynchronous D2H copies of the fixed-size outputs into a ring of pinned host buffers, and
+an event record.  ``submit`` returns immediately; ``collect`` waits for that frame's event
+and builds the reference's result dict, so the host-side work of frame i overlaps the
+device work of frame i+1 (``Mask2FormerVideoCustom.simple_test`` = submit + collect).
 """
 import numpy as np
 import torch
 
 from . import lib as _l
 from .mask2former import bbox2result
+
+RING = 3
+TOPK_INS = 10   # models/mask2former_vps/mask2former.py:192-195 keeps the 10 best instances
+
+
+class _Pending:
+    __slots__ = ('slot', 'event')
+
+    def __init__(self, slot, event):
+        self.slot, self.event = slot, event
 
 
 class FrameRunner:
@@ -22,12 +37,17 @@ class FrameRunner:
         self.meta = dict(meta)
         self.rescale = rescale
         dev = next(detector.parameters()).device
+        self.dev = dev
         hp, wp = meta['batch_input_shape']
         self.static_in = torch.zeros(1, 3, hp, wp, device=dev, dtype=torch.float32)
         self.graph = None
         self.out = None
         self.launches_per_frame = 0
         self._capture()
+        self.host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.out.items()}
+                     for _ in range(RING)]
+        self.events = [torch.cuda.Event() for _ in range(RING)]
+        self.next_slot = 0
 
     @torch.no_grad()
     def _device_forward(self):
@@ -38,11 +58,21 @@ class FrameRunner:
         in_hw = tuple(meta['batch_input_shape'])
         img_hw = tuple(meta['img_shape'][:2])
         out_hw = tuple(meta['ori_shape'][:2]) if self.rescale else img_hw
-        out = dict(cls=cls[0], mask_lr=mask_lr[0, 0], query=query[:, 0])
+        out = dict(query=query[:, 0].contiguous())
         if fh.test_cfg.get('panoptic_on', True):
             out['pan'], out['seg_info'] = fh._panoptic(cls[0], mask_lr[0, 0], in_hw, img_hw, out_hw)
         if fh.test_cfg.get('instance_on', False):
-            out['ins'] = fh._instance_device(cls[0], mask_lr[0, 0], in_hw, img_hw, out_hw, True)
+            d = fh._instance_device(cls[0], mask_lr[0, 0], in_hw, img_hw, out_hw, True)
+            # static-shape version of the detector's top-10 selection (mask2former.py:183-201)
+            is_thing = d['labels'] < det.num_things_classes
+            det_scores = d['scores'] * d['stats'][:, 0] / (d['stats'][:, 1] + 1e-6)
+            det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
+            ids = torch.cumsum(is_thing.to(torch.float32), 0)   # 1-based rank among thing candidates
+            inds = torch.argsort(det_scores, descending=True)[:TOPK_INS]
+            out['ins_boxes'] = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
+            out['ins_labels'] = d['labels'][inds].to(torch.int32)
+            out['ins_count'] = is_thing.sum().to(torch.int32).reshape(1)
+            out['ins_masks'] = d['masks'][inds]
         return out
 
     def _capture(self):
@@ -60,44 +90,47 @@ class FrameRunner:
         self.launches_per_frame = _l.launch_count[0] - n0
 
     @torch.no_grad()
-    def run(self, img):
-        """img [1,3,H,W] or [3,H,W], device or (pinned) host tensor.  Returns the static output
-        tensors (valid until the next run)."""
+    def submit(self, img):
+        """img [1,3,H,W] / [3,H,W], device or pinned host tensor.  Enqueues H2D, the graph and
+        the D2H of its outputs; returns a handle for ``collect``."""
+        slot = self.next_slot
+        self.next_slot = (slot + 1) % RING
         self.static_in.copy_(img.reshape(self.static_in.shape), non_blocking=True)
         self.graph.replay()
-        return self.out
+        hb = self.host[slot]
+        for k, v in self.out.items():
+            hb[k].copy_(v, non_blocking=True)
+        self.events[slot].record()
+        return _Pending(slot, self.events[slot])
 
     @torch.no_grad()
-    def results(self, out=None):
-        """Static outputs -> the reference's per-frame result dict
-        (models/mask2former_vps/mask2former.py:172-211)."""
-        out = out or self.out
+    def collect(self, pending, copy=True):
+        """Wait for a submitted frame and build the reference's per-frame result dict
+        (models/mask2former_vps/mask2former.py:172-211).  ``copy=False`` returns views of the
+        pinned ring buffers (valid until RING-1 further submits)."""
+        pending.event.synchronize()
+        hb = self.host[pending.slot]
         det = self.det
         fh = det.panoptic_fusion_head
         res = {}
-        if 'pan' in out:
-            seg_info = out['seg_info'].cpu().numpy()          # sync point
-            res['pan_results'] = out['pan'].cpu().numpy()
-            res['query_feats'] = fh._query_dict(seg_info, out['query'].clone())
-        if 'ins' in out:
-            d = out['ins']
-            is_thing = d['labels'] < det.num_things_classes
-            stats = d['stats']
-            det_scores = d['scores'] * stats[:, 0] / (stats[:, 1] + 1e-6)
-            det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
-            # ids are 1-based ranks among the thing candidates, as torch.arange(len(bboxes)) + 1 (:188)
-            ids = torch.cumsum(is_thing.to(torch.float32), 0)
-            n_thing = int(is_thing.sum().item())
-            inds = torch.argsort(det_scores, descending=True)[:min(10, n_thing)]
-            bboxes = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
-            labels = d['labels'][inds]
-            masks_np = d['masks'][inds].cpu().numpy().astype(bool)
-            bbox_results = bbox2result(bboxes, labels, det.num_things_classes)
+        own = (lambda a: a.copy()) if copy else (lambda a: a)
+        if 'pan' in hb:
+            res['pan_results'] = own(hb['pan'].numpy())
+            query = hb['query'].clone() if copy else hb['query']
+            res['query_feats'] = fh._query_dict(hb['seg_info'].numpy(), query)
+        if 'ins_boxes' in hb:
+            n = min(TOPK_INS, int(hb['ins_count'][0]))
+            labels = hb['ins_labels'][:n]
+            bbox_results = bbox2result(hb['ins_boxes'][:n], labels, det.num_things_classes)
+            masks_np = hb['ins_masks'][:n].numpy()
             mask_results = [[] for _ in range(det.num_things_classes)]
             for j, label in enumerate(labels.tolist()):
-                mask_results[label].append(masks_np[j])
+                mask_results[label].append(own(masks_np[j]).view(np.bool_))
             res['ins_results'] = bbox_results, mask_results
         return res
+
+    def run(self, img):
+        return self.collect(self.submit(img))
 
 
 def enable_cuda_graph(detector):

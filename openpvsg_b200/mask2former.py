@@ -975,8 +975,7 @@ class Mask2FormerVideoCustom(_DetectorBase):
             # CUDA-graph replay of the same kernels (openpvsg_b200/engine.py)
             from .engine import get_runner
             runner = get_runner(self, ref_img_metas[0][0], kwargs.get('rescale', False))
-            runner.run(ref_img)
-            return [[runner.results()]]
+            return [[runner.run(ref_img)]]
         video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
         results = [[] for _ in range(bs)]
         for i in range(bs):
