@@ -79,13 +79,14 @@ int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* 
                    float* C, void* C_hi, void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, int act, void* stream);
 
-/* pvsg_conv2d_nhwc (stride 1) on split operands: x planes [B,H,W,Cin], w planes
+/* pvsg_conv2d_nhwc (stride 1 or 2) on split operands: x planes [B,H,W,Cin], w planes
  * [Cout,R,S,Cin]; im2col-free -- a 4-D TMA box over the NHWC planes is shifted per filter
- * tap and out-of-bounds zero fill provides the padding.  Cin % 64 == 0. */
+ * tap (traversed with elementStrides = stride) and out-of-bounds zero fill provides the
+ * padding.  Cin % 64 == 0. */
 int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                    const float* bias, const float* residual, float* y, void* y_hi, void* y_lo,
-                   int B, int H, int W, int Cin, int Cout, int R, int S, int pad, int act,
-                   void* stream);
+                   int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
+                   int act, void* stream);
 
 /* 3x3 stride-2 pad-1 max pooling, NHWC (L0 ResNet stem). */
 int pvsg_maxpool3x3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream);

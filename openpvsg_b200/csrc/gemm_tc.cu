@@ -55,7 +55,7 @@ struct TcParams {
     int act;
     int tiles_m, tiles_n;
     // conv mode
-    int conv, OH, OW, cin_kb, S, pad, tiles_h, tiles_w;
+    int conv, OH, OW, cin_kb, S, pad, stride, tiles_h, tiles_w;
 };
 
 // ------------------------------------------------------------------ PTX wrappers -------
@@ -211,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     if (p.conv) {
                         const int rs = kb / p.cin_kb, cb = kb - rs * p.cin_kb;
                         const int r = rs / p.S, sx = rs - r * p.S;
-                        const int iy = tl.oh0 + r - p.pad, ix = tl.ow0 + sx - p.pad;
+                        const int iy = tl.oh0 * p.stride + r - p.pad, ix = tl.ow0 * p.stride + sx - p.pad;
                         tma_load_4d(&tmA_hi, &full[s], st, cb * BK, ix, iy, tl.tb);
                         tma_load_4d(&tmA_lo, &full[s], st + A_BYTES, cb * BK, ix, iy, tl.tb);
                     } else {
@@ -471,14 +471,15 @@ bool make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, in
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// 4-D map over NHWC bf16 [B, H, W, C]; box = [1, 8, 16, 64]
-bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+// 4-D map over NHWC bf16 [B, H, W, C]; box = [1, 8, 16, 64] output pixels; for a strided conv the
+// box spans 8*stride x 16*stride input pixels traversed with elementStrides = stride
+bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int stride) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)PATCH_W, (cuuint32_t)PATCH_H, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(PATCH_W * stride), (cuuint32_t)(PATCH_H * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -537,22 +538,24 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
 
 extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                               const float* bias, const float* residual, float* y, void* y_hi, void* y_lo, int B,
-                              int H, int W, int Cin, int Cout, int R, int S, int pad, int act, void* stream) {
+                              int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int act,
+                              void* stream) {
     PVSG_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && (y || y_hi) && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
     PVSG_CHECK_ARG((y_hi == nullptr) == (y_lo == nullptr) && R > 0 && S > 0 && pad >= 0);
     if (Cin % BK != 0 || !al16(x_hi) || !al16(x_lo) || !al16(w_hi) || !al16(w_lo)) return PVSG_ERR_UNSUPPORTED;
-    const int OH = H + 2 * pad - R + 1, OW = W + 2 * pad - S + 1;   // stride 1
+    if (stride < 1 || stride > 2) return PVSG_ERR_UNSUPPORTED;
+    const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
     PVSG_CHECK_ARG(OH > 0 && OW > 0);
     const int64_t K = (int64_t)R * S * Cin;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if (!make_map_4d(&ta_hi, x_hi, B, H, W, Cin) || !make_map_4d(&ta_lo, x_lo, B, H, W, Cin) ||
+    if (!make_map_4d(&ta_hi, x_hi, B, H, W, Cin, stride) || !make_map_4d(&ta_lo, x_lo, B, H, W, Cin, stride) ||
         !make_map_2d(&tb_hi, w_hi, Cout, K, K, BN) || !make_map_2d(&tb_lo, w_lo, Cout, K, K, BN))
         return PVSG_ERR_LAUNCH;
     TcParams p{};
     p.bias = bias; p.R = residual; p.C = y;
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
     p.M = (int64_t)B * OH * OW; p.N = Cout; p.ldc = Cout; p.ldr = Cout; p.act = act;
-    p.num_kb = (int)(K / BK); p.conv = 1; p.OH = OH; p.OW = OW; p.cin_kb = Cin / BK; p.S = S; p.pad = pad;
+    p.num_kb = (int)(K / BK); p.conv = 1; p.OH = OH; p.OW = OW; p.cin_kb = Cin / BK; p.S = S; p.pad = pad; p.stride = stride;
     p.tiles_h = (OH + PATCH_H - 1) / PATCH_H; p.tiles_w = (OW + PATCH_W - 1) / PATCH_W;
     const int64_t tiles_m = (int64_t)B * p.tiles_h * p.tiles_w;
     if (tiles_m * ((Cout + BN - 1) / BN) > 0x7fffffffLL) return PVSG_ERR_UNSUPPORTED;

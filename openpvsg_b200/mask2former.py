@@ -650,6 +650,9 @@ class _Mask2FormerHeadBase(_Prepared):
         # attention-mask features: mask features resized to each decoder level (linear, so it
         # commutes with the contraction -- see include/pvsg.h pvsg_mask_logits)
         pooled = [ops.bilinear_resize_nhwc(mf, s).view(B, -1, C) for s in lvl_shapes]
+        # operand planes of the (re-used) mask features for the tcgen05 engine, split once per frame
+        mf_planes = ops.maybe_split(mf_flat)
+        pooled_planes = [ops.maybe_split(pl) for pl in pooled]
         dec_in, dec_pe = [], []
         for i, m in enumerate(memories):
             tok = _tokens(m)                              # [BT,h,w,C]
@@ -667,8 +670,8 @@ class _Mask2FormerHeadBase(_Prepared):
         cls_pred, me = self._embeds(query)
         cls_list.append(cls_pred)
         if want_all:
-            mask_list.append(ops.mask_logits(me, mf_flat, True, False)[0].view(B, Q, T, h4, w4).transpose(1, 2))
-        _, mask, row_open = ops.mask_logits(me, pooled[0], False, True)
+            mask_list.append(ops.mask_logits(me, mf_flat, True, False, mf_planes)[0].view(B, Q, T, h4, w4).transpose(1, 2))
+        _, mask, row_open = ops.mask_logits(me, pooled[0], False, True, pooled_planes[0])
         if force_masks is not None:  # tests: teacher-force the discrete masks (see tests/test_models_gpu.py)
             mask, row_open = self._forced(force_masks[0])
         for i in range(nl):
@@ -679,9 +682,10 @@ class _Mask2FormerHeadBase(_Prepared):
             cls_list.append(cls_pred)
             last = i == nl - 1
             if want_all or last:
-                mask_list.append(ops.mask_logits(me, mf_flat, True, False)[0].view(B, Q, T, h4, w4).transpose(1, 2))
+                mask_list.append(ops.mask_logits(me, mf_flat, True, False, mf_planes)[0].view(B, Q, T, h4, w4).transpose(1, 2))
             if not last:
-                _, mask, row_open = ops.mask_logits(me, pooled[(i + 1) % self.num_transformer_feat_level], False, True)
+                nxt = (i + 1) % self.num_transformer_feat_level
+                _, mask, row_open = ops.mask_logits(me, pooled[nxt], False, True, pooled_planes[nxt])
                 if force_masks is not None:
                     mask, row_open = self._forced(force_masks[i + 1])
         return dict(cls=cls_list, masks=mask_list, query=query)

@@ -73,6 +73,11 @@ def split_bf16(x, add=None):
     return hi, lo
 
 
+def maybe_split(x):
+    """split_bf16(x) when the tcgen05 engine is active, else None."""
+    return split_bf16(x) if ENGINE[0] == 'tc' and x.shape[-1] % 64 == 0 and x.is_contiguous() else None
+
+
 def _weight_planes(w):
     """Cached split planes of a (possibly sliced) weight matrix.  The cache lives ON the base
     tensor object (the nn.Parameter / prepared weight), so it dies with it and can never be hit
@@ -154,21 +159,21 @@ def _linear_tc(lib, x, x2, w2, bias, add_input, residual, act, out, lead, M, N, 
 def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NONE, out=None):
     """x [B,H,W,Cin] token-major, weight [Cout,R,S,Cin] -> [B,OH,OW,Cout]."""
     lib = _l.load()
-    if (ENGINE[0] == 'tc' and stride == 1 and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
+    if (ENGINE[0] == 'tc' and stride in (1, 2) and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
             and weight.is_contiguous() and out is None):
         B, H, W, Cin = x.shape
         Cout, R, S, _ = weight.shape
-        if R == 1 and S == 1 and pad == 0:
+        if R == 1 and S == 1 and pad == 0 and stride == 1:
             return linear(x, weight.view(Cout, Cin), bias, residual=residual, act=act)
         x_hi, x_lo = split_bf16(x)
         w_hi, w_lo = _weight_planes(weight)
-        OH, OW = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+        OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
         y = torch.empty(B, OH, OW, Cout, device=x.device, dtype=torch.float32)
         if residual is not None and (tuple(residual.shape) != tuple(y.shape) or not residual.is_contiguous()):
             raise _l.PvsgError('conv2d_nhwc: bad residual')
         _l.check(lib.pvsg_conv2d_tc(_ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(_f32(bias)),
-                                    _ptr(_f32(residual)), _ptr(y), None, None, B, H, W, Cin, Cout, R, S, pad, act,
-                                    _stream()), 'pvsg_conv2d_tc')
+                                    _ptr(_f32(residual)), _ptr(y), None, None, B, H, W, Cin, Cout, R, S, stride, pad,
+                                    act, _stream()), 'pvsg_conv2d_tc')
         return y
     _f32(x, 'x'), _f32(weight, 'weight')
     if not (x.is_contiguous() and weight.is_contiguous() and x.dim() == 4 and weight.dim() == 4):
@@ -353,11 +358,27 @@ def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None
     return out
 
 
-def mask_logits(embed, feat, want_logits=True, want_mask=False):
-    """embed [B,Q,C], feat [B,P,C] token-major -> logits [B,Q,P] and/or (mask uint8, row_open int32)."""
+def mask_logits(embed, feat, want_logits=True, want_mask=False, feat_planes=None):
+    """embed [B,Q,C], feat [B,P,C] token-major -> logits [B,Q,P] and/or (mask uint8, row_open int32).
+    feat_planes: optional precomputed split_bf16(feat) (the mask features are reused by all ten
+    prediction heads of a frame)."""
     lib = _l.load()
     B, Q, C = _f32(embed).shape
     P = _f32(feat).shape[1]
+    if ENGINE[0] == 'tc' and C % 64 == 0 and embed.is_contiguous() and feat.is_contiguous():
+        dev = embed.device
+        logits = torch.empty(B, Q, P, device=dev, dtype=torch.float32) if want_logits else None
+        mask = torch.empty(B, Q, P, device=dev, dtype=torch.uint8) if want_mask else None
+        row_open = torch.zeros(B, Q, device=dev, dtype=torch.int32) if want_mask else None
+        e_hi, e_lo = split_bf16(embed)
+        f_hi, f_lo = feat_planes if feat_planes is not None else split_bf16(feat)
+        for b in range(B):
+            _l.check(lib.pvsg_linear_tc(_ptr(e_hi[b]), _ptr(e_lo[b]), C, _ptr(f_hi[b]), _ptr(f_lo[b]), C, None, None,
+                                        0, _ptr(logits[b]) if want_logits else None, None, None,
+                                        _ptr(mask[b]) if want_mask else None,
+                                        _ptr(row_open[b]) if want_mask else None, P, Q, P, C, ACT_NONE, _stream()),
+                     'pvsg_linear_tc')
+        return logits, mask, row_open
     logits = torch.empty(B, Q, P, device=embed.device, dtype=torch.float32) if want_logits else None
     mask = torch.empty(B, Q, P, device=embed.device, dtype=torch.uint8) if want_mask else None
     row_open = torch.empty(B, Q, device=embed.device, dtype=torch.int32) if want_mask else None

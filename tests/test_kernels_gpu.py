@@ -211,7 +211,8 @@ def test_mask_logits(ops):
     ref = torch.einsum('bqc,bchw->bqhw', embed, feat)
     ft = feat.permute(0, 2, 3, 1).reshape(B, h * w, C).contiguous().cuda()
     logits, mask, row_open = ops.mask_logits(embed.cuda(), ft, True, True)
-    close(logits.view(B, Q, h, w), ref, 2e-4, 'mask logits')
+    # N(0,1) operands, K = 256: |logit| reaches ~80; 1e-5 relative = split-bf16 / fp32 re-association level
+    close(logits.view(B, Q, h, w), ref, 1e-5 * ref.abs().max().item(), 'mask logits')
     # sign mask: identical wherever the oracle logit is not within rounding distance of 0
     refm = ref.flatten(2) < 0
     safe = ref.flatten(2).abs() > 1e-3

@@ -62,17 +62,20 @@ def test_linear_tc_add_input_and_slices(ops):
     assert (buf[:, :512].cpu().double() - ref1).abs().max().item() < 3e-5 * ref1.abs().max().item()
 
 
-@pytest.mark.parametrize('cin,cout,k,pad,hw,B', [(64, 64, 3, 1, (46, 80), 2), (256, 256, 3, 1, (23, 40), 1),
-                                                 (128, 128, 3, 1, (92, 160), 1), (64, 256, 1, 0, (45, 77), 2),
-                                                 (512, 512, 3, 1, (23, 40), 1), (64, 64, 3, 1, (184, 320), 1)])
-def test_conv_tc(ops, cin, cout, k, pad, hw, B):
+@pytest.mark.parametrize('cin,cout,k,pad,hw,B,stride', [
+    (64, 64, 3, 1, (46, 80), 2, 1), (256, 256, 3, 1, (23, 40), 1, 1), (128, 128, 3, 1, (92, 160), 1, 1),
+    (64, 256, 1, 0, (45, 77), 2, 1), (512, 512, 3, 1, (23, 40), 1, 1), (64, 64, 3, 1, (184, 320), 1, 1),
+    # strided convs of the ResNet stage transitions (TMA elementStrides = 2), odd sizes included
+    (128, 128, 3, 1, (92, 160), 1, 2), (256, 512, 1, 0, (92, 160), 1, 2), (64, 64, 3, 1, (47, 81), 2, 2),
+    (256, 256, 3, 1, (46, 80), 1, 2), (512, 1024, 1, 0, (45, 79), 1, 2)])
+def test_conv_tc(ops, cin, cout, k, pad, hw, B, stride):
     x = randn(1, B, cin, *hw)
     w = randn(2, cout, cin, k, k) / (cin * k * k) ** 0.5
     b = randn(3, cout)
-    ref = F.conv2d(x.double(), w.double(), b.double(), 1, pad)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride, pad)
     res = randn(4, *ref.shape)
     y = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().cuda(), w.permute(0, 2, 3, 1).contiguous().cuda(),
-                        b.cuda(), residual=res.permute(0, 2, 3, 1).contiguous().cuda(), stride=1, pad=pad,
+                        b.cuda(), residual=res.permute(0, 2, 3, 1).contiguous().cuda(), stride=stride, pad=pad,
                         act=ops.ACT_RELU)
     ref = F.relu(ref + res.double())
     err = (y.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
