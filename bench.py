@@ -199,9 +199,19 @@ def kernel_breakdown(det, img, meta):
         det._runners = runners
         for n, o in saved.items():
             setattr(ops, n, o)
+    # cost of an empty event pair on a busy stream (subtracted from every bracketed call)
+    torch.cuda._sleep(int(0.01 * 1.9e9))
+    pairs = []
+    for _ in range(200):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        b.record()
+        pairs.append((a, b))
+    torch.cuda.synchronize()
+    eps = float(np.median([a.elapsed_time(b) for a, b in pairs]))
     for family, e0, e1, fl, by in events:
         d = fam.setdefault(family, dict(ms=0.0, gflop=0.0, gbyte=0.0, launches=0))
-        d['ms'] += e0.elapsed_time(e1)
+        d['ms'] += max(e0.elapsed_time(e1) - eps, 0.0)
         d['gflop'] += fl / 1e9
         d['gbyte'] += by / 1e9
         d['launches'] += 1

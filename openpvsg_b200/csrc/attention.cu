@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(THREADS) attn_kernel(
     int nsplit, int keys_per_split) {
     constexpr int DPT = D / TPQ;  // 32
     constexpr int QPB = THREADS / TPQ;
-    static_assert(DPT == 32, "each thread owns 32 dims");
+    static_assert(DPT == 16, "each thread owns 16 dims");
     __shared__ __align__(16) float Ks[KC][D];
     __shared__ __align__(16) float Vs[KC][D];
 
@@ -70,43 +70,55 @@ __global__ void __launch_bounds__(THREADS) attn_kernel(
             reinterpret_cast<float4*>(&Vs[r][0])[c] = vv;
         }
         __syncthreads();
-        for (int j = 0; j < nk; ++j) {
-            float s = 0.f;
-            const float4* kr = reinterpret_cast<const float4*>(&Ks[j][sub * DPT]);
+        // keys in groups of 4: four independent dot-product chains, one softmax update per group
+        // (rows >= nk of the staged chunk are zero and are treated as blocked)
+        for (int j = 0; j < nk; j += 4) {
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int d = 0; d < DPT / 4; ++d) {
-                const float4 kk = kr[d];
-                s = fmaf(q[4 * d], kk.x, s);
-                s = fmaf(q[4 * d + 1], kk.y, s);
-                s = fmaf(q[4 * d + 2], kk.z, s);
-                s = fmaf(q[4 * d + 3], kk.w, s);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 kk = reinterpret_cast<const float4*>(&Ks[j + e][sub * DPT])[d];
+                    s[e] = fmaf(q[4 * d], kk.x, s[e]);
+                    s[e] = fmaf(q[4 * d + 1], kk.y, s[e]);
+                    s[e] = fmaf(q[4 * d + 2], kk.z, s[e]);
+                    s[e] = fmaf(q[4 * d + 3], kk.w, s[e]);
+                }
             }
             if (TPQ > 1) {
 #pragma unroll
-                for (int off = 1; off < TPQ; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int off = 1; off < TPQ; off <<= 1) s[e] += __shfl_xor_sync(0xffffffffu, s[e], off);
             }
-            const bool blocked = use_mask && mrow && mrow[k0 + j] != 0;
-            if (!blocked && qvalid) {  // uniform across the TPQ lanes of a query
-                float p;
-                if (s > m) {
-                    const float c = __expf(m - s);  // exp(-inf) = 0 on the first key
+            float mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool blocked = !qvalid || (j + e >= nk) || (use_mask && mrow && mrow[k0 + j + e] != 0);
+                if (blocked) s[e] = -INFINITY;
+                mx = fmaxf(mx, s[e]);
+            }
+            if (mx > -INFINITY) {  // else the whole group is blocked (uniform across the TPQ lanes of a query)
+                if (mx > m) {
+                    const float c = __expf(m - mx);  // exp(-inf) = 0 on the first open key
                     l *= c;
 #pragma unroll
                     for (int d = 0; d < DPT; ++d) o[d] *= c;
-                    m = s;
-                    p = 1.f;
-                } else {
-                    p = __expf(s - m);
+                    m = mx;
                 }
-                l += p;
-                const float4* vr = reinterpret_cast<const float4*>(&Vs[j][sub * DPT]);
 #pragma unroll
-                for (int d = 0; d < DPT / 4; ++d) {
-                    const float4 vv = vr[d];
-                    o[4 * d] = fmaf(p, vv.x, o[4 * d]);
-                    o[4 * d + 1] = fmaf(p, vv.y, o[4 * d + 1]);
-                    o[4 * d + 2] = fmaf(p, vv.z, o[4 * d + 2]);
-                    o[4 * d + 3] = fmaf(p, vv.w, o[4 * d + 3]);
+                for (int e = 0; e < 4; ++e) {
+                    const float p = __expf(s[e] - m);  // 0 for blocked keys
+                    l += p;
+                    const float4* vr = reinterpret_cast<const float4*>(&Vs[j + e][sub * DPT]);
+#pragma unroll
+                    for (int d = 0; d < DPT / 4; ++d) {
+                        const float4 vv = vr[d];
+                        o[4 * d] = fmaf(p, vv.x, o[4 * d]);
+                        o[4 * d + 1] = fmaf(p, vv.y, o[4 * d + 1]);
+                        o[4 * d + 2] = fmaf(p, vv.z, o[4 * d + 2]);
+                        o[4 * d + 3] = fmaf(p, vv.w, o[4 * d + 3]);
+                    }
                 }
             }
         }
@@ -159,15 +171,15 @@ int pick_splits(int B, int H, int Lq, int Lk, int qpb) {
     const int qtiles = (Lq + qpb - 1) / qpb;
     const int64_t base = (int64_t)B * H * qtiles;
     int ns = 1;
-    // aim for >= 2 CTAs per SM while keeping >= 4 key chunks per split
-    while (base * ns < 296 && Lk / (ns * 2) >= 4 * KC && ns < 64) ns *= 2;
+    // aim for ~4 CTAs per SM while keeping >= 2 key chunks per split
+    while (base * ns < 592 && Lk / (ns * 2) >= 2 * KC && ns < 128) ns *= 2;
     return ns;
 }
 
 }  // namespace
 
 extern "C" int64_t pvsg_attention_workspace_bytes(int B, int H, int Lq, int Lk, int D) {
-    const int qpb = D == 32 ? THREADS : THREADS / 4;
+    const int qpb = D == 32 ? THREADS / 2 : THREADS / 8;
     const int ns = pick_splits(B, H, Lq, Lk, qpb);
     if (ns == 1) return 16;
     return (int64_t)B * H * Lq * ns * (D + 2) * sizeof(float) + 16;
@@ -180,7 +192,7 @@ extern "C" int pvsg_attention(const float* Q, const float* K, const float* V, co
     PVSG_CHECK_ARG(Q && K && V && out && B > 0 && H > 0 && Lq > 0 && Lk > 0);
     PVSG_CHECK_ARG((q_bs | q_ts | k_bs | k_ts | v_bs | v_ts | o_bs | o_ts) % 4 == 0);
     if (D != 32 && D != 128) return PVSG_ERR_UNSUPPORTED;
-    const int qpb = D == 32 ? THREADS : THREADS / 4;
+    const int qpb = D == 32 ? THREADS / 2 : THREADS / 8;
     const int ns = pick_splits(B, H, Lq, Lk, qpb);
     PVSG_CHECK_ARG(ns == 1 || ws);
     int kps = (Lk + ns - 1) / ns;
@@ -191,10 +203,10 @@ extern "C" int pvsg_attention(const float* Q, const float* K, const float* V, co
     PVSG_CHECK_ARG(grid.z <= 65535);
     cudaStream_t st = as_stream(stream);
     if (D == 32)
-        attn_kernel<32, 1><<<grid, THREADS, 0, st>>>(Q, K, V, mask, row_open, out, part_o, part_ml, H, Lq, Lk, q_bs,
+        attn_kernel<32, 2><<<grid, THREADS, 0, st>>>(Q, K, V, mask, row_open, out, part_o, part_ml, H, Lq, Lk, q_bs,
                                                       q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, scale, ns, kps);
     else
-        attn_kernel<128, 4><<<grid, THREADS, 0, st>>>(Q, K, V, mask, row_open, out, part_o, part_ml, H, Lq, Lk, q_bs,
+        attn_kernel<128, 8><<<grid, THREADS, 0, st>>>(Q, K, V, mask, row_open, out, part_o, part_ml, H, Lq, Lk, q_bs,
                                                        q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts, scale, ns, kps);
     if (ns > 1) {
         const int64_t total = (int64_t)B * H * Lq * D;

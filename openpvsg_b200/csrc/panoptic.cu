@@ -7,6 +7,7 @@
 namespace {
 
 constexpr int NONE = 0x7fff;
+constexpr int INS_STRIPS = 8;   // 256-pixel strips per CTA in the instance statistics kernel
 
 struct UpGeom {
     int h, w;            // low-res logits
@@ -193,22 +194,25 @@ __global__ void __launch_bounds__(256) ins_pixel_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ query_idx, UpGeom g,
                                                         float* __restrict__ stats, int32_t* __restrict__ boxes,
                                                         uint8_t* __restrict__ masks_out) {
+    // one CTA = INS_STRIPS consecutive strips of 256 pixels of one candidate; statistics are
+    // reduced in registers -> warp shuffles -> shared memory, then ONE set of atomics per CTA
     const int i = blockIdx.y;
     const int q = query_idx[i];
     const int64_t npix = (int64_t)g.out_h * g.out_w;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < npix;
-    const int oy = valid ? (int)(p / g.out_w) : 0, ox = valid ? (int)(p % g.out_w) : 0;
+    const float* lg = mask_logits + (int64_t)q * g.h * g.w;
     float s = 0.f;
     int cnt = 0, xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
-    if (valid) {
-        const float v = final_logit(mask_logits + (int64_t)q * g.h * g.w, g, oy, ox);
+    for (int st = 0; st < INS_STRIPS; ++st) {
+        const int64_t p = ((int64_t)blockIdx.x * INS_STRIPS + st) * blockDim.x + threadIdx.x;
+        if (p >= npix) break;
+        const int oy = (int)(p / g.out_w), ox = (int)(p % g.out_w);
+        const float v = final_logit(lg, g, oy, ox);
         const bool on = v > 0.f;
         if (on) {
-            s = sigmoidf_(v);
-            cnt = 1;
-            xmin = xmax = ox;
-            ymin = ymax = oy;
+            s += sigmoidf_(v);
+            cnt += 1;
+            xmin = min(xmin, ox); xmax = max(xmax, ox);
+            ymin = min(ymin, oy); ymax = max(ymax, oy);
         }
         if (masks_out) masks_out[(int64_t)i * npix + p] = on ? 1 : 0;
     }
@@ -221,13 +225,29 @@ __global__ void __launch_bounds__(256) ins_pixel_kernel(const float* __restrict_
         xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
         ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
     }
-    if ((threadIdx.x & 31) == 0 && cnt) {
-        atomicAdd(&stats[2 * i], s);
-        atomicAdd(&stats[2 * i + 1], (float)cnt);
-        atomicMin(&boxes[4 * i], xmin);
-        atomicMin(&boxes[4 * i + 1], ymin);
-        atomicMax(&boxes[4 * i + 2], xmax);
-        atomicMax(&boxes[4 * i + 3], ymax);
+    __shared__ float sh_s[8];
+    __shared__ int sh_i[8][5];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sh_s[wid] = s;
+        sh_i[wid][0] = cnt; sh_i[wid][1] = xmin; sh_i[wid][2] = ymin; sh_i[wid][3] = xmax; sh_i[wid][4] = ymax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            s += sh_s[w];
+            cnt += sh_i[w][0];
+            xmin = min(xmin, sh_i[w][1]); ymin = min(ymin, sh_i[w][2]);
+            xmax = max(xmax, sh_i[w][3]); ymax = max(ymax, sh_i[w][4]);
+        }
+        if (cnt) {
+            atomicAdd(&stats[2 * i], s);
+            atomicAdd(&stats[2 * i + 1], (float)cnt);
+            atomicMin(&boxes[4 * i], xmin);
+            atomicMin(&boxes[4 * i + 1], ymin);
+            atomicMax(&boxes[4 * i + 2], xmax);
+            atomicMax(&boxes[4 * i + 3], ymax);
+        }
     }
 }
 
@@ -289,7 +309,7 @@ extern "C" int pvsg_instance_masks(const float* mask_logits, const int32_t* quer
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)out_h * out_w;
     ins_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, boxes, n);
-    dim3 grid((unsigned)((npix + 255) / 256), (unsigned)n);
+    dim3 grid((unsigned)((npix + 256 * INS_STRIPS - 1) / (256 * INS_STRIPS)), (unsigned)n);
     ins_pixel_kernel<<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
     ins_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(boxes, n);
     return pvsg_launch_status();
