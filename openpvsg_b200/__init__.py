@@ -10,7 +10,8 @@ from .registry import (build_backbone, build_detector, build_head, load_config, 
                        DETECTORS, HEADS, BACKBONES, POSITIONAL_ENCODING)
 from . import mask2former  # noqa: F401  (registers the modules)
 from .mask2former import (Mask2FormerCustom, Mask2FormerHeadCustom, Mask2FormerVideoCustom,  # noqa: F401
-                          Mask2FormerVideoHead, MaskFormerFusionHeadCustom, SinePositionalEncoding3D)
+                          Mask2FormerVideoCustomMinVIS, Mask2FormerVideoHead, MaskFormerFusionHeadCustom,
+                          SinePositionalEncoding3D)
 from .relation_head import (ObjectEncoder, PairProposalNetwork, TemporalTransformer, VanillaModel,  # noqa: F401
                             HandcraftedFilter, Learnable1DConv, pick_top_pairs_eval, concatenate_sub_obj,
                             generate_results, generate_pairwise_results)

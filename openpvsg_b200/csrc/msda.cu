@@ -16,6 +16,7 @@ struct MsdaLevels {
     int h[MAX_LEVELS];
     int w[MAX_LEVELS];
     int64_t start[MAX_LEVELS];
+    int64_t tile_start[MAX_LEVELS + 1];   // prefix sums of ceil(h/8) * ceil(w/8)
 };
 
 // Bilinear sample of value[b, start + (y, x), head, 4*q4 .. 4*q4+3] with zero padding,
@@ -40,7 +41,7 @@ __device__ __forceinline__ void sample_acc(const float4* __restrict__ vbase, int
     acc.w += w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
 }
 
-template <bool FUSED>
+template <bool FUSED, bool TILED>
 __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
                                                    const float* __restrict__ loc_or_proj,
                                                    const float* __restrict__ aw_or_ref, float* __restrict__ out,
@@ -50,15 +51,35 @@ __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ val
     const int LP = L * P;
     // work item = (b, query, head); consecutive warps of a CTA take consecutive QUERIES of one
     // head so that their sampling neighbourhoods overlap in L1.
+    // TILED (queries are the pyramid tokens themselves): a CTA owns an 8 x 8 tile of queries
+    // of one level, warp w walks row w -- the 64 sampling neighbourhoods overlap in 2-D, which is
+    // what keeps the bilinear corner lines in L1.
     const int wpb = blockDim.x >> 5;
-    const int64_t qblocks = (Nq + wpb - 1) / wpb;
+    const int warp = threadIdx.x >> 5;
+    const int64_t qblocks = TILED ? lv.tile_start[L] : (Nq + wpb - 1) / wpb;
     for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
         const int64_t qb = blk % qblocks;
         const int64_t t = blk / qblocks;
         const int head = (int)(t % H);
         const int64_t b = t / H;
-        const int64_t nq = qb * wpb + (threadIdx.x >> 5);
-        if (nq >= Nq) continue;
+        int tl = 0, ty = 0, tx = 0;
+        if (TILED) {
+            while (tl + 1 < L && qb >= lv.tile_start[tl + 1]) ++tl;
+            const int local = (int)(qb - lv.tile_start[tl]);
+            const int tiles_x = (lv.w[tl] + 7) >> 3;
+            ty = local / tiles_x;
+            tx = local - ty * tiles_x;
+        }
+      for (int qx = 0; qx < (TILED ? 8 : 1); ++qx) {
+        int64_t nq;
+        if (TILED) {
+            const int y = ty * 8 + warp, x = tx * 8 + qx;
+            if (y >= lv.h[tl] || x >= lv.w[tl]) continue;
+            nq = lv.start[tl] + (int64_t)y * lv.w[tl] + x;
+        } else {
+            nq = qb * wpb + warp;
+            if (nq >= Nq) continue;
+        }
         const int64_t pix_stride = (int64_t)H * 8;  // float4 per pixel (H heads * 32 ch / 4)
         const float4* vb = reinterpret_cast<const float4*>(value) + (b * N * H + head) * 8 + q4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -106,6 +127,7 @@ __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ val
             acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
         }
         if (g == 0) reinterpret_cast<float4*>(out)[((b * Nq + nq) * H + head) * 8 + q4] = acc;
+      }
     }
 }
 
@@ -119,6 +141,7 @@ int fill_levels(MsdaLevels& lv, const int64_t* spatial_shapes, const int64_t* le
         lv.start[l] = level_start_index[l];
         if (lv.h[l] <= 0 || lv.w[l] <= 0 || lv.start[l] != tot) return PVSG_ERR_INVALID_ARG;
         tot += (int64_t)lv.h[l] * lv.w[l];
+        lv.tile_start[l + 1] = lv.tile_start[l] + (int64_t)((lv.h[l] + 7) / 8) * ((lv.w[l] + 7) / 8);
     }
     return tot == N ? PVSG_OK : PVSG_ERR_INVALID_ARG;
 }
@@ -134,9 +157,15 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
     int rc = fill_levels(lv, spatial_shapes, level_start_index, L, N);
     if (rc != PVSG_OK) return rc;
     const int wpb = 8;
-    const int64_t total = (int64_t)B * H * ((Nq + wpb - 1) / wpb);
-    const unsigned grid = (unsigned)imin64(total, 148 * 64);
-    msda_kernel<FUSED><<<grid, wpb * 32, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P, total);
+    if (Nq == N) {   // queries = pyramid tokens: 2-D tiled query order
+        const int64_t total = (int64_t)B * H * lv.tile_start[L];
+        const unsigned grid = (unsigned)imin64(total, 148 * 64);
+        msda_kernel<FUSED, true><<<grid, wpb * 32, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P, total);
+    } else {
+        const int64_t total = (int64_t)B * H * ((Nq + wpb - 1) / wpb);
+        const unsigned grid = (unsigned)imin64(total, 148 * 64);
+        msda_kernel<FUSED, false><<<grid, wpb * 32, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P, total);
+    }
     return pvsg_launch_status();
 }
 

@@ -1007,3 +1007,82 @@ class Mask2FormerVideoCustom(_DetectorBase):
                     res['ins_results'] = bbox_results, mask_results
                 results[i].append(res)
         return results
+
+
+def _fusion_simple_test(self, mask_cls_results, mask_pred_results, img_metas, rescale=False, lowres=False, **kwargs):
+    """MaskFormerFusionHeadCustom.simple_test (mask2former_fusion_head.py:244-321): the
+    query-less form used by the MinVIS detector."""
+    dummy = [None] * len(img_metas)
+    out = []
+    for mask_cls, mask_pred, _, meta in zip(mask_cls_results, mask_pred_results, dummy, img_metas):
+        img_hw = tuple(meta['img_shape'][:2])
+        in_hw = tuple(meta['batch_input_shape']) if lowres else tuple(mask_pred.shape[-2:])
+        out_hw = tuple(meta['ori_shape'][:2]) if rescale else img_hw
+        result = dict()
+        if self.test_cfg.get('panoptic_on', True):
+            result['pan_results'], _info = self._panoptic(mask_cls, mask_pred, in_hw, img_hw, out_hw)
+        if self.test_cfg.get('instance_on', False):
+            result['ins_results'] = self.instance_postprocess(mask_cls, mask_pred, in_hw, img_hw, out_hw)
+        out.append(result)
+    return out
+
+
+MaskFormerFusionHeadCustom.simple_test = _fusion_simple_test
+
+
+@DETECTORS.register_module()
+class Mask2FormerVideoCustomMinVIS(Mask2FormerVideoCustom):
+    """models/mask2former_vps/mask2former_min_vis.py:35 -- per-frame inference, MinVIS query
+    matching between consecutive frames, clip-averaged class logits, per-frame fusion."""
+
+    @torch.no_grad()
+    def match_from_embds(self, tgt_embds, cur_embds):
+        """mask2former_min_vis.py:244-258: cosine cost on the device (one 100x256x100 GEMM through
+        pvsg_linear), Hungarian assignment on the host with scipy exactly as the reference."""
+        from scipy.optimize import linear_sum_assignment
+        cur = (cur_embds / cur_embds.norm(dim=1)[:, None]).contiguous()
+        tgt = (tgt_embds / tgt_embds.norm(dim=1)[:, None]).contiguous()
+        cos_sim = ops.linear(cur, tgt)                 # cur @ tgt^T
+        C = (1.0 - cos_sim).cpu()
+        indices = linear_sum_assignment(C.transpose(0, 1))
+        return torch.as_tensor(indices[1], device=cur_embds.device)
+
+    @torch.no_grad()
+    def simple_test(self, img, img_metas, ref_img, ref_img_metas, **kwargs):
+        """mask2former_min_vis.py:132-231 (batch size 1, as the reference's squeeze() implies)."""
+        bs, num_frame, three, h, w = ref_img.size()
+        assert bs == 1, 'MinVIS inference handles one clip at a time'
+        video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
+        pred_logits, mask_lr_list, query_list = [], [], []
+        for i in range(num_frame):
+            feats = [f[i:i + 1] for f in video_x]
+            cls, mask_lr, query = self.panoptic_head.simple_test_with_query(feats, [[ref_img_metas[0][i]]],
+                                                                            upsample=False)
+            pred_logits.append(cls[0])
+            mask_lr_list.append(mask_lr[0, 0])
+            query_list.append(query[:, 0])
+        out_logits, out_masks, out_embds = [pred_logits[0]], [mask_lr_list[0]], [query_list[0]]
+        for i in range(1, num_frame):
+            idx = self.match_from_embds(out_embds[-1], query_list[i])
+            out_logits.append(pred_logits[i][idx, :])
+            out_masks.append(mask_lr_list[i][idx, :, :])
+            out_embds.append(query_list[i][idx, :])
+        logits = (sum(out_logits) / len(out_logits)).unsqueeze(0)
+        results = [[]]
+        for frame_id in range(num_frame):
+            res = self.panoptic_fusion_head.simple_test(logits, out_masks[frame_id][None],
+                                                        [ref_img_metas[0][frame_id]], lowres=True, **kwargs)[0]
+            res['pan_results'] = res['pan_results'].cpu().numpy()
+            if 'ins_results' in res:
+                labels, bboxes, masks = res['ins_results']
+                ids = torch.arange(len(bboxes), dtype=bboxes.dtype, device=bboxes.device)[:, None] + 1
+                bboxes = torch.cat([ids, bboxes], dim=1)
+                inds = torch.argsort(bboxes[:, -1], descending=True)[:10]
+                labels, bboxes, masks = labels[inds], bboxes[inds], masks[inds]
+                mask_results = [[] for _ in range(self.num_things_classes)]
+                masks_np = masks.cpu().numpy()
+                for j, label in enumerate(labels.tolist()):
+                    mask_results[label].append(masks_np[j])
+                res['ins_results'] = bbox2result(bboxes, labels, self.num_things_classes), mask_results
+            results[0].append(res)
+        return results

@@ -563,3 +563,38 @@ def concat_seq(outputs):
             rows.append((frame_id + 1, tid, int(ins_id % 1000), mask.shape[0], mask.shape[1],
                          rle_to_string(rle_encode(mask))))
     return rows, feat_tubes
+
+
+def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True):
+    """Mask2FormerVideoCustomMinVIS.simple_test, models/mask2former_vps/mask2former_min_vis.py:132-231
+    (panoptic branch): per-frame heads, MinVIS matching, clip-averaged logits, per-frame fusion."""
+    bs, num_frame, three, h, w = ref_img.shape
+    video_x = resnet50(sd, ref_img.reshape(bs * num_frame, three, h, w))
+    pred_logits, mask_pred_list, query_pred_list = [], [], []
+    for i in range(num_frame):
+        cur = [f[i].unsqueeze(0) for f in video_x]
+        mask_cls, mask_pred, query_fea = head_simple_test_with_query(
+            sd, cur, ref_img_metas[0][0]['batch_input_shape'], video=True, num_frames=1)
+        pred_logits.append(mask_cls.squeeze())
+        mask_pred_list.append(mask_pred.squeeze())
+        query_pred_list.append(query_fea.permute(0, 2, 1).squeeze())
+    out_logits, out_masks, out_embds = [pred_logits[0]], [mask_pred_list[0]], [query_pred_list[0]]
+    perms = []
+    for i in range(1, num_frame):
+        indices = match_from_embds(out_embds[-1], query_pred_list[i])
+        perms.append(np.asarray(indices))
+        out_logits.append(pred_logits[i][indices, :])
+        out_masks.append(mask_pred_list[i][indices, :, :])
+        out_embds.append(query_pred_list[i][indices, :])
+    logits = (sum(out_logits) / len(out_logits)).unsqueeze(0)
+    masks = torch.stack(out_masks, dim=0).unsqueeze(0)
+    results = []
+    for frame_id in range(num_frame):
+        meta = ref_img_metas[0][frame_id]
+        mp = masks[0, frame_id][:, :meta['img_shape'][0], :meta['img_shape'][1]]
+        if rescale:
+            mp = F.interpolate(mp[:, None], size=tuple(meta['ori_shape'][:2]), mode='bilinear',
+                               align_corners=False)[:, 0]
+        pan, _ = panoptic_postprocess_with_query(logits[0], mp, torch.zeros(mp.shape[0], 1))
+        results.append(pan.numpy())
+    return results, perms, logits

@@ -195,6 +195,40 @@ def test_full_frame_vs_oracle_golden(detectors, cuda, golden_dir, name):
     assert sorted(res['query_feats']) == g['keys'].tolist()
 
 
+def test_minvis_clip_vs_oracle(cuda):
+    """Mask2FormerVideoCustomMinVIS on a 3-frame clip: MinVIS query permutations (the tube-linking
+    step, mask2former_min_vis.py:244-258) and per-frame panoptic ids vs the oracle."""
+    from openpvsg_b200 import build_detector
+    from oracle import m2f as om
+    sd = syn.mask2former_state_dict(seed=3)
+    cfg = model_cfg(True)
+    cfg['type'] = 'Mask2FormerVideoCustomMinVIS'
+    det = build_detector(cfg)
+    det.load_state_dict(sd)
+    det.to(cuda)
+    H, W, T = 96, 160, 3
+    clip = torch.stack([syn.synthetic_frame(40 + t, H, W) for t in range(T)])[None]   # [1,T,3,H,W]
+    metas = [[syn.frame_meta(H, W) for _ in range(T)]]
+    with torch.no_grad():
+        ref_pans, ref_perms, ref_logits = om.minvis_simple_test(sd, clip, metas)
+    res = det.simple_test(None, None, ref_img=clip.to(cuda), ref_img_metas=metas, rescale=True)
+    assert len(res) == 1 and len(res[0]) == T
+    # permutations: recompute them with the product path on the oracle's own per-frame embeddings
+    with torch.no_grad():
+        feats = om.resnet50(sd, clip[0])
+        embs = [om.head_simple_test_with_query(sd, [f[i:i + 1] for f in feats], (H, W), True, 1)[2][:, 0]
+                for i in range(T)]
+    prev = embs[0]
+    for i in range(1, T):
+        idx = det.match_from_embds(prev.to(cuda), embs[i].to(cuda)).cpu().numpy()
+        assert np.array_equal(idx, ref_perms[i - 1])
+        prev = embs[i][idx]
+    for t in range(T):
+        mism = float((res[0][t]['pan_results'] != ref_pans[t]).mean())
+        assert mism <= 1e-3, (t, mism)
+        assert 'ins_results' in res[0][t]
+
+
 def test_relation_head_vs_reference_golden(cuda, golden_dir):
     from openpvsg_b200 import relation_head as rh
     g = np.load(os.path.join(golden_dir, 'rel_small.npz'))
