@@ -88,6 +88,12 @@ int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const v
                    int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
                    int act, void* stream);
 
+/* Small-Cin convolutions (the 7x7/2 RGB stem, Cin = 3): gathers the patches of x [B,H,W,Cin]
+ * directly into split operand planes [B*OH*OW, Kpad] (k = (r*S + s)*Cin + c, zero-padded to
+ * Kpad >= R*S*Cin, Kpad % 64 == 0 for pvsg_linear_tc), so the stem also runs on tcgen05. */
+int pvsg_im2col_split(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int R,
+                      int S, int stride, int pad, int Kpad, void* stream);
+
 /* 3x3 stride-2 pad-1 max pooling, NHWC (L0 ResNet stem). */
 int pvsg_maxpool3x3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream);
 
@@ -100,6 +106,10 @@ int pvsg_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, void
  * transformer.py:26,44.) */
 int pvsg_layernorm(const float* x, const float* gamma, const float* beta, float* y,
                    int64_t rows, int C, float eps, void* stream);
+/* same, additionally emitting the split-bf16 planes (y_hi, y_lo) of y for a following
+ * pvsg_linear_tc (saves a pvsg_split_bf16 pass). */
+int pvsg_layernorm_split(const float* x, const float* gamma, const float* beta, float* y,
+                         void* y_hi, void* y_lo, int64_t rows, int C, float eps, void* stream);
 
 /* GroupNorm over token-major x [B,HW,C] (L0 ConvModule norm GN(32)); stats = workspace
  * of 2*B*groups doubles (zeroed by the call). y = act(GN(x)). */

@@ -405,6 +405,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
 }
 
+// Small-Cin convolutions (the 7x7/2 RGB stem): patches of the NHWC input are gathered straight into
+// operand planes [M, Kpad] (k = (r*S + s)*Cin + c, zero beyond R*S*Cin and outside the image),
+// which then go through the GEMM path.  One thread per (pixel, 4 consecutive k).
+__global__ void __launch_bounds__(256) im2col_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int Cin,
+                                                           int OH, int OW, int S, int stride, int pad, int Kreal,
+                                                           int Kpad, int64_t total4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kq = (int)(i % (Kpad / 4));
+        int64_t m = i / (Kpad / 4);
+        const int ow = (int)(m % OW);
+        int64_t t = m / OW;
+        const int oh = (int)(t % OH);
+        const int64_t b = t / OH;
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = kq * 4 + e;
+            float v = 0.f;
+            if (k < Kreal) {
+                const int c = k % Cin, rs = k / Cin;
+                const int r = rs / S, s = rs - r * S;
+                const int ih = oh * stride - pad + r, iw = ow * stride - pad + s;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + ((b * H + ih) * W + iw) * (int64_t)Cin + c);
+            }
+            const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+            h[e] = __bfloat16_as_ushort(hh);
+            l[e] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hh)));
+        }
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+        reinterpret_cast<uint2*>(lo)[i] = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+    }
+}
+
 // fp32 -> (hi, lo) bf16 planes, optionally of x + x2
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
@@ -503,6 +537,20 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+extern "C" int pvsg_im2col_split(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int R, int S,
+                                 int stride, int pad, int Kpad, void* stream) {
+    PVSG_CHECK_ARG(x && hi && lo && B > 0 && H > 0 && W > 0 && Cin > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0);
+    const int Kreal = R * S * Cin;
+    PVSG_CHECK_ARG(Kpad >= Kreal && Kpad % 4 == 0);
+    const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
+    PVSG_CHECK_ARG(OH > 0 && OW > 0);
+    const int64_t total4 = (int64_t)B * OH * OW * (Kpad / 4);
+    im2col_split_kernel<<<(unsigned)imin64((total4 + 255) / 256, 148 * 32), 256, 0, as_stream(stream)>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), H, W, Cin, OH, OW, S, stride,
+        pad, Kreal, Kpad, total4);
+    return pvsg_launch_status();
+}
 
 extern "C" int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* lo, int64_t n, void* stream) {
     PVSG_CHECK_ARG(x && hi && lo && n > 0 && n % 4 == 0 && al16(x) && (!x2 || al16(x2)));

@@ -1,4 +1,6 @@
 // LayerNorm, GroupNorm (token-major), broadcast add.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -8,7 +10,9 @@ template <int V>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
-                                                        float* __restrict__ y, int64_t rows, float eps) {
+                                                        float* __restrict__ y, int64_t rows, float eps,
+                                                        uint16_t* __restrict__ y_hi = nullptr,
+                                                        uint16_t* __restrict__ y_lo = nullptr) {
     constexpr int C = 128 * V;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -40,6 +44,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
         yr[lane + 32 * i] = o;
+        if (y_hi) {  // split-bf16 planes of the same values for the tcgen05 engine
+            const float a[4] = {o.x, o.y, o.z, o.w};
+            uint16_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 hh = __float2bfloat16_rn(a[e]);
+                h[e] = __bfloat16_as_ushort(hh);
+                l[e] = __bfloat16_as_ushort(__float2bfloat16_rn(a[e] - __bfloat162float(hh)));
+            }
+            const int64_t q = row * (C / 4) + lane + 32 * i;
+            reinterpret_cast<uint2*>(y_hi)[q] = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+            reinterpret_cast<uint2*>(y_lo)[q] = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        }
     }
 }
 
@@ -125,20 +142,32 @@ __global__ void __launch_bounds__(256) add_rowvec_kernel(const float* __restrict
 
 }  // namespace
 
-extern "C" int pvsg_layernorm(const float* x, const float* gamma, const float* beta, float* y,
-                              int64_t rows, int C, float eps, void* stream) {
-    PVSG_CHECK_ARG(x && gamma && beta && y && rows > 0);
+static int layernorm_launch(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int C,
+                            float eps, uint16_t* hi, uint16_t* lo, void* stream) {
     const int wpb = 8;
     dim3 grid((unsigned)((rows + wpb - 1) / wpb));
     cudaStream_t st = as_stream(stream);
     switch (C) {
-        case 128: layernorm_kernel<1><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps); break;
-        case 256: layernorm_kernel<2><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps); break;
-        case 512: layernorm_kernel<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps); break;
-        case 1024: layernorm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps); break;
+        case 128: layernorm_kernel<1><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
+        case 256: layernorm_kernel<2><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
+        case 512: layernorm_kernel<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
+        case 1024: layernorm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
         default: return PVSG_ERR_UNSUPPORTED;
     }
     return pvsg_launch_status();
+}
+
+extern "C" int pvsg_layernorm(const float* x, const float* gamma, const float* beta, float* y,
+                              int64_t rows, int C, float eps, void* stream) {
+    PVSG_CHECK_ARG(x && gamma && beta && y && rows > 0);
+    return layernorm_launch(x, gamma, beta, y, rows, C, eps, nullptr, nullptr, stream);
+}
+
+extern "C" int pvsg_layernorm_split(const float* x, const float* gamma, const float* beta, float* y, void* y_hi,
+                                    void* y_lo, int64_t rows, int C, float eps, void* stream) {
+    PVSG_CHECK_ARG(x && gamma && beta && y && y_hi && y_lo && rows > 0);
+    return layernorm_launch(x, gamma, beta, y, rows, C, eps, reinterpret_cast<uint16_t*>(y_hi),
+                            reinterpret_cast<uint16_t*>(y_lo), stream);
 }
 
 extern "C" int pvsg_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* y,

@@ -27,12 +27,14 @@ SIGNATURES = {
     'pvsg_linear': (I, [P, P, P, P, P, P, L, L, L, L, L, L, L, I, L, L, L, L, P]),
     'pvsg_conv2d_nhwc': (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_split_bf16': (I, [P, P, P, P, L, P]),
+    'pvsg_im2col_split': (I, [P, P, P, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_linear_tc': (I, [P, P, L, P, P, L, P, P, L, P, P, P, P, P, L, L, L, L, I, P]),
     'pvsg_conv2d_tc': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_maxpool3x3s2_nhwc': (I, [P, P, I, I, I, I, P]),
     'pvsg_nchw_to_nhwc': (I, [P, P, I, I, I, I, P]),
     'pvsg_nhwc_to_nchw': (I, [P, P, I, I, I, I, P]),
     'pvsg_layernorm': (I, [P, P, P, P, L, I, F, P]),
+    'pvsg_layernorm_split': (I, [P, P, P, P, P, P, L, I, F, P]),
     'pvsg_groupnorm_nhwc': (I, [P, P, P, P, P, I, L, I, I, F, I, P]),
     'pvsg_add_rowvec': (I, [P, P, P, L, I, P]),
     'pvsg_bilinear_resize_nhwc': (I, [P, P, I, I, I, I, I, I, I, P]),

@@ -138,19 +138,24 @@ class ResNet(_Prepared):
             self._prepare()
         p = self._prep
         x = _tokens(x)
+        ops.clear_split_cache()
         x = ops.conv2d_nhwc(x, *p['stem'], stride=2, pad=3, act=ops.ACT_RELU)
         x = ops.maxpool3x3s2_nhwc(x)
+        # Inside a bottleneck the 1x1 -> 3x3 -> 1x1 chain hands operand planes from epilogue to
+        # TMA loader (out_mode='split': the fp32 tensor is never written); the block output is
+        # needed both as fp32 (next residual) and as planes (next convs): out_mode='both'.
+        xs = ops.maybe_split(x)
         outs = []
         nblk = len(p['blocks'])
         for j, d in enumerate(p['blocks']):
-            idt = x
-            o = ops.conv2d_nhwc(x, *d['c1'], act=ops.ACT_RELU)
-            o = ops.conv2d_nhwc(o, *d['c2'], stride=d['stride'], pad=1, act=ops.ACT_RELU)
-            if d['ds'] is not None:
-                idt = ops.conv2d_nhwc(x, *d['ds'], stride=d['stride'])
-            x = ops.conv2d_nhwc(o, *d['c3'], residual=idt, act=ops.ACT_RELU)
+            inp = xs if xs is not None else x
+            o = ops.conv2d_nhwc(inp, *d['c1'], act=ops.ACT_RELU, out_mode='split')
+            o = ops.conv2d_nhwc(o, *d['c2'], stride=d['stride'], pad=1, act=ops.ACT_RELU, out_mode='split')
+            idt = x if d['ds'] is None else ops.conv2d_nhwc(inp, *d['ds'], stride=d['stride'])
+            x, xs = ops.conv2d_nhwc(o, *d['c3'], residual=idt, act=ops.ACT_RELU, out_mode='both')
             if j + 1 == nblk or p['blocks'][j + 1]['stage'] != d['stage']:
                 if d['stage'] in self.out_indices:
+                    ops.remember_split(x, xs)   # the pixel decoder's 1x1 convs reuse these planes
                     outs.append(_as_nchw(x))
         return tuple(outs)
 
@@ -221,12 +226,13 @@ class MultiScaleDeformableAttention(_Prepared):
             b=torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0).contiguous())
 
     @torch.no_grad()
-    def forward_tokens(self, x, pos, ref, spatial_shapes):
-        """x, pos [B,N,C]; ref [N,2] -> output_proj(msda) + x."""
+    def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None):
+        """x, pos [B,N,C]; ref [N,2] -> output_proj(msda) + x.  x_planes: operand planes of x when
+        the producer (the previous LayerNorm) already emitted them."""
         if self._prep is None:
             self._prepare()
         proj = ops.linear(x, self._prep['w'], self._prep['b'], add_input=pos)
-        value = ops.linear(x, self.value_proj.weight, self.value_proj.bias)
+        value = ops.linear(x_planes if x_planes is not None else x, self.value_proj.weight, self.value_proj.bias)
         samp = ops.msda_fused_forward(value, spatial_shapes, proj, ref, self.num_heads, self.num_points)
         return ops.linear(samp, self.output_proj.weight, self.output_proj.bias, residual=x)
 
@@ -309,11 +315,16 @@ class BaseTransformerLayer(nn.Module):
         self.norms = nn.ModuleList([_Norm(self.embed_dims), _Norm(self.embed_dims)])
 
     @torch.no_grad()
-    def forward_tokens(self, x, pos, ref, spatial_shapes):
-        x = self.attentions[0].forward_tokens(x, pos, ref, spatial_shapes)
-        x = self.norms[0](x)
-        x = self.ffns[0](x)
-        return self.norms[1](x)
+    def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None):
+        """Returns (x, planes of x): both LayerNorms emit the operand planes of their output for the
+        GEMMs that consume it, and the FFN hidden layer only ever exists as planes."""
+        n0, n1, ffn = self.norms[0], self.norms[1], self.ffns[0]
+        x = self.attentions[0].forward_tokens(x, pos, ref, spatial_shapes, x_planes)
+        x, xs = ops.layernorm(x, n0.weight, n0.bias, n0.eps, out_split=True)
+        h = ops.linear(xs if xs is not None else x, ffn.layers[0][0].weight, ffn.layers[0][0].bias,
+                       act=ops.ACT_RELU, out_mode='split')
+        x = ops.linear(h, ffn.layers[1].weight, ffn.layers[1].bias, residual=x if ffn.add_identity else None)
+        return ops.layernorm(x, n1.weight, n1.bias, n1.eps, out_split=True)
 
 
 @TRANSFORMER_LAYER_SEQUENCE.register_module()
@@ -341,7 +352,8 @@ class _ConvModule(nn.Module):
     def forward_tokens(self, x):
         if self._w is None or self._w.device != self.conv.weight.device:
             self._w = self.conv.weight.permute(0, 2, 3, 1).contiguous()
-        y = ops.conv2d_nhwc(x, self._w, self.conv.bias, pad=self.pad)
+        planes = ops.recall_split(x)   # e.g. backbone stage outputs already carry operand planes
+        y = ops.conv2d_nhwc(planes if planes is not None else x, self._w, self.conv.bias, pad=self.pad)
         return y
 
     def norm_tokens(self, y):
@@ -413,8 +425,9 @@ class MSDeformAttnPixelDecoder(_Prepared):
         x = torch.cat(toks, 1)  # pure data movement (torch.cat = cudaMemcpy-class op)
         pos, ref = self._shape_consts(shapes, x.device)
         posb = pos[None].expand(B, -1, -1).contiguous() if B > 1 else pos[None]
+        xs = None
         for layer in self.encoder.layers:
-            x = layer.forward_tokens(x, posb, ref, shapes)
+            x, xs = layer.forward_tokens(x, posb, ref, shapes, xs)
         outs, start = [], 0
         for (h, w) in shapes:
             outs.append(x[:, start:start + h * w].reshape(B, h, w, -1))
@@ -464,11 +477,15 @@ class MultiheadAttention(nn.Module):
         return ops.linear(o, self.attn.out_proj.weight, self.attn.out_proj.bias, residual=query)
 
     @torch.no_grad()
-    def project_kv(self, key, key_pos, value):
+    def project_kv(self, key, key_pos, value, key_planes=None, value_planes=None):
+        """key_planes / value_planes: operand planes of (key + key_pos) and value when the caller
+        has them (each decoder level is projected by three different layers)."""
         E = self.embed_dims
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
-        return (ops.linear(key, w[E:2 * E], b[E:2 * E], add_input=key_pos),
-                ops.linear(value, w[2 * E:], b[2 * E:]))
+        k = ops.linear(key_planes, w[E:2 * E], b[E:2 * E]) if key_planes is not None else \
+            ops.linear(key, w[E:2 * E], b[E:2 * E], add_input=key_pos)
+        v = ops.linear(value_planes if value_planes is not None else value, w[2 * E:], b[2 * E:])
+        return k, v
 
     @torch.no_grad()
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
@@ -613,11 +630,14 @@ class _Mask2FormerHeadBase(_Prepared):
     @torch.no_grad()
     def _embeds(self, query):
         """query [B,Q,C] -> (cls_pred [B,Q,NC+1], mask_embed [B,Q,C])."""
-        x = self.transformer_decoder.post_norm(query)
-        cls_pred = ops.linear(x, self.cls_embed.weight, self.cls_embed.bias)
-        me = ops.linear(x, self.mask_embed[0].weight, self.mask_embed[0].bias, act=ops.ACT_RELU)
-        me = ops.linear(me, self.mask_embed[2].weight, self.mask_embed[2].bias, act=ops.ACT_RELU)
-        me = ops.linear(me, self.mask_embed[4].weight, self.mask_embed[4].bias)
+        pn = self.transformer_decoder.post_norm
+        x, xs = ops.layernorm(query, pn.weight, pn.bias, pn.eps, out_split=True)
+        xin = xs if xs is not None else x
+        cls_pred = ops.linear(xin, self.cls_embed.weight, self.cls_embed.bias)
+        # the 3-layer mask-embed MLP and the mask-logit contraction chain on operand planes
+        me = ops.linear(xin, self.mask_embed[0].weight, self.mask_embed[0].bias, act=ops.ACT_RELU, out_mode='split')
+        me = ops.linear(me, self.mask_embed[2].weight, self.mask_embed[2].bias, act=ops.ACT_RELU, out_mode='split')
+        me = ops.linear(me, self.mask_embed[4].weight, self.mask_embed[4].bias, out_mode='split')
         return cls_pred, me
 
     @torch.no_grad()
@@ -660,6 +680,8 @@ class _Mask2FormerHeadBase(_Prepared):
             dec_in.append(ops.add_rowvec(tok, self.level_embed.weight[i].contiguous()).view(B, T * h * w, C))
             pe = self._decoder_pe((T, h, w), tok.device)
             dec_pe.append(pe[None].expand(B, -1, -1).contiguous() if B > 1 else pe[None])
+        kin_planes = [ops.maybe_split(d, pe) for d, pe in zip(dec_in, dec_pe)]
+        vin_planes = [ops.maybe_split(d) for d in dec_in]
         Q = self.num_queries
         query = self.query_feat.weight[None].expand(B, -1, -1).contiguous()
         qpos = self.query_embed.weight[None].expand(B, -1, -1).contiguous()
@@ -676,7 +698,8 @@ class _Mask2FormerHeadBase(_Prepared):
             mask, row_open = self._forced(force_masks[0])
         for i in range(nl):
             lvl = i % self.num_transformer_feat_level
-            kproj, vproj = layers[i].attentions[0].project_kv(dec_in[lvl], dec_pe[lvl], dec_in[lvl])
+            kproj, vproj = layers[i].attentions[0].project_kv(dec_in[lvl], dec_pe[lvl], dec_in[lvl],
+                                                              kin_planes[lvl], vin_planes[lvl])
             query = layers[i].forward_tokens(query, qpos, kproj, vproj, mask, row_open)
             cls_pred, me = self._embeds(query)
             cls_list.append(cls_pred)

@@ -73,9 +73,61 @@ def split_bf16(x, add=None):
     return hi, lo
 
 
-def maybe_split(x):
-    """split_bf16(x) when the tcgen05 engine is active, else None."""
-    return split_bf16(x) if ENGINE[0] == 'tc' and x.shape[-1] % 64 == 0 and x.is_contiguous() else None
+class Split:
+    """An fp32 activation carried as its two bf16 planes (the tcgen05 engine's operand format).
+    Producers can emit it directly (``out_mode='split'`` / ``'both'``) so that GEMM -> GEMM chains
+    never materialise the fp32 tensor nor run a separate split pass."""
+    __slots__ = ('hi', 'lo')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def dim(self):
+        return self.hi.dim()
+
+    def view(self, *shape):
+        return Split(self.hi.view(*shape), self.lo.view(*shape))
+
+    def __iter__(self):  # (hi, lo) unpacking
+        return iter((self.hi, self.lo))
+
+
+_split_cache = {}
+
+
+def clear_split_cache():
+    """Forget the planes remembered during the previous forward (called at the start of a frame)."""
+    _split_cache.clear()
+
+
+def remember_split(t, planes):
+    """Associate operand planes with an fp32 tensor that crosses a module interface as a plain
+    tensor (e.g. backbone stage outputs).  The tensor is held by the cache, so its address cannot
+    be recycled for another tensor while the entry is alive."""
+    if planes is not None:
+        _split_cache[(t.data_ptr(), tuple(t.shape))] = (t, planes)
+
+
+def recall_split(t):
+    hit = _split_cache.get((t.data_ptr(), tuple(t.shape)))
+    return hit[1] if hit is not None else None
+
+
+def maybe_split(x, add=None):
+    """Split planes of x (+ add) when the tcgen05 engine is active and the shape qualifies, else None."""
+    if isinstance(x, Split):
+        return x
+    if ENGINE[0] == 'tc' and x.shape[-1] % 64 == 0 and x.is_contiguous():
+        return Split(*split_bf16(x, add))
+    return None
 
 
 def _weight_planes(w):
@@ -102,16 +154,28 @@ def _tc_ok(K, lda):
     return ENGINE[0] == 'tc' and K % 64 == 0 and lda % 8 == 0
 
 
-def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, out=None):
-    """act((x + add_input) @ weight.T + bias + residual); x [..., K], weight [N, K] (row slices ok)."""
+def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, out=None, out_mode='f32'):
+    """act((x + add_input) @ weight.T + bias + residual); x [..., K], weight [N, K] (row slices ok).
+
+    x may be a ``Split`` (operand planes produced upstream).  out_mode: 'f32' -> fp32 tensor;
+    'split' -> ``Split`` planes only; 'both' -> (fp32, Split).  On the SIMT engine planes do not
+    exist: 'split' returns the fp32 tensor and 'both' returns (fp32, None); consumers accept either.
+    """
     lib = _l.load()
+    w2, N, Kw, ldw = _rows(weight, 'weight')
+    if isinstance(x, Split):
+        lead, K = x.shape[:-1], x.shape[-1]
+        M = x.hi.numel() // K
+        if add_input is not None or Kw != K:
+            raise _l.PvsgError('linear: Split input cannot take add_input / K mismatch')
+        return _linear_tc(lib, x.view(M, K), w2, bias, residual, act, out, lead, M, N, K, out_mode)
     lead = x.shape[:-1]
     x2, M, K, lda = _rows(x, 'x')
-    w2, N, Kw, ldw = _rows(weight, 'weight')
     if Kw != K:
         raise _l.PvsgError(f'linear: K mismatch {K} vs {Kw}')
     if _tc_ok(K, K) and x2.is_contiguous() and (add_input is None or add_input.is_contiguous()):
-        return _linear_tc(lib, x, x2, w2, bias, add_input, residual, act, out, lead, M, N, K)
+        planes = Split(*split_bf16(x2, None if add_input is None else add_input.reshape(M, K)))
+        return _linear_tc(lib, planes, w2, bias, residual, act, out, lead, M, N, K, out_mode)
     a2 = None
     if add_input is not None:
         a2, M2, K2, lda2 = _rows(add_input, 'add_input')
@@ -132,18 +196,32 @@ def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, ou
         raise _l.PvsgError('linear: bad bias')
     _l.check(lib.pvsg_linear(_ptr(x2), _ptr(a2), _ptr(w2), _ptr(bias), _ptr(r2), _ptr(o2), M, N, K, lda, ldw,
                              ldc, ldr, act, 1, 0, 0, 0, _stream()), 'pvsg_linear')
-    return out.reshape(*lead, N) if created else out
+    out = out.reshape(*lead, N) if created else out
+    return (out, None) if out_mode == 'both' else out
 
 
-def _linear_tc(lib, x, x2, w2, bias, add_input, residual, act, out, lead, M, N, K):
-    a_hi, a_lo = split_bf16(x2, None if add_input is None else add_input.reshape(M, K))
+def _linear_tc(lib, planes, w2, bias, residual, act, out, lead, M, N, K, out_mode='f32'):
+    """planes: Split [M,K].  Returns per out_mode (see linear)."""
     w_hi, w_lo = _weight_planes(w2)
+    dev = planes.device
+    want_f32 = out_mode in ('f32', 'both') or out is not None
+    want_split = out_mode in ('split', 'both') and N % 8 == 0
+    if not want_split and not want_f32:
+        want_f32 = True  # odd N: planes cannot be emitted; caller gets fp32
     created = out is None
-    if created:
-        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
-    o2, Mo, No, ldc = _rows(out, 'out')
-    if (Mo, No) != (M, N):
-        raise _l.PvsgError('linear: bad out shape')
+    o2, ldc = None, N
+    if want_f32:
+        if created:
+            out = torch.empty(M, N, device=dev, dtype=torch.float32)
+        o2, Mo, No, ldc = _rows(out, 'out')
+        if (Mo, No) != (M, N):
+            raise _l.PvsgError('linear: bad out shape')
+    c_hi = c_lo = None
+    if want_split:
+        if ldc != N:
+            raise _l.PvsgError('linear: split output needs a dense fp32 output')
+        c_hi = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        c_lo = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     r2, ldr = None, 0
     if residual is not None:
         r2, Mr, Nr, ldr = _rows(residual, 'residual')
@@ -151,30 +229,73 @@ def _linear_tc(lib, x, x2, w2, bias, add_input, residual, act, out, lead, M, N, 
             raise _l.PvsgError('linear: bad residual shape')
     if bias is not None and (_f32(bias, 'bias').numel() != N or not bias.is_contiguous()):
         raise _l.PvsgError('linear: bad bias')
-    _l.check(lib.pvsg_linear_tc(_ptr(a_hi), _ptr(a_lo), K, _ptr(w_hi), _ptr(w_lo), K, _ptr(bias), _ptr(r2), ldr,
-                                _ptr(o2), None, None, None, None, ldc, M, N, K, act, _stream()), 'pvsg_linear_tc')
-    return out.reshape(*lead, N) if created else out
+    _l.check(lib.pvsg_linear_tc(_ptr(planes.hi), _ptr(planes.lo), K, _ptr(w_hi), _ptr(w_lo), K, _ptr(bias), _ptr(r2),
+                                ldr, _ptr(o2), _ptr(c_hi), _ptr(c_lo), None, None, ldc, M, N, K, act, _stream()),
+             'pvsg_linear_tc')
+    f32 = (out.reshape(*lead, N) if created else out) if want_f32 else None
+    sp = Split(c_hi.view(*lead, N), c_lo.view(*lead, N)) if want_split else None
+    if out_mode == 'both':
+        return f32, sp
+    if out_mode == 'split' and sp is not None:
+        return sp
+    return f32
 
 
-def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NONE, out=None):
-    """x [B,H,W,Cin] token-major, weight [Cout,R,S,Cin] -> [B,OH,OW,Cout]."""
+def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NONE, out=None, out_mode='f32'):
+    """x [B,H,W,Cin] token-major (tensor or Split), weight [Cout,R,S,Cin] -> [B,OH,OW,Cout].
+    out_mode as in ``linear``."""
     lib = _l.load()
-    if (ENGINE[0] == 'tc' and stride in (1, 2) and x.dim() == 4 and x.shape[-1] % 64 == 0 and x.is_contiguous()
-            and weight.is_contiguous() and out is None):
+    if isinstance(x, Split) or (ENGINE[0] == 'tc' and stride in (1, 2) and x.dim() == 4 and x.shape[-1] % 64 == 0
+                                and x.is_contiguous() and weight.is_contiguous() and out is None):
         B, H, W, Cin = x.shape
         Cout, R, S, _ = weight.shape
         if R == 1 and S == 1 and pad == 0 and stride == 1:
-            return linear(x, weight.view(Cout, Cin), bias, residual=residual, act=act)
-        x_hi, x_lo = split_bf16(x)
+            r = residual.view(-1, Cout) if residual is not None else None
+            res = linear(x.view(B * H * W, Cin) if isinstance(x, Split) else x.view(B * H * W, Cin),
+                         weight.view(Cout, Cin), bias, residual=r, act=act, out_mode=out_mode)
+            shp = (B, H, W, Cout)
+            if out_mode == 'both':
+                return res[0].view(*shp), (res[1].view(*shp) if res[1] is not None else None)
+            return res.view(*shp)
+        xs = x if isinstance(x, Split) else Split(*split_bf16(x))
         w_hi, w_lo = _weight_planes(weight)
         OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
-        y = torch.empty(B, OH, OW, Cout, device=x.device, dtype=torch.float32)
-        if residual is not None and (tuple(residual.shape) != tuple(y.shape) or not residual.is_contiguous()):
+        dev = xs.device
+        want_split = out_mode in ('split', 'both') and Cout % 8 == 0
+        want_f32 = out_mode in ('f32', 'both') or not want_split
+        y = torch.empty(B, OH, OW, Cout, device=dev, dtype=torch.float32) if want_f32 else None
+        y_hi = torch.empty(B, OH, OW, Cout, device=dev, dtype=torch.bfloat16) if want_split else None
+        y_lo = torch.empty(B, OH, OW, Cout, device=dev, dtype=torch.bfloat16) if want_split else None
+        if residual is not None and (tuple(residual.shape) != (B, OH, OW, Cout) or not residual.is_contiguous()):
             raise _l.PvsgError('conv2d_nhwc: bad residual')
-        _l.check(lib.pvsg_conv2d_tc(_ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(_f32(bias)),
-                                    _ptr(_f32(residual)), _ptr(y), None, None, B, H, W, Cin, Cout, R, S, stride, pad,
-                                    act, _stream()), 'pvsg_conv2d_tc')
-        return y
+        _l.check(lib.pvsg_conv2d_tc(_ptr(xs.hi), _ptr(xs.lo), _ptr(w_hi), _ptr(w_lo), _ptr(_f32(bias)),
+                                    _ptr(_f32(residual)), _ptr(y), _ptr(y_hi), _ptr(y_lo), B, H, W, Cin, Cout, R, S,
+                                    stride, pad, act, _stream()), 'pvsg_conv2d_tc')
+        sp = Split(y_hi, y_lo) if want_split else None
+        if out_mode == 'both':
+            return y, sp
+        return sp if (out_mode == 'split' and sp is not None) else y
+    if (ENGINE[0] == 'tc' and x.dim() == 4 and x.shape[-1] % 64 != 0 and x.is_contiguous() and weight.is_contiguous()
+            and out is None and weight.shape[1] * weight.shape[2] * weight.shape[3] <= 2048):
+        # small-Cin conv (RGB stem): patches gathered straight into operand planes, then the GEMM path
+        B, H, W, Cin = _f32(x, 'x').shape
+        Cout, R, S, _ = _f32(weight, 'weight').shape
+        kreal = R * S * Cin
+        kpad = (kreal + 63) // 64 * 64
+        OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        M = B * OH * OW
+        hi = torch.empty(M, kpad, device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty(M, kpad, device=x.device, dtype=torch.bfloat16)
+        _l.check(lib.pvsg_im2col_split(_ptr(x), _ptr(hi), _ptr(lo), B, H, W, Cin, R, S, stride, pad, kpad, _stream()),
+                 'pvsg_im2col_split')
+        cache = weight.__dict__.get('_pvsg_padded')
+        if cache is None or cache[0] != (kpad, weight._version):
+            wp = torch.zeros(Cout, kpad, device=x.device, dtype=torch.float32)
+            wp[:, :kreal] = weight.view(Cout, kreal)
+            cache = ((kpad, weight._version), wp)
+            weight._pvsg_padded = cache
+        r = residual.view(M, Cout) if residual is not None else None
+        return _linear_tc(lib, Split(hi, lo), cache[1], bias, r, act, None, (B, OH, OW), M, Cout, kpad, out_mode)
     _f32(x, 'x'), _f32(weight, 'weight')
     if not (x.is_contiguous() and weight.is_contiguous() and x.dim() == 4 and weight.dim() == 4):
         raise _l.PvsgError('conv2d_nhwc: contiguous 4-D tensors required')
@@ -189,7 +310,7 @@ def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NO
         raise _l.PvsgError('conv2d_nhwc: bad residual')
     _l.check(lib.pvsg_conv2d_nhwc(_ptr(x), _ptr(weight), _ptr(_f32(bias)), _ptr(_f32(residual)), _ptr(out), B, H,
                                   W, Cin, Cout, R, S, stride, pad, act, _stream()), 'pvsg_conv2d_nhwc')
-    return out
+    return (out, None) if out_mode == 'both' else out
 
 
 def maxpool3x3s2_nhwc(x):
@@ -216,7 +337,9 @@ def nhwc_to_nchw(x):
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5, out=None):
+def layernorm(x, gamma, beta, eps=1e-5, out=None, out_split=False):
+    """LayerNorm over the last axis.  out_split=True additionally returns the Split planes of the
+    result (None on the SIMT engine): (y, planes)."""
     lib = _l.load()
     _f32(x)
     if not x.is_contiguous():
@@ -224,9 +347,15 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     C = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
+    if out_split and ENGINE[0] == 'tc' and C % 64 == 0:
+        hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        _l.check(lib.pvsg_layernorm_split(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), _ptr(hi), _ptr(lo),
+                                          x.numel() // C, C, eps, _stream()), 'pvsg_layernorm_split')
+        return out, Split(hi, lo)
     _l.check(lib.pvsg_layernorm(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), x.numel() // C, C, eps,
                                 _stream()), 'pvsg_layernorm')
-    return out
+    return (out, None) if out_split else out
 
 
 def groupnorm_nhwc(x, gamma, beta, groups=32, eps=1e-5, act=ACT_NONE, out=None):
@@ -363,14 +492,15 @@ def mask_logits(embed, feat, want_logits=True, want_mask=False, feat_planes=None
     feat_planes: optional precomputed split_bf16(feat) (the mask features are reused by all ten
     prediction heads of a frame)."""
     lib = _l.load()
-    B, Q, C = _f32(embed).shape
+    B, Q, C = embed.shape
     P = _f32(feat).shape[1]
-    if ENGINE[0] == 'tc' and C % 64 == 0 and embed.is_contiguous() and feat.is_contiguous():
+    if isinstance(embed, Split) or (ENGINE[0] == 'tc' and C % 64 == 0 and embed.is_contiguous()
+                                    and feat.is_contiguous()):
         dev = embed.device
         logits = torch.empty(B, Q, P, device=dev, dtype=torch.float32) if want_logits else None
         mask = torch.empty(B, Q, P, device=dev, dtype=torch.uint8) if want_mask else None
         row_open = torch.zeros(B, Q, device=dev, dtype=torch.int32) if want_mask else None
-        e_hi, e_lo = split_bf16(embed)
+        e_hi, e_lo = embed if isinstance(embed, Split) else split_bf16(embed)
         f_hi, f_lo = feat_planes if feat_planes is not None else split_bf16(feat)
         for b in range(B):
             _l.check(lib.pvsg_linear_tc(_ptr(e_hi[b]), _ptr(e_lo[b]), C, _ptr(f_hi[b]), _ptr(f_lo[b]), C, None, None,

@@ -67,7 +67,9 @@ def test_linear_tc_add_input_and_slices(ops):
     (64, 256, 1, 0, (45, 77), 2, 1), (512, 512, 3, 1, (23, 40), 1, 1), (64, 64, 3, 1, (184, 320), 1, 1),
     # strided convs of the ResNet stage transitions (TMA elementStrides = 2), odd sizes included
     (128, 128, 3, 1, (92, 160), 1, 2), (256, 512, 1, 0, (92, 160), 1, 2), (64, 64, 3, 1, (47, 81), 2, 2),
-    (256, 256, 3, 1, (46, 80), 1, 2), (512, 1024, 1, 0, (45, 79), 1, 2)])
+    (256, 256, 3, 1, (46, 80), 1, 2), (512, 1024, 1, 0, (45, 79), 1, 2),
+    # RGB stem: patches gathered straight into operand planes (pvsg_im2col_split) + GEMM
+    (3, 64, 7, 3, (96, 160), 2, 2), (3, 64, 7, 3, (75, 131), 1, 2)])
 def test_conv_tc(ops, cin, cout, k, pad, hw, B, stride):
     x = randn(1, B, cin, *hw)
     w = randn(2, cout, cin, k, k) / (cin * k * k) ** 0.5
