@@ -140,56 +140,70 @@ def run_reference(args, rank):
 # instrumented frame: per-kernel-family time / flops with CUDA events
 # --------------------------------------------------------------------------------------
 def kernel_breakdown(det, img, meta):
+    """Device time per kernel family for one frame.
+
+    One eager frame is run with every ops.* call recorded (function, arguments).  Then, per
+    family, the recorded calls are replayed inside ONE CUDA graph (same input tensors, outputs
+    discarded) and the graph is timed with CUDA events: pure device time, no host launch latency,
+    same kernels / shapes / launch order as the timed region."""
     from openpvsg_b200 import ops
-    fam = {}
-    events = []
+    calls = []
 
-    def wrap(name, family, flops_fn=None, bytes_fn=None):
-        orig = getattr(ops, name)
-
-        def f(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = orig(*a, **k)
-            e1.record()
-            events.append((family, e0, e1, flops_fn(a, k, out) if flops_fn else 0.0,
-                           bytes_fn(a, k, out) if bytes_fn else 0.0))
-            return out
-        setattr(ops, name, f)
-        return orig
-
-    def lin_flops(a, k, out):
+    def lin_flops(a, k):
         x, w = a[0], a[1]
-        return 2.0 * (x.numel() // x.shape[-1]) * w.shape[0] * w.shape[1]
+        return 2.0 * (int(np.prod(x.shape[:-1]))) * w.shape[0] * w.shape[1]
 
-    def conv_flops(a, k, out):
-        w = a[1]
-        return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+    def conv_flops(a, k):
+        x, w = a[0], a[1]
+        s = k.get('stride', 1)
+        return 2.0 * x.shape[0] * (x.shape[1] // s) * (x.shape[2] // s) * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3]
 
-    def ml_flops(a, k, out):
+    def ml_flops(a, k):
         e, f = a[0], a[1]
         return 2.0 * e.shape[0] * e.shape[1] * e.shape[2] * f.shape[1]
 
-    def msda_bytes(a, k, out):
+    def msda_bytes(a, k):
         v, proj = a[0], a[2]
-        return 4.0 * (v.numel() + proj.numel() + out.numel())
+        return 4.0 * (2 * v.numel() + proj.numel())
 
-    saved = {n: wrap(n, f, fl, by) for n, f, fl, by in (
-        ('linear', 'gemm', lin_flops, None), ('conv2d_nhwc', 'gemm', conv_flops, None),
-        ('mask_logits', 'mask_logits', ml_flops, None), ('msda_fused_forward', 'msda', None, msda_bytes),
-        ('attention', 'attention', None, None), ('layernorm', 'norm', None, None),
-        ('groupnorm_nhwc', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
-        ('instance_masks', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
-        ('maxpool3x3s2_nhwc', 'resize', None, None), ('add_rowvec', 'norm', None, None))}
+    spec = (('linear', 'gemm', lin_flops, None), ('conv2d_nhwc', 'gemm', conv_flops, None),
+            ('mask_logits', 'gemm', ml_flops, None), ('split_bf16', 'gemm', None, None),
+            ('msda_fused_forward', 'msda', None, msda_bytes), ('attention', 'attention', None, None),
+            ('layernorm', 'norm', None, None), ('groupnorm_nhwc', 'norm', None, None),
+            ('add_rowvec', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
+            ('instance_masks', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
+            ('maxpool3x3s2_nhwc', 'resize', None, None))
+    saved, depth = {}, [0]
+
+    def wrap(name, family, flops_fn, bytes_fn):
+        orig = getattr(ops, name)
+        saved[name] = orig
+
+        def f(*a, **k):
+            top = depth[0] == 0          # nested calls (linear -> split_bf16) belong to the outer call
+            depth[0] += 1
+            try:
+                out = orig(*a, **k)
+            finally:
+                depth[0] -= 1
+            if top:
+                fam_name = family
+                if name == 'linear':      # split the GEMM engine by regime: decoder M=100 chains are latency-bound
+                    fam_name = 'gemm_m100' if int(np.prod(a[0].shape[:-1])) <= 128 else 'gemm_tokens'
+                elif name == 'conv2d_nhwc':
+                    fam_name = 'gemm_conv'
+                elif name == 'mask_logits':
+                    fam_name = 'gemm_mask_logits'
+                calls.append((fam_name, orig, a, k, flops_fn(a, k) if flops_fn else 0.0,
+                              bytes_fn(a, k) if bytes_fn else 0.0))
+            return out
+        setattr(ops, name, f)
+
+    for s in spec:
+        wrap(*s)
     try:
         runners = getattr(det, '_runners', None)
-        det._runners = None  # eager path so that every launch is bracketed by events
-        det.simple_test(None, None, ref_img=img[None, None], ref_img_metas=[[meta]], rescale=True)
-        events.clear()
-        torch.cuda.synchronize()
-        # park the GPU behind a ~150 ms spin kernel so the whole frame is enqueued before it starts:
-        # event intervals then measure device time only, not host launch latency
-        torch.cuda._sleep(int(0.15 * 1.9e9))
+        det._runners = None
         cls, mlr, _ = det.panoptic_head.simple_test_with_query(det.extract_feat(img[None]), [[meta]], upsample=False)
         fh = det.panoptic_fusion_head
         fh._panoptic(cls[0], mlr[0, 0], (736, 1280), (H, W), (H, W))
@@ -199,22 +213,33 @@ def kernel_breakdown(det, img, meta):
         det._runners = runners
         for n, o in saved.items():
             setattr(ops, n, o)
-    # cost of an empty event pair on a busy stream (subtracted from every bracketed call)
-    torch.cuda._sleep(int(0.01 * 1.9e9))
-    pairs = []
-    for _ in range(200):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        b.record()
-        pairs.append((a, b))
-    torch.cuda.synchronize()
-    eps = float(np.median([a.elapsed_time(b) for a, b in pairs]))
-    for family, e0, e1, fl, by in events:
-        d = fam.setdefault(family, dict(ms=0.0, gflop=0.0, gbyte=0.0, launches=0))
-        d['ms'] += max(e0.elapsed_time(e1) - eps, 0.0)
-        d['gflop'] += fl / 1e9
-        d['gbyte'] += by / 1e9
-        d['launches'] += 1
+    fam = {}
+    for family in sorted(set(c[0] for c in calls)):
+        mine = [c for c in calls if c[0] == family]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _, fn, a, k, _, _ in mine:
+                fn(*a, **k)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _, fn, a, k, _, _ in mine:
+                fn(*a, **k)
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        fam[family] = dict(ms=float(np.median(ts)), gflop=sum(c[4] for c in mine) / 1e9,
+                           gbyte=sum(c[5] for c in mine) / 1e9, launches=len(mine))
+        del g
     return fam
 
 
@@ -340,7 +365,9 @@ def main():
     e2e_sync = args.frames * world * max(1, args.steps // 2) / (ms_sync * 1e-3)
     fam = kernel_breakdown(det, resident[0], meta)
     tot_ms = sum(d['ms'] for d in fam.values())
-    g = fam.get('gemm', dict(ms=1.0, gflop=0.0, launches=1))
+    gk = [k for k in fam if k.startswith('gemm')]
+    g = dict(ms=sum(fam[k]['ms'] for k in gk) or 1.0, gflop=sum(fam[k]['gflop'] for k in gk),
+             launches=sum(fam[k]['launches'] for k in gk))
     achieved_tf = g['gflop'] / g['ms']  # GFLOP / ms == TFLOP/s
     roofline = dict(kernel='gemm_tc_kernel + split_kernel (tcgen05 split-bf16 GEMM / implicit-GEMM conv engine; '
                            'algorithmic 2MNK flops, each product = 3 bf16 MMAs)', bound='tensor',
@@ -352,6 +379,9 @@ def main():
     m = fam.get('msda')
     kernels = {k: dict(ms_per_frame=round(d['ms'], 3), share=round(d['ms'] / tot_ms, 3), launches=d['launches'])
                for k, d in fam.items()}
+    for k in gk:
+        if fam[k]['gflop'] > 0:
+            kernels[k]['TFLOPs'] = round(fam[k]['gflop'] / fam[k]['ms'], 1)
     if m:
         kernels['msda']['achieved_GBps'] = round(m['gbyte'] / (m['ms'] * 1e-3), 1)
         kernels['msda']['frac_hbm'] = round(m['gbyte'] / (m['ms'] * 1e-3) / peaks['hbm_gbs'], 4)

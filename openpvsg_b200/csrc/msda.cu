@@ -21,20 +21,28 @@ struct MsdaLevels {
 
 // Bilinear sample of value[b, start + (y, x), head, 4*q4 .. 4*q4+3] with zero padding,
 // pixel coordinates (x, y) already in the align_corners=False frame (loc * size - 0.5).
-__device__ __forceinline__ void sample_acc(const float4* __restrict__ vbase, int hgt, int wid, int64_t pix_stride,
+__device__ __forceinline__ void sample_acc(const float4* __restrict__ vbase, int hgt, int wid, int pix_stride,
                                            float x, float y, float aw, float4& acc) {
-    // mmcv's CUDA op: skip samples entirely outside (-1, size)
-    if (!(y > -1.f && x > -1.f && y < (float)hgt && x < (float)wid)) return;
-    const int y0 = (int)floorf(y), x0 = (int)floorf(x);
-    const float ly = y - (float)y0, lx = x - (float)x0;
+    // Branch-free: corner indices are clamped into the map and out-of-range corners get weight 0
+    // (identical to zero padding, and to mmcv's "skip samples outside (-1, size)" rule), so the four
+    // loads of every sample are unconditional and the compiler can keep all of them in flight.
+    x = fminf(fmaxf(x, -2.f), (float)wid + 1.f);
+    y = fminf(fmaxf(y, -2.f), (float)hgt + 1.f);
+    const float fy = floorf(y), fx = floorf(x);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const float ly = y - fy, lx = x - fx;
     const float hy = 1.f - ly, hx = 1.f - lx;
-    const bool y0v = y0 >= 0, y1v = y0 + 1 <= hgt - 1, x0v = x0 >= 0, x1v = x0 + 1 <= wid - 1;
-    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-    if (y0v && x0v) v00 = __ldg(vbase + ((int64_t)y0 * wid + x0) * pix_stride);
-    if (y0v && x1v) v01 = __ldg(vbase + ((int64_t)y0 * wid + x0 + 1) * pix_stride);
-    if (y1v && x0v) v10 = __ldg(vbase + ((int64_t)(y0 + 1) * wid + x0) * pix_stride);
-    if (y1v && x1v) v11 = __ldg(vbase + ((int64_t)(y0 + 1) * wid + x0 + 1) * pix_stride);
-    const float w00 = hy * hx * aw, w01 = hy * lx * aw, w10 = ly * hx * aw, w11 = ly * lx * aw;
+    const bool y0v = y0 >= 0 && y0 < hgt, y1v = y0 + 1 >= 0 && y0 + 1 < hgt;
+    const bool x0v = x0 >= 0 && x0 < wid, x1v = x0 + 1 >= 0 && x0 + 1 < wid;
+    const int yc0 = min(max(y0, 0), hgt - 1), yc1 = min(max(y0 + 1, 0), hgt - 1);
+    const int xc0 = min(max(x0, 0), wid - 1), xc1 = min(max(x0 + 1, 0), wid - 1);
+    // 32-bit indices: N * H * 8 float4 < 2^31 (checked on the host)
+    const float4 v00 = __ldg(vbase + (yc0 * wid + xc0) * pix_stride);
+    const float4 v01 = __ldg(vbase + (yc0 * wid + xc1) * pix_stride);
+    const float4 v10 = __ldg(vbase + (yc1 * wid + xc0) * pix_stride);
+    const float4 v11 = __ldg(vbase + (yc1 * wid + xc1) * pix_stride);
+    const float w00 = (y0v && x0v) ? hy * hx * aw : 0.f, w01 = (y0v && x1v) ? hy * lx * aw : 0.f;
+    const float w10 = (y1v && x0v) ? ly * hx * aw : 0.f, w11 = (y1v && x1v) ? ly * lx * aw : 0.f;
     acc.x += w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
     acc.y += w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
     acc.z += w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
@@ -42,7 +50,7 @@ __device__ __forceinline__ void sample_acc(const float4* __restrict__ vbase, int
 }
 
 template <bool FUSED, bool TILED>
-__global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
+__global__ void __launch_bounds__(256, 5) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
                                                    const float* __restrict__ loc_or_proj,
                                                    const float* __restrict__ aw_or_ref, float* __restrict__ out,
                                                    int64_t N, int64_t Nq, int H, int L, int P, int64_t total) {
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ val
             nq = qb * wpb + warp;
             if (nq >= Nq) continue;
         }
-        const int64_t pix_stride = (int64_t)H * 8;  // float4 per pixel (H heads * 32 ch / 4)
+        const int pix_stride = H * 8;  // float4 per pixel (H heads * 32 ch / 4)
         const float4* vb = reinterpret_cast<const float4*>(value) + (b * N * H + head) * 8 + q4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (FUSED) {
@@ -95,6 +103,7 @@ __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ val
             const float o0 = lane < LP ? __ldg(offp + 2 * lane) : 0.f;      // x offset of sample `lane`
             const float o1 = lane < LP ? __ldg(offp + 2 * lane + 1) : 0.f;  // y offset
             const float rx = __ldg(aw_or_ref + nq * 2), ry = __ldg(aw_or_ref + nq * 2 + 1);
+#pragma unroll 3
             for (int s0 = 0; s0 < LP; s0 += 4) {  // trip count is warp-uniform (full-mask shuffles)
                 const int s = min(s0 + g, LP - 1);
                 float aw = __shfl_sync(0xffffffffu, wgt, s);
@@ -103,10 +112,10 @@ __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ val
                 if (s0 + g >= LP) aw = 0.f;
                 const int l = s / P;
                 const int hgt = lv.h[l], wid = lv.w[l];
-                // loc = ref + off / (w, h); pixel = loc * size - 0.5
-                const float x = (rx + ox / (float)wid) * (float)wid - 0.5f;
-                const float y = (ry + oy / (float)hgt) * (float)hgt - 0.5f;
-                sample_acc(vb + lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, aw, acc);
+                // loc = ref + off / (w, h); pixel = loc * size - 0.5 = ref * size + off - 0.5
+                const float x = fmaf(rx, (float)wid, ox) - 0.5f;
+                const float y = fmaf(ry, (float)hgt, oy) - 0.5f;
+                sample_acc(vb + (int)lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, aw, acc);
             }
         } else {
             const float* locp = loc_or_proj + ((b * Nq + nq) * H + head) * (int64_t)LP * 2;
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(256) msda_kernel(const float* __restrict__ val
                 const int hgt = lv.h[l], wid = lv.w[l];
                 const float x = __ldg(locp + 2 * s) * (float)wid - 0.5f;
                 const float y = __ldg(locp + 2 * s + 1) * (float)hgt - 0.5f;
-                sample_acc(vb + lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, __ldg(awp + s), acc);
+                sample_acc(vb + (int)lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, __ldg(awp + s), acc);
             }
         }
 #pragma unroll
@@ -152,7 +161,7 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
            int P, void* stream) {
     PVSG_CHECK_ARG(value && spatial_shapes && level_start_index && a && b2 && out);
     PVSG_CHECK_ARG(B > 0 && N > 0 && Nq > 0 && H > 0 && P > 0);
-    if (D != 32 || L * P > 32) return PVSG_ERR_UNSUPPORTED;
+    if (D != 32 || L * P > 32 || N * H * 8 >= (1LL << 31)) return PVSG_ERR_UNSUPPORTED;
     MsdaLevels lv{};
     int rc = fill_levels(lv, spatial_shapes, level_start_index, L, N);
     if (rc != PVSG_OK) return rc;
