@@ -139,7 +139,7 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------
 # instrumented frame: per-kernel-family time / flops with CUDA events
 # --------------------------------------------------------------------------------------
-def kernel_breakdown(det, img, meta):
+def kernel_breakdown(det, img, meta, batch=1):
     """Device time per kernel family for one frame.
 
     One eager frame is run with every ops.* call recorded (function, arguments).  Then, per
@@ -204,10 +204,13 @@ def kernel_breakdown(det, img, meta):
     try:
         runners = getattr(det, '_runners', None)
         det._runners = None
-        cls, mlr, _ = det.panoptic_head.simple_test_with_query(det.extract_feat(img[None]), [[meta]], upsample=False)
+        xb = img[None].expand(batch, -1, -1, -1).contiguous()
+        cls, mlr, _ = det.panoptic_head.simple_test_with_query(det.extract_feat(xb), [[meta]] * batch, upsample=False)
         fh = det.panoptic_fusion_head
-        fh._panoptic(cls[0], mlr[0, 0], (736, 1280), (H, W), (H, W))
-        fh._instance_device(cls[0], mlr[0, 0], (736, 1280), (H, W), (H, W), True)
+        for b in range(batch):
+            m = mlr[b, 0].contiguous()
+            fh._panoptic(cls[b], m, (736, 1280), (H, W), (H, W))
+            fh._instance_device(cls[b], m, (736, 1280), (H, W), (H, W), True)
         torch.cuda.synchronize()
     finally:
         det._runners = runners
@@ -237,8 +240,8 @@ def kernel_breakdown(det, img, meta):
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        fam[family] = dict(ms=float(np.median(ts)), gflop=sum(c[4] for c in mine) / 1e9,
-                           gbyte=sum(c[5] for c in mine) / 1e9, launches=len(mine))
+        fam[family] = dict(ms=float(np.median(ts)) / batch, gflop=sum(c[4] for c in mine) / 1e9 / batch,
+                           gbyte=sum(c[5] for c in mine) / 1e9 / batch, launches=len(mine) / batch)
         del g
     return fam
 
@@ -252,6 +255,7 @@ def main():
     ap.add_argument('--frames', type=int, default=100, help='frames per GPU per step')
     ap.add_argument('--distinct', type=int, default=8, help='distinct synthetic frames cycled through')
     ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the cpu_baseline sample')
+    ap.add_argument('--batch', type=int, default=8, help='frames pushed through the network together')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu launch lists)')
     args = ap.parse_args()
@@ -311,14 +315,16 @@ def main():
                 consume(res)
         else:
             # same kernels, software-pipelined: frame i+1 is submitted before frame i is collected
-            runner = engine.get_runner(det, meta, True)
+            runner = engine.get_runner(det, meta, True, batch=args.batch)
             pend = None
-            for i in range(args.frames):
-                nxt = runner.submit(frames[i % len(frames)])
+            for i in range(0, args.frames, args.batch):
+                nxt = runner.submit([frames[(i + j) % len(frames)] for j in range(min(args.batch, args.frames - i))])
                 if pend is not None:
-                    consume(runner.collect(pend, copy=False))
+                    for r in runner.collect(pend, copy=False):
+                        consume(r)
                 pend = nxt
-            consume(runner.collect(pend, copy=False))
+            for r in runner.collect(pend, copy=False):
+                consume(r)
         ids_feats = [(ids, torch.stack(f).cpu().numpy() if f else np.zeros((0, 256), np.float32)) for ids, f in entries]
         return tubes.gather_and_link(ids_feats, args.frames * world, device=dev if world > 1 else 'cpu')
 
@@ -348,12 +354,12 @@ def main():
     ms_e2e, _, _ = timed(host, 'pipelined', args.steps, 1)        # FrameRunner.submit/collect, pinned host frames
     ms_sync, _, _ = timed(host, 'sync', max(1, args.steps // 2), 1)  # model(return_loss=False, ...) per frame
     if det._runners:
-        per_frame = next(iter(det._runners.values())).launches_per_frame
+        per_frame = max(r.launches_per_frame for r in det._runners.values() if r.batch == args.batch)
     else:
         n0 = lib.launch_count[0]
         run_step(resident[:1] * 1, False) if args.frames == 1 else None
         per_frame = (lib.launch_count[0] - n0) or 638
-    launches = per_frame * args.frames * args.steps
+    launches = int(per_frame * args.frames * args.steps)
 
     if rank != 0:
         if world > 1:
@@ -363,7 +369,7 @@ def main():
     value = total_frames / (ms_dev * 1e-3)
     e2e = total_frames / (ms_e2e * 1e-3)
     e2e_sync = args.frames * world * max(1, args.steps // 2) / (ms_sync * 1e-3)
-    fam = kernel_breakdown(det, resident[0], meta)
+    fam = kernel_breakdown(det, resident[0], meta, args.batch)
     tot_ms = sum(d['ms'] for d in fam.values())
     gk = [k for k in fam if k.startswith('gemm')]
     g = dict(ms=sum(fam[k]['ms'] for k in gk) or 1.0, gflop=sum(fam[k]['gflop'] for k in gk),
@@ -374,10 +380,10 @@ def main():
                     achieved=round(achieved_tf, 2), peak=peaks['tf_sustained'], unit='TFLOP/s',
                     frac=round(achieved_tf / peaks['tf_sustained'], 4), traffic=None,
                     peak_source=peaks['source'] + ', sustained bf16 figure (kernel timed inside a long step)',
-                    launches_per_frame=g['launches'], gflop_per_frame=round(g['gflop'], 1),
+                    launches_per_frame=round(g['launches'], 1), gflop_per_frame=round(g['gflop'], 1),
                     share_of_frame=round(g['ms'] / tot_ms, 3))
     m = fam.get('msda')
-    kernels = {k: dict(ms_per_frame=round(d['ms'], 3), share=round(d['ms'] / tot_ms, 3), launches=d['launches'])
+    kernels = {k: dict(ms_per_frame=round(d['ms'], 3), share=round(d['ms'] / tot_ms, 3), launches=round(d['launches'], 1))
                for k, d in fam.items()}
     for k in gk:
         if fam[k]['gflop'] > 0:
@@ -401,7 +407,7 @@ def main():
                             frames_per_gpu_per_step=args.frames, distinct_frames=args.distinct,
                             resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
                             l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',
-                            cuda_graph=not args.no_graph, tubes=len(linker.object_list)),
+                            cuda_graph=not args.no_graph, frames_per_launch=args.batch, tubes=len(linker.object_list)),
                 e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames,
                          d2h_bytes_per_step=out_bytes * args.frames, ms_per_step=round(ms_e2e / args.steps, 3),
                          api='engine.FrameRunner.submit/collect (pipelined) on pinned host frames',

@@ -307,6 +307,85 @@ int dispatch(const GemmParams& p, int64_t batch, cudaStream_t st) {
 
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
+// "Skinny" GEMM for the decoder's M <= 128 chains (100 queries): latency, not throughput, is
+// what matters there.  One CTA per NB output columns; the weight slab [NB, K] sits in shared
+// memory (read as warp-wide broadcasts), thread (row, k-half) streams half of its A row with
+// 128-bit loads, the two halves meet in shared memory.  Exact fp32, fused (x + pos), bias,
+// residual and ReLU, no operand split pass.
+template <int NB>
+__global__ void __launch_bounds__(256) skinny_kernel(GemmParams p) {
+    extern __shared__ __align__(16) float sk_smem[];
+    const int K = (int)p.K, M = (int)p.M;
+    float* Ws = sk_smem;                 // [NB][K]
+    float* red = sk_smem + NB * K;       // [128][NB]
+    const int tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * NB;
+    const int kq_per_row = K >> 2;
+    for (int i = tid; i < NB * kq_per_row; i += 256) {
+        const int n = i / kq_per_row, kq = i - n * kq_per_row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + n < p.N) v = __ldg(reinterpret_cast<const float4*>(p.W + (n0 + n) * p.ldw) + kq);
+        reinterpret_cast<float4*>(Ws + n * K)[kq] = v;
+    }
+    __syncthreads();
+    const int m = tid & 127, half = tid >> 7;
+    const int kh = K >> 1;
+    float acc[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) acc[n] = 0.f;
+    if (m < M) {
+        const float4* a = reinterpret_cast<const float4*>(p.A + (int64_t)m * p.lda + half * kh);
+        const float4* a2 = p.A2 ? reinterpret_cast<const float4*>(p.A2 + (int64_t)m * p.lda + half * kh) : nullptr;
+        const float* w = Ws + half * kh;
+#pragma unroll 4
+        for (int k4 = 0; k4 < (kh >> 2); ++k4) {
+            float4 av = __ldg(a + k4);
+            if (a2) {
+                const float4 u = __ldg(a2 + k4);
+                av.x += u.x; av.y += u.y; av.z += u.z; av.w += u.w;
+            }
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + n * K + 4 * k4);
+                acc[n] = fmaf(av.x, wv.x, acc[n]);
+                acc[n] = fmaf(av.y, wv.y, acc[n]);
+                acc[n] = fmaf(av.z, wv.z, acc[n]);
+                acc[n] = fmaf(av.w, wv.w, acc[n]);
+            }
+        }
+    }
+    if (half == 1) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n) red[m * NB + n] = acc[n];
+    }
+    __syncthreads();
+    if (half == 0 && m < M) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            if (n0 + n >= p.N) break;
+            float v = acc[n] + red[m * NB + n];
+            if (p.bias) v += __ldg(p.bias + n0 + n);
+            if (p.R) v += __ldg(p.R + (int64_t)m * p.ldr + n0 + n);
+            if (p.act == PVSG_ACT_RELU) v = fmaxf(v, 0.f);
+            p.C[(int64_t)m * p.ldc + n0 + n] = v;
+        }
+    }
+}
+
+template <int NB>
+int launch_skinny(const GemmParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)NB * p.K + 128 * NB);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return PVSG_ERR_LAUNCH;
+        configured = smem;
+    }
+    skinny_kernel<NB><<<(unsigned)((p.N + NB - 1) / NB), 256, smem, st>>>(p);
+    return pvsg_launch_status();
+}
+
 }  // namespace
 
 extern "C" int pvsg_linear(const float* A, const float* A2, const float* W, const float* bias,
@@ -322,6 +401,11 @@ extern "C" int pvsg_linear(const float* A, const float* A2, const float* W, cons
     p.sA = sA; p.sW = sW; p.sC = sC; p.act = act;
     const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldw % 4 == 0) && (sA % 4 == 0) &&
                      (sW % 4 == 0) && aligned16(A) && aligned16(W) && (!A2 || aligned16(A2));
+    if (vec && M <= 128 && batch == 1 && K % 8 == 0 && K <= 4096) {
+        // 8 columns per CTA once that still gives ~1 CTA per SM, else 4 (more CTAs, shorter chains)
+        return (N >= 1024 && (size_t)K * 8 * 4 <= 200 * 1024) ? launch_skinny<8>(p, as_stream(stream))
+                                                              : launch_skinny<4>(p, as_stream(stream));
+    }
     return vec ? dispatch<true, false>(p, batch, as_stream(stream))
                : dispatch<false, false>(p, batch, as_stream(stream));
 }

@@ -1,16 +1,21 @@
 """CUDA-graph frame runner for the VPS detector.
 
 A frame's device work (backbone -> pixel decoder -> 9 decoder layers -> fused panoptic /
-instance post-processing, ~500 kernel launches) has static shapes, no host round trip
+instance post-processing, ~350 kernel launches) has static shapes, no host round trip
 and allocates only through torch's caching allocator, so it is captured once per input
-shape into one CUDA graph and replayed per frame: the launch-bound decoder stops paying
-Python + launch latency.
+shape into one CUDA graph and replayed: the launch-bound decoder stops paying Python +
+launch latency.
 
-Per frame the host does: one H2D copy into the static input buffer, one graph launch,
+Throughput mode: ``batch`` frames are pushed through the network together.  Frames stay
+independent work items (clip length 1: the batch axis of every kernel is the frame axis), but
+the latency-bound part of the path -- the decoder's 100-query chains, ~250 small launches per
+pass -- is amortised over the batch and the tcgen05 GEMMs get more tiles per launch.
+
+Per batch the host does: H2D copies into the static input buffer, one graph launch,
 asynchronous D2H copies of the fixed-size outputs into a ring of pinned host buffers, and
-an event record.  ``submit`` returns immediately; ``collect`` waits for that frame's event
-and builds the reference's result dict, so the host-side work of frame i overlaps the
-device work of frame i+1 (``Mask2FormerVideoCustom.simple_test`` = submit + collect).
+an event record.  ``submit`` returns immediately; ``collect`` waits for that batch's event
+and builds the reference's result dicts, so the host-side work of batch i overlaps the
+device work of batch i+1 (``Mask2FormerVideoCustom.simple_test`` = submit + collect, batch 1).
 """
 import numpy as np
 import torch
@@ -23,57 +28,62 @@ TOPK_INS = 10   # models/mask2former_vps/mask2former.py:192-195 keeps the 10 bes
 
 
 class _Pending:
-    __slots__ = ('slot', 'event')
+    __slots__ = ('slot', 'event', 'n')
 
-    def __init__(self, slot, event):
-        self.slot, self.event = slot, event
+    def __init__(self, slot, event, n):
+        self.slot, self.event, self.n = slot, event, n
 
 
 class FrameRunner:
     """Captured per (H, W) frame shape for a ``Mask2FormerVideoCustom`` (clip length 1)."""
 
-    def __init__(self, detector, meta, rescale=True):
+    def __init__(self, detector, meta, rescale=True, batch=1):
         self.det = detector
         self.meta = dict(meta)
         self.rescale = rescale
+        self.batch = int(batch)
         dev = next(detector.parameters()).device
         self.dev = dev
         hp, wp = meta['batch_input_shape']
-        self.static_in = torch.zeros(1, 3, hp, wp, device=dev, dtype=torch.float32)
+        self.static_in = torch.zeros(self.batch, 3, hp, wp, device=dev, dtype=torch.float32)
         self.graph = None
         self.out = None
         self.launches_per_frame = 0
         self._capture()
-        self.host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.out.items()}
-                     for _ in range(RING)]
+        self.host = [[{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in o.items()}
+                      for o in self.out] for _ in range(RING)]
         self.events = [torch.cuda.Event() for _ in range(RING)]
         self.next_slot = 0
 
     @torch.no_grad()
     def _device_forward(self):
-        det, meta = self.det, self.meta
+        det, meta, B = self.det, self.meta, self.batch
         feats = det.extract_feat(self.static_in)
-        cls, mask_lr, query = det.panoptic_head.simple_test_with_query(feats, [[meta]], upsample=False)
+        cls, mask_lr, query = det.panoptic_head.simple_test_with_query(feats, [[meta]] * B, upsample=False)
         fh = det.panoptic_fusion_head
         in_hw = tuple(meta['batch_input_shape'])
         img_hw = tuple(meta['img_shape'][:2])
         out_hw = tuple(meta['ori_shape'][:2]) if self.rescale else img_hw
-        out = dict(query=query[:, 0].contiguous())
-        if fh.test_cfg.get('panoptic_on', True):
-            out['pan'], out['seg_info'] = fh._panoptic(cls[0], mask_lr[0, 0], in_hw, img_hw, out_hw)
-        if fh.test_cfg.get('instance_on', False):
-            d = fh._instance_device(cls[0], mask_lr[0, 0], in_hw, img_hw, out_hw, True)
-            # static-shape version of the detector's top-10 selection (mask2former.py:183-201)
-            is_thing = d['labels'] < det.num_things_classes
-            det_scores = d['scores'] * d['stats'][:, 0] / (d['stats'][:, 1] + 1e-6)
-            det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
-            ids = torch.cumsum(is_thing.to(torch.float32), 0)   # 1-based rank among thing candidates
-            inds = torch.argsort(det_scores, descending=True)[:TOPK_INS]
-            out['ins_boxes'] = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
-            out['ins_labels'] = d['labels'][inds].to(torch.int32)
-            out['ins_count'] = is_thing.sum().to(torch.int32).reshape(1)
-            out['ins_masks'] = d['masks'][inds]
-        return out
+        outs = []
+        for b in range(B):
+            out = dict(query=query[:, b].contiguous())
+            mlr = mask_lr[b, 0].contiguous()
+            if fh.test_cfg.get('panoptic_on', True):
+                out['pan'], out['seg_info'] = fh._panoptic(cls[b], mlr, in_hw, img_hw, out_hw)
+            if fh.test_cfg.get('instance_on', False):
+                d = fh._instance_device(cls[b], mlr, in_hw, img_hw, out_hw, True)
+                # static-shape version of the detector's top-10 selection (mask2former.py:183-201)
+                is_thing = d['labels'] < det.num_things_classes
+                det_scores = d['scores'] * d['stats'][:, 0] / (d['stats'][:, 1] + 1e-6)
+                det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
+                ids = torch.cumsum(is_thing.to(torch.float32), 0)   # 1-based rank among thing candidates
+                inds = torch.argsort(det_scores, descending=True)[:TOPK_INS]
+                out['ins_boxes'] = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
+                out['ins_labels'] = d['labels'][inds].to(torch.int32)
+                out['ins_count'] = is_thing.sum().to(torch.int32).reshape(1)
+                out['ins_masks'] = d['masks'][inds]
+            outs.append(out)
+        return outs
 
     def _capture(self):
         s = torch.cuda.Stream()
@@ -87,50 +97,61 @@ class FrameRunner:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._device_forward()
-        self.launches_per_frame = _l.launch_count[0] - n0
+        self.launches_per_frame = (_l.launch_count[0] - n0) / self.batch
 
     @torch.no_grad()
-    def submit(self, img):
-        """img [1,3,H,W] / [3,H,W], device or pinned host tensor.  Enqueues H2D, the graph and
-        the D2H of its outputs; returns a handle for ``collect``."""
+    def submit(self, imgs):
+        """imgs: one frame ([1,3,H,W] / [3,H,W]) or a list of up to ``batch`` frames, device or
+        pinned host tensors.  Enqueues H2D, the graph and the D2H of its outputs; returns a handle
+        for ``collect``.  A short final batch is padded by repeating its last frame."""
+        if torch.is_tensor(imgs):
+            imgs = [imgs]
+        n = len(imgs)
+        if not 0 < n <= self.batch:
+            raise ValueError(f'submit: expected 1..{self.batch} frames, got {n}')
         slot = self.next_slot
         self.next_slot = (slot + 1) % RING
-        self.static_in.copy_(img.reshape(self.static_in.shape), non_blocking=True)
+        for b in range(self.batch):
+            self.static_in[b].copy_(imgs[min(b, n - 1)].reshape(self.static_in.shape[1:]), non_blocking=True)
         self.graph.replay()
-        hb = self.host[slot]
-        for k, v in self.out.items():
-            hb[k].copy_(v, non_blocking=True)
+        for b in range(n):
+            hb = self.host[slot][b]
+            for k, v in self.out[b].items():
+                hb[k].copy_(v, non_blocking=True)
         self.events[slot].record()
-        return _Pending(slot, self.events[slot])
+        return _Pending(slot, self.events[slot], n)
 
     @torch.no_grad()
     def collect(self, pending, copy=True):
-        """Wait for a submitted frame and build the reference's per-frame result dict
-        (models/mask2former_vps/mask2former.py:172-211).  ``copy=False`` returns views of the
-        pinned ring buffers (valid until RING-1 further submits)."""
+        """Wait for a submitted batch and build the reference's per-frame result dicts
+        (models/mask2former_vps/mask2former.py:172-211): a list with one dict per submitted frame.
+        ``copy=False`` returns views of the pinned ring buffers (valid until RING-1 further submits)."""
         pending.event.synchronize()
-        hb = self.host[pending.slot]
         det = self.det
         fh = det.panoptic_fusion_head
-        res = {}
         own = (lambda a: a.copy()) if copy else (lambda a: a)
-        if 'pan' in hb:
-            res['pan_results'] = own(hb['pan'].numpy())
-            query = hb['query'].clone() if copy else hb['query']
-            res['query_feats'] = fh._query_dict(hb['seg_info'].numpy(), query)
-        if 'ins_boxes' in hb:
-            n = min(TOPK_INS, int(hb['ins_count'][0]))
-            labels = hb['ins_labels'][:n]
-            bbox_results = bbox2result(hb['ins_boxes'][:n], labels, det.num_things_classes)
-            masks_np = hb['ins_masks'][:n].numpy()
-            mask_results = [[] for _ in range(det.num_things_classes)]
-            for j, label in enumerate(labels.tolist()):
-                mask_results[label].append(own(masks_np[j]).view(np.bool_))
-            res['ins_results'] = bbox_results, mask_results
-        return res
+        results = []
+        for b in range(pending.n):
+            hb = self.host[pending.slot][b]
+            res = {}
+            if 'pan' in hb:
+                res['pan_results'] = own(hb['pan'].numpy())
+                query = hb['query'].clone() if copy else hb['query']
+                res['query_feats'] = fh._query_dict(hb['seg_info'].numpy(), query)
+            if 'ins_boxes' in hb:
+                n = min(TOPK_INS, int(hb['ins_count'][0]))
+                labels = hb['ins_labels'][:n]
+                bbox_results = bbox2result(hb['ins_boxes'][:n], labels, det.num_things_classes)
+                masks_np = hb['ins_masks'][:n].numpy()
+                mask_results = [[] for _ in range(det.num_things_classes)]
+                for j, label in enumerate(labels.tolist()):
+                    mask_results[label].append(own(masks_np[j]).view(np.bool_))
+                res['ins_results'] = bbox_results, mask_results
+            results.append(res)
+        return results
 
     def run(self, img):
-        return self.collect(self.submit(img))
+        return self.collect(self.submit(img))[0]
 
 
 def enable_cuda_graph(detector):
@@ -139,9 +160,10 @@ def enable_cuda_graph(detector):
     return detector
 
 
-def get_runner(detector, meta, rescale=True):
-    key = (tuple(meta['batch_input_shape']), tuple(meta['img_shape']), tuple(meta['ori_shape']), bool(rescale))
+def get_runner(detector, meta, rescale=True, batch=1):
+    key = (tuple(meta['batch_input_shape']), tuple(meta['img_shape']), tuple(meta['ori_shape']), bool(rescale),
+           int(batch))
     runners = detector._runners
     if key not in runners:
-        runners[key] = FrameRunner(detector, meta, rescale)
+        runners[key] = FrameRunner(detector, meta, rescale, batch)
     return runners[key]

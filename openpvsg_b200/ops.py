@@ -51,6 +51,7 @@ def _rows(t, name):
 # library's CUDA kernels -- this is not a fallback to another backend.
 # ----------------------------------------------------------------------------------------
 ENGINE = [os.environ.get('PVSG_ENGINE', 'tc')]
+SKINNY_M = 128   # rows at or below which linear() uses the skinny SIMT kernel instead of tcgen05
 _wplanes = {}
 
 
@@ -125,7 +126,7 @@ def maybe_split(x, add=None):
     """Split planes of x (+ add) when the tcgen05 engine is active and the shape qualifies, else None."""
     if isinstance(x, Split):
         return x
-    if ENGINE[0] == 'tc' and x.shape[-1] % 64 == 0 and x.is_contiguous():
+    if ENGINE[0] == 'tc' and x.shape[-1] % 64 == 0 and x.is_contiguous() and x.numel() // x.shape[-1] > SKINNY_M:
         return Split(*split_bf16(x, add))
     return None
 
@@ -173,7 +174,10 @@ def linear(x, weight, bias=None, add_input=None, residual=None, act=ACT_NONE, ou
     x2, M, K, lda = _rows(x, 'x')
     if Kw != K:
         raise _l.PvsgError(f'linear: K mismatch {K} vs {Kw}')
-    if _tc_ok(K, K) and x2.is_contiguous() and (add_input is None or add_input.is_contiguous()):
+    # M <= 128 (the decoder's 100-query chains) goes to the latency-optimised skinny SIMT kernel
+    # inside pvsg_linear: exact fp32, (x + pos) / bias / residual / ReLU fused, no split pass
+    skinny = M <= SKINNY_M and K <= 512 and N <= 512   # measured: beyond that the tcgen05 kernel wins again
+    if not skinny and _tc_ok(K, K) and x2.is_contiguous() and (add_input is None or add_input.is_contiguous()):
         planes = Split(*split_bf16(x2, None if add_input is None else add_input.reshape(M, K)))
         return _linear_tc(lib, planes, w2, bias, residual, act, out, lead, M, N, K, out_mode)
     a2 = None
@@ -347,7 +351,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, out_split=False):
     C = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
-    if out_split and ENGINE[0] == 'tc' and C % 64 == 0:
+    if out_split and ENGINE[0] == 'tc' and C % 64 == 0 and x.numel() // C > SKINNY_M:
         hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
         lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
         _l.check(lib.pvsg_layernorm_split(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), _ptr(hi), _ptr(lo),

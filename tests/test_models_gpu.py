@@ -195,6 +195,38 @@ def test_full_frame_vs_oracle_golden(detectors, cuda, golden_dir, name):
     assert sorted(res['query_feats']) == g['keys'].tolist()
 
 
+def test_batched_runner_matches_single_frames(detectors, cuda):
+    """engine.FrameRunner with batch=3 (throughput mode, CUDA graph, pinned result ring) gives
+    frame-for-frame the same results as the reference-style per-frame call."""
+    from openpvsg_b200 import engine
+    dets, sd = detectors
+    det = dets[True]
+    H, W = 96, 160
+    meta = syn.frame_meta(H, W)
+    frames = [syn.synthetic_frame(60 + i, H, W) for i in range(5)]
+    singles = [det.simple_test(None, None, ref_img=f[None, None].to(cuda), ref_img_metas=[[meta]], rescale=True)[0][0]
+               for f in frames]
+    engine.enable_cuda_graph(det)
+    try:
+        runner = engine.get_runner(det, meta, True, batch=3)
+        got = []
+        p1 = runner.submit([f.pin_memory() for f in frames[:3]])
+        p2 = runner.submit([f.to(cuda) for f in frames[3:]])        # short final batch
+        got += runner.collect(p1)
+        got += runner.collect(p2)
+        # and the per-frame API through the graph path (batch 1)
+        g1 = det.simple_test(None, None, ref_img=frames[0][None, None].to(cuda), ref_img_metas=[[meta]], rescale=True)[0][0]
+    finally:
+        det._runners = None
+    assert len(got) == 5
+    for a, b in zip(got + [g1], singles + [singles[0]]):
+        assert np.array_equal(a['pan_results'], b['pan_results'])
+        assert sorted(a['query_feats']) == sorted(b['query_feats'])
+        for k in b['query_feats']:
+            close(torch.as_tensor(a['query_feats'][k][0]), torch.as_tensor(b['query_feats'][k][0]), 1e-4, 'query feat')
+        assert [len(x) for x in a['ins_results'][0]] == [len(x) for x in b['ins_results'][0]]
+
+
 def test_minvis_clip_vs_oracle(cuda):
     """Mask2FormerVideoCustomMinVIS on a 3-frame clip: MinVIS query permutations (the tube-linking
     step, mask2former_min_vis.py:244-258) and per-frame panoptic ids vs the oracle."""
