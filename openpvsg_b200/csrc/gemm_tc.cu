@@ -7,7 +7,8 @@
 // accumulated in the same TMEM tile:  hi.hi + hi.lo + lo.hi  (the dropped lo.lo term and
 // the residual of the split are ~2^-17 relative, i.e. fp32 re-association level).
 //
-// Persistent kernel, one CTA per SM, 192 threads, tiles of 128 x 128 handed out round-robin:
+// Persistent kernel, one CTA per SM, 576 threads, tiles of 128 x 128 (or 128 x 256) handed out
+// round-robin:
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B swizzle) of A_hi, A_lo, W_hi, W_lo
 //              k-blocks of 64 into a 3-stage shared-memory ring (mbarrier complete_tx); runs
 //              ahead across tile boundaries
@@ -15,9 +16,9 @@
 //              (kind::f16, bf16 x bf16 -> fp32, M = 128, N = 128, K = 16) x 3 x 4 per stage into
 //              one of TWO TMEM accumulators; tcgen05.commit releases the stage / publishes
 //              the accumulator
-//   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory
-//              transpose -> coalesced bias / residual / ReLU / fp32, split-bf16 or sign-mask
-//              stores; overlaps the next tile's main loop through the second accumulator
+//   warps 2-17: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), bias / residual / ReLU,
+//              128-bit fp32, split-bf16 or sign-mask stores; overlaps the next tile's main loop
+//              through the second accumulator
 // Convolutions use a 4-D tensor map over the NHWC planes: the M tile is an 8 x 16 patch of
 // output pixels and every filter tap is the same TMA box shifted by (r - pad, s - pad); TMA's
 // out-of-bounds zero fill is the convolution's zero padding.  No im2col buffer exists.
@@ -29,18 +30,27 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
 constexpr int BK = 64;             // bf16 elements = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 16;          // four column groups x four TMEM lane quarters
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int PATCH_H = 8, PATCH_W = 16;   // conv M tile = 8 x 16 output pixels
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-constexpr int B_BYTES = BN * BK * 2;        // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-constexpr int EPI_LD = 33;                  // padded row of the per-warp transpose buffer
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
-constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
-constexpr int TMEM_COLS = 2 * BN;
+// Tile width BN = 128 (3-stage ring) or 256 (2-stage ring).  The wide tile reads each A k-block
+// once per 256 output columns instead of once per 128: the engine is L2->SM bandwidth bound
+// (four bf16 planes per k-block), so operand bytes per flop, not MMA issue, set its speed.
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = BN == 128 ? 3 : 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    // weight-resident mode (K <= 256, BN = 128): all of W's k-blocks stay in shared memory for the
+    // CTA's lifetime (RES_KB x 32 KB) and only A streams through a ring of 32 KB stages
+    static constexpr int RES_KB = 4;
+    static constexpr int RES_BYTES = BN == 128 ? RES_KB * 2 * B_BYTES + STAGES * 2 * A_BYTES : 0;
+    static constexpr int DATA_BYTES = STAGES * STAGE_BYTES > RES_BYTES ? STAGES * STAGE_BYTES : RES_BYTES;
+    static constexpr int SMEM_TOTAL = DATA_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int TMEM_COLS = 2 * BN;   // two accumulators
+};
 
 struct TcParams {
     const float* bias;
@@ -54,6 +64,7 @@ struct TcParams {
     int num_kb;
     int act;
     int tiles_m, tiles_n;
+    int bres;   // weight-resident mode: a CTA keeps one 128-column slice of W and walks M tiles
     // conv mode
     int conv, OH, OW, cin_kb, S, pad, stride, tiles_h, tiles_w;
 };
@@ -146,11 +157,24 @@ struct Tile {
     int tb, oh0, ow0; // conv mode
 };
 
-__device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
+// i-th tile of this CTA: round-robin over all tiles, or (weight-resident) a fixed column slice
+__device__ __forceinline__ bool next_tile(const TcParams& p, int i, int& mt, int& nt) {
+    if (p.bres) {
+        const int per = gridDim.x / p.tiles_n;
+        nt = blockIdx.x % p.tiles_n;
+        mt = blockIdx.x / p.tiles_n + i * per;
+        return mt < p.tiles_m;
+    }
+    const int64_t t = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+    if (t >= (int64_t)p.tiles_m * p.tiles_n) return false;
+    nt = (int)(t % p.tiles_n);
+    mt = (int)(t / p.tiles_n);
+    return true;
+}
+
+__device__ __forceinline__ Tile decode_tile(const TcParams& p, int mt, int nt, int bn) {
     Tile tl;
-    const int nt = t % p.tiles_n;
-    int mt = t / p.tiles_n;
-    tl.n0 = nt * BN;
+    tl.n0 = nt * bn;
     tl.m0 = (int64_t)mt * BM;
     tl.tb = tl.oh0 = tl.ow0 = 0;
     if (p.conv) {
@@ -164,26 +188,32 @@ __device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
     return tl;
 }
 
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+    constexpr int STAGES = Cfg<BN>::STAGES, B_BYTES = Cfg<BN>::B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
+    constexpr int RING_RES = Cfg<BN>::RES_KB * 2 * B_BYTES;   // weight-resident mode: ring starts here
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg<BN>::DATA_BYTES);
     uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* w_full = acc_empty + 2;         // [1]       resident W landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int stage_bytes = p.bres ? 2 * A_BYTES : STAGE_BYTES;
+    uint8_t* ring = smem + (p.bres ? RING_RES : 0);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
+        mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: two 128-column fp32 accumulators x 128 lanes
@@ -200,14 +230,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ------------------------------ TMA producer ------------------------------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const Tile tl = decode_tile(p, t);
+            int mt, nt;
+            if (p.bres && next_tile(p, 0, mt, nt)) {
+                mbar_expect_tx(w_full, p.num_kb * 2 * B_BYTES);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    tma_load_2d(&tmB_hi, w_full, smem + kb * 2 * B_BYTES, kb * BK, nt * BN);
+                    tma_load_2d(&tmB_lo, w_full, smem + kb * 2 * B_BYTES + B_BYTES, kb * BK, nt * BN);
+                }
+            }
+            for (int i = 0; next_tile(p, i, mt, nt); ++i) {
+                const Tile tl = decode_tile(p, mt, nt, BN);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    uint8_t* st = ring + s * stage_bytes;
+                    mbar_expect_tx(&full[s], stage_bytes);
                     if (p.conv) {
                         const int rs = kb / p.cin_kb, cb = kb - rs * p.cin_kb;
                         const int r = rs / p.S, sx = rs - r * p.S;
@@ -218,8 +256,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         tma_load_2d(&tmA_hi, &full[s], st, kb * BK, (int)tl.m0);
                         tma_load_2d(&tmA_lo, &full[s], st + A_BYTES, kb * BK, (int)tl.m0);
                     }
-                    tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
-                    tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
+                    if (!p.bres) {
+                        tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
+                        tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
+                    }
                 }
             }
         }
@@ -230,7 +270,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
             uint32_t it = 0, ti = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+            int mt, nt;
+            if (p.bres && next_tile(p, 0, mt, nt)) mbar_wait(w_full, 0);
+            for (; next_tile(p, (int)ti, mt, nt); ++ti) {
                 const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -240,9 +282,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t a_hi = smem_u32(ring + s * stage_bytes);
                     const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
+                    const uint32_t b_hi = p.bres ? smem_u32(smem + kb * 2 * B_BYTES) : a_hi + 2 * A_BYTES;
                     const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
@@ -259,12 +301,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
         }
     } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-        // thread = one accumulator row; 32 columns per tcgen05.ld; 128-bit global accesses
+        // ---------------- epilogue: warps 2..17, TMEM lane quarter = warp % 4 --------------
+        // thread = one accumulator row; 32 columns per tcgen05.ld; 128-bit global accesses.  The
+        // four warps of a lane quarter interleave the tile's 32-column chunks: with short K the
+        // epilogue, not the MMA loop, bounds a tile, and its latency needs warps to hide behind.
         const int q = warp & 3;
+        const int part = (warp - 2) >> 2;
         uint32_t ti = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-            const Tile tl = decode_tile(p, t);
+        int mt, nt;
+        for (; next_tile(p, (int)ti, mt, nt); ++ti) {
+            const Tile tl = decode_tile(p, mt, nt, BN);
             const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -281,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             int open = 0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = part * 32; c0 < BN; c0 += (EPI_WARPS / 4) * 32) {
                 const int64_t n = (int64_t)tl.n0 + c0;
                 if (n >= p.N) break;                                  // warp-uniform
                 uint32_t v[32];
@@ -519,19 +565,34 @@ bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, in
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int BN>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
               const TcParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) !=
-            cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg<BN>::SMEM_TOTAL) != cudaSuccess)
             return PVSG_ERR_LAUNCH;
         configured = true;
     }
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-    const unsigned grid = (unsigned)imin64(tiles, sm_count());
-    gemm_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    unsigned grid = (unsigned)imin64(tiles, sm_count());
+    TcParams q = p;
+    static const bool no_res = getenv("PVSG_TC_NORES") != nullptr;
+    q.bres = (BN == 128 && !no_res && p.num_kb <= Cfg<BN>::RES_KB && (unsigned)p.tiles_n <= grid) ? 1 : 0;
+    if (q.bres) grid = grid / p.tiles_n * p.tiles_n;     // whole groups of column slices
+    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, q);
     return pvsg_launch_status();
+}
+
+// Wide tiles when they add no padding along N and still leave >= 4 tiles per SM (wave quantisation).
+int pick_bn(int64_t tiles_m, int64_t N, int num_kb) {
+    static const int forced = [] { const char* e = getenv("PVSG_TC_BN"); return e ? atoi(e) : 0; }();
+    if (forced == 128 || forced == 256) return forced;
+    if (num_kb <= Cfg<128>::RES_KB) return 128;          // weight-resident mode
+    const int64_t t256 = (N + 255) / 256;
+    if (t256 * 256 != ((N + 127) / 128) * 128) return 128;
+    return tiles_m * t256 >= 4 * (int64_t)sm_count() ? 256 : 128;
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -569,19 +630,21 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N));
     if (K % BK != 0 || lda % 8 != 0 || ldw % 8 != 0 || !al16(A_hi) || !al16(A_lo) || !al16(W_hi) || !al16(W_lo))
         return PVSG_ERR_UNSUPPORTED;
-    if (M > 0x7fffffffLL || N > 0x7fffffffLL || ((M + BM - 1) / BM) * ((N + BN - 1) / BN) > 0x7fffffffLL)
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || ((M + BM - 1) / BM) * ((N + 127) / 128) > 0x7fffffffLL)
         return PVSG_ERR_UNSUPPORTED;
+    const int bn = pick_bn((M + BM - 1) / BM, N, (int)(K / BK));
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_map_2d(&ta_hi, A_hi, M, K, lda, BM) || !make_map_2d(&ta_lo, A_lo, M, K, lda, BM) ||
-        !make_map_2d(&tb_hi, W_hi, N, K, ldw, BN) || !make_map_2d(&tb_lo, W_lo, N, K, ldw, BN))
+        !make_map_2d(&tb_hi, W_hi, N, K, ldw, bn) || !make_map_2d(&tb_lo, W_lo, N, K, ldw, bn))
         return PVSG_ERR_LAUNCH;
     TcParams p{};
     p.bias = bias; p.R = R; p.C = C;
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
-    p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
-    return launch_tc(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
+    p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + bn - 1) / bn);
+    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream))
+                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
 }
 
 extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
@@ -595,18 +658,21 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
     const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
     PVSG_CHECK_ARG(OH > 0 && OW > 0);
     const int64_t K = (int64_t)R * S * Cin;
+    const int tiles_h = (OH + PATCH_H - 1) / PATCH_H, tiles_w = (OW + PATCH_W - 1) / PATCH_W;
+    const int64_t tiles_m = (int64_t)B * tiles_h * tiles_w;
+    const int bn = pick_bn(tiles_m, Cout, (int)(K / BK));
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_map_4d(&ta_hi, x_hi, B, H, W, Cin, stride) || !make_map_4d(&ta_lo, x_lo, B, H, W, Cin, stride) ||
-        !make_map_2d(&tb_hi, w_hi, Cout, K, K, BN) || !make_map_2d(&tb_lo, w_lo, Cout, K, K, BN))
+        !make_map_2d(&tb_hi, w_hi, Cout, K, K, bn) || !make_map_2d(&tb_lo, w_lo, Cout, K, K, bn))
         return PVSG_ERR_LAUNCH;
     TcParams p{};
     p.bias = bias; p.R = residual; p.C = y;
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
     p.M = (int64_t)B * OH * OW; p.N = Cout; p.ldc = Cout; p.ldr = Cout; p.act = act;
     p.num_kb = (int)(K / BK); p.conv = 1; p.OH = OH; p.OW = OW; p.cin_kb = Cin / BK; p.S = S; p.pad = pad; p.stride = stride;
-    p.tiles_h = (OH + PATCH_H - 1) / PATCH_H; p.tiles_w = (OW + PATCH_W - 1) / PATCH_W;
-    const int64_t tiles_m = (int64_t)B * p.tiles_h * p.tiles_w;
-    if (tiles_m * ((Cout + BN - 1) / BN) > 0x7fffffffLL) return PVSG_ERR_UNSUPPORTED;
-    p.tiles_m = (int)tiles_m; p.tiles_n = (Cout + BN - 1) / BN;
-    return launch_tc(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
+    p.tiles_h = tiles_h; p.tiles_w = tiles_w;
+    if (tiles_m * ((Cout + 127) / 128) > 0x7fffffffLL) return PVSG_ERR_UNSUPPORTED;
+    p.tiles_m = (int)tiles_m; p.tiles_n = (Cout + bn - 1) / bn;
+    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream))
+                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
 }
