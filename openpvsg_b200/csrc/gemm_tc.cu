@@ -31,8 +31,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;             // bf16 elements = 128 bytes = one swizzle row
-constexpr int EPI_WARPS = 16;          // four column groups x four TMEM lane quarters
+constexpr int EPI_WARPS = 4;
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_STAGE_BYTES = 8192;      // per epilogue warp: 32 x 32 fp32 | 32 x 32 bf16 hi | lo
 constexpr int PATCH_H = 8, PATCH_W = 16;   // conv M tile = 8 x 16 output pixels
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 // Tile width BN = 128 (3-stage ring) or 256 (2-stage ring).  The wide tile reads each A k-block
@@ -43,11 +44,7 @@ struct Cfg {
     static constexpr int STAGES = BN == 128 ? 3 : 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    // weight-resident mode (K <= 256, BN = 128): all of W's k-blocks stay in shared memory for the
-    // CTA's lifetime (RES_KB x 32 KB) and only A streams through a ring of 32 KB stages
-    static constexpr int RES_KB = 4;
-    static constexpr int RES_BYTES = BN == 128 ? RES_KB * 2 * B_BYTES + STAGES * 2 * A_BYTES : 0;
-    static constexpr int DATA_BYTES = STAGES * STAGE_BYTES > RES_BYTES ? STAGES * STAGE_BYTES : RES_BYTES;
+    static constexpr int DATA_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
     static constexpr int SMEM_TOTAL = DATA_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
     static constexpr int TMEM_COLS = 2 * BN;   // two accumulators
 };
@@ -64,7 +61,7 @@ struct TcParams {
     int num_kb;
     int act;
     int tiles_m, tiles_n;
-    int bres;   // weight-resident mode: a CTA keeps one 128-column slice of W and walks M tiles
+    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do
     // conv mode
     int conv, OH, OW, cin_kb, S, pad, stride, tiles_h, tiles_w;
 };
@@ -102,6 +99,21 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 v4u(float a, float b, float c, float d) {
+    return make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -157,14 +169,8 @@ struct Tile {
     int tb, oh0, ow0; // conv mode
 };
 
-// i-th tile of this CTA: round-robin over all tiles, or (weight-resident) a fixed column slice
+// i-th tile of this CTA: round-robin over all tiles
 __device__ __forceinline__ bool next_tile(const TcParams& p, int i, int& mt, int& nt) {
-    if (p.bres) {
-        const int per = gridDim.x / p.tiles_n;
-        nt = blockIdx.x % p.tiles_n;
-        mt = blockIdx.x / p.tiles_n + i * per;
-        return mt < p.tiles_m;
-    }
     const int64_t t = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
     if (t >= (int64_t)p.tiles_m * p.tiles_n) return false;
     nt = (int)(t % p.tiles_n);
@@ -191,29 +197,26 @@ __device__ __forceinline__ Tile decode_tile(const TcParams& p, int mt, int nt, i
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC_hi,
+               const __grid_constant__ CUtensorMap tmC_lo, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int STAGES = Cfg<BN>::STAGES, B_BYTES = Cfg<BN>::B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
     constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
-    constexpr int RING_RES = Cfg<BN>::RES_KB * 2 * B_BYTES;   // weight-resident mode: ring starts here
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg<BN>::DATA_BYTES);
     uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
-    uint64_t* w_full = acc_empty + 2;         // [1]       resident W landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stage_bytes = p.bres ? 2 * A_BYTES : STAGE_BYTES;
-    uint8_t* ring = smem + (p.bres ? RING_RES : 0);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
-        mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: two 128-column fp32 accumulators x 128 lanes
@@ -231,21 +234,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             uint32_t it = 0;
             int mt, nt;
-            if (p.bres && next_tile(p, 0, mt, nt)) {
-                mbar_expect_tx(w_full, p.num_kb * 2 * B_BYTES);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    tma_load_2d(&tmB_hi, w_full, smem + kb * 2 * B_BYTES, kb * BK, nt * BN);
-                    tma_load_2d(&tmB_lo, w_full, smem + kb * 2 * B_BYTES + B_BYTES, kb * BK, nt * BN);
-                }
-            }
             for (int i = 0; next_tile(p, i, mt, nt); ++i) {
                 const Tile tl = decode_tile(p, mt, nt, BN);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* st = ring + s * stage_bytes;
-                    mbar_expect_tx(&full[s], stage_bytes);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
                     if (p.conv) {
                         const int rs = kb / p.cin_kb, cb = kb - rs * p.cin_kb;
                         const int r = rs / p.S, sx = rs - r * p.S;
@@ -256,10 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         tma_load_2d(&tmA_hi, &full[s], st, kb * BK, (int)tl.m0);
                         tma_load_2d(&tmA_lo, &full[s], st + A_BYTES, kb * BK, (int)tl.m0);
                     }
-                    if (!p.bres) {
-                        tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
-                        tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
-                    }
+                    tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
+                    tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
                 }
             }
         }
@@ -271,7 +265,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                    ((uint32_t)(BM >> 4) << 24);
             uint32_t it = 0, ti = 0;
             int mt, nt;
-            if (p.bres && next_tile(p, 0, mt, nt)) mbar_wait(w_full, 0);
             for (; next_tile(p, (int)ti, mt, nt); ++ti) {
                 const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);     // epilogue has drained this accumulator
@@ -282,9 +275,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi = smem_u32(ring + s * stage_bytes);
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
                     const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = p.bres ? smem_u32(smem + kb * 2 * B_BYTES) : a_hi + 2 * A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
                     const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
@@ -301,12 +294,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
         }
     } else {
-        // ---------------- epilogue: warps 2..17, TMEM lane quarter = warp % 4 --------------
-        // thread = one accumulator row; 32 columns per tcgen05.ld; 128-bit global accesses.  The
-        // four warps of a lane quarter interleave the tile's 32-column chunks: with short K the
-        // epilogue, not the MMA loop, bounds a tile, and its latency needs warps to hide behind.
+        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        // thread = one accumulator row, 32 columns per tcgen05.ld.  Row-per-thread 16-byte global
+        // stores reach only ~1.7 TB/s (every store instruction touches 32 lines), so fp32 and
+        // split-bf16 outputs are staged in swizzled shared memory and written by TMA as whole
+        // 32-row boxes (clipped to the matrix by the tensor map); unaligned outputs and the
+        // sign-mask bytes keep the direct path.
         const int q = warp & 3;
-        const int part = (warp - 2) >> 2;
+        uint8_t* stage = smem + STAGES * STAGE_BYTES + (warp - 2) * EPI_STAGE_BYTES;
+        const uint32_t st_f32 = smem_u32(stage), st_hi = st_f32 + 4096, st_lo = st_f32 + 6144;
+        const bool tma_c = (p.tma_out & 1) != 0, tma_p = (p.tma_out & 2) != 0;
         uint32_t ti = 0;
         int mt, nt;
         for (; next_tile(p, (int)ti, mt, nt); ++ti) {
@@ -327,12 +324,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             int open = 0;
 #pragma unroll 1
-            for (int c0 = part * 32; c0 < BN; c0 += (EPI_WARPS / 4) * 32) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int64_t n = (int64_t)tl.n0 + c0;
                 if (n >= p.N) break;                                  // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                if (!row_ok) continue;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -350,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
                     }
                 }
-                if (p.R) {
+                if (p.R && row_ok) {
                     const float* rr = p.R + out_row * p.ldr + n;
                     if (full_chunk && (p.ldr & 3) == 0) {
 #pragma unroll
@@ -368,23 +364,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
+                const bool use_tma = (p.C && tma_c) || (p.C_hi && tma_p);
+                if (use_tma) {
+                    // the previous chunk's boxes must have left shared memory before it is rewritten
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
                 if (p.C) {
-                    float* cc = p.C + out_row * p.ldc + n;
-                    if (full_chunk && (p.ldc & 3) == 0) {
+                    if (tma_c) {
+                        // 128-byte rows, 16-byte pieces XOR-swizzled by (row & 7): conflict-free
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            reinterpret_cast<float4*>(cc)[j] =
-                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
+                            sts_v4(st_f32 + lane * 128 + ((j ^ (lane & 7)) << 4), v4u(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    } else if (row_ok) {
+                        float* cc = p.C + out_row * p.ldc + n;
+                        if (full_chunk && (p.ldc & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n + j < p.N) cc[j] = f[j];
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<float4*>(cc)[j] =
+                                    make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n + j < p.N) cc[j] = f[j];
+                        }
                     }
                 }
                 if (p.C_hi) {
-                    __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
-                    __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
-                    if (full_chunk && (p.ldc & 7) == 0) {
+                    if (tma_p || (row_ok && full_chunk && (p.ldc & 7) == 0)) {
+                        __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
+                        __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t hw[4], lw[4];
@@ -397,10 +406,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                 hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                                 lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                             }
-                            reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            if (tma_p) {
+                                // 64-byte rows, 16-byte pieces XOR-swizzled by ((row >> 1) & 3)
+                                const uint32_t off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+                                sts_v4(st_hi + off, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                                sts_v4(st_lo + off, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+                            } else {
+                                reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
                         }
-                    } else {
+                    } else if (row_ok) {
+                        __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
+                        __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
                         for (int j = 0; j < 32; ++j) {
                             if (n + j < p.N) {
                                 const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
@@ -410,7 +428,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                     }
                 }
-                if (p.mask) {
+                if (use_tma) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int r0 = q * 32;
+                        if (p.conv) {
+                            const int oh = tl.oh0 + r0 / PATCH_W;
+                            if (p.C && tma_c) tma_store_4d(&tmC, st_f32, (int)n, tl.ow0, oh, tl.tb);
+                            if (p.C_hi && tma_p) {
+                                tma_store_4d(&tmC_hi, st_hi, (int)n, tl.ow0, oh, tl.tb);
+                                tma_store_4d(&tmC_lo, st_lo, (int)n, tl.ow0, oh, tl.tb);
+                            }
+                        } else {
+                            const int row0 = (int)(tl.m0 + r0);
+                            if (p.C && tma_c) tma_store_2d(&tmC, st_f32, (int)n, row0);
+                            if (p.C_hi && tma_p) {
+                                tma_store_2d(&tmC_hi, st_hi, (int)n, row0);
+                                tma_store_2d(&tmC_lo, st_lo, (int)n, row0);
+                            }
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (p.mask && row_ok) {
                     uint8_t* mm = p.mask + out_row * p.ldc + n;
                     if (full_chunk && (p.ldc & 15) == 0) {
                         uint32_t w[8];
@@ -442,6 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -565,9 +607,35 @@ bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, in
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Output maps for the TMA-store epilogue: one epilogue warp stores a box of 32 rows x 32 columns
+// (linear: 32 consecutive rows; conv: 2 x 16 output pixels), 128-byte (fp32) or 64-byte (bf16) rows.
+bool make_out_map(CUtensorMap* m, void* ptr, bool f32, const TcParams& p, int B) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t es = f32 ? 4 : 2;
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    cuuint32_t ones[4] = {1, 1, 1, 1};
+    if (p.conv) {
+        cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.ldc * es, (cuuint64_t)p.OW * p.ldc * es,
+                                 (cuuint64_t)p.OH * p.OW * p.ldc * es};
+        cuuint32_t box[4] = {32, (cuuint32_t)PATCH_W, (cuuint32_t)(32 / PATCH_W), 1};
+        return enc(m, dt, 4, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+    cuuint64_t strides[1] = {(cuuint64_t)p.ldc * es};
+    cuuint32_t box[2] = {32, 32};
+    return enc(m, dt, 2, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <int BN>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-              const TcParams& p, cudaStream_t st) {
+              const TcParams& p, int B, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -576,26 +644,27 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
         configured = true;
     }
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-    unsigned grid = (unsigned)imin64(tiles, sm_count());
+    const unsigned grid = (unsigned)imin64(tiles, sm_count());
     TcParams q = p;
-    static const bool no_res = getenv("PVSG_TC_NORES") != nullptr;
-    q.bres = (BN == 128 && !no_res && p.num_kb <= Cfg<BN>::RES_KB && (unsigned)p.tiles_n <= grid) ? 1 : 0;
-    if (q.bres) grid = grid / p.tiles_n * p.tiles_n;     // whole groups of column slices
-    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, q);
+    static const bool direct = getenv("PVSG_TC_DIRECT_STORE") != nullptr;
+    CUtensorMap c{}, c_hi{}, c_lo{};
+    q.tma_out = 0;
+    if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B)) q.tma_out |= 1;
+    if (!direct && p.C_hi && p.ldc % 8 == 0 && al16(p.C_hi) && al16(p.C_lo) &&
+        make_out_map(&c_hi, p.C_hi, false, p, B) && make_out_map(&c_lo, p.C_lo, false, p, B))
+        q.tma_out |= 2;
+    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, q);
     return pvsg_launch_status();
 }
 
 // Wide tiles when they add no padding along N and still leave >= 4 tiles per SM (wave quantisation).
-int pick_bn(int64_t tiles_m, int64_t N, int num_kb) {
+int pick_bn(int64_t tiles_m, int64_t N) {
     static const int forced = [] { const char* e = getenv("PVSG_TC_BN"); return e ? atoi(e) : 0; }();
     if (forced == 128 || forced == 256) return forced;
-    if (num_kb <= Cfg<128>::RES_KB) return 128;          // weight-resident mode
     const int64_t t256 = (N + 255) / 256;
     if (t256 * 256 != ((N + 127) / 128) * 128) return 128;
     return tiles_m * t256 >= 4 * (int64_t)sm_count() ? 256 : 128;
 }
-
-inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
@@ -632,7 +701,7 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
         return PVSG_ERR_UNSUPPORTED;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || ((M + BM - 1) / BM) * ((N + 127) / 128) > 0x7fffffffLL)
         return PVSG_ERR_UNSUPPORTED;
-    const int bn = pick_bn((M + BM - 1) / BM, N, (int)(K / BK));
+    const int bn = pick_bn((M + BM - 1) / BM, N);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_map_2d(&ta_hi, A_hi, M, K, lda, BM) || !make_map_2d(&ta_lo, A_lo, M, K, lda, BM) ||
         !make_map_2d(&tb_hi, W_hi, N, K, ldw, bn) || !make_map_2d(&tb_lo, W_lo, N, K, ldw, bn))
@@ -643,8 +712,8 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
     p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + bn - 1) / bn);
-    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream))
-                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
+    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream))
+                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
 }
 
 extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
@@ -660,7 +729,7 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
     const int64_t K = (int64_t)R * S * Cin;
     const int tiles_h = (OH + PATCH_H - 1) / PATCH_H, tiles_w = (OW + PATCH_W - 1) / PATCH_W;
     const int64_t tiles_m = (int64_t)B * tiles_h * tiles_w;
-    const int bn = pick_bn(tiles_m, Cout, (int)(K / BK));
+    const int bn = pick_bn(tiles_m, Cout);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_map_4d(&ta_hi, x_hi, B, H, W, Cin, stride) || !make_map_4d(&ta_lo, x_lo, B, H, W, Cin, stride) ||
         !make_map_2d(&tb_hi, w_hi, Cout, K, K, bn) || !make_map_2d(&tb_lo, w_lo, Cout, K, K, bn))
@@ -673,6 +742,6 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
     p.tiles_h = tiles_h; p.tiles_w = tiles_w;
     if (tiles_m * ((Cout + 127) / 128) > 0x7fffffffLL) return PVSG_ERR_UNSUPPORTED;
     p.tiles_m = (int)tiles_m; p.tiles_n = (Cout + bn - 1) / bn;
-    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream))
-                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, as_stream(stream));
+    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, B, as_stream(stream))
+                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, B, as_stream(stream));
 }
