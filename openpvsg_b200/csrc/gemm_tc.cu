@@ -61,7 +61,7 @@ struct TcParams {
     int num_kb;
     int act;
     int tiles_m, tiles_n;
-    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do
+    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do, bit 2: R arrives by TMA
     // conv mode
     int conv, OH, OW, cin_kb, S, pad, stride, tiles_h, tiles_w;
 };
@@ -111,6 +111,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+                 : "memory");
+    return v;
 }
 __device__ __forceinline__ uint4 v4u(float a, float b, float c, float d) {
     return make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC_hi,
-               const __grid_constant__ CUtensorMap tmC_lo, TcParams p) {
+               const __grid_constant__ CUtensorMap tmC_lo, const __grid_constant__ CUtensorMap tmR, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int STAGES = Cfg<BN>::STAGES, B_BYTES = Cfg<BN>::B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -209,7 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* r_full = acc_empty + 2;         // [EPI_WARPS] residual box landed (per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -217,6 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
+        for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&r_full[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: two 128-column fp32 accumulators x 128 lanes
@@ -303,7 +311,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int q = warp & 3;
         uint8_t* stage = smem + STAGES * STAGE_BYTES + (warp - 2) * EPI_STAGE_BYTES;
         const uint32_t st_f32 = smem_u32(stage), st_hi = st_f32 + 4096, st_lo = st_f32 + 6144;
-        const bool tma_c = (p.tma_out & 1) != 0, tma_p = (p.tma_out & 2) != 0;
+        const bool tma_c = (p.tma_out & 1) != 0, tma_p = (p.tma_out & 2) != 0, tma_r = (p.tma_out & 4) != 0;
+        const bool use_tma = (p.C && tma_c) || (p.C_hi && tma_p);
+        uint64_t* my_r = &r_full[warp - 2];
+        uint32_t rph = 0;
         uint32_t ti = 0;
         int mt, nt;
         for (; next_tile(p, (int)ti, mt, nt); ++ti) {
@@ -327,6 +338,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int64_t n = (int64_t)tl.n0 + c0;
                 if (n >= p.N) break;                                  // warp-uniform
+                if (use_tma || tma_r) {
+                    // the previous chunk's boxes must have left the staging buffers before they are
+                    // rewritten (by the residual load below or by this chunk's results)
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (tma_r) {   // residual box -> fp32 staging buffer, consumed (and overwritten) in place
+                            mbar_expect_tx(my_r, 32 * 32 * 4);
+                            if (p.conv)
+                                tma_load_4d(&tmR, my_r, stage, (int)n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
+                            else
+                                tma_load_2d(&tmR, my_r, stage, (int)n, (int)(tl.m0 + q * 32));
+                        }
+                    }
+                    __syncwarp();
+                }
                 uint32_t v[32];
                 tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 float f[32];
@@ -346,7 +373,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
                     }
                 }
-                if (p.R && row_ok) {
+                if (tma_r) {
+                    mbar_wait(my_r, rph);
+                    rph ^= 1;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 t4 = lds_v4(st_f32 + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        f[4 * j] += __uint_as_float(t4.x); f[4 * j + 1] += __uint_as_float(t4.y);
+                        f[4 * j + 2] += __uint_as_float(t4.z); f[4 * j + 3] += __uint_as_float(t4.w);
+                    }
+                } else if (p.R && row_ok) {
                     const float* rr = p.R + out_row * p.ldr + n;
                     if (full_chunk && (p.ldr & 3) == 0) {
 #pragma unroll
@@ -363,12 +399,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (p.act == PVSG_ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                const bool use_tma = (p.C && tma_c) || (p.C_hi && tma_p);
-                if (use_tma) {
-                    // the previous chunk's boxes must have left shared memory before it is rewritten
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
                 }
                 if (p.C) {
                     if (tma_c) {
@@ -609,7 +639,8 @@ bool make_map_4d(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, in
 
 // Output maps for the TMA-store epilogue: one epilogue warp stores a box of 32 rows x 32 columns
 // (linear: 32 consecutive rows; conv: 2 x 16 output pixels), 128-byte (fp32) or 64-byte (bf16) rows.
-bool make_out_map(CUtensorMap* m, void* ptr, bool f32, const TcParams& p, int B) {
+bool make_out_map(CUtensorMap* m, const void* cptr, bool f32, const TcParams& p, int B, int64_t ld) {
+    void* ptr = const_cast<void*>(cptr);
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     const cuuint64_t es = f32 ? 4 : 2;
@@ -618,14 +649,14 @@ bool make_out_map(CUtensorMap* m, void* ptr, bool f32, const TcParams& p, int B)
     cuuint32_t ones[4] = {1, 1, 1, 1};
     if (p.conv) {
         cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)p.ldc * es, (cuuint64_t)p.OW * p.ldc * es,
-                                 (cuuint64_t)p.OH * p.OW * p.ldc * es};
+        cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)p.OW * ld * es,
+                                 (cuuint64_t)p.OH * p.OW * ld * es};
         cuuint32_t box[4] = {32, (cuuint32_t)PATCH_W, (cuuint32_t)(32 / PATCH_W), 1};
         return enc(m, dt, 4, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
     cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
-    cuuint64_t strides[1] = {(cuuint64_t)p.ldc * es};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
     cuuint32_t box[2] = {32, 32};
     return enc(m, dt, 2, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -647,13 +678,14 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     const unsigned grid = (unsigned)imin64(tiles, sm_count());
     TcParams q = p;
     static const bool direct = getenv("PVSG_TC_DIRECT_STORE") != nullptr;
-    CUtensorMap c{}, c_hi{}, c_lo{};
+    CUtensorMap c{}, c_hi{}, c_lo{}, r{};
     q.tma_out = 0;
-    if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B)) q.tma_out |= 1;
+    if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B, p.ldc)) q.tma_out |= 1;
     if (!direct && p.C_hi && p.ldc % 8 == 0 && al16(p.C_hi) && al16(p.C_lo) &&
-        make_out_map(&c_hi, p.C_hi, false, p, B) && make_out_map(&c_lo, p.C_lo, false, p, B))
+        make_out_map(&c_hi, p.C_hi, false, p, B, p.ldc) && make_out_map(&c_lo, p.C_lo, false, p, B, p.ldc))
         q.tma_out |= 2;
-    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, q);
+    if (!direct && p.R && p.ldr % 4 == 0 && al16(p.R) && make_out_map(&r, p.R, true, p, B, p.ldr)) q.tma_out |= 4;
+    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, r, q);
     return pvsg_launch_status();
 }
 

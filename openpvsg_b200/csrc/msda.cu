@@ -49,6 +49,27 @@ __device__ __forceinline__ void sample_acc(const float4* __restrict__ vbase, int
     acc.w += w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
 }
 
+// Per-sample part of the bilinear lookup, done ONCE by the lane that owns the sample: clamped
+// corner pixel indices (relative to the value tensor, level start included) and the four corner
+// weights (attention weight folded in, 0 for corners outside the map).
+__device__ __forceinline__ void sample_prep(int hgt, int wid, int start, float x, float y, float aw, int (&idx)[4],
+                                            float (&w)[4]) {
+    x = fminf(fmaxf(x, -2.f), (float)wid + 1.f);
+    y = fminf(fmaxf(y, -2.f), (float)hgt + 1.f);
+    const float fy = floorf(y), fx = floorf(x);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const float ly = y - fy, lx = x - fx;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const bool y0v = y0 >= 0 && y0 < hgt, y1v = y0 + 1 >= 0 && y0 + 1 < hgt;
+    const bool x0v = x0 >= 0 && x0 < wid, x1v = x0 + 1 >= 0 && x0 + 1 < wid;
+    const int yc0 = min(max(y0, 0), hgt - 1), yc1 = min(max(y0 + 1, 0), hgt - 1);
+    const int xc0 = min(max(x0, 0), wid - 1), xc1 = min(max(x0 + 1, 0), wid - 1);
+    idx[0] = start + yc0 * wid + xc0; idx[1] = start + yc0 * wid + xc1;
+    idx[2] = start + yc1 * wid + xc0; idx[3] = start + yc1 * wid + xc1;
+    w[0] = (y0v && x0v) ? hy * hx * aw : 0.f; w[1] = (y0v && x1v) ? hy * lx * aw : 0.f;
+    w[2] = (y1v && x0v) ? ly * hx * aw : 0.f; w[3] = (y1v && x1v) ? ly * lx * aw : 0.f;
+}
+
 template <bool FUSED, bool TILED>
 __global__ void __launch_bounds__(256, 5) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
                                                    const float* __restrict__ loc_or_proj,
@@ -103,19 +124,33 @@ __global__ void __launch_bounds__(256, 5) msda_kernel(const float* __restrict__ 
             const float o0 = lane < LP ? __ldg(offp + 2 * lane) : 0.f;      // x offset of sample `lane`
             const float o1 = lane < LP ? __ldg(offp + 2 * lane + 1) : 0.f;  // y offset
             const float rx = __ldg(aw_or_ref + nq * 2), ry = __ldg(aw_or_ref + nq * 2 + 1);
-#pragma unroll 3
-            for (int s0 = 0; s0 < LP; s0 += 4) {  // trip count is warp-uniform (full-mask shuffles)
-                const int s = min(s0 + g, LP - 1);
-                float aw = __shfl_sync(0xffffffffu, wgt, s);
-                const float ox = __shfl_sync(0xffffffffu, o0, s);
-                const float oy = __shfl_sync(0xffffffffu, o1, s);
-                if (s0 + g >= LP) aw = 0.f;
-                const int l = s / P;
+            // lane s owns sample s: location arithmetic once per sample, not once per channel group
+            int idx[4];
+            float cw[4];
+            {
+                const int l = min(lane, LP - 1) / P;
                 const int hgt = lv.h[l], wid = lv.w[l];
                 // loc = ref + off / (w, h); pixel = loc * size - 0.5 = ref * size + off - 0.5
-                const float x = fmaf(rx, (float)wid, ox) - 0.5f;
-                const float y = fmaf(ry, (float)hgt, oy) - 0.5f;
-                sample_acc(vb + (int)lv.start[l] * pix_stride, hgt, wid, pix_stride, x, y, aw, acc);
+                const float x = fmaf(rx, (float)wid, o0) - 0.5f;
+                const float y = fmaf(ry, (float)hgt, o1) - 0.5f;
+                sample_prep(hgt, wid, (int)lv.start[l], x, y, wgt, idx, cw);   // wgt = 0 for lane >= LP
+            }
+#pragma unroll 3
+            for (int s0 = 0; s0 < LP; s0 += 4) {  // trip count is warp-uniform (full-mask shuffles)
+                const int s = min(s0 + g, 31);    // lanes >= LP carry weight 0 and in-range indices
+                float4 v[4];
+                float w[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int i = __shfl_sync(0xffffffffu, idx[c], s);
+                    w[c] = __shfl_sync(0xffffffffu, cw[c], s);
+                    v[c] = __ldg(vb + i * pix_stride);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc.x = fmaf(w[c], v[c].x, acc.x); acc.y = fmaf(w[c], v[c].y, acc.y);
+                    acc.z = fmaf(w[c], v[c].z, acc.z); acc.w = fmaf(w[c], v[c].w, acc.w);
+                }
             }
         } else {
             const float* locp = loc_or_proj + ((b * Nq + nq) * H + head) * (int64_t)LP * 2;
