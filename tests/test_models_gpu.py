@@ -223,7 +223,9 @@ def test_batched_runner_matches_single_frames(detectors, cuda):
         assert np.array_equal(a['pan_results'], b['pan_results'])
         assert sorted(a['query_feats']) == sorted(b['query_feats'])
         for k in b['query_feats']:
-            close(torch.as_tensor(a['query_feats'][k][0]), torch.as_tensor(b['query_feats'][k][0]), 1e-4, 'query feat')
+            # batch and single-frame passes pick different tile shapes (fp32 re-association), and the
+            # sign-test attention masks amplify that: same bar as vs the oracle
+            close(torch.as_tensor(a['query_feats'][k][0]), torch.as_tensor(b['query_feats'][k][0]), TOL, 'query feat')
         assert [len(x) for x in a['ins_results'][0]] == [len(x) for x in b['ins_results'][0]]
 
 

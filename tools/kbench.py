@@ -39,8 +39,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default='')
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--match', default='', help='only shapes whose name contains this')
+    ap.add_argument('--batch', type=int, default=1, help='frames per launch (bench.py runs 8)')
     args = ap.parse_args()
     dev = 'cuda'
+    NB = args.batch
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     rows = []
 
@@ -60,23 +63,26 @@ def main():
     N = sum(h * w for h, w in shapes)
     g = torch.Generator(device=dev).manual_seed(0)
     if want('msda'):
-        value = torch.randn(1, N, 256, device=dev, generator=g)
-        proj = torch.cat([torch.randn(1, N, 192, device=dev, generator=g) * 2, torch.randn(1, N, 96, device=dev, generator=g)], -1)
+        value = torch.randn(NB, N, 256, device=dev, generator=g)
+        proj = torch.cat([torch.randn(NB, N, 192, device=dev, generator=g) * 2, torch.randn(NB, N, 96, device=dev, generator=g)], -1)
         refs = []
         for h, w in shapes:
             ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
             refs.append(torch.stack(((xs.flatten() + 0.5) / w, (ys.flatten() + 0.5) / h), -1))
         ref = torch.cat(refs).to(dev)
         us = timeit(lambda: ops.msda_fused_forward(value, shapes, proj, ref), args.iters, flush=flush)
-        rec('msda_fused_720p', us, gbytes=N * (1024 + 1152 + 1024) / 1e9)
-        loc = torch.rand(1, N, 8, 3, 4, 2, device=dev, generator=g)
-        aw = torch.softmax(torch.randn(1, N, 8, 12, device=dev, generator=g), -1).view(1, N, 8, 3, 4)
-        v4 = value.view(1, N, 8, 32)
+        rec(f'msda_fused_720p_b{NB}', us, gbytes=NB * N * (1024 + 1152 + 1024) / 1e9)
+        loc = torch.rand(NB, N, 8, 3, 4, 2, device=dev, generator=g)
+        aw = torch.softmax(torch.randn(NB, N, 8, 12, device=dev, generator=g), -1).view(NB, N, 8, 3, 4)
+        v4 = value.view(NB, N, 8, 32)
         us = timeit(lambda: ops.msda_forward(v4, shapes, loc, aw), args.iters, flush=flush)
-        rec('msda_unfused_720p', us, gbytes=N * (1024 + 768 + 384 + 1024) / 1e9)
+        rec(f'msda_unfused_720p_b{NB}', us, gbytes=NB * N * (1024 + 768 + 384 + 1024) / 1e9)
     if want('gemm'):
         for (M, Nn, K) in [(19320, 256, 256), (19320, 1024, 256), (19320, 256, 1024), (58880, 256, 256),
                            (100, 256, 256), (100, 2048, 256), (100, 256, 2048), (14720, 256, 256)]:
+            M = M * NB
+            if args.match and args.match not in f'linear_{M}x{Nn}x{K}':
+                continue
             x = torch.randn(M, K, device=dev, generator=g)
             w = torch.randn(Nn, K, device=dev, generator=g)
             b = torch.randn(Nn, device=dev, generator=g)
@@ -94,16 +100,22 @@ def main():
         for (cin, cout, k, s, hw) in [(3, 64, 7, 2, (736, 1280)), (64, 64, 3, 1, (184, 320)), (128, 128, 3, 1, (92, 160)),
                                       (256, 256, 3, 1, (46, 80)), (512, 512, 3, 1, (23, 40)), (256, 256, 3, 1, (184, 320)),
                                       (64, 256, 1, 1, (184, 320)), (1024, 256, 1, 1, (46, 80)), (512, 2048, 1, 1, (23, 40))]:
-            x = torch.randn(1, hw[0], hw[1], cin, device=dev, generator=g)
+            if args.match and args.match not in f'conv{k}x{k}s{s}_{cin}->{cout}@{hw[0]}x{hw[1]}_b{NB}':
+                continue
+            x = torch.randn(NB, hw[0], hw[1], cin, device=dev, generator=g)
             w = torch.randn(cout, k, k, cin, device=dev, generator=g)
             b = torch.randn(cout, device=dev, generator=g)
             pad = k // 2
             oh, ow = (hw[0] + 2 * pad - k) // s + 1, (hw[1] + 2 * pad - k) // s + 1
             us = timeit(lambda: ops.conv2d_nhwc(x, w, b, stride=s, pad=pad, act=1), args.iters, flush=flush)
-            rec(f'conv{k}x{k}s{s}_{cin}->{cout}@{hw[0]}x{hw[1]}', us, gflop=2 * oh * ow * cout * cin * k * k / 1e9)
+            rec(f'conv{k}x{k}s{s}_{cin}->{cout}@{hw[0]}x{hw[1]}_b{NB}', us, gflop=2 * NB * oh * ow * cout * cin * k * k / 1e9)
     if want('attn'):
         for (B, H, Lq, Lk, E) in [(1, 8, 100, 920, 256), (1, 8, 100, 3680, 256), (1, 8, 100, 14720, 256),
                                   (1, 8, 100, 100, 256), (128, 8, 200, 200, 256), (100, 4, 128, 128, 512)]:
+            if Lq == 100:
+                B = B * NB
+            if args.match and args.match not in f'attention_B{B}_H{H}_{Lq}x{Lk}_E{E}':
+                continue
             q = torch.randn(B, Lq, E, device=dev, generator=g)
             k = torch.randn(B, Lk, E, device=dev, generator=g)
             v = torch.randn(B, Lk, E, device=dev, generator=g)

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""One replay of the batch-8 720p frame graph between cudaProfilerStart/Stop (run under
+`ncu --profile-from-start off`): the launch list of exactly the kernels bench.py times."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import openpvsg_b200 as pv  # noqa: E402
+from openpvsg_b200 import configs, engine, synthetic as syn  # noqa: E402
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = torch.device('cuda:0')
+det = pv.build_detector(configs.mask2former_r50(True))
+det.load_state_dict(syn.mask2former_state_dict(seed=0))
+det.to(dev)
+engine.enable_cuda_graph(det)
+meta = syn.frame_meta(720, 1280)
+frames = [syn.synthetic_frame(i, 720, 1280).to(dev) for i in range(batch)]
+runner = engine.get_runner(det, meta, True, batch=batch)
+runner.collect(runner.submit(frames))
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+runner.collect(runner.submit(frames))
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print('launches per frame', runner.launches_per_frame)
