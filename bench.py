@@ -171,7 +171,7 @@ def kernel_breakdown(det, img, meta, batch=1):
             ('msda_fused_forward', 'msda', None, msda_bytes), ('attention', 'attention', None, None),
             ('layernorm', 'norm', None, None), ('groupnorm_nhwc', 'norm', None, None),
             ('add_rowvec', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
-            ('instance_masks', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
+            ('instance_masks', 'postprocess', None, None), ('instance_select', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
             ('maxpool3x3s2_nhwc', 'resize', None, None))
     saved, depth = {}, [0]
 
@@ -206,11 +206,9 @@ def kernel_breakdown(det, img, meta, batch=1):
         det._runners = None
         xb = img[None].expand(batch, -1, -1, -1).contiguous()
         cls, mlr, _ = det.panoptic_head.simple_test_with_query(det.extract_feat(xb), [[meta]] * batch, upsample=False)
-        fh = det.panoptic_fusion_head
+        from openpvsg_b200 import engine as _engine
         for b in range(batch):
-            m = mlr[b, 0].contiguous()
-            fh._panoptic(cls[b], m, (736, 1280), (H, W), (H, W))
-            fh._instance_device(cls[b], m, (736, 1280), (H, W), (H, W), True)
+            _engine.postprocess_frame(det, cls[b], mlr[b, 0].contiguous(), (736, 1280), (H, W), (H, W))
         torch.cuda.synchronize()
     finally:
         det._runners = runners

@@ -218,6 +218,14 @@ int pvsg_instance_masks(const float* mask_logits, const int32_t* query_idx, int 
                         int in_h, int in_w, int img_h, int img_w, int out_h, int out_w,
                         float* stats, int32_t* boxes, uint8_t* masks_out, void* stream);
 
+/* Instance candidates (mask2former_fusion_head.py:214-222): scores = softmax(cls_logits)[:, :NC]
+ * (cls_logits [Q,NC+1], last column = void), then the k largest entries of the flattened
+ * [Q*NC] scores -- scores.flatten(0, 1).topk(k, sorted=False).  Outputs [k]: score, label
+ * (= index % NC) and query (= index / NC), in ascending flat-index order (torch leaves the order of
+ * sorted=False unspecified). */
+int pvsg_instance_select(const float* cls_logits, int Q, int NC, int k, float* top_scores,
+                         int32_t* top_labels, int32_t* top_query, void* stream);
+
 /* ------------------------------------------------------------ relation head ----- */
 
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */

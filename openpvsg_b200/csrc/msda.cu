@@ -71,7 +71,7 @@ __device__ __forceinline__ void sample_prep(int hgt, int wid, int start, float x
 }
 
 template <bool FUSED, bool TILED>
-__global__ void __launch_bounds__(256, 5) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
+__global__ void __launch_bounds__(256, 4) msda_kernel(const float* __restrict__ value, MsdaLevels lv,
                                                    const float* __restrict__ loc_or_proj,
                                                    const float* __restrict__ aw_or_ref, float* __restrict__ out,
                                                    int64_t N, int64_t Nq, int H, int L, int P, int64_t total) {
@@ -175,6 +175,142 @@ __global__ void __launch_bounds__(256, 5) msda_kernel(const float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused variant, L*P <= 16 (the reference configuration has 3 x 4 = 12 samples).
+//
+// ncu on the warp-per-item kernel above showed the LSU data pipe as the limiter (77 % busy) and
+// most of its wavefronts were not the bilinear gathers but warp shuffles (which travel through
+// the same pipe) and register spills.  Here a group of 8 LANES owns one (query, head) item and a
+// warp carries four items (4 consecutive queries of one head):
+//   * lane j of the group owns samples j and j + 8: softmax = 3-step butterfly inside the group,
+//     location arithmetic twice per lane instead of once per item-warp;
+//   * per sample the owner broadcasts 5 registers (packed corner index + 4 corner weights) with
+//     width-8 shuffles; there is no cross-group reduction at the end.
+// Shuffles per item: 12 x 5 + 6 (softmax) over FOUR items per instruction, i.e. ~16 per item
+// instead of 42.
+__device__ __forceinline__ void sample_prep_packed(int hgt, int wid, int start, float x, float y, float aw,
+                                                   uint32_t& pk, float (&w)[4]) {
+    x = fminf(fmaxf(x, -2.f), (float)wid + 1.f);
+    y = fminf(fmaxf(y, -2.f), (float)hgt + 1.f);
+    const float fy = floorf(y), fx = floorf(x);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const float ly = y - fy, lx = x - fx;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const bool y0v = y0 >= 0 && y0 < hgt, y1v = y0 + 1 >= 0 && y0 + 1 < hgt;
+    const bool x0v = x0 >= 0 && x0 < wid, x1v = x0 + 1 >= 0 && x0 + 1 < wid;
+    const int yc0 = min(max(y0, 0), hgt - 1), yc1 = min(max(y0 + 1, 0), hgt - 1);
+    const int xc0 = min(max(x0, 0), wid - 1), xc1 = min(max(x0 + 1, 0), wid - 1);
+    // corner (cy, cx) = base + cy * dy * wid + cx * dx with dx, dy in {0, 1} (0 where the clamp folds
+    // the two corners onto one pixel; that corner then carries weight 0 anyway)
+    pk = (uint32_t)(start + yc0 * wid + xc0) | ((uint32_t)(xc1 - xc0) << 30) | ((uint32_t)(yc1 - yc0) << 31);
+    w[0] = (y0v && x0v) ? hy * hx * aw : 0.f; w[1] = (y0v && x1v) ? hy * lx * aw : 0.f;
+    w[2] = (y1v && x0v) ? ly * hx * aw : 0.f; w[3] = (y1v && x1v) ? ly * lx * aw : 0.f;
+}
+
+template <bool TILED>
+__global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restrict__ value, MsdaLevels lv,
+                                                            const float* __restrict__ proj,
+                                                            const float* __restrict__ ref, float* __restrict__ out,
+                                                            int64_t N, int64_t Nq, int H, int L, int P,
+                                                            int64_t total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, j = lane & 7;
+    const int LP = L * P;
+    const int pix_stride = H * 8;   // float4 per pixel
+    // TILED: CTA = 8 x 8 query tile of one level and head, warp = one row, two passes of 4 queries.
+    // otherwise: CTA = 32 consecutive queries of one head, warp = 4 of them.
+    const int64_t qblocks = TILED ? lv.tile_start[L] : (Nq + 31) / 32;
+    for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+        const int64_t qb = blk % qblocks;
+        const int64_t t = blk / qblocks;
+        const int head = (int)(t % H);
+        const int64_t b = t / H;
+        int tl = 0, ty = 0, tx = 0;
+        if (TILED) {
+            while (tl + 1 < L && qb >= lv.tile_start[tl + 1]) ++tl;
+            const int local = (int)(qb - lv.tile_start[tl]);
+            const int tiles_x = (lv.w[tl] + 7) >> 3;
+            ty = local / tiles_x;
+            tx = local - ty * tiles_x;
+        }
+        const float4* vb = reinterpret_cast<const float4*>(value) + (b * N * H + head) * 8 + j;
+        for (int pass = 0; pass < (TILED ? 2 : 1); ++pass) {
+            int64_t nq;
+            bool valid;
+            if (TILED) {
+                const int y = ty * 8 + warp, x = tx * 8 + pass * 4 + g;
+                if (y >= lv.h[tl] || tx * 8 + pass * 4 >= lv.w[tl]) continue;   // warp-uniform
+                valid = x < lv.w[tl];
+                nq = lv.start[tl] + (int64_t)y * lv.w[tl] + min(x, lv.w[tl] - 1);
+            } else {
+                const int64_t q0 = qb * 32 + warp * 4;
+                if (q0 >= Nq) continue;                                         // warp-uniform
+                valid = q0 + g < Nq;
+                nq = min(q0 + g, Nq - 1);
+            }
+            const float* prow = proj + (b * Nq + nq) * (int64_t)(H * LP * 3);
+            const float2* offp = reinterpret_cast<const float2*>(prow + (int64_t)head * LP * 2);
+            const float* lgp = prow + (int64_t)H * LP * 2 + (int64_t)head * LP;
+            const bool has0 = j < LP, has1 = j + 8 < LP;
+            const float lg0 = has0 ? __ldg(lgp + j) : -INFINITY, lg1 = has1 ? __ldg(lgp + j + 8) : -INFINITY;
+            float mx = fmaxf(lg0, lg1);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float e0 = has0 ? __expf(lg0 - mx) : 0.f, e1 = has1 ? __expf(lg1 - mx) : 0.f;
+            float sum = e0 + e1;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float inv = 1.f / sum;
+            const float2 rf = __ldg(reinterpret_cast<const float2*>(ref) + nq);
+            uint32_t pk0, pk1;
+            float w0[4], w1[4];
+            {
+                const float2 o = has0 ? __ldg(offp + j) : make_float2(0.f, 0.f);
+                const int l = min(j, LP - 1) / P;
+                const int hgt = lv.h[l], wid = lv.w[l];
+                // loc = ref + off / (w, h); pixel = loc * size - 0.5 = ref * size + off - 0.5
+                sample_prep_packed(hgt, wid, (int)lv.start[l], fmaf(rf.x, (float)wid, o.x) - 0.5f,
+                                   fmaf(rf.y, (float)hgt, o.y) - 0.5f, e0 * inv, pk0, w0);
+            }
+            {
+                const float2 o = has1 ? __ldg(offp + j + 8) : make_float2(0.f, 0.f);
+                const int l = min(j + 8, LP - 1) / P;
+                const int hgt = lv.h[l], wid = lv.w[l];
+                sample_prep_packed(hgt, wid, (int)lv.start[l], fmaf(rf.x, (float)wid, o.x) - 0.5f,
+                                   fmaf(rf.y, (float)hgt, o.y) - 0.5f, e1 * inv, pk1, w1);
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int l = 0, pcount = 0;
+#pragma unroll 2
+            for (int s = 0; s < LP; ++s) {
+                const int wid = lv.w[l];
+                if (++pcount == P) { pcount = 0; ++l; }
+                const bool second = s >= 8;      // uniform
+                const int src = s & 7;
+                const uint32_t pk = __shfl_sync(0xffffffffu, second ? pk1 : pk0, src, 8);
+                float w[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) w[c] = __shfl_sync(0xffffffffu, second ? w1[c] : w0[c], src, 8);
+                const int base = (int)(pk & 0x3fffffffu);
+                const int dx = (int)((pk >> 30) & 1u), dyw = (pk >> 31) ? wid : 0;
+                const float4 v00 = __ldg(vb + base * pix_stride);
+                const float4 v01 = __ldg(vb + (base + dx) * pix_stride);
+                const float4 v10 = __ldg(vb + (base + dyw) * pix_stride);
+                const float4 v11 = __ldg(vb + (base + dyw + dx) * pix_stride);
+                acc.x = fmaf(w[0], v00.x, acc.x); acc.y = fmaf(w[0], v00.y, acc.y);
+                acc.z = fmaf(w[0], v00.z, acc.z); acc.w = fmaf(w[0], v00.w, acc.w);
+                acc.x = fmaf(w[1], v01.x, acc.x); acc.y = fmaf(w[1], v01.y, acc.y);
+                acc.z = fmaf(w[1], v01.z, acc.z); acc.w = fmaf(w[1], v01.w, acc.w);
+                acc.x = fmaf(w[2], v10.x, acc.x); acc.y = fmaf(w[2], v10.y, acc.y);
+                acc.z = fmaf(w[2], v10.z, acc.z); acc.w = fmaf(w[2], v10.w, acc.w);
+                acc.x = fmaf(w[3], v11.x, acc.x); acc.y = fmaf(w[3], v11.y, acc.y);
+                acc.z = fmaf(w[3], v11.z, acc.z); acc.w = fmaf(w[3], v11.w, acc.w);
+            }
+            if (valid) reinterpret_cast<float4*>(out)[((b * Nq + nq) * H + head) * 8 + j] = acc;
+        }
+    }
+}
+
 int fill_levels(MsdaLevels& lv, const int64_t* spatial_shapes, const int64_t* level_start_index, int L,
                 int64_t N) {
     if (L <= 0 || L > MAX_LEVELS) return PVSG_ERR_UNSUPPORTED;
@@ -201,6 +337,18 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
     int rc = fill_levels(lv, spatial_shapes, level_start_index, L, N);
     if (rc != PVSG_OK) return rc;
     const int wpb = 8;
+    if (FUSED && L * P <= 16 && N < (1LL << 30)) {
+        if (Nq == N) {
+            const int64_t total = (int64_t)B * H * lv.tile_start[L];
+            msda_group_kernel<true><<<(unsigned)imin64(total, 148 * 64), 256, 0, as_stream(stream)>>>(
+                value, lv, a, b2, out, N, Nq, H, L, P, total);
+        } else {
+            const int64_t total = (int64_t)B * H * ((Nq + 31) / 32);
+            msda_group_kernel<false><<<(unsigned)imin64(total, 148 * 64), 256, 0, as_stream(stream)>>>(
+                value, lv, a, b2, out, N, Nq, H, L, P, total);
+        }
+        return pvsg_launch_status();
+    }
     if (Nq == N) {   // queries = pyramid tokens: 2-D tiled query order
         const int64_t total = (int64_t)B * H * lv.tile_start[L];
         const unsigned grid = (unsigned)imin64(total, 148 * 64);

@@ -45,27 +45,39 @@ __device__ __forceinline__ float final_logit(const float* __restrict__ lg, const
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
-// Step 1 (one CTA): per-query softmax max / argmax, keep test, compaction in query order.
-__global__ void __launch_bounds__(128) pan_select_kernel(const float* __restrict__ cls, int Q, int NC, float thr,
-                                                         int32_t* __restrict__ seg_info, int32_t* __restrict__ work,
-                                                         float* __restrict__ scores) {
+// Step 1 (one CTA, one warp per query): softmax max / argmax over the classes, keep test,
+// compaction in query order.
+__global__ void __launch_bounds__(1024) pan_select_kernel(const float* __restrict__ cls, int Q, int NC, float thr,
+                                                          int32_t* __restrict__ seg_info, int32_t* __restrict__ work,
+                                                          float* __restrict__ scores) {
     __shared__ int keep[1024];
     __shared__ float sc[1024];
     __shared__ int lb[1024];
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 4 * Q; i += blockDim.x) work[i] = 0;
+    for (int q = warp; q < Q; q += nwarp) {
         const float* row = cls + (int64_t)q * (NC + 1);
         float mx = -INFINITY;
-        int arg = 0;
-        for (int c = 0; c <= NC; ++c) {
-            const float v = row[c];
+        int arg = 0x7fffffff;
+        for (int c = lane; c <= NC; c += 32) {
+            const float v = __ldg(row + c);
             if (v > mx) { mx = v; arg = c; }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // first maximum wins (torch.max)
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+        }
         float sum = 0.f;
-        for (int c = 0; c <= NC; ++c) sum += expf(row[c] - mx);
-        const float score = 1.f / sum;  // softmax value of the arg-max class
-        sc[q] = score;
-        lb[q] = arg;
-        keep[q] = (arg != NC && score > thr) ? 1 : 0;
+        for (int c = lane; c <= NC; c += 32) sum += expf(__ldg(row + c) - mx);
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            const float score = 1.f / sum;  // softmax value of the arg-max class
+            sc[q] = score;
+            lb[q] = arg;
+            keep[q] = (arg != NC && score > thr) ? 1 : 0;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -81,7 +93,6 @@ __global__ void __launch_bounds__(128) pan_select_kernel(const float* __restrict
             }
         }
         seg_info[0] = n;
-        for (int i = 0; i < 4 * Q; ++i) work[i] = 0;
     }
 }
 
@@ -263,6 +274,245 @@ __global__ void ins_finish_kernel(int32_t* boxes, int n) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast paths for the usual geometry (no rescale stage: out == img, i.e. only upsample + crop).
+// A thread owns one output COLUMN and walks ROWS consecutive output rows: the horizontal source
+// coordinates are computed once, the vertical ones are warp-uniform, and the horizontally
+// interpolated values of the two source rows,  top = a*wx0 + b*wx1,  bot = c*wx0 + d*wx1,  are
+// kept in registers while consecutive output rows fall between the same pair of source rows
+// (x4 upsampling: 4 loads per 4 rows instead of 16).  v = top*wy0 + bot*wy1 is the same
+// operation order as up_logit() above / ATen's upsample_bilinear2d.
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+
+constexpr int PAN_ROWS = 4;
+
+__global__ void __launch_bounds__(256) pan_pixel_fast_kernel(const float* __restrict__ mask_logits, UpGeom g, int Q,
+                                                             const int32_t* __restrict__ seg_info,
+                                                             const float* __restrict__ scores,
+                                                             int32_t* __restrict__ work, uint16_t* __restrict__ pix) {
+    extern __shared__ int sh_cnt[];  // [3 * n_kept]
+    const int n = seg_info[0];
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy0 = blockIdx.y * PAN_ROWS;
+    const bool xvalid = ox < g.out_w;
+    const int lane = threadIdx.x & 31;
+    int x0, x1;
+    float wx0, wx1;
+    bilinear_coord(xvalid ? ox : 0, g.sw, g.w, x0, x1, wx0, wx1);
+    int y0[PAN_ROWS], y1[PAN_ROWS];
+    float wy0[PAN_ROWS], wy1[PAN_ROWS];
+    float best[PAN_ROWS];
+    int bestk[PAN_ROWS];
+    bool best_hi[PAN_ROWS];
+#pragma unroll
+    for (int r = 0; r < PAN_ROWS; ++r) {
+        bilinear_coord(min(oy0 + r, g.out_h - 1), g.sh, g.h, y0[r], y1[r], wy0[r], wy1[r]);
+        best[r] = -INFINITY;
+        bestk[r] = NONE;
+        best_hi[r] = false;
+    }
+    const int64_t lstride = (int64_t)g.h * g.w;
+    for (int k = 0; k < n; ++k) {
+        const float* lg = mask_logits + seg_info[1 + 4 * k] * lstride;
+        const float sck = scores[k];
+        float top = 0.f, bot = 0.f;
+        int cy0 = -1, cy1 = -1, hi_cnt = 0;
+#pragma unroll
+        for (int r = 0; r < PAN_ROWS; ++r) {
+            if (y0[r] != cy0 || y1[r] != cy1) {   // warp-uniform
+                cy0 = y0[r]; cy1 = y1[r];
+                top = __ldg(lg + cy0 * g.w + x0) * wx0 + __ldg(lg + cy0 * g.w + x1) * wx1;
+                bot = __ldg(lg + cy1 * g.w + x0) * wx0 + __ldg(lg + cy1 * g.w + x1) * wx1;
+            }
+            const bool valid = xvalid && oy0 + r < g.out_h;
+            const float sig = fast_sigmoid(top * wy0[r] + bot * wy1[r]);
+            const bool hi = valid && sig >= 0.5f;
+            const float prob = sck * sig;
+            if (valid && prob > best[r]) { best[r] = prob; bestk[r] = k; best_hi[r] = hi; }  // first max wins
+            hi_cnt += __popc(__ballot_sync(0xffffffffu, hi));
+        }
+        if (lane == 0 && hi_cnt) atomicAdd(&sh_cnt[n + k], hi_cnt);
+    }
+#pragma unroll
+    for (int r = 0; r < PAN_ROWS; ++r) {
+        const bool valid = xvalid && oy0 + r < g.out_h;
+        const int bk = valid ? bestk[r] : NONE;
+        const unsigned peers = __match_any_sync(0xffffffffu, bk);
+        const unsigned hi_peers = __ballot_sync(0xffffffffu, best_hi[r]) & peers;
+        if (bk != NONE && lane == (__ffs(peers) - 1)) {
+            atomicAdd(&sh_cnt[bk], __popc(peers));
+            if (hi_peers) atomicAdd(&sh_cnt[2 * n + bk], __popc(hi_peers));
+        }
+        if (valid) pix[(int64_t)(oy0 + r) * g.out_w + ox] = (uint16_t)(bk | (best_hi[r] ? 0x8000 : 0));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
+        const int v = sh_cnt[i];
+        if (v) atomicAdd(&work[(i / n) * Q + (i % n)], v);
+    }
+}
+
+constexpr int INS_ROWS = 16;
+
+template <bool MASKS>
+__global__ void __launch_bounds__(256) ins_pixel_fast_kernel(const float* __restrict__ mask_logits,
+                                                             const int32_t* __restrict__ query_idx, UpGeom g,
+                                                             float* __restrict__ stats, int32_t* __restrict__ boxes,
+                                                             uint8_t* __restrict__ masks_out) {
+    const int i = blockIdx.z;
+    const float* lg = mask_logits + (int64_t)query_idx[i] * g.h * g.w;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy0 = blockIdx.y * INS_ROWS;
+    const bool xvalid = ox < g.out_w;
+    int x0, x1;
+    float wx0, wx1;
+    bilinear_coord(xvalid ? ox : 0, g.sw, g.w, x0, x1, wx0, wx1);
+    float s = 0.f, top = 0.f, bot = 0.f;
+    int cnt = 0, ymin = INT_MAX, ymax = -1, cy0 = -1, cy1 = -1;
+    const int rows = min(INS_ROWS, g.out_h - oy0);
+    for (int r = 0; r < rows; ++r) {
+        int y0, y1;
+        float wy0, wy1;
+        bilinear_coord(oy0 + r, g.sh, g.h, y0, y1, wy0, wy1);
+        if (y0 != cy0 || y1 != cy1) {   // warp-uniform
+            cy0 = y0; cy1 = y1;
+            top = __ldg(lg + cy0 * g.w + x0) * wx0 + __ldg(lg + cy0 * g.w + x1) * wx1;
+            bot = __ldg(lg + cy1 * g.w + x0) * wx0 + __ldg(lg + cy1 * g.w + x1) * wx1;
+        }
+        const float v = top * wy0 + bot * wy1;
+        const bool on = xvalid && v > 0.f;
+        if (on) {
+            s += fast_sigmoid(v);
+            cnt += 1;
+            ymin = min(ymin, oy0 + r);
+            ymax = oy0 + r;
+        }
+        if (MASKS && xvalid) masks_out[((int64_t)i * g.out_h + oy0 + r) * g.out_w + ox] = on ? 1 : 0;
+    }
+    int xmin = cnt ? ox : INT_MAX, xmax = cnt ? ox : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    __shared__ float sh_s[8];
+    __shared__ int sh_i[8][5];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sh_s[wid] = s;
+        sh_i[wid][0] = cnt; sh_i[wid][1] = xmin; sh_i[wid][2] = ymin; sh_i[wid][3] = xmax; sh_i[wid][4] = ymax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            s += sh_s[w];
+            cnt += sh_i[w][0];
+            xmin = min(xmin, sh_i[w][1]); ymin = min(ymin, sh_i[w][2]);
+            xmax = max(xmax, sh_i[w][3]); ymax = max(ymax, sh_i[w][4]);
+        }
+        if (cnt) {
+            atomicAdd(&stats[2 * i], s);
+            atomicAdd(&stats[2 * i + 1], (float)cnt);
+            atomicMin(&boxes[4 * i], xmin);
+            atomicMin(&boxes[4 * i + 1], ymin);
+            atomicMax(&boxes[4 * i + 2], xmax);
+            atomicMax(&boxes[4 * i + 3], ymax);
+        }
+    }
+}
+
+// Instance candidates (mask2former_fusion_head.py:214-222): softmax over the classes, drop the
+// void column, top-k over the flattened [Q * NC] scores.  One CTA: scores in shared memory, the
+// k-th largest value found by a 4 x 8-bit radix select on the float bit patterns (scores > 0, so
+// the unsigned order is the float order), then compaction in index order (torch.topk with
+// sorted=False leaves the order unspecified; ties at the threshold go to the lowest indices).
+__global__ void __launch_bounds__(1024) ins_select_kernel(const float* __restrict__ cls, int Q, int NC, int k,
+                                                          float* __restrict__ top_scores,
+                                                          int32_t* __restrict__ top_labels,
+                                                          int32_t* __restrict__ top_query) {
+    extern __shared__ float sc[];            // [Q * NC]
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sel_prefix, sel_remaining, out_gt, out_eq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int total = Q * NC;
+    for (int q = warp; q < Q; q += nwarp) {
+        const float* row = cls + (int64_t)q * (NC + 1);
+        float mx = -INFINITY;
+        for (int c = lane; c <= NC; c += 32) mx = fmaxf(mx, __ldg(row + c));
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int c = lane; c <= NC; c += 32) sum += expf(__ldg(row + c) - mx);
+        sum = warp_sum(sum);
+        for (int c = lane; c < NC; c += 32) sc[q * NC + c] = expf(__ldg(row + c) - mx) / sum;
+    }
+    if (threadIdx.x == 0) { sel_prefix = 0; sel_remaining = (unsigned)k; out_gt = 0; out_eq = 0; }
+    __syncthreads();
+    // radix select, most significant byte first
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = sel_prefix;
+        const unsigned pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const unsigned u = __float_as_uint(sc[i]);
+            if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned rem = sel_remaining;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            sel_prefix = prefix | ((unsigned)b << shift);
+            sel_remaining = rem;   // how many elements equal to the final threshold are taken
+        }
+        __syncthreads();
+    }
+    const unsigned thr = sel_prefix;
+    const unsigned n_eq = sel_remaining;
+    // compaction in index order: warp-strided chunks keep the order deterministic
+    // (chunk c = indices [c*1024, c*1024+1024) handled by all threads, prefix by ballot + smem base)
+    __shared__ unsigned wcount_gt[32], wcount_eq[32];
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned u = i < total ? __float_as_uint(sc[i]) : 0u;
+        const bool gt = i < total && u > thr, eq = i < total && u == thr;
+        const unsigned bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) { wcount_gt[warp] = __popc(bg); wcount_eq[warp] = __popc(be); }
+        __syncthreads();
+        unsigned og = out_gt, oe = out_eq;
+        for (int w = 0; w < warp; ++w) { og += wcount_gt[w]; oe += wcount_eq[w]; }
+        const unsigned lower = (1u << lane) - 1u;
+        // elements greater than the threshold: slots [0, k - n_eq); equal ones: the next n_eq slots
+        if (gt) {
+            const unsigned slot = og + __popc(bg & lower);
+            top_scores[slot] = sc[i]; top_labels[slot] = i % NC; top_query[slot] = i / NC;
+        } else if (eq) {
+            const unsigned r = oe + __popc(be & lower);
+            if (r < n_eq) {
+                const unsigned slot = (unsigned)k - n_eq + r;
+                top_scores[slot] = sc[i]; top_labels[slot] = i % NC; top_query[slot] = i / NC;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tg = 0, te = 0;
+            for (int w = 0; w < nwarp; ++w) { tg += wcount_gt[w]; te += wcount_eq[w]; }
+            out_gt += tg; out_eq += te;
+        }
+        __syncthreads();
+    }
+}
+
 int make_geom(UpGeom& g, int h, int w, int in_h, int in_w, int img_h, int img_w, int out_h, int out_w) {
     if (h <= 0 || w <= 0 || in_h <= 0 || in_w <= 0 || img_h <= 0 || img_w <= 0 || out_h <= 0 || out_w <= 0)
         return PVSG_ERR_INVALID_ARG;
@@ -290,9 +540,14 @@ extern "C" int pvsg_panoptic_fuse(const float* cls_logits, const float* mask_log
     if (rc != PVSG_OK) return rc;
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)out_h * out_w;
-    pan_select_kernel<<<1, 128, 0, st>>>(cls_logits, Q, NC, object_mask_thr, seg_info, work, scores);
-    pan_pixel_kernel<<<(unsigned)((npix + 255) / 256), 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info,
-                                                                                       scores, work, pix_ws);
+    pan_select_kernel<<<1, 1024, 0, st>>>(cls_logits, Q, NC, object_mask_thr, seg_info, work, scores);
+    if (!g.rescale) {
+        dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)((out_h + PAN_ROWS - 1) / PAN_ROWS));
+        pan_pixel_fast_kernel<<<grid, 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info, scores, work, pix_ws);
+    } else {
+        pan_pixel_kernel<<<(unsigned)((npix + 255) / 256), 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info,
+                                                                                           scores, work, pix_ws);
+    }
     pan_decide_kernel<<<1, 32, 0, st>>>(Q, num_things, iou_thr, filter_low_score, instance_offset, seg_info, work);
     pan_write_kernel<<<(unsigned)imin64((npix + 255) / 256, 148 * 16), 256, 0, st>>>(
         pix_ws, seg_info, NC, filter_low_score, pan_out, npix);
@@ -309,8 +564,33 @@ extern "C" int pvsg_instance_masks(const float* mask_logits, const int32_t* quer
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)out_h * out_w;
     ins_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, boxes, n);
-    dim3 grid((unsigned)((npix + 256 * INS_STRIPS - 1) / (256 * INS_STRIPS)), (unsigned)n);
-    ins_pixel_kernel<<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
+    if (!g.rescale) {
+        dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)((out_h + INS_ROWS - 1) / INS_ROWS), (unsigned)n);
+        if (masks_out)
+            ins_pixel_fast_kernel<true><<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
+        else
+            ins_pixel_fast_kernel<false><<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
+    } else {
+        dim3 grid((unsigned)((npix + 256 * INS_STRIPS - 1) / (256 * INS_STRIPS)), (unsigned)n);
+        ins_pixel_kernel<<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
+    }
     ins_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(boxes, n);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_instance_select(const float* cls_logits, int Q, int NC, int k, float* top_scores,
+                                    int32_t* top_labels, int32_t* top_query, void* stream) {
+    PVSG_CHECK_ARG(cls_logits && top_scores && top_labels && top_query && Q > 0 && NC > 0 && k > 0);
+    PVSG_CHECK_ARG((int64_t)k <= (int64_t)Q * NC);
+    const size_t smem = sizeof(float) * (size_t)Q * NC;
+    if (smem > 200 * 1024) return PVSG_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(ins_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+            cudaSuccess)
+            return PVSG_ERR_LAUNCH;
+        configured = true;
+    }
+    ins_select_kernel<<<1, 1024, smem, as_stream(stream)>>>(cls_logits, Q, NC, k, top_scores, top_labels, top_query);
     return pvsg_launch_status();
 }

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import lib as _l
+from . import ops
 from .mask2former import bbox2result
 
 RING = 3
@@ -32,6 +33,28 @@ class _Pending:
 
     def __init__(self, slot, event, n):
         self.slot, self.event, self.n = slot, event, n
+
+
+def postprocess_frame(det, cls, mlr, in_hw, img_hw, out_hw):
+    """Static-shape device post-processing of one frame (CUDA-graph capturable): fused panoptic
+    map + segment table, and the detector's top-10 instances (models/mask2former_vps/mask2former.py:
+    183-201): statistics of all max_per_image candidates first, binary masks only for the survivors."""
+    fh = det.panoptic_fusion_head
+    out = {}
+    if fh.test_cfg.get('panoptic_on', True):
+        out['pan'], out['seg_info'] = fh._panoptic(cls, mlr, in_hw, img_hw, out_hw)
+    if fh.test_cfg.get('instance_on', False):
+        d = fh._instance_device(cls, mlr, in_hw, img_hw, out_hw, False)
+        is_thing = d['labels'] < det.num_things_classes
+        det_scores = d['scores'] * d['stats'][:, 0] / (d['stats'][:, 1] + 1e-6)
+        det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
+        ids = torch.cumsum(is_thing.to(torch.float32), 0)   # 1-based rank among thing candidates
+        inds = torch.argsort(det_scores, descending=True)[:TOPK_INS]
+        out['ins_boxes'] = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
+        out['ins_labels'] = d['labels'][inds].to(torch.int32)
+        out['ins_count'] = is_thing.sum().to(torch.int32).reshape(1)
+        out['ins_masks'] = ops.instance_masks(mlr, d['query'][inds], in_hw, img_hw, out_hw, True)[2]
+    return out
 
 
 class FrameRunner:
@@ -50,9 +73,20 @@ class FrameRunner:
         self.out = None
         self.launches_per_frame = 0
         self._capture()
-        self.host = [[{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in o.items()}
-                      for o in self.out] for _ in range(RING)]
+        # copy engines run beside the compute stream: frames go up on ``h2d``, results come down on
+        # ``d2h`` (PCIe is full duplex), both through device-side staging slots so that batch i's
+        # copies overlap batch i+1's graph
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.in_stage = [torch.empty_like(self.static_in) for _ in range(RING)]
+        self.in_ready = [torch.cuda.Event() for _ in range(RING)]
+        self.in_free = [None] * RING
+        self.out_stage = [{k: torch.empty_like(v) for k, v in self.out.items()} for _ in range(RING)]
+        self.out_ready = [torch.cuda.Event() for _ in range(RING)]
+        self.host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.out.items()}
+                     for _ in range(RING)]
         self.events = [torch.cuda.Event() for _ in range(RING)]
+        self.busy = [False] * RING
         self.next_slot = 0
 
     @torch.no_grad()
@@ -67,23 +101,10 @@ class FrameRunner:
         outs = []
         for b in range(B):
             out = dict(query=query[:, b].contiguous())
-            mlr = mask_lr[b, 0].contiguous()
-            if fh.test_cfg.get('panoptic_on', True):
-                out['pan'], out['seg_info'] = fh._panoptic(cls[b], mlr, in_hw, img_hw, out_hw)
-            if fh.test_cfg.get('instance_on', False):
-                d = fh._instance_device(cls[b], mlr, in_hw, img_hw, out_hw, True)
-                # static-shape version of the detector's top-10 selection (mask2former.py:183-201)
-                is_thing = d['labels'] < det.num_things_classes
-                det_scores = d['scores'] * d['stats'][:, 0] / (d['stats'][:, 1] + 1e-6)
-                det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
-                ids = torch.cumsum(is_thing.to(torch.float32), 0)   # 1-based rank among thing candidates
-                inds = torch.argsort(det_scores, descending=True)[:TOPK_INS]
-                out['ins_boxes'] = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
-                out['ins_labels'] = d['labels'][inds].to(torch.int32)
-                out['ins_count'] = is_thing.sum().to(torch.int32).reshape(1)
-                out['ins_masks'] = d['masks'][inds]
+            out.update(postprocess_frame(det, cls[b], mask_lr[b, 0].contiguous(), in_hw, img_hw, out_hw))
             outs.append(out)
-        return outs
+        # one [B, ...] tensor per output kind: 7 copies per batch instead of 7 per frame
+        return {k: torch.stack([o[k] for o in outs]) for k in outs[0]}
 
     def _capture(self):
         s = torch.cuda.Stream()
@@ -111,14 +132,34 @@ class FrameRunner:
             raise ValueError(f'submit: expected 1..{self.batch} frames, got {n}')
         slot = self.next_slot
         self.next_slot = (slot + 1) % RING
-        for b in range(self.batch):
-            self.static_in[b].copy_(imgs[min(b, n - 1)].reshape(self.static_in.shape[1:]), non_blocking=True)
+        main = torch.cuda.current_stream()
+        shape = self.static_in.shape[1:]
+        if any(not t.is_cuda for t in imgs):
+            with torch.cuda.stream(self.h2d):
+                if self.in_free[slot] is not None:
+                    self.h2d.wait_event(self.in_free[slot])      # the compute stream has drained this slot
+                for b in range(self.batch):
+                    self.in_stage[slot][b].copy_(imgs[min(b, n - 1)].reshape(shape), non_blocking=True)
+                self.in_ready[slot].record(self.h2d)
+            main.wait_event(self.in_ready[slot])
+            self.static_in.copy_(self.in_stage[slot], non_blocking=True)
+            self.in_free[slot] = torch.cuda.Event()
+            self.in_free[slot].record(main)
+        else:
+            for b in range(self.batch):
+                self.static_in[b].copy_(imgs[min(b, n - 1)].reshape(shape), non_blocking=True)
         self.graph.replay()
-        for b in range(n):
-            hb = self.host[slot][b]
-            for k, v in self.out[b].items():
-                hb[k].copy_(v, non_blocking=True)
-        self.events[slot].record()
+        if self.busy[slot]:
+            main.wait_event(self.events[slot])                   # this slot's previous D2H has finished
+        for k, v in self.out.items():
+            self.out_stage[slot][k].copy_(v, non_blocking=True)
+        self.out_ready[slot].record(main)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.out_ready[slot])
+            for k, v in self.out_stage[slot].items():
+                self.host[slot][k].copy_(v, non_blocking=True)
+            self.events[slot].record(self.d2h)
+        self.busy[slot] = True
         return _Pending(slot, self.events[slot], n)
 
     @torch.no_grad()
@@ -132,7 +173,7 @@ class FrameRunner:
         own = (lambda a: a.copy()) if copy else (lambda a: a)
         results = []
         for b in range(pending.n):
-            hb = self.host[pending.slot][b]
+            hb = {k: v[b] for k, v in self.host[pending.slot].items()}
             res = {}
             if 'pan' in hb:
                 res['pan_results'] = own(hb['pan'].numpy())

@@ -46,6 +46,7 @@ SIGNATURES = {
     'pvsg_mask_logits': (I, [P, P, P, P, P, I, I, L, I, P]),
     'pvsg_panoptic_fuse': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),
     'pvsg_instance_masks': (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, P, P]),
+    'pvsg_instance_select': (I, [P, I, I, I, P, P, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
     'pvsg_pair_proposal': (I, [P, P, P, P, P, I, I, P]),
     'pvsg_top_pairs': (I, [P, I, I, P, P, P]),

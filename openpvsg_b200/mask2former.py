@@ -837,13 +837,11 @@ class MaskFormerFusionHeadCustom(nn.Module):
     def _instance_device(self, mask_cls, mask_lr, in_hw, img_hw, out_hw, want_masks=True):
         """Static-shape device part (CUDA-graph capturable): all ``max_per_image`` candidates are
         evaluated, stuff candidates are dropped afterwards by ``_instance_finish``."""
-        max_per_image = self.test_cfg.get('max_per_image', 100)
-        scores = torch.softmax(mask_cls, dim=-1)[:, :-1]
-        scores_per_image, top_indices = scores.flatten(0, 1).topk(max_per_image, sorted=False)
-        labels_per_image = top_indices % self.num_classes
-        query_indices = (top_indices // self.num_classes).to(torch.int32)
+        max_per_image = min(self.test_cfg.get('max_per_image', 100), mask_cls.shape[0] * self.num_classes)
+        scores_per_image, labels_per_image, query_indices = ops.instance_select(mask_cls, max_per_image)
         stats, boxes, masks = ops.instance_masks(mask_lr, query_indices, in_hw, img_hw, out_hw, want_masks)
-        return dict(scores=scores_per_image, labels=labels_per_image, stats=stats, boxes=boxes, masks=masks)
+        return dict(scores=scores_per_image, labels=labels_per_image.long(), stats=stats, boxes=boxes, masks=masks,
+                    query=query_indices)
 
     @torch.no_grad()
     def _instance_finish(self, d):

@@ -557,6 +557,20 @@ def instance_masks(mask_logits_lr, query_idx, in_hw, img_hw, out_hw, want_masks=
     return stats, boxes, masks
 
 
+def instance_select(cls_logits, k):
+    """softmax(cls_logits)[:, :-1].flatten().topk(k, sorted=False) -> (scores [k], labels int32 [k],
+    query index int32 [k]), in ascending flat-index order."""
+    lib = _l.load()
+    Q, C1 = _f32(cls_logits).shape
+    dev = cls_logits.device
+    scores = torch.empty(k, device=dev, dtype=torch.float32)
+    labels = torch.empty(k, device=dev, dtype=torch.int32)
+    query = torch.empty(k, device=dev, dtype=torch.int32)
+    _l.check(lib.pvsg_instance_select(_ptr(cls_logits.contiguous()), Q, C1 - 1, k, _ptr(scores), _ptr(labels),
+                                      _ptr(query), _stream()), 'pvsg_instance_select')
+    return scores, labels, query
+
+
 def max_over_time(x):
     lib = _l.load()
     N, T, C = _f32(x).shape

@@ -162,6 +162,33 @@ def test_msda_fused(ops, shapes):
     close(out, ref, 1e-4, 'msda fused')
 
 
+def _fused_ref(value, shapes, proj, ref_pts):
+    from oracle import m2f as om
+    B, nq = proj.shape[:2]
+    n = value.shape[1]
+    off = proj[..., :192].view(B, nq, 8, 3, 4, 2)
+    aw = proj[..., 192:].view(B, nq, 8, 12).softmax(-1).view(B, nq, 8, 3, 4)
+    normalizer = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
+    loc = ref_pts[None, :, None, None, None, :] + off / normalizer[None, None, None, :, None, :]
+    return om.msda_core(value.view(B, n, 8, 32), shapes, loc, aw)
+
+
+def test_msda_fused_ragged_batch_and_free_queries(ops):
+    """The 8-lane-group kernel: level sizes that are not multiples of the 8 x 8 / 4-query tiles,
+    batch 2, offsets far outside the maps, and queries that are NOT the pyramid tokens (Nq != N,
+    not a multiple of 4: linear query order)."""
+    shapes = [(3, 5), (7, 10), (13, 21)]
+    n = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(11)
+    value = torch.randn(2, n, 256, generator=g)
+    for nq in (n, 37):
+        proj = torch.cat([torch.randn(2, nq, 192, generator=g) * 6.0, torch.randn(2, nq, 96, generator=g) * 3.0], -1)
+        ref_pts = torch.rand(nq, 2, generator=g)
+        ref = _fused_ref(value, shapes, proj, ref_pts)
+        out = ops.msda_fused_forward(value.cuda(), shapes, proj.cuda(), ref_pts.cuda())
+        close(out, ref.reshape(2, nq, 256), 1e-4, f'msda fused nq={nq}')
+
+
 # ------------------------------------------------------------------ attention --------
 def _mha_ref(q, k, v, H, mask=None):
     B, Lq, E = q.shape
@@ -278,6 +305,24 @@ def test_panoptic_fuse_upsampled(ops):
                                            instance_on=False)[0]['pan_results'].numpy()
     pan, _ = ops.panoptic_fuse(cls.cuda(), mp.cuda(), (H, W), (H - 8, W - 4), (61, 97), 115, 126)
     assert (pan.cpu().numpy() != ref).mean() < 2e-3   # composite bilinear: only near-tie pixels may differ
+
+
+@pytest.mark.parametrize('Q,NC,k', [(100, 126, 100), (7, 5, 35), (100, 126, 1), (33, 126, 64)])
+def test_instance_select(ops, Q, NC, k):
+    """softmax + flattened top-k (mask2former_fusion_head.py:214-222): same candidate SET and scores
+    as torch.topk; the order of sorted=False is unspecified."""
+    g = torch.Generator().manual_seed(Q + k)
+    cls = torch.randn(Q, NC + 1, generator=g) * 3.0
+    cls[1] = cls[0]                      # exact ties inside the scores
+    scores = torch.softmax(cls, -1)[:, :-1].flatten()
+    ref_s, ref_i = scores.topk(k, sorted=True)
+    s, lab, qi = ops.instance_select(cls.cuda(), k)
+    flat = (qi.cpu().long() * NC + lab.cpu().long())
+    assert flat.unique().numel() == k
+    close(s.cpu().sort(descending=True).values, ref_s, 1e-6, 'top-k scores')
+    close(s.cpu(), scores[flat], 1e-6, 'score / index consistency')
+    strictly_in = scores > ref_s[-1] + 1e-7          # everything clearly above the k-th value is selected
+    assert set(strictly_in.nonzero().flatten().tolist()) <= set(flat.tolist())
 
 
 def test_instance_masks(ops):

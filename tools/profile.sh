@@ -15,5 +15,5 @@ full gemm_tc_conv gemm_tc_kernel 3 --only conv --match '256->256@184x320'
 full gemm_tc_linear gemm_tc_kernel 3 --only gemm --match 'linear_154560x1024x256'
 full msda msda_kernel 3 --only msda
 full attn attn_kernel 3 --only attn --match '100x14720'
-full pan 'pan_|ins_' 3 --only pan
+full pan pan_pixel_kernel 1 --only pan
 ls -la gpurun_out/ | grep ${TAG}
