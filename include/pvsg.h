@@ -73,20 +73,23 @@ int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* lo, int64_t
 /* pvsg_linear on split operands.  A [M,K] planes (row stride lda), W [N,K] planes (ldw);
  * outputs (any subset): C fp32, (C_hi, C_lo) split planes, or mask/row_open = the sign-mask
  * epilogue of pvsg_mask_logits; all with row stride ldc.  K % 64 == 0, lda/ldw % 8 == 0.
+ * The residual is either fp32 (R) or itself split planes (R_hi, R_lo; r = hi + lo), row stride
+ * ldr -- activations can then live as planes only (no fp32 copy is written or read).
  * Returns PVSG_ERR_UNSUPPORTED for shapes it does not cover (caller uses pvsg_linear). */
 int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
                    const void* W_lo, int64_t ldw, const float* bias, const float* R, int64_t ldr,
                    float* C, void* C_hi, void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc,
-                   int64_t M, int64_t N, int64_t K, int act, void* stream);
+                   int64_t M, int64_t N, int64_t K, int act, const void* R_hi, const void* R_lo,
+                   void* stream);
 
 /* pvsg_conv2d_nhwc (stride 1 or 2) on split operands: x planes [B,H,W,Cin], w planes
  * [Cout,R,S,Cin]; im2col-free -- a 4-D TMA box over the NHWC planes is shifted per filter
  * tap (traversed with elementStrides = stride) and out-of-bounds zero fill provides the
- * padding.  Cin % 64 == 0. */
+ * padding.  Cin % 64 == 0.  residual fp32 or split planes (res_hi, res_lo) [B,OH,OW,Cout]. */
 int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                    const float* bias, const float* residual, float* y, void* y_hi, void* y_lo,
                    int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
-                   int act, void* stream);
+                   int act, const void* res_hi, const void* res_lo, void* stream);
 
 /* Small-Cin convolutions (the 7x7/2 RGB stem, Cin = 3): gathers the patches of x [B,H,W,Cin]
  * directly into split operand planes [B*OH*OW, Kpad] (k = (r*S + s)*Cin + c, zero-padded to

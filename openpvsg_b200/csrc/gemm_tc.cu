@@ -52,6 +52,8 @@ struct Cfg {
 struct TcParams {
     const float* bias;
     const float* R;
+    const __nv_bfloat16* R_hi;   // residual carried as split planes (r = hi + lo)
+    const __nv_bfloat16* R_lo;
     float* C;
     __nv_bfloat16* C_hi;
     __nv_bfloat16* C_lo;
@@ -61,7 +63,8 @@ struct TcParams {
     int num_kb;
     int act;
     int tiles_m, tiles_n;
-    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do, bit 2: R arrives by TMA
+    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do, bit 2: R arrives by TMA,
+                   // bit 3: R_hi / R_lo arrive by TMA
     // conv mode
     int conv, OH, OW, cin_kb, S, pad, stride, tiles_h, tiles_w;
 };
@@ -160,6 +163,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// tcgen05.ld issued early (next chunk) and completed later: the wait names the destination
+// registers as in/out operands so that no use of them can be scheduled before it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                   "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                   "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -168,6 +194,8 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
+
+__device__ __forceinline__ int64_t imin64_dev(int64_t a, int64_t b) { return a < b ? a : b; }
 
 struct Tile {
     int64_t m0;       // linear mode: first row
@@ -205,7 +233,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC_hi,
-               const __grid_constant__ CUtensorMap tmC_lo, const __grid_constant__ CUtensorMap tmR, TcParams p) {
+               const __grid_constant__ CUtensorMap tmC_lo, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int STAGES = Cfg<BN>::STAGES, B_BYTES = Cfg<BN>::B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -308,20 +337,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // split-bf16 outputs are staged in swizzled shared memory and written by TMA as whole
         // 32-row boxes (clipped to the matrix by the tensor map); unaligned outputs and the
         // sign-mask bytes keep the direct path.
+        //
+        // The chunk loop is a latency chain (TMEM load -> residual -> math -> staging -> TMA store),
+        // so every link is taken off the critical path:
+        //   * the next chunk's tcgen05.ld is issued before the current chunk is processed, and the
+        //     accumulator is handed back to the MMA warp as soon as its last chunk is in registers;
+        //   * the residual box of chunk c+1 is requested as soon as chunk c's box has been read;
+        //   * the 8 KB staging area of the warp is two 4 KB zones:
+        //       one kind of TMA output, no TMA residual : zones alternate -> the store of chunk c
+        //                                                 overlaps chunk c+1 (wait_group.read 1)
+        //       one kind of TMA output + TMA residual   : Z0 = residual landing zone, Z1 = output
+        //       fp32 AND planes out                     : Z0 = fp32 (residual lands in place),
+        //                                                 Z1 = planes (no overlap; rare)
         const int q = warp & 3;
         uint8_t* stage = smem + STAGES * STAGE_BYTES + (warp - 2) * EPI_STAGE_BYTES;
-        const uint32_t st_f32 = smem_u32(stage), st_hi = st_f32 + 4096, st_lo = st_f32 + 6144;
-        const bool tma_c = (p.tma_out & 1) != 0, tma_p = (p.tma_out & 2) != 0, tma_r = (p.tma_out & 4) != 0;
-        const bool use_tma = (p.C && tma_c) || (p.C_hi && tma_p);
+        const uint32_t z0 = smem_u32(stage), z1 = z0 + 4096;
+        const bool tma_c = (p.tma_out & 1) != 0 && p.C, tma_p = (p.tma_out & 2) != 0 && p.C_hi;
+        const bool tma_rf = (p.tma_out & 4) != 0, tma_rp = (p.tma_out & 8) != 0;
+        const bool tma_r = tma_rf || tma_rp;
+        const bool use_tma = tma_c || tma_p;
+        const bool both = tma_c && tma_p;
+        const bool alternate = use_tma && !both && !tma_r;
         uint64_t* my_r = &r_full[warp - 2];
-        uint32_t rph = 0;
+        uint32_t rph = 0, cc = 0;
         uint32_t ti = 0;
         int mt, nt;
         for (; next_tile(p, (int)ti, mt, nt); ++ti) {
             const Tile tl = decode_tile(p, mt, nt, BN);
             const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
-            mbar_wait(&acc_full[buf], aph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int nch = (int)((imin64_dev((int64_t)BN, p.N - tl.n0) + 31) >> 5);   // warp-uniform
             const int row_in_tile = q * 32 + lane;
             int64_t out_row;
             bool row_ok;
@@ -333,32 +377,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 out_row = tl.m0 + row_in_tile;
                 row_ok = out_row < p.M;
             }
+            // residual box of chunk `c` (fp32, or both its planes) -> landing zone.  With one kind
+            // of output that is Z0 (Z1 = output).  When fp32 AND planes are written the box lands IN
+            // the output zone of its own kind (fp32 -> Z0, planes -> Z1): every thread reads exactly
+            // the bytes it later overwrites with its results.
+            uint8_t* rdst = stage + ((both && tma_rp) ? 4096 : 0);
+            const uint32_t rz = smem_u32(rdst);
+            auto request_residual = [&](int c) {
+                const int n = tl.n0 + c * 32;
+                mbar_expect_tx(my_r, 32 * 32 * 4);
+                if (tma_rp) {
+                    if (p.conv) {
+                        tma_load_4d(&tmR_hi, my_r, rdst, n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
+                        tma_load_4d(&tmR_lo, my_r, rdst + 2048, n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
+                    } else {
+                        tma_load_2d(&tmR_hi, my_r, rdst, n, (int)(tl.m0 + q * 32));
+                        tma_load_2d(&tmR_lo, my_r, rdst + 2048, n, (int)(tl.m0 + q * 32));
+                    }
+                } else if (p.conv) {
+                    tma_load_4d(&tmR, my_r, rdst, n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
+                } else {
+                    tma_load_2d(&tmR, my_r, rdst, n, (int)(tl.m0 + q * 32));
+                }
+            };
+            if (tma_r) {
+                __syncwarp();   // every lane is done with the previous tile's last box
+                if (lane == 0) {
+                    if (both) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    request_residual(0);
+                }
+            }
+            mbar_wait(&acc_full[buf], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tbase = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+            uint32_t v[32];
+            tmem_ld32_issue(tbase, v);
             int open = 0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int64_t n = (int64_t)tl.n0 + c0;
-                if (n >= p.N) break;                                  // warp-uniform
-                if (use_tma || tma_r) {
-                    // the previous chunk's boxes must have left the staging buffers before they are
-                    // rewritten (by the residual load below or by this chunk's results)
+            for (int c = 0; c < nch; ++c, ++cc) {
+                const int64_t n = (int64_t)tl.n0 + c * 32;
+                if (tma_r && both && c > 0) {   // in-place landing: after the zone's last store was read out
                     __syncwarp();
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        if (tma_r) {   // residual box -> fp32 staging buffer, consumed (and overwritten) in place
-                            mbar_expect_tx(my_r, 32 * 32 * 4);
-                            if (p.conv)
-                                tma_load_4d(&tmR, my_r, stage, (int)n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
-                            else
-                                tma_load_2d(&tmR, my_r, stage, (int)n, (int)(tl.m0 + q * 32));
-                        }
+                        request_residual(c);
                     }
-                    __syncwarp();
                 }
-                uint32_t v[32];
-                tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 float f[32];
+                tmem_ld32_wait(v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (c + 1 < nch) {
+                    tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);
+                } else {
+                    // the whole accumulator is in registers: give it back to the MMA warp now
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
                 const bool full_chunk = n + 32 <= p.N;
                 if (p.bias) {
                     if (full_chunk && ((n & 3) == 0)) {
@@ -376,12 +452,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (tma_r) {
                     mbar_wait(my_r, rph);
                     rph ^= 1;
+                    if (tma_rp) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint4 t4 = lds_v4(st_f32 + lane * 128 + ((j ^ (lane & 7)) << 4));
-                        f[4 * j] += __uint_as_float(t4.x); f[4 * j + 1] += __uint_as_float(t4.y);
-                        f[4 * j + 2] += __uint_as_float(t4.z); f[4 * j + 3] += __uint_as_float(t4.w);
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+                            const uint4 h4 = lds_v4(rz + off), l4 = lds_v4(rz + 2048 + off);
+                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {   // bf16 -> fp32 is a 16-bit shift
+                                f[8 * j + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                                f[8 * j + 2 * e + 1] +=
+                                    __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 t4 = lds_v4(rz + lane * 128 + ((j ^ (lane & 7)) << 4));
+                            f[4 * j] += __uint_as_float(t4.x); f[4 * j + 1] += __uint_as_float(t4.y);
+                            f[4 * j + 2] += __uint_as_float(t4.z); f[4 * j + 3] += __uint_as_float(t4.w);
+                        }
                     }
+                    if (!both && c + 1 < nch) {      // the landing zone is free again: prefetch
+                        __syncwarp();
+                        if (lane == 0) request_residual(c + 1);
+                    }
+                } else if (p.R_hi && row_ok) {
+                    const __nv_bfloat16* rh = p.R_hi + out_row * p.ldr + n;
+                    const __nv_bfloat16* rl = p.R_lo + out_row * p.ldr + n;
+                    for (int j = 0; j < 32; ++j)
+                        if (n + j < p.N) f[j] += __bfloat162float(rh[j]) + __bfloat162float(rl[j]);
                 } else if (p.R && row_ok) {
                     const float* rr = p.R + out_row * p.ldr + n;
                     if (full_chunk && (p.ldr & 3) == 0) {
@@ -400,6 +500,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
+                // staging zones of this chunk
+                const uint32_t zone = alternate ? ((cc & 1) ? z1 : z0) : (both ? z0 : (tma_r ? z1 : z0));
+                const uint32_t st_f32 = zone;
+                const uint32_t st_hi = both ? z1 : zone, st_lo = st_hi + 2048;
+                if (use_tma) {
+                    // the zone(s) about to be rewritten must have been read out by their last store
+                    if (lane == 0) {
+                        if (alternate) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                }
                 if (p.C) {
                     if (tma_c) {
                         // 128-byte rows, 16-byte pieces XOR-swizzled by (row & 7): conflict-free
@@ -407,16 +519,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         for (int j = 0; j < 8; ++j)
                             sts_v4(st_f32 + lane * 128 + ((j ^ (lane & 7)) << 4), v4u(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
                     } else if (row_ok) {
-                        float* cc = p.C + out_row * p.ldc + n;
+                        float* cp = p.C + out_row * p.ldc + n;
                         if (full_chunk && (p.ldc & 3) == 0) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                reinterpret_cast<float4*>(cc)[j] =
+                                reinterpret_cast<float4*>(cp)[j] =
                                     make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (n + j < p.N) cc[j] = f[j];
+                                if (n + j < p.N) cp[j] = f[j];
                         }
                     }
                 }
@@ -465,15 +577,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         const int r0 = q * 32;
                         if (p.conv) {
                             const int oh = tl.oh0 + r0 / PATCH_W;
-                            if (p.C && tma_c) tma_store_4d(&tmC, st_f32, (int)n, tl.ow0, oh, tl.tb);
-                            if (p.C_hi && tma_p) {
+                            if (tma_c) tma_store_4d(&tmC, st_f32, (int)n, tl.ow0, oh, tl.tb);
+                            if (tma_p) {
                                 tma_store_4d(&tmC_hi, st_hi, (int)n, tl.ow0, oh, tl.tb);
                                 tma_store_4d(&tmC_lo, st_lo, (int)n, tl.ow0, oh, tl.tb);
                             }
                         } else {
                             const int row0 = (int)(tl.m0 + r0);
-                            if (p.C && tma_c) tma_store_2d(&tmC, st_f32, (int)n, row0);
-                            if (p.C_hi && tma_p) {
+                            if (tma_c) tma_store_2d(&tmC, st_f32, (int)n, row0);
+                            if (tma_p) {
                                 tma_store_2d(&tmC_hi, st_hi, (int)n, row0);
                                 tma_store_2d(&tmC_lo, st_lo, (int)n, row0);
                             }
@@ -509,9 +621,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
             }
             if (p.mask && p.row_open && row_ok && open) atomicAdd(p.row_open + out_row, open);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     }
@@ -678,14 +787,17 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     const unsigned grid = (unsigned)imin64(tiles, sm_count());
     TcParams q = p;
     static const bool direct = getenv("PVSG_TC_DIRECT_STORE") != nullptr;
-    CUtensorMap c{}, c_hi{}, c_lo{}, r{};
+    CUtensorMap c{}, c_hi{}, c_lo{}, r{}, r_hi{}, r_lo{};
     q.tma_out = 0;
     if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B, p.ldc)) q.tma_out |= 1;
     if (!direct && p.C_hi && p.ldc % 8 == 0 && al16(p.C_hi) && al16(p.C_lo) &&
         make_out_map(&c_hi, p.C_hi, false, p, B, p.ldc) && make_out_map(&c_lo, p.C_lo, false, p, B, p.ldc))
         q.tma_out |= 2;
     if (!direct && p.R && p.ldr % 4 == 0 && al16(p.R) && make_out_map(&r, p.R, true, p, B, p.ldr)) q.tma_out |= 4;
-    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, r, q);
+    if (!direct && p.R_hi && p.ldr % 8 == 0 && al16(p.R_hi) && al16(p.R_lo) &&
+        make_out_map(&r_hi, p.R_hi, false, p, B, p.ldr) && make_out_map(&r_lo, p.R_lo, false, p, B, p.ldr))
+        q.tma_out |= 8;
+    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, r, r_hi, r_lo, q);
     return pvsg_launch_status();
 }
 
@@ -725,10 +837,11 @@ extern "C" int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* 
 extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo,
                               int64_t ldw, const float* bias, const float* R, int64_t ldr, float* C, void* C_hi,
                               void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc, int64_t M, int64_t N,
-                              int64_t K, int act, void* stream) {
+                              int64_t K, int act, const void* R_hi, const void* R_lo, void* stream) {
     PVSG_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && (C || C_hi || mask) && M > 0 && N > 0 && K > 0);
     PVSG_CHECK_ARG((C_hi == nullptr) == (C_lo == nullptr));
-    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N));
+    PVSG_CHECK_ARG((R_hi == nullptr) == (R_lo == nullptr) && !(R && R_hi));
+    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && ((!R && !R_hi) || ldr >= N));
     if (K % BK != 0 || lda % 8 != 0 || ldw % 8 != 0 || !al16(A_hi) || !al16(A_lo) || !al16(W_hi) || !al16(W_lo))
         return PVSG_ERR_UNSUPPORTED;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || ((M + BM - 1) / BM) * ((N + 127) / 128) > 0x7fffffffLL)
@@ -740,6 +853,7 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
         return PVSG_ERR_LAUNCH;
     TcParams p{};
     p.bias = bias; p.R = R; p.C = C;
+    p.R_hi = reinterpret_cast<const __nv_bfloat16*>(R_hi); p.R_lo = reinterpret_cast<const __nv_bfloat16*>(R_lo);
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
@@ -751,8 +865,9 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
 extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                               const float* bias, const float* residual, float* y, void* y_hi, void* y_lo, int B,
                               int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int act,
-                              void* stream) {
+                              const void* res_hi, const void* res_lo, void* stream) {
     PVSG_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && (y || y_hi) && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+    PVSG_CHECK_ARG((res_hi == nullptr) == (res_lo == nullptr) && !(residual && res_hi));
     PVSG_CHECK_ARG((y_hi == nullptr) == (y_lo == nullptr) && R > 0 && S > 0 && pad >= 0);
     if (Cin % BK != 0 || !al16(x_hi) || !al16(x_lo) || !al16(w_hi) || !al16(w_lo)) return PVSG_ERR_UNSUPPORTED;
     if (stride < 1 || stride > 2) return PVSG_ERR_UNSUPPORTED;
@@ -768,6 +883,7 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
         return PVSG_ERR_LAUNCH;
     TcParams p{};
     p.bias = bias; p.R = residual; p.C = y;
+    p.R_hi = reinterpret_cast<const __nv_bfloat16*>(res_hi); p.R_lo = reinterpret_cast<const __nv_bfloat16*>(res_lo);
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
     p.M = (int64_t)B * OH * OW; p.N = Cout; p.ldc = Cout; p.ldr = Cout; p.act = act;
     p.num_kb = (int)(K / BK); p.conv = 1; p.OH = OH; p.OW = OW; p.cin_kb = Cin / BK; p.S = S; p.pad = pad; p.stride = stride;

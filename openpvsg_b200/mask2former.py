@@ -141,9 +141,10 @@ class ResNet(_Prepared):
         ops.clear_split_cache()
         x = ops.conv2d_nhwc(x, *p['stem'], stride=2, pad=3, act=ops.ACT_RELU)
         x = ops.maxpool3x3s2_nhwc(x)
-        # Inside a bottleneck the 1x1 -> 3x3 -> 1x1 chain hands operand planes from epilogue to
-        # TMA loader (out_mode='split': the fp32 tensor is never written); the block output is
-        # needed both as fp32 (next residual) and as planes (next convs): out_mode='both'.
+        # On the tcgen05 engine activations live as operand planes only: the 1x1 -> 3x3 -> 1x1 chain
+        # hands planes from epilogue to TMA loader (out_mode='split'), and the identity branch is
+        # added from its planes too (r = hi + lo), so no fp32 copy of a block output is written or
+        # read.  Only the stage outputs that leave the backbone are also materialised as fp32.
         xs = ops.maybe_split(x)
         outs = []
         nblk = len(p['blocks'])
@@ -151,12 +152,15 @@ class ResNet(_Prepared):
             inp = xs if xs is not None else x
             o = ops.conv2d_nhwc(inp, *d['c1'], act=ops.ACT_RELU, out_mode='split')
             o = ops.conv2d_nhwc(o, *d['c2'], stride=d['stride'], pad=1, act=ops.ACT_RELU, out_mode='split')
-            idt = x if d['ds'] is None else ops.conv2d_nhwc(inp, *d['ds'], stride=d['stride'])
-            x, xs = ops.conv2d_nhwc(o, *d['c3'], residual=idt, act=ops.ACT_RELU, out_mode='both')
-            if j + 1 == nblk or p['blocks'][j + 1]['stage'] != d['stage']:
-                if d['stage'] in self.out_indices:
-                    ops.remember_split(x, xs)   # the pixel decoder's 1x1 convs reuse these planes
-                    outs.append(_as_nchw(x))
+            idt = inp if d['ds'] is None else ops.conv2d_nhwc(inp, *d['ds'], stride=d['stride'], out_mode='split')
+            leaves = (j + 1 == nblk or p['blocks'][j + 1]['stage'] != d['stage']) and d['stage'] in self.out_indices
+            if leaves or xs is None:
+                x, xs = ops.conv2d_nhwc(o, *d['c3'], residual=idt, act=ops.ACT_RELU, out_mode='both')
+            else:
+                x, xs = None, ops.conv2d_nhwc(o, *d['c3'], residual=idt, act=ops.ACT_RELU, out_mode='split')
+            if leaves:
+                ops.remember_split(x, xs)   # the pixel decoder's 1x1 convs reuse these planes
+                outs.append(_as_nchw(x))
         return tuple(outs)
 
 

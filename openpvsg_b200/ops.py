@@ -226,16 +226,20 @@ def _linear_tc(lib, planes, w2, bias, residual, act, out, lead, M, N, K, out_mod
             raise _l.PvsgError('linear: split output needs a dense fp32 output')
         c_hi = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         c_lo = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    r2, ldr = None, 0
-    if residual is not None:
+    r2, ldr, r_hi, r_lo = None, 0, None, None
+    if isinstance(residual, Split):      # residual carried as planes: r = hi + lo
+        if residual.hi.numel() != M * N or not (residual.hi.is_contiguous() and residual.lo.is_contiguous()):
+            raise _l.PvsgError('linear: bad residual planes')
+        r_hi, r_lo, ldr = residual.hi, residual.lo, N
+    elif residual is not None:
         r2, Mr, Nr, ldr = _rows(residual, 'residual')
         if (Mr, Nr) != (M, N):
             raise _l.PvsgError('linear: bad residual shape')
     if bias is not None and (_f32(bias, 'bias').numel() != N or not bias.is_contiguous()):
         raise _l.PvsgError('linear: bad bias')
     _l.check(lib.pvsg_linear_tc(_ptr(planes.hi), _ptr(planes.lo), K, _ptr(w_hi), _ptr(w_lo), K, _ptr(bias), _ptr(r2),
-                                ldr, _ptr(o2), _ptr(c_hi), _ptr(c_lo), None, None, ldc, M, N, K, act, _stream()),
-             'pvsg_linear_tc')
+                                ldr, _ptr(o2), _ptr(c_hi), _ptr(c_lo), None, None, ldc, M, N, K, act, _ptr(r_hi),
+                                _ptr(r_lo), _stream()), 'pvsg_linear_tc')
     f32 = (out.reshape(*lead, N) if created else out) if want_f32 else None
     sp = Split(c_hi.view(*lead, N), c_lo.view(*lead, N)) if want_split else None
     if out_mode == 'both':
@@ -255,6 +259,8 @@ def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NO
         Cout, R, S, _ = weight.shape
         if R == 1 and S == 1 and pad == 0 and stride == 1:
             r = residual.view(-1, Cout) if residual is not None else None
+            if r is not None and isinstance(r, Split) and not isinstance(x, Split):
+                raise _l.PvsgError('conv2d_nhwc: plane residual needs plane input')
             res = linear(x.view(B * H * W, Cin) if isinstance(x, Split) else x.view(B * H * W, Cin),
                          weight.view(Cout, Cin), bias, residual=r, act=act, out_mode=out_mode)
             shp = (B, H, W, Cout)
@@ -270,11 +276,16 @@ def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NO
         y = torch.empty(B, OH, OW, Cout, device=dev, dtype=torch.float32) if want_f32 else None
         y_hi = torch.empty(B, OH, OW, Cout, device=dev, dtype=torch.bfloat16) if want_split else None
         y_lo = torch.empty(B, OH, OW, Cout, device=dev, dtype=torch.bfloat16) if want_split else None
-        if residual is not None and (tuple(residual.shape) != (B, OH, OW, Cout) or not residual.is_contiguous()):
+        r_hi = r_lo = None
+        if isinstance(residual, Split):
+            if tuple(residual.shape) != (B, OH, OW, Cout) or not residual.hi.is_contiguous():
+                raise _l.PvsgError('conv2d_nhwc: bad residual planes')
+            r_hi, r_lo, residual = residual.hi, residual.lo, None
+        elif residual is not None and (tuple(residual.shape) != (B, OH, OW, Cout) or not residual.is_contiguous()):
             raise _l.PvsgError('conv2d_nhwc: bad residual')
         _l.check(lib.pvsg_conv2d_tc(_ptr(xs.hi), _ptr(xs.lo), _ptr(w_hi), _ptr(w_lo), _ptr(_f32(bias)),
                                     _ptr(_f32(residual)), _ptr(y), _ptr(y_hi), _ptr(y_lo), B, H, W, Cin, Cout, R, S,
-                                    stride, pad, act, _stream()), 'pvsg_conv2d_tc')
+                                    stride, pad, act, _ptr(r_hi), _ptr(r_lo), _stream()), 'pvsg_conv2d_tc')
         sp = Split(y_hi, y_lo) if want_split else None
         if out_mode == 'both':
             return y, sp
@@ -510,7 +521,7 @@ def mask_logits(embed, feat, want_logits=True, want_mask=False, feat_planes=None
             _l.check(lib.pvsg_linear_tc(_ptr(e_hi[b]), _ptr(e_lo[b]), C, _ptr(f_hi[b]), _ptr(f_lo[b]), C, None, None,
                                         0, _ptr(logits[b]) if want_logits else None, None, None,
                                         _ptr(mask[b]) if want_mask else None,
-                                        _ptr(row_open[b]) if want_mask else None, P, Q, P, C, ACT_NONE, _stream()),
+                                        _ptr(row_open[b]) if want_mask else None, P, Q, P, C, ACT_NONE, None, None, _stream()),
                      'pvsg_linear_tc')
         return logits, mask, row_open
     logits = torch.empty(B, Q, P, device=embed.device, dtype=torch.float32) if want_logits else None

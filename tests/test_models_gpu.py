@@ -220,13 +220,49 @@ def test_batched_runner_matches_single_frames(detectors, cuda):
         det._runners = None
     assert len(got) == 5
     for a, b in zip(got + [g1], singles + [singles[0]]):
-        assert np.array_equal(a['pan_results'], b['pan_results'])
+        # batch and single-frame passes pick different kernels / tile shapes (fp32 re-association) and
+        # the sign-test attention masks amplify that: same bar as vs the oracle
+        assert (a['pan_results'] != b['pan_results']).mean() <= 1e-3
         assert sorted(a['query_feats']) == sorted(b['query_feats'])
         for k in b['query_feats']:
-            # batch and single-frame passes pick different tile shapes (fp32 re-association), and the
-            # sign-test attention masks amplify that: same bar as vs the oracle
             close(torch.as_tensor(a['query_feats'][k][0]), torch.as_tensor(b['query_feats'][k][0]), TOL, 'query feat')
         assert [len(x) for x in a['ins_results'][0]] == [len(x) for x in b['ins_results'][0]]
+
+
+def test_runner_pipeline_is_deterministic(detectors, cuda):
+    """The copy-stream / staging-ring plumbing of engine.FrameRunner: the same frames pushed through
+    with more submits in flight than ring slots are wrapped around, mixed pinned-host and device
+    inputs, must give bit-identical results to a submit-collect-submit-collect pass."""
+    from openpvsg_b200 import engine
+    dets, sd = detectors
+    det = dets[True]
+    H, W = 96, 160
+    meta = syn.frame_meta(H, W)
+    frames = [syn.synthetic_frame(80 + i, H, W) for i in range(10)]
+    engine.enable_cuda_graph(det)
+    try:
+        runner = engine.get_runner(det, meta, True, batch=2)
+        serial = []
+        for i in range(0, 10, 2):
+            serial += runner.collect(runner.submit([f.to(cuda) for f in frames[i:i + 2]]))
+        piped, pend = [], []
+        for i in range(0, 10, 2):
+            src = [f.pin_memory() for f in frames[i:i + 2]] if (i // 2) % 2 == 0 else [f.to(cuda) for f in frames[i:i + 2]]
+            pend.append(runner.submit(src))
+            if len(pend) == engine.RING - 1:       # keep RING - 1 batches in flight
+                piped += runner.collect(pend.pop(0))
+        while pend:
+            piped += runner.collect(pend.pop(0))
+    finally:
+        det._runners = None
+    assert len(serial) == len(piped) == 10
+    for a, b in zip(serial, piped):
+        assert np.array_equal(a['pan_results'], b['pan_results'])
+        assert sorted(a['query_feats']) == sorted(b['query_feats'])
+        for k in a['query_feats']:
+            assert torch.equal(torch.as_tensor(a['query_feats'][k][0]), torch.as_tensor(b['query_feats'][k][0]))
+        for ma, mb in zip(a['ins_results'][1], b['ins_results'][1]):
+            assert len(ma) == len(mb) and all(np.array_equal(x, y) for x, y in zip(ma, mb))
 
 
 def test_minvis_clip_vs_oracle(cuda):

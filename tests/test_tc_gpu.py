@@ -82,3 +82,58 @@ def test_conv_tc(ops, cin, cout, k, pad, hw, B, stride):
     ref = F.relu(ref + res.double())
     err = (y.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
     assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+
+
+def _planes_value(sp):
+    return sp.hi.float().cpu().double() + sp.lo.float().cpu().double()
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 256, 64), (1000, 288, 256), (19320, 256, 128), (333, 1024, 256),
+                                   (257, 64, 576)])
+@pytest.mark.parametrize('res_kind', ['none', 'f32', 'planes'])
+@pytest.mark.parametrize('out_mode', ['f32', 'split', 'both'])
+def test_linear_tc_output_and_residual_modes(ops, M, N, K, res_kind, out_mode):
+    """Every epilogue staging scheme of gemm_tc_kernel: one / both kinds of TMA output x
+    (no residual | fp32 residual box | residual carried as split planes), ragged M and N."""
+    x, w, b = randn(1, M, K), randn(2, N, K) / K ** 0.5, randn(3, N)
+    res = randn(4, M, N)
+    planes = ops.Split(*ops.split_bf16(x.cuda()))
+    if res_kind == 'planes':
+        r = ops.Split(*ops.split_bf16(res.cuda()))
+        res_val = _planes_value(r)
+    elif res_kind == 'f32':
+        r, res_val = res.cuda(), res.double()
+    else:
+        r, res_val = None, torch.zeros(M, N, dtype=torch.float64)
+    y = ops.linear(planes, w.cuda(), b.cuda(), residual=r, act=ops.ACT_RELU, out_mode=out_mode)
+    ref = F.relu(F.linear(_planes_value(planes), w.double(), b.double()) + res_val)
+    tol = 3e-5 * max(1.0, ref.abs().max().item())
+    f32, sp = (y if out_mode == 'both' else (y, None) if out_mode == 'f32' else (None, y))
+    if f32 is not None:
+        assert (f32.cpu().double() - ref).abs().max().item() < tol
+    if sp is not None:
+        assert isinstance(sp, ops.Split)
+        assert (_planes_value(sp) - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize('cin,cout,k,pad,hw,B,stride', [(64, 256, 1, 0, (45, 77), 2, 1), (128, 128, 3, 1, (47, 81), 2, 1),
+                                                        (256, 512, 1, 0, (46, 80), 1, 2)])
+@pytest.mark.parametrize('out_mode', ['split', 'both'])
+def test_conv_tc_plane_residual(ops, cin, cout, k, pad, hw, B, stride, out_mode):
+    """The bottleneck's identity branch added from its operand planes (ResNet.forward)."""
+    x = randn(1, B, cin, *hw)
+    w = randn(2, cout, cin, k, k) / (cin * k * k) ** 0.5
+    b = randn(3, cout)
+    xs = ops.Split(*ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda()))
+    xv = _planes_value(xs).permute(0, 3, 1, 2)
+    ref = F.conv2d(xv, w.double(), b.double(), stride, pad)
+    res = randn(4, *ref.shape)
+    rs = ops.Split(*ops.split_bf16(res.permute(0, 2, 3, 1).contiguous().cuda()))
+    y = ops.conv2d_nhwc(xs, w.permute(0, 2, 3, 1).contiguous().cuda(), b.cuda(), residual=rs, stride=stride, pad=pad,
+                        act=ops.ACT_RELU, out_mode=out_mode)
+    ref = F.relu(ref + _planes_value(rs).permute(0, 3, 1, 2))
+    tol = 3e-5 * max(1.0, ref.abs().max().item())
+    f32, sp = y if out_mode == 'both' else (None, y)
+    assert (_planes_value(sp).permute(0, 3, 1, 2) - ref).abs().max().item() < tol
+    if f32 is not None:
+        assert (f32.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item() < tol
