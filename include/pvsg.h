@@ -74,13 +74,16 @@ int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* lo, int64_t
  * outputs (any subset): C fp32, (C_hi, C_lo) split planes, or mask/row_open = the sign-mask
  * epilogue of pvsg_mask_logits; all with row stride ldc.  K % 64 == 0, lda/ldw % 8 == 0.
  * The residual is either fp32 (R) or itself split planes (R_hi, R_lo; r = hi + lo), row stride
- * ldr -- activations can then live as planes only (no fp32 copy is written or read).
+ * ldr -- activations can then live as planes only (no fp32 copy is written or read).  With
+ * `ident` (a bf16 [256,256] identity matrix in device memory, supplied by the caller because the
+ * library never allocates) the plane residual is added BY THE TENSOR CORE as extra k-blocks
+ * R_hi.I + R_lo.I, exact in the fp32 accumulator, so its bytes ride the main TMA pipeline.
  * Returns PVSG_ERR_UNSUPPORTED for shapes it does not cover (caller uses pvsg_linear). */
 int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi,
                    const void* W_lo, int64_t ldw, const float* bias, const float* R, int64_t ldr,
                    float* C, void* C_hi, void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc,
                    int64_t M, int64_t N, int64_t K, int act, const void* R_hi, const void* R_lo,
-                   void* stream);
+                   const void* ident, void* stream);
 
 /* pvsg_conv2d_nhwc (stride 1 or 2) on split operands: x planes [B,H,W,Cin], w planes
  * [Cout,R,S,Cin]; im2col-free -- a 4-D TMA box over the NHWC planes is shifted per filter

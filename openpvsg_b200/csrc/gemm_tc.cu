@@ -7,7 +7,7 @@
 // accumulated in the same TMEM tile:  hi.hi + hi.lo + lo.hi  (the dropped lo.lo term and
 // the residual of the split are ~2^-17 relative, i.e. fp32 re-association level).
 //
-// Persistent kernel, one CTA per SM, 576 threads, tiles of 128 x 128 (or 128 x 256) handed out
+// Persistent kernel, one CTA per SM, 320 threads, tiles of 128 x 128 (or 128 x 256) handed out
 // round-robin:
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor (128B swizzle) of A_hi, A_lo, W_hi, W_lo
 //              k-blocks of 64 into a 3-stage shared-memory ring (mbarrier complete_tx); runs
@@ -16,9 +16,9 @@
 //              (kind::f16, bf16 x bf16 -> fp32, M = 128, N = 128, K = 16) x 3 x 4 per stage into
 //              one of TWO TMEM accumulators; tcgen05.commit releases the stage / publishes
 //              the accumulator
-//   warps 2-17: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), bias / residual / ReLU,
-//              128-bit fp32, split-bf16 or sign-mask stores; overlaps the next tile's main loop
-//              through the second accumulator
+//   warps 2-9: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), bias / residual / ReLU,
+//              fp32 / split-bf16 boxes staged in shared memory and written by TMA, or sign-mask
+//              stores; overlaps the next tile's main loop through the second accumulator
 // Convolutions use a 4-D tensor map over the NHWC planes: the M tile is an 8 x 16 patch of
 // output pixels and every filter tap is the same TMA box shifted by (r - pad, s - pad); TMA's
 // out-of-bounds zero fill is the convolution's zero padding.  No im2col buffer exists.
@@ -31,9 +31,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;             // bf16 elements = 128 bytes = one swizzle row
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
-constexpr int EPI_STAGE_BYTES = 8192;      // per epilogue warp: 32 x 32 fp32 | 32 x 32 bf16 hi | lo
+constexpr int EPI_STAGE_BYTES = 4096;      // per epilogue warp: 32 x 32 fp32, or 32 x 32 bf16 hi | lo
 constexpr int PATCH_H = 8, PATCH_W = 16;   // conv M tile = 8 x 16 output pixels
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 // Tile width BN = 128 (3-stage ring) or 256 (2-stage ring).  The wide tile reads each A k-block
@@ -54,6 +54,7 @@ struct TcParams {
     const float* R;
     const __nv_bfloat16* R_hi;   // residual carried as split planes (r = hi + lo)
     const __nv_bfloat16* R_lo;
+    const void* ident;           // bf16 [256, 256] identity matrix (B operand of the residual k-blocks)
     float* C;
     __nv_bfloat16* C_hi;
     __nv_bfloat16* C_lo;
@@ -63,8 +64,8 @@ struct TcParams {
     int num_kb;
     int act;
     int tiles_m, tiles_n;
-    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do, bit 2: R arrives by TMA,
-                   // bit 3: R_hi / R_lo arrive by TMA
+    int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do, bit 2: fp32 R arrives by TMA
+    int res_mma;   // residual planes are added by the tensor core (extra k-blocks against the identity)
     // conv mode
     int conv, OH, OW, cin_kb, S, pad, stride, tiles_h, tiles_w;
 };
@@ -234,7 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC_hi,
                const __grid_constant__ CUtensorMap tmC_lo, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo, TcParams p) {
+               const __grid_constant__ CUtensorMap tmRa_hi, const __grid_constant__ CUtensorMap tmRa_lo,
+               const __grid_constant__ CUtensorMap tmE, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int STAGES = Cfg<BN>::STAGES, B_BYTES = Cfg<BN>::B_BYTES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
@@ -244,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
     uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
-    uint64_t* r_full = acc_empty + 2;         // [EPI_WARPS] residual box landed (per epilogue warp)
+    uint64_t* r_full = acc_empty + 2;         // [EPI_WARPS] fp32 residual box landed (per epilogue warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&r_full[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: two 128-column fp32 accumulators x 128 lanes
+    if (warp == 1) {   // TMEM: two BN-column fp32 accumulators x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -265,6 +267,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+
+    // Residual carried as split planes (linear mode): it goes through the TENSOR CORE.  After the
+    // K blocks of A.W^T the tile gets BN/64 more k-blocks whose A operand is the residual's own
+    // (hi, lo) planes, columns n0 + 64j .., and whose B operand is a slice of the identity matrix:
+    // acc += R_hi.I + R_lo.I, exact in the fp32 accumulator.  The residual bytes then ride the deep
+    // TMA ring of the main loop instead of a 4 KB-at-a-time epilogue fetch (which capped these
+    // HBM-bound layers at ~1.6 TB/s of residual traffic), and the epilogue has no residual at all.
+    const int res_kb = p.res_mma ? BN / BK : 0;
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------------
@@ -292,6 +302,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
                     tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
                 }
+                for (int j = 0; j < res_kb; ++j) {
+                    if ((int64_t)tl.n0 + j * BK >= p.N) break;      // same rule in the MMA warp
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ++it;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], 2 * A_BYTES + B_BYTES);
+                    tma_load_2d(&tmRa_hi, &full[s], st, tl.n0 + j * BK, (int)tl.m0);
+                    tma_load_2d(&tmRa_lo, &full[s], st + A_BYTES, tl.n0 + j * BK, (int)tl.m0);
+                    tma_load_2d(&tmE, &full[s], st + 2 * A_BYTES, j * BK, 0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -304,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             int mt, nt;
             for (; next_tile(p, (int)ti, mt, nt); ++ti) {
                 const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
+                const int n0 = nt * BN;
                 mbar_wait(&acc_empty[buf], aph ^ 1);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + buf * BN;
@@ -327,39 +350,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                     umma_commit(&empty[s]);          // stage reusable once these MMAs retire
                 }
+                for (int j = 0; j < res_kb; ++j) {    // acc += R_lo.I + R_hi.I
+                    if ((int64_t)n0 + j * BK >= p.N) break;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ++it;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t off = k * 32;
+                        const uint64_t dbh = umma_desc(b_hi + off);
+                        umma_bf16(tmem_d, umma_desc(a_lo + off), dbh, idesc, 1);
+                        umma_bf16(tmem_d, umma_desc(a_hi + off), dbh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
+                }
                 umma_commit(&acc_full[buf]);         // accumulator complete
             }
         }
     } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-        // thread = one accumulator row, 32 columns per tcgen05.ld.  Row-per-thread 16-byte global
-        // stores reach only ~1.7 TB/s (every store instruction touches 32 lines), so fp32 and
-        // split-bf16 outputs are staged in swizzled shared memory and written by TMA as whole
-        // 32-row boxes (clipped to the matrix by the tensor map); unaligned outputs and the
-        // sign-mask bytes keep the direct path.
-        //
-        // The chunk loop is a latency chain (TMEM load -> residual -> math -> staging -> TMA store),
-        // so every link is taken off the critical path:
-        //   * the next chunk's tcgen05.ld is issued before the current chunk is processed, and the
-        //     accumulator is handed back to the MMA warp as soon as its last chunk is in registers;
-        //   * the residual box of chunk c+1 is requested as soon as chunk c's box has been read;
-        //   * the 8 KB staging area of the warp is two 4 KB zones:
-        //       one kind of TMA output, no TMA residual : zones alternate -> the store of chunk c
-        //                                                 overlaps chunk c+1 (wait_group.read 1)
-        //       one kind of TMA output + TMA residual   : Z0 = residual landing zone, Z1 = output
-        //       fp32 AND planes out                     : Z0 = fp32 (residual lands in place),
-        //                                                 Z1 = planes (no overlap; rare)
-        const int q = warp & 3;
+        // ---------------- epilogue: warps 2..9 ------------------------------------------------
+        // TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter take the even /
+        // odd 32-column chunks.  thread = one accumulator row, 32 columns per tcgen05.ld.
+        // A lone warp per scheduler cannot hide its own ALU / shared-memory latencies (measured IPC
+        // ~0.2 with four epilogue warps), so the epilogue runs EIGHT warps and software-pipelines
+        // the TMEM loads; the accumulator goes back to the MMA warp as soon as its last chunk is in
+        // registers.
+        // Row-per-thread 16-byte global stores reach only ~1.7 TB/s (every store instruction touches
+        // 32 lines), so fp32 and split-bf16 outputs are staged in swizzled shared memory (4 KB per
+        // warp: 32 x 32 fp32, or 32 x 32 bf16 hi | lo) and written by TMA as whole 32-row boxes
+        // (clipped to the matrix by the tensor map); when both kinds are written they take turns in
+        // the zone.  An fp32 residual box lands in the zone and is consumed in place (every thread
+        // reads exactly the bytes it later overwrites).  Unaligned outputs and the sign-mask bytes
+        // keep the direct path.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         uint8_t* stage = smem + STAGES * STAGE_BYTES + (warp - 2) * EPI_STAGE_BYTES;
-        const uint32_t z0 = smem_u32(stage), z1 = z0 + 4096;
+        const uint32_t zone = smem_u32(stage);
         const bool tma_c = (p.tma_out & 1) != 0 && p.C, tma_p = (p.tma_out & 2) != 0 && p.C_hi;
-        const bool tma_rf = (p.tma_out & 4) != 0, tma_rp = (p.tma_out & 8) != 0;
-        const bool tma_r = tma_rf || tma_rp;
+        const bool tma_r = (p.tma_out & 4) != 0;
         const bool use_tma = tma_c || tma_p;
-        const bool both = tma_c && tma_p;
-        const bool alternate = use_tma && !both && !tma_r;
         uint64_t* my_r = &r_full[warp - 2];
-        uint32_t rph = 0, cc = 0;
+        uint32_t rph = 0;
         uint32_t ti = 0;
         int mt, nt;
         for (; next_tile(p, (int)ti, mt, nt); ++ti) {
@@ -377,60 +412,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 out_row = tl.m0 + row_in_tile;
                 row_ok = out_row < p.M;
             }
-            // residual box of chunk `c` (fp32, or both its planes) -> landing zone.  With one kind
-            // of output that is Z0 (Z1 = output).  When fp32 AND planes are written the box lands IN
-            // the output zone of its own kind (fp32 -> Z0, planes -> Z1): every thread reads exactly
-            // the bytes it later overwrites with its results.
-            uint8_t* rdst = stage + ((both && tma_rp) ? 4096 : 0);
-            const uint32_t rz = smem_u32(rdst);
-            auto request_residual = [&](int c) {
-                const int n = tl.n0 + c * 32;
-                mbar_expect_tx(my_r, 32 * 32 * 4);
-                if (tma_rp) {
-                    if (p.conv) {
-                        tma_load_4d(&tmR_hi, my_r, rdst, n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
-                        tma_load_4d(&tmR_lo, my_r, rdst + 2048, n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
-                    } else {
-                        tma_load_2d(&tmR_hi, my_r, rdst, n, (int)(tl.m0 + q * 32));
-                        tma_load_2d(&tmR_lo, my_r, rdst + 2048, n, (int)(tl.m0 + q * 32));
-                    }
-                } else if (p.conv) {
-                    tma_load_4d(&tmR, my_r, rdst, n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
-                } else {
-                    tma_load_2d(&tmR, my_r, rdst, n, (int)(tl.m0 + q * 32));
-                }
-            };
-            if (tma_r) {
-                __syncwarp();   // every lane is done with the previous tile's last box
-                if (lane == 0) {
-                    if (both) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    request_residual(0);
-                }
-            }
             mbar_wait(&acc_full[buf], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tbase = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
             uint32_t v[32];
-            tmem_ld32_issue(tbase, v);
+            if (half < nch) tmem_ld32_issue(tbase + (uint32_t)(half * 32), v);
+            else {   // nothing to do in this tile (narrow edge tile): just hand the accumulator back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
             int open = 0;
 #pragma unroll 1
-            for (int c = 0; c < nch; ++c, ++cc) {
+            for (int c = half; c < nch; c += 2) {
                 const int64_t n = (int64_t)tl.n0 + c * 32;
-                if (tma_r && both && c > 0) {   // in-place landing: after the zone's last store was read out
+                if (tma_r) {
+                    // fp32 residual box -> zone (after the zone's last store has been read out)
                     __syncwarp();
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        request_residual(c);
+                        mbar_expect_tx(my_r, 32 * 32 * 4);
+                        if (p.conv)
+                            tma_load_4d(&tmR, my_r, stage, (int)n, tl.ow0, tl.oh0 + (q * 32) / PATCH_W, tl.tb);
+                        else
+                            tma_load_2d(&tmR, my_r, stage, (int)n, (int)(tl.m0 + q * 32));
                     }
                 }
                 float f[32];
                 tmem_ld32_wait(v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (c + 1 < nch) {
-                    tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);
+                if (c + 2 < nch) {
+                    tmem_ld32_issue(tbase + (uint32_t)((c + 2) * 32), v);
                 } else {
-                    // the whole accumulator is in registers: give it back to the MMA warp now
+                    // this warp's share of the accumulator is in registers: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -452,32 +467,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (tma_r) {
                     mbar_wait(my_r, rph);
                     rph ^= 1;
-                    if (tma_rp) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-                            const uint4 h4 = lds_v4(rz + off), l4 = lds_v4(rz + 2048 + off);
-                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {   // bf16 -> fp32 is a 16-bit shift
-                                f[8 * j + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-                                f[8 * j + 2 * e + 1] +=
-                                    __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint4 t4 = lds_v4(rz + lane * 128 + ((j ^ (lane & 7)) << 4));
-                            f[4 * j] += __uint_as_float(t4.x); f[4 * j + 1] += __uint_as_float(t4.y);
-                            f[4 * j + 2] += __uint_as_float(t4.z); f[4 * j + 3] += __uint_as_float(t4.w);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 t4 = lds_v4(zone + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        f[4 * j] += __uint_as_float(t4.x); f[4 * j + 1] += __uint_as_float(t4.y);
+                        f[4 * j + 2] += __uint_as_float(t4.z); f[4 * j + 3] += __uint_as_float(t4.w);
                     }
-                    if (!both && c + 1 < nch) {      // the landing zone is free again: prefetch
-                        __syncwarp();
-                        if (lane == 0) request_residual(c + 1);
-                    }
-                } else if (p.R_hi && row_ok) {
+                } else if (p.R_hi && !p.res_mma && row_ok) {
                     const __nv_bfloat16* rh = p.R_hi + out_row * p.ldr + n;
                     const __nv_bfloat16* rl = p.R_lo + out_row * p.ldr + n;
                     for (int j = 0; j < 32; ++j)
@@ -500,24 +496,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
-                // staging zones of this chunk
-                const uint32_t zone = alternate ? ((cc & 1) ? z1 : z0) : (both ? z0 : (tma_r ? z1 : z0));
-                const uint32_t st_f32 = zone;
-                const uint32_t st_hi = both ? z1 : zone, st_lo = st_hi + 2048;
-                if (use_tma) {
-                    // the zone(s) about to be rewritten must have been read out by their last store
-                    if (lane == 0) {
-                        if (alternate) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                    __syncwarp();
-                }
+                const int r0 = q * 32;
                 if (p.C) {
                     if (tma_c) {
+                        if (!tma_r) {   // (with a residual the zone was already waited for)
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                        }
                         // 128-byte rows, 16-byte pieces XOR-swizzled by (row & 7): conflict-free
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            sts_v4(st_f32 + lane * 128 + ((j ^ (lane & 7)) << 4), v4u(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                            sts_v4(zone + lane * 128 + ((j ^ (lane & 7)) << 4), v4u(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (p.conv) tma_store_4d(&tmC, zone, (int)n, tl.ow0, tl.oh0 + r0 / PATCH_W, tl.tb);
+                            else tma_store_2d(&tmC, zone, (int)n, (int)(tl.m0 + r0));
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
                     } else if (row_ok) {
                         float* cp = p.C + out_row * p.ldc + n;
                         if (full_chunk && (p.ldc & 3) == 0) {
@@ -536,6 +532,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     if (tma_p || (row_ok && full_chunk && (p.ldc & 7) == 0)) {
                         __nv_bfloat16* ch = p.C_hi + out_row * p.ldc + n;
                         __nv_bfloat16* cl = p.C_lo + out_row * p.ldc + n;
+                        if (tma_p) {
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t hw[4], lw[4];
@@ -551,11 +551,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             if (tma_p) {
                                 // 64-byte rows, 16-byte pieces XOR-swizzled by ((row >> 1) & 3)
                                 const uint32_t off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-                                sts_v4(st_hi + off, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-                                sts_v4(st_lo + off, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+                                sts_v4(zone + off, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                                sts_v4(zone + 2048 + off, make_uint4(lw[0], lw[1], lw[2], lw[3]));
                             } else {
                                 reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                                 reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
+                        }
+                        if (tma_p) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (p.conv) {
+                                    const int oh = tl.oh0 + r0 / PATCH_W;
+                                    tma_store_4d(&tmC_hi, zone, (int)n, tl.ow0, oh, tl.tb);
+                                    tma_store_4d(&tmC_lo, zone + 2048, (int)n, tl.ow0, oh, tl.tb);
+                                } else {
+                                    tma_store_2d(&tmC_hi, zone, (int)n, (int)(tl.m0 + r0));
+                                    tma_store_2d(&tmC_lo, zone + 2048, (int)n, (int)(tl.m0 + r0));
+                                }
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             }
                         }
                     } else if (row_ok) {
@@ -568,29 +583,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                 cl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
                             }
                         }
-                    }
-                }
-                if (use_tma) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int r0 = q * 32;
-                        if (p.conv) {
-                            const int oh = tl.oh0 + r0 / PATCH_W;
-                            if (tma_c) tma_store_4d(&tmC, st_f32, (int)n, tl.ow0, oh, tl.tb);
-                            if (tma_p) {
-                                tma_store_4d(&tmC_hi, st_hi, (int)n, tl.ow0, oh, tl.tb);
-                                tma_store_4d(&tmC_lo, st_lo, (int)n, tl.ow0, oh, tl.tb);
-                            }
-                        } else {
-                            const int row0 = (int)(tl.m0 + r0);
-                            if (tma_c) tma_store_2d(&tmC, st_f32, (int)n, row0);
-                            if (tma_p) {
-                                tma_store_2d(&tmC_hi, st_hi, (int)n, row0);
-                                tma_store_2d(&tmC_lo, st_lo, (int)n, row0);
-                            }
-                        }
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
                 if (p.mask && row_ok) {
@@ -622,6 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             if (p.mask && p.row_open && row_ok && open) atomicAdd(p.row_open + out_row, open);
         }
+        (void)use_tma;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -787,17 +780,21 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     const unsigned grid = (unsigned)imin64(tiles, sm_count());
     TcParams q = p;
     static const bool direct = getenv("PVSG_TC_DIRECT_STORE") != nullptr;
-    CUtensorMap c{}, c_hi{}, c_lo{}, r{}, r_hi{}, r_lo{};
+    CUtensorMap c{}, c_hi{}, c_lo{}, r{}, ra_hi{}, ra_lo{}, e{};
     q.tma_out = 0;
+    q.res_mma = 0;
     if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B, p.ldc)) q.tma_out |= 1;
     if (!direct && p.C_hi && p.ldc % 8 == 0 && al16(p.C_hi) && al16(p.C_lo) &&
         make_out_map(&c_hi, p.C_hi, false, p, B, p.ldc) && make_out_map(&c_lo, p.C_lo, false, p, B, p.ldc))
         q.tma_out |= 2;
     if (!direct && p.R && p.ldr % 4 == 0 && al16(p.R) && make_out_map(&r, p.R, true, p, B, p.ldr)) q.tma_out |= 4;
-    if (!direct && p.R_hi && p.ldr % 8 == 0 && al16(p.R_hi) && al16(p.R_lo) &&
-        make_out_map(&r_hi, p.R_hi, false, p, B, p.ldr) && make_out_map(&r_lo, p.R_lo, false, p, B, p.ldr))
-        q.tma_out |= 8;
-    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, r, r_hi, r_lo, q);
+    // residual planes as extra k-blocks against the identity (linear mode; operand-style maps)
+    if (p.R_hi && !p.conv && p.ident && p.ldr % 8 == 0 && al16(p.R_hi) && al16(p.R_lo) && al16(p.ident) &&
+        make_map_2d(&ra_hi, p.R_hi, p.M, p.N, p.ldr, BM) && make_map_2d(&ra_lo, p.R_lo, p.M, p.N, p.ldr, BM) &&
+        make_map_2d(&e, p.ident, 256, 256, 256, BN))
+        q.res_mma = 1;
+    gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, c, c_hi, c_lo, r, ra_hi, ra_lo,
+                                                                    e, q);
     return pvsg_launch_status();
 }
 
@@ -837,7 +834,8 @@ extern "C" int pvsg_split_bf16(const float* x, const float* x2, void* hi, void* 
 extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* W_hi, const void* W_lo,
                               int64_t ldw, const float* bias, const float* R, int64_t ldr, float* C, void* C_hi,
                               void* C_lo, uint8_t* mask, int32_t* row_open, int64_t ldc, int64_t M, int64_t N,
-                              int64_t K, int act, const void* R_hi, const void* R_lo, void* stream) {
+                              int64_t K, int act, const void* R_hi, const void* R_lo, const void* ident,
+                              void* stream) {
     PVSG_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && (C || C_hi || mask) && M > 0 && N > 0 && K > 0);
     PVSG_CHECK_ARG((C_hi == nullptr) == (C_lo == nullptr));
     PVSG_CHECK_ARG((R_hi == nullptr) == (R_lo == nullptr) && !(R && R_hi));
@@ -854,6 +852,7 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     TcParams p{};
     p.bias = bias; p.R = R; p.C = C;
     p.R_hi = reinterpret_cast<const __nv_bfloat16*>(R_hi); p.R_lo = reinterpret_cast<const __nv_bfloat16*>(R_lo);
+    p.ident = ident;
     p.C_hi = reinterpret_cast<__nv_bfloat16*>(C_hi); p.C_lo = reinterpret_cast<__nv_bfloat16*>(C_lo);
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;

@@ -151,6 +151,17 @@ def _weight_planes(w):
     return hit
 
 
+_ident = {}
+
+
+def _identity(dev):
+    """bf16 [256,256] identity per device: the B operand of the residual-by-tensor-core k-blocks."""
+    key = str(dev)
+    if key not in _ident:
+        _ident[key] = torch.eye(256, device=dev, dtype=torch.bfloat16).contiguous()
+    return _ident[key]
+
+
 def _tc_ok(K, lda):
     return ENGINE[0] == 'tc' and K % 64 == 0 and lda % 8 == 0
 
@@ -239,7 +250,8 @@ def _linear_tc(lib, planes, w2, bias, residual, act, out, lead, M, N, K, out_mod
         raise _l.PvsgError('linear: bad bias')
     _l.check(lib.pvsg_linear_tc(_ptr(planes.hi), _ptr(planes.lo), K, _ptr(w_hi), _ptr(w_lo), K, _ptr(bias), _ptr(r2),
                                 ldr, _ptr(o2), _ptr(c_hi), _ptr(c_lo), None, None, ldc, M, N, K, act, _ptr(r_hi),
-                                _ptr(r_lo), _stream()), 'pvsg_linear_tc')
+                                _ptr(r_lo), _ptr(_identity(dev)) if r_hi is not None else None, _stream()),
+             'pvsg_linear_tc')
     f32 = (out.reshape(*lead, N) if created else out) if want_f32 else None
     sp = Split(c_hi.view(*lead, N), c_lo.view(*lead, N)) if want_split else None
     if out_mode == 'both':
@@ -521,7 +533,7 @@ def mask_logits(embed, feat, want_logits=True, want_mask=False, feat_planes=None
             _l.check(lib.pvsg_linear_tc(_ptr(e_hi[b]), _ptr(e_lo[b]), C, _ptr(f_hi[b]), _ptr(f_lo[b]), C, None, None,
                                         0, _ptr(logits[b]) if want_logits else None, None, None,
                                         _ptr(mask[b]) if want_mask else None,
-                                        _ptr(row_open[b]) if want_mask else None, P, Q, P, C, ACT_NONE, None, None, _stream()),
+                                        _ptr(row_open[b]) if want_mask else None, P, Q, P, C, ACT_NONE, None, None, None, _stream()),
                      'pvsg_linear_tc')
         return logits, mask, row_open
     logits = torch.empty(B, Q, P, device=embed.device, dtype=torch.float32) if want_logits else None
