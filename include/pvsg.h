@@ -232,6 +232,17 @@ int pvsg_instance_masks(const float* mask_logits, const int32_t* query_idx, int 
 int pvsg_instance_select(const float* cls_logits, int Q, int NC, int k, float* top_scores,
                          int32_t* top_labels, int32_t* top_query, void* stream);
 
+/* The detector's instance selection (models/mask2former_vps/mask2former.py:192-201) with static
+ * shapes: for the n candidates of pvsg_instance_select / pvsg_instance_masks, det_score = score *
+ * stats[:,0] / (stats[:,1] + 1e-6) for thing labels (< num_things), stuff candidates rank last;
+ * sorted descending, the best `topk` are written: boxes6 [topk,6] = (1-based id among the thing
+ * candidates, x0, y0, x1, y1, det_score), labels [topk], sel_query [topk]; count[0] = number of
+ * thing candidates (rows beyond it are padding the caller drops). */
+int pvsg_instance_finalize(const float* scores, const int32_t* labels, const int32_t* query,
+                           const float* stats, const int32_t* boxes, int n, int num_things, int topk,
+                           float* boxes6, int32_t* out_labels, int32_t* sel_query, int32_t* count,
+                           void* stream);
+
 /* ------------------------------------------------------------ relation head ----- */
 
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */

@@ -462,7 +462,11 @@ __global__ void __launch_bounds__(1024) ins_select_kernel(const float* __restric
         const unsigned pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const unsigned u = __float_as_uint(sc[i]);
-            if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+            const bool in = (u & pmask) == prefix;
+            // softmax scores share their leading bytes: aggregate equal bins inside the warp first
+            const unsigned bin = in ? ((u >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(__activemask(), bin);
+            if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -510,6 +514,54 @@ __global__ void __launch_bounds__(1024) ins_select_kernel(const float* __restric
             out_gt += tg; out_eq += te;
         }
         __syncthreads();
+    }
+}
+
+// The detector's instance selection (models/mask2former_vps/mask2former.py:192-201) on the device,
+// static shapes: det_score = class score * mask score for thing candidates, 1-based id = rank of the
+// candidate among the thing candidates (candidate order), descending sort by det_score, keep `topk`.
+// Outputs: boxes6 [topk,6] = (id, x0, y0, x1, y1, det_score), labels [topk], sel_query [topk] (input
+// of the mask pass), count[0] = number of thing candidates.  One CTA.
+__global__ void __launch_bounds__(128) ins_finalize_kernel(const float* __restrict__ scores,
+                                                           const int32_t* __restrict__ labels,
+                                                           const int32_t* __restrict__ query,
+                                                           const float* __restrict__ stats,
+                                                           const int32_t* __restrict__ boxes, int n, int num_things,
+                                                           int topk, float* __restrict__ boxes6,
+                                                           int32_t* __restrict__ out_labels,
+                                                           int32_t* __restrict__ sel_query,
+                                                           int32_t* __restrict__ count) {
+    __shared__ float ds[1024];
+    __shared__ int thing[1024];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int t = labels[i] < num_things ? 1 : 0;
+        thing[i] = t;
+        ds[i] = t ? scores[i] * stats[2 * i] / (stats[2 * i + 1] + 1e-6f) : -1.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int rank = 0, id = 0;
+        const float si = ds[i];
+        for (int j = 0; j < n; ++j) {
+            const float sj = ds[j];
+            rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+            id += (j <= i) ? thing[j] : 0;
+        }
+        if (rank < topk) {
+            boxes6[6 * rank + 0] = (float)id;
+            boxes6[6 * rank + 1] = (float)boxes[4 * i + 0];
+            boxes6[6 * rank + 2] = (float)boxes[4 * i + 1];
+            boxes6[6 * rank + 3] = (float)boxes[4 * i + 2];
+            boxes6[6 * rank + 4] = (float)boxes[4 * i + 3];
+            boxes6[6 * rank + 5] = si;
+            out_labels[rank] = labels[i];
+            sel_query[rank] = query[i];
+        }
+    }
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int j = 0; j < n; ++j) c += thing[j];
+        count[0] = c;
     }
 }
 
@@ -592,5 +644,16 @@ extern "C" int pvsg_instance_select(const float* cls_logits, int Q, int NC, int 
         configured = true;
     }
     ins_select_kernel<<<1, 1024, smem, as_stream(stream)>>>(cls_logits, Q, NC, k, top_scores, top_labels, top_query);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_instance_finalize(const float* scores, const int32_t* labels, const int32_t* query,
+                                      const float* stats, const int32_t* boxes, int n, int num_things, int topk,
+                                      float* boxes6, int32_t* out_labels, int32_t* sel_query, int32_t* count,
+                                      void* stream) {
+    PVSG_CHECK_ARG(scores && labels && query && stats && boxes && boxes6 && out_labels && sel_query && count);
+    PVSG_CHECK_ARG(n > 0 && n <= 1024 && topk > 0 && topk <= n && num_things >= 0);
+    ins_finalize_kernel<<<1, 128, 0, as_stream(stream)>>>(scores, labels, query, stats, boxes, n, num_things, topk,
+                                                          boxes6, out_labels, sel_query, count);
     return pvsg_launch_status();
 }

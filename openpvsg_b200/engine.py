@@ -45,15 +45,9 @@ def postprocess_frame(det, cls, mlr, in_hw, img_hw, out_hw):
         out['pan'], out['seg_info'] = fh._panoptic(cls, mlr, in_hw, img_hw, out_hw)
     if fh.test_cfg.get('instance_on', False):
         d = fh._instance_device(cls, mlr, in_hw, img_hw, out_hw, False)
-        is_thing = d['labels'] < det.num_things_classes
-        det_scores = d['scores'] * d['stats'][:, 0] / (d['stats'][:, 1] + 1e-6)
-        det_scores = torch.where(is_thing, det_scores, det_scores.new_full((), -1.0))
-        ids = torch.cumsum(is_thing.to(torch.float32), 0)   # 1-based rank among thing candidates
-        inds = torch.argsort(det_scores, descending=True)[:TOPK_INS]
-        out['ins_boxes'] = torch.cat([ids[inds, None], d['boxes'][inds].float(), det_scores[inds, None]], dim=1)
-        out['ins_labels'] = d['labels'][inds].to(torch.int32)
-        out['ins_count'] = is_thing.sum().to(torch.int32).reshape(1)
-        out['ins_masks'] = ops.instance_masks(mlr, d['query'][inds], in_hw, img_hw, out_hw, True)[2]
+        out['ins_boxes'], out['ins_labels'], sel, out['ins_count'] = ops.instance_finalize(
+            d['scores'], d['labels32'], d['query'], d['stats'], d['boxes'], det.num_things_classes, TOPK_INS)
+        out['ins_masks'] = ops.instance_masks(mlr, sel, in_hw, img_hw, out_hw, True)[2]
     return out
 
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     'pvsg_panoptic_fuse': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),
     'pvsg_instance_masks': (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, P, P]),
     'pvsg_instance_select': (I, [P, I, I, I, P, P, P, P]),
+    'pvsg_instance_finalize': (I, [P, P, P, P, P, I, I, I, P, P, P, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
     'pvsg_pair_proposal': (I, [P, P, P, P, P, I, I, P]),
     'pvsg_top_pairs': (I, [P, I, I, P, P, P]),

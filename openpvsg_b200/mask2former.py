@@ -845,7 +845,7 @@ class MaskFormerFusionHeadCustom(nn.Module):
         scores_per_image, labels_per_image, query_indices = ops.instance_select(mask_cls, max_per_image)
         stats, boxes, masks = ops.instance_masks(mask_lr, query_indices, in_hw, img_hw, out_hw, want_masks)
         return dict(scores=scores_per_image, labels=labels_per_image.long(), stats=stats, boxes=boxes, masks=masks,
-                    query=query_indices)
+                    query=query_indices, labels32=labels_per_image)
 
     @torch.no_grad()
     def _instance_finish(self, d):

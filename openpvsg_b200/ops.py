@@ -594,6 +594,26 @@ def instance_select(cls_logits, k):
     return scores, labels, query
 
 
+def instance_finalize(scores, labels, query, stats, boxes, num_things, topk):
+    """Top-`topk` instances by class score x mask score -> (boxes6 [topk,6], labels int32 [topk],
+    query int32 [topk], count int32 [1]); see pvsg_instance_finalize."""
+    lib = _l.load()
+    n = scores.numel()
+    dev = scores.device
+    topk = min(topk, n)
+    boxes6 = torch.empty(topk, 6, device=dev, dtype=torch.float32)
+    out_labels = torch.empty(topk, device=dev, dtype=torch.int32)
+    sel_query = torch.empty(topk, device=dev, dtype=torch.int32)
+    count = torch.empty(1, device=dev, dtype=torch.int32)
+    if labels.dtype != torch.int32 or query.dtype != torch.int32 or boxes.dtype != torch.int32:
+        raise _l.PvsgError('instance_finalize: int32 labels / query / boxes expected')
+    _l.check(lib.pvsg_instance_finalize(_ptr(_f32(scores).contiguous()), _ptr(labels.contiguous()),
+                                        _ptr(query.contiguous()), _ptr(_f32(stats).contiguous()),
+                                        _ptr(boxes.contiguous()), n, num_things, topk, _ptr(boxes6), _ptr(out_labels),
+                                        _ptr(sel_query), _ptr(count), _stream()), 'pvsg_instance_finalize')
+    return boxes6, out_labels, sel_query, count
+
+
 def max_over_time(x):
     lib = _l.load()
     N, T, C = _f32(x).shape

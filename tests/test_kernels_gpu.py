@@ -325,6 +325,30 @@ def test_instance_select(ops, Q, NC, k):
     assert set(strictly_in.nonzero().flatten().tolist()) <= set(flat.tolist())
 
 
+def test_instance_finalize(ops):
+    """Static-shape top-10 selection (models/mask2former_vps/mask2former.py:192-201) vs the torch
+    formulation: things only, det_score = score * mask score, 1-based ids in candidate order."""
+    g = torch.Generator().manual_seed(5)
+    n, num_things, topk = 100, 115, 10
+    scores = torch.rand(n, generator=g)
+    labels = torch.randint(0, 126, (n,), generator=g).int()
+    labels[::3] = 120                                    # plenty of stuff candidates
+    query = torch.randint(0, 100, (n,), generator=g).int()
+    stats = torch.stack([torch.rand(n, generator=g) * 500, torch.randint(0, 900, (n,), generator=g).float()], 1)
+    stats[5] = 0.0                                        # empty mask -> score 0
+    boxes = torch.randint(0, 700, (n, 4), generator=g).int()
+    b6, lab, sel, cnt = ops.instance_finalize(scores.cuda(), labels.cuda(), query.cuda(), stats.cuda(), boxes.cuda(),
+                                              num_things, topk)
+    is_thing = labels < num_things
+    det = scores * stats[:, 0] / (stats[:, 1] + 1e-6)
+    ids = torch.cumsum(is_thing.float(), 0)
+    order = torch.argsort(torch.where(is_thing, det, torch.full_like(det, -1.0)), descending=True, stable=True)[:topk]
+    assert int(cnt.item()) == int(is_thing.sum())
+    assert torch.equal(lab.cpu(), labels[order]) and torch.equal(sel.cpu(), query[order])
+    ref = torch.cat([ids[order, None], boxes[order].float(), det[order, None]], 1)
+    close(b6, ref, 1e-4 * float(ref.abs().max()), 'instance boxes')
+
+
 def test_instance_masks(ops):
     from oracle import m2f as om
     Q, h, w = 12, 24, 40
