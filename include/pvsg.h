@@ -94,7 +94,16 @@ int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const v
                    int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad,
                    int act, const void* res_hi, const void* res_lo, void* stream);
 
-/* Small-Cin convolutions (the 7x7/2 RGB stem, Cin = 3): gathers the patches of x [B,H,W,Cin]
+/* ResNet stem (7x7, stride 2, pad 3, C <= 4 input channels; mmdet ResNet conv1) without im2col:
+ * packs x [B,C,H,W] (NCHW fp32, the detector's input layout) into operand planes
+ * X2 [B, OH+3, OW, 64], X2[b,yp,ox, par*32 + s*4 + c] = x[b, c, 2yp+par-3, 2ox+s-3] (zero outside
+ * the frame and for s = 7 / c >= C), OH = (H-1)/2+1, OW = (W-1)/2+1.  The stem is then the 4 x 1
+ * stride-1 convolution pvsg_conv2d_tc(X2, W2 [Cout,4,1,64]) with W2[co, j, 0, par*32 + s*4 + c] =
+ * w[co, 2j+par, s, c]. */
+int pvsg_stem7x7s2_pack(const float* x_nchw, void* hi, void* lo, int B, int C, int H, int W,
+                        void* stream);
+
+/* Small-Cin convolutions (generic form, Cin % 64 != 0): gathers the patches of x [B,H,W,Cin]
  * directly into split operand planes [B*OH*OW, Kpad] (k = (r*S + s)*Cin + c, zero-padded to
  * Kpad >= R*S*Cin, Kpad % 64 == 0 for pvsg_linear_tc), so the stem also runs on tcgen05. */
 int pvsg_im2col_split(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int R,

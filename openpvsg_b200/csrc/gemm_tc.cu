@@ -659,6 +659,44 @@ __global__ void __launch_bounds__(256) im2col_split_kernel(const float* __restri
     }
 }
 
+// 7x7 stride-2 pad-3 stem (ResNet conv1) without im2col.  The frame (NCHW fp32, C <= 4) is packed
+// ONCE into operand planes X2 [B, OH + 3, OW, 64]:
+//     X2[b, yp, ox, par*32 + s*4 + c] = x[b, c, 2*yp + par - 3, 2*ox + s - 3]      (0 outside, s = 7, c >= C)
+// i.e. a pair of input rows and the 8-pixel window of output column ox per 128-byte row.  Because the
+// conv stride (2) equals the row-pair size, output row oy needs exactly the row pairs oy .. oy+3:
+// the stem becomes a 4 x 1 convolution with 64 "channels" over X2 and runs through pvsg_conv2d_tc
+// (weights re-laid to [Cout, 4, 1, 64]).  Bytes written: 2 planes x 128 B x B (OH+3) OW = 0.49 GB for
+// 8 720p frames instead of the 1.45 GB of full im2col rows.
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, uint4* __restrict__ hi,
+                                                        uint4* __restrict__ lo, int C, int H, int W, int rows2,
+                                                        int OW, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i & 7);            // 16-byte piece of the 128-byte row: 2 pixels x 4 channels
+        int64_t t = i >> 3;
+        const int ox = (int)(t % OW);
+        t /= OW;
+        const int yp = (int)(t % rows2);
+        const int64_t b = t / rows2;
+        const int par = chunk >> 2, s0 = (chunk & 3) * 2;
+        const int y = 2 * yp + par - 3;
+        uint16_t h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int s = s0 + (e >> 2), c = e & 3;
+            const int xx = 2 * ox + s - 3;
+            float v = 0.f;
+            if (c < C && s < 7 && y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + ((b * C + c) * H + y) * (int64_t)W + xx);
+            const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+            h[e] = __bfloat16_as_ushort(hh);
+            l[e] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hh)));
+        }
+        hi[i] = make_uint4(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16), h[4] | ((uint32_t)h[5] << 16),
+                           h[6] | ((uint32_t)h[7] << 16));
+        lo[i] = make_uint4(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16), l[4] | ((uint32_t)l[5] << 16),
+                           l[6] | ((uint32_t)l[7] << 16));
+    }
+}
+
 // fp32 -> (hi, lo) bf16 planes, optionally of x + x2
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
@@ -820,6 +858,16 @@ extern "C" int pvsg_im2col_split(const float* x, void* hi, void* lo, int B, int 
     im2col_split_kernel<<<(unsigned)imin64((total4 + 255) / 256, 148 * 32), 256, 0, as_stream(stream)>>>(
         x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), H, W, Cin, OH, OW, S, stride,
         pad, Kreal, Kpad, total4);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_stem7x7s2_pack(const float* x_nchw, void* hi, void* lo, int B, int C, int H, int W,
+                                    void* stream) {
+    PVSG_CHECK_ARG(x_nchw && hi && lo && B > 0 && C > 0 && C <= 4 && H > 0 && W > 0 && al16(hi) && al16(lo));
+    const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+    const int64_t total = (int64_t)B * (OH + 3) * OW * 8;
+    stem_pack_kernel<<<(unsigned)imin64((total + 255) / 256, 148 * 32), 256, 0, as_stream(stream)>>>(
+        x_nchw, reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo), C, H, W, OH + 3, OW, total);
     return pvsg_launch_status();
 }
 

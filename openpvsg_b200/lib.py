@@ -27,6 +27,7 @@ SIGNATURES = {
     'pvsg_linear': (I, [P, P, P, P, P, P, L, L, L, L, L, L, L, I, L, L, L, L, P]),
     'pvsg_conv2d_nhwc': (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_split_bf16': (I, [P, P, P, P, L, P]),
+    'pvsg_stem7x7s2_pack': (I, [P, P, P, I, I, I, I, P]),
     'pvsg_im2col_split': (I, [P, P, P, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_linear_tc': (I, [P, P, L, P, P, L, P, P, L, P, P, P, P, P, L, L, L, L, I, P, P, P, P]),
     'pvsg_conv2d_tc': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P]),

@@ -137,9 +137,13 @@ class ResNet(_Prepared):
         if self._prep is None:
             self._prepare()
         p = self._prep
-        x = _tokens(x)
         ops.clear_split_cache()
-        x = ops.conv2d_nhwc(x, *p['stem'], stride=2, pad=3, act=ops.ACT_RELU)
+        if ops.ENGINE[0] == 'tc' and x.is_contiguous():
+            if 'stem2' not in p:
+                p['stem2'] = ops.stem_weight(p['stem'][0])
+            x = ops.stem7x7s2(x, p['stem2'], p['stem'][1])
+        else:
+            x = ops.conv2d_nhwc(_tokens(x), *p['stem'], stride=2, pad=3, act=ops.ACT_RELU)
         x = ops.maxpool3x3s2_nhwc(x)
         # On the tcgen05 engine activations live as operand planes only: the 1x1 -> 3x3 -> 1x1 chain
         # hands planes from epilogue to TMA loader (out_mode='split'), and the identity branch is

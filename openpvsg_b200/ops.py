@@ -340,6 +340,34 @@ def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, act=ACT_NO
     return (out, None) if out_mode == 'both' else out
 
 
+def stem_weight(weight):
+    """[Cout,7,7,C<=4] stem weight (token-major taps) -> [Cout,4,1,64] for ``stem7x7s2``:
+    W2[co, j, 0, par*32 + s*4 + c] = w[co, 2j+par, s, c]."""
+    Cout, R, S, C = weight.shape
+    if (R, S) != (7, 7) or C > 4:
+        raise _l.PvsgError('stem_weight: 7x7 kernel with <= 4 input channels expected')
+    w2 = torch.zeros(Cout, 4, 2, 8, 4, device=weight.device, dtype=torch.float32)
+    wp = torch.zeros(Cout, 8, 8, 4, device=weight.device, dtype=torch.float32)
+    wp[:, :7, :7, :C] = weight
+    w2[:] = wp.view(Cout, 4, 2, 8, 4)
+    return w2.view(Cout, 4, 1, 64).contiguous()
+
+
+def stem7x7s2(x_nchw, w2, bias, act=ACT_RELU, out_mode='f32'):
+    """ResNet conv1 (7x7 / stride 2 / pad 3) on the NCHW fp32 frame: one packing pass into row-pair
+    operand planes, then the tcgen05 conv engine as a 4 x 1 convolution (no im2col buffer).
+    Returns token-major [B,OH,OW,Cout]."""
+    lib = _l.load()
+    B, C, H, W = _f32(x_nchw, 'x').shape
+    if not x_nchw.is_contiguous():
+        raise _l.PvsgError('stem7x7s2: contiguous NCHW input required')
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    hi = torch.empty(B, OH + 3, OW, 64, device=x_nchw.device, dtype=torch.bfloat16)
+    lo = torch.empty(B, OH + 3, OW, 64, device=x_nchw.device, dtype=torch.bfloat16)
+    _l.check(lib.pvsg_stem7x7s2_pack(_ptr(x_nchw), _ptr(hi), _ptr(lo), B, C, H, W, _stream()), 'pvsg_stem7x7s2_pack')
+    return conv2d_nhwc(Split(hi, lo), w2, bias, stride=1, pad=0, act=act, out_mode=out_mode)
+
+
 def maxpool3x3s2_nhwc(x):
     lib = _l.load()
     B, H, W, C = _f32(x).shape

@@ -137,3 +137,17 @@ def test_conv_tc_plane_residual(ops, cin, cout, k, pad, hw, B, stride, out_mode)
     assert (_planes_value(sp).permute(0, 3, 1, 2) - ref).abs().max().item() < tol
     if f32 is not None:
         assert (f32.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize('B,C,H,W', [(2, 3, 96, 160), (1, 3, 75, 131), (1, 3, 736, 1280)])
+def test_stem7x7s2_rowpair_conv(ops, B, C, H, W):
+    """ResNet conv1 through the row-pair packing (pvsg_stem7x7s2_pack) + 4x1 tcgen05 conv."""
+    x = randn(1, B, C, H, W)
+    w = randn(2, 64, C, 7, 7) / (C * 49) ** 0.5
+    b = randn(3, 64)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), 2, 3))
+    w2 = ops.stem_weight(w.permute(0, 2, 3, 1).contiguous().cuda())
+    y = ops.stem7x7s2(x.cuda(), w2, b.cuda())
+    assert tuple(y.shape) == (B, ref.shape[2], ref.shape[3], 64)
+    err = (y.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
