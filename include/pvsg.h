@@ -187,6 +187,18 @@ int pvsg_attention(const float* Q, const float* K, const float* V, const uint8_t
                    int64_t v_bs, int64_t v_ts, int64_t o_bs, int64_t o_ts, float scale,
                    void* stream);
 
+/* Same contraction on the tensor cores for head dim 32 (the decoder's masked cross-attention,
+ * mask2former_head.py:457-468): K and V are given as the split-bf16 operand planes their
+ * projection emitted (element (b, i, h, d) at b*k_bs + i*k_ts + h*32 + d, strides in elements),
+ * Q / out fp32 as above; every product is three m16n8k16 MMAs (fp32-grade).  Workspace:
+ * pvsg_attention_tc_workspace_bytes. */
+int64_t pvsg_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk);
+int pvsg_attention_tc(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi,
+                      const void* V_lo, const uint8_t* mask, const int32_t* row_open, float* out,
+                      void* ws, int B, int H, int Lq, int Lk, int D, int64_t q_bs, int64_t q_ts,
+                      int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts, int64_t o_bs,
+                      int64_t o_ts, float scale, void* stream);
+
 /* ------------------------------------------------------------ mask logits ------- */
 
 /* The per-frame query x pixel contraction einsum('bqc,bchw->bqhw')

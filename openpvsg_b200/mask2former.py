@@ -490,9 +490,14 @@ class MultiheadAttention(nn.Module):
         has them (each decoder level is projected by three different layers)."""
         E = self.embed_dims
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
-        k = ops.linear(key_planes, w[E:2 * E], b[E:2 * E]) if key_planes is not None else \
-            ops.linear(key, w[E:2 * E], b[E:2 * E], add_input=key_pos)
-        v = ops.linear(value_planes if value_planes is not None else value, w[2 * E:], b[2 * E:])
+        # on the tcgen05 engine the projections leave as operand planes: the tensor-core attention
+        # kernel consumes them directly (head dim 32)
+        mode = 'split' if E // self.num_heads == 32 else 'f32'
+        k = ops.linear(key_planes, w[E:2 * E], b[E:2 * E], out_mode=mode) if key_planes is not None else \
+            ops.linear(key, w[E:2 * E], b[E:2 * E], add_input=key_pos, out_mode=mode)
+        v = ops.linear(value_planes if value_planes is not None else value, w[2 * E:], b[2 * E:], out_mode=mode)
+        if isinstance(k, ops.Split) != isinstance(v, ops.Split):   # mixed engines cannot happen for equal shapes
+            raise ops._l.PvsgError('project_kv: inconsistent operand formats')
         return k, v
 
     @torch.no_grad()

@@ -515,8 +515,38 @@ def msda_fused_forward(value, spatial_shapes, proj, ref, num_heads=8, num_points
 
 def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None):
     """q [B,Lq,E], k/v [B,Lk,E] (any batch / token strides, unit inner stride) -> [B,Lq,E].
-    mask uint8 [B,Lq,Lk] (non-zero = blocked), row_open int32 [B,Lq]."""
+    mask uint8 [B,Lq,Lk] (non-zero = blocked), row_open int32 [B,Lq].
+    k / v may be ``Split`` operand planes (head dim 32): tensor-core path (csrc/attention_mma.cu)."""
     lib = _l.load()
+    if isinstance(k, Split) or isinstance(v, Split):
+        if not (isinstance(k, Split) and isinstance(v, Split)):
+            raise _l.PvsgError('attention: k and v must both be planes')
+        _f32(q, 'q')
+        B, Lq, E = q.shape
+        Lk = k.shape[1]
+        D = E // num_heads
+        if D != 32 or q.stride(2) != 1 or tuple(k.shape) != (B, Lk, E) or tuple(v.shape) != (B, Lk, E):
+            raise _l.PvsgError('attention: plane inputs need head dim 32 and [B,Lk,E] planes')
+        for t in (k.hi, k.lo, v.hi, v.lo):
+            if t.stride(2) != 1:
+                raise _l.PvsgError('attention: planes need unit inner stride')
+        if scale is None:
+            scale = float(D) ** -0.5
+        if out is None:
+            out = torch.empty(B, Lq, E, device=q.device, dtype=torch.float32)
+        if mask is not None and not (mask.dtype == torch.uint8 and mask.is_contiguous() and
+                                     tuple(mask.shape) == (B, Lq, Lk)):
+            raise _l.PvsgError('attention: mask must be contiguous uint8 [B,Lq,Lk]')
+        if row_open is not None and not (row_open.dtype == torch.int32 and row_open.is_contiguous()):
+            raise _l.PvsgError('attention: row_open must be contiguous int32')
+        if (k.hi.stride() != k.lo.stride()) or (v.hi.stride() != v.lo.stride()):
+            raise _l.PvsgError('attention: hi / lo planes must share their layout')
+        ws = torch.empty(lib.pvsg_attention_tc_workspace_bytes(B, num_heads, Lq, Lk), device=q.device, dtype=torch.uint8)
+        _l.check(lib.pvsg_attention_tc(_ptr(q), _ptr(k.hi), _ptr(k.lo), _ptr(v.hi), _ptr(v.lo), _ptr(mask),
+                                       _ptr(row_open), _ptr(out), _ptr(ws), B, num_heads, Lq, Lk, D, q.stride(0),
+                                       q.stride(1), k.hi.stride(0), k.hi.stride(1), v.hi.stride(0), v.hi.stride(1),
+                                       out.stride(0), out.stride(1), scale, _stream()), 'pvsg_attention_tc')
+        return out
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _f32(t, n)
         if t.dim() != 3 or t.stride(2) != 1:

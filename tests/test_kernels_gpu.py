@@ -210,6 +210,33 @@ def test_attention(ops, B, H, Lq, Lk, E):
     close(out, _mha_ref(q, k, v, H), 2e-5, 'attention')
 
 
+@pytest.mark.parametrize('B,Lq,Lk', [(2, 100, 920), (1, 100, 14720), (2, 37, 129), (1, 200, 3680), (3, 16, 64)])
+def test_attention_tensor_core_planes(ops, B, Lq, Lk):
+    """csrc/attention_mma.cu: K / V as split-bf16 planes, masks with fully blocked rows (open-row
+    rule), ragged key counts (odd Lk exercises the byte mask loads), several query tiles."""
+    H, E = 8, 256
+    g = torch.Generator().manual_seed(Lq * 7 + Lk)
+    q = torch.randn(B, Lq, E, generator=g)
+    k = torch.randn(B, Lk, E, generator=g)
+    v = torch.randn(B, Lk, E, generator=g)
+    mask = (torch.rand(B, Lq, Lk, generator=g) < 0.6)
+    mask[:, 3] = True                      # fully blocked row -> attends to everything
+    mask[:, 5, : Lk // 2] = False
+    row_open = (~mask).sum(-1).to(torch.int32)
+    eff = mask.clone()
+    eff[row_open == 0] = False
+    ref = _mha_ref(q, k, v, H, eff)
+    ks = ops.Split(*ops.split_bf16(k.cuda()))
+    vs = ops.Split(*ops.split_bf16(v.cuda()))
+    out = ops.attention(q.cuda(), ks, vs, H, mask=mask.to(torch.uint8).cuda(), row_open=row_open.cuda())
+    close(out, ref, 2e-4, 'tensor-core attention (masked)')
+    out = ops.attention(q.cuda(), ks, vs, H)
+    close(out, _mha_ref(q, k, v, H), 2e-4, 'tensor-core attention (no mask)')
+    # agrees with the fp32 SIMT kernel
+    out2 = ops.attention(q.cuda(), k.cuda(), v.cuda(), H)
+    close(out, out2.cpu(), 2e-4, 'tensor-core vs SIMT attention')
+
+
 def test_attention_masked_and_strided(ops):
     B, H, Lq, Lk, E = 1, 8, 100, 3680, 256
     q, k, v = randn(1, B, Lq, E), randn(2, B, Lk, E), randn(3, B, Lk, E)
