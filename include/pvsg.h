@@ -126,11 +126,22 @@ int pvsg_layernorm(const float* x, const float* gamma, const float* beta, float*
 int pvsg_layernorm_split(const float* x, const float* gamma, const float* beta, float* y,
                          void* y_hi, void* y_lo, int64_t rows, int C, float eps, void* stream);
 
+/* same as pvsg_layernorm_split, additionally the planes (s_hi, s_lo) of y + add (add [rows,C]):
+ * the (query + query_pos) operand of the next MSDeformAttn's offset / weight projections. */
+int pvsg_layernorm_split2(const float* x, const float* gamma, const float* beta, float* y,
+                          void* y_hi, void* y_lo, const float* add, void* s_hi, void* s_lo,
+                          int64_t rows, int C, float eps, void* stream);
+
 /* GroupNorm over token-major x [B,HW,C] (L0 ConvModule norm GN(32)); stats = workspace
  * of 2*B*groups doubles (zeroed by the call). y = act(GN(x)). */
 int pvsg_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* y,
                         double* stats, int B, int64_t HW, int C, int groups, float eps,
                         int act, void* stream);
+
+/* same, emitting the split planes of y (y itself optional: may be NULL). */
+int pvsg_groupnorm_nhwc_split(const float* x, const float* gamma, const float* beta, float* y,
+                              void* y_hi, void* y_lo, double* stats, int B, int64_t HW, int C,
+                              int groups, float eps, int act, void* stream);
 
 /* y[r,:] = x[r,:] + v[:]  (level_embed add, mask2former_head.py:424-426). */
 int pvsg_add_rowvec(const float* x, const float* v, float* y, int64_t rows, int C, void* stream);
@@ -168,6 +179,12 @@ int pvsg_msda_fused_forward(const float* value, const int64_t* spatial_shapes,
                             const int64_t* level_start_index, const float* proj,
                             const float* ref, float* out, int B, int64_t N, int64_t Nq,
                             int H, int D, int L, int P, void* stream);
+
+/* same, emitting the split planes of the result for the output projection (out optional). L*P <= 16. */
+int pvsg_msda_fused_forward_split(const float* value, const int64_t* spatial_shapes,
+                                  const int64_t* level_start_index, const float* proj,
+                                  const float* ref, float* out, void* out_hi, void* out_lo, int B,
+                                  int64_t N, int64_t Nq, int H, int D, int L, int P, void* stream);
 
 /* ------------------------------------------------------------------ attention --- */
 

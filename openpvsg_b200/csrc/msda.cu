@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
                                                             const float* __restrict__ proj,
                                                             const float* __restrict__ ref, float* __restrict__ out,
                                                             int64_t N, int64_t Nq, int H, int L, int P,
-                                                            int64_t total) {
+                                                            int64_t total, uint2* __restrict__ out_hi = nullptr,
+                                                            uint2* __restrict__ out_lo = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, j = lane & 7;
     const int LP = L * P;
@@ -306,7 +307,26 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
                 acc.x = fmaf(w[3], v11.x, acc.x); acc.y = fmaf(w[3], v11.y, acc.y);
                 acc.z = fmaf(w[3], v11.z, acc.z); acc.w = fmaf(w[3], v11.w, acc.w);
             }
-            if (valid) reinterpret_cast<float4*>(out)[((b * Nq + nq) * H + head) * 8 + j] = acc;
+            if (valid) {
+                const int64_t oi = ((b * Nq + nq) * H + head) * 8 + j;
+                if (out) reinterpret_cast<float4*>(out)[oi] = acc;
+                if (out_hi) {   // operand planes for the output projection GEMM
+                    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t u = __float_as_uint(a4[e]);
+                        // round-to-nearest-even bf16 of a4[e], then of the remainder
+                        const uint32_t hb = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
+                        const float rem = a4[e] - __uint_as_float(hb);
+                        const uint32_t ur = __float_as_uint(rem);
+                        hh[e] = hb >> 16;
+                        ll[e] = ((ur + 0x7fffu + ((ur >> 16) & 1u)) >> 16) & 0xffffu;
+                    }
+                    out_hi[oi] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
+                    out_lo[oi] = make_uint2(ll[0] | (ll[1] << 16), ll[2] | (ll[3] << 16));
+                }
+            }
         }
     }
 }
@@ -329,8 +349,9 @@ int fill_levels(MsdaLevels& lv, const int64_t* spatial_shapes, const int64_t* le
 template <bool FUSED>
 int launch(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
            const float* a, const float* b2, float* out, int B, int64_t N, int64_t Nq, int H, int D, int L,
-           int P, void* stream) {
-    PVSG_CHECK_ARG(value && spatial_shapes && level_start_index && a && b2 && out);
+           int P, void* stream, void* out_hi = nullptr, void* out_lo = nullptr) {
+    PVSG_CHECK_ARG(value && spatial_shapes && level_start_index && a && b2 && (out || out_hi));
+    PVSG_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr));
     PVSG_CHECK_ARG(B > 0 && N > 0 && Nq > 0 && H > 0 && P > 0);
     if (D != 32 || L * P > 32 || N * H * 8 >= (1LL << 31)) return PVSG_ERR_UNSUPPORTED;
     MsdaLevels lv{};
@@ -341,14 +362,17 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
         if (Nq == N) {
             const int64_t total = (int64_t)B * H * lv.tile_start[L];
             msda_group_kernel<true><<<(unsigned)imin64(total, 148 * 64), 256, 0, as_stream(stream)>>>(
-                value, lv, a, b2, out, N, Nq, H, L, P, total);
+                value, lv, a, b2, out, N, Nq, H, L, P, total, reinterpret_cast<uint2*>(out_hi),
+                reinterpret_cast<uint2*>(out_lo));
         } else {
             const int64_t total = (int64_t)B * H * ((Nq + 31) / 32);
             msda_group_kernel<false><<<(unsigned)imin64(total, 148 * 64), 256, 0, as_stream(stream)>>>(
-                value, lv, a, b2, out, N, Nq, H, L, P, total);
+                value, lv, a, b2, out, N, Nq, H, L, P, total, reinterpret_cast<uint2*>(out_hi),
+                reinterpret_cast<uint2*>(out_lo));
         }
         return pvsg_launch_status();
     }
+    if (out_hi || !out) return PVSG_ERR_UNSUPPORTED;   // planes only from the group kernel
     if (Nq == N) {   // queries = pyramid tokens: 2-D tiled query order
         const int64_t total = (int64_t)B * H * lv.tile_start[L];
         const unsigned grid = (unsigned)imin64(total, 148 * 64);
@@ -376,4 +400,13 @@ extern "C" int pvsg_msda_fused_forward(const float* value, const int64_t* spatia
                                        const float* ref, float* out, int B, int64_t N, int64_t Nq, int H,
                                        int D, int L, int P, void* stream) {
     return launch<true>(value, spatial_shapes, level_start_index, proj, ref, out, B, N, Nq, H, D, L, P, stream);
+}
+
+extern "C" int pvsg_msda_fused_forward_split(const float* value, const int64_t* spatial_shapes,
+                                             const int64_t* level_start_index, const float* proj,
+                                             const float* ref, float* out, void* out_hi, void* out_lo, int B,
+                                             int64_t N, int64_t Nq, int H, int D, int L, int P, void* stream) {
+    PVSG_CHECK_ARG(out_hi && out_lo);
+    return launch<true>(value, spatial_shapes, level_start_index, proj, ref, out, B, N, Nq, H, D, L, P, stream,
+                        out_hi, out_lo);
 }

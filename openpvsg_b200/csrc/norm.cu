@@ -12,7 +12,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta,
                                                         float* __restrict__ y, int64_t rows, float eps,
                                                         uint16_t* __restrict__ y_hi = nullptr,
-                                                        uint16_t* __restrict__ y_lo = nullptr) {
+                                                        uint16_t* __restrict__ y_lo = nullptr,
+                                                        const float* __restrict__ add = nullptr,
+                                                        uint16_t* __restrict__ s_hi = nullptr,
+                                                        uint16_t* __restrict__ s_lo = nullptr) {
     constexpr int C = 128 * V;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -56,6 +59,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             const int64_t q = row * (C / 4) + lane + 32 * i;
             reinterpret_cast<uint2*>(y_hi)[q] = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
             reinterpret_cast<uint2*>(y_lo)[q] = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        }
+        if (s_hi) {  // planes of y + add (the query = x + pos operand of the next attention's projections)
+            const int64_t q = row * (C / 4) + lane + 32 * i;
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(add) + q);
+            const float a[4] = {o.x + p4.x, o.y + p4.y, o.z + p4.z, o.w + p4.w};
+            uint16_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 hh = __float2bfloat16_rn(a[e]);
+                h[e] = __bfloat16_as_ushort(hh);
+                l[e] = __bfloat16_as_ushort(__float2bfloat16_rn(a[e] - __bfloat162float(hh)));
+            }
+            reinterpret_cast<uint2*>(s_hi)[q] = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+            reinterpret_cast<uint2*>(s_lo)[q] = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
         }
     }
 }
@@ -101,7 +118,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const double* __restrict__ stats,
                                                        float* __restrict__ y, int64_t HW, int C, int groups,
-                                                       float eps, int act, int64_t total_quads) {
+                                                       float eps, int act, int64_t total_quads,
+                                                       uint16_t* __restrict__ y_hi = nullptr,
+                                                       uint16_t* __restrict__ y_lo = nullptr) {
     const int cq = C >> 2;
     const int qpg = (C / groups) >> 2;
     const double cnt = (double)HW * (C / groups);
@@ -125,7 +144,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         if (act == PVSG_ACT_RELU) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
-        reinterpret_cast<float4*>(y)[i] = o;
+        if (y) reinterpret_cast<float4*>(y)[i] = o;
+        if (y_hi) {
+            const float a[4] = {o.x, o.y, o.z, o.w};
+            uint16_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 hh = __float2bfloat16_rn(a[e]);
+                h[e] = __bfloat16_as_ushort(hh);
+                l[e] = __bfloat16_as_ushort(__float2bfloat16_rn(a[e] - __bfloat162float(hh)));
+            }
+            reinterpret_cast<uint2*>(y_hi)[i] = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+            reinterpret_cast<uint2*>(y_lo)[i] = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+        }
     }
 }
 
@@ -143,15 +174,16 @@ __global__ void __launch_bounds__(256) add_rowvec_kernel(const float* __restrict
 }  // namespace
 
 static int layernorm_launch(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int C,
-                            float eps, uint16_t* hi, uint16_t* lo, void* stream) {
+                            float eps, uint16_t* hi, uint16_t* lo, void* stream, const float* add = nullptr,
+                            uint16_t* s_hi = nullptr, uint16_t* s_lo = nullptr) {
     const int wpb = 8;
     dim3 grid((unsigned)((rows + wpb - 1) / wpb));
     cudaStream_t st = as_stream(stream);
     switch (C) {
-        case 128: layernorm_kernel<1><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
-        case 256: layernorm_kernel<2><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
-        case 512: layernorm_kernel<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
-        case 1024: layernorm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo); break;
+        case 128: layernorm_kernel<1><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo, add, s_hi, s_lo); break;
+        case 256: layernorm_kernel<2><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo, add, s_hi, s_lo); break;
+        case 512: layernorm_kernel<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo, add, s_hi, s_lo); break;
+        case 1024: layernorm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y, rows, eps, hi, lo, add, s_hi, s_lo); break;
         default: return PVSG_ERR_UNSUPPORTED;
     }
     return pvsg_launch_status();
@@ -170,10 +202,19 @@ extern "C" int pvsg_layernorm_split(const float* x, const float* gamma, const fl
                             reinterpret_cast<uint16_t*>(y_lo), stream);
 }
 
-extern "C" int pvsg_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* y,
-                                   double* stats, int B, int64_t HW, int C, int groups, float eps,
-                                   int act, void* stream) {
-    PVSG_CHECK_ARG(x && gamma && beta && y && stats && B > 0 && HW > 0 && C > 0 && groups > 0);
+extern "C" int pvsg_layernorm_split2(const float* x, const float* gamma, const float* beta, float* y, void* y_hi,
+                                     void* y_lo, const float* add, void* s_hi, void* s_lo, int64_t rows, int C,
+                                     float eps, void* stream) {
+    PVSG_CHECK_ARG(x && gamma && beta && y && y_hi && y_lo && add && s_hi && s_lo && rows > 0);
+    return layernorm_launch(x, gamma, beta, y, rows, C, eps, reinterpret_cast<uint16_t*>(y_hi),
+                            reinterpret_cast<uint16_t*>(y_lo), stream, add, reinterpret_cast<uint16_t*>(s_hi),
+                            reinterpret_cast<uint16_t*>(s_lo));
+}
+
+static int groupnorm_launch(const float* x, const float* gamma, const float* beta, float* y, uint16_t* y_hi,
+                            uint16_t* y_lo, double* stats, int B, int64_t HW, int C, int groups, float eps, int act,
+                            void* stream) {
+    PVSG_CHECK_ARG(x && gamma && beta && (y || y_hi) && stats && B > 0 && HW > 0 && C > 0 && groups > 0);
     PVSG_CHECK_ARG(C % groups == 0 && (C / groups) % 4 == 0 && groups <= 64 && C / 4 <= 256);
     cudaStream_t st = as_stream(stream);
     if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B * groups, st) != cudaSuccess)
@@ -183,8 +224,22 @@ extern "C" int pvsg_groupnorm_nhwc(const float* x, const float* gamma, const flo
     gn_stats_kernel<<<g1, 256, 0, st>>>(x, stats, HW, C, groups, pix_per_cta);
     const int64_t total = (int64_t)B * HW * (C / 4);
     const unsigned g2 = (unsigned)imin64((total + 255) / 256, 148 * 16);
-    gn_apply_kernel<<<g2, 256, 0, st>>>(x, gamma, beta, stats, y, HW, C, groups, eps, act, total);
+    gn_apply_kernel<<<g2, 256, 0, st>>>(x, gamma, beta, stats, y, HW, C, groups, eps, act, total, y_hi, y_lo);
     return pvsg_launch_status();
+}
+
+extern "C" int pvsg_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* y,
+                                   double* stats, int B, int64_t HW, int C, int groups, float eps,
+                                   int act, void* stream) {
+    return groupnorm_launch(x, gamma, beta, y, nullptr, nullptr, stats, B, HW, C, groups, eps, act, stream);
+}
+
+extern "C" int pvsg_groupnorm_nhwc_split(const float* x, const float* gamma, const float* beta, float* y, void* y_hi,
+                                         void* y_lo, double* stats, int B, int64_t HW, int C, int groups, float eps,
+                                         int act, void* stream) {
+    PVSG_CHECK_ARG(y_hi && y_lo);
+    return groupnorm_launch(x, gamma, beta, y, reinterpret_cast<uint16_t*>(y_hi), reinterpret_cast<uint16_t*>(y_lo),
+                            stats, B, HW, C, groups, eps, act, stream);
 }
 
 extern "C" int pvsg_add_rowvec(const float* x, const float* v, float* y, int64_t rows, int C, void* stream) {

@@ -36,12 +36,15 @@ SIGNATURES = {
     'pvsg_nhwc_to_nchw': (I, [P, P, I, I, I, I, P]),
     'pvsg_layernorm': (I, [P, P, P, P, L, I, F, P]),
     'pvsg_layernorm_split': (I, [P, P, P, P, P, P, L, I, F, P]),
+    'pvsg_layernorm_split2': (I, [P, P, P, P, P, P, P, P, P, L, I, F, P]),
     'pvsg_groupnorm_nhwc': (I, [P, P, P, P, P, I, L, I, I, F, I, P]),
+    'pvsg_groupnorm_nhwc_split': (I, [P, P, P, P, P, P, P, I, L, I, I, F, I, P]),
     'pvsg_add_rowvec': (I, [P, P, P, L, I, P]),
     'pvsg_bilinear_resize_nhwc': (I, [P, P, I, I, I, I, I, I, I, P]),
     'pvsg_sine_pe': (I, [P, P, P, P, I, I, I, I, F, F, P]),
     'pvsg_msda_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
     'pvsg_msda_fused_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
+    'pvsg_msda_fused_forward_split': (I, [P, P, P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
     'pvsg_attention_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_attention': (I, [P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_attention_tc_workspace_bytes': (L, [I, I, I, I]),
@@ -96,7 +99,7 @@ def load():
 
 
 # kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)
-KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3}
+KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_groupnorm_nhwc_split': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3}
 launch_count = [0]
 
 

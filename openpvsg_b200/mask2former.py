@@ -234,14 +234,16 @@ class MultiScaleDeformableAttention(_Prepared):
             b=torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0).contiguous())
 
     @torch.no_grad()
-    def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None):
-        """x, pos [B,N,C]; ref [N,2] -> output_proj(msda) + x.  x_planes: operand planes of x when
-        the producer (the previous LayerNorm) already emitted them."""
+    def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None, q_planes=None):
+        """x, pos [B,N,C]; ref [N,2] -> output_proj(msda) + x.  x_planes / q_planes: operand planes of
+        x and of x + pos when the producer (the previous LayerNorm) already emitted them."""
         if self._prep is None:
             self._prepare()
-        proj = ops.linear(x, self._prep['w'], self._prep['b'], add_input=pos)
+        proj = ops.linear(q_planes, self._prep['w'], self._prep['b']) if q_planes is not None else \
+            ops.linear(x, self._prep['w'], self._prep['b'], add_input=pos)
         value = ops.linear(x_planes if x_planes is not None else x, self.value_proj.weight, self.value_proj.bias)
-        samp = ops.msda_fused_forward(value, spatial_shapes, proj, ref, self.num_heads, self.num_points)
+        samp = ops.msda_fused_forward(value, spatial_shapes, proj, ref, self.num_heads, self.num_points,
+                                      out_mode='split')   # planes for the output projection
         return ops.linear(samp, self.output_proj.weight, self.output_proj.bias, residual=x)
 
     @torch.no_grad()
@@ -323,16 +325,19 @@ class BaseTransformerLayer(nn.Module):
         self.norms = nn.ModuleList([_Norm(self.embed_dims), _Norm(self.embed_dims)])
 
     @torch.no_grad()
-    def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None):
-        """Returns (x, planes of x): both LayerNorms emit the operand planes of their output for the
-        GEMMs that consume it, and the FFN hidden layer only ever exists as planes."""
+    def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None, q_planes=None, next_q=True):
+        """Returns (x, planes of x, planes of x + pos): both LayerNorms emit the operand planes of
+        their output for the GEMMs that consume it (the last one also those of x + pos, the next
+        layer's query), and the FFN hidden layer only ever exists as planes."""
         n0, n1, ffn = self.norms[0], self.norms[1], self.ffns[0]
-        x = self.attentions[0].forward_tokens(x, pos, ref, spatial_shapes, x_planes)
+        x = self.attentions[0].forward_tokens(x, pos, ref, spatial_shapes, x_planes, q_planes)
         x, xs = ops.layernorm(x, n0.weight, n0.bias, n0.eps, out_split=True)
         h = ops.linear(xs if xs is not None else x, ffn.layers[0][0].weight, ffn.layers[0][0].bias,
                        act=ops.ACT_RELU, out_mode='split')
         x = ops.linear(h, ffn.layers[1].weight, ffn.layers[1].bias, residual=x if ffn.add_identity else None)
-        return ops.layernorm(x, n1.weight, n1.bias, n1.eps, out_split=True)
+        if next_q:
+            return ops.layernorm(x, n1.weight, n1.bias, n1.eps, out_split=True, add=pos)
+        return ops.layernorm(x, n1.weight, n1.bias, n1.eps, out_split=True) + (None,)
 
 
 @TRANSFORMER_LAYER_SEQUENCE.register_module()
@@ -364,9 +369,9 @@ class _ConvModule(nn.Module):
         y = ops.conv2d_nhwc(planes if planes is not None else x, self._w, self.conv.bias, pad=self.pad)
         return y
 
-    def norm_tokens(self, y):
+    def norm_tokens(self, y, out_mode='f32'):
         return ops.groupnorm_nhwc(y, self.gn.weight, self.gn.bias, self.gn.num_groups, self.gn.eps,
-                                  ops.ACT_RELU if self.act else ops.ACT_NONE)
+                                  ops.ACT_RELU if self.act else ops.ACT_NONE, out_mode=out_mode)
 
     def _load_from_state_dict(self, *a, **k):
         self._w = None
@@ -433,9 +438,10 @@ class MSDeformAttnPixelDecoder(_Prepared):
         x = torch.cat(toks, 1)  # pure data movement (torch.cat = cudaMemcpy-class op)
         pos, ref = self._shape_consts(shapes, x.device)
         posb = pos[None].expand(B, -1, -1).contiguous() if B > 1 else pos[None]
-        xs = None
-        for layer in self.encoder.layers:
-            x, xs = layer.forward_tokens(x, posb, ref, shapes, xs)
+        xs = qs = None
+        nlay = len(self.encoder.layers)
+        for li, layer in enumerate(self.encoder.layers):
+            x, xs, qs = layer.forward_tokens(x, posb, ref, shapes, xs, qs, next_q=li + 1 < nlay)
         outs, start = [], 0
         for (h, w) in shapes:
             outs.append(x[:, start:start + h * w].reshape(B, h, w, -1))
@@ -446,7 +452,9 @@ class MSDeformAttnPixelDecoder(_Prepared):
             cur = lat.norm_tokens(lat.forward_tokens(_tokens(feats[i])))
             ops.bilinear_resize_nhwc(outs[-1].contiguous(), cur.shape[1:3], out=cur, accumulate=True)
             oc = self.output_convs[j]
-            outs.append(oc.norm_tokens(oc.forward_tokens(cur)))
+            # maps beyond num_outs only feed the next FPN step / the mask-feature conv: planes suffice
+            last = i == 0 and len(outs) >= self.num_outs
+            outs.append(oc.norm_tokens(oc.forward_tokens(cur), out_mode='split' if last else 'f32'))
         wmf = self.mask_feature.weight.view(self.mask_feature.out_channels, -1)
         mf = ops.linear(outs[-1], wmf, self.mask_feature.bias)
         return _as_nchw(mf), [_as_nchw(o) for o in outs[:self.num_outs]]

@@ -392,9 +392,10 @@ def nhwc_to_nchw(x):
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5, out=None, out_split=False):
+def layernorm(x, gamma, beta, eps=1e-5, out=None, out_split=False, add=None):
     """LayerNorm over the last axis.  out_split=True additionally returns the Split planes of the
-    result (None on the SIMT engine): (y, planes)."""
+    result (None on the SIMT engine): (y, planes).  With ``add`` (same shape as x) also the planes of
+    y + add: (y, planes, planes_of_sum)."""
     lib = _l.load()
     _f32(x)
     if not x.is_contiguous():
@@ -402,31 +403,52 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, out_split=False):
     C = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
+    if add is not None and not out_split:
+        raise _l.PvsgError('layernorm: add needs out_split')
     if out_split and ENGINE[0] == 'tc' and C % 64 == 0 and x.numel() // C > SKINNY_M:
         hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
         lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        if add is not None:
+            if tuple(add.shape) != tuple(x.shape) or not add.is_contiguous():
+                raise _l.PvsgError('layernorm: add must match x')
+            shi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+            slo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+            _l.check(lib.pvsg_layernorm_split2(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), _ptr(hi),
+                                               _ptr(lo), _ptr(_f32(add)), _ptr(shi), _ptr(slo), x.numel() // C, C, eps,
+                                               _stream()), 'pvsg_layernorm_split2')
+            return out, Split(hi, lo), Split(shi, slo)
         _l.check(lib.pvsg_layernorm_split(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), _ptr(hi), _ptr(lo),
                                           x.numel() // C, C, eps, _stream()), 'pvsg_layernorm_split')
         return out, Split(hi, lo)
     _l.check(lib.pvsg_layernorm(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), x.numel() // C, C, eps,
                                 _stream()), 'pvsg_layernorm')
+    if add is not None:
+        return out, None, None
     return (out, None) if out_split else out
 
 
-def groupnorm_nhwc(x, gamma, beta, groups=32, eps=1e-5, act=ACT_NONE, out=None):
-    """x [B, H, W, C] (or [B, HW, C]) token-major."""
+def groupnorm_nhwc(x, gamma, beta, groups=32, eps=1e-5, act=ACT_NONE, out=None, out_mode='f32'):
+    """x [B, H, W, C] (or [B, HW, C]) token-major.  out_mode as in ``linear`` ('split': planes only)."""
     lib = _l.load()
     _f32(x)
     if not x.is_contiguous():
         raise _l.PvsgError('groupnorm: contiguous input required')
     B, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * C)
+    stats = torch.empty(B * groups * 2, device=x.device, dtype=torch.float64)
+    if out_mode != 'f32' and ENGINE[0] == 'tc' and C % 64 == 0 and out is None:
+        y = torch.empty_like(x) if out_mode == 'both' else None
+        hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        _l.check(lib.pvsg_groupnorm_nhwc_split(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(y), _ptr(hi),
+                                               _ptr(lo), _ptr(stats), B, HW, C, groups, eps, act, _stream()),
+                 'pvsg_groupnorm_nhwc_split')
+        return (y, Split(hi, lo)) if out_mode == 'both' else Split(hi, lo)
     if out is None:
         out = torch.empty_like(x)
-    stats = torch.empty(B * groups * 2, device=x.device, dtype=torch.float64)
     _l.check(lib.pvsg_groupnorm_nhwc(_ptr(x), _ptr(_f32(gamma)), _ptr(_f32(beta)), _ptr(out), _ptr(stats), B, HW,
                                      C, groups, eps, act, _stream()), 'pvsg_groupnorm_nhwc')
-    return out
+    return (out, None) if out_mode == 'both' else out
 
 
 def add_rowvec(x, v, out=None):
@@ -497,8 +519,9 @@ def msda_forward(value, spatial_shapes, sampling_locations, attention_weights):
     return out
 
 
-def msda_fused_forward(value, spatial_shapes, proj, ref, num_heads=8, num_points=4):
-    """value [B,N,H*D]; proj [B,Nq,H*L*P*3] raw (offsets | logits); ref [Nq,2]."""
+def msda_fused_forward(value, spatial_shapes, proj, ref, num_heads=8, num_points=4, out_mode='f32'):
+    """value [B,N,H*D]; proj [B,Nq,H*L*P*3] raw (offsets | logits); ref [Nq,2].
+    out_mode='split': the result leaves as operand planes only (tcgen05 engine, L*P <= 16)."""
     lib = _l.load()
     B, N, C = _f32(value).shape
     ss, ls, L, tot = _levels(spatial_shapes)
@@ -506,6 +529,14 @@ def msda_fused_forward(value, spatial_shapes, proj, ref, num_heads=8, num_points
     D = C // num_heads
     if tot != N or _f32(proj).shape[2] != num_heads * L * num_points * 3 or tuple(_f32(ref).shape) != (Nq, 2):
         raise _l.PvsgError('msda_fused_forward: shape mismatch')
+    if out_mode == 'split' and ENGINE[0] == 'tc' and L * num_points <= 16 and C % 64 == 0:
+        hi = torch.empty(B, Nq, C, device=value.device, dtype=torch.bfloat16)
+        lo = torch.empty(B, Nq, C, device=value.device, dtype=torch.bfloat16)
+        _l.check(lib.pvsg_msda_fused_forward_split(_ptr(value.contiguous()), ss, ls, _ptr(proj.contiguous()),
+                                                   _ptr(ref.contiguous()), None, _ptr(hi), _ptr(lo), B, N, Nq,
+                                                   num_heads, D, L, num_points, _stream()),
+                 'pvsg_msda_fused_forward_split')
+        return Split(hi, lo)
     out = torch.empty(B, Nq, C, device=value.device, dtype=torch.float32)
     _l.check(lib.pvsg_msda_fused_forward(_ptr(value.contiguous()), ss, ls, _ptr(proj.contiguous()),
                                          _ptr(ref.contiguous()), _ptr(out), B, N, Nq, num_heads, D, L,

@@ -151,3 +151,33 @@ def test_stem7x7s2_rowpair_conv(ops, B, C, H, W):
     assert tuple(y.shape) == (B, ref.shape[2], ref.shape[3], 64)
     err = (y.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
     assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+
+
+def test_plane_emitting_norms_and_msda(ops):
+    """LayerNorm (y and y + pos planes), GroupNorm planes and MSDA planes equal the split of the fp32
+    results of the same kernels."""
+    x, pos = randn(1, 300, 256), randn(2, 300, 256)
+    g, b = randn(3, 256), randn(4, 256)
+    y, ys, qs = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), out_split=True, add=pos.cuda())
+    ref = F.layer_norm(x, (256,), g, b)
+    assert (y.cpu() - ref).abs().max().item() < 1e-5
+    assert (_planes_value(ys) - y.cpu().double()).abs().max().item() < 2e-5
+    assert (_planes_value(qs) - (y.cpu() + pos).double()).abs().max().item() < 2e-5
+    xg = randn(5, 2, 20, 24, 256)
+    yg = ops.groupnorm_nhwc(xg.cuda(), g.cuda(), b.cuda(), 32, act=ops.ACT_RELU)
+    yf, sp = ops.groupnorm_nhwc(xg.cuda(), g.cuda(), b.cuda(), 32, act=ops.ACT_RELU, out_mode='both')
+    sp2 = ops.groupnorm_nhwc(xg.cuda(), g.cuda(), b.cuda(), 32, act=ops.ACT_RELU, out_mode='split')
+    assert torch.equal(yf, yg)
+    assert (_planes_value(sp) - yg.cpu().double()).abs().max().item() < 2e-5
+    assert torch.equal(sp2.hi, sp.hi) and torch.equal(sp2.lo, sp.lo)
+    shapes = [(5, 7), (10, 14), (20, 28)]
+    n = sum(h * w for h, w in shapes)
+    value = randn(6, 2, n, 256)
+    proj = torch.cat([randn(7, 2, n, 192) * 3, randn(8, 2, n, 96)], -1)
+    ref_pts = torch.rand(n, 2, generator=torch.Generator().manual_seed(9))
+    o = ops.msda_fused_forward(value.cuda(), shapes, proj.cuda(), ref_pts.cuda())
+    osp = ops.msda_fused_forward(value.cuda(), shapes, proj.cuda(), ref_pts.cuda(), out_mode='split')
+    assert isinstance(osp, ops.Split)
+    assert (_planes_value(osp) - o.cpu().double()).abs().max().item() < 2e-5 * max(1.0, o.abs().max().item())
+    hi, lo = ops.split_bf16(o)
+    assert torch.equal(osp.hi, hi) and torch.equal(osp.lo, lo)     # same rounding as the split kernel
