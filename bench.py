@@ -48,6 +48,17 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
+def gemm_traffic():
+    """DRAM bytes per gemm_tc_kernel launch, from the committed ncu pass over one frame-graph replay
+    (profiles/*_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, averaged over launches)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_gemm_traffic.json')))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get('avg_bytes_per_launch'), os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -373,12 +384,16 @@ def main():
     g = dict(ms=sum(fam[k]['ms'] for k in gk) or 1.0, gflop=sum(fam[k]['gflop'] for k in gk),
              launches=sum(fam[k]['launches'] for k in gk))
     achieved_tf = g['gflop'] / g['ms']  # GFLOP / ms == TFLOP/s
-    roofline = dict(kernel='gemm_tc_kernel + split_kernel (tcgen05 split-bf16 GEMM / implicit-GEMM conv engine; '
-                           'algorithmic 2MNK flops, each product = 3 bf16 MMAs)', bound='tensor',
+    traffic, traffic_src = gemm_traffic()
+    roofline = dict(kernel='gemm_tc_kernel (tcgen05 split-bf16 GEMM / implicit-GEMM conv engine; algorithmic 2MNK '
+                           'flops, each product = 3 bf16 MMAs => ceiling peak/3 on algorithmic flops)', bound='tensor',
                     achieved=round(achieved_tf, 2), peak=peaks['tf_sustained'], unit='TFLOP/s',
-                    frac=round(achieved_tf / peaks['tf_sustained'], 4), traffic=None,
+                    frac=round(achieved_tf / peaks['tf_sustained'], 4), traffic=traffic, traffic_source=traffic_src,
+                    frac_of_split_bf16_ceiling=round(3 * achieved_tf / peaks['tf_sustained'], 4),
                     peak_source=peaks['source'] + ', sustained bf16 figure (kernel timed inside a long step)',
                     launches_per_frame=round(g['launches'], 1), gflop_per_frame=round(g['gflop'], 1),
+                    gflop_per_launch=round(g['gflop'] / max(g['launches'], 1e-9), 2),
+                    us_per_launch=round(1e3 * g['ms'] / max(g['launches'], 1e-9), 2),
                     share_of_frame=round(g['ms'] / tot_ms, 3))
     m = fam.get('msda')
     kernels = {k: dict(ms_per_frame=round(d['ms'], 3), share=round(d['ms'] / tot_ms, 3), launches=round(d['launches'], 1))
@@ -386,9 +401,25 @@ def main():
     for k in gk:
         if fam[k]['gflop'] > 0:
             kernels[k]['TFLOPs'] = round(fam[k]['gflop'] / fam[k]['ms'], 1)
+    extra = {}
     if m:
-        kernels['msda']['achieved_GBps'] = round(m['gbyte'] / (m['ms'] * 1e-3), 1)
-        kernels['msda']['frac_hbm'] = round(m['gbyte'] / (m['ms'] * 1e-3) / peaks['hbm_gbs'], 4)
+        gbps = m['gbyte'] / (m['ms'] * 1e-3)
+        kernels['msda']['achieved_GBps'] = round(gbps, 1)
+        kernels['msda']['frac_hbm'] = round(gbps / peaks['hbm_gbs'], 4)
+        # north_star target: MSDeformAttn as a fraction of the HBM roofline (algorithmic bytes: value + raw
+        # projections + output = 3200 B per token and layer)
+        extra['roofline_msda'] = dict(kernel='msda_group_kernel', bound='hbm', achieved=round(gbps, 1),
+                                      peak=peaks['hbm_gbs'], unit='GB/s', frac=round(gbps / peaks['hbm_gbs'], 4),
+                                      traffic=None, note='LSU-pipe / issue bound: 48 bilinear corner lines of 128 B per '
+                                      '(query, head) pass through L1 (ncu profiles/r01i_ncu_msda_group.json)')
+    ml = fam.get('gemm_mask_logits')
+    if ml and ml['gflop'] > 0:
+        tf = ml['gflop'] / ml['ms']
+        extra['roofline_mask_einsum'] = dict(
+            kernel='gemm_tc_kernel (pvsg_mask_logits)', bound='hbm', unit='TFLOP/s', achieved=round(tf, 1),
+            peak=peaks['tf_sustained'], frac=round(tf / peaks['tf_sustained'], 4),
+            note='AI = 36 FLOP/B (fp32 I/O, Q = 100 rows) << ridge 250: HBM-bound by construction (SURVEY.md 8d); '
+                 'nine of the ten calls run on pooled features (exact, 3x fewer flops)')
     cpu = None
     if not args.no_cpu_baseline:
         fps, times = cpu_oracle_fps(args.cpu_frames)
@@ -411,7 +442,7 @@ def main():
                          api='engine.FrameRunner.submit/collect (pipelined) on pinned host frames',
                          sync_api_value=round(e2e_sync, 3),
                          sync_api='model(return_loss=False, rescale=True, img=..., ref_img=...) per frame'),
-                gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+                gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu, **extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -424,6 +424,18 @@ class MSDeformAttnPixelDecoder(_Prepared):
             self._prep = True
         return self._shape_cache[key]
 
+    def _batched_pos(self, pos, B):
+        """pos broadcast over the batch, materialised once per (shape, batch)."""
+        if B == 1:
+            return pos[None]
+        key = ('posb', pos.data_ptr(), tuple(pos.shape), B)
+        hit = self._shape_cache.get(key)
+        if hit is None:
+            hit = pos[None].expand(B, -1, -1).contiguous()
+            if not (pos.is_cuda and torch.cuda.is_current_stream_capturing()):
+                self._shape_cache[key] = hit   # tensors created during graph capture belong to the graph
+        return hit
+
     @torch.no_grad()
     def forward(self, feats):
         """feats: 4 maps [B,C,H,W] (C2..C5) -> (mask_feature [B,C,h4,w4], [m32, m16, m8])."""
@@ -437,7 +449,7 @@ class MSDeformAttnPixelDecoder(_Prepared):
             toks.append(y.view(B, -1, y.shape[-1]))
         x = torch.cat(toks, 1)  # pure data movement (torch.cat = cudaMemcpy-class op)
         pos, ref = self._shape_consts(shapes, x.device)
-        posb = pos[None].expand(B, -1, -1).contiguous() if B > 1 else pos[None]
+        posb = self._batched_pos(pos, B)
         xs = qs = None
         nlay = len(self.encoder.layers)
         for li, layer in enumerate(self.encoder.layers):
@@ -669,6 +681,18 @@ class _Mask2FormerHeadBase(_Prepared):
             self._pe_cache[key] = self.decoder_positional_encoding.tokens(h, w, device, t=t if self.video else 0)
         return self._pe_cache[key]
 
+    def _batched(self, t, B):
+        """t broadcast over the batch, materialised once per (tensor, batch)."""
+        if B == 1:
+            return t[None]
+        key = ('b', t.data_ptr(), t._version, tuple(t.shape), B)   # _version: parameters reloaded in place
+        hit = self._pe_cache.get(key)
+        if hit is None:
+            hit = t[None].expand(B, -1, -1).contiguous()
+            if not (t.is_cuda and torch.cuda.is_current_stream_capturing()):
+                self._pe_cache[key] = hit
+        return hit
+
     @torch.no_grad()
     def _run(self, feats, num_frames, want_all, force_masks=None):
         """Core forward on token-major tensors.
@@ -700,12 +724,12 @@ class _Mask2FormerHeadBase(_Prepared):
             h, w = lvl_shapes[i]
             dec_in.append(ops.add_rowvec(tok, self.level_embed.weight[i].contiguous()).view(B, T * h * w, C))
             pe = self._decoder_pe((T, h, w), tok.device)
-            dec_pe.append(pe[None].expand(B, -1, -1).contiguous() if B > 1 else pe[None])
+            dec_pe.append(self._batched(pe, B))
         kin_planes = [ops.maybe_split(d, pe) for d, pe in zip(dec_in, dec_pe)]
         vin_planes = [ops.maybe_split(d) for d in dec_in]
         Q = self.num_queries
         query = self.query_feat.weight[None].expand(B, -1, -1).contiguous()
-        qpos = self.query_embed.weight[None].expand(B, -1, -1).contiguous()
+        qpos = self._batched(self.query_embed.weight, B)
         layers = self.transformer_decoder.layers
         nl = self.num_transformer_decoder_layers
         # K / V projections of every (layer, level) pair: independent of the queries
