@@ -85,6 +85,15 @@ int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* 
                    int64_t M, int64_t N, int64_t K, int act, const void* R_hi, const void* R_lo,
                    const void* ident, void* stream);
 
+/* `batch` independent contractions C[b] = A[b] . W[b]^T in ONE launch (3-D tensor maps; batch strides
+ * a_bs / w_bs in elements): the per-frame query x pixel mask-logit einsum of a batch of frames
+ * ('bqc,bchw->bqhw', mask2former_head.py:382).  Outputs as pvsg_mask_logits: C fp32 [batch,M,ldc] and/or
+ * mask uint8 [batch,M,ldc] (1 where the logit < 0) + row_open int32 [batch,M] (+=, caller zeroes). */
+int pvsg_linear_tc_batched(const void* A_hi, const void* A_lo, int64_t lda, int64_t a_bs,
+                           const void* W_hi, const void* W_lo, int64_t ldw, int64_t w_bs, float* C,
+                           uint8_t* mask, int32_t* row_open, int64_t ldc, int batch, int64_t M,
+                           int64_t N, int64_t K, void* stream);
+
 /* pvsg_conv2d_nhwc (stride 1 or 2) on split operands: x planes [B,H,W,Cin], w planes
  * [Cout,R,S,Cin]; im2col-free -- a 4-D TMA box over the NHWC planes is shifted per filter
  * tap (traversed with elementStrides = stride) and out-of-bounds zero fill provides the

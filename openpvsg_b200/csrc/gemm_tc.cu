@@ -64,6 +64,7 @@ struct TcParams {
     int num_kb;
     int act;
     int tiles_m, tiles_n;
+    int batch, tiles_mb;   // batched linear mode: `batch` independent problems, tiles_mb M-tiles each
     int tma_out;   // bit 0: C leaves through TMA stores, bit 1: C_hi / C_lo do, bit 2: fp32 R arrives by TMA
     int res_mma;   // residual planes are added by the tensor core (extra k-blocks against the identity)
     // conv mode
@@ -103,6 +104,15 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -225,6 +235,9 @@ __device__ __forceinline__ Tile decode_tile(const TcParams& p, int mt, int nt, i
         tl.tb = mt / p.tiles_h;
         tl.oh0 = th * PATCH_H;
         tl.ow0 = tw * PATCH_W;
+    } else if (p.batch > 1) {
+        tl.tb = mt / p.tiles_mb;
+        tl.m0 = (int64_t)(mt - tl.tb * p.tiles_mb) * BM;
     }
     return tl;
 }
@@ -295,12 +308,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         const int iy = tl.oh0 * p.stride + r - p.pad, ix = tl.ow0 * p.stride + sx - p.pad;
                         tma_load_4d(&tmA_hi, &full[s], st, cb * BK, ix, iy, tl.tb);
                         tma_load_4d(&tmA_lo, &full[s], st + A_BYTES, cb * BK, ix, iy, tl.tb);
+                    } else if (p.batch > 1) {
+                        tma_load_3d(&tmA_hi, &full[s], st, kb * BK, (int)tl.m0, tl.tb);
+                        tma_load_3d(&tmA_lo, &full[s], st + A_BYTES, kb * BK, (int)tl.m0, tl.tb);
                     } else {
                         tma_load_2d(&tmA_hi, &full[s], st, kb * BK, (int)tl.m0);
                         tma_load_2d(&tmA_lo, &full[s], st + A_BYTES, kb * BK, (int)tl.m0);
                     }
-                    tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
-                    tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
+                    if (p.batch > 1) {   // every problem of the batch has its own W
+                        tma_load_3d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0, tl.tb);
+                        tma_load_3d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0, tl.tb);
+                    } else {
+                        tma_load_2d(&tmB_hi, &full[s], st + 2 * A_BYTES, kb * BK, tl.n0);
+                        tma_load_2d(&tmB_lo, &full[s], st + 2 * A_BYTES + B_BYTES, kb * BK, tl.n0);
+                    }
                 }
                 for (int j = 0; j < res_kb; ++j) {
                     if ((int64_t)tl.n0 + j * BK >= p.N) break;      // same rule in the MMA warp
@@ -411,6 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             } else {
                 out_row = tl.m0 + row_in_tile;
                 row_ok = out_row < p.M;
+                out_row += (int64_t)tl.tb * p.M;     // batched linear: problem tb's rows (tb = 0 otherwise)
             }
             mbar_wait(&acc_full[buf], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -511,6 +533,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         __syncwarp();
                         if (lane == 0) {
                             if (p.conv) tma_store_4d(&tmC, zone, (int)n, tl.ow0, tl.oh0 + r0 / PATCH_W, tl.tb);
+                            else if (p.batch > 1) tma_store_3d(&tmC, zone, (int)n, (int)(tl.m0 + r0), tl.tb);
                             else tma_store_2d(&tmC, zone, (int)n, (int)(tl.m0 + r0));
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
@@ -802,6 +825,33 @@ bool make_out_map(CUtensorMap* m, const void* cptr, bool f32, const TcParams& p,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D map over `batch` row-major [rows, cols] bf16 matrices (pitch ld, batch stride bs, elements)
+bool make_map_3d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int64_t bs, int batch,
+                 int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fp32 output of the batched mode: [batch, M, N] with row pitch ld, 32 x 32 boxes
+bool make_out_map_3d(CUtensorMap* m, const void* ptr, int64_t M, int64_t N, int64_t ld, int batch) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)M * ld * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN>
@@ -821,11 +871,15 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
     CUtensorMap c{}, c_hi{}, c_lo{}, r{}, ra_hi{}, ra_lo{}, e{};
     q.tma_out = 0;
     q.res_mma = 0;
-    if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B, p.ldc)) q.tma_out |= 1;
-    if (!direct && p.C_hi && p.ldc % 8 == 0 && al16(p.C_hi) && al16(p.C_lo) &&
+    if (p.batch > 1) {
+        if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map_3d(&c, p.C, p.M, p.N, p.ldc, p.batch))
+            q.tma_out |= 1;
+    } else if (!direct && p.C && p.ldc % 4 == 0 && al16(p.C) && make_out_map(&c, p.C, true, p, B, p.ldc)) q.tma_out |= 1;
+    if (p.batch <= 1 && !direct && p.C_hi && p.ldc % 8 == 0 && al16(p.C_hi) && al16(p.C_lo) &&
         make_out_map(&c_hi, p.C_hi, false, p, B, p.ldc) && make_out_map(&c_lo, p.C_lo, false, p, B, p.ldc))
         q.tma_out |= 2;
-    if (!direct && p.R && p.ldr % 4 == 0 && al16(p.R) && make_out_map(&r, p.R, true, p, B, p.ldr)) q.tma_out |= 4;
+    if (p.batch <= 1 && !direct && p.R && p.ldr % 4 == 0 && al16(p.R) && make_out_map(&r, p.R, true, p, B, p.ldr))
+        q.tma_out |= 4;
     // residual planes as extra k-blocks against the identity (linear mode; operand-style maps)
     if (p.R_hi && !p.conv && p.ident && p.ldr % 8 == 0 && al16(p.R_hi) && al16(p.R_lo) && al16(p.ident) &&
         make_map_2d(&ra_hi, p.R_hi, p.M, p.N, p.ldr, BM) && make_map_2d(&ra_lo, p.R_lo, p.M, p.N, p.ldr, BM) &&
@@ -905,6 +959,37 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
     p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + bn - 1) / bn);
+    return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream))
+                     : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
+}
+
+extern "C" int pvsg_linear_tc_batched(const void* A_hi, const void* A_lo, int64_t lda, int64_t a_bs, const void* W_hi,
+                                      const void* W_lo, int64_t ldw, int64_t w_bs, float* C, uint8_t* mask,
+                                      int32_t* row_open, int64_t ldc, int batch, int64_t M, int64_t N, int64_t K,
+                                      void* stream) {
+    PVSG_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && (C || mask) && batch > 0 && M > 0 && N > 0 && K > 0);
+    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && a_bs >= M * lda && w_bs >= N * ldw);
+    if (K % BK != 0 || (lda | ldw | a_bs | w_bs) % 8 != 0 || !al16(A_hi) || !al16(A_lo) || !al16(W_hi) || !al16(W_lo))
+        return PVSG_ERR_UNSUPPORTED;
+    const int64_t tiles_mb = (M + BM - 1) / BM;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || batch * tiles_mb * ((N + 127) / 128) > 0x7fffffffLL)
+        return PVSG_ERR_UNSUPPORTED;
+    const int bn = pick_bn(batch * tiles_mb, N);
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    // rank-3 maps for a real batch; batch 1 is the plain 2-D problem
+    if (batch > 1) {
+        if (!make_map_3d(&ta_hi, A_hi, M, K, lda, a_bs, batch, BM) || !make_map_3d(&ta_lo, A_lo, M, K, lda, a_bs, batch, BM) ||
+            !make_map_3d(&tb_hi, W_hi, N, K, ldw, w_bs, batch, bn) || !make_map_3d(&tb_lo, W_lo, N, K, ldw, w_bs, batch, bn))
+            return PVSG_ERR_LAUNCH;
+    } else if (!make_map_2d(&ta_hi, A_hi, M, K, lda, BM) || !make_map_2d(&ta_lo, A_lo, M, K, lda, BM) ||
+               !make_map_2d(&tb_hi, W_hi, N, K, ldw, bn) || !make_map_2d(&tb_lo, W_lo, N, K, ldw, bn)) {
+        return PVSG_ERR_LAUNCH;
+    }
+    TcParams p{};
+    p.C = C; p.mask = mask; p.row_open = row_open;
+    p.M = M; p.N = N; p.ldc = ldc; p.num_kb = (int)(K / BK); p.act = PVSG_ACT_NONE; p.conv = 0;
+    p.batch = batch; p.tiles_mb = (int)tiles_mb;
+    p.tiles_m = (int)(batch * tiles_mb); p.tiles_n = (int)((N + bn - 1) / bn);
     return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream))
                      : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
 }

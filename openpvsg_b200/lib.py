@@ -30,6 +30,7 @@ SIGNATURES = {
     'pvsg_stem7x7s2_pack': (I, [P, P, P, I, I, I, I, P]),
     'pvsg_im2col_split': (I, [P, P, P, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_linear_tc': (I, [P, P, L, P, P, L, P, P, L, P, P, P, P, P, L, L, L, L, I, P, P, P, P]),
+    'pvsg_linear_tc_batched': (I, [P, P, L, L, P, P, L, L, P, P, P, L, I, L, L, L, P]),
     'pvsg_conv2d_tc': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P]),
     'pvsg_maxpool3x3s2_nhwc': (I, [P, P, I, I, I, I, P]),
     'pvsg_nchw_to_nhwc': (I, [P, P, I, I, I, I, P]),

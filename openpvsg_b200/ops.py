@@ -618,12 +618,12 @@ def mask_logits(embed, feat, want_logits=True, want_mask=False, feat_planes=None
         row_open = torch.zeros(B, Q, device=dev, dtype=torch.int32) if want_mask else None
         e_hi, e_lo = embed if isinstance(embed, Split) else split_bf16(embed)
         f_hi, f_lo = feat_planes if feat_planes is not None else split_bf16(feat)
-        for b in range(B):
-            _l.check(lib.pvsg_linear_tc(_ptr(e_hi[b]), _ptr(e_lo[b]), C, _ptr(f_hi[b]), _ptr(f_lo[b]), C, None, None,
-                                        0, _ptr(logits[b]) if want_logits else None, None, None,
-                                        _ptr(mask[b]) if want_mask else None,
-                                        _ptr(row_open[b]) if want_mask else None, P, Q, P, C, ACT_NONE, None, None, None, _stream()),
-                     'pvsg_linear_tc')
+        if not (e_hi.is_contiguous() and e_lo.is_contiguous() and f_hi.is_contiguous() and f_lo.is_contiguous()):
+            raise _l.PvsgError('mask_logits: contiguous operand planes required')
+        # all frames of the batch in one launch (3-D tensor maps)
+        _l.check(lib.pvsg_linear_tc_batched(_ptr(e_hi), _ptr(e_lo), C, Q * C, _ptr(f_hi), _ptr(f_lo), C, P * C,
+                                            _ptr(logits), _ptr(mask), _ptr(row_open), P, B, Q, P, C, _stream()),
+                 'pvsg_linear_tc_batched')
         return logits, mask, row_open
     logits = torch.empty(B, Q, P, device=embed.device, dtype=torch.float32) if want_logits else None
     mask = torch.empty(B, Q, P, device=embed.device, dtype=torch.uint8) if want_mask else None
