@@ -182,7 +182,8 @@ def kernel_breakdown(det, img, meta, batch=1):
             ('msda_fused_forward', 'msda', None, msda_bytes), ('attention', 'attention', None, None),
             ('layernorm', 'norm', None, None), ('groupnorm_nhwc', 'norm', None, None),
             ('add_rowvec', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
-            ('instance_masks', 'postprocess', None, None), ('instance_select', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
+            ('instance_masks', 'postprocess', None, None), ('instance_select', 'postprocess', None, None),
+            ('postprocess_batched', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
             ('maxpool3x3s2_nhwc', 'resize', None, None))
     saved, depth = {}, [0]
 
@@ -218,8 +219,7 @@ def kernel_breakdown(det, img, meta, batch=1):
         xb = img[None].expand(batch, -1, -1, -1).contiguous()
         cls, mlr, _ = det.panoptic_head.simple_test_with_query(det.extract_feat(xb), [[meta]] * batch, upsample=False)
         from openpvsg_b200 import engine as _engine
-        for b in range(batch):
-            _engine.postprocess_frame(det, cls[b], mlr[b, 0].contiguous(), (736, 1280), (H, W), (H, W))
+        _engine.postprocess_batch(det, cls, mlr[:, 0].contiguous(), (736, 1280), (H, W), (H, W))
         torch.cuda.synchronize()
     finally:
         det._runners = runners

@@ -290,6 +290,27 @@ int pvsg_instance_finalize(const float* scores, const int32_t* labels, const int
                            float* boxes6, int32_t* out_labels, int32_t* sel_query, int32_t* count,
                            void* stream);
 
+/* Batched forms (B frames per launch; every array gains a leading [B] axis, mask_logits is
+ * [B,Q,h,w], query_idx [B,n] indexes the queries of its own frame).  The single-frame entry
+ * points above are these with B = 1. */
+int pvsg_panoptic_fuse_batched(const float* cls_logits, const float* mask_logits, int B, int Q, int NC,
+                               int num_things, int h, int w, int in_h, int in_w, int img_h, int img_w,
+                               int out_h, int out_w, float object_mask_thr, double iou_thr,
+                               int filter_low_score, int instance_offset, int32_t* pan_out,
+                               int32_t* seg_info, int32_t* work, float* scores, uint16_t* pix_ws,
+                               void* stream);
+int pvsg_instance_select_batched(const float* cls_logits, int B, int Q, int NC, int k,
+                                 float* top_scores, int32_t* top_labels, int32_t* top_query,
+                                 void* stream);
+int pvsg_instance_masks_batched(const float* mask_logits, const int32_t* query_idx, int B, int Q, int n,
+                                int h, int w, int in_h, int in_w, int img_h, int img_w, int out_h,
+                                int out_w, float* stats, int32_t* boxes, uint8_t* masks_out,
+                                void* stream);
+int pvsg_instance_finalize_batched(const float* scores, const int32_t* labels, const int32_t* query,
+                                   const float* stats, const int32_t* boxes, int B, int n,
+                                   int num_things, int topk, float* boxes6, int32_t* out_labels,
+                                   int32_t* sel_query, int32_t* count, void* stream);
+
 /* ------------------------------------------------------------ relation head ----- */
 
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */

@@ -53,6 +53,11 @@ __global__ void __launch_bounds__(1024) pan_select_kernel(const float* __restric
     __shared__ int keep[1024];
     __shared__ float sc[1024];
     __shared__ int lb[1024];
+    {   // one CTA per frame of the batch
+        const int bz = blockIdx.x;
+        cls += (int64_t)bz * Q * (NC + 1); seg_info += (int64_t)bz * (1 + 4 * Q);
+        work += (int64_t)bz * 4 * Q; scores += (int64_t)bz * Q;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 4 * Q; i += blockDim.x) work[i] = 0;
     for (int q = warp; q < Q; q += nwarp) {
@@ -103,10 +108,15 @@ __global__ void __launch_bounds__(256) pan_pixel_kernel(const float* __restrict_
                                                         const float* __restrict__ scores, int32_t* __restrict__ work,
                                                         uint16_t* __restrict__ pix) {
     extern __shared__ int sh_cnt[];  // [3 * n_kept]
+    const int64_t npix = (int64_t)g.out_h * g.out_w;
+    {   // blockIdx.y = frame of the batch
+        const int bz = blockIdx.y;
+        mask_logits += (int64_t)bz * Q * g.h * g.w; seg_info += (int64_t)bz * (1 + 4 * Q);
+        scores += (int64_t)bz * Q; work += (int64_t)bz * 4 * Q; pix += (int64_t)bz * npix;
+    }
     const int n = seg_info[0];
     for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) sh_cnt[i] = 0;
     __syncthreads();
-    const int64_t npix = (int64_t)g.out_h * g.out_w;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = p < npix;
     const int oy = valid ? (int)(p / g.out_w) : 0, ox = valid ? (int)(p % g.out_w) : 0;
@@ -149,7 +159,9 @@ __global__ void __launch_bounds__(256) pan_pixel_kernel(const float* __restrict_
 // mask2former_fusion_head.py:140-169.
 __global__ void pan_decide_kernel(int Q, int num_things, double iou_thr, int filter_low_score, int instance_offset,
                                   int32_t* __restrict__ seg_info, const int32_t* __restrict__ work) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x != 0) return;
+    seg_info += (int64_t)blockIdx.x * (1 + 4 * Q);   // one CTA per frame of the batch
+    work += (int64_t)blockIdx.x * 4 * Q;
     const int n = seg_info[0];
     int instance_id = 1;
     for (int k = 0; k < n; ++k) {
@@ -175,7 +187,10 @@ __global__ void pan_decide_kernel(int Q, int num_things, double iou_thr, int fil
 // Step 4: winner index -> segment id.
 __global__ void __launch_bounds__(256) pan_write_kernel(const uint16_t* __restrict__ pix,
                                                         const int32_t* __restrict__ seg_info, int NC,
-                                                        int filter_low_score, int32_t* __restrict__ pan, int64_t npix) {
+                                                        int filter_low_score, int32_t* __restrict__ pan, int64_t npix,
+                                                        int Q) {
+    pix += (int64_t)blockIdx.y * npix; pan += (int64_t)blockIdx.y * npix;   // blockIdx.y = frame
+    seg_info += (int64_t)blockIdx.y * (1 + 4 * Q);
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
          p += (int64_t)gridDim.x * blockDim.x) {
         const int v = pix[p];
@@ -204,13 +219,13 @@ __global__ void ins_init_kernel(float* stats, int32_t* boxes, int n) {
 __global__ void __launch_bounds__(256) ins_pixel_kernel(const float* __restrict__ mask_logits,
                                                         const int32_t* __restrict__ query_idx, UpGeom g,
                                                         float* __restrict__ stats, int32_t* __restrict__ boxes,
-                                                        uint8_t* __restrict__ masks_out) {
+                                                        uint8_t* __restrict__ masks_out, int Q, int n) {
     // one CTA = INS_STRIPS consecutive strips of 256 pixels of one candidate; statistics are
     // reduced in registers -> warp shuffles -> shared memory, then ONE set of atomics per CTA
-    const int i = blockIdx.y;
+    const int i = blockIdx.y;          // candidate i of frame i / n
     const int q = query_idx[i];
     const int64_t npix = (int64_t)g.out_h * g.out_w;
-    const float* lg = mask_logits + (int64_t)q * g.h * g.w;
+    const float* lg = mask_logits + ((int64_t)(i / n) * Q + q) * g.h * g.w;
     float s = 0.f;
     int cnt = 0, xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
     for (int st = 0; st < INS_STRIPS; ++st) {
@@ -291,6 +306,11 @@ __global__ void __launch_bounds__(256) pan_pixel_fast_kernel(const float* __rest
                                                              const float* __restrict__ scores,
                                                              int32_t* __restrict__ work, uint16_t* __restrict__ pix) {
     extern __shared__ int sh_cnt[];  // [3 * n_kept]
+    {   // blockIdx.z = frame of the batch
+        const int bz = blockIdx.z;
+        mask_logits += (int64_t)bz * Q * g.h * g.w; seg_info += (int64_t)bz * (1 + 4 * Q);
+        scores += (int64_t)bz * Q; work += (int64_t)bz * 4 * Q; pix += (int64_t)bz * g.out_h * g.out_w;
+    }
     const int n = seg_info[0];
     for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) sh_cnt[i] = 0;
     __syncthreads();
@@ -360,11 +380,18 @@ template <bool MASKS>
 __global__ void __launch_bounds__(256) ins_pixel_fast_kernel(const float* __restrict__ mask_logits,
                                                              const int32_t* __restrict__ query_idx, UpGeom g,
                                                              float* __restrict__ stats, int32_t* __restrict__ boxes,
-                                                             uint8_t* __restrict__ masks_out) {
-    const int i = blockIdx.z;
-    const float* lg = mask_logits + (int64_t)query_idx[i] * g.h * g.w;
+                                                             uint8_t* __restrict__ masks_out, int Q, int n) {
+    const int i = blockIdx.z;          // candidate i of frame i / n
+    const float* lg = mask_logits + ((int64_t)(i / n) * Q + query_idx[i]) * g.h * g.w;
     const int ox = blockIdx.x * blockDim.x + threadIdx.x;
     const int oy0 = blockIdx.y * INS_ROWS;
+    // vertical source coordinates of the CTA's rows: computed once, read as broadcasts
+    __shared__ int sy0[INS_ROWS], sy1[INS_ROWS];
+    __shared__ float swy0[INS_ROWS], swy1[INS_ROWS];
+    if (threadIdx.x < INS_ROWS)
+        bilinear_coord(min(oy0 + (int)threadIdx.x, g.out_h - 1), g.sh, g.h, sy0[threadIdx.x], sy1[threadIdx.x],
+                       swy0[threadIdx.x], swy1[threadIdx.x]);
+    __syncthreads();
     const bool xvalid = ox < g.out_w;
     int x0, x1;
     float wx0, wx1;
@@ -373,9 +400,8 @@ __global__ void __launch_bounds__(256) ins_pixel_fast_kernel(const float* __rest
     int cnt = 0, ymin = INT_MAX, ymax = -1, cy0 = -1, cy1 = -1;
     const int rows = min(INS_ROWS, g.out_h - oy0);
     for (int r = 0; r < rows; ++r) {
-        int y0, y1;
-        float wy0, wy1;
-        bilinear_coord(oy0 + r, g.sh, g.h, y0, y1, wy0, wy1);
+        const int y0 = sy0[r], y1 = sy1[r];
+        const float wy0 = swy0[r], wy1 = swy1[r];
         if (y0 != cy0 || y1 != cy1) {   // warp-uniform
             cy0 = y0; cy1 = y1;
             top = __ldg(lg + cy0 * g.w + x0) * wx0 + __ldg(lg + cy0 * g.w + x1) * wx1;
@@ -441,6 +467,11 @@ __global__ void __launch_bounds__(1024) ins_select_kernel(const float* __restric
     __shared__ unsigned sel_prefix, sel_remaining, out_gt, out_eq;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int total = Q * NC;
+    {   // one CTA per frame of the batch
+        const int bz = blockIdx.x;
+        cls += (int64_t)bz * Q * (NC + 1);
+        top_scores += (int64_t)bz * k; top_labels += (int64_t)bz * k; top_query += (int64_t)bz * k;
+    }
     for (int q = warp; q < Q; q += nwarp) {
         const float* row = cls + (int64_t)q * (NC + 1);
         float mx = -INFINITY;
@@ -469,15 +500,35 @@ __global__ void __launch_bounds__(1024) ins_select_kernel(const float* __restric
             if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned rem = sel_remaining;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (hist[b] >= rem) break;
-                rem -= hist[b];
+        if (warp == 0) {
+            // bin holding the rem-th largest element: lane L owns bins 255 - 8L .. 248 - 8L (descending),
+            // exclusive prefix over lanes by shuffles, then a scan of the owning lane's 8 bins
+            const unsigned rem0 = sel_remaining;
+            unsigned mine[8], tot = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { mine[e] = hist[255 - 8 * lane - e]; tot += mine[e]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            sel_prefix = prefix | ((unsigned)b << shift);
-            sel_remaining = rem;   // how many elements equal to the final threshold are taken
+            const unsigned excl = incl - tot;
+            const bool owner = excl < rem0 && rem0 <= incl;       // exactly one lane (total >= rem0)
+            const unsigned ball = __ballot_sync(0xffffffffu, owner);
+            if (ball == 0) {            // cannot happen (k <= total); keep the state consistent
+                if (lane == 0) { sel_prefix = prefix; sel_remaining = rem0; }
+            } else if (owner) {
+                unsigned rem = rem0 - excl;
+                int b = 255 - 8 * lane;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (mine[e] >= rem) { b = 255 - 8 * lane - e; break; }
+                    rem -= mine[e];
+                }
+                sel_prefix = prefix | ((unsigned)b << shift);
+                sel_remaining = rem;   // how many elements equal to the final threshold are taken
+            }
         }
         __syncthreads();
     }
@@ -533,6 +584,13 @@ __global__ void __launch_bounds__(128) ins_finalize_kernel(const float* __restri
                                                            int32_t* __restrict__ count) {
     __shared__ float ds[1024];
     __shared__ int thing[1024];
+    {   // one CTA per frame of the batch
+        const int bz = blockIdx.x;
+        scores += (int64_t)bz * n; labels += (int64_t)bz * n; query += (int64_t)bz * n;
+        stats += (int64_t)bz * 2 * n; boxes += (int64_t)bz * 4 * n;
+        boxes6 += (int64_t)bz * 6 * topk; out_labels += (int64_t)bz * topk; sel_query += (int64_t)bz * topk;
+        count += bz;
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int t = labels[i] < num_things ? 1 : 0;
         thing[i] = t;
@@ -579,60 +637,81 @@ int make_geom(UpGeom& g, int h, int w, int in_h, int in_w, int img_h, int img_w,
 
 }  // namespace
 
+extern "C" int pvsg_panoptic_fuse_batched(const float* cls_logits, const float* mask_logits, int B, int Q, int NC,
+                                          int num_things, int h, int w, int in_h, int in_w, int img_h, int img_w,
+                                          int out_h, int out_w, float object_mask_thr, double iou_thr,
+                                          int filter_low_score, int instance_offset, int32_t* pan_out,
+                                          int32_t* seg_info, int32_t* work, float* scores, uint16_t* pix_ws,
+                                          void* stream) {
+    PVSG_CHECK_ARG(cls_logits && mask_logits && pan_out && seg_info && work && scores && pix_ws);
+    PVSG_CHECK_ARG(B > 0 && B <= 65535 && Q > 0 && Q <= 1024 && NC > 0 && num_things >= 0 && num_things <= NC);
+    UpGeom g{};
+    int rc = make_geom(g, h, w, in_h, in_w, img_h, img_w, out_h, out_w);
+    if (rc != PVSG_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int64_t npix = (int64_t)out_h * out_w;
+    pan_select_kernel<<<B, 1024, 0, st>>>(cls_logits, Q, NC, object_mask_thr, seg_info, work, scores);
+    if (!g.rescale) {
+        dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)((out_h + PAN_ROWS - 1) / PAN_ROWS), (unsigned)B);
+        pan_pixel_fast_kernel<<<grid, 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info, scores, work, pix_ws);
+    } else {
+        dim3 grid((unsigned)((npix + 255) / 256), (unsigned)B);
+        pan_pixel_kernel<<<grid, 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info, scores, work, pix_ws);
+    }
+    pan_decide_kernel<<<B, 32, 0, st>>>(Q, num_things, iou_thr, filter_low_score, instance_offset, seg_info, work);
+    dim3 gw((unsigned)imin64((npix + 255) / 256, 148 * 16), (unsigned)B);
+    pan_write_kernel<<<gw, 256, 0, st>>>(pix_ws, seg_info, NC, filter_low_score, pan_out, npix, Q);
+    return pvsg_launch_status();
+}
+
 extern "C" int pvsg_panoptic_fuse(const float* cls_logits, const float* mask_logits, int Q, int NC,
                                   int num_things, int h, int w, int in_h, int in_w, int img_h, int img_w,
                                   int out_h, int out_w, float object_mask_thr, double iou_thr,
                                   int filter_low_score, int instance_offset, int32_t* pan_out,
                                   int32_t* seg_info, int32_t* work, float* scores, uint16_t* pix_ws,
                                   void* stream) {
-    PVSG_CHECK_ARG(cls_logits && mask_logits && pan_out && seg_info && work && scores && pix_ws);
-    PVSG_CHECK_ARG(Q > 0 && Q <= 1024 && NC > 0 && num_things >= 0 && num_things <= NC);
+    return pvsg_panoptic_fuse_batched(cls_logits, mask_logits, 1, Q, NC, num_things, h, w, in_h, in_w, img_h, img_w,
+                                      out_h, out_w, object_mask_thr, iou_thr, filter_low_score, instance_offset,
+                                      pan_out, seg_info, work, scores, pix_ws, stream);
+}
+
+extern "C" int pvsg_instance_masks_batched(const float* mask_logits, const int32_t* query_idx, int B, int Q, int n,
+                                           int h, int w, int in_h, int in_w, int img_h, int img_w, int out_h,
+                                           int out_w, float* stats, int32_t* boxes, uint8_t* masks_out,
+                                           void* stream) {
+    PVSG_CHECK_ARG(mask_logits && query_idx && stats && boxes && B > 0 && Q > 0 && n > 0 && (int64_t)B * n <= 65535);
     UpGeom g{};
     int rc = make_geom(g, h, w, in_h, in_w, img_h, img_w, out_h, out_w);
     if (rc != PVSG_OK) return rc;
     cudaStream_t st = as_stream(stream);
     const int64_t npix = (int64_t)out_h * out_w;
-    pan_select_kernel<<<1, 1024, 0, st>>>(cls_logits, Q, NC, object_mask_thr, seg_info, work, scores);
+    const int nb = B * n;
+    ins_init_kernel<<<(nb + 127) / 128, 128, 0, st>>>(stats, boxes, nb);
     if (!g.rescale) {
-        dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)((out_h + PAN_ROWS - 1) / PAN_ROWS));
-        pan_pixel_fast_kernel<<<grid, 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info, scores, work, pix_ws);
+        dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)((out_h + INS_ROWS - 1) / INS_ROWS), (unsigned)nb);
+        if (masks_out)
+            ins_pixel_fast_kernel<true><<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out, Q, n);
+        else
+            ins_pixel_fast_kernel<false><<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out, Q, n);
     } else {
-        pan_pixel_kernel<<<(unsigned)((npix + 255) / 256), 256, sizeof(int) * 3 * Q, st>>>(mask_logits, g, Q, seg_info,
-                                                                                           scores, work, pix_ws);
+        dim3 grid((unsigned)((npix + 256 * INS_STRIPS - 1) / (256 * INS_STRIPS)), (unsigned)nb);
+        ins_pixel_kernel<<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out, Q, n);
     }
-    pan_decide_kernel<<<1, 32, 0, st>>>(Q, num_things, iou_thr, filter_low_score, instance_offset, seg_info, work);
-    pan_write_kernel<<<(unsigned)imin64((npix + 255) / 256, 148 * 16), 256, 0, st>>>(
-        pix_ws, seg_info, NC, filter_low_score, pan_out, npix);
+    ins_finish_kernel<<<(nb + 127) / 128, 128, 0, st>>>(boxes, nb);
     return pvsg_launch_status();
 }
 
 extern "C" int pvsg_instance_masks(const float* mask_logits, const int32_t* query_idx, int n, int h, int w,
                                    int in_h, int in_w, int img_h, int img_w, int out_h, int out_w,
                                    float* stats, int32_t* boxes, uint8_t* masks_out, void* stream) {
-    PVSG_CHECK_ARG(mask_logits && query_idx && stats && boxes && n > 0 && n <= 65535);
-    UpGeom g{};
-    int rc = make_geom(g, h, w, in_h, in_w, img_h, img_w, out_h, out_w);
-    if (rc != PVSG_OK) return rc;
-    cudaStream_t st = as_stream(stream);
-    const int64_t npix = (int64_t)out_h * out_w;
-    ins_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, boxes, n);
-    if (!g.rescale) {
-        dim3 grid((unsigned)((out_w + 255) / 256), (unsigned)((out_h + INS_ROWS - 1) / INS_ROWS), (unsigned)n);
-        if (masks_out)
-            ins_pixel_fast_kernel<true><<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
-        else
-            ins_pixel_fast_kernel<false><<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
-    } else {
-        dim3 grid((unsigned)((npix + 256 * INS_STRIPS - 1) / (256 * INS_STRIPS)), (unsigned)n);
-        ins_pixel_kernel<<<grid, 256, 0, st>>>(mask_logits, query_idx, g, stats, boxes, masks_out);
-    }
-    ins_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(boxes, n);
-    return pvsg_launch_status();
+    // a single frame: the query count only enters as the per-frame stride, which is unused for B = 1
+    return pvsg_instance_masks_batched(mask_logits, query_idx, 1, 1 << 20, n, h, w, in_h, in_w, img_h, img_w, out_h,
+                                       out_w, stats, boxes, masks_out, stream);
 }
 
-extern "C" int pvsg_instance_select(const float* cls_logits, int Q, int NC, int k, float* top_scores,
-                                    int32_t* top_labels, int32_t* top_query, void* stream) {
-    PVSG_CHECK_ARG(cls_logits && top_scores && top_labels && top_query && Q > 0 && NC > 0 && k > 0);
+extern "C" int pvsg_instance_select_batched(const float* cls_logits, int B, int Q, int NC, int k, float* top_scores,
+                                            int32_t* top_labels, int32_t* top_query, void* stream) {
+    PVSG_CHECK_ARG(cls_logits && top_scores && top_labels && top_query && B > 0 && Q > 0 && NC > 0 && k > 0);
     PVSG_CHECK_ARG((int64_t)k <= (int64_t)Q * NC);
     const size_t smem = sizeof(float) * (size_t)Q * NC;
     if (smem > 200 * 1024) return PVSG_ERR_UNSUPPORTED;
@@ -643,7 +722,23 @@ extern "C" int pvsg_instance_select(const float* cls_logits, int Q, int NC, int 
             return PVSG_ERR_LAUNCH;
         configured = true;
     }
-    ins_select_kernel<<<1, 1024, smem, as_stream(stream)>>>(cls_logits, Q, NC, k, top_scores, top_labels, top_query);
+    ins_select_kernel<<<B, 1024, smem, as_stream(stream)>>>(cls_logits, Q, NC, k, top_scores, top_labels, top_query);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_instance_select(const float* cls_logits, int Q, int NC, int k, float* top_scores,
+                                    int32_t* top_labels, int32_t* top_query, void* stream) {
+    return pvsg_instance_select_batched(cls_logits, 1, Q, NC, k, top_scores, top_labels, top_query, stream);
+}
+
+extern "C" int pvsg_instance_finalize_batched(const float* scores, const int32_t* labels, const int32_t* query,
+                                              const float* stats, const int32_t* boxes, int B, int n, int num_things,
+                                              int topk, float* boxes6, int32_t* out_labels, int32_t* sel_query,
+                                              int32_t* count, void* stream) {
+    PVSG_CHECK_ARG(scores && labels && query && stats && boxes && boxes6 && out_labels && sel_query && count);
+    PVSG_CHECK_ARG(B > 0 && n > 0 && n <= 1024 && topk > 0 && topk <= n && num_things >= 0);
+    ins_finalize_kernel<<<B, 128, 0, as_stream(stream)>>>(scores, labels, query, stats, boxes, n, num_things, topk,
+                                                          boxes6, out_labels, sel_query, count);
     return pvsg_launch_status();
 }
 
@@ -651,9 +746,6 @@ extern "C" int pvsg_instance_finalize(const float* scores, const int32_t* labels
                                       const float* stats, const int32_t* boxes, int n, int num_things, int topk,
                                       float* boxes6, int32_t* out_labels, int32_t* sel_query, int32_t* count,
                                       void* stream) {
-    PVSG_CHECK_ARG(scores && labels && query && stats && boxes && boxes6 && out_labels && sel_query && count);
-    PVSG_CHECK_ARG(n > 0 && n <= 1024 && topk > 0 && topk <= n && num_things >= 0);
-    ins_finalize_kernel<<<1, 128, 0, as_stream(stream)>>>(scores, labels, query, stats, boxes, n, num_things, topk,
-                                                          boxes6, out_labels, sel_query, count);
-    return pvsg_launch_status();
+    return pvsg_instance_finalize_batched(scores, labels, query, stats, boxes, 1, n, num_things, topk, boxes6,
+                                          out_labels, sel_query, count, stream);
 }

@@ -22,7 +22,7 @@ import torch
 
 from . import lib as _l
 from . import ops
-from .mask2former import bbox2result
+from .mask2former import INSTANCE_OFFSET, bbox2result
 
 RING = 3
 TOPK_INS = 10   # models/mask2former_vps/mask2former.py:192-195 keeps the 10 best instances
@@ -35,20 +35,19 @@ class _Pending:
         self.slot, self.event, self.n = slot, event, n
 
 
-def postprocess_frame(det, cls, mlr, in_hw, img_hw, out_hw):
-    """Static-shape device post-processing of one frame (CUDA-graph capturable): fused panoptic
-    map + segment table, and the detector's top-10 instances (models/mask2former_vps/mask2former.py:
-    183-201): statistics of all max_per_image candidates first, binary masks only for the survivors."""
+def postprocess_batch(det, cls, mask_lr, in_hw, img_hw, out_hw):
+    """Static-shape device post-processing of a batch of frames (CUDA-graph capturable), one launch
+    per kernel for the whole batch: fused panoptic map + segment table, and the detector's top-10
+    instances (models/mask2former_vps/mask2former.py:183-201): statistics of all max_per_image
+    candidates first, binary masks only for the survivors.  cls [B,Q,NC+1], mask_lr [B,Q,h,w]."""
     fh = det.panoptic_fusion_head
-    out = {}
-    if fh.test_cfg.get('panoptic_on', True):
-        out['pan'], out['seg_info'] = fh._panoptic(cls, mlr, in_hw, img_hw, out_hw)
-    if fh.test_cfg.get('instance_on', False):
-        d = fh._instance_device(cls, mlr, in_hw, img_hw, out_hw, False)
-        out['ins_boxes'], out['ins_labels'], sel, out['ins_count'] = ops.instance_finalize(
-            d['scores'], d['labels32'], d['query'], d['stats'], d['boxes'], det.num_things_classes, TOPK_INS)
-        out['ins_masks'] = ops.instance_masks(mlr, sel, in_hw, img_hw, out_hw, True)[2]
-    return out
+    cfg = fh.test_cfg
+    if not cfg.get('panoptic_on', True):
+        raise NotImplementedError('FrameRunner needs panoptic_on (the VPS test configuration)')
+    return ops.postprocess_batched(cls, mask_lr, in_hw, img_hw, out_hw, fh.num_things_classes, fh.num_classes,
+                                   float(cfg.get('object_mask_thr', 0.8)), float(cfg.get('iou_thr', 0.8)),
+                                   bool(cfg.get('filter_low_score', False)), INSTANCE_OFFSET,
+                                   bool(cfg.get('instance_on', False)), cfg.get('max_per_image', 100), TOPK_INS)
 
 
 class FrameRunner:
@@ -92,13 +91,9 @@ class FrameRunner:
         in_hw = tuple(meta['batch_input_shape'])
         img_hw = tuple(meta['img_shape'][:2])
         out_hw = tuple(meta['ori_shape'][:2]) if self.rescale else img_hw
-        outs = []
-        for b in range(B):
-            out = dict(query=query[:, b].contiguous())
-            out.update(postprocess_frame(det, cls[b], mask_lr[b, 0].contiguous(), in_hw, img_hw, out_hw))
-            outs.append(out)
-        # one [B, ...] tensor per output kind: 7 copies per batch instead of 7 per frame
-        return {k: torch.stack([o[k] for o in outs]) for k in outs[0]}
+        out = postprocess_batch(det, cls, mask_lr[:, 0].contiguous(), in_hw, img_hw, out_hw)
+        out['query'] = query.transpose(0, 1).contiguous()      # [B,Q,C]
+        return out
 
     def _capture(self):
         s = torch.cuda.Stream()

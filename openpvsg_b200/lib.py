@@ -55,6 +55,10 @@ SIGNATURES = {
     'pvsg_instance_masks': (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, P, P]),
     'pvsg_instance_select': (I, [P, I, I, I, P, P, P, P]),
     'pvsg_instance_finalize': (I, [P, P, P, P, P, I, I, I, P, P, P, P, P]),
+    'pvsg_panoptic_fuse_batched': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),
+    'pvsg_instance_select_batched': (I, [P, I, I, I, I, P, P, P, P]),
+    'pvsg_instance_masks_batched': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P]),
+    'pvsg_instance_finalize_batched': (I, [P, P, P, P, P, I, I, I, I, P, P, P, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
     'pvsg_pair_proposal': (I, [P, P, P, P, P, I, I, P]),
     'pvsg_top_pairs': (I, [P, I, I, P, P, P]),
@@ -100,7 +104,8 @@ def load():
 
 
 # kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)
-KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_groupnorm_nhwc_split': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3}
+KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_groupnorm_nhwc_split': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3,
+                    'pvsg_panoptic_fuse_batched': 4, 'pvsg_instance_masks_batched': 3}
 launch_count = [0]
 
 

@@ -703,6 +703,59 @@ def instance_finalize(scores, labels, query, stats, boxes, num_things, topk):
     return boxes6, out_labels, sel_query, count
 
 
+def postprocess_batched(cls_logits, mask_logits_lr, in_hw, img_hw, out_hw, num_things, num_classes, object_mask_thr,
+                        iou_thr, filter_low_score, instance_offset, instance_on, max_per_image, topk):
+    """Fused panoptic + instance post-processing of a BATCH of frames (static shapes, graph
+    capturable): cls_logits [B,Q,NC+1], mask_logits_lr [B,Q,h,w] -> dict of [B, ...] tensors
+    (pan int32 [B,H,W], seg_info int32 [B,1+4Q], and with instance_on: ins_boxes [B,topk,6],
+    ins_labels [B,topk], ins_count [B,1], ins_masks uint8 [B,topk,H,W])."""
+    lib = _l.load()
+    B, Q, C1 = _f32(cls_logits).shape
+    _, _, h, w = _f32(mask_logits_lr).shape
+    dev = cls_logits.device
+    cls_logits, mask_logits_lr = cls_logits.contiguous(), mask_logits_lr.contiguous()
+    H, W = out_hw
+    out = {}
+    pan = torch.empty(B, H, W, device=dev, dtype=torch.int32)
+    seg_info = torch.empty(B, 1 + 4 * Q, device=dev, dtype=torch.int32)
+    work = torch.empty(B, 4 * Q, device=dev, dtype=torch.int32)
+    scores = torch.empty(B, Q, device=dev, dtype=torch.float32)
+    pix = torch.empty(B, H * W, device=dev, dtype=torch.int16)
+    _l.check(lib.pvsg_panoptic_fuse_batched(_ptr(cls_logits), _ptr(mask_logits_lr), B, Q, num_classes, num_things, h, w,
+                                            in_hw[0], in_hw[1], img_hw[0], img_hw[1], H, W, object_mask_thr, iou_thr,
+                                            1 if filter_low_score else 0, instance_offset, _ptr(pan), _ptr(seg_info),
+                                            _ptr(work), _ptr(scores), _ptr(pix), _stream()),
+             'pvsg_panoptic_fuse_batched')
+    out['pan'], out['seg_info'] = pan, seg_info
+    if instance_on:
+        n = min(max_per_image, Q * num_classes)
+        topk = min(topk, n)
+        ts = torch.empty(B, n, device=dev, dtype=torch.float32)
+        tl = torch.empty(B, n, device=dev, dtype=torch.int32)
+        tq = torch.empty(B, n, device=dev, dtype=torch.int32)
+        _l.check(lib.pvsg_instance_select_batched(_ptr(cls_logits), B, Q, C1 - 1, n, _ptr(ts), _ptr(tl), _ptr(tq),
+                                                  _stream()), 'pvsg_instance_select_batched')
+        stats = torch.empty(B, n, 2, device=dev, dtype=torch.float32)
+        boxes = torch.empty(B, n, 4, device=dev, dtype=torch.int32)
+        geom = (h, w, in_hw[0], in_hw[1], img_hw[0], img_hw[1], H, W)
+        _l.check(lib.pvsg_instance_masks_batched(_ptr(mask_logits_lr), _ptr(tq), B, Q, n, *geom, _ptr(stats), _ptr(boxes),
+                                                 None, _stream()), 'pvsg_instance_masks_batched')
+        boxes6 = torch.empty(B, topk, 6, device=dev, dtype=torch.float32)
+        labels = torch.empty(B, topk, device=dev, dtype=torch.int32)
+        sel = torch.empty(B, topk, device=dev, dtype=torch.int32)
+        count = torch.empty(B, 1, device=dev, dtype=torch.int32)
+        _l.check(lib.pvsg_instance_finalize_batched(_ptr(ts), _ptr(tl), _ptr(tq), _ptr(stats), _ptr(boxes), B, n,
+                                                    num_things, topk, _ptr(boxes6), _ptr(labels), _ptr(sel),
+                                                    _ptr(count), _stream()), 'pvsg_instance_finalize_batched')
+        stats2 = torch.empty(B, topk, 2, device=dev, dtype=torch.float32)
+        boxes2 = torch.empty(B, topk, 4, device=dev, dtype=torch.int32)
+        masks = torch.empty(B, topk, H, W, device=dev, dtype=torch.uint8)
+        _l.check(lib.pvsg_instance_masks_batched(_ptr(mask_logits_lr), _ptr(sel), B, Q, topk, *geom, _ptr(stats2),
+                                                 _ptr(boxes2), _ptr(masks), _stream()), 'pvsg_instance_masks_batched')
+        out.update(ins_boxes=boxes6, ins_labels=labels, ins_count=count, ins_masks=masks)
+    return out
+
+
 def max_over_time(x):
     lib = _l.load()
     N, T, C = _f32(x).shape
