@@ -197,6 +197,17 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
                  :: "memory");
 }
 
+// (x0, x1) -> packed bf16 pairs hi = bf16(x), lo = bf16(x - hi).  The packed conversion
+// (cvt.rn.bf16x2.f32 = F2FP, ALU pipe) replaces four single F2F conversions, which issue on the
+// quarter-rate XU pipe and dominated the epilogue's instruction time.
+__device__ __forceinline__ void split_pair_packed(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);          // .x (low half) = x0
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -460,6 +471,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             tma_load_2d(&tmR, my_r, stage, (int)n, (int)(tl.m0 + q * 32));
                     }
                 }
+                // bias of this chunk: requested before the TMEM wait so the two latencies overlap
+                const bool full_chunk = n + 32 <= p.N;
+                const bool bias_vec = p.bias && full_chunk && ((n & 3) == 0);
+                float4 b4[8];
+                if (bias_vec) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+                }
                 float f[32];
                 tmem_ld32_wait(v);
 #pragma unroll
@@ -472,13 +491,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
-                const bool full_chunk = n + 32 <= p.N;
                 if (p.bias) {
-                    if (full_chunk && ((n & 3) == 0)) {
+                    if (bias_vec) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                            f[4 * j] += b4[j].x; f[4 * j + 1] += b4[j].y; f[4 * j + 2] += b4[j].z; f[4 * j + 3] += b4[j].w;
                         }
                     } else {
 #pragma unroll
@@ -563,14 +580,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         for (int j = 0; j < 4; ++j) {
                             uint32_t hw[4], lw[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float x0 = f[8 * j + 2 * e], x1 = f[8 * j + 2 * e + 1];
-                                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                            }
+                            for (int e = 0; e < 4; ++e) split_pair_packed(f[8 * j + 2 * e], f[8 * j + 2 * e + 1], hw[e], lw[e]);
                             if (tma_p) {
                                 // 64-byte rows, 16-byte pieces XOR-swizzled by ((row >> 1) & 3)
                                 const uint32_t off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
