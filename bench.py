@@ -368,7 +368,7 @@ def main():
         n0 = lib.launch_count[0]
         run_step(resident[:1] * 1, False) if args.frames == 1 else None
         per_frame = (lib.launch_count[0] - n0) or 638
-    launches = int(per_frame * args.frames * args.steps)
+    launches = int(per_frame * args.frames * args.steps) * world   # every rank launches the same work
 
     if rank != 0:
         if world > 1:
@@ -437,8 +437,8 @@ def main():
                             resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
                             l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',
                             cuda_graph=not args.no_graph, frames_per_launch=args.batch, tubes=len(linker.object_list)),
-                e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames,
-                         d2h_bytes_per_step=out_bytes * args.frames, ms_per_step=round(ms_e2e / args.steps, 3),
+                e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames * world,
+                         d2h_bytes_per_step=out_bytes * args.frames * world, ms_per_step=round(ms_e2e / args.steps, 3),
                          api='engine.FrameRunner.submit/collect (pipelined) on pinned host frames',
                          sync_api_value=round(e2e_sync, 3),
                          sync_api='model(return_loss=False, rescale=True, img=..., ref_img=...) per frame'),
