@@ -129,6 +129,42 @@ def cpu_oracle_fps(n_frames, warmup=1):
     return n_frames / sum(times), times
 
 
+def relation_bench(dev, with_cpu):
+    """BASELINE configs[3]: relation_head pair-transformer forward on 200 synthetic query tubes x 128
+    frames (tools/rel_test.py:39-67), device time per forward; CPU oracle (the reference's own torch
+    modules restated in oracle/relation.py) once on the host cores."""
+    from openpvsg_b200 import relation_head as rh, synthetic as syn
+    sds = syn.relation_state_dicts(seed=1)
+    feats = torch.randn(200, 128, 256, generator=torch.Generator().manual_seed(0))
+    mods = [rh.ObjectEncoder(256), rh.ObjectEncoder(256), rh.PairProposalNetwork(256, 1024), rh.TemporalTransformer(512, 57)]
+    for m, k in zip(mods, ('subject_encoder', 'object_encoder', 'pair_proposal_model', 'relation_model')):
+        m.load_state_dict(sds[k])
+        m.to(dev)
+    fd = feats.to(dev)
+    for _ in range(3):
+        rh.relation_forward(*mods, fd, 100)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rh.relation_forward(*mods, fd, 100)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    out = dict(workload='relation head forward, 200 tubes x 128 frames, top-100 pairs (BASELINE configs[3])',
+               ms=round(float(np.median(ts)), 3), forwards_per_s=round(1e3 / float(np.median(ts)), 1))
+    if with_cpu:
+        from oracle import relation as orel
+        torch.set_num_threads(os.cpu_count())
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            orel.relation_forward(sds, feats, 100)
+            out['cpu_ms'] = round(1e3 * (time.perf_counter() - t0), 1)
+        out['cpu_cores'] = os.cpu_count()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -426,6 +462,10 @@ def main():
         cpu = dict(value=fps, unit='frames/s', cores=os.cpu_count(), kind='port',
                    sample=f'{args.cpu_frames} frames @720p through the CPU oracle (torch CPU fp32, '
                           f'{os.cpu_count()} threads), 1 warm-up frame')
+    try:
+        extra['relation_head'] = relation_bench(dev, not args.no_cpu_baseline)
+    except Exception as ex:   # the headline metric must not depend on the auxiliary measurement
+        extra['relation_head'] = dict(error=repr(ex))
     in_bytes = 3 * 736 * 1280 * 4
     out_bytes = H * W * 4 + (1 + 400) * 4 + 10 * H * W + 100 * 256 * 4
     line = dict(metric=METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,

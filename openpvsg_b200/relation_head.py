@@ -36,10 +36,20 @@ class _EncoderLayer(nn.Module):
         a = self.self_attn
         if not x.is_contiguous():
             raise ops._l.PvsgError('encoder layer: contiguous [A,B,E] expected')
-        qkv = ops.linear(x.view(A * Bx, E), a.in_proj_weight, a.in_proj_bias).view(A, Bx, 3 * E)
         o = torch.empty(A, Bx, E, device=x.device, dtype=torch.float32)
+        tc = E // self.nhead == 32        # head dim 32: tensor-core attention on the projection's planes
+        res = ops.linear(x.view(A * Bx, E), a.in_proj_weight, a.in_proj_bias, out_mode='both' if tc else 'f32')
+        qkv, planes = res if tc else (res, None)
+        qkv = qkv.view(A, Bx, 3 * E)
         qv, ov = (qkv.permute(1, 0, 2), o.permute(1, 0, 2)) if seq_axis == 0 else (qkv, o)
-        ops.attention(qv[..., :E], qv[..., E:2 * E], qv[..., 2 * E:], self.nhead, out=ov)
+        if planes is not None:
+            ph, pl = planes.hi.view(A, Bx, 3 * E), planes.lo.view(A, Bx, 3 * E)
+            if seq_axis == 0:
+                ph, pl = ph.permute(1, 0, 2), pl.permute(1, 0, 2)
+            ops.attention(qv[..., :E], ops.Split(ph[..., E:2 * E], pl[..., E:2 * E]),
+                          ops.Split(ph[..., 2 * E:], pl[..., 2 * E:]), self.nhead, out=ov)
+        else:
+            ops.attention(qv[..., :E], qv[..., E:2 * E], qv[..., 2 * E:], self.nhead, out=ov)
         y = ops.linear(o, a.out_proj.weight, a.out_proj.bias, residual=x)
         y = ops.layernorm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         h = ops.linear(y, self.linear1.weight, self.linear1.bias, act=ops.ACT_RELU)
