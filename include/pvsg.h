@@ -213,12 +213,12 @@ int pvsg_attention(const float* Q, const float* K, const float* V, const uint8_t
                    int64_t v_bs, int64_t v_ts, int64_t o_bs, int64_t o_ts, float scale,
                    void* stream);
 
-/* Same contraction on the tensor cores for head dim 32 (the decoder's masked cross-attention,
- * mask2former_head.py:457-468): K and V are given as the split-bf16 operand planes their
- * projection emitted (element (b, i, h, d) at b*k_bs + i*k_ts + h*32 + d, strides in elements),
+/* Same contraction on the tensor cores for head dim 32 or 128 (the decoder's masked cross-attention,
+ * mask2former_head.py:457-468; the relation head's encoders, base.py:32-37, transformer.py:20-25): K and V are given as the split-bf16 operand planes their
+ * projection emitted (element (b, i, h, d) at b*k_bs + i*k_ts + h*D + d, strides in elements),
  * Q / out fp32 as above; every product is three m16n8k16 MMAs (fp32-grade).  Workspace:
  * pvsg_attention_tc_workspace_bytes. */
-int64_t pvsg_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk);
+int64_t pvsg_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int D);
 int pvsg_attention_tc(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi,
                       const void* V_lo, const uint8_t* mask, const int32_t* row_open, float* out,
                       void* ws, int B, int H, int Lq, int Lk, int D, int64_t q_bs, int64_t q_ts,
@@ -324,7 +324,7 @@ int pvsg_pair_proposal(const float* U, const float* V, const float* w2, const fl
 
 /* pick_top_pairs_eval (test_utils.py:4-22): diagonal -> -inf, the min(N*N, k) largest
  * entries in descending order (ties: lower flat index first); pairs int32 [k,2] = (s,o),
- * diagonal hits removed; n_out int32 [1]. N*N <= 65536*4. */
+ * diagonal hits removed; n_out int32 [1]. k <= 1024 (radix select + ranking in one CTA). */
 int pvsg_top_pairs(const float* pair, int N, int k, int32_t* pairs, int32_t* n_out, void* stream);
 
 /* concatenate_sub_obj (train_utils.py:67-81) + PositionalEncoding add (transformer.py:77-81):

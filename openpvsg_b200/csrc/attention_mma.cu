@@ -1,4 +1,4 @@
-// Masked cross-attention on the tensor cores, head dim 32, fp32-grade ("split-bf16").
+// Masked attention on the tensor cores, head dim 32 or 128, fp32-grade ("split-bf16").
 //
 //   out = softmax(scale * Q K^T + mask) V        per (batch, head)
 //
@@ -21,10 +21,10 @@
 
 namespace {
 
-constexpr int D = 32;
-constexpr int KT = 64;        // keys per tile
-constexpr int PITCH = 40;     // bf16 per shared-memory row (80 B): conflict-free ldmatrix
 constexpr int MAXWARP = 8;    // 128 queries per CTA
+// head dim D in {32, 128}; KT keys per tile (64 / 32); shared-memory rows of D + 8 bf16 (pitch = 16 B mod
+// 128 B: conflict-free ldmatrix)
+template <int D> struct Tile { static constexpr int KT = D == 32 ? 64 : 32; static constexpr int PITCH = D + 8; };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,8 +71,15 @@ struct AttnArgs {
     int nsplit, keys_per_split;
 };
 
+template <int D>
 __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
-    __shared__ __align__(16) __nv_bfloat16 tile[2][4][KT][PITCH];   // stage, plane (Khi Klo Vhi Vlo), key, dim
+    constexpr int KT = Tile<D>::KT, PITCH = Tile<D>::PITCH;
+    constexpr int NT = KT / 8;      // S n-tiles (8 keys each)
+    constexpr int KS = D / 16;      // k-steps of QK^T
+    constexpr int OT = D / 8;       // O n-tiles (8 dims each)
+    extern __shared__ __align__(16) uint8_t attn_smem[];
+    // [stage][plane (Khi Klo Vhi Vlo)][key][dim]
+    __nv_bfloat16 (*tile)[4][KT][PITCH] = reinterpret_cast<__nv_bfloat16 (*)[4][KT][PITCH]>(attn_smem);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -86,9 +93,9 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
     // ---- Q fragments (rows q0 + g, q0 + g + 8), scaled, split ----
     const int row[2] = {q0 + g, q0 + g + 8};
     const bool rvalid[2] = {row[0] < a.Lq, row[1] < a.Lq};
-    uint32_t qh[2][4], ql[2][4];
+    uint32_t qh[KS][4], ql[KS][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
+    for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int half = 0; half < 2; ++half)
 #pragma unroll
@@ -113,8 +120,8 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
                                      a.V_hi + b * a.v_bs + h * D, a.V_lo + b * a.v_bs + h * D};
     auto issue_tile = [&](int ti, int stage) {
         const int k0 = k_begin + ti * KT;
-        for (int c = threadIdx.x; c < KT * 4; c += blockDim.x) {
-            const int r = c >> 2, ch = c & 3;
+        for (int c = threadIdx.x; c < KT * (D / 8); c += blockDim.x) {
+            const int r = c / (D / 8), ch = c % (D / 8);
             const bool ok = k0 + r < k_end;
             const int64_t key = ok ? k0 + r : k_begin;
 #pragma unroll
@@ -126,9 +133,9 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    float o[4][4];
+    float o[OT][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < OT; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
@@ -144,9 +151,9 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         // mask bytes of this tile (independent of the shared-memory tile: issued before the barrier)
-        uint32_t mk[8][2];
+        uint32_t mk[NT][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int key = k0 + 8 * j + 2 * t;
@@ -159,27 +166,31 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
             }
         __syncthreads();
 
-        // ---- S = Q K^T (16 x 64 per warp) ----
-        float s[8][4];
+        // ---- S = Q K^T (16 x KT per warp) ----
+        float s[NT][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NT; ++j) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
-            uint32_t kh[4], kl[4];
-            const int r = 8 * j + (lane & 7), c = (lane >> 3) * 8;
-            ldsm4(kh, smem_addr(&tile[stage][0][r][c]));
-            ldsm4(kl, smem_addr(&tile[stage][1][r][c]));
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                mma16816(s[j], ql[ks], kh[2 * ks], kh[2 * ks + 1]);   // small terms first
-                mma16816(s[j], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
-                mma16816(s[j], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
+            for (int dq = 0; dq < D / 32; ++dq) {      // 32 dims (two k-steps) per ldmatrix.x4
+                uint32_t kh[4], kl[4];
+                const int r = 8 * j + (lane & 7), c = 32 * dq + (lane >> 3) * 8;
+                ldsm4(kh, smem_addr(&tile[stage][0][r][c]));
+                ldsm4(kl, smem_addr(&tile[stage][1][r][c]));
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const int ks = 2 * dq + k2;
+                    mma16816(s[j], ql[ks], kh[2 * k2], kh[2 * k2 + 1]);   // small terms first
+                    mma16816(s[j], qh[ks], kl[2 * k2], kl[2 * k2 + 1]);
+                    mma16816(s[j], qh[ks], kh[2 * k2], kh[2 * k2 + 1]);
+                }
             }
         }
         // ---- mask, online softmax ----
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int r = e >> 1;
@@ -200,12 +211,12 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
             l[r] *= corr[r];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < OT; ++i) {
             o[i][0] *= corr[0]; o[i][1] *= corr[0];
             o[i][2] *= corr[1]; o[i][3] *= corr[1];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float p = __expf(s[j][e] - mu[e >> 1]);
@@ -214,14 +225,14 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
             }
         // ---- O += P V ----
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < KT / 16; ++kk) {
             uint32_t ph[4], pl[4];
             split_pair(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
             split_pair(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
             split_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
             split_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
 #pragma unroll
-            for (int np = 0; np < 2; ++np) {
+            for (int np = 0; np < D / 16; ++np) {
                 uint32_t vh[4], vl[4];
                 const int mi = lane >> 3;
                 const int r = 16 * kk + (mi & 1) * 8 + (lane & 7), c = 16 * np + (mi >> 1) * 8;
@@ -249,13 +260,13 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
             const float inv = l[r] > 0.f ? 1.f / l[r] : 0.f;
             float* op = a.out + b * a.o_bs + (int64_t)row[r] * a.o_ts + h * D + 2 * t;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < OT; ++i)
                 *reinterpret_cast<float2*>(op + 8 * i) = make_float2(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
         } else {
             const int64_t prow = ((int64_t)bh * a.Lq + row[r]) * a.nsplit + split;
             float* op = a.part_o + prow * D + 2 * t;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(op + 8 * i) = make_float2(o[i][2 * r], o[i][2 * r + 1]);
+            for (int i = 0; i < OT; ++i) *reinterpret_cast<float2*>(op + 8 * i) = make_float2(o[i][2 * r], o[i][2 * r + 1]);
             if (t == 0) {
                 a.part_ml[prow * 2] = m[r];
                 a.part_ml[prow * 2 + 1] = l[r];
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(32 * MAXWARP) attn_mma_kernel(AttnArgs a) {
 __global__ void __launch_bounds__(256) attn_mma_combine_kernel(const float* __restrict__ part_o,
                                                                const float* __restrict__ part_ml,
                                                                float* __restrict__ out, int H, int Lq, int nsplit,
-                                                               int64_t o_bs, int64_t o_ts, int64_t total) {
+                                                               int64_t o_bs, int64_t o_ts, int64_t total, int D) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int d = (int)(i % D);
@@ -293,13 +304,27 @@ int pick_splits_tc(int B, int H, int qtiles, int Lk) {
     const int64_t base = (int64_t)B * H * qtiles;
     int ns = 1;
     // ~2 CTAs per SM, at least two 64-key tiles per split
-    while (base * ns < 296 && Lk / (ns * 2) >= 2 * KT && ns < 64) ns *= 2;
+    while (base * ns < 296 && Lk / (ns * 2) >= 2 * 64 && ns < 64) ns *= 2;
     return ns;
+}
+
+template <int D>
+int launch_attn(const AttnArgs& a, dim3 grid, int nwarp, cudaStream_t st) {
+    constexpr size_t smem = 2ull * 4 * Tile<D>::KT * Tile<D>::PITCH * sizeof(__nv_bfloat16);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return PVSG_ERR_LAUNCH;
+        configured = true;
+    }
+    attn_mma_kernel<D><<<grid, 32 * nwarp, smem, st>>>(a);
+    return PVSG_OK;
 }
 
 }  // namespace
 
-extern "C" int64_t pvsg_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk) {
+extern "C" int64_t pvsg_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int D) {
     const int qtiles = (Lq + 16 * MAXWARP - 1) / (16 * MAXWARP);
     const int ns = pick_splits_tc(B, H, qtiles, Lk);
     if (ns == 1) return 16;
@@ -312,7 +337,8 @@ extern "C" int pvsg_attention_tc(const float* Q, const void* K_hi, const void* K
                                  int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts, int64_t o_bs,
                                  int64_t o_ts, float scale, void* stream) {
     PVSG_CHECK_ARG(Q && K_hi && K_lo && V_hi && V_lo && out && B > 0 && H > 0 && Lq > 0 && Lk > 0);
-    if (Dh != D) return PVSG_ERR_UNSUPPORTED;
+    if (Dh != 32 && Dh != 128) return PVSG_ERR_UNSUPPORTED;
+    const int D = Dh;
     // 16-byte cp.async chunks of the planes, 8-byte loads / stores of Q and out
     PVSG_CHECK_ARG((k_bs | k_ts | v_bs | v_ts) % 8 == 0 && (q_bs | q_ts | o_bs | o_ts) % 2 == 0);
     PVSG_CHECK_ARG(((reinterpret_cast<uintptr_t>(K_hi) | reinterpret_cast<uintptr_t>(K_lo) |
@@ -323,7 +349,7 @@ extern "C" int pvsg_attention_tc(const float* Q, const void* K_hi, const void* K
     const int ns = pick_splits_tc(B, H, (Lq + 16 * MAXWARP - 1) / (16 * MAXWARP), Lk);
     PVSG_CHECK_ARG(ns == 1 || ws);
     int kps = (Lk + ns - 1) / ns;
-    kps = (kps + KT - 1) / KT * KT;
+    kps = (kps + 63) / 64 * 64;      // multiple of both tile sizes
     AttnArgs a;
     a.Q = Q;
     a.K_hi = reinterpret_cast<const __nv_bfloat16*>(K_hi); a.K_lo = reinterpret_cast<const __nv_bfloat16*>(K_lo);
@@ -337,11 +363,12 @@ extern "C" int pvsg_attention_tc(const float* Q, const void* K_hi, const void* K
     dim3 grid((unsigned)qtiles, (unsigned)ns, (unsigned)(B * H));
     PVSG_CHECK_ARG(grid.z <= 65535);
     cudaStream_t st = as_stream(stream);
-    attn_mma_kernel<<<grid, 32 * nwarp, 0, st>>>(a);
+    const int rc = D == 32 ? launch_attn<32>(a, grid, nwarp, st) : launch_attn<128>(a, grid, nwarp, st);
+    if (rc != PVSG_OK) return rc;
     if (ns > 1) {
         const int64_t total = (int64_t)B * H * Lq * D;
         attn_mma_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.part_o, a.part_ml, out, H, Lq, ns,
-                                                                                o_bs, o_ts, total);
+                                                                                o_bs, o_ts, total, D);
     }
     return pvsg_launch_status();
 }

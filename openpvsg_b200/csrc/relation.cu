@@ -43,74 +43,121 @@ __global__ void __launch_bounds__(256) pair_kernel(const float* __restrict__ U, 
     if (lane == 0) pair[wid] = s + __ldg(b2);
 }
 
-// Single CTA: iterative selection of the k largest entries (diagonal = -inf) in descending
-// order, ties -> lower flat index.
+// Single CTA: the k largest entries (diagonal = -inf) in descending order, ties -> lower flat index.
+// Radix select on order-preserving integer keys (4 passes of 8 bits) finds the k-th largest value,
+// the <= k survivors are compacted in index order into shared memory and ranked by counting.
+// (The first version re-scanned the whole matrix once per selected pair: 937 us for 200 x 200, k = 100.)
 constexpr int TP_THREADS = 1024;
-constexpr int TP_PER = 256;  // up to 1024*256 = 262144 entries
+constexpr int TP_MAXK = 1024;
+__device__ __forceinline__ unsigned tp_key(const float* __restrict__ pair, int e, int N) {
+    const int r = e / N, c = e - r * N;
+    const unsigned u = __float_as_uint((r == c) ? -INFINITY : __ldg(pair + e));
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);     // larger float <=> larger key
+}
 __global__ void __launch_bounds__(TP_THREADS) top_pairs_kernel(const float* __restrict__ pair, int N, int k,
                                                                int32_t* __restrict__ pairs, int32_t* __restrict__ n_out) {
-    __shared__ float sv[32];
-    __shared__ int si[32];
-    __shared__ int chosen;
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sel_prefix, sel_remaining, out_gt, out_eq;
+    __shared__ unsigned wc_gt[32], wc_eq[32];
+    __shared__ unsigned ckey[TP_MAXK];
+    __shared__ int cidx[TP_MAXK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int total = N * N;
     const int kk = min(k, total);
-    int count = 0;
-    // Bounded selection: at step `it` pick the largest (value, -index) strictly below the
-    // previously chosen one in the (value desc, index asc) order.  No scratch memory needed.
-    float pv = INFINITY;
-    int pi = -1;
-    for (int it = 0; it < kk; ++it) {
-        float bv = -INFINITY;
-        int bi = INT_MAX;
-        bool have = false;
-        for (int e = threadIdx.x; e < total; e += TP_THREADS) {
-            const int r = e / N, c = e % N;
-            const float v = (r == c) ? -INFINITY : __ldg(pair + e);
-            // strictly after (pv, pi) in the order: v < pv, or v == pv and e > pi
-            const bool after = (v < pv) || (v == pv && e > pi);
-            if (!after) continue;
-            if (!have || v > bv || (v == bv && e < bi)) { bv = v; bi = e; have = true; }
+    if (threadIdx.x == 0) { sel_prefix = 0; sel_remaining = (unsigned)kk; out_gt = 0; out_eq = 0; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = sel_prefix;
+        const unsigned pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int base = 0; base < total; base += blockDim.x) {
+            const int e = base + threadIdx.x;
+            const unsigned u = e < total ? tp_key(pair, e, N) : 0u;
+            const bool in = e < total && (u & pmask) == prefix;
+            const unsigned bin = in ? ((u >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (in && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
         }
-        // warp reduce (value desc, index asc); lanes without a candidate carry bi = INT_MAX
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned rem0 = sel_remaining;
+            unsigned mine[8], tot = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi != INT_MAX && (bi == INT_MAX || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-        }
-        if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            bv = sv[threadIdx.x];
-            bi = si[threadIdx.x];
+            for (int e = 0; e < 8; ++e) { mine[e] = hist[255 - 8 * lane - e]; tot += mine[e]; }
+            unsigned incl = tot;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oi != INT_MAX && (bi == INT_MAX || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            if (threadIdx.x == 0) {
-                chosen = bi;
-                sv[0] = bv;
+            const unsigned excl = incl - tot;
+            if (excl < rem0 && rem0 <= incl) {
+                unsigned rem = rem0 - excl;
+                int b = 255 - 8 * lane;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (mine[e] >= rem) { b = 255 - 8 * lane - e; break; }
+                    rem -= mine[e];
+                }
+                sel_prefix = prefix | ((unsigned)b << shift);
+                sel_remaining = rem;
             }
         }
         __syncthreads();
-        const int ci = chosen;
-        const float cv = sv[0];
+    }
+    const unsigned thr = sel_prefix;
+    const unsigned n_eq = sel_remaining;
+    // survivors -> shared memory, in flat-index order
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int e = base + threadIdx.x;
+        const unsigned u = e < total ? tp_key(pair, e, N) : 0u;
+        const bool gt = e < total && u > thr, eq = e < total && u == thr;
+        const unsigned bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) { wc_gt[warp] = __popc(bg); wc_eq[warp] = __popc(be); }
         __syncthreads();
-        if (ci == INT_MAX) break;
-        pv = cv;
-        pi = ci;
-        const int r = ci / N, c = ci % N;
-        if (r != c) {  // diagonal entries (value -inf) are dropped like the reference's filter
-            if (threadIdx.x == 0) {
-                pairs[2 * count] = r;
-                pairs[2 * count + 1] = c;
+        unsigned og = out_gt, oe = out_eq;
+        for (int w = 0; w < warp; ++w) { og += wc_gt[w]; oe += wc_eq[w]; }
+        const unsigned lower = (1u << lane) - 1u;
+        if (gt) {
+            const unsigned slot = og + __popc(bg & lower);
+            ckey[slot] = u; cidx[slot] = e;
+        } else if (eq) {
+            const unsigned r = oe + __popc(be & lower);
+            if (r < n_eq) {
+                const unsigned slot = (unsigned)kk - n_eq + r;
+                ckey[slot] = u; cidx[slot] = e;
             }
-            ++count;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tg = 0, te = 0;
+            for (int w = 0; w < nwarp; ++w) { tg += wc_gt[w]; te += wc_eq[w]; }
+            out_gt += tg; out_eq += te;
+        }
+        __syncthreads();
+    }
+    // rank by counting: (value desc, index asc); diagonal entries (-inf) rank last and are dropped
+    int local_valid = 0;
+    for (int i = threadIdx.x; i < kk; i += blockDim.x) {
+        const unsigned ki = ckey[i];
+        const int ei = cidx[i];
+        int rank = 0;
+        for (int j = 0; j < kk; ++j) rank += (ckey[j] > ki || (ckey[j] == ki && cidx[j] < ei)) ? 1 : 0;
+        const int r = ei / N, c = ei - r * N;
+        if (r != c) {
+            pairs[2 * rank] = r;
+            pairs[2 * rank + 1] = c;
+            ++local_valid;
         }
     }
-    if (threadIdx.x == 0) *n_out = count;
+    __syncthreads();
+    if (threadIdx.x == 0) { out_gt = 0; }
+    __syncthreads();
+    if (local_valid) atomicAdd(&out_gt, (unsigned)local_valid);
+    __syncthreads();
+    if (threadIdx.x == 0) n_out[0] = (int)out_gt;
 }
 
 __global__ void __launch_bounds__(256) gather_pairs_kernel(const float* __restrict__ sub, const float* __restrict__ obj,
@@ -154,7 +201,7 @@ extern "C" int pvsg_pair_proposal(const float* U, const float* V, const float* w
 
 extern "C" int pvsg_top_pairs(const float* pair, int N, int k, int32_t* pairs, int32_t* n_out, void* stream) {
     PVSG_CHECK_ARG(pair && pairs && n_out && N > 0 && k > 0);
-    if ((int64_t)N * N > (int64_t)TP_THREADS * TP_PER) return PVSG_ERR_UNSUPPORTED;
+    if ((int64_t)N * N > (1LL << 30) || k > TP_MAXK) return PVSG_ERR_UNSUPPORTED;
     top_pairs_kernel<<<1, TP_THREADS, 0, as_stream(stream)>>>(pair, N, k, pairs, n_out);
     return pvsg_launch_status();
 }

@@ -48,7 +48,7 @@ SIGNATURES = {
     'pvsg_msda_fused_forward_split': (I, [P, P, P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
     'pvsg_attention_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_attention': (I, [P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
-    'pvsg_attention_tc_workspace_bytes': (L, [I, I, I, I]),
+    'pvsg_attention_tc_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_attention_tc': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_mask_logits': (I, [P, P, P, P, P, I, I, L, I, P]),
     'pvsg_panoptic_fuse': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),

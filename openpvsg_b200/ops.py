@@ -556,8 +556,8 @@ def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None
         B, Lq, E = q.shape
         Lk = k.shape[1]
         D = E // num_heads
-        if D != 32 or q.stride(2) != 1 or tuple(k.shape) != (B, Lk, E) or tuple(v.shape) != (B, Lk, E):
-            raise _l.PvsgError('attention: plane inputs need head dim 32 and [B,Lk,E] planes')
+        if D not in (32, 128) or q.stride(2) != 1 or tuple(k.shape) != (B, Lk, E) or tuple(v.shape) != (B, Lk, E):
+            raise _l.PvsgError('attention: plane inputs need head dim 32 / 128 and [B,Lk,E] planes')
         for t in (k.hi, k.lo, v.hi, v.lo):
             if t.stride(2) != 1:
                 raise _l.PvsgError('attention: planes need unit inner stride')
@@ -572,7 +572,8 @@ def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None
             raise _l.PvsgError('attention: row_open must be contiguous int32')
         if (k.hi.stride() != k.lo.stride()) or (v.hi.stride() != v.lo.stride()):
             raise _l.PvsgError('attention: hi / lo planes must share their layout')
-        ws = torch.empty(lib.pvsg_attention_tc_workspace_bytes(B, num_heads, Lq, Lk), device=q.device, dtype=torch.uint8)
+        ws = torch.empty(lib.pvsg_attention_tc_workspace_bytes(B, num_heads, Lq, Lk, D), device=q.device,
+                         dtype=torch.uint8)
         _l.check(lib.pvsg_attention_tc(_ptr(q), _ptr(k.hi), _ptr(k.lo), _ptr(v.hi), _ptr(v.lo), _ptr(mask),
                                        _ptr(row_open), _ptr(out), _ptr(ws), B, num_heads, Lq, Lk, D, q.stride(0),
                                        q.stride(1), k.hi.stride(0), k.hi.stride(1), v.hi.stride(0), v.hi.stride(1),

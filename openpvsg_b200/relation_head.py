@@ -37,7 +37,7 @@ class _EncoderLayer(nn.Module):
         if not x.is_contiguous():
             raise ops._l.PvsgError('encoder layer: contiguous [A,B,E] expected')
         o = torch.empty(A, Bx, E, device=x.device, dtype=torch.float32)
-        tc = E // self.nhead == 32        # head dim 32: tensor-core attention on the projection's planes
+        tc = E // self.nhead in (32, 128)  # tensor-core attention on the projection's planes
         res = ops.linear(x.view(A * Bx, E), a.in_proj_weight, a.in_proj_bias, out_mode='both' if tc else 'f32')
         qkv, planes = res if tc else (res, None)
         qkv = qkv.view(A, Bx, 3 * E)

@@ -237,6 +237,43 @@ def test_attention_tensor_core_planes(ops, B, Lq, Lk):
     close(out, out2.cpu(), 2e-4, 'tensor-core vs SIMT attention')
 
 
+@pytest.mark.parametrize('B,H,Lq,Lk,E', [(5, 4, 128, 128, 512), (2, 4, 50, 77, 512), (3, 8, 200, 200, 256)])
+def test_attention_tensor_core_relation_shapes(ops, B, H, Lq, Lk, E):
+    """Head dim 128 (TemporalTransformer, transformer.py:20-25) and the ObjectEncoder shape, K / V as
+    strided slices of a fused qkv plane buffer (the relation head's layout)."""
+    g = torch.Generator().manual_seed(B * 100 + Lk)
+    qkv = torch.randn(B, max(Lq, Lk), 3 * E, generator=g)
+    q, k, v = qkv[:, :Lq, :E], qkv[:, :Lk, E:2 * E], qkv[:, :Lk, 2 * E:]
+    ref = _mha_ref(q.contiguous(), k.contiguous(), v.contiguous(), H)
+    dev = qkv.cuda()
+    hi, lo = ops.split_bf16(dev)
+    out = ops.attention(dev[:, :Lq, :E], ops.Split(hi[:, :Lk, E:2 * E], lo[:, :Lk, E:2 * E]),
+                        ops.Split(hi[:, :Lk, 2 * E:], lo[:, :Lk, 2 * E:]), H)
+    close(out, ref, 2e-4, 'tensor-core attention, strided planes')
+
+
+def test_top_pairs_matches_torch_topk(ops):
+    """pick_top_pairs_eval (test_utils.py:4-22): radix-select kernel vs torch.topk(sorted=True), with
+    exact ties, negative scores and k larger than the number of off-diagonal entries."""
+    g = torch.Generator().manual_seed(3)
+    for N, k in ((200, 100), (7, 100), (33, 1)):
+        m = torch.randn(N, N, generator=g)
+        m[1, 2] = m[3, 4] = m[5, 6] = 9.0            # ties at the top: lower flat index first
+        pairs, n = ops.top_pairs(m.cuda(), k)
+        n = int(n.item())
+        mm = m.clone()
+        mm.fill_diagonal_(float('-inf'))
+        kk = min(k, N * N)
+        vals, idx = mm.flatten().topk(kk, sorted=True)
+        keep = ~torch.isinf(vals)
+        assert n == int(keep.sum())
+        got = pairs[:n].cpu()
+        got_vals = mm[got[:, 0].long(), got[:, 1].long()]
+        assert torch.equal(got_vals, vals[keep])      # same scores in the same (descending) order
+        ties = got[(got_vals == 9.0)]
+        assert ties.tolist() == [[1, 2], [3, 4], [5, 6]]
+
+
 def test_attention_masked_and_strided(ops):
     B, H, Lq, Lk, E = 1, 8, 100, 3680, 256
     q, k, v = randn(1, B, Lq, E), randn(2, B, Lk, E), randn(3, B, Lk, E)
