@@ -271,7 +271,7 @@ def test_top_pairs_matches_torch_topk(ops):
         got_vals = mm[got[:, 0].long(), got[:, 1].long()]
         assert torch.equal(got_vals, vals[keep])      # same scores in the same (descending) order
         ties = got[(got_vals == 9.0)]
-        assert ties.tolist() == [[1, 2], [3, 4], [5, 6]]
+        assert ties.tolist() == [[1, 2], [3, 4], [5, 6]][:min(3, n)]
 
 
 def test_attention_masked_and_strided(ops):
