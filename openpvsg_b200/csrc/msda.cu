@@ -188,35 +188,43 @@ __global__ void __launch_bounds__(256, 4) msda_kernel(const float* __restrict__ 
 //     width-8 shuffles; there is no cross-group reduction at the end.
 // Shuffles per item: 12 x 5 + 6 (softmax) over FOUR items per instruction, i.e. ~16 per item
 // instead of 42.
-__device__ __forceinline__ void sample_prep_packed(int hgt, int wid, int start, float x, float y, float aw,
-                                                   uint32_t& pk, float (&w)[4]) {
+// Sample preparation with FIXED corner offsets: the four corners are always the pixels
+// (yb, xb), (yb, xb+1), (yb+1, xb), (yb+1, xb+1) with xb = clamp(x0, 0, wid-2), yb likewise, so
+// their addresses are base + {0, S, R, R+S} for strides that are uniform per level -- no per-corner
+// index arithmetic.  Zero padding and the clamp are folded into the weights: a corner that the
+// bilinear footprint does not touch (outside the map, or shifted by the clamp) gets weight 0.
+// Needs wid, hgt >= 2.
+__device__ __forceinline__ void sample_prep_fixed(int hgt, int wid, int start, float x, float y, float aw,
+                                                  int& base, float (&w)[4]) {
     x = fminf(fmaxf(x, -2.f), (float)wid + 1.f);
     y = fminf(fmaxf(y, -2.f), (float)hgt + 1.f);
     const float fy = floorf(y), fx = floorf(x);
     const int y0 = (int)fy, x0 = (int)fx;
     const float ly = y - fy, lx = x - fx;
     const float hy = 1.f - ly, hx = 1.f - lx;
-    const bool y0v = y0 >= 0 && y0 < hgt, y1v = y0 + 1 >= 0 && y0 + 1 < hgt;
-    const bool x0v = x0 >= 0 && x0 < wid, x1v = x0 + 1 >= 0 && x0 + 1 < wid;
-    const int yc0 = min(max(y0, 0), hgt - 1), yc1 = min(max(y0 + 1, 0), hgt - 1);
-    const int xc0 = min(max(x0, 0), wid - 1), xc1 = min(max(x0 + 1, 0), wid - 1);
-    // corner (cy, cx) = base + cy * dy * wid + cx * dx with dx, dy in {0, 1} (0 where the clamp folds
-    // the two corners onto one pixel; that corner then carries weight 0 anyway)
-    pk = (uint32_t)(start + yc0 * wid + xc0) | ((uint32_t)(xc1 - xc0) << 30) | ((uint32_t)(yc1 - yc0) << 31);
-    w[0] = (y0v && x0v) ? hy * hx * aw : 0.f; w[1] = (y0v && x1v) ? hy * lx * aw : 0.f;
-    w[2] = (y1v && x0v) ? ly * hx * aw : 0.f; w[3] = (y1v && x1v) ? ly * lx * aw : 0.f;
+    const int xb = min(max(x0, 0), wid - 2), yb = min(max(y0, 0), hgt - 2);
+    const float wxa = (x0 == xb) ? hx : ((x0 + 1 == xb) ? lx : 0.f);
+    const float wxb = (x0 == xb) ? lx : ((x0 == xb + 1) ? hx : 0.f);
+    const float wya = (y0 == yb) ? hy : ((y0 + 1 == yb) ? ly : 0.f);
+    const float wyb = (y0 == yb) ? ly : ((y0 == yb + 1) ? hy : 0.f);
+    base = start + yb * wid + xb;
+    w[0] = wya * wxa * aw; w[1] = wya * wxb * aw;
+    w[2] = wyb * wxa * aw; w[3] = wyb * wxb * aw;
 }
 
-template <bool TILED>
+// LPC / PC: compile-time L*P and P (12 / 4 in the reference configuration) so that the sample loop
+// is fully unrolled (owner lane, register slot and level of every sample are constants); 0 = runtime.
+template <bool TILED, int LPC, int PC>
 __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restrict__ value, MsdaLevels lv,
                                                             const float* __restrict__ proj,
                                                             const float* __restrict__ ref, float* __restrict__ out,
-                                                            int64_t N, int64_t Nq, int H, int L, int P,
+                                                            int64_t N, int64_t Nq, int H, int L, int P_rt,
                                                             int64_t total, uint2* __restrict__ out_hi = nullptr,
                                                             uint2* __restrict__ out_lo = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, j = lane & 7;
-    const int LP = L * P;
+    const int P = PC > 0 ? PC : P_rt;
+    const int LP = LPC > 0 ? LPC : L * P;
     const int pix_stride = H * 8;   // float4 per pixel
     // TILED: CTA = 8 x 8 query tile of one level and head, warp = one row, two passes of 4 queries.
     // otherwise: CTA = 32 consecutive queries of one head, warp = 4 of them.
@@ -263,41 +271,37 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
             for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             const float inv = 1.f / sum;
             const float2 rf = __ldg(reinterpret_cast<const float2*>(ref) + nq);
-            uint32_t pk0, pk1;
+            int base0, base1;
             float w0[4], w1[4];
             {
                 const float2 o = has0 ? __ldg(offp + j) : make_float2(0.f, 0.f);
                 const int l = min(j, LP - 1) / P;
                 const int hgt = lv.h[l], wid = lv.w[l];
                 // loc = ref + off / (w, h); pixel = loc * size - 0.5 = ref * size + off - 0.5
-                sample_prep_packed(hgt, wid, (int)lv.start[l], fmaf(rf.x, (float)wid, o.x) - 0.5f,
-                                   fmaf(rf.y, (float)hgt, o.y) - 0.5f, e0 * inv, pk0, w0);
+                sample_prep_fixed(hgt, wid, (int)lv.start[l], fmaf(rf.x, (float)wid, o.x) - 0.5f,
+                                  fmaf(rf.y, (float)hgt, o.y) - 0.5f, e0 * inv, base0, w0);
             }
             {
                 const float2 o = has1 ? __ldg(offp + j + 8) : make_float2(0.f, 0.f);
                 const int l = min(j + 8, LP - 1) / P;
                 const int hgt = lv.h[l], wid = lv.w[l];
-                sample_prep_packed(hgt, wid, (int)lv.start[l], fmaf(rf.x, (float)wid, o.x) - 0.5f,
-                                   fmaf(rf.y, (float)hgt, o.y) - 0.5f, e1 * inv, pk1, w1);
+                sample_prep_fixed(hgt, wid, (int)lv.start[l], fmaf(rf.x, (float)wid, o.x) - 0.5f,
+                                  fmaf(rf.y, (float)hgt, o.y) - 0.5f, e1 * inv, base1, w1);
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int l = 0, pcount = 0;
-#pragma unroll 2
-            for (int s = 0; s < LP; ++s) {
-                const int wid = lv.w[l];
-                if (++pcount == P) { pcount = 0; ++l; }
-                const bool second = s >= 8;      // uniform
+            auto one_sample = [&](int s, int l) {
+                const int rowstride = lv.w[l] * pix_stride;      // uniform per level
+                const bool second = s >= 8;                      // uniform (compile-time when unrolled)
                 const int src = s & 7;
-                const uint32_t pk = __shfl_sync(0xffffffffu, second ? pk1 : pk0, src, 8);
+                const int base = __shfl_sync(0xffffffffu, second ? base1 : base0, src, 8);
                 float w[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) w[c] = __shfl_sync(0xffffffffu, second ? w1[c] : w0[c], src, 8);
-                const int base = (int)(pk & 0x3fffffffu);
-                const int dx = (int)((pk >> 30) & 1u), dyw = (pk >> 31) ? wid : 0;
-                const float4 v00 = __ldg(vb + base * pix_stride);
-                const float4 v01 = __ldg(vb + (base + dx) * pix_stride);
-                const float4 v10 = __ldg(vb + (base + dyw) * pix_stride);
-                const float4 v11 = __ldg(vb + (base + dyw + dx) * pix_stride);
+                const float4* p00 = vb + (int64_t)base * pix_stride;
+                const float4 v00 = __ldg(p00);
+                const float4 v01 = __ldg(p00 + pix_stride);
+                const float4 v10 = __ldg(p00 + rowstride);
+                const float4 v11 = __ldg(p00 + rowstride + pix_stride);
                 acc.x = fmaf(w[0], v00.x, acc.x); acc.y = fmaf(w[0], v00.y, acc.y);
                 acc.z = fmaf(w[0], v00.z, acc.z); acc.w = fmaf(w[0], v00.w, acc.w);
                 acc.x = fmaf(w[1], v01.x, acc.x); acc.y = fmaf(w[1], v01.y, acc.y);
@@ -306,6 +310,17 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
                 acc.z = fmaf(w[2], v10.z, acc.z); acc.w = fmaf(w[2], v10.w, acc.w);
                 acc.x = fmaf(w[3], v11.x, acc.x); acc.y = fmaf(w[3], v11.y, acc.y);
                 acc.z = fmaf(w[3], v11.z, acc.z); acc.w = fmaf(w[3], v11.w, acc.w);
+            };
+            if (LPC > 0) {
+#pragma unroll
+                for (int s = 0; s < (LPC > 0 ? LPC : 1); ++s) one_sample(s, s / (PC > 0 ? PC : 1));
+            } else {
+                int l = 0, pcount = 0;
+#pragma unroll 2
+                for (int s = 0; s < LP; ++s) {
+                    one_sample(s, l);
+                    if (++pcount == P) { pcount = 0; ++l; }
+                }
             }
             if (valid) {
                 const int64_t oi = ((b * Nq + nq) * H + head) * 8 + j;
@@ -358,17 +373,30 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
     int rc = fill_levels(lv, spatial_shapes, level_start_index, L, N);
     if (rc != PVSG_OK) return rc;
     const int wpb = 8;
-    if (FUSED && L * P <= 16 && N < (1LL << 30)) {
+    bool wide = true;   // the fixed-corner kernel needs every level to be at least 2 x 2
+    for (int l = 0; l < L; ++l) wide = wide && lv.h[l] >= 2 && lv.w[l] >= 2;
+    if (FUSED && L * P <= 16 && N < (1LL << 30) && wide) {
+        uint2* oh = reinterpret_cast<uint2*>(out_hi);
+        uint2* ol = reinterpret_cast<uint2*>(out_lo);
+        const bool ref_cfg = L == 3 && P == 4;     // fully unrolled instance
         if (Nq == N) {
             const int64_t total = (int64_t)B * H * lv.tile_start[L];
-            msda_group_kernel<true><<<(unsigned)imin64(total, 148 * 64), 256, 0, as_stream(stream)>>>(
-                value, lv, a, b2, out, N, Nq, H, L, P, total, reinterpret_cast<uint2*>(out_hi),
-                reinterpret_cast<uint2*>(out_lo));
+            const unsigned grid = (unsigned)imin64(total, 148 * 64);
+            if (ref_cfg)
+                msda_group_kernel<true, 12, 4><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                                                                                  total, oh, ol);
+            else
+                msda_group_kernel<true, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                                                                                 total, oh, ol);
         } else {
             const int64_t total = (int64_t)B * H * ((Nq + 31) / 32);
-            msda_group_kernel<false><<<(unsigned)imin64(total, 148 * 64), 256, 0, as_stream(stream)>>>(
-                value, lv, a, b2, out, N, Nq, H, L, P, total, reinterpret_cast<uint2*>(out_hi),
-                reinterpret_cast<uint2*>(out_lo));
+            const unsigned grid = (unsigned)imin64(total, 148 * 64);
+            if (ref_cfg)
+                msda_group_kernel<false, 12, 4><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                                                                                   total, oh, ol);
+            else
+                msda_group_kernel<false, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                                                                                  total, oh, ol);
         }
         return pvsg_launch_status();
     }
