@@ -212,9 +212,10 @@ __device__ __forceinline__ void sample_prep_fixed(int hgt, int wid, int start, f
     w[2] = wyb * wxa * aw; w[3] = wyb * wxb * aw;
 }
 
-// LPC / PC: compile-time L*P and P (12 / 4 in the reference configuration) so that the sample loop
-// is fully unrolled (owner lane, register slot and level of every sample are constants); 0 = runtime.
-template <bool TILED, int LPC, int PC>
+// LPC / PC / HC: compile-time L*P, P and head count (12 / 4 / 8 in the reference configuration) so
+// that the sample loop is fully unrolled (owner lane, register slot and level of every sample are
+// constants) and the pixel stride is an immediate address offset; 0 = runtime.
+template <bool TILED, int LPC, int PC, int HC>
 __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restrict__ value, MsdaLevels lv,
                                                             const float* __restrict__ proj,
                                                             const float* __restrict__ ref, float* __restrict__ out,
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
     const int g = lane >> 3, j = lane & 7;
     const int P = PC > 0 ? PC : P_rt;
     const int LP = LPC > 0 ? LPC : L * P;
-    const int pix_stride = H * 8;   // float4 per pixel
+    const int pix_stride = HC > 0 ? HC * 8 : H * 8;   // float4 per pixel
     // TILED: CTA = 8 x 8 query tile of one level and head, warp = one row, two passes of 4 queries.
     // otherwise: CTA = 32 consecutive queries of one head, warp = 4 of them.
     const int64_t qblocks = TILED ? lv.tile_start[L] : (Nq + 31) / 32;
@@ -298,10 +299,11 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
 #pragma unroll
                 for (int c = 0; c < 4; ++c) w[c] = __shfl_sync(0xffffffffu, second ? w1[c] : w0[c], src, 8);
                 const float4* p00 = vb + (int64_t)base * pix_stride;
+                const float4* p10 = p00 + rowstride;
                 const float4 v00 = __ldg(p00);
-                const float4 v01 = __ldg(p00 + pix_stride);
-                const float4 v10 = __ldg(p00 + rowstride);
-                const float4 v11 = __ldg(p00 + rowstride + pix_stride);
+                const float4 v01 = __ldg(p00 + pix_stride);     // immediate offset when HC is set
+                const float4 v10 = __ldg(p10);
+                const float4 v11 = __ldg(p10 + pix_stride);
                 acc.x = fmaf(w[0], v00.x, acc.x); acc.y = fmaf(w[0], v00.y, acc.y);
                 acc.z = fmaf(w[0], v00.z, acc.z); acc.w = fmaf(w[0], v00.w, acc.w);
                 acc.x = fmaf(w[1], v01.x, acc.x); acc.y = fmaf(w[1], v01.y, acc.y);
@@ -378,24 +380,24 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
     if (FUSED && L * P <= 16 && N < (1LL << 30) && wide) {
         uint2* oh = reinterpret_cast<uint2*>(out_hi);
         uint2* ol = reinterpret_cast<uint2*>(out_lo);
-        const bool ref_cfg = L == 3 && P == 4;     // fully unrolled instance
+        const bool ref_cfg = L == 3 && P == 4 && H == 8;     // fully unrolled instance
         if (Nq == N) {
             const int64_t total = (int64_t)B * H * lv.tile_start[L];
             const unsigned grid = (unsigned)imin64(total, 148 * 64);
             if (ref_cfg)
-                msda_group_kernel<true, 12, 4><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                msda_group_kernel<true, 12, 4, 8><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
                                                                                   total, oh, ol);
             else
-                msda_group_kernel<true, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                msda_group_kernel<true, 0, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
                                                                                  total, oh, ol);
         } else {
             const int64_t total = (int64_t)B * H * ((Nq + 31) / 32);
             const unsigned grid = (unsigned)imin64(total, 148 * 64);
             if (ref_cfg)
-                msda_group_kernel<false, 12, 4><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                msda_group_kernel<false, 12, 4, 8><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
                                                                                    total, oh, ol);
             else
-                msda_group_kernel<false, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
+                msda_group_kernel<false, 0, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(value, lv, a, b2, out, N, Nq, H, L, P,
                                                                                   total, oh, ol);
         }
         return pvsg_launch_status();
