@@ -165,6 +165,30 @@ def relation_bench(dev, with_cpu):
     return out
 
 
+def tube_dump_bench(det, meta, frames, batch):
+    """masks.txt rows of a batch of frames -- device run-length events
+    (pvsg_rle_events + tubes.rle_from_events) vs the host encoder working on the panoptic map
+    (what concat_seq does with pycocotools in the reference)."""
+    from openpvsg_b200 import engine, tubes
+    runner = engine.get_runner(det, meta, True, batch=batch, rle=True)
+    res = runner.collect(runner.submit(frames[:batch]))
+    t0 = time.perf_counter()
+    dev_rows = 0
+    for r in runner.collect(runner.submit(frames[:batch])):    # collect() builds the strings from the events
+        dev_rows += len(r['rle'])
+    t_dev = (time.perf_counter() - t0) / batch
+    t0 = time.perf_counter()
+    host_rows = 0
+    for r in res:
+        for sid in r['query_feats']:
+            tubes.rle_string(tubes.rle_counts(r['pan_results'] == sid))
+            host_rows += 1
+    t_host = (time.perf_counter() - t0) / batch
+    return dict(workload='masks.txt RLE rows per 720p frame (tube wire format)', segments_per_frame=round(host_rows / batch, 1),
+                device_events_ms_per_frame=round(1e3 * t_dev, 2), host_encoder_ms_per_frame=round(1e3 * t_host, 2),
+                note='device figure = whole submit+collect of a batch incl. the network forward')
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -466,6 +490,11 @@ def main():
         extra['relation_head'] = relation_bench(dev, not args.no_cpu_baseline)
     except Exception as ex:   # the headline metric must not depend on the auxiliary measurement
         extra['relation_head'] = dict(error=repr(ex))
+    try:
+        if det._runners is not None:
+            extra['tube_dump'] = tube_dump_bench(det, meta, resident, args.batch)
+    except Exception as ex:
+        extra['tube_dump'] = dict(error=repr(ex))
     in_bytes = 3 * 736 * 1280 * 4
     out_bytes = H * W * 4 + (1 + 400) * 4 + 10 * H * W + 100 * 256 * 4
     line = dict(metric=METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,

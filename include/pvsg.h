@@ -311,6 +311,18 @@ int pvsg_instance_finalize_batched(const float* scores, const int32_t* labels, c
                                    int num_things, int topk, float* boxes6, int32_t* out_labels,
                                    int32_t* sel_query, int32_t* count, void* stream);
 
+/* Run-length events of the kept segments of B panoptic maps for the tube wire format (reference:
+ * concat_seq, models/mask2former_vps/utils.py:38-54, pycocotools RLE of `pan == id`, masks.txt rows of
+ * models/unitrack/utils/io.py:14-37).  pan int32 [B,H,W]; seg_info [B,1+4Q] as written by
+ * pvsg_panoptic_fuse (segment slot = order of first appearance of a segment id among the kept
+ * rows).  Outputs per frame, in COLUMN-major walk order: ev_pos uint32 [B,cap] (position x*H + y
+ * where a run of the segment starts or ends), ev_slot int16 [B,cap], n_events int32 [B] (may
+ * exceed cap: the caller then falls back to the map).  RLE counts of a segment = differences of
+ * its positions, with 0 prepended and H*W appended.  col_ws: int32 workspace [2,B,W]. */
+int pvsg_rle_events(const int32_t* pan, const int32_t* seg_info, int B, int Q, int H, int W,
+                    int32_t* col_ws, uint32_t* ev_pos, int16_t* ev_slot, int32_t* n_events, int cap,
+                    void* stream);
+
 /* ------------------------------------------------------------ relation head ----- */
 
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */

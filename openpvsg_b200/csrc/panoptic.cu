@@ -749,3 +749,118 @@ extern "C" int pvsg_instance_finalize(const float* scores, const int32_t* labels
     return pvsg_instance_finalize_batched(scores, labels, query, stats, boxes, 1, n, num_things, topk, boxes6,
                                           out_labels, sel_query, count, stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// Device-side run-length events for the tube wire format (reference: concat_seq,
+// models/mask2former_vps/utils.py:38-54 -> pycocotools RLE of `pan == id` per kept segment, written as
+// `masks.txt` rows by models/unitrack/utils/io.py:14-37).  COCO RLE walks the mask COLUMN-major; a
+// run boundary of segment s sits wherever the label changes to or from s along that walk.  One pass
+// over the panoptic map finds the boundaries of ALL kept segments at once:
+//   rle_count_kernel : thread = image column, counts its boundary events
+//   rle_scan_kernel  : exclusive scan over the columns of a frame (events stay in walk order)
+//   rle_emit_kernel  : same walk, writes (position, segment slot) at the scanned offset
+// The host gets ~10^4 events per frame instead of the 3.7 MB map; counts = differences of a
+// segment's positions (first run = zeros, so a segment that owns pixel 0 starts with a 0 count).
+namespace {
+
+__device__ __forceinline__ int rle_slot(const int* __restrict__ ids, int n, int label) {
+    for (int k = 0; k < n; ++k)
+        if (ids[k] == label) return k;
+    return -1;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) rle_walk_kernel(const int32_t* __restrict__ pan, const int32_t* __restrict__ seg_info,
+                                                       int Q, int H, int W, int32_t* __restrict__ col_events,
+                                                       const int32_t* __restrict__ col_offset, uint32_t* __restrict__ ev_pos,
+                                                       int16_t* __restrict__ ev_slot, int cap) {
+    __shared__ int ids[1024];
+    __shared__ int nseg;
+    const int b = blockIdx.y;
+    pan += (int64_t)b * H * W;
+    seg_info += (int64_t)b * (1 + 4 * Q);
+    if (threadIdx.x == 0) {
+        int n = 0;
+        const int kept = seg_info[0];
+        for (int k = 0; k < kept; ++k) {
+            const int seg = seg_info[1 + 4 * k + 2];
+            // a stuff class kept by several queries is ONE segment: first occurrence defines the slot
+            bool dup = false;
+            for (int j = 0; j < n; ++j) dup = dup || ids[j] == seg;
+            if (seg >= 0 && !dup) ids[n++] = seg;
+        }
+        nseg = n;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const int n = nseg;
+    int prev = x == 0 ? INT_MIN : pan[(int64_t)(H - 1) * W + x - 1];
+    int count = 0;
+    int64_t off = EMIT ? col_offset[(int64_t)b * W + x] : 0;
+    for (int y = 0; y < H; ++y) {
+        const int cur = __ldg(pan + (int64_t)y * W + x);
+        if (cur != prev) {
+            const int sp = prev == INT_MIN ? -1 : rle_slot(ids, n, prev);
+            const int sc = rle_slot(ids, n, cur);
+            const uint32_t pos = (uint32_t)x * (uint32_t)H + (uint32_t)y;
+            if (sp >= 0) {      // segment `prev` ends here
+                if (EMIT && off + count < cap) { ev_pos[(int64_t)b * cap + off + count] = pos; ev_slot[(int64_t)b * cap + off + count] = (int16_t)sp; }
+                ++count;
+            }
+            if (sc >= 0) {      // segment `cur` starts here
+                if (EMIT && off + count < cap) { ev_pos[(int64_t)b * cap + off + count] = pos; ev_slot[(int64_t)b * cap + off + count] = (int16_t)sc; }
+                ++count;
+            }
+            prev = cur;
+        }
+    }
+    if (!EMIT) col_events[(int64_t)b * W + x] = count;
+}
+
+// exclusive scan of the per-column event counts of one frame (one CTA per frame), total -> n_events[b]
+__global__ void __launch_bounds__(1024) rle_scan_kernel(const int32_t* __restrict__ col_events, int32_t* __restrict__ col_offset,
+                                                        int32_t* __restrict__ n_events, int W) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < W; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < W ? col_events[(int64_t)b * W + i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+        if (i < W) col_offset[(int64_t)b * W + i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_events[b] = carry;
+}
+
+}  // namespace
+
+extern "C" int pvsg_rle_events(const int32_t* pan, const int32_t* seg_info, int B, int Q, int H, int W,
+                               int32_t* col_ws, uint32_t* ev_pos, int16_t* ev_slot, int32_t* n_events, int cap,
+                               void* stream) {
+    PVSG_CHECK_ARG(pan && seg_info && col_ws && ev_pos && ev_slot && n_events);
+    PVSG_CHECK_ARG(B > 0 && B <= 65535 && Q > 0 && Q <= 1024 && H > 0 && W > 0 && cap > 0 && (int64_t)H * W < (1LL << 32));
+    cudaStream_t st = as_stream(stream);
+    int32_t* col_events = col_ws;                       // [B, W]
+    int32_t* col_offset = col_ws + (int64_t)B * W;      // [B, W]
+    dim3 grid((unsigned)((W + 255) / 256), (unsigned)B);
+    rle_walk_kernel<false><<<grid, 256, 0, st>>>(pan, seg_info, Q, H, W, col_events, nullptr, nullptr, nullptr, cap);
+    rle_scan_kernel<<<B, 1024, 0, st>>>(col_events, col_offset, n_events, W);
+    rle_walk_kernel<true><<<grid, 256, 0, st>>>(pan, seg_info, Q, H, W, nullptr, col_offset, ev_pos, ev_slot, cap);
+    return pvsg_launch_status();
+}

@@ -53,11 +53,12 @@ def postprocess_batch(det, cls, mask_lr, in_hw, img_hw, out_hw):
 class FrameRunner:
     """Captured per (H, W) frame shape for a ``Mask2FormerVideoCustom`` (clip length 1)."""
 
-    def __init__(self, detector, meta, rescale=True, batch=1, lanes=None):
+    def __init__(self, detector, meta, rescale=True, batch=1, lanes=None, rle=False):
         self.det = detector
         self.meta = dict(meta)
         self.rescale = rescale
         self.batch = int(batch)
+        self.rle = bool(rle)      # also emit the tube wire format's run-length events (ops.rle_events)
         dev = next(detector.parameters()).device
         self.dev = dev
         hp, wp = meta['batch_input_shape']
@@ -106,6 +107,8 @@ class FrameRunner:
         out_hw = tuple(meta['ori_shape'][:2]) if self.rescale else img_hw
         out = postprocess_batch(det, cls, mask_lr[:, 0].contiguous(), in_hw, img_hw, out_hw)
         out['query'] = query.transpose(0, 1).contiguous()      # [B,Q,C]
+        if self.rle:
+            out['rle_pos'], out['rle_slot'], out['rle_n'] = ops.rle_events(out['pan'], out['seg_info'])
         return out
 
     def _capture(self, first=True):
@@ -187,6 +190,10 @@ class FrameRunner:
                 res['pan_results'] = own(hb['pan'].numpy())
                 query = hb['query'].clone() if copy else hb['query']
                 res['query_feats'] = fh._query_dict(hb['seg_info'].numpy(), query)
+                if 'rle_n' in hb and int(hb['rle_n']) <= hb['rle_pos'].numel():
+                    from . import tubes
+                    res['rle'] = tubes.rle_from_events(hb['rle_pos'].numpy(), hb['rle_slot'].numpy(), int(hb['rle_n']),
+                                                       tubes.slot_ids(hb['seg_info'].numpy()), *hb['pan'].shape)
             if 'ins_boxes' in hb:
                 n = min(TOPK_INS, int(hb['ins_count'][0]))
                 labels = hb['ins_labels'][:n]
@@ -209,10 +216,10 @@ def enable_cuda_graph(detector):
     return detector
 
 
-def get_runner(detector, meta, rescale=True, batch=1):
+def get_runner(detector, meta, rescale=True, batch=1, rle=False):
     key = (tuple(meta['batch_input_shape']), tuple(meta['img_shape']), tuple(meta['ori_shape']), bool(rescale),
-           int(batch))
+           int(batch), bool(rle))
     runners = detector._runners
     if key not in runners:
-        runners[key] = FrameRunner(detector, meta, rescale, batch)
+        runners[key] = FrameRunner(detector, meta, rescale, batch, rle=rle)
     return runners[key]

@@ -757,6 +757,25 @@ def postprocess_batched(cls_logits, mask_logits_lr, in_hw, img_hw, out_hw, num_t
     return out
 
 
+def rle_events(pan, seg_info, cap=1 << 17):
+    """Run boundaries of every kept segment of pan int32 [B,H,W] (seg_info [B,1+4Q] from the panoptic
+    post-process), column-major like pycocotools: (ev_pos uint32-as-int32 [B,cap], ev_slot int16 [B,cap],
+    n_events int32 [B]).  See ``tubes.rle_from_events`` for the host side."""
+    lib = _l.load()
+    if pan.dtype != torch.int32 or seg_info.dtype != torch.int32 or not pan.is_cuda:
+        raise _l.PvsgError('rle_events: CUDA int32 pan / seg_info expected')
+    B, H, W = pan.shape
+    Q = (seg_info.shape[1] - 1) // 4
+    dev = pan.device
+    ws = torch.empty(2, B, W, device=dev, dtype=torch.int32)
+    ev_pos = torch.empty(B, cap, device=dev, dtype=torch.int32)
+    ev_slot = torch.empty(B, cap, device=dev, dtype=torch.int16)
+    n_events = torch.empty(B, device=dev, dtype=torch.int32)
+    _l.check(lib.pvsg_rle_events(_ptr(pan.contiguous()), _ptr(seg_info.contiguous()), B, Q, H, W, _ptr(ws), _ptr(ev_pos),
+                                 _ptr(ev_slot), _ptr(n_events), cap, _stream()), 'pvsg_rle_events')
+    return ev_pos, ev_slot, n_events
+
+
 def max_over_time(x):
     lib = _l.load()
     N, T, C = _f32(x).shape

@@ -68,6 +68,58 @@ def rle_decode(string, h, w):
     return flat.reshape((h, w), order='F')
 
 
+def rle_string_np(counts):
+    """Vectorised ``rle_string`` (same bytes): counts int array -> str."""
+    c = np.asarray(counts, dtype=np.int64)
+    x = c.copy()
+    if c.size > 3:
+        x[3:] -= c[1:-2]
+    n = x.size
+    chars = np.zeros((n, 8), np.uint8)
+    nchar = np.zeros(n, np.int64)
+    active = np.ones(n, bool)
+    for r in range(8):
+        low = x & 0x1f
+        x = x >> 5
+        more = np.where((low & 0x10) != 0, x != -1, x != 0)
+        ch = (low | (more.astype(np.int64) << 5)) + 48
+        chars[active, r] = ch[active]
+        nchar[active] += 1
+        active &= more
+        if not active.any():
+            break
+    keep = np.arange(8)[None, :] < nchar[:, None]
+    return chars[keep].tobytes().decode('ascii')
+
+
+def rle_from_events(ev_pos, ev_slot, n_events, seg_ids, h, w):
+    """Host side of ``ops.rle_events`` for one frame: the run-boundary events (column-major positions,
+    segment slots) -> {segment id: COCO RLE string}, identical to ``rle_string(rle_counts(pan == id))``.
+    seg_ids: kept segment ids in slot order (first appearance among the kept rows of seg_info)."""
+    n = int(n_events)
+    pos = np.asarray(ev_pos[:n]).astype(np.uint32).astype(np.int64)     # stored as the bits of a uint32
+    slot = np.asarray(ev_slot[:n]).astype(np.int64)
+    order = np.argsort(slot, kind='stable')                              # events of a segment stay in walk order
+    pos, slot = pos[order], slot[order]
+    bounds = np.searchsorted(slot, np.arange(len(seg_ids) + 1))
+    out = {}
+    for k, sid in enumerate(seg_ids):
+        p = pos[bounds[k]:bounds[k + 1]]
+        counts = np.diff(np.concatenate(([0], p, [h * w])))
+        out[int(sid)] = rle_string_np(counts)
+    return out
+
+
+def slot_ids(seg_info):
+    """Kept segment ids of a seg_info row in slot order (as pvsg_rle_events numbers them)."""
+    n = int(seg_info[0])
+    ids = []
+    for seg in np.asarray(seg_info[1:1 + 4 * n]).reshape(n, 4)[:, 2].tolist():
+        if seg >= 0 and seg not in ids:
+            ids.append(int(seg))
+    return ids
+
+
 # ------------------------------------------------------------------- tube linking -----
 class TubeLinker:
     """Incremental ``concat_seq``: tube id = 1 + order of first appearance of a panoptic id."""
@@ -78,9 +130,10 @@ class TubeLinker:
         self.rows = []          # (frame (1-based), tube id, class id, h, w, rle string)
         self.num_frames = 0
 
-    def add_frame(self, seg_ids, feats, pan=None):
+    def add_frame(self, seg_ids, feats, pan=None, rle=None, hw=None):
         """seg_ids: iterable of panoptic ids kept in this frame (reference dict order);
-        feats: matching [n,256] array; pan: optional int32 [H,W] map (-> masks.txt rows)."""
+        feats: matching [n,256] array; pan: optional int32 [H,W] map (-> masks.txt rows), or
+        rle: {segment id: RLE string} from the device encoder together with hw = (H, W)."""
         frame_id = self.num_frames
         for ins_id, feat in zip(seg_ids, feats):
             ins_id = int(ins_id)
@@ -90,7 +143,9 @@ class TubeLinker:
             tid = self.object_list.index(ins_id) + 1
             self.feat_tubes[tid][frame_id] = dict(query_feat=np.array(feat, dtype=np.float32, copy=True).reshape(-1),
                                                   cls_id=int(ins_id % 1000))
-            if pan is not None:
+            if rle is not None:
+                self.rows.append((frame_id + 1, tid, int(ins_id % 1000), hw[0], hw[1], rle[ins_id]))
+            elif pan is not None:
                 mask = (pan == ins_id)
                 self.rows.append((frame_id + 1, tid, int(ins_id % 1000), mask.shape[0], mask.shape[1],
                                   rle_string(rle_counts(mask))))
@@ -117,7 +172,10 @@ def concat_seq(outputs):
         output = output[0]
         ids = list(output['query_feats'].keys())
         feats = [np.asarray(torch.as_tensor(output['query_feats'][k][0]).cpu()) for k in ids]
-        linker.add_frame(ids, feats, output.get('pan_results'))
+        if 'rle' in output:     # FrameRunner(rle=True): strings from the device encoder
+            linker.add_frame(ids, feats, rle=output['rle'], hw=output['pan_results'].shape)
+        else:
+            linker.add_frame(ids, feats, output.get('pan_results'))
     return linker
 
 

@@ -265,6 +265,34 @@ def test_runner_pipeline_is_deterministic(detectors, cuda):
             assert len(ma) == len(mb) and all(np.array_equal(x, y) for x, y in zip(ma, mb))
 
 
+def test_device_rle_matches_host_encoder(detectors, cuda):
+    """the device-side run-length events (pvsg_rle_events) give, for every kept
+    segment of every frame, exactly the masks.txt RLE string the host encoder derives from the
+    panoptic map (concat_seq, models/mask2former_vps/utils.py:38-54; io.py:14-37)."""
+    from openpvsg_b200 import engine, tubes
+    dets, sd = detectors
+    det = dets[True]
+    H, W = 96, 160
+    meta = syn.frame_meta(H, W)
+    frames = [syn.synthetic_frame(90 + i, H, W) for i in range(3)]
+    engine.enable_cuda_graph(det)
+    try:
+        runner = engine.get_runner(det, meta, True, batch=3, rle=True)
+        res = runner.collect(runner.submit([f.to(cuda) for f in frames]))
+    finally:
+        det._runners = None
+    n_seg = 0
+    for r in res:
+        assert set(r['rle']) == set(r['query_feats'])
+        for sid, s in r['rle'].items():
+            assert s == tubes.rle_string(tubes.rle_counts(r['pan_results'] == sid))
+            n_seg += 1
+    assert n_seg > 0
+    a = tubes.concat_seq([[r] for r in res])                                     # device strings
+    b = tubes.concat_seq([[{k: v for k, v in r.items() if k != 'rle'}] for r in res])   # host encoder
+    assert a.masks_txt() == b.masks_txt() and len(a.rows) == n_seg
+
+
 def test_minvis_clip_vs_oracle(cuda):
     """Mask2FormerVideoCustomMinVIS on a 3-frame clip: MinVIS query permutations (the tube-linking
     step, mask2former_min_vis.py:244-258) and per-frame panoptic ids vs the oracle."""

@@ -103,3 +103,38 @@ def test_gather_and_link_world2_gloo():
     for rank, object_list, feats in got:
         assert object_list == ref.object_list
         assert np.array_equal(feats, ref.tube_features())
+
+
+def test_rle_events_host_side_matches_scalar_encoder():
+    """tubes.rle_from_events / rle_string_np (host side of the device RLE encoder, pvsg_rle_events)
+    against the scalar pycocotools-style encoder, including a segment that owns pixel 0, an absent
+    segment (empty mask) and a stuff class kept twice."""
+    import numpy as np
+    from openpvsg_b200 import tubes
+    rng = np.random.default_rng(0)
+    H, W = 37, 53
+    pan = np.full((H, W), 126, np.int32)
+    for sid in (5, 1003, 2007, 120):
+        y0, x0 = rng.integers(0, H - 8), rng.integers(0, W - 8)
+        pan[y0:y0 + rng.integers(3, 20), x0:x0 + rng.integers(3, 25)] = sid
+    pan[0, 0] = 5
+    ids = [5, 1003, 2007, 120, 77]
+    flat = pan.reshape(-1, order='F')
+    ev_pos, ev_slot, prev = [], [], None
+    for p, cur in enumerate(flat.tolist()):          # the walk pvsg_rle_events performs
+        if prev is None or cur != prev:
+            if prev is not None and prev in ids:
+                ev_pos.append(p), ev_slot.append(ids.index(prev))
+            if cur in ids:
+                ev_pos.append(p), ev_slot.append(ids.index(cur))
+            prev = cur
+    out = tubes.rle_from_events(np.array(ev_pos, np.uint32).view(np.int32), np.array(ev_slot, np.int16), len(ev_pos),
+                                ids, H, W)
+    for sid in ids:
+        assert out[sid] == tubes.rle_string(tubes.rle_counts(pan == sid))
+        assert np.array_equal(tubes.rle_decode(out[sid], H, W), (pan == sid).astype(np.uint8))
+    for _ in range(20):
+        c = rng.integers(0, 200000, size=rng.integers(1, 50))
+        assert tubes.rle_string_np(c) == tubes.rle_string(c.tolist())
+    info = np.array([3, 0, 5, 120, 10, 1, 7, -1, 0, 2, 5, 120, 4] + [0] * 8, np.int32)
+    assert tubes.slot_ids(info) == [120]
