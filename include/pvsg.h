@@ -323,6 +323,13 @@ int pvsg_rle_events(const int32_t* pan, const int32_t* seg_info, int B, int Q, i
                     int32_t* col_ws, uint32_t* ev_pos, int16_t* ev_slot, int32_t* n_events, int cap,
                     void* stream);
 
+/* HOST function (CPU): the events of one frame (after the D2H copy) -> pycocotools RLE strings.
+ * Stable counting sort by slot, run lengths = position differences (0 prepended, hw = H*W
+ * appended), rleToString encoding.  out: byte buffer of out_cap bytes; seg_off int64 [nseg+1]:
+ * string k = out[seg_off[k] .. seg_off[k+1]).  Returns the total length or a negative error. */
+int64_t pvsg_rle_strings_host(const uint32_t* ev_pos, const int16_t* ev_slot, int64_t n, int nseg,
+                              uint32_t hw, char* out, int64_t out_cap, int64_t* seg_off);
+
 /* ------------------------------------------------------------ relation head ----- */
 
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */

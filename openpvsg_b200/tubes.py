@@ -92,13 +92,31 @@ def rle_string_np(counts):
     return chars[keep].tobytes().decode('ascii')
 
 
-def rle_from_events(ev_pos, ev_slot, n_events, seg_ids, h, w):
+def rle_from_events(ev_pos, ev_slot, n_events, seg_ids, h, w, native=True):
     """Host side of ``ops.rle_events`` for one frame: the run-boundary events (column-major positions,
     segment slots) -> {segment id: COCO RLE string}, identical to ``rle_string(rle_counts(pan == id))``.
-    seg_ids: kept segment ids in slot order (first appearance among the kept rows of seg_info)."""
+    seg_ids: kept segment ids in slot order (first appearance among the kept rows of seg_info).
+    native: use the library's C++ host routine (pvsg_rle_strings_host); the numpy path is kept as its
+    cross-check."""
     n = int(n_events)
+    if not seg_ids:
+        return {}
+    if native:
+        from . import lib as _l
+        lib = _l.load()
+        pos = np.ascontiguousarray(ev_pos[:n]).view(np.uint32) if n else np.zeros(1, np.uint32)
+        slot = np.ascontiguousarray(ev_slot[:n], dtype=np.int16) if n else np.zeros(1, np.int16)
+        cap = 6 * (n + 2 * len(seg_ids)) + 16
+        buf = np.empty(cap, np.uint8)
+        off = np.empty(len(seg_ids) + 1, np.int64)
+        rc = lib.pvsg_rle_strings_host(pos.ctypes.data, slot.ctypes.data, n, len(seg_ids), h * w, buf.ctypes.data, cap,
+                                       off.ctypes.data)
+        if rc < 0:
+            raise _l.PvsgError(f'pvsg_rle_strings_host failed ({rc})')
+        raw = buf[:rc].tobytes()
+        return {int(sid): raw[off[k]:off[k + 1]].decode('ascii') for k, sid in enumerate(seg_ids)}
     pos = np.asarray(ev_pos[:n]).astype(np.uint32).astype(np.int64)     # stored as the bits of a uint32
-    slot = np.asarray(ev_slot[:n]).astype(np.int64)
+    slot = np.asarray(ev_slot[:n]).astype(np.int16)
     order = np.argsort(slot, kind='stable')                              # events of a segment stay in walk order
     pos, slot = pos[order], slot[order]
     bounds = np.searchsorted(slot, np.arange(len(seg_ids) + 1))

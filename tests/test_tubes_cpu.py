@@ -129,7 +129,9 @@ def test_rle_events_host_side_matches_scalar_encoder():
                 ev_pos.append(p), ev_slot.append(ids.index(cur))
             prev = cur
     out = tubes.rle_from_events(np.array(ev_pos, np.uint32).view(np.int32), np.array(ev_slot, np.int16), len(ev_pos),
-                                ids, H, W)
+                                ids, H, W)                       # C++ host routine of the library
+    assert out == tubes.rle_from_events(np.array(ev_pos, np.uint32).view(np.int32), np.array(ev_slot, np.int16),
+                                        len(ev_pos), ids, H, W, native=False)   # numpy cross-check
     for sid in ids:
         assert out[sid] == tubes.rle_string(tubes.rle_counts(pan == sid))
         assert np.array_equal(tubes.rle_decode(out[sid], H, W), (pan == sid).astype(np.uint8))
