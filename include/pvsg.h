@@ -160,6 +160,11 @@ int pvsg_add_rowvec(const float* x, const float* v, float* y, int64_t rows, int 
  * pooling that the attn-mask downsample of mask2former_head.py:383-387 reduces to.) */
 int pvsg_bilinear_resize_nhwc(const float* src, float* dst, int B, int IH, int IW, int OH,
                               int OW, int C, int accumulate, void* stream);
+/* same with a source batch stride (elements; frames of a batch that are slices of a longer token
+ * buffer) and optional split-bf16 planes (dst_hi, dst_lo) of the final dst values. */
+int pvsg_bilinear_resize_nhwc_ex(const float* src, int64_t src_batch_stride, float* dst, void* dst_hi,
+                                 void* dst_lo, int B, int IH, int IW, int OH, int OW, int C,
+                                 int accumulate, void* stream);
 
 /* Sine positional encoding, token-major out [T*H*W, 2*num_feats] (+ add_vec[2*num_feats]
  * if non-null).  dim_t [num_feats] / dim_t_z [2*num_feats] are the temperature tables

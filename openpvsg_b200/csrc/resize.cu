@@ -5,7 +5,9 @@ namespace {
 
 __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                             int IH, int IW, int OH, int OW, int cq,
-                                                            float sh, float sw, int accumulate, int64_t total) {
+                                                            float sh, float sw, int accumulate, int64_t total,
+                                                            int64_t src_bs, uint2* __restrict__ d_hi = nullptr,
+                                                            uint2* __restrict__ d_lo = nullptr) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int q = (int)(i % cq);
@@ -18,7 +20,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const float* __restr
         float wy0, wy1, wx0, wx1;
         bilinear_coord(oy, sh, IH, y0, y1, wy0, wy1);
         bilinear_coord(ox, sw, IW, x0, x1, wx0, wx1);
-        const float4* s = reinterpret_cast<const float4*>(src) + b * IH * IW * (int64_t)cq;
+        const float4* s = reinterpret_cast<const float4*>(src) + b * src_bs;   // batch stride in float4
         const float4 a = __ldg(s + ((int64_t)y0 * IW + x0) * cq + q);
         const float4 bb = __ldg(s + ((int64_t)y0 * IW + x1) * cq + q);
         const float4 c = __ldg(s + ((int64_t)y1 * IW + x0) * cq + q);
@@ -34,6 +36,20 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const float* __restr
             o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
         }
         *dp = o;
+        if (d_hi) {   // split-bf16 operand planes of the result (for the conv that consumes it)
+            const float a4[4] = {o.x, o.y, o.z, o.w};
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t u = __float_as_uint(a4[e]);
+                const uint32_t hb = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;    // RNE to bf16
+                const uint32_t ur = __float_as_uint(a4[e] - __uint_as_float(hb));
+                hh[e] = hb >> 16;
+                ll[e] = ((ur + 0x7fffu + ((ur >> 16) & 1u)) >> 16) & 0xffffu;
+            }
+            d_hi[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
+            d_lo[i] = make_uint2(ll[0] | (ll[1] << 16), ll[2] | (ll[3] << 16));
+        }
     }
 }
 
@@ -131,7 +147,21 @@ extern "C" int pvsg_bilinear_resize_nhwc(const float* src, float* dst, int B, in
     PVSG_CHECK_ARG(src && dst && B > 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && C > 0 && C % 4 == 0);
     const int64_t total = (int64_t)B * OH * OW * (C / 4);
     bilinear_nhwc_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
-        src, dst, IH, IW, OH, OW, C / 4, (float)IH / (float)OH, (float)IW / (float)OW, accumulate, total);
+        src, dst, IH, IW, OH, OW, C / 4, (float)IH / (float)OH, (float)IW / (float)OW, accumulate, total,
+        (int64_t)IH * IW * (C / 4));
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_bilinear_resize_nhwc_ex(const float* src, int64_t src_batch_stride, float* dst, void* dst_hi,
+                                            void* dst_lo, int B, int IH, int IW, int OH, int OW, int C,
+                                            int accumulate, void* stream) {
+    PVSG_CHECK_ARG(src && dst && B > 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && C > 0 && C % 4 == 0);
+    PVSG_CHECK_ARG((dst_hi == nullptr) == (dst_lo == nullptr) && src_batch_stride % 4 == 0 &&
+                   src_batch_stride >= (int64_t)IH * IW * C);
+    const int64_t total = (int64_t)B * OH * OW * (C / 4);
+    bilinear_nhwc_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
+        src, dst, IH, IW, OH, OW, C / 4, (float)IH / (float)OH, (float)IW / (float)OW, accumulate, total,
+        src_batch_stride / 4, reinterpret_cast<uint2*>(dst_hi), reinterpret_cast<uint2*>(dst_lo));
     return pvsg_launch_status();
 }
 

@@ -42,6 +42,7 @@ SIGNATURES = {
     'pvsg_groupnorm_nhwc_split': (I, [P, P, P, P, P, P, P, I, L, I, I, F, I, P]),
     'pvsg_add_rowvec': (I, [P, P, P, L, I, P]),
     'pvsg_bilinear_resize_nhwc': (I, [P, P, I, I, I, I, I, I, I, P]),
+    'pvsg_bilinear_resize_nhwc_ex': (I, [P, L, P, P, P, I, I, I, I, I, I, I, P]),
     'pvsg_sine_pe': (I, [P, P, P, P, I, I, I, I, F, F, P]),
     'pvsg_msda_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
     'pvsg_msda_fused_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),

@@ -35,7 +35,11 @@ def _tokens(x):
     if x.dim() != 4:
         raise ValueError('expected a [B,C,H,W] tensor')
     t = x.permute(0, 2, 3, 1)
-    return t if t.is_contiguous() else ops.nchw_to_nhwc(x.contiguous())
+    if t.is_contiguous():
+        return t
+    if t.stride(3) == 1:            # token-major data behind a batch-strided view: one plain copy
+        return t.contiguous()
+    return ops.nchw_to_nhwc(x.contiguous())
 
 
 def _as_nchw(t):
@@ -362,10 +366,11 @@ class _ConvModule(nn.Module):
         self._w = None
 
     @torch.no_grad()
-    def forward_tokens(self, x):
+    def forward_tokens(self, x, planes=None):
         if self._w is None or self._w.device != self.conv.weight.device:
             self._w = self.conv.weight.permute(0, 2, 3, 1).contiguous()
-        planes = ops.recall_split(x)   # e.g. backbone stage outputs already carry operand planes
+        if planes is None:
+            planes = ops.recall_split(x)   # e.g. backbone stage outputs already carry operand planes
         y = ops.conv2d_nhwc(planes if planes is not None else x, self._w, self.conv.bias, pad=self.pad)
         return y
 
@@ -462,13 +467,16 @@ class MSDeformAttnPixelDecoder(_Prepared):
             j = self.num_input_levels - self.num_encoder_levels - 1 - i
             lat = self.lateral_convs[j]
             cur = lat.norm_tokens(lat.forward_tokens(_tokens(feats[i])))
-            ops.bilinear_resize_nhwc(outs[-1].contiguous(), cur.shape[1:3], out=cur, accumulate=True)
+            # += upsampled coarser map (read through its batch-strided view), planes for the 3x3 conv
+            cur, cur_planes = ops.bilinear_resize_nhwc(outs[-1], cur.shape[1:3], out=cur, accumulate=True, out_split=True)
             oc = self.output_convs[j]
             # maps beyond num_outs only feed the next FPN step / the mask-feature conv: planes suffice
             last = i == 0 and len(outs) >= self.num_outs
-            outs.append(oc.norm_tokens(oc.forward_tokens(cur), out_mode='split' if last else 'f32'))
+            outs.append(oc.norm_tokens(oc.forward_tokens(cur, cur_planes), out_mode='split' if last else 'f32'))
         wmf = self.mask_feature.weight.view(self.mask_feature.out_channels, -1)
-        mf = ops.linear(outs[-1], wmf, self.mask_feature.bias)
+        # fp32 for the API / pooling, planes for the ten mask-logit contractions
+        mf, mf_planes = ops.linear(outs[-1], wmf, self.mask_feature.bias, out_mode='both')
+        ops.remember_split(mf, mf_planes)
         return _as_nchw(mf), [_as_nchw(o) for o in outs[:self.num_outs]]
 
 
@@ -716,7 +724,8 @@ class _Mask2FormerHeadBase(_Prepared):
         # commutes with the contraction -- see include/pvsg.h pvsg_mask_logits)
         pooled = [ops.bilinear_resize_nhwc(mf, s).view(B, -1, C) for s in lvl_shapes]
         # operand planes of the (re-used) mask features for the tcgen05 engine, split once per frame
-        mf_planes = ops.maybe_split(mf_flat)
+        mf_planes = ops.recall_split(mf)    # emitted by the mask-feature conv
+        mf_planes = mf_planes.view(B, T * h4 * w4, C) if mf_planes is not None else ops.maybe_split(mf_flat)
         pooled_planes = [ops.maybe_split(pl) for pl in pooled]
         dec_in, dec_pe = [], []
         for i, m in enumerate(memories):

@@ -462,17 +462,28 @@ def add_rowvec(x, v, out=None):
     return out
 
 
-def bilinear_resize_nhwc(src, out_hw, out=None, accumulate=False):
-    """F.interpolate(mode='bilinear', align_corners=False) on token-major [B,H,W,C]."""
+def bilinear_resize_nhwc(src, out_hw, out=None, accumulate=False, out_split=False):
+    """F.interpolate(mode='bilinear', align_corners=False) on token-major [B,H,W,C].  src may be a
+    batch-strided view (frames that are slices of a longer token buffer).  out_split=True also returns
+    the operand planes of the final values: (out, Split)."""
     lib = _l.load()
     B, IH, IW, C = _f32(src).shape
     OH, OW = out_hw
+    if src.stride(3) != 1 or src.stride(2) != C or src.stride(1) != IW * C:
+        src = src.contiguous()
     if out is None:
         if accumulate:
             raise _l.PvsgError('bilinear_resize: accumulate needs out')
         out = torch.empty(B, OH, OW, C, device=src.device, dtype=torch.float32)
-    _l.check(lib.pvsg_bilinear_resize_nhwc(_ptr(src.contiguous()), _ptr(out), B, IH, IW, OH, OW, C,
-                                           1 if accumulate else 0, _stream()), 'pvsg_bilinear_resize_nhwc')
+    hi = lo = None
+    if out_split and ENGINE[0] == 'tc' and C % 64 == 0:
+        hi = torch.empty(B, OH, OW, C, device=src.device, dtype=torch.bfloat16)
+        lo = torch.empty(B, OH, OW, C, device=src.device, dtype=torch.bfloat16)
+    _l.check(lib.pvsg_bilinear_resize_nhwc_ex(_ptr(src), src.stride(0) if B > 1 else IH * IW * C, _ptr(out), _ptr(hi),
+                                              _ptr(lo), B, IH, IW, OH, OW, C, 1 if accumulate else 0, _stream()),
+             'pvsg_bilinear_resize_nhwc')
+    if out_split:
+        return out, (Split(hi, lo) if hi is not None else None)
     return out
 
 
