@@ -31,8 +31,13 @@ def close(a, b, tol, what=''):
     a = a.detach().float().cpu()
     b = b.detach().float().cpu()
     assert a.shape == b.shape, (what, a.shape, b.shape)
-    err = (a - b).abs().max().item()
-    assert err <= tol, f'{what}: max abs err {err:.3e} > {tol:.1e}'
+    d = (a - b).abs()
+    err = d.max().item()
+    if err > tol:   # say where: an intermittent mismatch is only diagnosable with the offending element
+        i = int(d.flatten().argmax())
+        idx = tuple(int(v) for v in np.unravel_index(i, tuple(a.shape)))
+        raise AssertionError(f'{what}: max abs err {err:.3e} > {tol:.1e} at {idx}: got {a.flatten()[i].item():.9g}, '
+                             f'expected {b.flatten()[i].item():.9g}; {int((d > tol).sum())} of {d.numel()} beyond tol')
     return err
 
 
