@@ -1,0 +1,75 @@
+"""End-to-end PVSG inference on one clip: VPS forward -> tube linking -> relation head.
+
+The reference splits this over three tools with files in between
+(tools/prepare_query_tube_vps.py -> work_dirs/.../{quantitive/masks.txt, query_feats.pickle};
+utils/relation_matching.py:431-442 / datasets/datasets/pvsg_relation.py:47-53 build the zero-filled
+[N_tubes, T, 256] tube features; tools/rel_test.py:35-67 runs the relation head) and leaves
+tools/end2end_inference.py empty.  Here the stages hand over in memory:
+
+  frames --FrameRunner (8 frames per graph replay, device RLE events)--> per-frame results
+         --TubeLinker (concat_seq semantics: tube id = first appearance of a panoptic id)-->
+  tube features [N, T, 256] --relation_forward--> top pairs, span / relation scores --> triplets
+
+Multi-GPU: ranks own contiguous frame blocks (tubes.shard_frames); the only exchange is the
+all-gather of the kept (segment id, query feature) entries (tubes.gather_and_link); the relation
+stage then runs on every rank (it is ~2 ms).
+"""
+import numpy as np
+import torch
+
+from . import engine, relation_head as rh, tubes
+
+
+@torch.no_grad()
+def vps_clip(detector, frames, meta, batch=8, rle=True):
+    """frames: list of [3,H,W] tensors (pinned host or device).  Returns the per-frame result dicts
+    (reference format, plus 'rle' strings) of this rank's frames, pipelined through the runner."""
+    if getattr(detector, '_runners', None) is None:
+        engine.enable_cuda_graph(detector)
+    runner = engine.get_runner(detector, meta, True, batch=batch, rle=rle)
+    results, pend = [], None
+    for i in range(0, len(frames), batch):
+        nxt = runner.submit(frames[i:i + batch])
+        if pend is not None:
+            results += runner.collect(pend)
+        pend = nxt
+    if pend is not None:
+        results += runner.collect(pend)
+    return results
+
+
+def link_tubes(results, num_frames=None, device='cpu'):
+    """concat_seq over the clip.  Single process: local linking with masks.txt rows.  Under
+    torch.distributed every rank passes the results of its own frame block; the kept entries are
+    all-gathered and every rank gets the same tubes (mask rows stay with the owning rank)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        entries = []
+        for r in results:
+            ids = list(r['query_feats'].keys())
+            feats = np.stack([np.asarray(torch.as_tensor(r['query_feats'][k][0]).cpu()) for k in ids]) if ids \
+                else np.zeros((0, 256), np.float32)
+            entries.append((ids, feats))
+        return tubes.gather_and_link(entries, num_frames, device=device)
+    return tubes.concat_seq([[r] for r in results])
+
+
+@torch.no_grad()
+def relations(linker, models, num_top_pairs=100, device='cuda'):
+    """models: (subject_encoder, object_encoder, pair_proposal_model, relation_model).
+    Returns (results list as generate_results / test_utils.py:59-84, raw forward dict)."""
+    feats = torch.as_tensor(linker.tube_features()).to(device)
+    if feats.shape[0] < 2:
+        return [], None
+    out = rh.relation_forward(*models, feats, num_top_pairs)
+    res = rh.generate_results(out['span_pred'], out['prob'], out['pairs'].cpu().tolist())
+    return res, out
+
+
+@torch.no_grad()
+def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100):
+    """The whole path for one clip on this process.  Returns dict(results, linker, relations, raw)."""
+    results = vps_clip(detector, frames, meta, batch)
+    linker = link_tubes(results, len(frames))
+    rel, raw = relations(linker, models, num_top_pairs, device=next(detector.parameters()).device)
+    return dict(results=results, linker=linker, relations=rel, raw=raw)

@@ -293,6 +293,54 @@ def test_device_rle_matches_host_encoder(detectors, cuda):
     assert a.masks_txt() == b.masks_txt() and len(a.rows) == n_seg
 
 
+def test_end2end_clip_vs_oracle(detectors, cuda):
+    """BASELINE configs[4] scaled down: VPS forward over a clip -> tube linking (concat_seq) -> zero-filled
+    tube features -> relation head -> triplets, against the same pipeline built from the CPU oracle.
+    Tubes (ids, classes, frames, masks.txt rows) and the top relation pairs must be identical."""
+    from openpvsg_b200 import end2end, relation_head as rh, tubes
+    from oracle import m2f as om
+    from oracle import relation as orel
+    dets, sd = detectors
+    det = dets[True]
+    H, W, T = 96, 160, 6
+    meta = syn.frame_meta(H, W)
+    frames = [syn.synthetic_frame(200 + i // 2, H, W) for i in range(T)]     # repeated frames -> persistent tubes
+    sds = syn.relation_state_dicts(seed=1)
+    mods = [rh.ObjectEncoder(256), rh.ObjectEncoder(256), rh.PairProposalNetwork(256, 1024), rh.TemporalTransformer(512, 57)]
+    for m, k in zip(mods, ('subject_encoder', 'object_encoder', 'pair_proposal_model', 'relation_model')):
+        m.load_state_dict(sds[k])
+        m.to(cuda)
+    try:
+        got = end2end.run_clip(det, mods, [f.to(cuda) for f in frames], meta, batch=4, num_top_pairs=20)
+    finally:
+        det._runners = None
+    # oracle pipeline
+    ref_outputs = []
+    with torch.no_grad():
+        for f in frames:
+            ref_outputs.append(om.vps_simple_test(sd, f[None, None], [[meta]], instance_on=False)[0])
+    ref_linker = tubes.concat_seq(ref_outputs)
+    lk = got['linker']
+    assert lk.object_list == ref_linker.object_list and lk.num_frames == T
+    assert lk.masks_txt() == ref_linker.masks_txt()              # device RLE rows == host rows of the oracle maps
+    a, b = lk.tube_features(), ref_linker.tube_features()
+    assert a.shape == b.shape and (np.abs(a - b).max() < TOL)
+    assert ((a != 0).any(-1) == (b != 0).any(-1)).all()          # same frames present per tube
+    if a.shape[0] >= 2:
+        with torch.no_grad():
+            rref = orel.relation_forward(sds, torch.as_tensor(b), 20)
+        assert got['raw']['pairs'].cpu().tolist() == rref['pairs']
+        close(got['raw']['span_pred'], rref['span_pred'], 2e-3, 'span_pred')
+        close(got['raw']['prob'], rref['prob'], 2e-3, 'relation prob')
+        ref_res = orel.generate_results(rref['span_pred'], rref['prob'], rref['pairs'])
+        # triplet ranking: identical wherever the reference scores are separated by more than the tolerance
+        top = [(r['subject_index'], r['object_index'], r['relation']) for r in got['relations'][:10]]
+        ref_top = [(r['subject_index'], r['object_index'], r['relation']) for r in ref_res[:10]]
+        flat = rref['prob'].flatten().sort(descending=True).values
+        if (flat[:10] - flat[1:11]).min() > 4e-3:
+            assert top == ref_top
+
+
 def test_minvis_clip_vs_oracle(cuda):
     """Mask2FormerVideoCustomMinVIS on a 3-frame clip: MinVIS query permutations (the tube-linking
     step, mask2former_min_vis.py:244-258) and per-frame panoptic ids vs the oracle."""
