@@ -322,7 +322,13 @@ def test_end2end_clip_vs_oracle(detectors, cuda):
     ref_linker = tubes.concat_seq(ref_outputs)
     lk = got['linker']
     assert lk.object_list == ref_linker.object_list and lk.num_frames == T
-    assert lk.masks_txt() == ref_linker.masks_txt()              # device RLE rows == host rows of the oracle maps
+    # masks.txt rows: same (frame, tube, class, h, w) and the same masks up to the free-running near-tie
+    # pixels (<= 1e-3 of the frame); the strings themselves are checked bit-exactly
+    # against the host encoder on the SAME map in test_device_rle_matches_host_encoder
+    assert [r[:5] for r in lk.rows] == [r[:5] for r in ref_linker.rows]
+    for ra, rb in zip(lk.rows, ref_linker.rows):
+        ma, mb = tubes.rle_decode(ra[5], ra[3], ra[4]), tubes.rle_decode(rb[5], rb[3], rb[4])
+        assert (ma != mb).mean() <= 1e-3
     a, b = lk.tube_features(), ref_linker.tube_features()
     assert a.shape == b.shape and (np.abs(a - b).max() < TOL)
     assert ((a != 0).any(-1) == (b != 0).any(-1)).all()          # same frames present per tube
