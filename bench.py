@@ -196,6 +196,28 @@ def tube_dump_bench(det, meta, frames, batch):
                      'host path: numpy RLE of pan == id per segment (the reference uses pycocotools per segment)')
 
 
+def end2end_bench(det, meta, host_frames, batch, dev):
+    """BASELINE configs[4] on one GPU: 380 frames (76 s @ 5 FPS) @720p through VPS -> tube linking
+    (device RLE rows) -> relation head, wall clock of the whole clip from pinned host frames."""
+    from openpvsg_b200 import end2end, relation_head as rh, synthetic as syn
+    sds = syn.relation_state_dicts(seed=1)
+    mods = [rh.ObjectEncoder(256), rh.ObjectEncoder(256), rh.PairProposalNetwork(256, 1024), rh.TemporalTransformer(512, 57)]
+    for m, k in zip(mods, ('subject_encoder', 'object_encoder', 'pair_proposal_model', 'relation_model')):
+        m.load_state_dict(sds[k])
+        m.to(dev)
+    T = 380
+    clip = [host_frames[i % len(host_frames)] for i in range(T)]
+    end2end.run_clip(det, mods, clip[:2 * batch], meta, batch=batch)          # warm-up (graph with RLE, relation kernels)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = end2end.run_clip(det, mods, clip, meta, batch=batch)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dict(workload='end-to-end VPS + tube linking + relation head, 380 frames @720p (BASELINE configs[4]), 1 GPU',
+                seconds=round(dt, 3), frames_per_s=round(T / dt, 1), tubes=len(out['linker'].object_list),
+                mask_rows=len(out['linker'].rows), triplets=len(out['relations']))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -502,6 +524,11 @@ def main():
             extra['tube_dump'] = tube_dump_bench(det, meta, resident, args.batch)
     except Exception as ex:
         extra['tube_dump'] = dict(error=repr(ex))
+    try:
+        if det._runners is not None and world == 1:
+            extra['end2end_clip'] = end2end_bench(det, meta, host, args.batch, dev)
+    except Exception as ex:
+        extra['end2end_clip'] = dict(error=repr(ex))
     in_bytes = 3 * 736 * 1280 * 4
     out_bytes = H * W * 4 + (1 + 400) * 4 + 10 * H * W + 100 * 256 * 4
     line = dict(metric=METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,
