@@ -21,20 +21,30 @@ from . import engine, relation_head as rh, tubes
 
 
 @torch.no_grad()
-def vps_clip(detector, frames, meta, batch=8, rle=True):
+def vps_clip(detector, frames, meta, batch=8, rle=True, consume=None):
     """frames: list of [3,H,W] tensors (pinned host or device).  Returns the per-frame result dicts
-    (reference format, plus 'rle' strings) of this rank's frames, pipelined through the runner."""
+    (reference format, plus 'rle' strings) of this rank's frames, pipelined through the runner.
+    consume(result): called per frame as soon as its batch is collected; the results are then views
+    of the runner's pinned ring (no 13 MB-per-frame host copies) and nothing is retained."""
     if getattr(detector, '_runners', None) is None:
         engine.enable_cuda_graph(detector)
     runner = engine.get_runner(detector, meta, True, batch=batch, rle=rle)
     results, pend = [], None
+
+    def drain(p):
+        for r in runner.collect(p, copy=consume is None):
+            if consume is None:
+                results.append(r)
+            else:
+                consume(r)
+
     for i in range(0, len(frames), batch):
         nxt = runner.submit(frames[i:i + batch])
         if pend is not None:
-            results += runner.collect(pend)
+            drain(pend)
         pend = nxt
     if pend is not None:
-        results += runner.collect(pend)
+        drain(pend)
     return results
 
 
@@ -66,10 +76,25 @@ def relations(linker, models, num_top_pairs=100, device='cuda'):
     return res, out
 
 
+def _add_result(linker, r):
+    ids = list(r['query_feats'].keys())
+    feats = [np.asarray(torch.as_tensor(r['query_feats'][k][0]).cpu()) for k in ids]
+    if 'rle' in r:
+        linker.add_frame(ids, feats, rle=r['rle'], hw=r['pan_results'].shape)
+    else:
+        linker.add_frame(ids, feats, r.get('pan_results'))
+
+
 @torch.no_grad()
-def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100):
-    """The whole path for one clip on this process.  Returns dict(results, linker, relations, raw)."""
-    results = vps_clip(detector, frames, meta, batch)
-    linker = link_tubes(results, len(frames))
+def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_results=False):
+    """The whole path for one clip on this process.  Returns dict(results, linker, relations, raw).
+    With keep_results=False (default) frames are linked as their batch completes and the per-frame
+    panoptic maps are not retained (the tube wire format carries the masks as RLE rows)."""
+    if keep_results:
+        results = vps_clip(detector, frames, meta, batch)
+        linker = link_tubes(results, len(frames))
+    else:
+        results, linker = None, tubes.TubeLinker()
+        vps_clip(detector, frames, meta, batch, consume=lambda r: _add_result(linker, r))
     rel, raw = relations(linker, models, num_top_pairs, device=next(detector.parameters()).device)
     return dict(results=results, linker=linker, relations=rel, raw=raw)
