@@ -400,17 +400,21 @@ def main():
             entries.append((ids, [res['query_feats'][k][0].clone() for k in ids]))
 
         if api == 'sync' or det._runners is None:
-            # the reference's call, one frame at a time (public API; pinned host input when `api`)
-            for i in range(args.frames):
-                x = frames[i % len(frames)]
+            # the reference's call (public API; pinned host input when `api`): samples_per_gpu = batch
+            # frames per call, as mmdet's single_gpu_test would feed them
+            nb = args.batch if api == 'sync' else 1
+            for i in range(0, args.frames, nb):
+                xs = [frames[(i + j) % len(frames)] for j in range(min(nb, args.frames - i))]
                 if api == 'sync':
-                    xd = x.to(dev, non_blocking=True)[None]
-                    res = det(return_loss=False, rescale=True, img=[xd], img_metas=[[dict(meta)]],
-                              ref_img=[xd[None]], ref_img_metas=[[dict(meta)]])[0][0]
+                    xd = torch.stack(xs).to(dev, non_blocking=True) if len(xs) > 1 else xs[0].to(dev, non_blocking=True)[None]
+                    out = det(return_loss=False, rescale=True, img=[xd], img_metas=[[dict(meta)] * len(xs)],
+                              ref_img=[xd[:, None]], ref_img_metas=[[dict(meta)] for _ in xs])
+                    for r in out:
+                        consume(r[0])
                 else:
-                    res = det.simple_test(None, None, ref_img=x[None, None], ref_img_metas=[[meta]],
+                    res = det.simple_test(None, None, ref_img=xs[0][None, None], ref_img_metas=[[meta]],
                                           rescale=True)[0][0]
-                consume(res)
+                    consume(res)
         else:
             # same kernels, software-pipelined: frame i+1 is submitted before frame i is collected
             runner = engine.get_runner(det, meta, True, batch=args.batch)
@@ -544,7 +548,7 @@ def main():
                          d2h_bytes_per_step=out_bytes * args.frames * world, ms_per_step=round(ms_e2e / args.steps, 3),
                          api='engine.FrameRunner.submit/collect (pipelined) on pinned host frames',
                          sync_api_value=round(e2e_sync, 3),
-                         sync_api='model(return_loss=False, rescale=True, img=..., ref_img=...) per frame'),
+                         sync_api=f'model(return_loss=False, rescale=True, img=..., ref_img=...) with {args.batch} samples per call, synchronous'),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu, **extra)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -1036,10 +1036,11 @@ class Mask2FormerVideoCustom(_DetectorBase):
         for img, img_meta in zip(imgs, img_metas):
             for m in img_meta:
                 m['batch_input_shape'] = tuple(img.size()[-2:])
-        for ref_img, ref_img_meta in zip(kwargs['ref_img'], kwargs['ref_img_metas']):
-            for frame_meta in ref_img_meta:
-                frame_meta['batch_input_shape'] = tuple(ref_img.size()[-2:])
-        kwargs['ref_img'] = kwargs['ref_img'][0] if isinstance(kwargs['ref_img'], (list, tuple)) else kwargs['ref_img']
+        ref = kwargs['ref_img'][0] if isinstance(kwargs['ref_img'], (list, tuple)) else kwargs['ref_img']
+        for sample_metas in kwargs['ref_img_metas']:          # [batch][frame] dicts, as the reference indexes them
+            for frame_meta in sample_metas:
+                frame_meta['batch_input_shape'] = tuple(ref.size()[-2:])
+        kwargs['ref_img'] = ref
         return self.simple_test(img=imgs, img_metas=img_metas, **kwargs)
 
     @torch.no_grad()
@@ -1050,11 +1051,18 @@ class Mask2FormerVideoCustom(_DetectorBase):
             # frames >= 2 call self.match_from_embds, which the reference class does not define
             # (mask2former.py:155) -- same failure mode here.
             raise AttributeError("'Mask2FormerVideoCustom' object has no attribute 'match_from_embds'")
-        if getattr(self, '_runners', None) is not None and bs == 1:
-            # CUDA-graph replay of the same kernels (openpvsg_b200/engine.py)
+        if getattr(self, '_runners', None) is not None:
+            # CUDA-graph replay of the same kernels (openpvsg_b200/engine.py); a batch of samples
+            # (samples_per_gpu > 1, all of one shape) goes through one batched replay
             from .engine import get_runner
-            runner = get_runner(self, ref_img_metas[0][0], kwargs.get('rescale', False))
-            return [[runner.run(ref_img)]]
+            metas = [m[0] for m in ref_img_metas]
+            key = lambda d: (tuple(d['batch_input_shape']), tuple(d['img_shape']), tuple(d['ori_shape']))  # noqa: E731
+            if bs == 1:
+                runner = get_runner(self, metas[0], kwargs.get('rescale', False))
+                return [[runner.run(ref_img)]]
+            if all(key(d) == key(metas[0]) for d in metas):
+                runner = get_runner(self, metas[0], kwargs.get('rescale', False), batch=bs)
+                return [[r] for r in runner.collect(runner.submit([ref_img[i, 0] for i in range(bs)]))]
         video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
         results = [[] for _ in range(bs)]
         for i in range(bs):

@@ -229,6 +229,32 @@ def test_batched_runner_matches_single_frames(detectors, cuda):
         assert [len(x) for x in a['ins_results'][0]] == [len(x) for x in b['ins_results'][0]]
 
 
+def test_reference_api_with_several_samples_per_call(detectors, cuda):
+    """model(return_loss=False, ...) with samples_per_gpu = 3 (ref_img [3,1,3,H,W], ref_img_metas
+    [batch][frame]) goes through one batched graph replay and returns one result list per sample, equal
+    to the per-sample calls up to the free-running bound."""
+    from openpvsg_b200 import engine
+    dets, sd = detectors
+    det = dets[True]
+    H, W = 96, 160
+    meta = syn.frame_meta(H, W)
+    frames = torch.stack([syn.synthetic_frame(120 + i, H, W) for i in range(3)])
+    singles = [det(return_loss=False, rescale=True, img=[f[None].to(cuda)], img_metas=[[dict(meta)]],
+                   ref_img=[f[None, None].to(cuda)], ref_img_metas=[[dict(meta)]])[0][0] for f in frames]
+    engine.enable_cuda_graph(det)
+    try:
+        x = frames.to(cuda)
+        out = det(return_loss=False, rescale=True, img=[x], img_metas=[[dict(meta) for _ in range(3)]],
+                  ref_img=[x[:, None]], ref_img_metas=[[dict(meta)] for _ in range(3)])
+    finally:
+        det._runners = None
+    assert len(out) == 3 and all(len(o) == 1 for o in out)
+    for o, b in zip(out, singles):
+        a = o[0]
+        assert (a['pan_results'] != b['pan_results']).mean() <= 1e-3
+        assert sorted(a['query_feats']) == sorted(b['query_feats'])
+
+
 def test_runner_pipeline_is_deterministic(detectors, cuda):
     """The copy-stream / staging-ring plumbing of engine.FrameRunner: the same frames pushed through
     with more submits in flight than ring slots are wrapped around, mixed pinned-host and device
