@@ -384,6 +384,8 @@ def main():
     meta = syn.frame_meta(H, W)
     host = [f.pin_memory() for f in make_frames(args.distinct, rank)]
     resident = [f.to(dev) for f in host]
+    host_batches = [torch.stack([host[(k + j) % len(host)] for j in range(args.batch)]).pin_memory()
+                    for k in range(0, len(host), max(1, args.batch))] or [torch.stack(host).pin_memory()]
     torch.cuda.synchronize()
 
     def barrier():
@@ -406,7 +408,9 @@ def main():
             for i in range(0, args.frames, nb):
                 xs = [frames[(i + j) % len(frames)] for j in range(min(nb, args.frames - i))]
                 if api == 'sync':
-                    xd = torch.stack(xs).to(dev, non_blocking=True) if len(xs) > 1 else xs[0].to(dev, non_blocking=True)[None]
+                    # the collated, pinned batch tensor a DataLoader(pin_memory=True) hands over
+                    xb = host_batches[(i // nb) % len(host_batches)] if len(xs) == nb else torch.stack(xs)
+                    xd = xb.to(dev, non_blocking=True)
                     out = det(return_loss=False, rescale=True, img=[xd], img_metas=[[dict(meta)] * len(xs)],
                               ref_img=[xd[:, None]], ref_img_metas=[[dict(meta)] for _ in xs])
                     for r in out:
