@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One replay of the batch-8 720p frame graph between cudaProfilerStart/Stop (run under
+"""One replay of the 720p frame graph (default: the 20 frames per replay bench.py uses) between cudaProfilerStart/Stop (run under
 `ncu --profile-from-start off`): the launch list of exactly the kernels bench.py times."""
 import os
 import sys
@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import openpvsg_b200 as pv  # noqa: E402
 from openpvsg_b200 import configs, engine, synthetic as syn  # noqa: E402
 
-batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 dev = torch.device('cuda:0')
 det = pv.build_detector(configs.mask2former_r50(True))
 det.load_state_dict(syn.mask2former_state_dict(seed=0))
