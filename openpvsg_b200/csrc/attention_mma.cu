@@ -301,11 +301,20 @@ __global__ void __launch_bounds__(256) attn_mma_combine_kernel(const float* __re
 }
 
 int pick_splits_tc(int B, int H, int qtiles, int Lk) {
+    // Key splits so that the CTA count fills whole waves of the GPU (2 CTAs per SM): with 160
+    // (batch, head) pairs a 2-way split gave 320 CTAs = 1.08 waves, i.e. the last 24 CTAs ran alone.
     const int64_t base = (int64_t)B * H * qtiles;
-    int ns = 1;
-    // ~2 CTAs per SM, at least two 64-key tiles per split
-    while (base * ns < 296 && Lk / (ns * 2) >= 2 * 64 && ns < 64) ns *= 2;
-    return ns;
+    const double slots = 2.0 * 148.0;
+    int best = 1;
+    double best_score = -1.0;
+    for (int ns = 1; ns <= 32; ns *= 2) {
+        if (ns > 1 && Lk / ns < 2 * 64) break;               // at least two 64-key tiles per split
+        const double waves = (double)(base * ns) / slots;
+        const double eff = waves / (double)(int64_t)(waves + 0.999999);
+        double score = eff - 0.015 * (ns > 1 ? __builtin_ctz((unsigned)ns) : 0);  // partials + combine cost
+        if (score > best_score + 1e-9) { best_score = score; best = ns; }
+    }
+    return best;
 }
 
 template <int D>
