@@ -580,13 +580,35 @@ class DetrTransformerDecoderLayer(nn.Module):
         self.norms = nn.ModuleList([_Norm(self.embed_dims) for _ in range(3)])
 
     @torch.no_grad()
-    def forward_tokens(self, query, query_pos, kproj, vproj, mask, row_open):
-        x = self.attentions[0].forward_tokens(query, query_pos, kproj, vproj, mask, row_open)
-        x = self.norms[0](x)
-        x = self.attentions[1].forward_tokens(x, query_pos)
-        x = self.norms[1](x)
-        x = self.ffns[0](x)
-        return self.norms[2](x)
+    def forward_tokens(self, query, query_pos, kproj, vproj, mask, row_open, q_planes=None):
+        """One decoder layer on batch-first tokens.  Returns (query, planes of query + query_pos): the
+        LayerNorms emit the operand planes their consumers need (y, and y + pos for the projections that
+        take the positional embedding), so the chain runs without separate split passes.
+        q_planes: planes of query + query_pos from the previous layer (None on the first / SIMT path)."""
+        ca, sa, ffn = self.attentions[0], self.attentions[1], self.ffns[0]
+        n0, n1, n2 = self.norms
+        E = self.embed_dims
+        # cross attention
+        w, b = ca.attn.in_proj_weight, ca.attn.in_proj_bias
+        q = ops.linear(q_planes, w[:E], b[:E]) if q_planes is not None else \
+            ops.linear(query, w[:E], b[:E], add_input=query_pos)
+        o = ops.attention(q, kproj, vproj, ca.num_heads, mask=mask, row_open=row_open)
+        x = ops.linear(o, ca.attn.out_proj.weight, ca.attn.out_proj.bias, residual=query)
+        x, xs, xq = ops.layernorm(x, n0.weight, n0.bias, n0.eps, out_split=True, add=query_pos)
+        # self attention: q, k from x + pos; v from x
+        w, b = sa.attn.in_proj_weight, sa.attn.in_proj_bias
+        qk = ops.linear(xq, w[:2 * E], b[:2 * E]) if xq is not None else \
+            ops.linear(x, w[:2 * E], b[:2 * E], add_input=query_pos)
+        v = ops.linear(xs if xs is not None else x, w[2 * E:], b[2 * E:])
+        o = ops.attention(qk[..., :E], qk[..., E:], v, sa.num_heads)
+        x = ops.linear(o, sa.attn.out_proj.weight, sa.attn.out_proj.bias, residual=x)
+        x, xs = ops.layernorm(x, n1.weight, n1.bias, n1.eps, out_split=True)
+        # FFN: the hidden layer only exists as planes
+        h = ops.linear(xs if xs is not None else x, ffn.layers[0][0].weight, ffn.layers[0][0].bias,
+                       act=ops.ACT_RELU, out_mode='split')
+        x = ops.linear(h, ffn.layers[1].weight, ffn.layers[1].bias, residual=x if ffn.add_identity else None)
+        x, _, xq = ops.layernorm(x, n2.weight, n2.bias, n2.eps, out_split=True, add=query_pos)
+        return x, xq
 
     @torch.no_grad()
     def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
@@ -750,11 +772,12 @@ class _Mask2FormerHeadBase(_Prepared):
         _, mask, row_open = ops.mask_logits(me, pooled[0], False, True, pooled_planes[0])
         if force_masks is not None:  # tests: teacher-force the discrete masks (see tests/test_models_gpu.py)
             mask, row_open = self._forced(force_masks[0])
+        q_planes = None
         for i in range(nl):
             lvl = i % self.num_transformer_feat_level
             kproj, vproj = layers[i].attentions[0].project_kv(dec_in[lvl], dec_pe[lvl], dec_in[lvl],
                                                               kin_planes[lvl], vin_planes[lvl])
-            query = layers[i].forward_tokens(query, qpos, kproj, vproj, mask, row_open)
+            query, q_planes = layers[i].forward_tokens(query, qpos, kproj, vproj, mask, row_open, q_planes)
             cls_pred, me = self._embeds(query)
             cls_list.append(cls_pred)
             last = i == nl - 1
