@@ -397,10 +397,15 @@ def main():
     def run_step(frames, api):
         """One clip shard: every frame through the detector, then tube linking."""
         entries = []
+        local_linker = tubes.TubeLinker() if world == 1 else None
 
         def consume(res):
             ids = list(res['query_feats'].keys())
-            entries.append((ids, [res['query_feats'][k][0].clone() for k in ids]))
+            if local_linker is not None:
+                # single process: link while the GPU works on the next batch (concat_seq is incremental)
+                local_linker.add_frame(ids, [np.asarray(torch.as_tensor(res['query_feats'][k][0]).cpu()) for k in ids])
+            else:
+                entries.append((ids, [res['query_feats'][k][0].clone() for k in ids]))
 
         if api == 'sync' or det._runners is None:
             # the reference's call (public API; pinned host input when `api`): samples_per_gpu = batch
@@ -432,8 +437,10 @@ def main():
                 pend = nxt
             for r in runner.collect(pend, copy=False):
                 consume(r)
+        if local_linker is not None:
+            return local_linker
         ids_feats = [(ids, torch.stack(f).cpu().numpy() if f else np.zeros((0, 256), np.float32)) for ids, f in entries]
-        return tubes.gather_and_link(ids_feats, args.frames * world, device=dev if world > 1 else 'cpu')
+        return tubes.gather_and_link(ids_feats, args.frames * world, device=dev)
 
     def timed(frames, api, steps, warmup):
         for _ in range(warmup):
