@@ -1,19 +1,26 @@
 #!/bin/bash
-# ncu evidence for profiles/ (run under gpurun, 1 GPU).  $1 = tag (e.g. r01e)
+# ncu evidence for profiles/ (run under gpurun, 1 GPU).  $1 = tag (e.g. r01q).  Summaries:
+#   python tools/ncu_summary.py launches gpurun_out/${TAG}_launches.csv profiles/${TAG}_launches_graph_b20.json "<note>"
+#   python tools/gemm_traffic.py gpurun_out/${TAG}_gemm_traffic.csv profiles/${TAG}_gemm_traffic.json 20
+#   python tools/ncu_summary.py full gpurun_out/${TAG}_prof_<k>.ncu-rep profiles/${TAG}_ncu_<k>.json
 TAG=${1:-r01}
 mkdir -p gpurun_out
-# (1) launch list of ONE replay of the batch-8 720p frame graph (the kernels bench.py times)
+# (1) launch list of ONE replay of the 20-frame 720p graph (exactly the kernels bench.py times)
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file gpurun_out/${TAG}_launches.csv python tools/ncu_frame.py 8 > gpurun_out/${TAG}_ncu_frame.log 2>&1
-# (2) full captures of the top kernels at the batch-8 shapes
-full() {  # name, kernel regex, skip, kbench args...
+    --log-file gpurun_out/${TAG}_launches.csv python tools/ncu_frame.py 20 > gpurun_out/${TAG}_ncu_frame.log 2>&1
+# (2) DRAM traffic of every GEMM launch of that replay (bench.py roofline.traffic)
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    --profile-from-start off -k regex:gemm_tc_kernel --csv --log-file gpurun_out/${TAG}_gemm_traffic.csv \
+    python tools/ncu_frame.py 20 > gpurun_out/${TAG}_traffic.log 2>&1
+# (3) full captures of the top kernels (8-frame shapes: quick to replay ~40 times)
+full() {  # name, kernel regex, skip, command...
     local name=$1 rx=$2 skip=$3; shift 3
     ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 \
-        -o gpurun_out/${TAG}_prof_$name -f python tools/kbench.py --iters 1 --batch 8 "$@" > gpurun_out/${TAG}_prof_$name.log 2>&1
+        -o gpurun_out/${TAG}_prof_$name -f "$@" > gpurun_out/${TAG}_prof_$name.log 2>&1
 }
-full gemm_tc_conv gemm_tc_kernel 3 --only conv --match '256->256@184x320'
-full gemm_tc_linear gemm_tc_kernel 3 --only gemm --match 'linear_154560x1024x256'
-full msda msda_kernel 3 --only msda
-full attn attn_kernel 3 --only attn --match '100x14720'
-full pan pan_pixel_kernel 1 --only pan
+full gemm_tc_conv gemm_tc_kernel 3 python tools/kbench.py --iters 1 --batch 8 --only conv --match '256->256@184x320'
+full msda msda_group_kernel 3 python tools/kbench.py --iters 1 --batch 8 --only msda
+# kernels inside the frame graph: profile between cudaProfilerStart/Stop of tools/ncu_frame.py
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_mma_kernel -s 8 -c 1 \
+    -o gpurun_out/${TAG}_prof_attn -f python tools/ncu_frame.py 8 > gpurun_out/${TAG}_prof_attn.log 2>&1
 ls -la gpurun_out/ | grep ${TAG}
