@@ -335,6 +335,18 @@ int pvsg_rle_events(const int32_t* pan, const int32_t* seg_info, int B, int Q, i
 int64_t pvsg_rle_strings_host(const uint32_t* ev_pos, const int16_t* ev_slot, int64_t n, int nseg,
                               uint32_t hw, char* out, int64_t out_cap, int64_t* seg_off);
 
+/* Joint histogram of a ground-truth instance-id map and a predicted panoptic map, per frame, for
+ * the relation-set builder (reference: match_and_process_gt_tubes / calculate_iou,
+ * utils/relation_matching.py:156-165,205-260 -- per (frame, GT object, same-class tube) it decodes
+ * the tube's RLE mask and runs two full-frame logical passes).  gt int32 [B,H,W] holds object ids
+ * (ids outside [0,G) are counted in row G); pan int32 [B,H,W] and seg_info [B,1+4Q] as written by
+ * pvsg_panoptic_fuse (slots numbered as in pvsg_rle_events; column Q = pixels of no kept segment).
+ * counts int32 [B,G+1,Q+1] (zeroed by the call): counts[b][g][s] = |gt g & slot s|; row sums =
+ * GT areas, column sums = segment areas, so IoU(g,s) = c / (row_g + col_s - c) for every pair.
+ * (G+1)*(Q+1) <= 51200 (shared-memory histogram). */
+int pvsg_tube_overlap(const int32_t* gt, const int32_t* pan, const int32_t* seg_info, int B, int Q,
+                      int H, int W, int G, int32_t* counts, void* stream);
+
 /* ------------------------------------------------------------ relation head ----- */
 
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */

@@ -17,7 +17,7 @@ stage then runs on every rank (it is ~2 ms).
 import numpy as np
 import torch
 
-from . import engine, relation_head as rh, tubes
+from . import engine, relation_head as rh, relation_set, tubes
 
 
 @torch.no_grad()
@@ -98,3 +98,46 @@ def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_re
         vps_clip(detector, frames, meta, batch, consume=lambda r: _add_result(linker, r))
     rel, raw = relations(linker, models, num_top_pairs, device=next(detector.parameters()).device)
     return dict(results=results, linker=linker, relations=rel, raw=raw)
+
+
+@torch.no_grad()
+def relation_set_clip(detector, frames, meta, gt_maps, object_list, gt_relations, batch=8, max_segments=100):
+    """tools/prepare_query_tube_vps.py:170-240 + tools/prepare_rel_set.py:24-52 for one video, in memory: VPS
+    forward -> tube linking -> overlap of every frame's panoptic map with its ground-truth instance-id map
+    (``ops.tube_overlap``, one device pass per batch of frames) -> matched tubes -> the ``relations.pickle``
+    dictionary that ``relation_set.PVSGRelationDataset(memory=...)`` serves.  gt_maps: [T,H,W] integer maps at the
+    frames' ``ori_shape``; object_list / gt_relations as ``PVSGRelationAnnotation.__getitem__`` returns them.
+    Returns dict(linker, counts [T,G+1,Q+1], frame_tube_ids, relation_dict)."""
+    from . import ops
+    device = next(detector.parameters()).device
+    linker = tubes.TubeLinker()
+    num_gt = max([int(o['object_id']) for o in object_list] + [0]) + 1
+    counts, slot_tubes, held = [], [], []
+
+    def flush():
+        if not held:
+            return
+        lo = len(counts)
+        pan = torch.stack([h[0] for h in held])
+        seg_info = torch.zeros(len(held), 1 + 4 * max_segments, dtype=torch.int32)
+        for b, (_, ids) in enumerate(held):
+            seg_info[b, 0] = len(ids)
+            for k, seg in enumerate(ids):
+                seg_info[b, 3 + 4 * k] = seg
+        gt = torch.as_tensor(np.ascontiguousarray(gt_maps[lo:lo + len(held)])).to(device=device, dtype=torch.int32)
+        counts.extend(ops.tube_overlap(gt, pan, seg_info.to(device), num_gt).cpu().numpy())
+        held.clear()
+
+    def consume(r):
+        _add_result(linker, r)
+        ids = [int(k) for k in r['query_feats'].keys()]
+        slot_tubes.append([linker.object_list.index(i) + 1 for i in ids])
+        held.append((torch.as_tensor(r['pan_results']).to(device=device, dtype=torch.int32), ids))
+        if len(held) == batch:
+            flush()
+
+    vps_clip(detector, frames, meta, batch, consume=consume)
+    flush()
+    counts = np.stack(counts) if counts else np.zeros((0, num_gt + 1, max_segments + 1), np.int32)
+    rd = relation_set.build_relation_dict(linker, counts, slot_tubes, object_list, gt_relations)
+    return dict(linker=linker, counts=counts, frame_tube_ids=slot_tubes, relation_dict=rd)

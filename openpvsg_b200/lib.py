@@ -62,6 +62,7 @@ SIGNATURES = {
     'pvsg_instance_finalize_batched': (I, [P, P, P, P, P, I, I, I, I, P, P, P, P, P]),
     'pvsg_rle_events': (I, [P, P, I, I, I, I, P, P, P, P, I, P]),
     'pvsg_rle_strings_host': (L, [P, P, L, I, ctypes.c_uint32, P, L, P]),
+    'pvsg_tube_overlap': (I, [P, P, P, I, I, I, I, I, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
     'pvsg_pair_proposal': (I, [P, P, P, P, P, I, I, P]),
     'pvsg_top_pairs': (I, [P, I, I, P, P, P]),
@@ -108,7 +109,7 @@ def load():
 
 # kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)
 KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_groupnorm_nhwc_split': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3,
-                    'pvsg_panoptic_fuse_batched': 4, 'pvsg_instance_masks_batched': 3, 'pvsg_rle_events': 3}
+                    'pvsg_panoptic_fuse_batched': 4, 'pvsg_instance_masks_batched': 3, 'pvsg_rle_events': 3, 'pvsg_tube_overlap': 1}
 launch_count = [0]
 
 

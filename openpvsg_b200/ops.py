@@ -787,6 +787,22 @@ def rle_events(pan, seg_info, cap=1 << 17):
     return ev_pos, ev_slot, n_events
 
 
+def tube_overlap(gt, pan, seg_info, num_gt):
+    """counts int32 [B, num_gt + 1, Q + 1]: joint histogram of GT object ids (gt int32 [B,H,W]) and the kept
+    segments of pan int32 [B,H,W] (slot order of ``tubes.slot_ids``); row num_gt = other GT ids, column Q = pixels
+    of no kept segment.  One pass over both maps (``relation_set.match_clip`` derives every IoU from it)."""
+    lib = _l.load()
+    if gt.dtype != torch.int32 or pan.dtype != torch.int32 or seg_info.dtype != torch.int32 or not pan.is_cuda \
+            or not gt.is_cuda or gt.shape != pan.shape:
+        raise _l.PvsgError('tube_overlap: CUDA int32 gt / pan of one shape and int32 seg_info expected')
+    B, H, W = pan.shape
+    Q = (seg_info.shape[1] - 1) // 4
+    counts = torch.empty(B, num_gt + 1, Q + 1, device=pan.device, dtype=torch.int32)
+    _l.check(lib.pvsg_tube_overlap(_ptr(gt.contiguous()), _ptr(pan.contiguous()), _ptr(seg_info.contiguous()), B, Q, H, W,
+                                   int(num_gt), _ptr(counts), _stream()), 'pvsg_tube_overlap')
+    return counts
+
+
 def max_over_time(x):
     lib = _l.load()
     N, T, C = _f32(x).shape

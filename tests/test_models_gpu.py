@@ -374,6 +374,55 @@ def test_end2end_clip_vs_oracle(detectors, cuda):
             assert top == ref_top
 
 
+def test_relation_set_clip_in_memory(detectors, cuda):
+    """frames -> tubes -> GT matching -> relation samples without files.  The ground truth is
+    cut from the detector's own panoptic maps (two segments merged, one shifted), so the expected matching is
+    known; counts are checked bit-exactly against the oracle histogram on the returned maps."""
+    from openpvsg_b200 import end2end, relation_set as rs, tubes
+    from oracle import relset as orl
+    dets, sd = detectors
+    det = dets[True]
+    H, W, T = 96, 160, 8
+    meta = syn.frame_meta(H, W)
+    frames = [syn.synthetic_frame(200 + i // 4, H, W).to(cuda) for i in range(T)]
+    try:
+        res = end2end.vps_clip(det, frames, meta, batch=4)
+        seg_ids = sorted({int(k) for r in res for k in r['query_feats']})
+        assert seg_ids, 'synthetic detector kept no segment'
+        # GT object id = 1 + rank of the panoptic id; class = id % 1000 (so every tube is a candidate)
+        gt = np.zeros((T, H, W), np.int32)
+        for t, r in enumerate(res):
+            for g, s in enumerate(seg_ids):
+                gt[t][r['pan_results'] == s] = g + 1
+        gt[:, :, :W // 8] = 0                                   # ground truth is missing a strip
+        objects = [dict(object_id=g + 1, category=s % 1000) for g, s in enumerate(seg_ids)]
+        gt_rel = [[1, min(2, len(seg_ids)), 0, [[0, T]]]]
+        got = end2end.relation_set_clip(det, frames, meta, gt, objects, gt_rel, batch=4)
+    finally:
+        det._runners = None
+    lk = got['linker']
+    assert lk.num_frames == T and got['counts'].shape == (T, len(seg_ids) + 2, 101)
+    for t, r in enumerate(res):
+        ids = [int(k) for k in r['query_feats']]
+        seg_info = np.zeros((1, 401), np.int32)
+        seg_info[0, 0] = len(ids)
+        seg_info[0, 3:3 + 4 * len(ids):4] = ids
+        want = orl.joint_histogram(gt[t:t + 1], r['pan_results'][None].astype(np.int32), seg_info, len(seg_ids) + 1)
+        assert np.array_equal(got['counts'][t:t + 1], want), t
+    # host flow from the same counts == the one-call result; dataset sample is well-formed
+    cids = {tid: str(lk.object_list[tid - 1] % 1000) for tid in sorted(lk.feat_tubes, key=str)}
+    md = rs.compact_matching_dict(rs.match_from_counts(got['counts'], got['frame_tube_ids'], cids, objects))
+    rels = rs.translate_gt_relations(md, gt_rel)
+    rd = got['relation_dict']
+    assert len(rd['relations']) == len([r for r in rels if sum(b - a for a, b in r[3]) >= 3])
+    assert set(rd['feats']) == set(lk.feat_tubes)
+    anno = dict(split=dict(vidor=dict(train=['v'], val=[]), epic_kitchen=dict(train=[], val=[]), ego4d=dict(train=[], val=[])),
+                objects=dict(thing=[], stuff=[]), relations=['r'], data=[dict(video_id='v', objects=[], relations=[])])
+    sample = rs.PVSGRelationDataset(anno, 'train', memory={'v': rd})[0]
+    assert sample['feats'].shape == (len(lk.feat_tubes), T, 256)
+    assert np.allclose(sample['feats'], lk.tube_features()[[t - 1 for t in rd['feats']]])
+
+
 def test_minvis_clip_vs_oracle(cuda):
     """Mask2FormerVideoCustomMinVIS on a 3-frame clip: MinVIS query permutations (the tube-linking
     step, mask2former_min_vis.py:244-258) and per-frame panoptic ids vs the oracle."""
