@@ -32,6 +32,7 @@ extern "C" {
 
 #define PVSG_ACT_NONE 0
 #define PVSG_ACT_RELU 1
+#define PVSG_ACT_GELU 2 /* exact erf GELU (torch nn.GELU default; Swin FFN) */
 
 int pvsg_version(void);
 const char* pvsg_error_string(int code);
@@ -334,6 +335,27 @@ int pvsg_rle_events(const int32_t* pan, const int32_t* seg_info, int B, int Q, i
  * string k = out[seg_off[k] .. seg_off[k+1]).  Returns the total length or a negative error. */
 int64_t pvsg_rle_strings_host(const uint32_t* ev_pos, const int16_t* ev_slot, int64_t n, int nseg,
                               uint32_t hw, char* out, int64_t out_cap, int64_t* seg_off);
+
+/* ------------------------------------------------------------ Swin backbone ----- */
+/* BASELINE configs[2] names a Swin-B backbone; the reference ships none, so the interface replaced
+ * here is mmdet 2.25.0's (the version the reference pins, README.md:123-125):
+ * mmdet/models/backbones/swin.py ShiftWindowMSA.forward :175-246 + WindowMSA.forward :84-117
+ * between the qkv and proj linears.  qkv fp32 [B,H,W,3C] (channel = which*C + head*32 + d) as the
+ * qkv linear wrote it for the UNPADDED map; qkv_bias [3C] stands in for the zero-padded positions;
+ * bias_table [(2*window-1)^2, heads] = relative_position_bias_table.  Pad to a multiple of
+ * `window`, cyclic shift by `shift` (0 or window/2), window partition, softmax(q k^T / sqrt(32) +
+ * relative position bias + shift mask (-100 across img_mask regions)) v, window reverse, shift
+ * back and crop are folded into the addressing.  out fp32 [B,H,W,C].  C == heads*32,
+ * window <= 12, else PVSG_ERR_UNSUPPORTED. */
+int pvsg_window_attention(const float* qkv, const float* qkv_bias, const float* bias_table, float* out,
+                          int B, int H, int W, int C, int heads, int window, int shift, void* stream);
+
+/* mmdet/models/utils/transformer.py PatchMerging.forward :300-352 up to (not including) the
+ * reduction linear: nn.Unfold(kernel 2, stride 2) channel order (c*4 + kh*2 + kw), zero padding
+ * at the bottom / right for odd H / W ("corner" adaptive padding), LayerNorm over 4C.
+ * x fp32 [B,H,W,C] -> y fp32 [B,ceil(H/2),ceil(W/2),4C]; gamma / beta [4C].  C % 4 == 0, C <= 1024. */
+int pvsg_patch_merge_ln(const float* x, const float* gamma, const float* beta, float* y, int B, int H,
+                        int W, int C, float eps, void* stream);
 
 /* Joint histogram of a ground-truth instance-id map and a predicted panoptic map, per frame, for
  * the relation-set builder (reference: match_and_process_gt_tubes / calculate_iou,

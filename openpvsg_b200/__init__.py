@@ -9,6 +9,8 @@ registries of ``openpvsg_b200.registry``.  The arithmetic lives in libpvsg_sm100
 from .registry import (build_backbone, build_detector, build_head, load_config,  # noqa: F401
                        DETECTORS, HEADS, BACKBONES, POSITIONAL_ENCODING)
 from . import mask2former  # noqa: F401  (registers the modules)
+from . import swin  # noqa: F401  (registers SwinTransformer)
+from .swin import SwinTransformer  # noqa: F401
 from .mask2former import (Mask2FormerCustom, Mask2FormerHeadCustom, Mask2FormerVideoCustom,  # noqa: F401
                           Mask2FormerVideoCustomMinVIS, Mask2FormerVideoHead, MaskFormerFusionHeadCustom,
                           SinePositionalEncoding3D)

@@ -54,3 +54,21 @@ def mask2former_r50(video=True, num_things=115, num_stuff=11, num_queries=100, i
         test_cfg=dict(panoptic_on=True, semantic_on=False, instance_on=instance_on, max_per_image=100,
                       iou_thr=0.8, filter_low_score=True, object_mask_thr=0.8, return_query=True),
         init_cfg=None)
+
+
+SWIN_B = dict(embed_dims=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32), window_size=12)
+
+
+def mask2former_swin(video=True, swin=None, **kwargs):
+    """Mask2Former(-VPS) with a Swin backbone (BASELINE configs[2]: Swin-B).  Not a reference config file -- the
+    reference ships R50 only; the backbone block and ``in_channels`` follow mmdet 2.25.0
+    ``configs/mask2former/mask2former_swin-b-p4-w12-384_lsj_8x2_50e_coco-panoptic.py`` (via its swin-t base),
+    everything else is the R50 video config above."""
+    sw = dict(SWIN_B, **(swin or {}))
+    cfg = mask2former_r50(video, **kwargs)
+    cfg['backbone'] = dict(type='SwinTransformer', pretrain_img_size=384, embed_dims=sw['embed_dims'], depths=sw['depths'],
+                           num_heads=sw['num_heads'], window_size=sw['window_size'], mlp_ratio=4, qkv_bias=True,
+                           qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.3, patch_norm=True,
+                           out_indices=(0, 1, 2, 3), with_cp=False, convert_weights=True, frozen_stages=-1, init_cfg=None)
+    cfg['panoptic_head']['in_channels'] = [sw['embed_dims'] * 2 ** i for i in range(4)]
+    return cfg

@@ -41,3 +41,6 @@ __device__ __forceinline__ void bilinear_coord(int dst, float scale, int in_size
     w1 = src - (float)i0;
     w0 = 1.f - w1;
 }
+
+// exact GELU, torch nn.GELU(approximate='none'): 0.5 x (1 + erf(x / sqrt 2))
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }

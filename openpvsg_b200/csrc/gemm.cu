@@ -261,6 +261,9 @@ gemm_kernel(GemmParams p) {
                 if (p.act == PVSG_ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == PVSG_ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
                 }
                 if (C) {
                     if (vec_out) {
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(256) skinny_kernel(GemmParams p) {
             if (p.bias) v += __ldg(p.bias + n0 + n);
             if (p.R) v += __ldg(p.R + (int64_t)m * p.ldr + n0 + n);
             if (p.act == PVSG_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (p.act == PVSG_ACT_GELU) v = gelu_erf(v);
             p.C[(int64_t)m * p.ldc + n0 + n] = v;
         }
     }
@@ -394,7 +398,7 @@ extern "C" int pvsg_linear(const float* A, const float* A2, const float* W, cons
                            int64_t sA, int64_t sW, int64_t sC, void* stream) {
     PVSG_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0 && batch > 0);
     PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N));
-    PVSG_CHECK_ARG(act == PVSG_ACT_NONE || act == PVSG_ACT_RELU);
+    PVSG_CHECK_ARG(act == PVSG_ACT_NONE || act == PVSG_ACT_RELU || act == PVSG_ACT_GELU);
     GemmParams p{};
     p.A = A; p.A2 = A2; p.W = W; p.bias = bias; p.R = R; p.C = C;
     p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.ldr = ldr;
@@ -432,7 +436,7 @@ extern "C" int pvsg_conv2d_nhwc(const float* x, const float* w, const float* bia
                                 int Cout, int R, int S, int stride, int pad, int act, void* stream) {
     PVSG_CHECK_ARG(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0);
     PVSG_CHECK_ARG(stride > 0 && pad >= 0);
-    PVSG_CHECK_ARG(act == PVSG_ACT_NONE || act == PVSG_ACT_RELU);
+    PVSG_CHECK_ARG(act == PVSG_ACT_NONE || act == PVSG_ACT_RELU || act == PVSG_ACT_GELU);
     const int OH = (H + 2 * pad - R) / stride + 1, OW = (W + 2 * pad - S) / stride + 1;
     PVSG_CHECK_ARG(OH > 0 && OW > 0);
     GemmParams p{};

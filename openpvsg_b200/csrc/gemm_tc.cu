@@ -534,6 +534,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (p.act == PVSG_ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (p.act == PVSG_ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
                 }
                 const int r0 = q * 32;
                 if (p.C) {

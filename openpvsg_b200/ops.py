@@ -14,7 +14,7 @@ import torch
 
 from . import lib as _l
 
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 
 def _stream():
@@ -785,6 +785,38 @@ def rle_events(pan, seg_info, cap=1 << 17):
     _l.check(lib.pvsg_rle_events(_ptr(pan.contiguous()), _ptr(seg_info.contiguous()), B, Q, H, W, _ptr(ws), _ptr(ev_pos),
                                  _ptr(ev_slot), _ptr(n_events), cap, _stream()), 'pvsg_rle_events')
     return ev_pos, ev_slot, n_events
+
+
+def window_attention(qkv, qkv_bias, bias_table, num_heads, window, shift):
+    """Swin (shifted-)window attention between the qkv and proj linears (mmdet swin.py ShiftWindowMSA / WindowMSA):
+    qkv [B,H,W,3C] of the unpadded map -> [B,H,W,C]; padding, roll, partition, bias, mask, reverse, crop inside."""
+    lib = _l.load()
+    _f32(qkv, 'qkv')
+    if qkv.dim() != 4 or not qkv.is_contiguous():
+        raise _l.PvsgError('window_attention: contiguous [B,H,W,3C] expected')
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    if _f32(qkv_bias).numel() != C3 or tuple(_f32(bias_table).shape) != ((2 * window - 1) ** 2, num_heads):
+        raise _l.PvsgError('window_attention: bad qkv_bias / relative_position_bias_table shape')
+    out = torch.empty(B, H, W, C, device=qkv.device, dtype=torch.float32)
+    _l.check(lib.pvsg_window_attention(_ptr(qkv), _ptr(qkv_bias.contiguous()), _ptr(bias_table.contiguous()), _ptr(out), B, H,
+                                       W, C, num_heads, window, shift, _stream()), 'pvsg_window_attention')
+    return out
+
+
+def patch_merge_ln(x, gamma, beta, eps=1e-5):
+    """mmdet PatchMerging up to the reduction linear: x [B,H,W,C] -> LayerNorm(unfold 2x2) [B,ceil(H/2),ceil(W/2),4C]."""
+    lib = _l.load()
+    _f32(x, 'x')
+    if x.dim() != 4 or not x.is_contiguous():
+        raise _l.PvsgError('patch_merge_ln: contiguous [B,H,W,C] expected')
+    B, H, W, C = x.shape
+    if _f32(gamma).numel() != 4 * C or _f32(beta).numel() != 4 * C:
+        raise _l.PvsgError('patch_merge_ln: norm over 4C expected')
+    y = torch.empty(B, (H + 1) // 2, (W + 1) // 2, 4 * C, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_patch_merge_ln(_ptr(x), _ptr(gamma.contiguous()), _ptr(beta.contiguous()), _ptr(y), B, H, W, C, eps,
+                                     _stream()), 'pvsg_patch_merge_ln')
+    return y
 
 
 def tube_overlap(gt, pan, seg_info, num_gt):

@@ -61,12 +61,47 @@ def resnet50_state_dict(g, prefix='backbone.'):
     return sd
 
 
+def swin_state_dict(g, prefix='backbone.', embed_dims=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32), window_size=12,
+                    patch_size=4, mlp_ratio=4, out_indices=(0, 1, 2, 3)):
+    """mmdet 2.25 ``SwinTransformer`` key layout (mmdet/models/backbones/swin.py), incl. the persistent
+    ``relative_position_index`` buffers.  Residual-branch outputs are damped so 24 blocks stay O(1)."""
+    sd = {}
+    p = prefix
+    sd[p + 'patch_embed.projection.weight'] = _conv_w(g, embed_dims, 3, patch_size, gain=1.0)
+    sd[p + 'patch_embed.projection.bias'] = torch.randn(embed_dims, generator=g) * 0.02
+    _norm(g, sd, p + 'patch_embed.norm', embed_dims)
+    ws = window_size
+    seq = torch.arange(0, (2 * ws - 1) * ws, 2 * ws - 1)[:, None] + torch.arange(ws)[None, :]
+    coords = seq.reshape(1, -1)
+    rel_index = (coords + coords.T).flip(1).contiguous()
+    C = embed_dims
+    for i, depth in enumerate(depths):
+        for j in range(depth):
+            b = f'{p}stages.{i}.blocks.{j}.'
+            _norm(g, sd, b + 'norm1', C)
+            sd[b + 'attn.w_msa.relative_position_bias_table'] = torch.randn((2 * ws - 1) ** 2, num_heads[i], generator=g) * 0.5
+            sd[b + 'attn.w_msa.relative_position_index'] = rel_index.clone()
+            _lin(g, sd, b + 'attn.w_msa.qkv', 3 * C, C, gain=2.0, bias_std=0.1)
+            _lin(g, sd, b + 'attn.w_msa.proj', C, C, gain=0.25)
+            _norm(g, sd, b + 'norm2', C)
+            _lin(g, sd, b + 'ffn.layers.0.0', mlp_ratio * C, C, gain=2.0, bias_std=0.1)
+            _lin(g, sd, b + 'ffn.layers.1', C, mlp_ratio * C, gain=0.25)
+        if i < len(depths) - 1:
+            _norm(g, sd, f'{p}stages.{i}.downsample.norm', 4 * C)
+            sd[f'{p}stages.{i}.downsample.reduction.weight'] = torch.randn(2 * C, 4 * C, generator=g) * math.sqrt(1.0 / (4 * C))
+        if i in out_indices:
+            _norm(g, sd, f'{p}norm{i}', C)
+        C *= 2
+    return sd
+
+
 def mask2former_state_dict(seed=0, num_classes=126, num_queries=100, enc_layers=6, dec_layers=9,
                            in_channels=(256, 512, 1024, 2048), cls_gain=40.0, mask_shift=14.0,
-                           dec_gain=0.02):
-    """Full detector state_dict (backbone + panoptic_head) with mmdet 2.25 key names."""
+                           dec_gain=0.02, backbone=None):
+    """Full detector state_dict (backbone + panoptic_head) with mmdet 2.25 key names.  backbone: None = ResNet-50;
+    a dict of ``swin_state_dict`` keyword arguments = Swin (then in_channels must be its stage widths)."""
     g = torch.Generator().manual_seed(seed)
-    sd = resnet50_state_dict(g)
+    sd = resnet50_state_dict(g) if backbone is None else swin_state_dict(g, **backbone)
     C = 256
     ph = 'panoptic_head.'
     pd = ph + 'pixel_decoder.'
