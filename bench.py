@@ -112,18 +112,26 @@ def make_frames(n_distinct, rank):
 # --------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_oracle_fps(n_frames, warmup=1):
+SWIN_SD = dict(in_channels=(128, 256, 512, 1024),
+               backbone=dict(embed_dims=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32), window_size=12))
+
+
+def cpu_oracle_fps(n_frames, warmup=1, swin=False):
     from openpvsg_b200 import synthetic as syn
     from oracle import m2f as om
     torch.set_num_threads(os.cpu_count())
-    sd = syn.mask2former_state_dict(seed=0)
+    sd = syn.mask2former_state_dict(seed=0, **SWIN_SD) if swin else syn.mask2former_state_dict(seed=0)
+    kw = {}
+    if swin:
+        from oracle import swin as osw
+        kw['backbone'] = lambda sd_, x: osw.swin_forward(sd_, x, prefix='backbone.', **SWIN_SD['backbone'])
     meta = syn.frame_meta(H, W)
     frames = [syn.synthetic_frame(i, H, W) for i in range(max(1, min(n_frames, 2)))]
     times = []
     with torch.no_grad():
         for i in range(warmup + n_frames):
             t0 = time.perf_counter()
-            om.vps_simple_test(sd, frames[i % len(frames)][None, None], [[meta]], rescale=True)
+            om.vps_simple_test(sd, frames[i % len(frames)][None, None], [[meta]], rescale=True, **kw)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     return n_frames / sum(times), times
@@ -273,7 +281,8 @@ def kernel_breakdown(det, img, meta, batch=1):
             ('add_rowvec', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
             ('instance_masks', 'postprocess', None, None), ('instance_select', 'postprocess', None, None),
             ('postprocess_batched', 'postprocess', None, None), ('bilinear_resize_nhwc', 'resize', None, None),
-            ('maxpool3x3s2_nhwc', 'resize', None, None))
+            ('maxpool3x3s2_nhwc', 'resize', None, None), ('window_attention', 'window_attention', None, None),
+            ('patch_merge_ln', 'norm', None, None))
     saved, depth = {}, [0]
 
     def wrap(name, family, flops_fn, bytes_fn):
@@ -355,6 +364,8 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the cpu_baseline sample')
     ap.add_argument('--batch', type=int, default=20, help='frames pushed through the network together (one graph replay); '
                     '100 frames per step = 5 replays of 20, measured 8 -> 322, 10 -> 342, 20 -> 348, 25 -> 347 frames/s')
+    ap.add_argument('--backbone', default='r50', choices=['r50', 'swin_b'],
+                    help='r50 = BASELINE configs[1] (the headline); swin_b = the Swin-B backbone BASELINE configs[2] names')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu launch lists)')
     args = ap.parse_args()
@@ -375,8 +386,9 @@ def main():
     import openpvsg_b200 as pv
     from openpvsg_b200 import configs, engine, lib, synthetic as syn, tubes
     peaks = load_peaks()
-    det = pv.build_detector(configs.mask2former_r50(True))
-    det.load_state_dict(syn.mask2former_state_dict(seed=0))
+    swin = args.backbone == 'swin_b'
+    det = pv.build_detector(configs.mask2former_swin(True) if swin else configs.mask2former_r50(True))
+    det.load_state_dict(syn.mask2former_state_dict(seed=0, **SWIN_SD) if swin else syn.mask2former_state_dict(seed=0))
     det.to(dev)
     if not args.no_graph:
         engine.enable_cuda_graph(det)
@@ -527,7 +539,7 @@ def main():
                  'nine of the ten calls run on pooled features (exact, 3x fewer flops)')
     cpu = None
     if not args.no_cpu_baseline:
-        fps, times = cpu_oracle_fps(args.cpu_frames)
+        fps, times = cpu_oracle_fps(args.cpu_frames, swin=swin)
         cpu = dict(value=fps, unit='frames/s', cores=os.cpu_count(), kind='port',
                    sample=f'{args.cpu_frames} frames @720p through the CPU oracle (torch CPU fp32, '
                           f'{os.cpu_count()} threads), 1 warm-up frame')
@@ -547,11 +559,15 @@ def main():
         extra['end2end_clip'] = dict(error=repr(ex))
     in_bytes = 3 * 736 * 1280 * 4
     out_bytes = H * W * 4 + (1 + 400) * 4 + 10 * H * W + 100 * 256 * 4
-    line = dict(metric=METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,
+    workload = ('Mask2Former-VPS Swin-B inference (mmdet 2.25 Swin-B: embed 128, depths 2-2-18-2, window 12), synthetic 720p '
+                'clip, 100 frames per GPU (the backbone of BASELINE configs[2]); random-init weights'
+                if swin else
+                'Mask2Former-VPS R50 inference, synthetic 720p clip, 100 frames per GPU '
+                '(BASELINE configs[1]); random-init weights of the reference architecture')
+    line = dict(metric=METRIC.replace('R50', 'Swin-B') if swin else METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 3), higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='Mask2Former-VPS R50 inference, synthetic 720p clip, 100 frames per GPU '
-                                     '(BASELINE configs[1]); random-init weights of the reference architecture',
+                config=dict(workload=workload, backbone=args.backbone,
                             frames_per_gpu_per_step=args.frames, distinct_frames=args.distinct,
                             resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
                             l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',

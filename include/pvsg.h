@@ -345,10 +345,12 @@ int64_t pvsg_rle_strings_host(const uint32_t* ev_pos, const int16_t* ev_slot, in
  * bias_table [(2*window-1)^2, heads] = relative_position_bias_table.  Pad to a multiple of
  * `window`, cyclic shift by `shift` (0 or window/2), window partition, softmax(q k^T / sqrt(32) +
  * relative position bias + shift mask (-100 across img_mask regions)) v, window reverse, shift
- * back and crop are folded into the addressing.  out fp32 [B,H,W,C].  C == heads*32,
- * window <= 12, else PVSG_ERR_UNSUPPORTED. */
+ * back and crop are folded into the addressing.  out fp32 [B,H,W,C] and / or (out_hi, out_lo)
+ * bf16 [B,H,W,C]: the split operand planes of the result for the proj pvsg_linear_tc (hi = rn(v),
+ * lo = rn(v - hi)).  C == heads*32, window <= 12, else PVSG_ERR_UNSUPPORTED. */
 int pvsg_window_attention(const float* qkv, const float* qkv_bias, const float* bias_table, float* out,
-                          int B, int H, int W, int C, int heads, int window, int shift, void* stream);
+                          void* out_hi, void* out_lo, int B, int H, int W, int C, int heads, int window,
+                          int shift, void* stream);
 
 /* mmdet/models/utils/transformer.py PatchMerging.forward :300-352 up to (not including) the
  * reduction linear: nn.Unfold(kernel 2, stride 2) channel order (c*4 + kh*2 + kw), zero padding

@@ -6,6 +6,8 @@
 // versions the reference pins (README.md:123-125).  Dense projections (qkv, proj, FFN with exact
 // GELU, reduction) run on the tcgen05 GEMM engine; these two kernels are the glue around them.
 #include "common.cuh"
+#include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -16,20 +18,54 @@ constexpr int kMaxWs = 12;
 // One CTA = one (window, head).  Pad + cyclic shift + window partition + reverse + crop are index
 // arithmetic: token (iy, ix) of window (wy, wx) sits at (y, x) = (wy ws + iy, wx ws + ix) of the
 // rolled, padded map, i.e. at ((y + shift) mod Hp, (x + shift) mod Wp) of the padded map; padded
-// positions (>= H or >= W) carry a zero input, so their q/k/v are the qkv bias.  Thread i owns
-// query row i (q and the output accumulator in registers), K and V of the window live in shared
-// memory and are read as broadcasts; softmax is online over chunks of four keys.  fp32 throughout.
-__global__ void __launch_bounds__(160) window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                                                               const float* __restrict__ bias_table, float* __restrict__ out,
-                                                               int H, int W, int C, int heads, int ws, int shift,
-                                                               int nwy, int nwx, float scale) {
+// positions (>= H or >= W) carry a zero input, so their q/k/v are the qkv bias.  A thread owns TWO
+// query rows (t and t + ceil(N/2)): q and the output accumulators stay in registers, K and V of the
+// window live in shared memory and every broadcast read of a key / value row feeds both rows (the
+// kernel is bound by the shared-memory pipe: 16 LDS.128 per key).  Softmax is online over chunks
+// of four keys.  fp32 throughout; the result leaves as fp32 or directly as the split-bf16 operand
+// planes of the proj GEMM.
+
+__device__ __forceinline__ void store_row(float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                          __nv_bfloat16* __restrict__ out_lo, int64_t off, const float* acc, float inv) {
+    if (out) {
+#pragma unroll
+        for (int d = 0; d < kHeadDim; d += 4)
+            *reinterpret_cast<float4*>(out + off + d) =
+                make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+    }
+    if (out_hi) {
+#pragma unroll
+        for (int d = 0; d < kHeadDim; d += 8) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v0 = acc[d + 2 * e] * inv, v1 = acc[d + 2 * e + 1] * inv;
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                h[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                l[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4*>(out_hi + off + d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(out_lo + off + d) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+    }
+}
+
+template <int kRows>
+__global__ void __launch_bounds__(kRows == 2 ? 96 : 160) window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                              const float* __restrict__ bias_table, float* __restrict__ out,
+                                                              __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                              int H, int W, int C, int heads, int ws, int shift,
+                                                              int nwy, int nwx, float scale) {
     __shared__ __align__(16) float Ks[kMaxTokens * kHeadDim];
     __shared__ __align__(16) float Vs[kMaxTokens * kHeadDim];
     __shared__ float tbl[(2 * kMaxWs - 1) * (2 * kMaxWs - 1)];
-    __shared__ int64_t src[kMaxTokens];   // token offset (elements) into qkv rows, -1 = padded position
+    __shared__ int64_t src[kMaxTokens];   // token row of the unpadded map, -1 = padded position
     __shared__ unsigned char region[kMaxTokens];
 
     const int N = ws * ws;
+    const int half = kRows == 2 ? (N + 1) / 2 : N;
     const int head = blockIdx.y;
     int win = blockIdx.x;
     const int wx = win % nwx; win /= nwx;
@@ -40,20 +76,20 @@ __global__ void __launch_bounds__(160) window_attention_kernel(const float* __re
     const int span = 2 * ws - 1;
 
     for (int i = tid; i < span * span; i += blockDim.x) tbl[i] = __ldg(bias_table + (int64_t)i * heads + head);
-    if (tid < N) {
-        const int iy = tid / ws, ix = tid - iy * ws;
+    for (int t = tid; t < N; t += blockDim.x) {
+        const int iy = t / ws, ix = t - iy * ws;
         const int y = wy * ws + iy, x = wx * ws + ix;
         int ys = y + shift, xs = x + shift;
         if (ys >= Hp) ys -= Hp;
         if (xs >= Wp) xs -= Wp;
-        src[tid] = (ys < H && xs < W) ? (((int64_t)b * H + ys) * W + xs) : -1;
+        src[t] = (ys < H && xs < W) ? (((int64_t)b * H + ys) * W + xs) : -1;
         int r = 0;
         if (shift > 0) {   // img_mask regions of ShiftWindowMSA: slices (0,-ws), (-ws,-shift), (-shift,None)
             const int ry = y < Hp - ws ? 0 : (y < Hp - shift ? 1 : 2);
             const int rx = x < Wp - ws ? 0 : (x < Wp - shift ? 1 : 2);
             r = ry * 3 + rx;
         }
-        region[tid] = (unsigned char)r;
+        region[t] = (unsigned char)r;
     }
     __syncthreads();
     // K, V -> shared memory: 8 lanes x float4 per token
@@ -73,79 +109,102 @@ __global__ void __launch_bounds__(160) window_attention_kernel(const float* __re
         reinterpret_cast<float4*>(Ks)[e] = kk;
         reinterpret_cast<float4*>(Vs)[e] = vv;
     }
-    float q[kHeadDim];
-    int iy = 0, ix = 0, my_region = 0;
-    int64_t my_src = -1;
-    if (tid < N) {
-        iy = tid / ws; ix = tid - iy * ws;
-        my_src = src[tid];
-        my_region = region[tid];
-        const float* qp = my_src >= 0 ? qkv + my_src * C3 + head * kHeadDim : qkv_bias + head * kHeadDim;
+    // rows of this thread; a row that does not exist or is a padded position computes on row 0 and is not stored
+    float q[kRows][kHeadDim], acc[kRows][kHeadDim], m[kRows], l[kRows];
+    int bias_row[kRows], my_region[kRows];
+    int64_t my_src[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int t = tid + r * half;
+        const bool live = tid < half && t < N;
+        const int tt = live ? t : 0;
+        my_src[r] = live ? src[tt] : -1;
+        my_region[r] = region[tt];
+        const int iy = tt / ws, ix = tt - iy * ws;
+        bias_row[r] = (iy + ws - 1) * span + (ix + ws - 1);   // index(i, j) = bias_row - (jy span + jx)
+        const float* qp = my_src[r] >= 0 ? qkv + my_src[r] * C3 + head * kHeadDim : qkv_bias + head * kHeadDim;
 #pragma unroll
         for (int d = 0; d < kHeadDim; d += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(qp + d));
-            q[d] = t.x * scale; q[d + 1] = t.y * scale; q[d + 2] = t.z * scale; q[d + 3] = t.w * scale;
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(qp + d));
+            q[r][d] = t4.x * scale; q[r][d + 1] = t4.y * scale; q[r][d + 2] = t4.z * scale; q[r][d + 3] = t4.w * scale;
         }
+#pragma unroll
+        for (int d = 0; d < kHeadDim; ++d) acc[r][d] = 0.f;
+        m[r] = -INFINITY;
+        l[r] = 0.f;
     }
     __syncthreads();
-    if (tid >= N || my_src < 0) return;   // padded rows are cropped away
+    if (my_src[0] < 0 && my_src[kRows - 1] < 0) return;   // nothing to store (padded rows are cropped away)
 
-    float acc[kHeadDim];
-#pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) acc[d] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    const int bias_row = (iy + ws - 1) * span + (ix + ws - 1);   // index(i, j) = bias_row - (jy span + jx)
     for (int j0 = 0; j0 < N; j0 += 4) {
-        float s[4];
+        float s[kRows][4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u;
             if (j < N) {
                 const float4* kr = reinterpret_cast<const float4*>(Ks + j * kHeadDim);
-                float dot = 0.f;
+                float dot[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) dot[r] = 0.f;
 #pragma unroll
                 for (int d = 0; d < kHeadDim / 4; ++d) {
                     const float4 k4 = kr[d];
-                    dot = fmaf(q[4 * d], k4.x, dot); dot = fmaf(q[4 * d + 1], k4.y, dot);
-                    dot = fmaf(q[4 * d + 2], k4.z, dot); dot = fmaf(q[4 * d + 3], k4.w, dot);
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        dot[r] = fmaf(q[r][4 * d], k4.x, dot[r]); dot[r] = fmaf(q[r][4 * d + 1], k4.y, dot[r]);
+                        dot[r] = fmaf(q[r][4 * d + 2], k4.z, dot[r]); dot[r] = fmaf(q[r][4 * d + 3], k4.w, dot[r]);
+                    }
                 }
                 const int jy = j / ws, jx = j - jy * ws;
-                dot += tbl[bias_row - (jy * span + jx)];
-                if (region[j] != my_region) dot += -100.f;
-                s[u] = dot;
+                const int rj = region[j];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    float v = dot[r] + tbl[bias_row[r] - (jy * span + jx)];
+                    if (rj != my_region[r]) v += -100.f;
+                    s[r][u] = v;
+                }
             } else {
-                s[u] = -INFINITY;
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) s[r][u] = -INFINITY;
             }
         }
-        const float cm = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-        if (cm > m) {
-            const float corr = expf(m - cm);   // m = -inf on the first chunk: corr = 0, acc = l = 0
-            l *= corr;
 #pragma unroll
-            for (int d = 0; d < kHeadDim; ++d) acc[d] *= corr;
-            m = cm;
+        for (int r = 0; r < kRows; ++r) {
+            const float cm = fmaxf(fmaxf(s[r][0], s[r][1]), fmaxf(s[r][2], s[r][3]));
+            if (cm > m[r]) {
+                const float corr = expf(m[r] - cm);   // m = -inf on the first chunk: corr = 0, acc = l = 0
+                l[r] *= corr;
+#pragma unroll
+                for (int d = 0; d < kHeadDim; ++d) acc[r][d] *= corr;
+                m[r] = cm;
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u;
             if (j < N) {
-                const float p = expf(s[u] - m);
-                l += p;
+                float p[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    p[r] = expf(s[r][u] - m[r]);
+                    l[r] += p[r];
+                }
                 const float4* vr = reinterpret_cast<const float4*>(Vs + j * kHeadDim);
 #pragma unroll
                 for (int d = 0; d < kHeadDim / 4; ++d) {
                     const float4 v4 = vr[d];
-                    acc[4 * d] = fmaf(p, v4.x, acc[4 * d]); acc[4 * d + 1] = fmaf(p, v4.y, acc[4 * d + 1]);
-                    acc[4 * d + 2] = fmaf(p, v4.z, acc[4 * d + 2]); acc[4 * d + 3] = fmaf(p, v4.w, acc[4 * d + 3]);
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        acc[r][4 * d] = fmaf(p[r], v4.x, acc[r][4 * d]); acc[r][4 * d + 1] = fmaf(p[r], v4.y, acc[r][4 * d + 1]);
+                        acc[r][4 * d + 2] = fmaf(p[r], v4.z, acc[r][4 * d + 2]); acc[r][4 * d + 3] = fmaf(p[r], v4.w, acc[r][4 * d + 3]);
+                    }
                 }
             }
         }
     }
-    const float inv = 1.f / l;
-    float* op = out + my_src * C + head * kHeadDim;
 #pragma unroll
-    for (int d = 0; d < kHeadDim; d += 4)
-        *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+    for (int r = 0; r < kRows; ++r)
+        if (my_src[r] >= 0) store_row(out, out_hi, out_lo, my_src[r] * C + head * kHeadDim, acc[r], 1.f / l[r]);
 }
 
 // One warp = one merged token: gathers the 2x2 neighbourhood in nn.Unfold channel order
@@ -196,9 +255,10 @@ __global__ void __launch_bounds__(128) patch_merge_ln_kernel(const float* __rest
 
 }  // namespace
 
-extern "C" int pvsg_window_attention(const float* qkv, const float* qkv_bias, const float* bias_table, float* out, int B,
-                                     int H, int W, int C, int heads, int window, int shift, void* stream) {
-    PVSG_CHECK_ARG(qkv && qkv_bias && bias_table && out);
+extern "C" int pvsg_window_attention(const float* qkv, const float* qkv_bias, const float* bias_table, float* out,
+                                     void* out_hi, void* out_lo, int B, int H, int W, int C, int heads, int window,
+                                     int shift, void* stream) {
+    PVSG_CHECK_ARG(qkv && qkv_bias && bias_table && (out || out_hi) && (out_hi == nullptr) == (out_lo == nullptr));
     PVSG_CHECK_ARG(B > 0 && H > 0 && W > 0 && heads > 0 && window > 0 && shift >= 0 && shift < window);
     if (window > kMaxWs || C != heads * kHeadDim) return PVSG_ERR_UNSUPPORTED;
     const int nwy = (H + window - 1) / window, nwx = (W + window - 1) / window;
@@ -206,8 +266,17 @@ extern "C" int pvsg_window_attention(const float* qkv, const float* qkv_bias, co
     PVSG_CHECK_ARG(wins <= 0x7fffffffLL && heads <= 65535);
     const float scale = 1.f / sqrtf((float)kHeadDim);
     dim3 grid((unsigned)wins, (unsigned)heads);
-    window_attention_kernel<<<grid, 160, 0, as_stream(stream)>>>(qkv, qkv_bias, bias_table, out, H, W, C, heads, window,
-                                                                shift, nwy, nwx, scale);
+    // two query rows per thread halve the shared-memory traffic per FMA (measured faster, profiles/README.md);
+    // PVSG_WINATT_ROWS=1 keeps the one-row variant selectable for A/B timing
+    static const int rows = [] { const char* e = getenv("PVSG_WINATT_ROWS"); return (e && e[0] == '1') ? 1 : 2; }();
+    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
+    __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
+    if (rows == 2)
+        window_attention_kernel<2><<<grid, 96, 0, as_stream(stream)>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
+                                                                      window, shift, nwy, nwx, scale);
+    else
+        window_attention_kernel<1><<<grid, 160, 0, as_stream(stream)>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
+                                                                       window, shift, nwy, nwx, scale);
     return pvsg_launch_status();
 }
 

@@ -62,7 +62,7 @@ SIGNATURES = {
     'pvsg_instance_finalize_batched': (I, [P, P, P, P, P, I, I, I, I, P, P, P, P, P]),
     'pvsg_rle_events': (I, [P, P, I, I, I, I, P, P, P, P, I, P]),
     'pvsg_rle_strings_host': (L, [P, P, L, I, ctypes.c_uint32, P, L, P]),
-    'pvsg_window_attention': (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
+    'pvsg_window_attention': (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
     'pvsg_patch_merge_ln': (I, [P, P, P, P, I, I, I, I, F, P]),
     'pvsg_tube_overlap': (I, [P, P, P, I, I, I, I, I, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),

@@ -787,9 +787,10 @@ def rle_events(pan, seg_info, cap=1 << 17):
     return ev_pos, ev_slot, n_events
 
 
-def window_attention(qkv, qkv_bias, bias_table, num_heads, window, shift):
+def window_attention(qkv, qkv_bias, bias_table, num_heads, window, shift, out_mode='f32'):
     """Swin (shifted-)window attention between the qkv and proj linears (mmdet swin.py ShiftWindowMSA / WindowMSA):
-    qkv [B,H,W,3C] of the unpadded map -> [B,H,W,C]; padding, roll, partition, bias, mask, reverse, crop inside."""
+    qkv [B,H,W,3C] of the unpadded map -> [B,H,W,C]; padding, roll, partition, bias, mask, reverse, crop inside.
+    out_mode 'split': the result leaves as ``Split`` operand planes only (tcgen05 engine), 'both': (fp32, Split)."""
     lib = _l.load()
     _f32(qkv, 'qkv')
     if qkv.dim() != 4 or not qkv.is_contiguous():
@@ -798,10 +799,18 @@ def window_attention(qkv, qkv_bias, bias_table, num_heads, window, shift):
     C = C3 // 3
     if _f32(qkv_bias).numel() != C3 or tuple(_f32(bias_table).shape) != ((2 * window - 1) ** 2, num_heads):
         raise _l.PvsgError('window_attention: bad qkv_bias / relative_position_bias_table shape')
-    out = torch.empty(B, H, W, C, device=qkv.device, dtype=torch.float32)
-    _l.check(lib.pvsg_window_attention(_ptr(qkv), _ptr(qkv_bias.contiguous()), _ptr(bias_table.contiguous()), _ptr(out), B, H,
-                                       W, C, num_heads, window, shift, _stream()), 'pvsg_window_attention')
-    return out
+    want_split = out_mode in ('split', 'both') and ENGINE[0] == 'tc' and B * H * W > SKINNY_M
+    want_f32 = out_mode in ('f32', 'both') or not want_split
+    out = torch.empty(B, H, W, C, device=qkv.device, dtype=torch.float32) if want_f32 else None
+    hi = torch.empty(B, H, W, C, device=qkv.device, dtype=torch.bfloat16) if want_split else None
+    lo = torch.empty(B, H, W, C, device=qkv.device, dtype=torch.bfloat16) if want_split else None
+    _l.check(lib.pvsg_window_attention(_ptr(qkv), _ptr(qkv_bias.contiguous()), _ptr(bias_table.contiguous()), _ptr(out),
+                                       _ptr(hi), _ptr(lo), B, H, W, C, num_heads, window, shift, _stream()),
+             'pvsg_window_attention')
+    sp = Split(hi, lo) if want_split else None
+    if out_mode == 'both':
+        return out, sp
+    return sp if (out_mode == 'split' and sp is not None) else out
 
 
 def patch_merge_ln(x, gamma, beta, eps=1e-5):

@@ -9,8 +9,8 @@ name, constructor arguments, ``forward(img) -> tuple of [B,C_i,H_i,W_i]`` and ``
 relative_position_index,qkv,proj},norm2,ffn.layers.{0.0,1}}``, ``stages.{i}.downsample.{norm,reduction}``,
 ``norm{i}``) so an mmdet checkpoint loads with ``strict=True``.
 
-Device path per block (8 launches): LayerNorm (+ operand planes) -> qkv GEMM (tcgen05) -> ``pvsg_window_attention``
-(pad / roll / partition / relative-position bias / shift mask / reverse / crop folded into addressing) -> proj GEMM
+Device path per block (7 launches): LayerNorm (+ operand planes) -> qkv GEMM (tcgen05) -> ``pvsg_window_attention``
+(pad / roll / partition / relative-position bias / shift mask / reverse / crop folded into addressing, result emitted as operand planes) -> proj GEMM
 (+ residual) -> LayerNorm (+ planes) -> fc1 GEMM with exact-GELU epilogue emitting planes -> fc2 GEMM (+ residual).
 Patch merging = ``pvsg_patch_merge_ln`` + reduction GEMM.  Tokens stay token-major [B,H,W,C] throughout.
 """
@@ -65,7 +65,8 @@ class _SwinBlock(nn.Module):
         w = a.w_msa
         y, yp = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out_split=True)
         qkv = ops.linear(yp if yp is not None else y, w.qkv.weight, w.qkv.bias)
-        att = ops.window_attention(qkv, w.qkv.bias, w.relative_position_bias_table, a.num_heads, a.window_size, a.shift_size)
+        att = ops.window_attention(qkv, w.qkv.bias, w.relative_position_bias_table, a.num_heads, a.window_size, a.shift_size,
+                                   out_mode='split')
         x = ops.linear(att, w.proj.weight, w.proj.bias, residual=x)
         y, yp = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, out_split=True)
         fc1, fc2 = self.ffn.layers[0][0], self.ffn.layers[1]

@@ -469,13 +469,13 @@ def match_from_embds(tgt_embds, cur_embds):
     return indices[1]
 
 
-def vps_simple_test(sd, ref_img, ref_img_metas, rescale=True, instance_on=True, return_raw=False):
+def vps_simple_test(sd, ref_img, ref_img_metas, rescale=True, instance_on=True, return_raw=False, backbone=None):
     """Mask2FormerVideoCustom.simple_test, models/mask2former_vps/mask2former.py:125-223.
 
     ref_img [B, T, 3, H, W]; the shipped test config uses T = 1 and B = 1.
     """
     bs, num_frame, three, h, w = ref_img.shape
-    video_x = resnet50(sd, ref_img.reshape(bs * num_frame, three, h, w))
+    video_x = (backbone or resnet50)(sd, ref_img.reshape(bs * num_frame, three, h, w))
     pred_logits, mask_pred_list, query_pred_list = [], [], []
     for i in range(video_x[0].shape[0]):
         cur = [f[i].unsqueeze(0) for f in video_x]
@@ -569,7 +569,7 @@ def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True):
     """Mask2FormerVideoCustomMinVIS.simple_test, models/mask2former_vps/mask2former_min_vis.py:132-231
     (panoptic branch): per-frame heads, MinVIS matching, clip-averaged logits, per-frame fusion."""
     bs, num_frame, three, h, w = ref_img.shape
-    video_x = resnet50(sd, ref_img.reshape(bs * num_frame, three, h, w))
+    video_x = (backbone or resnet50)(sd, ref_img.reshape(bs * num_frame, three, h, w))
     pred_logits, mask_pred_list, query_pred_list = [], [], []
     for i in range(num_frame):
         cur = [f[i].unsqueeze(0) for f in video_x]

@@ -102,6 +102,11 @@ def test_window_attention_kernel(B, H, W, heads, ws, shift):
     want = osw.window_attention_core(qkv, bias, table, heads, ws, shift)
     got = ops.window_attention(qkv.cuda(), bias.cuda(), table.cuda(), heads, ws, shift)
     _close(got, want, 2e-5, 'window_attention')
+    both = ops.window_attention(qkv.cuda(), bias.cuda(), table.cuda(), heads, ws, shift, out_mode='both')
+    assert torch.equal(both[0], got)
+    if both[1] is not None:       # operand planes: hi = rn_bf16(v), lo = rn_bf16(v - hi), bit-exact from the fp32 result
+        hi = got.to(torch.bfloat16)
+        assert torch.equal(both[1].hi, hi) and torch.equal(both[1].lo, (got - hi.float()).to(torch.bfloat16))
 
 
 @pytest.mark.gpu
@@ -195,5 +200,6 @@ def test_swin_b_detector_features_and_forward():
     # the whole detector runs and returns a well-formed panoptic result
     meta = syn.frame_meta(H, W)
     res = det.simple_test(None, None, ref_img=img.to(cuda)[None], ref_img_metas=[[meta]], rescale=True)
-    pan = res[0]['pan_results']
-    assert pan.shape == (H, W) and pan.dtype == np.int32 or pan.dtype == np.int64
+    pan = res[0][0]['pan_results']
+    assert pan.shape == (H, W) and pan.dtype in (np.int32, np.int64)
+    assert set(res[0][0]['query_feats']) <= set(np.unique(pan).tolist())
