@@ -207,6 +207,257 @@ __global__ void __launch_bounds__(kRows == 2 ? 96 : 160) window_attention_kernel
         if (my_src[r] >= 0) store_row(out, out_hi, out_lo, my_src[r] * C + head * kHeadDim, acc[r], 1.f / l[r]);
 }
 
+// ---- tensor-core variant ------------------------------------------------------------------
+// Same (window, head) decomposition on mma.sync.m16n8k16 with split-bf16 operands (every product =
+// lo.hi + hi.lo + hi.hi, fp32 accumulate: fp32-grade like the rest of the engine; scheme and
+// fragment addressing as csrc/attention_mma.cu).  A warp owns 16 query rows; all keys of the
+// window (<= 144) form ONE tile, so the whole score row lives in the accumulator fragments and the
+// softmax is exact two-pass (no online rescaling).  K and V are converted to (hi, lo) planes while
+// they are staged into shared memory ([key][32 + 8] bf16, conflict-free ldmatrix); the S fragment
+// of Q K^T is the A fragment of P V.  ~20x fewer issue slots per row than the SIMT kernels above.
+constexpr int kPitch = kHeadDim + 8;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// KS16 = key steps of 16 (9 for window 12, 4 for windows <= 8); blockDim = 32 * ceil(N / 16)
+template <int KS16>
+__global__ void __launch_bounds__(32 * KS16) window_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                                         const float* __restrict__ bias_table, float* __restrict__ out,
+                                                                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                                         int H, int W, int C, int heads, int ws, int shift,
+                                                                         int nwy, int nwx, float scale) {
+    constexpr int NK = 16 * KS16;          // padded key count
+    constexpr int NT = 2 * KS16;           // S n-tiles of 8 keys
+    extern __shared__ __align__(16) uint8_t wsm[];
+    __nv_bfloat16 (*plane)[NK][kPitch] = reinterpret_cast<__nv_bfloat16 (*)[NK][kPitch]>(wsm);   // Khi Klo Vhi Vlo
+    float* tbl = reinterpret_cast<float*>(wsm + sizeof(__nv_bfloat16) * 4 * NK * kPitch);       // [(2 ws - 1)^2]
+    int64_t* src = reinterpret_cast<int64_t*>(tbl + (2 * kMaxWs - 1) * (2 * kMaxWs - 1) + 1);     // [NK] (8-byte aligned: 530 floats)
+    int* kinfo = reinterpret_cast<int*>(src + NK);                                               // [NK]: key offset | region << 16
+
+    const int N = ws * ws;
+    const int head = blockIdx.y;
+    int win = blockIdx.x;
+    const int wx = win % nwx; win /= nwx;
+    const int wy = win % nwy;
+    const int b = win / nwy;
+    const int Hp = nwy * ws, Wp = nwx * ws;
+    const int tid = threadIdx.x;
+    const int span = 2 * ws - 1;
+
+    for (int i = tid; i < span * span; i += blockDim.x) tbl[i] = __ldg(bias_table + (int64_t)i * heads + head);
+    for (int tk = tid; tk < NK; tk += blockDim.x) {
+        int64_t so = -1;
+        int info = 0;
+        if (tk < N) {
+            const int iy = tk / ws, ix = tk - iy * ws;
+            const int y = wy * ws + iy, x = wx * ws + ix;
+            int ys = y + shift, xs = x + shift;
+            if (ys >= Hp) ys -= Hp;
+            if (xs >= Wp) xs -= Wp;
+            so = (ys < H && xs < W) ? (((int64_t)b * H + ys) * W + xs) : -1;
+            int r = 0;
+            if (shift > 0) {
+                const int ry = y < Hp - ws ? 0 : (y < Hp - shift ? 1 : 2);
+                const int rx = x < Wp - ws ? 0 : (x < Wp - shift ? 1 : 2);
+                r = ry * 3 + rx;
+            }
+            info = (iy * span + ix) | (r << 16);
+        }
+        src[tk] = so;
+        kinfo[tk] = info;
+    }
+    __syncthreads();
+    // K, V -> (hi, lo) planes in shared memory; rows beyond N are zero (0 * garbage must not become NaN)
+    const int C3 = 3 * C;
+    for (int e = tid; e < NK * 8; e += blockDim.x) {
+        const int tk = e >> 3, part = e & 7;
+        const int ch = head * kHeadDim + part * 4;
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (tk < N) {
+            const int64_t so = src[tk];
+            const float* base = so >= 0 ? qkv + so * C3 : qkv_bias;
+            kk = __ldg(reinterpret_cast<const float4*>(base + C + ch));
+            vv = __ldg(reinterpret_cast<const float4*>(base + 2 * C + ch));
+        }
+        uint32_t h0, l0, h1, l1;
+        split_pair(kk.x, kk.y, h0, l0); split_pair(kk.z, kk.w, h1, l1);
+        *reinterpret_cast<uint2*>(&plane[0][tk][part * 4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&plane[1][tk][part * 4]) = make_uint2(l0, l1);
+        split_pair(vv.x, vv.y, h0, l0); split_pair(vv.z, vv.w, h1, l1);
+        *reinterpret_cast<uint2*>(&plane[2][tk][part * 4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&plane[3][tk][part * 4]) = make_uint2(l0, l1);
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // ---- Q fragments (rows 16 warp + g, + 8), scaled, split ----
+    int row[2] = {16 * warp + g, 16 * warp + g + 8};
+    int64_t my_src[2];
+    int bias_row[2], my_region[2];
+    uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const bool live = row[r] < N;
+        const int tt = live ? row[r] : 0;
+        my_src[r] = live ? src[tt] : -1;
+        const int info = kinfo[tt];
+        my_region[r] = info >> 16;
+        bias_row[r] = (info & 0xffff) + (ws - 1) * span + (ws - 1);   // index(i, j) = bias_row - key offset(j)
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float* qp = my_src[r] >= 0 ? qkv + my_src[r] * C3 : qkv_bias;
+                const float2 v = __ldg(reinterpret_cast<const float2*>(qp + head * kHeadDim + 16 * ks + 8 * half + 2 * t));
+                split_pair(v.x * scale, v.y * scale, qh[ks][2 * half + r], ql[ks][2 * half + r]);
+            }
+    __syncthreads();
+    if (16 * warp >= N) return;
+
+    // ---- S = Q K^T over all keys ----
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+        uint32_t kh[4], kl[4];
+        const int r = 8 * j + (lane & 7), c = (lane >> 3) * 8;
+        ldsm4(kh, smem_addr(&plane[0][r][c]));
+        ldsm4(kl, smem_addr(&plane[1][r][c]));
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+            mma16816(s[j], ql[k2], kh[2 * k2], kh[2 * k2 + 1]);   // small terms first
+            mma16816(s[j], qh[k2], kl[2 * k2], kl[2 * k2 + 1]);
+            mma16816(s[j], qh[k2], kh[2 * k2], kh[2 * k2 + 1]);
+        }
+    }
+    // ---- relative position bias, shift mask, exact softmax over the row ----
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = e >> 1;
+            const int key = 8 * j + 2 * t + (e & 1);
+            float v = -INFINITY;
+            if (key < N) {
+                const int info = kinfo[key];
+                v = s[j][e] + tbl[bias_row[r] - (info & 0xffff)];
+                if ((info >> 16) != my_region[r]) v += -100.f;
+            }
+            s[j][e] = v;
+            mx[r] = fmaxf(mx[r], v);
+        }
+    float l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = expf(s[j][e] - mx[e >> 1]);
+            s[j][e] = p;
+            l[e >> 1] += p;
+        }
+    // ---- O = P V ----
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS16; ++kk) {
+        uint32_t ph[4], pl[4];
+        split_pair(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+        split_pair(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+        split_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+        split_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            uint32_t vh[4], vl[4];
+            const int mi = lane >> 3;
+            const int r = 16 * kk + (mi & 1) * 8 + (lane & 7), c = 16 * np + (mi >> 1) * 8;
+            ldsm4_t(vh, smem_addr(&plane[2][r][c]));
+            ldsm4_t(vl, smem_addr(&plane[3][r][c]));
+            mma16816(o[2 * np], pl, vh[0], vh[1]);
+            mma16816(o[2 * np], ph, vl[0], vl[1]);
+            mma16816(o[2 * np], ph, vh[0], vh[1]);
+            mma16816(o[2 * np + 1], pl, vh[2], vh[3]);
+            mma16816(o[2 * np + 1], ph, vl[2], vl[3]);
+            mma16816(o[2 * np + 1], ph, vh[2], vh[3]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+        if (my_src[r] < 0) continue;      // padded position or no such row: cropped away
+        const float inv = 1.f / l[r];
+        const int64_t off = my_src[r] * C + head * kHeadDim + 2 * t;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v0 = o[i][2 * r] * inv, v1 = o[i][2 * r + 1] * inv;
+            if (out) *reinterpret_cast<float2*>(out + off + 8 * i) = make_float2(v0, v1);
+            if (out_hi) {
+                uint32_t hh, ll;
+                split_pair(v0, v1, hh, ll);
+                *reinterpret_cast<uint32_t*>(out_hi + off + 8 * i) = hh;
+                *reinterpret_cast<uint32_t*>(out_lo + off + 8 * i) = ll;
+            }
+        }
+    }
+}
+
+template <int KS16>
+static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv, const float* qkv_bias, const float* bias_table,
+                             float* out, __nv_bfloat16* oh, __nv_bfloat16* ol, int H, int W, int C, int heads, int window,
+                             int shift, int nwy, int nwx, float scale) {
+    constexpr int NK = 16 * KS16;
+    constexpr size_t smem = sizeof(__nv_bfloat16) * 4 * NK * kPitch + sizeof(float) * ((2 * kMaxWs - 1) * (2 * kMaxWs - 1) + 1) +
+                            sizeof(int64_t) * NK + sizeof(int) * NK;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(window_attention_mma_kernel<KS16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess)
+            return PVSG_ERR_LAUNCH;
+        configured = true;
+    }
+    const int warps = (N + 15) / 16;
+    window_attention_mma_kernel<KS16><<<grid, 32 * warps, smem, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
+                                                                      window, shift, nwy, nwx, scale);
+    return pvsg_launch_status();
+}
+
 // One warp = one merged token: gathers the 2x2 neighbourhood in nn.Unfold channel order
 // (channel c of tap (kh, kw) -> c*4 + kh*2 + kw; zeros beyond an odd edge), LayerNorm over 4C.
 __global__ void __launch_bounds__(128) patch_merge_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -266,17 +517,24 @@ extern "C" int pvsg_window_attention(const float* qkv, const float* qkv_bias, co
     PVSG_CHECK_ARG(wins <= 0x7fffffffLL && heads <= 65535);
     const float scale = 1.f / sqrtf((float)kHeadDim);
     dim3 grid((unsigned)wins, (unsigned)heads);
-    // two query rows per thread halve the shared-memory traffic per FMA (measured faster, profiles/README.md);
-    // PVSG_WINATT_ROWS=1 keeps the one-row variant selectable for A/B timing
-    static const int rows = [] { const char* e = getenv("PVSG_WINATT_ROWS"); return (e && e[0] == '1') ? 1 : 2; }();
+    // PVSG_WINATT_IMPL: 0 / unset = tensor-core kernel; 1, 2 = the SIMT fp32 kernels with one / two query rows
+    // per thread (kept for A/B timing and as the exact-fp32 cross-check of the split-bf16 path)
+    static const int impl = [] { const char* e = getenv("PVSG_WINATT_IMPL"); return e ? atoi(e) : 0; }();
     __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
     __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
-    if (rows == 2)
-        window_attention_kernel<2><<<grid, 96, 0, as_stream(stream)>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
-                                                                      window, shift, nwy, nwx, scale);
+    cudaStream_t st = as_stream(stream);
+    const int N = window * window;
+    if (impl == 0)
+        return N <= 64 ? launch_window_mma<4>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
+                                              nwy, nwx, scale)
+                       : launch_window_mma<9>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
+                                              nwy, nwx, scale);
+    if (impl == 2)
+        window_attention_kernel<2><<<grid, 96, 0, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
+                                                        nwy, nwx, scale);
     else
-        window_attention_kernel<1><<<grid, 160, 0, as_stream(stream)>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
-                                                                       window, shift, nwy, nwx, scale);
+        window_attention_kernel<1><<<grid, 160, 0, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
+                                                         nwy, nwx, scale);
     return pvsg_launch_status();
 }
 

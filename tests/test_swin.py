@@ -101,7 +101,9 @@ def test_window_attention_kernel(B, H, W, heads, ws, shift):
     table = torch.randn((2 * ws - 1) ** 2, heads, generator=g)
     want = osw.window_attention_core(qkv, bias, table, heads, ws, shift)
     got = ops.window_attention(qkv.cuda(), bias.cuda(), table.cuda(), heads, ws, shift)
-    _close(got, want, 2e-5, 'window_attention')
+    # default = tensor-core kernel (split-bf16 products, fp32 accumulate): fp32-grade, gate 1e-4 like the other
+    # MMA kernels; PVSG_WINATT_IMPL=1 selects the exact-fp32 SIMT kernel (measured 2e-5 on the same cases)
+    _close(got, want, 1e-4, 'window_attention')
     both = ops.window_attention(qkv.cuda(), bias.cuda(), table.cuda(), heads, ws, shift, out_mode='both')
     assert torch.equal(both[0], got)
     if both[1] is not None:       # operand planes: hi = rn_bf16(v), lo = rn_bf16(v - hi), bit-exact from the fp32 result
