@@ -173,6 +173,51 @@ def relation_bench(dev, with_cpu):
     return out
 
 
+def relset_bench(dev, with_cpu, frames=20, num_gt=32, slots=100):
+    """SURVEY 8f rank 1 (relation-set builder): per-frame overlap of a GT instance-id map with the panoptic map
+    (``pvsg_tube_overlap``) against the HBM roofline; algorithmic bytes = two int32 maps per frame.  CPU baseline =
+    the reference's evaluation (utils/relation_matching.py:156-165,205-260): one logical_and + logical_or pass per
+    (GT object, same-class tube) pair of a frame, here for 12 objects x 4 candidate tubes on one frame."""
+    from openpvsg_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    gt = torch.randint(0, num_gt, (frames, H // 16, W // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2).int()
+    slot = torch.randint(0, 40, (frames, H // 8, W // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    ids = (torch.arange(slots) % 127 + 1000 * (torch.arange(slots) // 3)).int()
+    pan = ids[slot].int()
+    seg_info = torch.zeros(frames, 1 + 4 * slots, dtype=torch.int32)
+    seg_info[:, 0] = 40
+    seg_info[:, 3:3 + 4 * 40:4] = ids[:40]
+    gt_d, pan_d, si_d = gt.to(dev), pan.to(dev), seg_info.to(dev)
+    for _ in range(3):
+        ops.tube_overlap(gt_d, pan_d, si_d, num_gt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        counts = ops.tube_overlap(gt_d, pan_d, si_d, num_gt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    gbytes = 2 * 4 * frames * H * W / 1e9
+    out = dict(frames=frames, ms=round(ms, 4), us_per_frame=round(1e3 * ms / frames, 2), achieved_GBps=round(gbytes / (ms * 1e-3), 1),
+               algorithmic_bytes_per_frame=2 * 4 * H * W, checksum=int(counts.sum().item()),
+               note='inputs (2 x 74 MB) fit the 126 MB L2 only partly; 20 back-to-back launches over the same maps')
+    if with_cpu:
+        gm, pm = gt[0].numpy(), pan[0].numpy()
+        t0 = time.perf_counter()
+        hits = 0
+        for obj in range(12):
+            gmask = gm == obj
+            for k in range(4):
+                pmask = pm == int(ids[(obj + k) % 40])
+                inter, union = np.logical_and(gmask, pmask).sum(), np.logical_or(gmask, pmask).sum()
+                hits += int(union > 0 and inter / union > 0.5)
+        out['cpu_ms_per_frame'] = round(1e3 * (time.perf_counter() - t0), 2)
+        out['cpu_sample'] = '1 frame, 12 GT objects x 4 candidate tubes, numpy masks (RLE decode not included)'
+    return out
+
+
 def tube_dump_bench(det, meta, frames, batch):
     """masks.txt rows of a batch of frames -- device run-length events
     (pvsg_rle_events + tubes.rle_from_events) vs the host encoder working on the panoptic map
@@ -547,6 +592,11 @@ def main():
         extra['relation_head'] = relation_bench(dev, not args.no_cpu_baseline)
     except Exception as ex:   # the headline metric must not depend on the auxiliary measurement
         extra['relation_head'] = dict(error=repr(ex))
+    try:
+        extra['relation_set'] = relset_bench(dev, not args.no_cpu_baseline)
+        extra['relation_set']['frac_hbm'] = round(extra['relation_set']['achieved_GBps'] / peaks['hbm_gbs'], 4)
+    except Exception as ex:
+        extra['relation_set'] = dict(error=repr(ex))
     try:
         if det._runners is not None:
             extra['tube_dump'] = tube_dump_bench(det, meta, resident, args.batch)

@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(kRows == 2 ? 96 : 160) window_attention_kernel
 // Same (window, head) decomposition on mma.sync.m16n8k16 with split-bf16 operands (every product =
 // lo.hi + hi.lo + hi.hi, fp32 accumulate: fp32-grade like the rest of the engine; scheme and
 // fragment addressing as csrc/attention_mma.cu).  A warp owns 16 query rows; all keys of the
-// window (<= 144) form ONE tile, so the whole score row lives in the accumulator fragments and the
-// softmax is exact two-pass (no online rescaling).  K and V are converted to (hi, lo) planes while
+// window (<= 144) are staged once; the score row is processed in chunks of 48 keys with an online
+// softmax in base 2 (ex2.approx).  K and V are converted to (hi, lo) planes while
 // they are staged into shared memory ([key][32 + 8] bf16, conflict-free ldmatrix); the S fragment
 // of Q K^T is the A fragment of P V.  ~20x fewer issue slots per row than the SIMT kernels above.
 constexpr int kPitch = kHeadDim + 8;
@@ -244,15 +244,16 @@ __device__ __forceinline__ void ldsm4_t(uint32_t (&r)[4], uint32_t addr) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// KS16 = key steps of 16 (9 for window 12, 4 for windows <= 8); blockDim = 32 * ceil(N / 16)
-template <int KS16>
-__global__ void __launch_bounds__(32 * KS16) window_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
+// KS16 = key steps of 16 (9 for window 12, 4 for windows <= 8), processed in chunks of CH16 steps so that the score
+// fragment stays at 8 CH16 registers and two CTAs fit an SM (the one-tile version needed 164 registers = one CTA of
+// nine warps per SM and ran latency-bound); blockDim = 32 * ceil(N / 16)
+template <int KS16, int CH16>
+__global__ void __launch_bounds__(32 * KS16, CH16 == 1 ? 3 : 2) window_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
                                                                          const float* __restrict__ bias_table, float* __restrict__ out,
                                                                          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                                                                          int H, int W, int C, int heads, int ws, int shift,
                                                                          int nwy, int nwx, float scale) {
     constexpr int NK = 16 * KS16;          // padded key count
-    constexpr int NT = 2 * KS16;           // S n-tiles of 8 keys
     extern __shared__ __align__(16) uint8_t wsm[];
     __nv_bfloat16 (*plane)[NK][kPitch] = reinterpret_cast<__nv_bfloat16 (*)[NK][kPitch]>(wsm);   // Khi Klo Vhi Vlo
     float* tbl = reinterpret_cast<float*>(wsm + sizeof(__nv_bfloat16) * 4 * NK * kPitch);       // [(2 ws - 1)^2]
@@ -341,80 +342,91 @@ __global__ void __launch_bounds__(32 * KS16) window_attention_mma_kernel(const f
     __syncthreads();
     if (16 * warp >= N) return;
 
-    // ---- S = Q K^T over all keys ----
-    float s[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
-        uint32_t kh[4], kl[4];
-        const int r = 8 * j + (lane & 7), c = (lane >> 3) * 8;
-        ldsm4(kh, smem_addr(&plane[0][r][c]));
-        ldsm4(kl, smem_addr(&plane[1][r][c]));
-#pragma unroll
-        for (int k2 = 0; k2 < 2; ++k2) {
-            mma16816(s[j], ql[k2], kh[2 * k2], kh[2 * k2 + 1]);   // small terms first
-            mma16816(s[j], qh[k2], kl[2 * k2], kl[2 * k2 + 1]);
-            mma16816(s[j], qh[k2], kh[2 * k2], kh[2 * k2 + 1]);
-        }
-    }
-    // ---- relative position bias, shift mask, exact softmax over the row ----
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int r = e >> 1;
-            const int key = 8 * j + 2 * t + (e & 1);
-            float v = -INFINITY;
-            if (key < N) {
-                const int info = kinfo[key];
-                v = s[j][e] + tbl[bias_row[r] - (info & 0xffff)];
-                if ((info >> 16) != my_region[r]) v += -100.f;
-            }
-            s[j][e] = v;
-            mx[r] = fmaxf(mx[r], v);
-        }
-    float l[2] = {0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-    }
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float p = expf(s[j][e] - mx[e >> 1]);
-            s[j][e] = p;
-            l[e >> 1] += p;
-        }
-    // ---- O = P V ----
+    // ---- key chunks of 16 CH16 keys: S = Q K^T, bias + mask, online softmax (base 2), O += P V ----
+    constexpr int CT = 2 * CH16;           // S n-tiles per chunk
+    constexpr float kLog2e = 1.4426950408889634f;
     float o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll 1
+    for (int c0 = 0; c0 < KS16; c0 += CH16) {
+        const int key0 = 16 * c0;
+        float s[CT][4];
 #pragma unroll
-    for (int kk = 0; kk < KS16; ++kk) {
-        uint32_t ph[4], pl[4];
-        split_pair(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
-        split_pair(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
-        split_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
-        split_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+        for (int j = 0; j < CT; ++j) {
 #pragma unroll
-        for (int np = 0; np < 2; ++np) {
-            uint32_t vh[4], vl[4];
-            const int mi = lane >> 3;
-            const int r = 16 * kk + (mi & 1) * 8 + (lane & 7), c = 16 * np + (mi >> 1) * 8;
-            ldsm4_t(vh, smem_addr(&plane[2][r][c]));
-            ldsm4_t(vl, smem_addr(&plane[3][r][c]));
-            mma16816(o[2 * np], pl, vh[0], vh[1]);
-            mma16816(o[2 * np], ph, vl[0], vl[1]);
-            mma16816(o[2 * np], ph, vh[0], vh[1]);
-            mma16816(o[2 * np + 1], pl, vh[2], vh[3]);
-            mma16816(o[2 * np + 1], ph, vl[2], vl[3]);
-            mma16816(o[2 * np + 1], ph, vh[2], vh[3]);
+            for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+            uint32_t kh[4], kl[4];
+            const int r = key0 + 8 * j + (lane & 7), c = (lane >> 3) * 8;
+            ldsm4(kh, smem_addr(&plane[0][r][c]));
+            ldsm4(kl, smem_addr(&plane[1][r][c]));
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                mma16816(s[j], ql[k2], kh[2 * k2], kh[2 * k2 + 1]);   // small terms first
+                mma16816(s[j], qh[k2], kl[2 * k2], kl[2 * k2 + 1]);
+                mma16816(s[j], qh[k2], kh[2 * k2], kh[2 * k2 + 1]);
+            }
+        }
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < CT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = e >> 1;
+                const int key = key0 + 8 * j + 2 * t + (e & 1);
+                float v = -INFINITY;
+                if (key < N) {
+                    const int info = kinfo[key];
+                    v = s[j][e] + tbl[bias_row[r] - (info & 0xffff)];
+                    if ((info >> 16) != my_region[r]) v += -100.f;
+                    v *= kLog2e;
+                }
+                s[j][e] = v;
+                mx[r] = fmaxf(mx[r], v);
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float mn = fmaxf(m[r], mx[r]);          // finite from the first chunk on (key 0 always exists)
+            const float corr = exp2f(m[r] - mn);           // exp2(-inf) = 0 on the first chunk
+            m[r] = mn;
+            l[r] *= corr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { o[i][2 * r] *= corr; o[i][2 * r + 1] *= corr; }
+        }
+#pragma unroll
+        for (int j = 0; j < CT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = exp2f(s[j][e] - m[e >> 1]);
+                s[j][e] = p;
+                l[e >> 1] += p;
+            }
+#pragma unroll
+        for (int kk = 0; kk < CH16; ++kk) {
+            uint32_t ph[4], pl[4];
+            split_pair(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+            split_pair(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+            split_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+            split_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t vh[4], vl[4];
+                const int mi = lane >> 3;
+                const int r = key0 + 16 * kk + (mi & 1) * 8 + (lane & 7), c = 16 * np + (mi >> 1) * 8;
+                ldsm4_t(vh, smem_addr(&plane[2][r][c]));
+                ldsm4_t(vl, smem_addr(&plane[3][r][c]));
+                mma16816(o[2 * np], pl, vh[0], vh[1]);
+                mma16816(o[2 * np], ph, vl[0], vl[1]);
+                mma16816(o[2 * np], ph, vh[0], vh[1]);
+                mma16816(o[2 * np + 1], pl, vh[2], vh[3]);
+                mma16816(o[2 * np + 1], ph, vl[2], vl[3]);
+                mma16816(o[2 * np + 1], ph, vh[2], vh[3]);
+            }
         }
     }
 #pragma unroll
@@ -438,7 +450,7 @@ __global__ void __launch_bounds__(32 * KS16) window_attention_mma_kernel(const f
     }
 }
 
-template <int KS16>
+template <int KS16, int CH16>
 static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv, const float* qkv_bias, const float* bias_table,
                              float* out, __nv_bfloat16* oh, __nv_bfloat16* ol, int H, int W, int C, int heads, int window,
                              int shift, int nwy, int nwx, float scale) {
@@ -447,13 +459,17 @@ static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv
                             sizeof(int64_t) * NK + sizeof(int) * NK;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(window_attention_mma_kernel<KS16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
+        // 50 KB per CTA: ask for the large shared-memory carve-out so that three CTAs fit an SM (ncu showed the default
+        // carve-out capping the kernel at two, profiles/r01s_ncu_window_attention_mma.json); L1 is not reused here
+        if (cudaFuncSetAttribute(window_attention_mma_kernel<KS16, CH16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(window_attention_mma_kernel<KS16, CH16>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return PVSG_ERR_LAUNCH;
         configured = true;
     }
     const int warps = (N + 15) / 16;
-    window_attention_mma_kernel<KS16><<<grid, 32 * warps, smem, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
+    window_attention_mma_kernel<KS16, CH16><<<grid, 32 * warps, smem, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
                                                                       window, shift, nwy, nwx, scale);
     return pvsg_launch_status();
 }
@@ -524,11 +540,18 @@ extern "C" int pvsg_window_attention(const float* qkv, const float* qkv_bias, co
     __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
     cudaStream_t st = as_stream(stream);
     const int N = window * window;
-    if (impl == 0)
-        return N <= 64 ? launch_window_mma<4>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
-                                              nwy, nwx, scale)
-                       : launch_window_mma<9>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
-                                              nwy, nwx, scale);
+    if (impl == 0) {
+        // key chunk per online-softmax step: 16 keys / 72 registers / three CTAs per SM (default, measured 399 vs 453 us at
+        // stage 0), or PVSG_WINATT_CHUNK=3: 48 keys / 96 registers / two CTAs per SM
+        static const int chunk = [] { const char* e = getenv("PVSG_WINATT_CHUNK"); return e ? atoi(e) : 1; }();
+        if (N <= 64)
+            return launch_window_mma<4, 2>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
+                                           nwy, nwx, scale);
+        return chunk == 1 ? launch_window_mma<9, 1>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window,
+                                                    shift, nwy, nwx, scale)
+                          : launch_window_mma<9, 3>(grid, N, st, qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window,
+                                                    shift, nwy, nwx, scale);
+    }
     if (impl == 2)
         window_attention_kernel<2><<<grid, 96, 0, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads, window, shift,
                                                         nwy, nwx, scale);

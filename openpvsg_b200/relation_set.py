@@ -29,7 +29,7 @@ __all__ = ['PVSGRelationAnnotation', 'PVSGRelationDataset', 'SimpleTracker', 'ge
            'pred_mask_tubes_from_rows', 'calculate_iou', 'convert_to_ranges', 'find_ranges', 'match_from_counts',
            'match_and_process_gt_tubes', 'compact_matching_dict', 'translate_gt_relations', 'process_relations',
            'process_feats', 'process_pairs', 'process_feats_and_relations', 'query_feat_tubes',
-           'build_relation_dict', 'label_maps_from_tubes']
+           'build_relation_dict', 'label_maps_from_tubes', 'overlap_counts', 'load_pickle', 'save_pickle']
 
 _SOURCES = ('vidor', 'epic_kitchen', 'ego4d')
 

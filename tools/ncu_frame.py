@@ -12,9 +12,14 @@ import openpvsg_b200 as pv  # noqa: E402
 from openpvsg_b200 import configs, engine, synthetic as syn  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+swin = len(sys.argv) > 2 and sys.argv[2] == 'swin_b'      # python tools/ncu_frame.py 8 swin_b
 dev = torch.device('cuda:0')
-det = pv.build_detector(configs.mask2former_r50(True))
-det.load_state_dict(syn.mask2former_state_dict(seed=0))
+if swin:
+    det = pv.build_detector(configs.mask2former_swin(True))
+    det.load_state_dict(syn.mask2former_state_dict(seed=0, in_channels=(128, 256, 512, 1024), backbone=dict(configs.SWIN_B)))
+else:
+    det = pv.build_detector(configs.mask2former_r50(True))
+    det.load_state_dict(syn.mask2former_state_dict(seed=0))
 det.to(dev)
 engine.enable_cuda_graph(det)
 meta = syn.frame_meta(720, 1280)
