@@ -274,13 +274,15 @@ def end2end_bench(det, meta, host_frames, batch, dev):
 def run_reference(args, rank):
     if rank != 0:
         return
-    fps, times = cpu_oracle_fps(args.steps, warmup=min(args.warmup, 1))
+    swin = args.backbone == 'swin_b'
+    fps, times = cpu_oracle_fps(args.steps, warmup=min(args.warmup, 1), swin=swin)
     cores = os.cpu_count()
-    line = dict(metric=METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    line = dict(metric=METRIC.replace('R50', 'Swin-B') if swin else METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * float(np.mean(times)), higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload='Mask2Former R50 inference, synthetic 720p clip (BASELINE configs[1])',
-                            frames_per_step=1, note='CPU oracle port of the reference algorithm; mmcv/mmdet '
+                config=dict(workload='Mask2Former Swin-B inference, synthetic 720p clip (backbone of BASELINE configs[2])' if swin
+                            else 'Mask2Former R50 inference, synthetic 720p clip (BASELINE configs[1])',
+                            backbone=args.backbone, frames_per_step=1, note='CPU oracle port of the reference algorithm; mmcv/mmdet '
                             'are not installable offline so the reference itself cannot run'),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port',
                                   sample=f'{args.steps} frame(s) @720p, 1 frame per step, torch CPU fp32, {cores} threads'),

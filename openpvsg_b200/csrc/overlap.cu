@@ -116,8 +116,9 @@ extern "C" int pvsg_tube_overlap(const int32_t* gt, const int32_t* pan, const in
     if (cudaMemsetAsync(counts, 0, (size_t)B * cells * sizeof(int32_t), st) != cudaSuccess) return PVSG_ERR_LAUNCH;
     const int64_t HW = (int64_t)H * W;
     const int64_t strips = (HW + kStrip - 1) / kStrip;
-    // enough CTAs for two waves over the 148 SMs, but no more than the strips need
-    int per_frame = (int)imin64((strips + 255) / 256, (int64_t)((2 * 148 + B - 1) / B));
+    // ~8 CTAs per SM (first version: 2 per SM = 16 warps per SM, 21 % of HBM peak -- too little in flight for a
+    // streaming kernel whose threads serialise on their run atomics), but no more than the strips need
+    int per_frame = (int)imin64((strips + 255) / 256, (int64_t)((8 * 148 + B - 1) / B));
     if (per_frame < 1) per_frame = 1;
     dim3 grid((unsigned)per_frame, (unsigned)B);
     // int4 loads need 16-byte aligned frames

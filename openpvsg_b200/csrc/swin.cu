@@ -219,12 +219,13 @@ constexpr int kPitch = kHeadDim + 8;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// packed conversions (cvt.rn.bf16x2.f32, ALU pipe) as in gemm_tc.cu: hi = rn(x), lo = rn(x - hi)
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
-    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);          // .x (low half) = a
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - h0, b - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(32 * KS16, CH16 == 1 ? 3 : 2) window_attention
     const int tid = threadIdx.x;
     const int span = 2 * ws - 1;
 
-    for (int i = tid; i < span * span; i += blockDim.x) tbl[i] = __ldg(bias_table + (int64_t)i * heads + head);
+    constexpr float kLog2e = 1.4426950408889634f;   // scores are kept in base 2: folded into q and the bias table
+    for (int i = tid; i < span * span; i += blockDim.x) tbl[i] = kLog2e * __ldg(bias_table + (int64_t)i * heads + head);
     for (int tk = tid; tk < NK; tk += blockDim.x) {
         int64_t so = -1;
         int info = 0;
@@ -337,14 +339,13 @@ __global__ void __launch_bounds__(32 * KS16, CH16 == 1 ? 3 : 2) window_attention
             for (int r = 0; r < 2; ++r) {
                 const float* qp = my_src[r] >= 0 ? qkv + my_src[r] * C3 : qkv_bias;
                 const float2 v = __ldg(reinterpret_cast<const float2*>(qp + head * kHeadDim + 16 * ks + 8 * half + 2 * t));
-                split_pair(v.x * scale, v.y * scale, qh[ks][2 * half + r], ql[ks][2 * half + r]);
+                split_pair(v.x * (scale * kLog2e), v.y * (scale * kLog2e), qh[ks][2 * half + r], ql[ks][2 * half + r]);
             }
     __syncthreads();
     if (16 * warp >= N) return;
 
     // ---- key chunks of 16 CH16 keys: S = Q K^T, bias + mask, online softmax (base 2), O += P V ----
     constexpr int CT = 2 * CH16;           // S n-tiles per chunk
-    constexpr float kLog2e = 1.4426950408889634f;
     float o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -381,8 +382,7 @@ __global__ void __launch_bounds__(32 * KS16, CH16 == 1 ? 3 : 2) window_attention
                 if (key < N) {
                     const int info = kinfo[key];
                     v = s[j][e] + tbl[bias_row[r] - (info & 0xffff)];
-                    if ((info >> 16) != my_region[r]) v += -100.f;
-                    v *= kLog2e;
+                    if ((info >> 16) != my_region[r]) v += -100.f * kLog2e;
                 }
                 s[j][e] = v;
                 mx[r] = fmaxf(mx[r], v);

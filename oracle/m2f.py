@@ -565,7 +565,7 @@ def concat_seq(outputs):
     return rows, feat_tubes
 
 
-def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True):
+def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True, backbone=None):
     """Mask2FormerVideoCustomMinVIS.simple_test, models/mask2former_vps/mask2former_min_vis.py:132-231
     (panoptic branch): per-frame heads, MinVIS matching, clip-averaged logits, per-frame fusion."""
     bs, num_frame, three, h, w = ref_img.shape
