@@ -180,8 +180,9 @@ def relset_bench(dev, with_cpu, frames=20, num_gt=32, slots=100):
     (GT object, same-class tube) pair of a frame, here for 12 objects x 4 candidate tubes on one frame."""
     from openpvsg_b200 import ops
     g = torch.Generator().manual_seed(0)
-    gt = torch.randint(0, num_gt, (frames, H // 16, W // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2).int()
-    slot = torch.randint(0, 40, (frames, H // 8, W // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    # blocky label maps with ~1.4e4 (gt, segment) runs per frame -- the run density of real 720p panoptic maps
+    gt = torch.randint(0, num_gt, (frames, H // 80, W // 80), generator=g).repeat_interleave(80, 1).repeat_interleave(80, 2).int()
+    slot = torch.randint(0, 40, (frames, H // 16, W // 64), generator=g).repeat_interleave(16, 1).repeat_interleave(64, 2)
     ids = (torch.arange(slots) % 127 + 1000 * (torch.arange(slots) // 3)).int()
     pan = ids[slot].int()
     seg_info = torch.zeros(frames, 1 + 4 * slots, dtype=torch.int32)

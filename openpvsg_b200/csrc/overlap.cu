@@ -59,9 +59,7 @@ __global__ void __launch_bounds__(256) overlap_kernel(const int32_t* __restrict_
         const int kept = seg_info[0];
         for (int k = 0; k < kept; ++k) {
             const int seg = seg_info[1 + 4 * k + 2];
-            bool dup = false;
-            for (int j = 0; j < n; ++j) dup = dup || ids[j] == seg;
-            if (seg >= 0 && !dup) {
+            if (seg >= 0 && find_slot(hkey, hval, seg, -1) < 0) {   // a stuff class kept by several queries is one slot
                 int h = hash_id(seg);
                 while (hkey[h] != INT_MIN) h = (h + 1) & (kHash - 1);
                 hkey[h] = seg;
@@ -73,10 +71,14 @@ __global__ void __launch_bounds__(256) overlap_kernel(const int32_t* __restrict_
     }
     __syncthreads();
     const int64_t strips = (HW + kStrip - 1) / kStrip;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < strips; s += (int64_t)ctas_per_frame * blockDim.x) {
-        const int64_t base = s * kStrip;
+    // the trip count is uniform over the CTA (strips beyond the map just carry len = 0), so the warp-level
+    // aggregation of the closing run below sees all 32 lanes
+    for (int64_t sb = (int64_t)blockIdx.x * blockDim.x; sb < strips; sb += (int64_t)ctas_per_frame * blockDim.x) {
+        const int64_t base = (sb + threadIdx.x) * kStrip;
         int g_run = INT_MIN, p_run = INT_MIN, cell = 0, len = 0;
-        if (vec && base + kStrip <= HW) {
+        if (base >= HW) {
+            // nothing to read
+        } else if (vec && base + kStrip <= HW) {
             int4 gv[kStrip / 4], pv[kStrip / 4];
 #pragma unroll
             for (int v = 0; v < kStrip / 4; ++v) {
@@ -110,7 +112,11 @@ __global__ void __launch_bounds__(256) overlap_kernel(const int32_t* __restrict_
                 ++len;
             }
         }
-        if (len) atomicAdd(&hist[cell], len);
+        // closing run of every lane: neighbouring strips mostly end in the same (gt, segment) cell -- one atomic per
+        // group of equal cells instead of up to 32 same-address atomics
+        const unsigned grp = __match_any_sync(0xffffffffu, len ? cell : -1 - (int)(threadIdx.x & 31));
+        const int total = __reduce_add_sync(grp, len);
+        if (total && (threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[cell], total);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {

@@ -29,7 +29,7 @@ __all__ = ['PVSGRelationAnnotation', 'PVSGRelationDataset', 'SimpleTracker', 'ge
            'pred_mask_tubes_from_rows', 'calculate_iou', 'convert_to_ranges', 'find_ranges', 'match_from_counts',
            'match_and_process_gt_tubes', 'compact_matching_dict', 'translate_gt_relations', 'process_relations',
            'process_feats', 'process_pairs', 'process_feats_and_relations', 'query_feat_tubes',
-           'build_relation_dict', 'label_maps_from_tubes', 'overlap_counts', 'load_pickle', 'save_pickle']
+           'build_relation_dict', 'label_maps_from_tubes', 'overlap_counts', 'gather_counts', 'load_pickle', 'save_pickle']
 
 _SOURCES = ('vidor', 'epic_kitchen', 'ego4d')
 
@@ -208,6 +208,25 @@ def overlap_counts(gt_maps, pan_maps, seg_info, num_gt, device='cuda', chunk=64)
             return x.to(device=device, dtype=torch.int32).contiguous()
         out.append(ops.tube_overlap(dev(gt_maps), dev(pan_maps), dev(seg_info), num_gt).cpu())
     return torch.cat(out, 0).numpy()
+
+
+def gather_counts(local_counts, num_frames, device='cpu'):
+    """Multi-GPU form: ranks own contiguous frame blocks (``tubes.shard_frames``) and compute the overlap counts of
+    their own frames; the small count tensors ([frames, G+1, Q+1] int32, ~13 KB per frame at G = 32) are all-gathered
+    (NCCL for device tensors, gloo on CPU) so that every rank can run the matching over the whole clip.  Maps and
+    masks are never exchanged.  Single process: returns the input."""
+    import torch
+    import torch.distributed as dist
+    counts = torch.as_tensor(np.asarray(local_counts)).to(device=device, dtype=torch.int32)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return counts.cpu().numpy()
+    ws = dist.get_world_size()
+    per = (num_frames + ws - 1) // ws
+    pad = torch.zeros((per,) + tuple(counts.shape[1:]), dtype=torch.int32, device=device)
+    pad[:counts.shape[0]] = counts
+    parts = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad)
+    return torch.cat(parts, 0)[:num_frames].cpu().numpy()
 
 
 def match_and_process_gt_tubes(vid, pvsg_dataset, pred_mask_tubes, data_dir='./data', gt_maps=None, device='cuda'):

@@ -142,6 +142,45 @@ def test_no_cpu_path_for_counts(clip):
         rs.overlap_counts(clip['gt'], clip['pan'], clip['seg_info'], NUM_GT, device='cpu')
 
 
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    c = fx.make_clip()
+    lo, hi = tubes.shard_frames(c['T'], world, rank)
+    local = orl.joint_histogram(c['gt'][lo:hi], c['pan'][lo:hi], c['seg_info'][lo:hi], NUM_GT)   # this rank's frames only
+    counts = rs.gather_counts(local, c['T'])
+    linker = fx.link(c)
+    info = rs.PVSGRelationAnnotation(fx.make_anno())[fx.VID]
+    rd = rs.build_relation_dict(linker, counts, fx.frame_tube_ids(c, linker), info['objects'], info['relations'])
+    q.put((rank, counts.shape, [(r['subject_index'], r['object_index'], r['relation'], r['relation_span'].tolist())
+                                for r in rd['relations']]))
+    dist.destroy_process_group()
+
+
+def test_sharded_counts_world2_gloo(golden):
+    """N > 1: every rank computes the overlap counts of its own frame block; an all-gather of the counts (not of the
+    maps) gives every rank the reference's relation set."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    want = [(r['subject_index'], r['object_index'], r['relation'], r['relation_span'])
+            for r in golden['relation_dict']['relations']]
+    for rank, shape, rels in got:
+        assert tuple(shape) == (40, NUM_GT + 1, fx.Q + 1)
+        assert rels == want
+
+
 # ------------------------------------------------------------------------------ GPU ----------
 @pytest.mark.gpu
 def test_tube_overlap_kernel_bit_exact(golden, clip):
