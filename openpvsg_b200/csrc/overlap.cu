@@ -40,10 +40,8 @@ __global__ void __launch_bounds__(256) overlap_kernel(const int32_t* __restrict_
                                                       const int32_t* __restrict__ seg_info, int Q, int64_t HW, int G,
                                                       int ctas_per_frame, int vec, int32_t* __restrict__ counts) {
     extern __shared__ int32_t hist[];     // [(G + 1), (Q + 1)]
-    __shared__ int ids[1024];
     __shared__ int hkey[kHash];            // open-addressing table: panoptic id -> slot (load factor <= 0.5)
     __shared__ short hval[kHash];
-    __shared__ int nseg;
     const int b = blockIdx.y;
     const int cols = Q + 1;
     const int cells = (G + 1) * cols;
@@ -64,10 +62,9 @@ __global__ void __launch_bounds__(256) overlap_kernel(const int32_t* __restrict_
                 while (hkey[h] != INT_MIN) h = (h + 1) & (kHash - 1);
                 hkey[h] = seg;
                 hval[h] = (short)n;
-                ids[n++] = seg;
+                ++n;
             }
         }
-        nseg = n;
     }
     __syncthreads();
     const int64_t strips = (HW + kStrip - 1) / kStrip;
