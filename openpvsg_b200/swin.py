@@ -115,6 +115,8 @@ class SwinTransformer(_Prepared):
             raise NotImplementedError('SwinTransformer: absolute position embedding / qk_scale / custom strides')
         if (act_cfg or {}).get('type', 'GELU') != 'GELU' or (norm_cfg or {}).get('type', 'LN') != 'LN':
             raise NotImplementedError('SwinTransformer: GELU + LN only')
+        if not qkv_bias:
+            raise NotImplementedError('SwinTransformer: qkv_bias=False (the padded window positions read the qkv bias)')
         if any(embed_dims * 2 ** i != h * 32 for i, h in enumerate(num_heads)) or window_size > 12:
             raise NotImplementedError('SwinTransformer: head dim 32 and window <= 12 (every published Swin variant)')
         self.out_indices = tuple(out_indices)
