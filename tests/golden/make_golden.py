@@ -411,15 +411,41 @@ def golden_full_frames():
             qfeats=np.stack([np.asarray(res['query_feats'][k][0]) for k in keys]) if keys else np.zeros((0, 256)))
         print(name, 'segments', keys, 'near-zero mask logits per layer', near)
 
+# ----------------------------------------------------------------------------------
+# Swin-B stage outputs at the BASELINE full size (ORACLE-derived, like frame_720x1280.npz: the reference has no
+# Swin code; oracle/swin.py is pinned to torchvision in tests/test_swin.py).  Run: python tests/golden/make_golden.py swin
+# ----------------------------------------------------------------------------------
+def golden_swin_b_720p():
+    from openpvsg_b200 import configs
+    from oracle import swin as osw
+    g = torch.Generator().manual_seed(5)
+    sd = syn.swin_state_dict(g, prefix='', **configs.SWIN_B)
+    img = syn.synthetic_frame(21, 720, 1280)[None]
+    with torch.no_grad():
+        outs = osw.swin_forward(sd, img, **configs.SWIN_B)
+    data = dict(input_checksum=np.float64(checksum(img)), weight_checksum=np.float64(checksum(*[v.float() for v in sd.values()])))
+    for i, o in enumerate(outs):
+        data[f'stage{i}_shape'] = np.array(o.shape)
+        data[f'stage{i}_sub'] = o[0, ::8, ::4, ::4].numpy().copy()          # every 8th channel, every 4th pixel
+        data[f'stage{i}_abs_sum'] = np.float64(o.double().abs().sum().item())
+    np.savez_compressed(os.path.join(HERE, 'swin_b_720x1280.npz'), **data)
+    print('swin_b_720x1280.npz', {k: (v.shape if hasattr(v, 'shape') else v) for k, v in data.items()})
+
+
 
 if __name__ == '__main__':
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == 'frames':
         golden_full_frames()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'swin':
+        golden_swin_b_720p()
+        sys.exit(0)
     golden_relation()
     golden_m2f()
     golden_full_frames()
+    golden_swin_b_720p()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
+

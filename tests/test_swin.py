@@ -80,6 +80,32 @@ def test_swin_b_builds_and_loads_strictly():
         det.backbone(torch.zeros(1, 3, 96, 96))  # CPU tensor: no fallback
 
 
+def _golden_720p():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'swin_b_720x1280.npz'))
+
+
+def _swin_b_720p_inputs():
+    g = torch.Generator().manual_seed(5)
+    sd = syn.swin_state_dict(g, prefix='', **configs.SWIN_B)
+    img = syn.synthetic_frame(21, 720, 1280)[None]
+    gold = _golden_720p()
+    assert float(img.double().abs().sum()) == pytest.approx(float(gold['input_checksum']), rel=1e-9), 'frame RNG drifted'
+    assert float(sum(v.double().abs().sum() for v in sd.values())) == pytest.approx(float(gold['weight_checksum']), rel=1e-9)
+    return sd, img, gold
+
+
+def test_swin_b_720p_golden_matches_oracle():
+    """The committed full-size fixture (oracle-derived, tests/golden/make_golden.py swin) is what the oracle computes."""
+    sd, img, gold = _swin_b_720p_inputs()
+    with torch.no_grad():
+        outs = osw.swin_forward(sd, img, **configs.SWIN_B)
+    for i, o in enumerate(outs):
+        assert list(o.shape) == gold[f'stage{i}_shape'].tolist()
+        assert np.abs(o[0, ::8, ::4, ::4].numpy() - gold[f'stage{i}_sub']).max() < 1e-5
+        assert float(o.double().abs().sum()) == pytest.approx(float(gold[f'stage{i}_abs_sum']), rel=1e-6)
+
+
 # ----------------------------------------------------------------------------- GPU ----------
 def _close(a, b, tol, name):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
@@ -205,3 +231,54 @@ def test_swin_b_detector_features_and_forward():
     pan = res[0][0]['pan_results']
     assert pan.shape == (H, W) and pan.dtype in (np.int32, np.int64)
     assert set(res[0][0]['query_feats']) <= set(np.unique(pan).tolist())
+
+
+@pytest.mark.gpu
+def test_swin_b_full_size_720p_vs_golden():
+    """BASELINE full size (720 x 1280 -> 184 x 320 patches, window padding on every level): all four stage outputs of
+    the CUDA Swin-B against the committed oracle-derived fixture (sub-sampled values + whole-tensor sums)."""
+    sd, img, gold = _swin_b_720p_inputs()
+    net = pv.build_backbone(dict(type='SwinTransformer', **configs.SWIN_B))
+    assert net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        outs = net.to('cuda')(img.cuda())
+    for i, o in enumerate(outs):
+        assert list(o.shape) == gold[f'stage{i}_shape'].tolist()
+        sub = o[0, ::8, ::4, ::4].float().cpu().numpy()
+        want = gold[f'stage{i}_sub']
+        err = np.abs(sub - want).max()
+        assert err <= 1e-3 * max(1.0, np.abs(want).max()), f'stage {i}: max abs err {err:.3e}'
+        assert np.abs(sub - want).mean() < 5e-5
+        assert float(o.double().abs().sum()) == pytest.approx(float(gold[f'stage{i}_abs_sum']), rel=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shift', [0, 6])
+def test_window_attention_full_size_properties(shift):
+    """Stage-0 size of a 720p frame (184 x 320 tokens, 4 heads, window 12), no oracle: the output is linear in V,
+    rows of a window that see identical keys are convex combinations of V (bounded by its extremes), and a constant V
+    comes back unchanged (softmax rows sum to one, also for padded / masked windows)."""
+    from openpvsg_b200 import ops
+    g = torch.Generator().manual_seed(shift)
+    B, H, W, heads = 1, 184, 320, 4
+    C = 32 * heads
+    qkv = torch.randn(B, H, W, 3 * C, generator=g).cuda()
+    bias = torch.zeros(3 * C).cuda()          # zero bias: padded positions contribute V = 0 rows
+    table = torch.randn(23 * 23, heads, generator=g).cuda()
+    v2 = torch.randn(B, H, W, C, generator=g).cuda()
+    a = ops.window_attention(qkv, bias, table, heads, 12, shift)
+    q2 = qkv.clone()
+    q2[..., 2 * C:] = v2
+    b = ops.window_attention(q2, bias, table, heads, 12, shift)
+    q3 = qkv.clone()
+    q3[..., 2 * C:] = 0.5 * qkv[..., 2 * C:] - 2.0 * v2
+    c = ops.window_attention(q3, bias, table, heads, 12, shift)
+    assert (c - (0.5 * a - 2.0 * b)).abs().max().item() < 2e-4
+    assert a.abs().max().item() <= qkv[..., 2 * C:].abs().max().item() + 1e-4
+    # constant V with a matching bias row (so padded positions carry the same value): output == that constant
+    q4 = qkv.clone()
+    q4[..., 2 * C:] = 1.25
+    bias4 = bias.clone()
+    bias4[2 * C:] = 1.25
+    d = ops.window_attention(q4, bias4, table, heads, 12, shift)
+    assert (d - 1.25).abs().max().item() < 1e-4
