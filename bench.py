@@ -112,7 +112,9 @@ def make_frames(n_distinct, rank):
 # --------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle on the host cores
 # --------------------------------------------------------------------------------------
-SWIN_SD = dict(in_channels=(128, 256, 512, 1024),
+# mask_shift: the synthetic head is calibrated per backbone so that the fusion head keeps a realistic set of segments
+# (Swin-B features with the R50 value give half-plane masks and an all-void panoptic map; 32 -> ~10 segments per frame)
+SWIN_SD = dict(in_channels=(128, 256, 512, 1024), mask_shift=32.0,
                backbone=dict(embed_dims=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32), window_size=12))
 
 

@@ -101,12 +101,15 @@ def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_re
 
 
 @torch.no_grad()
-def relation_set_clip(detector, frames, meta, gt_maps, object_list, gt_relations, batch=8, max_segments=100):
+def relation_set_clip(detector, frames, meta, gt_maps, object_list, gt_relations, batch=8, max_segments=100, num_frames=None):
     """tools/prepare_query_tube_vps.py:170-240 + tools/prepare_rel_set.py:24-52 for one video, in memory: VPS
     forward -> tube linking -> overlap of every frame's panoptic map with its ground-truth instance-id map
     (``ops.tube_overlap``, one device pass per batch of frames) -> matched tubes -> the ``relations.pickle``
     dictionary that ``relation_set.PVSGRelationDataset(memory=...)`` serves.  gt_maps: [T,H,W] integer maps at the
     frames' ``ori_shape``; object_list / gt_relations as ``PVSGRelationAnnotation.__getitem__`` returns them.
+    Under torch.distributed (world size > 1) ``frames`` / ``gt_maps`` are this rank's contiguous block
+    (``tubes.shard_frames``) and ``num_frames`` the clip length: the kept entries and the overlap counts are
+    all-gathered (``relation_set.assemble_sharded``) and every rank returns the clip-wide result.
     Returns dict(linker, counts [T,G+1,Q+1], frame_tube_ids, relation_dict)."""
     from . import ops
     device = next(detector.parameters()).device
@@ -139,5 +142,11 @@ def relation_set_clip(detector, frames, meta, gt_maps, object_list, gt_relations
     vps_clip(detector, frames, meta, batch, consume=consume)
     flush()
     counts = np.stack(counts) if counts else np.zeros((0, num_gt + 1, max_segments + 1), np.int32)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        entries = [(ids, np.stack([linker.feat_tubes[linker.object_list.index(i) + 1][t]['query_feat'] for i in ids])
+                    if ids else np.zeros((0, 256), np.float32)) for t, ids in enumerate(linker.frame_seg_ids)]
+        return relation_set.assemble_sharded(entries, counts, num_frames, object_list, gt_relations, device=device,
+                                             max_segments=max_segments)
     rd = relation_set.build_relation_dict(linker, counts, slot_tubes, object_list, gt_relations)
     return dict(linker=linker, counts=counts, frame_tube_ids=slot_tubes, relation_dict=rd)

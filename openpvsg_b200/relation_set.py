@@ -29,7 +29,7 @@ __all__ = ['PVSGRelationAnnotation', 'PVSGRelationDataset', 'SimpleTracker', 'ge
            'pred_mask_tubes_from_rows', 'calculate_iou', 'convert_to_ranges', 'find_ranges', 'match_from_counts',
            'match_and_process_gt_tubes', 'compact_matching_dict', 'translate_gt_relations', 'process_relations',
            'process_feats', 'process_pairs', 'process_feats_and_relations', 'query_feat_tubes',
-           'build_relation_dict', 'label_maps_from_tubes', 'overlap_counts', 'gather_counts', 'load_pickle', 'save_pickle']
+           'build_relation_dict', 'label_maps_from_tubes', 'overlap_counts', 'gather_counts', 'assemble_sharded', 'load_pickle', 'save_pickle']
 
 _SOURCES = ('vidor', 'epic_kitchen', 'ego4d')
 
@@ -227,6 +227,19 @@ def gather_counts(local_counts, num_frames, device='cpu'):
     parts = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(parts, pad)
     return torch.cat(parts, 0)[:num_frames].cpu().numpy()
+
+
+def assemble_sharded(frame_entries, local_counts, num_frames, object_list, gt_relations, device='cpu', max_segments=100):
+    """The N > 1 tail of ``end2end.relation_set_clip``: every rank passes the kept (panoptic ids, query features) of
+    its own contiguous frame block and the overlap counts of those frames.  Two small all-gathers (entries:
+    ``tubes.gather_and_link``; counts: ``gather_counts``) give every rank the clip-wide tubes and matching; panoptic
+    maps, GT maps and masks stay on the rank that owns the frame.  Returns dict(linker, counts, frame_tube_ids,
+    relation_dict), identical on every rank and identical to the single-process result."""
+    linker = tubes.gather_and_link(frame_entries, num_frames, max_segments=max_segments, device=device)
+    counts = gather_counts(local_counts, num_frames, device=device)
+    slot_tubes = linker.frame_tube_ids()
+    rd = build_relation_dict(linker, counts, slot_tubes, object_list, gt_relations)
+    return dict(linker=linker, counts=counts, frame_tube_ids=slot_tubes, relation_dict=rd)
 
 
 def match_and_process_gt_tubes(vid, pvsg_dataset, pred_mask_tubes, data_dir='./data', gt_maps=None, device='cuda'):

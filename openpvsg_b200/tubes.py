@@ -146,6 +146,7 @@ class TubeLinker:
         self.object_list = []
         self.feat_tubes = {}
         self.rows = []          # (frame (1-based), tube id, class id, h, w, rle string)
+        self.frame_seg_ids = []  # per frame: kept panoptic ids in slot order (what pvsg_rle_events / pvsg_tube_overlap index)
         self.num_frames = 0
 
     def add_frame(self, seg_ids, feats, pan=None, rle=None, hw=None):
@@ -153,6 +154,8 @@ class TubeLinker:
         feats: matching [n,256] array; pan: optional int32 [H,W] map (-> masks.txt rows), or
         rle: {segment id: RLE string} from the device encoder together with hw = (H, W)."""
         frame_id = self.num_frames
+        seg_ids = [int(i) for i in seg_ids]
+        self.frame_seg_ids.append(seg_ids)
         for ins_id, feat in zip(seg_ids, feats):
             ins_id = int(ins_id)
             if ins_id not in self.object_list:
@@ -177,6 +180,10 @@ class TubeLinker:
             for f, d in frames.items():
                 out[tid - 1, f] = d['query_feat']
         return out
+
+    def frame_tube_ids(self):
+        """Per frame: tube id of every slot (slot = position of a kept panoptic id in the frame's result)."""
+        return [[self.object_list.index(i) + 1 for i in ids] for ids in self.frame_seg_ids]
 
     def masks_txt(self):
         return ''.join(f'{fr} {tid} {cid} {h} {w} {rle}\n' for fr, tid, cid, h, w, rle in self.rows)

@@ -148,18 +148,20 @@ def _shard_worker(rank, world, port, q):
     c = fx.make_clip()
     lo, hi = tubes.shard_frames(c['T'], world, rank)
     local = orl.joint_histogram(c['gt'][lo:hi], c['pan'][lo:hi], c['seg_info'][lo:hi], NUM_GT)   # this rank's frames only
-    counts = rs.gather_counts(local, c['T'])
-    linker = fx.link(c)
+    entries = [(c['seg_ids'][t], c['feats'][t]) for t in range(lo, hi)]                          # and its kept entries
     info = rs.PVSGRelationAnnotation(fx.make_anno())[fx.VID]
-    rd = rs.build_relation_dict(linker, counts, fx.frame_tube_ids(c, linker), info['objects'], info['relations'])
+    out = rs.assemble_sharded(entries, local, c['T'], info['objects'], info['relations'], max_segments=fx.Q)
+    counts, rd = out['counts'], out['relation_dict']
+    assert out['frame_tube_ids'] == fx.frame_tube_ids(c, fx.link(c))
     q.put((rank, counts.shape, [(r['subject_index'], r['object_index'], r['relation'], r['relation_span'].tolist())
                                 for r in rd['relations']]))
     dist.destroy_process_group()
 
 
 def test_sharded_counts_world2_gloo(golden):
-    """N > 1: every rank computes the overlap counts of its own frame block; an all-gather of the counts (not of the
-    maps) gives every rank the reference's relation set."""
+    """N > 1 (relation_set.assemble_sharded, the tail of end2end.relation_set_clip): every rank passes the kept entries
+    and the overlap counts of its own frame block; two all-gathers (entries, counts -- never maps) give every rank the
+    reference's relation set."""
     import socket
     import torch.multiprocessing as mp
     s = socket.socket()

@@ -16,7 +16,8 @@ swin = len(sys.argv) > 2 and sys.argv[2] == 'swin_b'      # python tools/ncu_fra
 dev = torch.device('cuda:0')
 if swin:
     det = pv.build_detector(configs.mask2former_swin(True))
-    det.load_state_dict(syn.mask2former_state_dict(seed=0, in_channels=(128, 256, 512, 1024), backbone=dict(configs.SWIN_B)))
+    det.load_state_dict(syn.mask2former_state_dict(seed=0, in_channels=(128, 256, 512, 1024), mask_shift=32.0,
+                                                   backbone=dict(configs.SWIN_B)))
 else:
     det = pv.build_detector(configs.mask2former_r50(True))
     det.load_state_dict(syn.mask2former_state_dict(seed=0))
