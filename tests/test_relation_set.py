@@ -142,6 +142,41 @@ def test_no_cpu_path_for_counts(clip):
         rs.overlap_counts(clip['gt'], clip['pan'], clip['seg_info'], NUM_GT, device='cpu')
 
 
+class _FakeDetector:
+    def parameters(self):
+        yield torch.zeros(1)
+
+
+def _mock_device_side(monkeypatch_setattr, c, lo, hi):
+    """end2end.relation_set_clip with the device side replaced: frames come from the fixture, the overlap counts from
+    the oracle -- what remains is exactly the host logic of the function (hand-over, slot order, batching, gathers)."""
+    from openpvsg_b200 import end2end, ops
+
+    def fake_vps_clip(det, frames, meta, batch, consume=None, rle=True):
+        for t in range(lo, hi):
+            consume(dict(pan_results=c['pan'][t],
+                         query_feats={int(s): [torch.as_tensor(c['feats'][t][k])] for k, s in enumerate(c['seg_ids'][t])}))
+
+    monkeypatch_setattr(end2end, 'vps_clip', fake_vps_clip)
+    monkeypatch_setattr(ops, 'tube_overlap',
+                        lambda gt, pan, si, n: torch.as_tensor(orl.joint_histogram(gt.numpy(), pan.numpy(), si.numpy(), n)))
+    return end2end
+
+
+def _relations(rd):
+    return [(r['subject_index'], r['object_index'], r['relation'], np.asarray(r['relation_span']).tolist()) for r in rd['relations']]
+
+
+def test_relation_set_clip_host_logic(golden, clip, monkeypatch):
+    e2e = _mock_device_side(monkeypatch.setattr, clip, 0, clip['T'])
+    info = rs.PVSGRelationAnnotation(fx.make_anno())[fx.VID]
+    out = e2e.relation_set_clip(_FakeDetector(), None, None, clip['gt'], info['objects'], info['relations'], batch=7,
+                                max_segments=fx.Q)
+    assert _relations(out['relation_dict']) == _relations(golden['relation_dict'])
+    assert out['counts'].shape == (clip['T'], NUM_GT + 1, fx.Q + 1)
+    assert out['frame_tube_ids'] == out['linker'].frame_tube_ids() == fx.frame_tube_ids(clip, clip['linker'])
+
+
 def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
@@ -153,6 +188,11 @@ def _shard_worker(rank, world, port, q):
     out = rs.assemble_sharded(entries, local, c['T'], info['objects'], info['relations'], max_segments=fx.Q)
     counts, rd = out['counts'], out['relation_dict']
     assert out['frame_tube_ids'] == fx.frame_tube_ids(c, fx.link(c))
+    # the same through end2end.relation_set_clip's distributed branch (device side mocked)
+    e2e = _mock_device_side(setattr, c, lo, hi)
+    out2 = e2e.relation_set_clip(_FakeDetector(), None, None, c['gt'][lo:hi], info['objects'], info['relations'], batch=7,
+                                 max_segments=fx.Q, num_frames=c['T'])
+    assert _relations(out2['relation_dict']) == _relations(rd) and np.array_equal(out2['counts'], counts)
     q.put((rank, counts.shape, [(r['subject_index'], r['object_index'], r['relation'], r['relation_span'].tolist())
                                 for r in rd['relations']]))
     dist.destroy_process_group()
