@@ -86,7 +86,8 @@ def ordered(d):
     return [[k, v] for k, v in d.items()]
 
 
-def main():
+def setup_reference_modules():
+    """pycocotools stub + the reference's utils/relation_matching.py and datasets/datasets/pvsg_relation.py by path."""
     pm = types.ModuleType('pycocotools')
     pm.mask = types.ModuleType('pycocotools.mask')
     pm.mask.decode = _decode
@@ -97,21 +98,31 @@ def main():
     utils_pkg.relation_matching = rm
     sys.modules['utils'] = utils_pkg
     ds = _load('ref_pvsg_relation', f'{REF}/datasets/datasets/pvsg_relation.py')
+    return rm, ds
 
+
+def write_clip_files(tmp, clip, linker):
+    """The files the reference flow reads: pvsg.json, GT PNGs, masks.txt, query_feats.pickle."""
     from PIL import Image
+    data_dir, work_dir = os.path.join(tmp, 'data'), os.path.join(tmp, 'work')
+    os.makedirs(os.path.join(data_dir, 'vidor', 'masks', fx.VID))
+    os.makedirs(os.path.join(work_dir, fx.VID, 'quantitive'))
+    json.dump(fx.make_anno(), open(os.path.join(data_dir, 'pvsg.json'), 'w'))
+    for t in range(clip['T']):
+        Image.fromarray(clip['gt'][t].astype(np.uint8)).save(
+            os.path.join(data_dir, 'vidor', 'masks', fx.VID, f'{t:04d}.png'))
+    open(os.path.join(work_dir, fx.VID, 'quantitive', 'masks.txt'), 'w').write(linker.masks_txt())
+    pickle.dump(rs.query_feat_tubes(linker), open(os.path.join(work_dir, fx.VID, 'query_feats.pickle'), 'wb'))
+    return data_dir, work_dir
+
+
+def main():
+    rm, ds = setup_reference_modules()
     clip = fx.make_clip()
     linker = fx.link(clip)
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        data_dir, work_dir = os.path.join(tmp, 'data'), os.path.join(tmp, 'work')
-        os.makedirs(os.path.join(data_dir, 'vidor', 'masks', fx.VID))
-        os.makedirs(os.path.join(work_dir, fx.VID, 'quantitive'))
-        json.dump(fx.make_anno(), open(os.path.join(data_dir, 'pvsg.json'), 'w'))
-        for t in range(clip['T']):
-            Image.fromarray(clip['gt'][t].astype(np.uint8)).save(
-                os.path.join(data_dir, 'vidor', 'masks', fx.VID, f'{t:04d}.png'))
-        open(os.path.join(work_dir, fx.VID, 'quantitive', 'masks.txt'), 'w').write(linker.masks_txt())
-        pickle.dump(rs.query_feat_tubes(linker), open(os.path.join(work_dir, fx.VID, 'query_feats.pickle'), 'wb'))
+        data_dir, work_dir = write_clip_files(tmp, clip, linker)
 
         # ---- tools/prepare_rel_set.py:24-52, the reference's own calls
         pvsg_dataset = rm.PVSGRelationAnnotation(os.path.join(data_dir, 'pvsg.json'), 'train')
