@@ -3,7 +3,7 @@
 tests/golden/releval.json comes from the reference's own ``tools/rel_test.py::evaluate`` run on CPU with the
 reference's relation-head classes, metrics, dataset and a torch DataLoader (tests/golden/make_golden_releval.py).
 CPU: ``rel_eval.evaluate`` with the oracle forward reproduces every number.  GPU: the same call through the CUDA
-relation head (passes on a B200: gpurun_out/s54_releval.log of round 1).  File named to sort last: it was the round's last
+relation head (passes on a B200: profiles/r01u_gpu_test_logs.txt).  File named to sort last: it was the round's last
 addition."""
 import json
 import os
