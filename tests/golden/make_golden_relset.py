@@ -116,9 +116,9 @@ def write_clip_files(tmp, clip, linker):
     return data_dir, work_dir
 
 
-def main():
+def main(variant='base', out_name='relset.json'):
     rm, ds = setup_reference_modules()
-    clip = fx.make_clip()
+    clip = fx.make_clip(variant=variant)
     linker = fx.link(clip)
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
@@ -169,7 +169,7 @@ def main():
         out['find_ranges'] = [[fr, rm.find_ranges(fr)] for fr in ([0, 1, 2, 3, 4], [0, 5, 11, 12, 30], [7])]
         out['checksum'] = float(np.abs(np.concatenate([f.ravel() for f in clip['feats']])).sum()
                                 + clip['gt'].sum() + clip['pan'].sum())
-    json.dump(out, open(os.path.join(HERE, 'relset.json'), 'w'), indent=0)
+    json.dump(out, open(os.path.join(HERE, out_name), 'w'), indent=0)
     print('matching:', out['matching'])
     print('compact:', out['compact'])
     print('pred_relations:', out['pred_relations'])
@@ -178,3 +178,4 @@ def main():
 
 if __name__ == '__main__':
     main()
+    main('gaps', 'relset_gaps.json')

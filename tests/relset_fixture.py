@@ -20,8 +20,13 @@ def _boxes(t):
     }
 
 
-def make_clip(T=40, H=48, W=64, seed=0):
+def make_clip(T=40, H=48, W=64, seed=0, variant='base'):
+    """variant 'base': every object predicted in (almost) every frame.  variant 'gaps': the edge cases of the matching /
+    compaction rules -- frames without any kept segment, an object whose prediction comes and goes in stretches
+    separated by more than 5 frames (find_ranges splits), a second tube for the same object (list-of-ranges form), a tube
+    matched on fewer than 5 frames (dropped), and a GT object that is never predicted."""
     rng = np.random.default_rng(seed)
+    gaps = variant == 'gaps'
     gt = np.zeros((T, H, W), np.int32)
     pan = np.full((T, H, W), 126, np.int32)            # void label of the panoptic head
     seg_info = np.zeros((T, 1 + 4 * Q), np.int32)
@@ -29,9 +34,15 @@ def make_clip(T=40, H=48, W=64, seed=0):
     for t in range(T):
         gt[t, H // 2:] = 5                             # stuff object 'floor' (id 5)
         pan[t, H // 2 + (t % 3 == 0):] = 3             # stuff class 3 ('floor'), a row off every third frame
+        if gaps and t in (10, 11, 12):
+            pan[t] = 126
         rows = [(0, 3, 3)]                             # (query, class, segment id)
+        empty = gaps and t in (10, 11, 12)              # the detector kept nothing in these frames
         for oid, (cls, y0, x0, h, w) in _boxes(t).items():
             gt[t, y0:y0 + h, x0:x0 + w] = oid
+            if empty or (gaps and oid == 2 and not (t < 7 or 14 <= t < 21 or 28 <= t < 35)) \
+                    or (gaps and oid == 4 and not (3 <= t < 7)) or (gaps and oid == 3):
+                continue                                 # 2: three stretches; 4: four frames only; 3: never predicted
             # prediction: shifted / shrunk copy; object 1 is lost for frames 14..21 and comes back as a NEW
             # instance id (two tubes for one GT object); the ball is badly localised on odd frames
             if oid == 1 and 14 <= t < 22:

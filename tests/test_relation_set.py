@@ -86,6 +86,26 @@ def test_flow_matches_reference_cpu(golden, clip):
     _check_flow(golden, clip, counts)
 
 
+def test_flow_matches_reference_cpu_gaps_variant():
+    """Edge cases of the matching / compaction rules (tests/relset_fixture.py variant 'gaps'): frames without any
+    kept segment, a prediction that comes and goes, a tube matched on fewer than 5 frames (dropped), a GT object
+    that is never predicted, relations whose span shrinks below 3 frames (dropped) -- against the reference's outputs."""
+    golden = json.load(open(os.path.join(HERE, 'golden', 'relset_gaps.json')))
+    c = fx.make_clip(variant='gaps')
+    cs = float(np.abs(np.concatenate([f.ravel() for f in c['feats']])).sum() + c['gt'].sum() + c['pan'].sum())
+    assert cs == pytest.approx(golden['checksum'], rel=1e-9)
+    assert any(len(ids) == 0 for ids in c['seg_ids'])
+    c['linker'] = fx.link(c)
+    counts = orl.joint_histogram(c['gt'], c['pan'], c['seg_info'], NUM_GT)
+    _check_flow(golden, c, counts)
+    tubes_ = rs.pred_mask_tubes_from_rows(c['linker'].rows)
+    got = [[tid, v['cid'], [list(m.keys())[0] for m in v['mask']], [int(list(m.values())[0].sum()) for m in v['mask']]]
+           for tid, v in tubes_.items()]
+    assert got == golden['pred_mask_tubes']
+    assert len(golden['relation_dict']['relations']) < len(golden['pred_relations'])      # the >= 3 frames rule fired
+    assert len(golden['compact']) < len(golden['matching'])                              # the >= 5 frames rule fired
+
+
 def test_oracle_counts_are_the_reference_ious(clip):
     """Pins the oracle's histogram to calculate_iou on decoded masks (what the reference evaluates)."""
     counts = orl.joint_histogram(clip['gt'], clip['pan'], clip['seg_info'], NUM_GT).astype(np.int64)
