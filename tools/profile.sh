@@ -24,3 +24,13 @@ full msda msda_group_kernel 3 python tools/kbench.py --iters 1 --batch 8 --only 
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_mma_kernel -s 8 -c 1 \
     -o gpurun_out/${TAG}_prof_attn -f python tools/ncu_frame.py 8 > gpurun_out/${TAG}_prof_attn.log 2>&1
 ls -la gpurun_out/ | grep ${TAG}
+# (4) Swin-B backbone (bench.py --backbone swin_b): launch list of one 8-frame replay, window-attention and
+#     overlap-kernel captures (profiles/r01s_*, r01u_*):
+#   python tools/ncu_summary.py launches gpurun_out/${TAG}_swin_launches.csv profiles/${TAG}_swin_b_launches_graph_b8.json "<note>"
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file gpurun_out/${TAG}_swin_launches.csv python tools/ncu_frame.py 8 swin_b > gpurun_out/${TAG}_swin_ncu_frame.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:window_attention_mma -s 3 -c 1 \
+    -o gpurun_out/${TAG}_prof_winatt -f python tools/swin_time.py 4 > gpurun_out/${TAG}_prof_winatt.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:overlap_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_overlap -f \
+    python -c "import bench, torch; bench.relset_bench(torch.device('cuda'), False)" > gpurun_out/${TAG}_prof_overlap.log 2>&1
+ls -la gpurun_out/ | grep ${TAG}
