@@ -119,6 +119,9 @@ class SwinTransformer(_Prepared):
             raise NotImplementedError('SwinTransformer: qkv_bias=False (the padded window positions read the qkv bias)')
         if any(embed_dims * 2 ** i != h * 32 for i, h in enumerate(num_heads)) or window_size > 12:
             raise NotImplementedError('SwinTransformer: head dim 32 and window <= 12 (every published Swin variant)')
+        if any(embed_dims * 2 ** i not in (128, 256, 512, 1024) for i in range(len(depths))):
+            raise NotImplementedError('SwinTransformer: stage widths must be in {128, 256, 512, 1024} (pvsg_layernorm); '
+                                      'Swin-B (embed_dims=128) is the supported variant')
         self.out_indices = tuple(out_indices)
         self.patch_size = patch_size
         self.patch_embed = _PatchEmbed(in_channels, embed_dims, patch_size, patch_norm)

@@ -76,6 +76,10 @@ def test_swin_b_builds_and_loads_strictly():
     assert torch.equal(det.state_dict()[k], osw.relative_position_index(12))
     with pytest.raises(NotImplementedError):
         pv.build_backbone(dict(type='SwinTransformer', embed_dims=96, num_heads=(3, 6, 12, 25)))
+    with pytest.raises(NotImplementedError):      # Swin-T widths: rejected at build time, not at the first forward
+        pv.build_backbone(dict(type='SwinTransformer', embed_dims=96, num_heads=(3, 6, 12, 24)))
+    with pytest.raises(NotImplementedError):
+        pv.build_backbone(dict(type='SwinTransformer', embed_dims=128, num_heads=(4, 8, 16, 32), qkv_bias=False))
     with pytest.raises(pv.lib.PvsgError if hasattr(pv, 'lib') else Exception):
         det.backbone(torch.zeros(1, 3, 96, 96))  # CPU tensor: no fallback
 
