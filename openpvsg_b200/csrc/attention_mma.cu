@@ -320,13 +320,10 @@ int pick_splits_tc(int B, int H, int qtiles, int Lk) {
 template <int D>
 int launch_attn(const AttnArgs& a, dim3 grid, int nwarp, cudaStream_t st) {
     constexpr size_t smem = 2ull * 4 * Tile<D>::KT * Tile<D>::PITCH * sizeof(__nv_bfloat16);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess)
-            return PVSG_ERR_LAUNCH;
-        configured = true;
-    }
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
     attn_mma_kernel<D><<<grid, 32 * nwarp, smem, st>>>(a);
     return PVSG_OK;
 }

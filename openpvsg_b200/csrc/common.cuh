@@ -14,6 +14,17 @@ static inline int pvsg_launch_status() {
     return e == cudaSuccess ? PVSG_OK : PVSG_ERR_LAUNCH;
 }
 
+// Function attributes (dynamic shared-memory opt-in, carve-out) are PER DEVICE: a process driving several GPUs
+// must configure each kernel once on every device it launches on.  `flags` is a zero-initialised static array.
+constexpr int PVSG_MAX_DEVICES = 64;
+static inline bool pvsg_first_use_on_device(bool (&flags)[PVSG_MAX_DEVICES]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PVSG_MAX_DEVICES) dev = 0;
+    const bool first = !flags[dev];
+    flags[dev] = true;
+    return first;
+}
+
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

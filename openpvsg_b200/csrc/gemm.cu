@@ -379,12 +379,14 @@ __global__ void __launch_bounds__(256) skinny_kernel(GemmParams p) {
 template <int NB>
 int launch_skinny(const GemmParams& p, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)NB * p.K + 128 * NB);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[PVSG_MAX_DEVICES];   // per device (function attributes are)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PVSG_MAX_DEVICES) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         if (cudaFuncSetAttribute(skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess)
             return PVSG_ERR_LAUNCH;
-        configured = smem;
+        configured[dev] = smem;
     }
     skinny_kernel<NB><<<(unsigned)((p.N + NB - 1) / NB), 256, smem, st>>>(p);
     return pvsg_launch_status();

@@ -776,14 +776,12 @@ EncodeTiledFn get_encode() {
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
+    static int n[PVSG_MAX_DEVICES];   // per device: a process may drive several GPUs
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PVSG_MAX_DEVICES) dev = 0;
+    if (n[dev] == 0 && (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0))
+        n[dev] = 148;
+    return n[dev];
 }
 
 // 2-D map over a row-major [rows, cols] bf16 matrix with row pitch ld (elements); box = [box_rows, 64]
@@ -870,13 +868,10 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 template <int BN>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
               const TcParams& p, int B, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg<BN>::SMEM_TOTAL) != cudaSuccess)
-            return PVSG_ERR_LAUNCH;
-        configured = true;
-    }
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_TOTAL) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
     const unsigned grid = (unsigned)imin64(tiles, sm_count());
     TcParams q = p;

@@ -132,12 +132,10 @@ extern "C" int pvsg_tube_overlap(const int32_t* gt, const int32_t* pan, const in
     const size_t smem = (size_t)cells * sizeof(int32_t);
     PVSG_CHECK_ARG(smem <= 200 * 1024);
     cudaStream_t st = as_stream(stream);
-    static bool attr_set = false;   // idempotent, value-independent of the call
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return PVSG_ERR_LAUNCH;
-        attr_set = true;
-    }
+    static bool configured[PVSG_MAX_DEVICES];   // idempotent, value-independent of the call
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
     if (cudaMemsetAsync(counts, 0, (size_t)B * cells * sizeof(int32_t), st) != cudaSuccess) return PVSG_ERR_LAUNCH;
     const int64_t HW = (int64_t)H * W;
     const int64_t strips = (HW + kStrip - 1) / kStrip;

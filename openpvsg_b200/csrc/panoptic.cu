@@ -715,13 +715,10 @@ extern "C" int pvsg_instance_select_batched(const float* cls_logits, int B, int 
     PVSG_CHECK_ARG((int64_t)k <= (int64_t)Q * NC);
     const size_t smem = sizeof(float) * (size_t)Q * NC;
     if (smem > 200 * 1024) return PVSG_ERR_UNSUPPORTED;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(ins_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-            cudaSuccess)
-            return PVSG_ERR_LAUNCH;
-        configured = true;
-    }
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(ins_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
     ins_select_kernel<<<B, 1024, smem, as_stream(stream)>>>(cls_logits, Q, NC, k, top_scores, top_labels, top_query);
     return pvsg_launch_status();
 }

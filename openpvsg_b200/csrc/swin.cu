@@ -457,8 +457,8 @@ static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv
     constexpr int NK = 16 * KS16;
     constexpr size_t smem = sizeof(__nv_bfloat16) * 4 * NK * kPitch + sizeof(float) * ((2 * kMaxWs - 1) * (2 * kMaxWs - 1) + 1) +
                             sizeof(int64_t) * NK + sizeof(int) * NK;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured)) {
         // 50 KB per CTA: ask for the large shared-memory carve-out so that three CTAs fit an SM (ncu showed the default
         // carve-out capping the kernel at two, profiles/r01s_ncu_window_attention_mma.json); L1 is not reused here
         if (cudaFuncSetAttribute(window_attention_mma_kernel<KS16, CH16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
@@ -466,7 +466,6 @@ static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv
             cudaFuncSetAttribute(window_attention_mma_kernel<KS16, CH16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return PVSG_ERR_LAUNCH;
-        configured = true;
     }
     const int warps = (N + 15) / 16;
     window_attention_mma_kernel<KS16, CH16><<<grid, 32 * warps, smem, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
@@ -568,13 +567,10 @@ extern "C" int pvsg_patch_merge_ln(const float* x, const float* gamma, const flo
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const int64_t total = (int64_t)B * OH * OW;
     const size_t smem = (size_t)4 * 4 * C * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(patch_merge_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * 4) !=
-            cudaSuccess)
-            return PVSG_ERR_LAUNCH;
-        configured = true;
-    }
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(patch_merge_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * 4) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
     const unsigned grid = (unsigned)imin64((total + 3) / 4, 148 * 16);
     patch_merge_ln_kernel<<<grid, 128, smem, as_stream(stream)>>>(x, gamma, beta, y, B, H, W, C, OH, OW, eps);
     return pvsg_launch_status();

@@ -40,10 +40,10 @@ TOPK_INS = 10   # models/mask2former_vps/mask2former.py:192-195 keeps the 10 bes
 
 
 class _Pending:
-    __slots__ = ('slot', 'event', 'n')
+    __slots__ = ('slot', 'event', 'n', 'gen')
 
-    def __init__(self, slot, event, n):
-        self.slot, self.event, self.n = slot, event, n
+    def __init__(self, slot, event, n, gen):
+        self.slot, self.event, self.n, self.gen = slot, event, n, gen
 
 
 def postprocess_batch(det, cls, mask_lr, in_hw, img_hw, out_hw):
@@ -104,6 +104,8 @@ class FrameRunner:
                      for _ in range(RING)]
         self.events = [torch.cuda.Event() for _ in range(RING)]
         self.busy = [False] * RING
+        self.gen = [0] * RING           # generation of the batch occupying a slot (stale-handle detection)
+        self.pending = [None] * RING    # uncollected handle per slot
         self.next_slot = 0
         self.next_lane = 0
 
@@ -147,6 +149,9 @@ class FrameRunner:
         if not 0 < n <= self.batch:
             raise ValueError(f'submit: expected 1..{self.batch} frames, got {n}')
         slot = self.next_slot
+        if self.pending[slot] is not None:
+            # the ring is full: this slot's pinned buffers and event still belong to an uncollected batch
+            raise RuntimeError(f'FrameRunner.submit: {RING} batches are in flight; collect() the oldest one first')
         self.next_slot = (slot + 1) % RING
         lane = self.next_lane
         self.next_lane = (lane + 1) % self.nlanes
@@ -182,14 +187,19 @@ class FrameRunner:
                 self.host[slot][k].copy_(v, non_blocking=True)
             self.events[slot].record(self.d2h)
         self.busy[slot] = True
-        return _Pending(slot, self.events[slot], n)
+        self.gen[slot] += 1
+        self.pending[slot] = _Pending(slot, self.events[slot], n, self.gen[slot])
+        return self.pending[slot]
 
     @torch.no_grad()
     def collect(self, pending, copy=True):
         """Wait for a submitted batch and build the reference's per-frame result dicts
         (models/mask2former_vps/mask2former.py:172-211): a list with one dict per submitted frame.
         ``copy=False`` returns views of the pinned ring buffers (valid until RING-1 further submits)."""
+        if self.pending[pending.slot] is not pending or pending.gen != self.gen[pending.slot]:
+            raise RuntimeError('FrameRunner.collect: stale handle (already collected, or its ring slot was reused)')
         pending.event.synchronize()
+        self.pending[pending.slot] = None   # the slot may be submitted again; copy=False views live until then
         det = self.det
         fh = det.panoptic_fusion_head
         own = (lambda a: a.copy()) if copy else (lambda a: a)
@@ -231,13 +241,30 @@ class FrameRunner:
 def enable_cuda_graph(detector):
     """Make ``Mask2FormerVideoCustom.simple_test`` replay a captured graph per frame shape."""
     detector._runners = {}
+    detector._runners_epoch = weights_epoch(detector)
     return detector
+
+
+def weights_epoch(detector):
+    """Changes whenever a parameter / buffer is updated in place (load_state_dict, optimizer steps: the version
+    counters) or the module is moved / cast / reloaded (``_DetectorBase._apply`` / ``_load_from_state_dict`` bump
+    ``_weights_gen``).  A captured graph bakes in pointers to the kernel-layout copies of the weights (folded
+    conv + BN tensors, bf16 operand planes), so it is only valid for the epoch it was captured in."""
+    ts = detector.__dict__.get('_epoch_tensors')
+    if ts is None or ts[0] != getattr(detector, '_weights_gen', 0):
+        ts = (getattr(detector, '_weights_gen', 0), list(detector.parameters()) + list(detector.buffers()))
+        detector.__dict__['_epoch_tensors'] = ts
+    return hash((ts[0],) + tuple(t._version for t in ts[1]))
 
 
 def get_runner(detector, meta, rescale=True, batch=1, rle=False):
     key = (tuple(meta['batch_input_shape']), tuple(meta['img_shape']), tuple(meta['ori_shape']), bool(rescale),
            int(batch), bool(rle))
     runners = detector._runners
+    epoch = weights_epoch(detector)
+    if getattr(detector, '_runners_epoch', None) != epoch:
+        runners.clear()               # weights changed under the captured graphs: drop them, re-capture on demand
+        detector._runners_epoch = epoch
     if key not in runners:
         runners[key] = FrameRunner(detector, meta, rescale, batch, rle=rle)
     return runners[key]

@@ -994,6 +994,20 @@ class _DetectorBase(nn.Module):
             raise NotImplementedError('inference backend only')
         return super().train(False)
 
+    # Captured CUDA graphs (engine.FrameRunner) hold raw pointers to kernel-layout copies of the weights:
+    # reloading, moving or casting the detector starts a new weights epoch and drops them (engine.get_runner).
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._weights_gen = getattr(self, '_weights_gen', 0) + 1
+        if getattr(self, '_runners', None):
+            self._runners.clear()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *a, **k):
+        self._weights_gen = getattr(self, '_weights_gen', 0) + 1
+        if getattr(self, '_runners', None):
+            self._runners.clear()
+        return super()._apply(fn, *a, **k)
+
     def extract_feat(self, img):
         return self.backbone(img)
 

@@ -26,6 +26,10 @@ def _f32(t, name='tensor'):
         return None
     if not (t.is_cuda and t.dtype == torch.float32):
         raise _l.PvsgError(f'{name}: expected a CUDA float32 tensor, got {t.device} {t.dtype}')
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the CURRENT device's stream with raw pointers: a tensor of another GPU would be
+        # dereferenced on the wrong device (one process per GPU is the supported layout; use torch.cuda.device(...))
+        raise _l.PvsgError(f'{name}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}')
     return t
 
 
@@ -141,10 +145,11 @@ def _weight_planes(w):
     if cache is None:
         cache = {}
         base._pvsg_planes = cache
-    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), base._version)
+    # data_ptr / device: nn.Module._apply (.to, .float) swaps param.data without bumping the version
+    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), base._version, base.data_ptr(), str(base.device))
     hit = cache.get(key)
     if hit is None:
-        for k in [k for k in cache if k[3] != base._version]:
+        for k in [k for k in cache if k[3:] != key[3:]]:
             del cache[k]
         hit = split_bf16(w.contiguous())
         cache[key] = hit
@@ -876,7 +881,14 @@ def gather_pairs(sub, obj, pairs, pe=None):
     lib = _l.load()
     N, T, Fd = _f32(sub).shape
     Pn = pairs.shape[0]
+    if tuple(_f32(obj).shape) != (N, T, Fd) or pairs.dtype != torch.int32 or pairs.dim() != 2 or pairs.shape[1] != 2:
+        raise _l.PvsgError('gather_pairs: sub / obj [N,T,F] of one shape and int32 pairs [P,2] expected')
+    if pe is not None and (_f32(pe).dim() != 2 or pe.shape[0] < T or pe.shape[1] != 2 * Fd or not pe.is_contiguous()):
+        # the reference's PositionalEncoding fails the same way for clips longer than max_len (transformer.py:59-81)
+        raise _l.PvsgError(f'gather_pairs: positional table {tuple(pe.shape)} does not cover T={T}, 2F={2 * Fd}')
     out = torch.empty(Pn, T, 2 * Fd, device=sub.device, dtype=torch.float32)
+    if Pn == 0:
+        return out
     _l.check(lib.pvsg_gather_pairs(_ptr(sub.contiguous()), _ptr(_f32(obj).contiguous()), _ptr(pairs.contiguous()),
                                    _ptr(_f32(pe)), _ptr(out), Pn, T, Fd, _stream()), 'pvsg_gather_pairs')
     return out
