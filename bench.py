@@ -37,6 +37,9 @@ import torch  # noqa: E402
 
 H, W = 720, 1280
 METRIC = 'Mask2Former-VPS R50 inference frames/sec @720p'
+MSDA_KERNEL = 'msda_group_kernel'
+MSDA_NOTE = ('LSU-pipe / issue bound: 48 bilinear corner lines of 128 B per (query, head) pass through L1 '
+             '(ncu profiles/r01n_ncu_msda_group.json)')
 
 
 def load_peaks():
@@ -48,65 +51,43 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
-def gemm_traffic():
-    """DRAM bytes per gemm_tc_kernel launch, from the committed ncu pass over one frame-graph replay
-    (profiles/*_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, averaged over launches)."""
+def kernel_traffic(family):
+    """DRAM bytes per launch of a kernel family, from the committed ncu pass over one frame-graph replay
+    (profiles/*_<family>_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, averaged over launches)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_gemm_traffic.json')))
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', f'*_{family}_traffic.json')))
     if not files:
         return None, None
     d = json.load(open(files[-1]))
     return d.get('avg_bytes_per_launch'), os.path.relpath(files[-1], ROOT)
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+DTYPE = 'f32 io / bf16x3 mma (split-bf16 operands, ~16-bit mantissa per product) / f32 accumulate'
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(',')]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
-                    samples=len(sm))
+def workload_config(args, world):
+    """The `config` object of the JSON line -- identical for both arms (the reference arm runs a bounded sample
+    of the same workload; what it sampled is in its `cpu_baseline.sample`)."""
+    swin = args.backbone == 'swin_b'
+    workload = ('Mask2Former-VPS Swin-B inference (mmdet 2.25 Swin-B: embed 128, depths 2-2-18-2, window 12), synthetic 720p '
+                'clip, 100 frames per GPU (the backbone of BASELINE configs[2]); random-init weights'
+                if swin else
+                'Mask2Former-VPS R50 inference, synthetic 720p clip, 100 frames per GPU '
+                '(BASELINE configs[1]); random-init weights of the reference architecture')
+    frames, distinct = getattr(args, 'frames', 100), getattr(args, 'distinct', 100)
+    return dict(workload=workload, backbone=args.backbone, frames_per_gpu_per_step=frames,
+                distinct_frames=distinct, frame_seeds=f'rank * {distinct} + 0..{distinct - 1}',
+                resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
+                l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',
+                cuda_graph=not getattr(args, 'no_graph', False), frames_per_launch=getattr(args, 'batch', 20))
 
 
 def make_frames(n_distinct, rank):
+    """100 distinct frames, seeds 0..99 (rank r of a weak-scaled run owns seeds 100 r .. 100 r + 99)."""
+    from concurrent.futures import ThreadPoolExecutor
     from openpvsg_b200 import synthetic as syn
-    return [syn.synthetic_frame(1000 * rank + i, H, W) for i in range(n_distinct)]
+    with ThreadPoolExecutor(8) as ex:
+        return list(ex.map(lambda i: syn.synthetic_frame(n_distinct * rank + i, H, W), range(n_distinct)))
 
 
 # --------------------------------------------------------------------------------------
@@ -252,26 +233,99 @@ def tube_dump_bench(det, meta, frames, batch):
                      'host path: numpy RLE of pan == id per segment (the reference uses pycocotools per segment)')
 
 
-def end2end_bench(det, meta, host_frames, batch, dev):
-    """BASELINE configs[4] on one GPU: 380 frames (76 s @ 5 FPS) @720p through VPS -> tube linking
-    (device RLE rows) -> relation head, wall clock of the whole clip from pinned host frames."""
-    from openpvsg_b200 import end2end, relation_head as rh, synthetic as syn
+def _relation_models(dev):
+    from openpvsg_b200 import relation_head as rh, synthetic as syn
     sds = syn.relation_state_dicts(seed=1)
     mods = [rh.ObjectEncoder(256), rh.ObjectEncoder(256), rh.PairProposalNetwork(256, 1024), rh.TemporalTransformer(512, 57)]
     for m, k in zip(mods, ('subject_encoder', 'object_encoder', 'pair_proposal_model', 'relation_model')):
         m.load_state_dict(sds[k])
         m.to(dev)
+    return mods, sds
+
+
+def end2end_bench(det, meta, host_frames, batch, dev, world, rank, timed, with_cpu=True):
+    """BASELINE configs[4]: 380 frames (76 s @ 5 FPS) @720p through VPS -> tube linking (device RLE rows; all-gather of
+    the kept entries when the clip is sharded over `world` ranks) -> relation head, from pinned host frames, timed
+    between barriers as the max over ranks.  With the CPU baseline enabled, rank 0 also runs the CPU oracle's relation
+    stage on the same tubes and reports R@20/50/100 of both backends against synthetic ground truth drawn from the
+    oracle's own top triplets (the two must be equal)."""
+    from openpvsg_b200 import end2end, rel_eval, tubes
+    mods, sds = _relation_models(dev)
     T = 380
-    clip = [host_frames[i % len(host_frames)] for i in range(T)]
-    end2end.run_clip(det, mods, clip[:2 * batch], meta, batch=batch)          # warm-up (graph with RLE, relation kernels)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = end2end.run_clip(det, mods, clip, meta, batch=batch)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    return dict(workload='end-to-end VPS + tube linking + relation head, 380 frames @720p (BASELINE configs[4]), 1 GPU',
-                seconds=round(dt, 3), frames_per_s=round(T / dt, 1), tubes=len(out['linker'].object_list),
-                mask_rows=len(out['linker'].rows), triplets=len(out['relations']))
+    lo, hi = tubes.shard_frames(T, world, rank)
+    clip = [host_frames[i % len(host_frames)] for i in range(lo, hi)]   # this rank's contiguous block
+
+    def run():
+        return end2end.run_clip(det, mods, clip, meta, batch=batch, num_frames=T)
+
+    ms, out, _ = timed(run, 1, 1)          # warm-up run captures the RLE graph / relation kernels
+    res = dict(workload=f'end-to-end VPS + tube linking + relation head, 380 frames @720p (BASELINE configs[4]), {world} GPU(s), '
+                        'frames sharded in contiguous blocks, one all-gather at tube linking',
+               seconds=round(ms * 1e-3, 3), frames_per_s=round(T / (ms * 1e-3), 1), tubes=len(out['linker'].object_list),
+               mask_rows_rank0=len(out['linker'].rows), triplets=len(out['relations']))
+    if with_cpu and rank == 0 and out['raw'] is not None:
+        from oracle import relation as orel        # checker only (cpu_baseline leg)
+        feats = torch.as_tensor(out['linker'].tube_features())
+        torch.set_num_threads(os.cpu_count())
+        with torch.no_grad():
+            ref = orel.relation_forward(sds, feats, 100)
+        ref_res = orel.generate_pairwise_results(ref['span_pred'], ref['prob'], ref['pairs'])
+        gt = [dict(subject_index=r['subject_index'], object_index=r['object_index'], relation=r['relation'],
+                   relation_span=np.asarray(r['relation_span'])) for r in ref_res[::3][:30]]
+        from openpvsg_b200 import relation_head as rh
+        gpu_res = rh.generate_pairwise_results(out['raw']['span_pred'], out['raw']['prob'], out['raw']['pairs'].cpu().tolist())
+        names = [f'relation_{i}' for i in range(57)]
+        recalls = {}
+        for tag, results in (('b200', gpu_res), ('cpu_oracle', ref_res)):
+            d = rel_eval.new_recall_dict(names)
+            rel_eval.accumulate(d, results, gt)
+            fm = rel_eval.calculate_final_metrics(d, list(rel_eval.K_VALUES))
+            recalls[tag] = {f'R@{K}': round(fm[K]['recall'], 6) for K in rel_eval.K_VALUES}
+        res['recall'] = dict(recalls, equal=recalls['b200'] == recalls['cpu_oracle'], gt_relations=len(gt),
+                             note='relation stage of the CPU oracle on the same tube features; GT = every 3rd of the '
+                                  "oracle's top pairwise triplets (first 30)")
+    return res
+
+
+def swin_clip_bench(pv, configs, engine, syn, tubes, meta, host_frames, batch, dev, world, rank, timed):
+    """BASELINE configs[2]: Mask2Former-VPS with the Swin-B backbone on a 300-frame 720p clip sharded over the ranks
+    (contiguous blocks of ceil(300 / N) frames), pinned host frames in, results + tube linking out."""
+    det = pv.build_detector(configs.mask2former_swin(True))
+    det.load_state_dict(syn.mask2former_state_dict(seed=0, **SWIN_SD))
+    det.to(dev)
+    engine.enable_cuda_graph(det)
+    T = 300
+    lo, hi = tubes.shard_frames(T, world, rank)
+    clip = [host_frames[i % len(host_frames)] for i in range(lo, hi)]
+    runner = engine.get_runner(det, meta, True, batch=batch)
+
+    def run():
+        entries, pend = [], None
+
+        def consume(res):
+            ids = list(res['query_feats'].keys())
+            entries.append((ids, np.stack([np.asarray(res['query_feats'][k][0]) for k in ids]) if ids
+                            else np.zeros((0, 256), np.float32)))
+
+        for i in range(0, len(clip), batch):
+            nxt = runner.submit(clip[i:i + batch])
+            if pend is not None:
+                for r in runner.collect(pend, copy=False):
+                    consume(r)
+            pend = nxt
+        for r in runner.collect(pend, copy=False):
+            consume(r)
+        return tubes.gather_and_link(entries, T, device=dev)
+
+    ms, linker, _ = timed(run, 2, 1)
+    out = dict(workload=f'Mask2Former-VPS Swin-B inference, synthetic 720p 300-frame clip sharded across {world} GPU(s) '
+                        '(BASELINE configs[2]; Swin-B is not in the reference: oracle-checked by us, SURVEY 8d)',
+               seconds_per_clip=round(ms * 1e-3 / 2, 3), frames_per_s=round(2 * T / (ms * 1e-3), 1), tubes=len(linker.object_list),
+               frames_per_rank=hi - lo, api='engine.FrameRunner.submit/collect on pinned host frames + tubes.gather_and_link')
+    det._runners.clear()
+    del runner, det
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args, rank):
@@ -283,10 +337,9 @@ def run_reference(args, rank):
     line = dict(metric=METRIC.replace('R50', 'Swin-B') if swin else METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * float(np.mean(times)), higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload='Mask2Former Swin-B inference, synthetic 720p clip (backbone of BASELINE configs[2])' if swin
-                            else 'Mask2Former R50 inference, synthetic 720p clip (BASELINE configs[1])',
-                            backbone=args.backbone, frames_per_step=1, note='CPU oracle port of the reference algorithm; mmcv/mmdet '
-                            'are not installable offline so the reference itself cannot run'),
+                config=workload_config(args, args.gpus),
+                note='CPU oracle port of the reference algorithm (mmcv / mmdet are not installable offline, so the reference '
+                     'itself cannot run); one step = ONE frame of the workload (bounded sample)',
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port',
                                   sample=f'{args.steps} frame(s) @720p, 1 frame per step, torch CPU fp32, {cores} threads'),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -324,8 +377,30 @@ def kernel_breakdown(det, img, meta, batch=1):
         v, proj = a[0], a[2]
         return 4.0 * (2 * v.numel() + proj.numel())
 
-    spec = (('linear', 'gemm', lin_flops, None), ('conv2d_nhwc', 'gemm', conv_flops, None),
-            ('mask_logits', 'gemm', ml_flops, None), ('split_bf16', 'gemm', None, None),
+    def numel(t):
+        return int(np.prod(t.shape))
+
+    def lin_bytes(a, k):      # fp32-equivalent operand + result bytes (a plane pair is 2 + 2 bytes per element)
+        x, w = a[0], a[1]
+        mn = numel(x) // x.shape[-1] * w.shape[0]
+        res = k.get('residual', a[4] if len(a) > 4 else None)
+        return 4.0 * (numel(x) + numel(w) + mn + (mn if res is not None else 0))
+
+    def conv_bytes(a, k):
+        x, w = a[0], a[1]
+        s = k.get('stride', 1)
+        out = x.shape[0] * (x.shape[1] // s) * (x.shape[2] // s) * w.shape[0]
+        return 4.0 * (numel(x) + numel(w) + out + (out if k.get('residual') is not None else 0))
+
+    def ml_bytes(a, k):
+        e, f = a[0], a[1]
+        want_logits = a[2] if len(a) > 2 else k.get('want_logits', True)
+        want_mask = a[3] if len(a) > 3 else k.get('want_mask', False)
+        qp = e.shape[0] * e.shape[1] * f.shape[1]
+        return 4.0 * (numel(e) + numel(f)) + (4.0 * qp if want_logits else 0.0) + (1.0 * qp if want_mask else 0.0)
+
+    spec = (('linear', 'gemm', lin_flops, lin_bytes), ('conv2d_nhwc', 'gemm', conv_flops, conv_bytes),
+            ('mask_logits', 'gemm', ml_flops, ml_bytes), ('split_bf16', 'gemm', None, None),
             ('msda_fused_forward', 'msda', None, msda_bytes), ('attention', 'attention', None, None),
             ('layernorm', 'norm', None, None), ('groupnorm_nhwc', 'norm', None, None),
             ('add_rowvec', 'norm', None, None), ('panoptic_fuse', 'postprocess', None, None),
@@ -410,7 +485,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--frames', type=int, default=100, help='frames per GPU per step')
-    ap.add_argument('--distinct', type=int, default=8, help='distinct synthetic frames cycled through')
+    ap.add_argument('--distinct', type=int, default=100, help='distinct synthetic frames per rank (SURVEY 8d: 100 frames, seeds 0..99)')
     ap.add_argument('--cpu-frames', type=int, default=2, help='frames of the cpu_baseline sample')
     ap.add_argument('--batch', type=int, default=20, help='frames pushed through the network together (one graph replay); '
                     '100 frames per step = 5 replays of 20, measured 8 -> 322, 10 -> 342, 20 -> 348, 25 -> 347 frames/s')
@@ -467,17 +542,19 @@ def main():
                 # single process: link while the GPU works on the next batch (concat_seq is incremental)
                 local_linker.add_frame(ids, [np.asarray(torch.as_tensor(res['query_feats'][k][0]).cpu()) for k in ids])
             else:
-                entries.append((ids, [res['query_feats'][k][0].clone() for k in ids]))
+                # compact copy of the kept entries (the pinned ring is reused); they are exchanged once per clip
+                entries.append((ids, np.stack([np.asarray(res['query_feats'][k][0]) for k in ids]) if ids
+                                else np.zeros((0, 256), np.float32)))
 
-        if api == 'sync' or det._runners is None:
+        if api in ('sync', 'sync1') or det._runners is None:
             # the reference's call (public API; pinned host input when `api`): samples_per_gpu = batch
-            # frames per call, as mmdet's single_gpu_test would feed them
+            # frames per call, as mmdet's single_gpu_test would feed them ('sync1': samples_per_gpu = 1)
             nb = args.batch if api == 'sync' else 1
             for i in range(0, args.frames, nb):
                 xs = [frames[(i + j) % len(frames)] for j in range(min(nb, args.frames - i))]
-                if api == 'sync':
+                if api in ('sync', 'sync1'):
                     # the collated, pinned batch tensor a DataLoader(pin_memory=True) hands over
-                    xb = host_batches[(i // nb) % len(host_batches)] if len(xs) == nb else torch.stack(xs)
+                    xb = host_batches[(i // nb) % len(host_batches)] if (len(xs) == nb and nb > 1) else torch.stack(xs)
                     xd = xb.to(dev, non_blocking=True)
                     out = det(return_loss=False, rescale=True, img=[xd], img_metas=[[dict(meta)] * len(xs)],
                               ref_img=[xd[:, None]], ref_img_metas=[[dict(meta)] for _ in xs])
@@ -501,18 +578,18 @@ def main():
                 consume(r)
         if local_linker is not None:
             return local_linker
-        ids_feats = [(ids, torch.stack(f).cpu().numpy() if f else np.zeros((0, 256), np.float32)) for ids, f in entries]
-        return tubes.gather_and_link(ids_feats, args.frames * world, device=dev)
+        return tubes.gather_and_link(entries, args.frames * world, device=dev)
 
-    def timed(frames, api, steps, warmup):
+    def timed(fn, steps, warmup):
+        """`steps` calls of fn() between two barriers, device-timed (CUDA events on the current stream), max over ranks."""
         for _ in range(warmup):
-            run_step(frames, api)
+            fn()
         barrier()
         n0 = lib.launch_count[0]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            linker = run_step(frames, api)
+            out = fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -520,15 +597,24 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, linker, lib.launch_count[0] - n0
+        return ms, out, lib.launch_count[0] - n0
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, linker, _ = timed(resident, 'device', args.steps, args.warmup)
+    ms_dev, linker, _ = timed(lambda: run_step(resident, 'device'), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, _ = timed(host, 'pipelined', args.steps, 1)        # FrameRunner.submit/collect, pinned host frames
-    ms_sync, _, _ = timed(host, 'sync', max(1, args.steps // 2), 1)  # model(return_loss=False, ...) per frame
+    ms_e2e, _, _ = timed(lambda: run_step(host, 'pipelined'), args.steps, 1)     # FrameRunner.submit/collect, pinned host frames
+    sync_steps = max(1, args.steps // 2)
+    ms_sync, _, _ = timed(lambda: run_step(host, 'sync'), sync_steps, 1)         # model(return_loss=False, ...), `batch` samples per call
+    lat1 = None
+    if det._runners is not None:
+        # the reference's own test configuration: samples_per_gpu = 1, one synchronous call per frame
+        fr = args.frames
+        args.frames = min(20, fr)
+        ms_one, _, _ = timed(lambda: run_step(host, 'sync1'), 1, 1)
+        lat1 = ms_one / args.frames
+        args.frames = fr
     if det._runners:
         per_frame = max(r.launches_per_frame for r in det._runners.values() if r.batch == args.batch)
     else:
@@ -537,6 +623,20 @@ def main():
         per_frame = (lib.launch_count[0] - n0) or 638
     launches = int(per_frame * args.frames * args.steps) * world   # every rank launches the same work
 
+    # ---- BASELINE configs[4] at this N: 380-frame clip (76 s @ 5 FPS) sharded over the ranks, VPS -> all-gather at
+    # tube linking -> relation head on every rank; configs[2]: 300-frame Swin-B clip sharded the same way
+    extra = {}
+    if det._runners is not None and not swin:
+        try:
+            extra['end2end_clip'] = end2end_bench(det, meta, host, args.batch, dev, world, rank, timed,
+                                                  with_cpu=not args.no_cpu_baseline)
+        except Exception as ex:   # the headline metric must not depend on the auxiliary measurements
+            extra['end2end_clip'] = dict(error=repr(ex))
+        try:
+            extra['swin_b_clip'] = swin_clip_bench(pv, configs, engine, syn, tubes, meta, host, args.batch, dev, world, rank, timed)
+        except Exception as ex:
+            extra['swin_b_clip'] = dict(error=repr(ex))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -544,14 +644,14 @@ def main():
     total_frames = args.frames * world * args.steps
     value = total_frames / (ms_dev * 1e-3)
     e2e = total_frames / (ms_e2e * 1e-3)
-    e2e_sync = args.frames * world * max(1, args.steps // 2) / (ms_sync * 1e-3)
+    e2e_sync = args.frames * world * sync_steps / (ms_sync * 1e-3)
     fam = kernel_breakdown(det, resident[0], meta, args.batch)
     tot_ms = sum(d['ms'] for d in fam.values())
     gk = [k for k in fam if k.startswith('gemm')]
     g = dict(ms=sum(fam[k]['ms'] for k in gk) or 1.0, gflop=sum(fam[k]['gflop'] for k in gk),
-             launches=sum(fam[k]['launches'] for k in gk))
+             gbyte=sum(fam[k]['gbyte'] for k in gk), launches=sum(fam[k]['launches'] for k in gk))
     achieved_tf = g['gflop'] / g['ms']  # GFLOP / ms == TFLOP/s
-    traffic, traffic_src = gemm_traffic()
+    traffic, traffic_src = kernel_traffic('gemm')
     roofline = dict(kernel='gemm_tc_kernel (tcgen05 split-bf16 GEMM / implicit-GEMM conv engine; algorithmic 2MNK '
                            'flops, each product = 3 bf16 MMAs => ceiling peak/3 on algorithmic flops)', bound='tensor',
                     achieved=round(achieved_tf, 2), peak=peaks['tf_sustained'], unit='TFLOP/s',
@@ -561,6 +661,11 @@ def main():
                     launches_per_frame=round(g['launches'], 1), gflop_per_frame=round(g['gflop'], 1),
                     gflop_per_launch=round(g['gflop'] / max(g['launches'], 1e-9), 2),
                     us_per_launch=round(1e3 * g['ms'] / max(g['launches'], 1e-9), 2),
+                    algorithmic_bytes_per_frame=int(g['gbyte'] * 1e9),
+                    algorithmic_bytes_per_launch=int(g['gbyte'] * 1e9 / max(g['launches'], 1e-9)),
+                    algorithmic_bytes_note='fp32-equivalent operand + result bytes of every call of the family (activations, '
+                                           'weights, residual, output; 4 B per element: a (hi, lo) bf16 plane pair is the same size)',
+                    achieved_GBps_algorithmic=round(g['gbyte'] / (g['ms'] * 1e-3), 1),
                     share_of_frame=round(g['ms'] / tot_ms, 3))
     m = fam.get('msda')
     kernels = {k: dict(ms_per_frame=round(d['ms'], 3), share=round(d['ms'] / tot_ms, 3), launches=round(d['launches'], 1))
@@ -568,25 +673,31 @@ def main():
     for k in gk:
         if fam[k]['gflop'] > 0:
             kernels[k]['TFLOPs'] = round(fam[k]['gflop'] / fam[k]['ms'], 1)
-    extra = {}
     if m:
         gbps = m['gbyte'] / (m['ms'] * 1e-3)
         kernels['msda']['achieved_GBps'] = round(gbps, 1)
         kernels['msda']['frac_hbm'] = round(gbps / peaks['hbm_gbs'], 4)
+        mt, mt_src = kernel_traffic('msda')
         # north_star target: MSDeformAttn as a fraction of the HBM roofline (algorithmic bytes: value + raw
         # projections + output = 3200 B per token and layer)
-        extra['roofline_msda'] = dict(kernel='msda_group_kernel', bound='hbm', achieved=round(gbps, 1),
+        extra['roofline_msda'] = dict(kernel=MSDA_KERNEL, bound='hbm', achieved=round(gbps, 1),
                                       peak=peaks['hbm_gbs'], unit='GB/s', frac=round(gbps / peaks['hbm_gbs'], 4),
-                                      traffic=None, note='LSU-pipe / issue bound: 48 bilinear corner lines of 128 B per '
-                                      '(query, head) pass through L1 (ncu profiles/r01i_ncu_msda_group.json)')
+                                      traffic=mt, traffic_source=mt_src,
+                                      algorithmic_bytes_per_launch=int(m['gbyte'] * 1e9 * args.batch / max(m['launches'] * args.batch, 1e-9)),
+                                      us_per_launch=round(1e3 * m['ms'] / max(m['launches'], 1e-9), 2),
+                                      note=MSDA_NOTE)
     ml = fam.get('gemm_mask_logits')
     if ml and ml['gflop'] > 0:
         tf = ml['gflop'] / ml['ms']
+        gbps = ml['gbyte'] / (ml['ms'] * 1e-3)
         extra['roofline_mask_einsum'] = dict(
-            kernel='gemm_tc_kernel (pvsg_mask_logits)', bound='hbm', unit='TFLOP/s', achieved=round(tf, 1),
-            peak=peaks['tf_sustained'], frac=round(tf / peaks['tf_sustained'], 4),
-            note='AI = 36 FLOP/B (fp32 I/O, Q = 100 rows) << ridge 250: HBM-bound by construction (SURVEY.md 8d); '
-                 'nine of the ten calls run on pooled features (exact, 3x fewer flops)')
+            kernel='gemm_tc_kernel (pvsg_mask_logits)', bound='hbm', unit='GB/s', achieved=round(gbps, 1),
+            peak=peaks['hbm_gbs'], frac=round(gbps / peaks['hbm_gbs'], 4),
+            algorithmic_bytes_per_frame=int(ml['gbyte'] * 1e9), tflops=round(tf, 1),
+            tensor_frac=round(tf / peaks['tf_sustained'], 4),
+            note='AI = 36 FLOP/B (fp32 I/O, Q = 100 rows) << ridge 250: HBM-bound by construction (SURVEY.md 8d); bytes = embed + '
+                 'feature operands + the result actually written (fp32 logits for the last layer, 1-byte sign masks for the nine '
+                 'intermediate calls, which run on pooled features: exact, 3x fewer flops)')
     cpu = None
     if not args.no_cpu_baseline:
         fps, times = cpu_oracle_fps(args.cpu_frames, swin=swin)
@@ -595,7 +706,7 @@ def main():
                           f'{os.cpu_count()} threads), 1 warm-up frame')
     try:
         extra['relation_head'] = relation_bench(dev, not args.no_cpu_baseline)
-    except Exception as ex:   # the headline metric must not depend on the auxiliary measurement
+    except Exception as ex:
         extra['relation_head'] = dict(error=repr(ex))
     try:
         extra['relation_set'] = relset_bench(dev, not args.no_cpu_baseline)
@@ -607,31 +718,20 @@ def main():
             extra['tube_dump'] = tube_dump_bench(det, meta, resident, args.batch)
     except Exception as ex:
         extra['tube_dump'] = dict(error=repr(ex))
-    try:
-        if det._runners is not None and world == 1:
-            extra['end2end_clip'] = end2end_bench(det, meta, host, args.batch, dev)
-    except Exception as ex:
-        extra['end2end_clip'] = dict(error=repr(ex))
     in_bytes = 3 * 736 * 1280 * 4
     out_bytes = H * W * 4 + (1 + 400) * 4 + 10 * H * W + 100 * 256 * 4
-    workload = ('Mask2Former-VPS Swin-B inference (mmdet 2.25 Swin-B: embed 128, depths 2-2-18-2, window 12), synthetic 720p '
-                'clip, 100 frames per GPU (the backbone of BASELINE configs[2]); random-init weights'
-                if swin else
-                'Mask2Former-VPS R50 inference, synthetic 720p clip, 100 frames per GPU '
-                '(BASELINE configs[1]); random-init weights of the reference architecture')
     line = dict(metric=METRIC.replace('R50', 'Swin-B') if swin else METRIC, value=round(value, 3), unit='frames/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 3), higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=workload, backbone=args.backbone,
-                            frames_per_gpu_per_step=args.frames, distinct_frames=args.distinct,
-                            resolution='720x1280 padded to 736x1280', clip_length=1, parallelism=f'frames x{world}',
-                            l2='per-frame working set (~1.5 GB of activations) >> 126 MB L2, no explicit flush',
-                            cuda_graph=not args.no_graph, frames_per_launch=args.batch, tubes=len(linker.object_list)),
+                scaling='weak', vs_baseline=None, dtype=DTYPE, data='synthetic',
+                config=workload_config(args, world), tubes=len(linker.object_list),
                 e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames * world,
                          d2h_bytes_per_step=out_bytes * args.frames * world, ms_per_step=round(ms_e2e / args.steps, 3),
                          api='engine.FrameRunner.submit/collect (pipelined) on pinned host frames',
                          sync_api_value=round(e2e_sync, 3),
-                         sync_api=f'model(return_loss=False, rescale=True, img=..., ref_img=...) with {args.batch} samples per call, synchronous'),
+                         sync_api=f'model(return_loss=False, rescale=True, img=..., ref_img=...) with {args.batch} samples per call, synchronous',
+                         latency_ms_batch1=None if lat1 is None else round(lat1, 3),
+                         latency_api='model(return_loss=False, rescale=True, ...) with samples_per_gpu = 1 (the reference test '
+                                     'config), pinned host frame in, result dict out, synchronous; mean over 20 frames'),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu, **extra)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -85,18 +85,53 @@ def _add_result(linker, r):
         linker.add_frame(ids, feats, r.get('pan_results'))
 
 
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 @torch.no_grad()
-def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_results=False):
-    """The whole path for one clip on this process.  Returns dict(results, linker, relations, raw).
+def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_results=False, num_frames=None):
+    """The whole path for one clip.  Returns dict(results, linker, relations, raw).
     With keep_results=False (default) frames are linked as their batch completes and the per-frame
-    panoptic maps are not retained (the tube wire format carries the masks as RLE rows)."""
-    if keep_results:
+    panoptic maps are not retained (the tube wire format carries the masks as RLE rows).
+    Under torch.distributed (world size > 1) ``frames`` is this rank's contiguous block of the clip
+    (``tubes.shard_frames``) and ``num_frames`` the clip length: the kept (segment id, query feature) entries are
+    all-gathered once (``tubes.gather_and_link``), every rank links the same clip-wide tubes and runs the ~1 ms
+    relation stage on them; ``linker.rows`` (masks.txt) holds only the rows of this rank's frames."""
+    device = next(detector.parameters()).device
+    if _world() > 1:
+        if num_frames is None:
+            raise ValueError('run_clip: num_frames (clip length) is required when the clip is sharded over ranks')
+        entries, rows = [], []
+
+        def consume(r):
+            ids = [int(k) for k in r['query_feats'].keys()]
+            feats = np.stack([np.asarray(torch.as_tensor(r['query_feats'][k][0]).cpu()) for k in ids]) if ids \
+                else np.zeros((0, 256), np.float32)
+            entries.append((ids, feats))
+            if 'rle' in r:
+                rows.append((ids, r['rle'], r['pan_results'].shape))
+
+        results = None
+        if keep_results:
+            results = vps_clip(detector, frames, meta, batch)
+            for r in results:
+                consume(r)
+        else:
+            vps_clip(detector, frames, meta, batch, consume=consume)
+        linker = tubes.gather_and_link(entries, num_frames, device=device)
+        import torch.distributed as dist
+        lo, _ = tubes.shard_frames(num_frames, dist.get_world_size(), dist.get_rank())
+        for f, (ids, rle, hw) in enumerate(rows):       # masks.txt rows of the frames this rank owns, clip-wide ids
+            linker.rows.extend((lo + f + 1, linker._tube_of[i], i % 1000, hw[0], hw[1], rle[i]) for i in ids)
+    elif keep_results:
         results = vps_clip(detector, frames, meta, batch)
         linker = link_tubes(results, len(frames))
     else:
         results, linker = None, tubes.TubeLinker()
         vps_clip(detector, frames, meta, batch, consume=lambda r: _add_result(linker, r))
-    rel, raw = relations(linker, models, num_top_pairs, device=next(detector.parameters()).device)
+    rel, raw = relations(linker, models, num_top_pairs, device=device)
     return dict(results=results, linker=linker, relations=rel, raw=raw)
 
 
@@ -134,7 +169,7 @@ def relation_set_clip(detector, frames, meta, gt_maps, object_list, gt_relations
     def consume(r):
         _add_result(linker, r)
         ids = [int(k) for k in r['query_feats'].keys()]
-        slot_tubes.append([linker.object_list.index(i) + 1 for i in ids])
+        slot_tubes.append([linker._tube_of[i] for i in ids])
         held.append((torch.as_tensor(r['pan_results']).to(device=device, dtype=torch.int32), ids))
         if len(held) == batch:
             flush()
@@ -144,7 +179,7 @@ def relation_set_clip(detector, frames, meta, gt_maps, object_list, gt_relations
     counts = np.stack(counts) if counts else np.zeros((0, num_gt + 1, max_segments + 1), np.int32)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        entries = [(ids, np.stack([linker.feat_tubes[linker.object_list.index(i) + 1][t]['query_feat'] for i in ids])
+        entries = [(ids, np.stack([linker.feat_tubes[linker._tube_of[i]][t]['query_feat'] for i in ids])
                     if ids else np.zeros((0, 256), np.float32)) for t, ids in enumerate(linker.frame_seg_ids)]
         return relation_set.assemble_sharded(entries, counts, num_frames, object_list, gt_relations, device=device,
                                              max_segments=max_segments)

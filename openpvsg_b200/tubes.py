@@ -144,10 +144,19 @@ class TubeLinker:
 
     def __init__(self):
         self.object_list = []
+        self._tube_of = {}      # panoptic id -> tube id (the reference searches object_list linearly, utils.py:38-42)
         self.feat_tubes = {}
         self.rows = []          # (frame (1-based), tube id, class id, h, w, rle string)
         self.frame_seg_ids = []  # per frame: kept panoptic ids in slot order (what pvsg_rle_events / pvsg_tube_overlap index)
         self.num_frames = 0
+
+    def _tube(self, ins_id):
+        tid = self._tube_of.get(ins_id)
+        if tid is None:
+            self.object_list.append(ins_id)
+            tid = self._tube_of[ins_id] = len(self.object_list)
+            self.feat_tubes[tid] = {}
+        return tid
 
     def add_frame(self, seg_ids, feats, pan=None, rle=None, hw=None):
         """seg_ids: iterable of panoptic ids kept in this frame (reference dict order);
@@ -157,11 +166,7 @@ class TubeLinker:
         seg_ids = [int(i) for i in seg_ids]
         self.frame_seg_ids.append(seg_ids)
         for ins_id, feat in zip(seg_ids, feats):
-            ins_id = int(ins_id)
-            if ins_id not in self.object_list:
-                self.object_list.append(ins_id)
-                self.feat_tubes[len(self.object_list)] = {}
-            tid = self.object_list.index(ins_id) + 1
+            tid = self._tube(ins_id)
             self.feat_tubes[tid][frame_id] = dict(query_feat=np.array(feat, dtype=np.float32, copy=True).reshape(-1),
                                                   cls_id=int(ins_id % 1000))
             if rle is not None:
@@ -171,6 +176,24 @@ class TubeLinker:
                 self.rows.append((frame_id + 1, tid, int(ins_id % 1000), mask.shape[0], mask.shape[1],
                                   rle_string(rle_counts(mask))))
         self.num_frames += 1
+
+    def add_frames_bulk(self, counts, ids, feats):
+        """Link a whole block of frames from compact arrays (the all-gathered form): counts int [F] kept segments
+        per frame, ids int [n] their panoptic ids in frame order, feats fp32 [n,256].  Same result as F calls of
+        ``add_frame``; the per-entry Python work is two dict operations (no array copies, no list searches)."""
+        counts = np.asarray(counts, np.int64)
+        ids = np.asarray(ids, np.int64)
+        feats = np.ascontiguousarray(feats, np.float32).reshape(len(ids), -1)
+        if int(counts.sum()) != len(ids):
+            raise ValueError('add_frames_bulk: counts do not add up to the number of entries')
+        frame_of = np.repeat(np.arange(len(counts)), counts) + self.num_frames
+        id_list = ids.tolist()
+        bounds = np.concatenate(([0], np.cumsum(counts))).tolist()
+        for f in range(len(counts)):
+            self.frame_seg_ids.append(id_list[bounds[f]:bounds[f + 1]])
+        for k, (ins_id, fr) in enumerate(zip(id_list, frame_of.tolist())):
+            self.feat_tubes[self._tube(ins_id)][fr] = dict(query_feat=feats[k], cls_id=ins_id % 1000)
+        self.num_frames += len(counts)
 
     def tube_features(self, feature_dim=256):
         """[N_tubes, T, 256] with zero rows for absent frames -- the relation head's input
@@ -183,7 +206,7 @@ class TubeLinker:
 
     def frame_tube_ids(self):
         """Per frame: tube id of every slot (slot = position of a kept panoptic id in the frame's result)."""
-        return [[self.object_list.index(i) + 1 for i in ids] for ids in self.frame_seg_ids]
+        return [[self._tube_of[i] for i in ids] for ids in self.frame_seg_ids]
 
     def masks_txt(self):
         return ''.join(f'{fr} {tid} {cid} {h} {w} {rle}\n' for fr, tid, cid, h, w, rle in self.rows)
@@ -212,38 +235,63 @@ def shard_frames(num_frames, world_size, rank):
     return lo, min(lo + per, num_frames)
 
 
-def pack_frames(frame_entries, max_frames, max_segments, feature_dim=256, device='cpu'):
-    """frame_entries: list over local frames of (seg_ids list, feats [n,256]).  Fixed-size tensors
-    for the all-gather: ids int32 [max_frames, max_segments] (-1 = empty), feats fp32."""
-    ids = torch.full((max_frames, max_segments), -1, dtype=torch.int32)
-    feats = torch.zeros(max_frames, max_segments, feature_dim)
-    for f, (sid, ft) in enumerate(frame_entries):
-        n = len(sid)
-        if n:
-            ids[f, :n] = torch.as_tensor(list(sid), dtype=torch.int32)
-            feats[f, :n] = torch.as_tensor(np.asarray(ft, np.float32).reshape(n, -1))
-    return ids.to(device), feats.to(device)
+def pack_frames(frame_entries, feature_dim=256):
+    """frame_entries: list over local frames of (seg_ids list, feats [n,256]).  Compact form of a frame block:
+    (counts int32 [F], ids int32 [n], feats fp32 [n,feature_dim]) -- only kept entries, no padding."""
+    counts = np.fromiter((len(sid) for sid, _ in frame_entries), np.int32, len(frame_entries))
+    n = int(counts.sum())
+    ids = np.fromiter((int(i) for sid, _ in frame_entries for i in sid), np.int32, n)
+    feats = np.empty((n, feature_dim), np.float32)
+    k = 0
+    for sid, ft in frame_entries:
+        if len(sid):
+            feats[k:k + len(sid)] = np.asarray(ft, np.float32).reshape(len(sid), feature_dim)
+            k += len(sid)
+    return counts, ids, feats
 
 
-def gather_and_link(frame_entries, num_frames, max_segments=100, device='cpu'):
-    """All-gather the per-frame kept entries of every rank (NCCL when the tensors are on the
-    GPU, gloo on CPU) and link tubes over the whole clip.  Every rank returns the same
-    TubeLinker (without masks.txt rows: masks stay on the rank that owns the frame)."""
+def gather_and_link(frame_entries, num_frames, max_segments=100, device='cpu', feature_dim=256):
+    """The one exchange of the path: all-gather the kept (segment id, query feature) entries of every rank's
+    frame block (NCCL over NVLink when ``device`` is a GPU, gloo on CPU) and link tubes over the whole clip.
+    Every rank returns the same TubeLinker (without masks.txt rows: masks stay on the rank that owns the frame).
+
+    Wire format per rank: ONE fp32 buffer [per + n_max * (1 + feature_dim)] = frame counts | ids | features
+    (ids / counts < 2^24 are exact in fp32), n_max = the largest entry count of any rank (a 4-byte all-gather
+    precedes the payload).  Only kept entries travel: ~4 KB per frame instead of the 100-slot padded 103 KB."""
     import torch.distributed as dist
     ws = dist.get_world_size() if dist.is_initialized() else 1
     per = (num_frames + ws - 1) // ws
-    ids, feats = pack_frames(frame_entries, per, max_segments, device=device)
-    if ws > 1:
-        all_ids = [torch.empty_like(ids) for _ in range(ws)]
-        all_feats = [torch.empty_like(feats) for _ in range(ws)]
-        dist.all_gather(all_ids, ids)
-        dist.all_gather(all_feats, feats)
-    else:
-        all_ids, all_feats = [ids], [feats]
-    ids = torch.cat(all_ids, 0)[:num_frames].cpu().numpy()
-    feats = torch.cat(all_feats, 0)[:num_frames].cpu().numpy()
+    if len(frame_entries) > per:
+        raise ValueError(f'gather_and_link: {len(frame_entries)} local frames exceed the block size {per}')
+    counts, ids, feats = pack_frames(frame_entries, feature_dim)
+    if ids.size and (int(ids.max()) >= 1 << 24 or int(ids.min()) < 0 or int(counts.max()) > max_segments):
+        raise ValueError('gather_and_link: segment ids must be in [0, 2^24) and at most max_segments per frame')
+    if ws == 1:
+        linker = TubeLinker()
+        linker.add_frames_bulk(counts, ids, feats)
+        return linker
+    n = torch.tensor([len(ids)], dtype=torch.int64, device=device)
+    all_n = [torch.empty_like(n) for _ in range(ws)]
+    dist.all_gather(all_n, n)
+    all_n = [int(t.item()) for t in all_n]
+    n_max = max(all_n)
+    buf = np.zeros(per + n_max * (1 + feature_dim), np.float32)
+    buf[:len(counts)] = counts
+    buf[per:per + len(ids)] = ids
+    buf[per + n_max:per + n_max + feats.size] = feats.reshape(-1)
+    local = torch.from_numpy(buf).to(device, non_blocking=True)
+    gathered = torch.empty(ws * buf.size, dtype=torch.float32, device=device)
+    dist.all_gather(list(gathered.view(ws, -1).unbind(0)), local)
+    g = gathered.view(ws, -1).cpu().numpy()
     linker = TubeLinker()
-    for f in range(num_frames):
-        keep = ids[f] >= 0
-        linker.add_frame(ids[f][keep].tolist(), feats[f][keep])
+    left = num_frames
+    for r in range(ws):
+        f = min(per, left)
+        left -= f
+        c = g[r, :f].astype(np.int64)
+        m = int(c.sum())
+        if m > all_n[r]:
+            raise ValueError('gather_and_link: inconsistent frame counts')
+        linker.add_frames_bulk(c, g[r, per:per + m].astype(np.int64),
+                               g[r, per + n_max:per + n_max + m * feature_dim].reshape(m, feature_dim))
     return linker

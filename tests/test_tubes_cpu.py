@@ -63,6 +63,34 @@ def test_concat_seq_matches_oracle():
     assert tubes.concat_seq([[dict(pan_results=np.full((4, 4), 126, np.int32), query_feats={})]]).rows == []
 
 
+def test_bulk_linking_equals_incremental():
+    """TubeLinker.add_frames_bulk (the all-gathered compact form) == frame-by-frame add_frame, incl. empty frames,
+    a stuff id kept in several frames and a block appended after incremental frames."""
+    outs = _fake_outputs(num_frames=11, seed=5)
+    ref = tubes.concat_seq(outs)
+    entries = []
+    for o in outs:
+        ids = list(o[0]['query_feats'].keys())
+        entries.append((ids, [o[0]['query_feats'][k][0].numpy() for k in ids]))
+    counts, ids, feats = tubes.pack_frames(entries)
+    assert counts.tolist() == [len(e[0]) for e in entries] and feats.shape == (len(ids), 256)
+    lk = tubes.TubeLinker()
+    for e in entries[:4]:
+        lk.add_frame(*e)
+    c2, i2, f2 = tubes.pack_frames(entries[4:])
+    lk.add_frames_bulk(c2, i2, f2)
+    assert lk.object_list == ref.object_list and lk.num_frames == ref.num_frames
+    assert lk.frame_seg_ids == ref.frame_seg_ids and lk.frame_tube_ids() == ref.frame_tube_ids()
+    assert np.array_equal(lk.tube_features(), ref.tube_features())
+    for tid in ref.feat_tubes:
+        assert {f: d['cls_id'] for f, d in lk.feat_tubes[tid].items()} == {f: d['cls_id'] for f, d in ref.feat_tubes[tid].items()}
+    with pytest.raises(ValueError):
+        tubes.TubeLinker().add_frames_bulk([2], [5], np.zeros((1, 256), np.float32))
+    # single process gather_and_link = the bulk path
+    one = tubes.gather_and_link(entries, len(entries))
+    assert one.object_list == ref.object_list and np.array_equal(one.tube_features(), ref.tube_features())
+
+
 def test_shard_frames():
     for T, G in ((100, 1), (300, 8), (380, 8), (5, 8), (0, 2)):
         blocks = [tubes.shard_frames(T, G, r) for r in range(G)]
@@ -87,6 +115,7 @@ def _worker(rank, world, port, outs, q):
 
 def test_gather_and_link_world2_gloo():
     outs = _fake_outputs(num_frames=9, seed=3)
+    outs[6][0]['query_feats'] = {}          # a frame that keeps nothing
     ref = tubes.concat_seq(outs)
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
