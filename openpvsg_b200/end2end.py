@@ -21,14 +21,14 @@ from . import engine, relation_head as rh, relation_set, tubes
 
 
 @torch.no_grad()
-def vps_clip(detector, frames, meta, batch=8, rle=True, consume=None):
+def vps_clip(detector, frames, meta, batch=8, rle=True, consume=None, debug_masks=False):
     """frames: list of [3,H,W] tensors (pinned host or device).  Returns the per-frame result dicts
     (reference format, plus 'rle' strings) of this rank's frames, pipelined through the runner.
     consume(result): called per frame as soon as its batch is collected; the results are then views
     of the runner's pinned ring (no 13 MB-per-frame host copies) and nothing is retained."""
     if getattr(detector, '_runners', None) is None:
         engine.enable_cuda_graph(detector)
-    runner = engine.get_runner(detector, meta, True, batch=batch, rle=rle)
+    runner = engine.get_runner(detector, meta, True, batch=batch, rle=rle, debug_masks=debug_masks)
     results, pend = [], None
 
     def drain(p):
@@ -91,7 +91,8 @@ def _world():
 
 
 @torch.no_grad()
-def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_results=False, num_frames=None):
+def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_results=False, num_frames=None,
+             debug_masks=False):
     """The whole path for one clip.  Returns dict(results, linker, relations, raw).
     With keep_results=False (default) frames are linked as their batch completes and the per-frame
     panoptic maps are not retained (the tube wire format carries the masks as RLE rows).
@@ -115,7 +116,7 @@ def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_re
 
         results = None
         if keep_results:
-            results = vps_clip(detector, frames, meta, batch)
+            results = vps_clip(detector, frames, meta, batch, debug_masks=debug_masks)
             for r in results:
                 consume(r)
         else:
@@ -126,7 +127,7 @@ def run_clip(detector, models, frames, meta, batch=8, num_top_pairs=100, keep_re
         for f, (ids, rle, hw) in enumerate(rows):       # masks.txt rows of the frames this rank owns, clip-wide ids
             linker.rows.extend((lo + f + 1, linker._tube_of[i], i % 1000, hw[0], hw[1], rle[i]) for i in ids)
     elif keep_results:
-        results = vps_clip(detector, frames, meta, batch)
+        results = vps_clip(detector, frames, meta, batch, debug_masks=debug_masks)
         linker = link_tubes(results, len(frames))
     else:
         results, linker = None, tubes.TubeLinker()

@@ -25,6 +25,7 @@ from . import ops
 from .mask2former import INSTANCE_OFFSET, bbox2result
 
 RING = 3
+DEBUG_MASKS = False   # parity tests: every runner also returns the decoder's sign masks and class logits
 _copy_pool = None
 
 
@@ -64,12 +65,13 @@ def postprocess_batch(det, cls, mask_lr, in_hw, img_hw, out_hw):
 class FrameRunner:
     """Captured per (H, W) frame shape for a ``Mask2FormerVideoCustom`` (clip length 1)."""
 
-    def __init__(self, detector, meta, rescale=True, batch=1, lanes=None, rle=False):
+    def __init__(self, detector, meta, rescale=True, batch=1, lanes=None, rle=False, debug_masks=False):
         self.det = detector
         self.meta = dict(meta)
         self.rescale = rescale
         self.batch = int(batch)
         self.rle = bool(rle)      # also emit the tube wire format's run-length events (ops.rle_events)
+        self.debug_masks = bool(debug_masks)   # parity tests: also return the decoder's sign masks (attn_mask_<layer>)
         dev = next(detector.parameters()).device
         self.dev = dev
         hp, wp = meta['batch_input_shape']
@@ -113,13 +115,22 @@ class FrameRunner:
     def _device_forward(self):
         det, meta, B = self.det, self.meta, self.batch
         feats = det.extract_feat(self.static_in)
-        cls, mask_lr, query = det.panoptic_head.simple_test_with_query(feats, [[meta]] * B, upsample=False)
+        if self.debug_masks:
+            det.panoptic_head._capture_masks = []
+        try:
+            cls, mask_lr, query = det.panoptic_head.simple_test_with_query(feats, [[meta]] * B, upsample=False)
+        finally:
+            captured, det.panoptic_head._capture_masks = det.panoptic_head._capture_masks, None
         fh = det.panoptic_fusion_head
         in_hw = tuple(meta['batch_input_shape'])
         img_hw = tuple(meta['img_shape'][:2])
         out_hw = tuple(meta['ori_shape'][:2]) if self.rescale else img_hw
         out = postprocess_batch(det, cls, mask_lr[:, 0].contiguous(), in_hw, img_hw, out_hw)
         out['query'] = query.transpose(0, 1).contiguous()      # [B,Q,C]
+        if self.debug_masks:
+            out['cls'] = cls.contiguous()
+            for i, m in enumerate(captured):
+                out[f'attn_mask_{i}'] = m
         if self.rle:
             out['rle_pos'], out['rle_slot'], out['rle_n'] = ops.rle_events(out['pan'], out['seg_info'])
         return out
@@ -221,6 +232,9 @@ class FrameRunner:
                     from . import tubes
                     res['rle'] = tubes.rle_from_events(hb['rle_pos'].numpy(), hb['rle_slot'].numpy(), int(hb['rle_n']),
                                                        tubes.slot_ids(hb['seg_info'].numpy()), *hb['pan'].shape)
+            if self.debug_masks:
+                res['attn_masks'] = [hb[f'attn_mask_{i}'].numpy().copy() for i in range(len(hb)) if f'attn_mask_{i}' in hb]
+                res['cls'] = hb['cls'].numpy().copy()
             if 'ins_boxes' in hb:
                 n = min(TOPK_INS, int(hb['ins_count'][0]))
                 labels = hb['ins_labels'][:n]
@@ -257,14 +271,15 @@ def weights_epoch(detector):
     return hash((ts[0],) + tuple(t._version for t in ts[1]))
 
 
-def get_runner(detector, meta, rescale=True, batch=1, rle=False):
+def get_runner(detector, meta, rescale=True, batch=1, rle=False, debug_masks=False):
+    debug_masks = bool(debug_masks or DEBUG_MASKS)
     key = (tuple(meta['batch_input_shape']), tuple(meta['img_shape']), tuple(meta['ori_shape']), bool(rescale),
-           int(batch), bool(rle))
+           int(batch), bool(rle), debug_masks)
     runners = detector._runners
     epoch = weights_epoch(detector)
     if getattr(detector, '_runners_epoch', None) != epoch:
         runners.clear()               # weights changed under the captured graphs: drop them, re-capture on demand
         detector._runners_epoch = epoch
     if key not in runners:
-        runners[key] = FrameRunner(detector, meta, rescale, batch, rle=rle)
+        runners[key] = FrameRunner(detector, meta, rescale, batch, rle=rle, debug_masks=debug_masks)
     return runners[key]

@@ -680,6 +680,9 @@ class _Mask2FormerHeadBase(_Prepared):
                                         nn.Linear(feat_channels, out_channels))
         self.test_cfg, self.train_cfg = test_cfg, train_cfg
         self._pe_cache = {}
+        # debug / parity hook: when set to a list, ``_run`` appends the raw sign masks (uint8 [B,Q,hw], non-zero =
+        # blocked) it computes for decoder layers 0..L-1, so a test can resolve near-threshold ties the same way
+        self._capture_masks = None
 
     def init_weights(self):
         pass
@@ -770,6 +773,8 @@ class _Mask2FormerHeadBase(_Prepared):
         if want_all:
             mask_list.append(ops.mask_logits(me, mf_flat, True, False, mf_planes)[0].view(B, Q, T, h4, w4).transpose(1, 2))
         _, mask, row_open = ops.mask_logits(me, pooled[0], False, True, pooled_planes[0])
+        if self._capture_masks is not None:
+            self._capture_masks.append(mask)
         if force_masks is not None:  # tests: teacher-force the discrete masks (see tests/test_models_gpu.py)
             mask, row_open = self._forced(force_masks[0])
         q_planes = None
@@ -786,6 +791,8 @@ class _Mask2FormerHeadBase(_Prepared):
             if not last:
                 nxt = (i + 1) % self.num_transformer_feat_level
                 _, mask, row_open = ops.mask_logits(me, pooled[nxt], False, True, pooled_planes[nxt])
+                if self._capture_masks is not None:
+                    self._capture_masks.append(mask)
                 if force_masks is not None:
                     mask, row_open = self._forced(force_masks[i + 1])
         return dict(cls=cls_list, masks=mask_list, query=query)

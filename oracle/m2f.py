@@ -229,7 +229,7 @@ def decoder_layer(sd, p, query, key, value, query_pos, key_pos, attn_mask):
 # --------------------------------------------------------------------------
 # head: models/mask2former/mask2former_head.py, models/mask2former_vps/mask2former_video_head.py
 # --------------------------------------------------------------------------
-def forward_head(sd, prefix, decoder_out, mask_feature, attn_mask_target_size, num_heads=8):
+def forward_head(sd, prefix, decoder_out, mask_feature, attn_mask_target_size, num_heads=8, return_attn_logits=False):
     """models/mask2former/mask2former_head.py:355-395.
 
     decoder_out [Q, B, C]; mask_feature [B, C, h, w].
@@ -243,11 +243,14 @@ def forward_head(sd, prefix, decoder_out, mask_feature, attn_mask_target_size, n
     mask_pred = torch.einsum('bqc,bchw->bqhw', me, mask_feature)
     attn_mask = F.interpolate(mask_pred, attn_mask_target_size, mode='bilinear', align_corners=False)
     attn_mask = attn_mask.flatten(2).unsqueeze(1).repeat((1, num_heads, 1, 1)).flatten(0, 1)
+    if return_attn_logits:
+        return cls_pred, mask_pred, attn_mask.sigmoid() < 0.5, attn_mask
     attn_mask = attn_mask.sigmoid() < 0.5
     return cls_pred, mask_pred, attn_mask
 
 
-def forward_head_video(sd, prefix, decoder_out, mask_feature, attn_mask_target_size, num_heads=8):
+def forward_head_video(sd, prefix, decoder_out, mask_feature, attn_mask_target_size, num_heads=8,
+                       return_attn_logits=False):
     """models/mask2former_vps/mask2former_video_head.py:337-359.
 
     mask_feature [B, T, C, h, w] -> mask_pred [B, T, Q, h, w].
@@ -264,16 +267,41 @@ def forward_head_video(sd, prefix, decoder_out, mask_feature, attn_mask_target_s
                               align_corners=False).unflatten(0, (bs, nf))
     attn_mask = attn_mask.flatten(3).unsqueeze(1).repeat((1, num_heads, 1, 1, 1)).flatten(0, 1)
     attn_mask = attn_mask.transpose(1, 2).flatten(2)
+    if return_attn_logits:
+        return cls_pred, mask_pred, attn_mask.sigmoid() < 0.5, attn_mask
     attn_mask = attn_mask.sigmoid() < 0.5
     return cls_pred, mask_pred, attn_mask
 
 
+def _resolve_ties(attn_mask, attn_logits, other, tie_eps, stats, layer):
+    """Tie-aware comparison of a discrete decision (tests only).  The attention mask is a SIGN TEST on fp32
+    logits (mask2former_head.py:391), so two correct fp32 implementations may disagree on a bit whose logit is
+    within re-association noise of zero.  ``other`` is another implementation's mask for the same layer
+    ([B, Q, hw] or [B*heads, Q, hw], non-zero = blocked): where it differs from ours AND our logit is within
+    ``tie_eps`` of the threshold, its decision is adopted (so the two runs stay comparable downstream); differing
+    bits farther than ``tie_eps`` from the threshold are genuine errors and are only counted."""
+    other = torch.as_tensor(other).bool()
+    heads = attn_mask.shape[0] // other.shape[0]
+    if heads > 1:      # [B, Q, hw] -> [B*heads, Q, hw] in the reference's order (index = b * heads + h)
+        other = other.unsqueeze(1).repeat(1, heads, 1, 1).flatten(0, 1)
+    diff = other != attn_mask
+    tie = attn_logits.abs() < tie_eps
+    per_head = lambda m: int(m.sum()) // heads      # noqa: E731  (every head carries the same mask)
+    stats.append(dict(layer=layer, flipped_ties=per_head(diff & tie), flipped_non_ties=per_head(diff & ~tie),
+                      near_threshold=per_head(tie),
+                      max_abs_logit_of_flips=float(attn_logits[diff].abs().max()) if diff.any() else 0.0))
+    return torch.where(diff & tie, other, attn_mask)
+
+
 def head_forward(sd, feats, video=False, num_frames=1, prefix='panoptic_head.', num_layers=9,
-                 return_all=False):
+                 return_all=False, tie_masks=None, tie_eps=1e-3):
     """Mask2FormerHeadCustom.forward (models/mask2former/mask2former_head.py:397-479) /
     Mask2FormerVideoHead.forward (models/mask2former_vps/mask2former_video_head.py:361-462).
 
     Returns (cls_pred_list, mask_pred_list, query_feat[, extras]).
+    tie_masks (tests only): the attention masks ANOTHER implementation computed for layers 0..num_layers-1
+    (raw sign masks, before the all-blocked-row rule); near-threshold disagreements are resolved in its favour
+    (``_resolve_ties``) and reported in extras['tie_stats'].
     """
     mask_features, memories = pixel_decoder(sd, feats, prefix + 'pixel_decoder.')
     if video:
@@ -300,33 +328,42 @@ def head_forward(sd, feats, video=False, num_frames=1, prefix='panoptic_head.', 
     query_feat = sd[prefix + 'query_feat.weight'].unsqueeze(1).repeat((1, batch_size, 1))
     query_embed = sd[prefix + 'query_embed.weight'].unsqueeze(1).repeat((1, batch_size, 1))
     fh = forward_head_video if video else forward_head
-    cls_list, mask_list, attn_list = [], [], []
-    cls_pred, mask_pred, attn_mask = fh(sd, prefix, query_feat, mask_features, memories[0].shape[-2:])
+    cls_list, mask_list, attn_list, raw_list, tie_stats = [], [], [], [], []
+    cls_pred, mask_pred, attn_mask, attn_logits = fh(sd, prefix, query_feat, mask_features, memories[0].shape[-2:],
+                                                     return_attn_logits=True)
     cls_list.append(cls_pred)
     mask_list.append(mask_pred)
     for i in range(num_layers):
         level_idx = i % 3
         attn_mask = attn_mask.clone()
+        raw_list.append(attn_mask.clone())      # the sign mask before tie resolution / the all-blocked-row rule
+        if tie_masks is not None:
+            attn_mask = _resolve_ties(attn_mask, attn_logits, tie_masks[i], tie_eps, tie_stats, i)
         attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False
         attn_list.append(attn_mask)
         query_feat = decoder_layer(
             sd, f'{prefix}transformer_decoder.layers.{i}.', query_feat,
             decoder_inputs[level_idx], decoder_inputs[level_idx], query_embed,
             decoder_pos[level_idx], attn_mask)
-        cls_pred, mask_pred, attn_mask = fh(sd, prefix, query_feat, mask_features,
-                                            memories[(i + 1) % 3].shape[-2:])
+        cls_pred, mask_pred, attn_mask, attn_logits = fh(sd, prefix, query_feat, mask_features,
+                                                         memories[(i + 1) % 3].shape[-2:], return_attn_logits=True)
         cls_list.append(cls_pred)
         mask_list.append(mask_pred)
     if return_all:
         return cls_list, mask_list, query_feat, dict(mask_features=mask_features, memories=memories,
-                                                      attn_masks=attn_list)
+                                                      attn_masks=attn_list, raw_attn_masks=raw_list, tie_stats=tie_stats)
     return cls_list, mask_list, query_feat
 
 
-def head_simple_test_with_query(sd, feats, batch_input_shape, video=False, num_frames=1):
+def head_simple_test_with_query(sd, feats, batch_input_shape, video=False, num_frames=1, tie_masks=None, tie_eps=1e-3,
+                                tie_stats=None):
     """models/mask2former/mask2former_head.py:650-681,
-    models/mask2former_vps/mask2former_video_head.py:637-669."""
-    cls_list, mask_list, query_feat = head_forward(sd, feats, video, num_frames)
+    models/mask2former_vps/mask2former_video_head.py:637-669.
+    tie_masks / tie_eps: see ``head_forward`` (tests only); the per-layer statistics are appended to ``tie_stats``."""
+    cls_list, mask_list, query_feat, extras = head_forward(sd, feats, video, num_frames, return_all=True,
+                                                           tie_masks=tie_masks, tie_eps=tie_eps)
+    if tie_stats is not None:
+        tie_stats.extend(extras['tie_stats'])
     mask_cls = cls_list[-1]
     mask_pred = mask_list[-1]
     if video:
@@ -444,17 +481,19 @@ def fusion_simple_test_with_query(mask_cls_results, mask_pred_results, query_fea
 # --------------------------------------------------------------------------
 # detectors
 # --------------------------------------------------------------------------
-def ips_simple_test(sd, img, img_metas, rescale=True, instance_on=True):
+def ips_simple_test(sd, img, img_metas, rescale=True, instance_on=True, return_raw=False, backbone=None, **tie):
     """Mask2FormerCustom.simple_test, models/mask2former/mask2former.py:121-191
-    (up to the numpy conversion of pan_results / query feats)."""
-    feats = resnet50(sd, img)
+    (up to the numpy conversion of pan_results / query feats).  **tie: tie_masks / tie_eps / tie_stats (tests)."""
+    feats = (backbone or resnet50)(sd, img)
     mask_cls, mask_pred, query_feats = head_simple_test_with_query(
-        sd, feats, img_metas[0]['batch_input_shape'])
+        sd, feats, img_metas[0]['batch_input_shape'], **tie)
     results = fusion_simple_test_with_query(mask_cls, mask_pred, query_feats, img_metas,
                                             rescale=rescale, instance_on=instance_on)
     for r in results:
         r['pan_results'] = r['pan_results'].numpy()
         r['query_feats'] = {k: [x.numpy() for x in v] for k, v in r['query_feats'].items()}
+    if return_raw:
+        return results, dict(cls=mask_cls, masks=mask_pred, embds=query_feats)
     return results
 
 
@@ -469,10 +508,13 @@ def match_from_embds(tgt_embds, cur_embds):
     return indices[1]
 
 
-def vps_simple_test(sd, ref_img, ref_img_metas, rescale=True, instance_on=True, return_raw=False, backbone=None):
+def vps_simple_test(sd, ref_img, ref_img_metas, rescale=True, instance_on=True, return_raw=False, backbone=None,
+                    tie_masks=None, tie_eps=1e-3, tie_stats=None):
     """Mask2FormerVideoCustom.simple_test, models/mask2former_vps/mask2former.py:125-223.
 
     ref_img [B, T, 3, H, W]; the shipped test config uses T = 1 and B = 1.
+    tie_masks (tests only): per frame of the flattened batch, the list of attention masks of another implementation
+    (see ``head_forward``); statistics are appended to ``tie_stats``.
     """
     bs, num_frame, three, h, w = ref_img.shape
     video_x = (backbone or resnet50)(sd, ref_img.reshape(bs * num_frame, three, h, w))
@@ -480,7 +522,8 @@ def vps_simple_test(sd, ref_img, ref_img_metas, rescale=True, instance_on=True, 
     for i in range(video_x[0].shape[0]):
         cur = [f[i].unsqueeze(0) for f in video_x]
         mask_cls, mask_pred, query_fea = head_simple_test_with_query(
-            sd, cur, ref_img_metas[0][0]['batch_input_shape'], video=True, num_frames=1)
+            sd, cur, ref_img_metas[0][0]['batch_input_shape'], video=True, num_frames=1,
+            tie_masks=None if tie_masks is None else tie_masks[i], tie_eps=tie_eps, tie_stats=tie_stats)
         pred_logits.append(mask_cls.squeeze())
         mask_pred_list.append(mask_pred.squeeze())
         query_pred_list.append(query_fea.permute(0, 2, 1).squeeze())
@@ -565,7 +608,8 @@ def concat_seq(outputs):
     return rows, feat_tubes
 
 
-def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True, backbone=None):
+def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True, backbone=None, tie_masks=None, tie_eps=1e-3,
+                       tie_stats=None, return_masks=False):
     """Mask2FormerVideoCustomMinVIS.simple_test, models/mask2former_vps/mask2former_min_vis.py:132-231
     (panoptic branch): per-frame heads, MinVIS matching, clip-averaged logits, per-frame fusion."""
     bs, num_frame, three, h, w = ref_img.shape
@@ -574,7 +618,8 @@ def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True, backbone=None):
     for i in range(num_frame):
         cur = [f[i].unsqueeze(0) for f in video_x]
         mask_cls, mask_pred, query_fea = head_simple_test_with_query(
-            sd, cur, ref_img_metas[0][0]['batch_input_shape'], video=True, num_frames=1)
+            sd, cur, ref_img_metas[0][0]['batch_input_shape'], video=True, num_frames=1,
+            tie_masks=None if tie_masks is None else tie_masks[i], tie_eps=tie_eps, tie_stats=tie_stats)
         pred_logits.append(mask_cls.squeeze())
         mask_pred_list.append(mask_pred.squeeze())
         query_pred_list.append(query_fea.permute(0, 2, 1).squeeze())
@@ -597,4 +642,6 @@ def minvis_simple_test(sd, ref_img, ref_img_metas, rescale=True, backbone=None):
                                align_corners=False)[:, 0]
         pan, _ = panoptic_postprocess_with_query(logits[0], mp, torch.zeros(mp.shape[0], 1))
         results.append(pan.numpy())
+    if return_masks:
+        return results, perms, logits, masks
     return results, perms, logits

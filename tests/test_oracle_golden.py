@@ -197,3 +197,97 @@ def test_rle_known_answer():
     assert om.rle_encode(np.ones((2, 2), np.uint8)) == [0, 4]
     # pycocotools string coding: small counts map to chr(48 + x)
     assert om.rle_to_string([1, 3, 6, 2]) == '1365'[:0] + ''.join(chr(48 + c) for c in (1, 3, 6)) + chr(48 + ((2 - 3) & 0x1f))
+
+
+def _hf():
+    tr = pytest.importorskip('transformers')
+    from transformers.models.mask2former import modeling_mask2former as mm
+    cfg = tr.Mask2FormerConfig(feature_size=256, mask_feature_size=256, hidden_dim=256, encoder_feedforward_dim=1024,
+                               encoder_layers=6, decoder_layers=10, num_attention_heads=8, dropout=0.0, dim_feedforward=2048,
+                               pre_norm=False, feature_strides=[4, 8, 16, 32], common_stride=4, activation_function='relu',
+                               use_pretrained_backbone=False)
+    return mm, cfg
+
+
+def test_assembled_pixel_decoder_vs_hf_mask2former():
+    """The ASSEMBLED mmdet ``MSDeformAttnPixelDecoder`` restatement (oracle/m2f.py::pixel_decoder: input convs + GN,
+    sine PE + level embedding, reference points, 6 x (MSDeformAttn, LN, FFN, LN), FPN step, mask-feature conv) against
+    an independent implementation of the same published module, HF transformers' ``Mask2FormerPixelDecoder``, with
+    the weights re-keyed.  (mmdet 2.25 is not installable here; this pins the assembly, the per-op
+    cross-checks above pin the parts.)"""
+    mm, cfg = _hf()
+    sd = syn.mask2former_state_dict(seed=7)
+    p = 'panoptic_head.pixel_decoder.'
+    hf = mm.Mask2FormerPixelDecoder(cfg, feature_channels=[256, 512, 1024, 2048]).eval()
+    m = {}
+    for i in range(3):
+        m[f'input_projections.{i}.0.weight'] = sd[f'{p}input_convs.{i}.conv.weight']
+        m[f'input_projections.{i}.0.bias'] = sd[f'{p}input_convs.{i}.conv.bias']
+        m[f'input_projections.{i}.1.weight'] = sd[f'{p}input_convs.{i}.gn.weight']
+        m[f'input_projections.{i}.1.bias'] = sd[f'{p}input_convs.{i}.gn.bias']
+    m['level_embed'] = sd[p + 'level_encoding.weight']
+    for l in range(6):
+        a, b = f'encoder.layers.{l}.', f'{p}encoder.layers.{l}.'
+        for name in ('sampling_offsets', 'attention_weights', 'value_proj', 'output_proj'):
+            for wb in ('weight', 'bias'):
+                m[f'{a}self_attn.{name}.{wb}'] = sd[f'{b}attentions.0.{name}.{wb}']
+        for wb in ('weight', 'bias'):
+            m[f'{a}self_attn_layer_norm.{wb}'] = sd[f'{b}norms.0.{wb}']
+            m[f'{a}final_layer_norm.{wb}'] = sd[f'{b}norms.1.{wb}']
+            m[f'{a}fc1.{wb}'] = sd[f'{b}ffns.0.layers.0.0.{wb}']
+            m[f'{a}fc2.{wb}'] = sd[f'{b}ffns.0.layers.1.{wb}']
+    m['mask_projection.weight'], m['mask_projection.bias'] = sd[p + 'mask_feature.weight'], sd[p + 'mask_feature.bias']
+    m['adapter_1.0.weight'] = sd[p + 'lateral_convs.0.conv.weight']
+    m['adapter_1.1.weight'], m['adapter_1.1.bias'] = sd[p + 'lateral_convs.0.gn.weight'], sd[p + 'lateral_convs.0.gn.bias']
+    m['layer_1.0.weight'] = sd[p + 'output_convs.0.conv.weight']
+    m['layer_1.1.weight'], m['layer_1.1.bias'] = sd[p + 'output_convs.0.gn.weight'], sd[p + 'output_convs.0.gn.bias']
+    missing = hf.load_state_dict(m, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    # odd sizes: every level has a different aspect, none divides the next exactly
+    feats = [_randn(10 + i, 2, c, h, w) for i, (c, h, w) in enumerate(((256, 36, 52), (512, 18, 26), (1024, 9, 13), (2048, 5, 7)))]
+    with torch.no_grad():
+        want = hf(feats)
+        mf, mem = om.pixel_decoder(sd, feats)
+    _close(mf, want.mask_features, 5e-5)
+    assert len(mem) == len(want.multi_scale_features) == 3
+    for a, b in zip(mem, want.multi_scale_features):
+        _close(a, b, 5e-5)
+
+
+def test_assembled_decoder_layer_vs_hf_mask2former():
+    """mmdet ``DetrTransformerDecoderLayer`` with operation order (cross_attn, norm, self_attn, norm, ffn, norm) and
+    mmcv ``MultiheadAttention`` semantics (oracle/m2f.py::decoder_layer) against HF's
+    ``Mask2FormerMaskedAttentionDecoderLayer`` (post-norm form) with re-keyed weights, masked cross-attention included."""
+    mm, cfg = _hf()
+    sd = syn.mask2former_state_dict(seed=7)
+    p = 'panoptic_head.transformer_decoder.layers.3.'
+    hf = mm.Mask2FormerMaskedAttentionDecoderLayer(cfg).eval()
+    E = 256
+    w, b = sd[p + 'attentions.1.attn.in_proj_weight'], sd[p + 'attentions.1.attn.in_proj_bias']
+    m = {'cross_attn.in_proj_weight': sd[p + 'attentions.0.attn.in_proj_weight'],
+         'cross_attn.in_proj_bias': sd[p + 'attentions.0.attn.in_proj_bias'],
+         'cross_attn.out_proj.weight': sd[p + 'attentions.0.attn.out_proj.weight'],
+         'cross_attn.out_proj.bias': sd[p + 'attentions.0.attn.out_proj.bias'],
+         'self_attn.q_proj.weight': w[:E], 'self_attn.q_proj.bias': b[:E],
+         'self_attn.k_proj.weight': w[E:2 * E], 'self_attn.k_proj.bias': b[E:2 * E],
+         'self_attn.v_proj.weight': w[2 * E:], 'self_attn.v_proj.bias': b[2 * E:],
+         'self_attn.out_proj.weight': sd[p + 'attentions.1.attn.out_proj.weight'],
+         'self_attn.out_proj.bias': sd[p + 'attentions.1.attn.out_proj.bias']}
+    for wb in ('weight', 'bias'):
+        m[f'cross_attn_layer_norm.{wb}'] = sd[f'{p}norms.0.{wb}']
+        m[f'self_attn_layer_norm.{wb}'] = sd[f'{p}norms.1.{wb}']
+        m[f'final_layer_norm.{wb}'] = sd[f'{p}norms.2.{wb}']
+        m[f'fc1.{wb}'] = sd[f'{p}ffns.0.layers.0.0.{wb}']
+        m[f'fc2.{wb}'] = sd[f'{p}ffns.0.layers.1.{wb}']
+    missing = hf.load_state_dict(m, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    Q, B, L = 17, 2, 45
+    query, qpos = _randn(1, Q, B, E), _randn(2, Q, B, E)
+    key, kpos = _randn(3, L, B, E), _randn(4, L, B, E)
+    mask = torch.rand(B * 8, Q, L, generator=torch.Generator().manual_seed(5)) < 0.6
+    mask[:, 3] = False                       # an all-open row; all-blocked rows are unblocked by the head before the layer
+    with torch.no_grad():
+        want = hf.forward_post(query, level_index=0, position_embeddings=[kpos], query_position_embeddings=qpos,
+                               encoder_hidden_states=[key], encoder_attention_mask=mask)[0]
+        got = om.decoder_layer(sd, p, query, key, key, qpos, kpos, mask)
+    _close(got, want, 5e-5)

@@ -229,12 +229,24 @@ def test_swin_b_detector_features_and_forward():
     _close(mf, ref_mf, 1e-3, 'mask features')
     for a, b in zip(mem, ref_mem):
         _close(a, b, 1e-3, 'memory level')
-    # the whole detector runs and returns a well-formed panoptic result
+    # the whole detector, free-running, against the oracle detector (Swin oracle backbone + the Mask2Former oracle),
+    # tie-aware: panoptic ids, segment set, query features (oracle/parity.py)
+    from oracle import parity
     meta = syn.frame_meta(H, W)
-    res = det.simple_test(None, None, ref_img=img.to(cuda)[None], ref_img_metas=[[meta]], rescale=True)
-    pan = res[0][0]['pan_results']
-    assert pan.shape == (H, W) and pan.dtype in (np.int32, np.int64)
-    assert set(res[0][0]['query_feats']) <= set(np.unique(pan).tolist())
+    head = det.panoptic_head
+    head._capture_masks = []
+    try:
+        res = det.simple_test(None, None, ref_img=img.to(cuda)[None], ref_img_metas=[[meta]], rescale=True)[0][0]
+        gpu_masks = [m[0].cpu().numpy() for m in head._capture_masks]
+    finally:
+        head._capture_masks = None
+    pan = res['pan_results']
+    assert pan.shape == (H, W) and pan.dtype == np.int32
+    assert set(res['query_feats']) <= set(np.unique(pan).tolist())
+    backbone = lambda sd_, x: osw.swin_forward(sd_, x, prefix='backbone.', **configs.SWIN_B)   # noqa: E731
+    st = parity.check_frame(res, sd, img[0], meta, gpu_masks, what='swin-b detector', backbone=backbone)
+    assert st['pan_mismatch_pixels'] == 0, st
+    assert len(res['query_feats']) > 0, 'degenerate synthetic checkpoint: nothing kept'
 
 
 @pytest.mark.gpu
