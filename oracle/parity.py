@@ -52,7 +52,7 @@ def tie_pixels(cls, masks, meta, num_classes=126, object_mask_thr=0.8, rescale=T
     """Pixels whose panoptic id is not decided by a clear margin in the ORACLE's own scores: the top-2 candidates of
     ``score * sigmoid(mask)`` are within PIX_EPS (and at least one of them would be written), or the winner's mask
     logit is within PIX_EPS of 0 (the >= 0.5 test of filter_low_score).  cls [Q,NC+1], masks [Q,Hp,Wp] full-resolution
-    logits."""
+    logits.  Returns (tie mask, distance of every pixel's decision from a tie)."""
     ih, iw = meta['img_shape'][:2]
     mp = masks[:, :ih, :iw]
     if rescale:
@@ -60,7 +60,7 @@ def tie_pixels(cls, masks, meta, num_classes=126, object_mask_thr=0.8, rescale=T
     scores, labels = F.softmax(cls, dim=-1).max(-1)
     keep = labels.ne(num_classes) & (scores > object_mask_thr)
     if int(keep.sum()) == 0:
-        return torch.zeros(mp.shape[-2:], dtype=torch.bool).numpy()
+        return torch.zeros(mp.shape[-2:], dtype=torch.bool).numpy(), torch.full(mp.shape[-2:], 1e9).numpy()
     logits = mp[keep]
     prob = scores[keep].view(-1, 1, 1) * logits.sigmoid()
     if prob.shape[0] > 1:
@@ -75,7 +75,8 @@ def tie_pixels(cls, masks, meta, num_classes=126, object_mask_thr=0.8, rescale=T
     l1 = logits.gather(0, win[None])[0]
     # a swap of the two best candidates only shows if one of them passes the >= 0.5 test (filter_low_score)
     visible = (l1 > -PIX_EPS) | (l2 > -PIX_EPS)
-    return (((gap < PIX_EPS) & visible) | (l1.abs() < PIX_EPS)).numpy()
+    closeness = torch.minimum(torch.where(visible, gap, torch.full_like(gap, 1e9)), l1.abs())   # distance from a tie
+    return (closeness < PIX_EPS).numpy(), closeness.numpy()
 
 
 def assert_pan_tie_aware(pan, ref, what=''):
@@ -86,6 +87,9 @@ def assert_pan_tie_aware(pan, ref, what=''):
     diff = pan != ref_pan
     n = int(diff.sum())
     ties = ref.get('_tie_pixels')
+    if isinstance(ties, tuple):
+        ties, closeness = ties
+        ref['_max_tie_distance_of_mismatch'] = float(closeness[diff].max()) if n else 0.0
     if n:
         assert ties is not None, f'{what}: {n} panoptic ids differ'
         assert not (diff & ~ties).any(), f'{what}: {int((diff & ~ties).sum())} panoptic ids differ away from any tie'
@@ -111,4 +115,7 @@ def check_frame(res, sd, img, meta, gpu_masks, what='', video=True, backbone=Non
         cls_err = (torch.as_tensor(np.asarray(gpu_cls)).float().reshape(ref['cls'].shape) - ref['cls']).abs().max().item()
         assert cls_err <= TOL, f'{what}: class logits differ by {cls_err:.3e}'
     return dict(what=what, adopted_tie_bits=flips, near_threshold_bits=sum(s['near_threshold'] for s in ref['tie_stats']),
-                pan_mismatch_pixels=n_diff, pan_tie_pixels=n_tie, query_feat_max_err=err, cls_max_err=cls_err)
+                max_abs_logit_of_adopted_bits=max([s['max_abs_logit_of_flips'] for s in ref['tie_stats']] + [0.0]),
+                pan_mismatch_pixels=n_diff, pan_tie_pixels=n_tie,
+                max_tie_distance_of_mismatching_pixels=ref.get('_max_tie_distance_of_mismatch', 0.0),
+                pixels=int(np.asarray(res['pan_results']).size), query_feat_max_err=err, cls_max_err=cls_err)

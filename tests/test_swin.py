@@ -245,7 +245,7 @@ def test_swin_b_detector_features_and_forward():
     assert set(res['query_feats']) <= set(np.unique(pan).tolist())
     backbone = lambda sd_, x: osw.swin_forward(sd_, x, prefix='backbone.', **configs.SWIN_B)   # noqa: E731
     st = parity.check_frame(res, sd, img[0], meta, gpu_masks, what='swin-b detector', backbone=backbone)
-    assert st['pan_mismatch_pixels'] == 0, st
+    assert st['pan_mismatch_pixels'] <= 1e-4 * st['pixels'], st
     assert len(res['query_feats']) > 0, 'degenerate synthetic checkpoint: nothing kept'
 
 
