@@ -37,9 +37,11 @@ import torch  # noqa: E402
 
 H, W = 720, 1280
 METRIC = 'Mask2Former-VPS R50 inference frames/sec @720p'
-MSDA_KERNEL = 'msda_group_kernel'
-MSDA_NOTE = ('LSU-pipe / issue bound: 48 bilinear corner lines of 128 B per (query, head) pass through L1 '
-             '(ncu profiles/r01n_ncu_msda_group.json)')
+MSDA_KERNEL = 'msda_tile_kernel (csrc/msda_tile.cu: TMA-staged value windows in shared memory)'
+MSDA_NOTE = ('bound by the LSU data pipe (shared-memory crossbar, 128 B/clk/SM), not by HBM: 12 samples x 4 corners x 128 B per '
+             '(query, head) = 48 wavefronts minimum = 27 us per 720p frame and layer at 100 % of that pipe, against 9.5 us for the '
+             'algorithmic HBM bytes, i.e. a ceiling of ~0.35 of the HBM roofline for fp32 values; ncu: data pipe 75 % busy, DRAM traffic '
+             '0.99 x algorithmic (profiles/r02c_ncu_msda_tile.json, r02c_msda_traffic.json)')
 
 
 def load_peaks():

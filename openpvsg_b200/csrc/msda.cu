@@ -6,6 +6,8 @@
 // are combined with two warp shuffles.  In the fused variant the warp also does the
 // softmax over the L*P attention logits and the location arithmetic from the raw
 // projections, so sampling_locations / attention_weights never exist in memory.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -348,6 +350,14 @@ __global__ void __launch_bounds__(256, 4) msda_group_kernel(const float* __restr
     }
 }
 
+}  // namespace
+
+// csrc/msda_tile.cu: region-tiled kernel with TMA-staged value windows (queries = pyramid tokens, reference configuration)
+int pvsg_msda_tile_launch(const float* value, const int* hs, const int* ws, const int* starts, const float* proj,
+                          const float* ref, float* out, void* out_hi, void* out_lo, int B, int64_t N, void* stream);
+
+namespace {
+
 int fill_levels(MsdaLevels& lv, const int64_t* spatial_shapes, const int64_t* level_start_index, int L,
                 int64_t N) {
     if (L <= 0 || L > MAX_LEVELS) return PVSG_ERR_UNSUPPORTED;
@@ -381,6 +391,15 @@ int launch(const float* value, const int64_t* spatial_shapes, const int64_t* lev
         uint2* oh = reinterpret_cast<uint2*>(out_hi);
         uint2* ol = reinterpret_cast<uint2*>(out_lo);
         const bool ref_cfg = L == 3 && P == 4 && H == 8;     // fully unrolled instance
+        const char* impl = getenv("PVSG_MSDA_IMPL");      // debug switch: "group" forces the lane-group kernel
+        const bool force_group = impl != nullptr && impl[0] == 'g';
+        if (ref_cfg && Nq == N && !force_group) {
+            // the encoder's case: TMA-staged windows in shared memory (msda_tile.cu); other shapes use the lane-group kernel
+            const int hs[3] = {lv.h[0], lv.h[1], lv.h[2]}, ws[3] = {lv.w[0], lv.w[1], lv.w[2]};
+            const int starts[3] = {(int)lv.start[0], (int)lv.start[1], (int)lv.start[2]};
+            rc = pvsg_msda_tile_launch(value, hs, ws, starts, a, b2, out, out_hi, out_lo, B, N, stream);
+            if (rc != PVSG_ERR_UNSUPPORTED) return rc;
+        }
         if (Nq == N) {
             const int64_t total = (int64_t)B * H * lv.tile_start[L];
             const unsigned grid = (unsigned)imin64(total, 148 * 64);

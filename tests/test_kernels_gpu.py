@@ -206,6 +206,36 @@ def test_msda_fused_ragged_batch_and_free_queries(ops):
         close(out, ref.reshape(2, nq, 256), 1e-4, f'msda fused nq={nq}')
 
 
+@pytest.mark.parametrize('shapes,B,scale', [([(5, 6), (10, 12), (20, 24)], 2, 6.0), ([(2, 2), (4, 4), (8, 8)], 3, 3.0),
+                                            ([(23, 40), (46, 80), (92, 160)], 2, 1.7), ([(15, 20), (30, 40), (60, 80)], 1, 8.0)])
+def test_msda_region_tiled_kernel(ops, shapes, B, scale):
+    """csrc/msda_tile.cu (TMA-staged value windows, the encoder's kernel): regions cut by the map border (sizes that are
+    not multiples of the 16 x 8 region), maps smaller than one window, batches, and offsets far beyond the halo (the
+    compacted global-memory pass) and beyond the map (zero padding by TMA fill) -- against the oracle, and against
+    the lane-group kernel (PVSG_MSDA_IMPL=group), which must agree to re-association level."""
+    import os
+    n = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(int(scale * 10) + n)
+    value = torch.randn(B, n, 256, generator=g)
+    proj = torch.cat([torch.randn(B, n, 192, generator=g) * scale, torch.randn(B, n, 96, generator=g) * 2.0], -1)
+    refs = []
+    for h, w in shapes:
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+        refs.append(torch.stack(((xs.flatten() + 0.5) / w, (ys.flatten() + 0.5) / h), -1))
+    ref_pts = torch.cat(refs, 0)
+    want = _fused_ref(value, shapes, proj, ref_pts)
+    out = ops.msda_fused_forward(value.cuda(), shapes, proj.cuda(), ref_pts.cuda())
+    close(out, want.reshape(B, n, 256), 1e-4, 'msda tile')
+    sp = ops.msda_fused_forward(value.cuda(), shapes, proj.cuda(), ref_pts.cuda(), out_mode='split')
+    close(sp.hi.float() + sp.lo.float(), want.reshape(B, n, 256), 1e-4, 'msda tile planes')
+    os.environ['PVSG_MSDA_IMPL'] = 'group'
+    try:
+        old = ops.msda_fused_forward(value.cuda(), shapes, proj.cuda(), ref_pts.cuda())
+    finally:
+        del os.environ['PVSG_MSDA_IMPL']
+    close(out, old, 2e-5, 'tile vs lane-group kernel')
+
+
 # ------------------------------------------------------------------ attention --------
 def _mha_ref(q, k, v, H, mask=None):
     B, Lq, E = q.shape
