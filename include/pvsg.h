@@ -376,6 +376,14 @@ int pvsg_tube_overlap(const int32_t* gt, const int32_t* pan, const int32_t* seg_
 /* y[n,c] = max_t x[n,t,c]  (base.py:50-51). */
 int pvsg_max_over_time(const float* x, float* y, int N, int T, int C, void* stream);
 
+/* Temporal taps of x [P,T,C] (zero padded cross-correlation along T, odd K, C % 4 == 0), the two baseline relation
+ * models of models/relation_head/convolution.py:
+ *   pvsg_temporal_fir    y[p,t,c] = sum_k w[k] x[p,t+k-K/2,c]      HandcraftedFilter's depthwise F.conv1d (:26-30)
+ *   pvsg_temporal_unfold y[p,t,k*C+c] = x[p,t+k-K/2,c]  [P,T,K*C]  operand of Learnable1DConv's nn.Conv1d (:49-56),
+ *                                                                   which then runs as ONE pvsg_linear[_tc] GEMM. */
+int pvsg_temporal_fir(const float* x, const float* w, float* y, int P, int T, int C, int K, void* stream);
+int pvsg_temporal_unfold(const float* x, float* y, int P, int T, int C, int K, void* stream);
+
 /* PairProposalNetwork.forward (base.py:49-62), factorised: U = sub_tok W1[:, :F]^T + b1 and
  * V = obj_tok W1[:, F:]^T are precomputed [N,Hd] (two pvsg_linear calls);
  * pair[i,j] = b2 + sum_h w2[h] * relu(U[i,h] + V[j,h]) for i != j, 0 on the diagonal. */

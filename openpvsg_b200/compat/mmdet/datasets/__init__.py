@@ -1,0 +1,33 @@
+"""mmdet.datasets.build_dataloader / replace_ImageToTensor for test-mode loaders."""
+import torch
+from torch.utils.data import DataLoader, DistributedSampler
+
+
+def _collate(batch):
+    """Samples are dicts of tensors (stacked over the batch) and metas (kept as lists): the call signature of
+    BaseDetector.forward_test / Mask2FormerVideoCustom.forward_test -- img=[B,3,H,W] wrapped in the test-time
+    augmentation list, img_metas=[[dict] * B], ref_img=[B,T,3,H,W], ref_img_metas=[[dict] * T] * B."""
+    out = {}
+    for key in batch[0]:
+        vals = [b[key] for b in batch]
+        if key == 'img':
+            out[key] = [torch.stack(vals)]
+        elif key == 'img_metas':
+            out[key] = [vals]
+        elif torch.is_tensor(vals[0]):
+            out[key] = torch.stack(vals)
+        else:
+            out[key] = vals
+    return out
+
+
+def build_dataloader(dataset, samples_per_gpu=1, workers_per_gpu=0, num_gpus=1, dist=False, shuffle=False, seed=None,
+                     persistent_workers=False, **kwargs):
+    sampler = DistributedSampler(dataset, shuffle=False) if dist else None
+    return DataLoader(dataset, batch_size=samples_per_gpu, sampler=sampler, shuffle=False, num_workers=workers_per_gpu,
+                      collate_fn=_collate, pin_memory=torch.cuda.is_available(),
+                      persistent_workers=persistent_workers and workers_per_gpu > 0)
+
+
+def replace_ImageToTensor(pipelines):
+    return pipelines

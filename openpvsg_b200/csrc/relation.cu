@@ -16,6 +16,33 @@ __global__ void __launch_bounds__(256) max_over_time_kernel(const float* __restr
     y[i] = m;
 }
 
+// Temporal taps of a [P, T, C] tube-pair tensor (zero padded, cross-correlation as F.conv1d):
+//   FIR    : y[p,t,c]       = sum_k w[k] * x[p, t + k - K/2, c]          (HandcraftedFilter, convolution.py:26-30)
+//   UNFOLD : y[p,t,k*C + c] =              x[p, t + k - K/2, c]          (operand of Learnable1DConv's Conv1d as one GEMM)
+template <bool FIR>
+__global__ void __launch_bounds__(256) temporal_taps_kernel(const float4* __restrict__ x, const float* __restrict__ w,
+                                                            float4* __restrict__ y, int T, int C4, int K, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int64_t pt = i / C4;
+        const int t = (int)(pt % T);
+        const int64_t p = pt / T;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < K; ++k) {
+            const int ts = t + k - K / 2;
+            const float4 v = (ts >= 0 && ts < T) ? __ldg(x + (p * T + ts) * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FIR) {
+                const float wk = __ldg(w + k);
+                acc.x = fmaf(wk, v.x, acc.x); acc.y = fmaf(wk, v.y, acc.y);
+                acc.z = fmaf(wk, v.z, acc.z); acc.w = fmaf(wk, v.w, acc.w);
+            } else {
+                y[(pt * K + k) * C4 + c] = v;
+            }
+        }
+        if (FIR) y[i] = acc;
+    }
+}
+
 // One warp per (i, j): pair = b2 + sum_h w2[h] * relu(U[i,h] + V[j,h]); diagonal = 0.
 __global__ void __launch_bounds__(256) pair_kernel(const float* __restrict__ U, const float* __restrict__ V,
                                                    const float* __restrict__ w2, const float* __restrict__ b2,
@@ -188,6 +215,22 @@ extern "C" int pvsg_max_over_time(const float* x, float* y, int N, int T, int C,
     PVSG_CHECK_ARG(x && y && N > 0 && T > 0 && C > 0);
     const int64_t total = (int64_t)N * C;
     max_over_time_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, y, T, C, total);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_temporal_fir(const float* x, const float* w, float* y, int P, int T, int C, int K, void* stream) {
+    PVSG_CHECK_ARG(x && w && y && P > 0 && T > 0 && C > 0 && C % 4 == 0 && K > 0 && (K & 1));
+    const int64_t total = (int64_t)P * T * (C / 4);
+    temporal_taps_kernel<true><<<(unsigned)imin64((total + 255) / 256, 148 * 16), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), w, reinterpret_cast<float4*>(y), T, C / 4, K, total);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_temporal_unfold(const float* x, float* y, int P, int T, int C, int K, void* stream) {
+    PVSG_CHECK_ARG(x && y && P > 0 && T > 0 && C > 0 && C % 4 == 0 && K > 0 && (K & 1));
+    const int64_t total = (int64_t)P * T * (C / 4);
+    temporal_taps_kernel<false><<<(unsigned)imin64((total + 255) / 256, 148 * 16), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), nullptr, reinterpret_cast<float4*>(y), T, C / 4, K, total);
     return pvsg_launch_status();
 }
 

@@ -66,6 +66,8 @@ SIGNATURES = {
     'pvsg_patch_merge_ln': (I, [P, P, P, P, I, I, I, I, F, P]),
     'pvsg_tube_overlap': (I, [P, P, P, I, I, I, I, I, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
+    'pvsg_temporal_fir': (I, [P, P, P, I, I, I, I, P]),
+    'pvsg_temporal_unfold': (I, [P, P, I, I, I, I, P]),
     'pvsg_pair_proposal': (I, [P, P, P, P, P, I, I, P]),
     'pvsg_top_pairs': (I, [P, I, I, P, P, P]),
     'pvsg_gather_pairs': (I, [P, P, P, P, P, I, I, I, P]),

@@ -857,6 +857,25 @@ def max_over_time(x):
     return out
 
 
+def temporal_fir(x, w):
+    """x [P,T,C], w [K] (odd K) -> zero-padded cross-correlation along T (depthwise F.conv1d with one shared filter)."""
+    lib = _l.load()
+    Pn, T, C = _f32(x).shape
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    _l.check(lib.pvsg_temporal_fir(_ptr(x.contiguous()), _ptr(_f32(w).contiguous()), _ptr(y), Pn, T, C, w.numel(), _stream()),
+             'pvsg_temporal_fir')
+    return y
+
+
+def temporal_unfold(x, k):
+    """x [P,T,C] -> [P,T,k*C]: the k zero-padded temporal taps of every frame side by side (tap-major)."""
+    lib = _l.load()
+    Pn, T, C = _f32(x).shape
+    y = torch.empty(Pn, T, k * C, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_temporal_unfold(_ptr(x.contiguous()), _ptr(y), Pn, T, C, k, _stream()), 'pvsg_temporal_unfold')
+    return y
+
+
 def pair_proposal(U, V, w2, b2):
     lib = _l.load()
     N, Hd = _f32(U).shape

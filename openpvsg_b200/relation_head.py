@@ -187,27 +187,34 @@ class VanillaModel(_Inference):
 
 
 class HandcraftedFilter(_Inference):
-    """convolution.py:6-41 -- baseline kept constructor / state_dict compatible; its temporal
-    filter is outside the accelerated path (component 3)."""
+    """convolution.py:6-41: a fixed 5-tap temporal filter [1/4, 1/2, 1, 1/2, 1/4] on every channel (depthwise
+    F.conv1d, padding 2), then the VanillaModel heads.  ``tools/rel_test.py:167-175`` selects it with
+    ``--model-name filter``."""
 
     def __init__(self, feat_dim, num_relations):
         super().__init__()
         self.num_relations = num_relations
+        self.filter_weights = torch.tensor([1 / 4, 1 / 2, 1, 1 / 2, 1 / 4], dtype=torch.float32)   # plain attribute, as the reference
+        self.expanded_filter_weights = self.filter_weights.view(1, 1, -1).repeat(feat_dim, 1, 1)
         self.fc1 = nn.Linear(feat_dim, feat_dim // 2)
         self.fc2 = nn.Linear(feat_dim // 2, feat_dim // 4)
         self.span_head = nn.Linear(feat_dim // 4, num_relations)
         self.pred_head = nn.Linear(feat_dim // 4, num_relations)
         self.eval()
 
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError('HandcraftedFilter is a reference baseline outside the B200 hot path')
+        return _heads(self, ops.temporal_fir(x.contiguous(), self.filter_weights.to(x.device)))
 
 
 class Learnable1DConv(_Inference):
-    """convolution.py:44-75 -- see HandcraftedFilter."""
+    """convolution.py:44-75: ``num_layers`` x (Conv1d(C, C, k, padding k // 2) + ReLU) along time, then the
+    VanillaModel heads.  Each Conv1d is ONE GEMM over the k temporal taps laid side by side
+    (``ops.temporal_unfold`` -> [P*T, k*C] x [C, k*C]^T, bias + ReLU in the epilogue)."""
 
     def __init__(self, input_dim, num_relations, kernel_size=5, num_layers=1):
         super().__init__()
+        self.num_relations = num_relations
         layers = []
         for _ in range(num_layers):
             layers += [nn.Conv1d(input_dim, input_dim, kernel_size, padding=kernel_size // 2), nn.ReLU()]
@@ -216,10 +223,25 @@ class Learnable1DConv(_Inference):
         self.fc2 = nn.Linear(input_dim // 2, input_dim // 4)
         self.span_head = nn.Linear(input_dim // 4, num_relations)
         self.pred_head = nn.Linear(input_dim // 4, num_relations)
+        self._w = {}
         self.eval()
 
+    def _tap_major(self, conv):
+        """Conv1d weight [Cout, Cin, k] -> [Cout, k*Cin] matching temporal_unfold's column order."""
+        key = (id(conv), conv.weight._version, conv.weight.data_ptr())
+        if key not in self._w:
+            self._w = {key: conv.weight.permute(0, 2, 1).reshape(conv.out_channels, -1).contiguous()}
+        return self._w[key]
+
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError('Learnable1DConv is a reference baseline outside the B200 hot path')
+        x = x.contiguous()
+        for conv in self.conv_layers:
+            if isinstance(conv, nn.Conv1d):
+                if conv.kernel_size[0] % 2 == 0 or conv.padding[0] != conv.kernel_size[0] // 2:
+                    raise NotImplementedError('Learnable1DConv: odd kernel with "same" padding (the reference form)')
+                x = ops.linear(ops.temporal_unfold(x, conv.kernel_size[0]), self._tap_major(conv), conv.bias, act=ops.ACT_RELU)
+        return _heads(self, x)
 
 
 # --------------------------------------------------------------------------------------

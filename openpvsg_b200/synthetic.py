@@ -203,6 +203,26 @@ def relation_state_dicts(seed=0, feature_dim=256, hidden_dim=1024, num_relations
     return out
 
 
+def relation_baseline_state_dicts(seed=0, input_dim=512, num_relations=57, kernel_size=5, num_layers=1):
+    """state_dicts of the two baseline relation models of models/relation_head/convolution.py (``--model-name filter`` /
+    ``conv`` of tools/rel_test.py:167-175): HandcraftedFilter (heads only, its filter is a constant) and Learnable1DConv."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name in ('filter', 'conv'):
+        sd = {}
+        if name == 'conv':
+            for l in range(num_layers):
+                sd[f'conv_layers.{2 * l}.weight'] = torch.randn(input_dim, input_dim, kernel_size, generator=g) * \
+                    math.sqrt(2.0 / (input_dim * kernel_size))
+                sd[f'conv_layers.{2 * l}.bias'] = torch.randn(input_dim, generator=g) * 0.02
+        _lin(g, sd, 'fc1', input_dim // 2, input_dim, gain=2.0)
+        _lin(g, sd, 'fc2', input_dim // 4, input_dim // 2, gain=2.0)
+        _lin(g, sd, 'span_head', num_relations, input_dim // 4)
+        _lin(g, sd, 'pred_head', num_relations, input_dim // 4)
+        out[name] = sd
+    return out
+
+
 def synthetic_frame(seed, height=720, width=1280, size_divisor=32):
     """One normalised, padded frame [3, Hp, Wp] fp32:
     uint8 ~ U{0..255} from default_rng(seed), SeqNormalize (to_rgb=False), SeqPad(32)."""

@@ -111,6 +111,24 @@ def vanilla_model(sd, x):
     return span_pred, relation_pred
 
 
+def handcrafted_filter(sd, x):
+    """HandcraftedFilter.forward, models/relation_head/convolution.py:23-41: depthwise F.conv1d with the fixed taps
+    [1/4, 1/2, 1, 1/2, 1/4] (padding 2) along time, then the VanillaModel heads."""
+    c = x.shape[-1]
+    w = torch.tensor([1 / 4, 1 / 2, 1, 1 / 2, 1 / 4], dtype=torch.float32).view(1, 1, -1).repeat(c, 1, 1)
+    y = F.conv1d(x.permute(0, 2, 1), w, padding=2, groups=c).permute(0, 2, 1)
+    return vanilla_model(sd, y)
+
+
+def learnable_conv(sd, x, num_layers=1):
+    """Learnable1DConv.forward, models/relation_head/convolution.py:63-75."""
+    y = x.permute(0, 2, 1)
+    for l in range(num_layers):
+        w = sd[f'conv_layers.{2 * l}.weight']
+        y = F.relu(F.conv1d(y, w, sd[f'conv_layers.{2 * l}.bias'], padding=w.shape[-1] // 2))
+    return vanilla_model(sd, y.permute(0, 2, 1))
+
+
 def generate_pairwise_results(span_pred, prob, selected_pairs):
     """models/relation_head/test_utils.py:56-84."""
     max_probs, max_indices = torch.max(prob, dim=1)

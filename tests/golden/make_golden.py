@@ -102,6 +102,22 @@ def golden_relation():
         all_triplets=np.array([[r['subject_index'], r['object_index'], r['relation']] for r in res_all[:200]]),
     )
     print('rel_small.npz', len(pairs), 'pairs')
+    # the two baseline relation models (tools/rel_test.py:167-175 `--model-name filter | conv`), reference classes
+    conv = load_by_path('ref_rel_convolution', f'{REF}/models/relation_head/convolution.py')
+    bsd = syn.relation_baseline_state_dicts(seed=2)
+    filt = conv.HandcraftedFilter(512, 57).eval()
+    lconv = conv.Learnable1DConv(512, 57).eval()
+    filt.load_state_dict(bsd['filter'])
+    lconv.load_state_dict(bsd['conv'])
+    x = randn(12, 9, 21, 512)
+    x[2, 7:] = 0.0
+    with torch.no_grad():
+        fs, fp = filt(x)
+        cs, cp = lconv(x)
+    np.savez_compressed(f'{HERE}/rel_baselines.npz', P=9, T=21, x_seed=12, weights_seed=2,
+                        in_checksum=checksum(x, *[v for sd in bsd.values() for v in sd.values()]),
+                        fspan=fs.numpy(), fprob=fp.numpy(), cspan=cs.numpy(), cprob=cp.numpy())
+    print('rel_baselines.npz')
 
 
 # ----------------------------------------------------------------------------------
@@ -440,6 +456,9 @@ if __name__ == '__main__':
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'swin':
         golden_swin_b_720p()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'relation':
+        golden_relation()
         sys.exit(0)
     golden_relation()
     golden_m2f()

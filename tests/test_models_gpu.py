@@ -588,6 +588,38 @@ def test_relation_head_vs_reference_golden(cuda, golden_dir):
     close(out['span_pred'], g['span'], TOL, 'fused span_pred')
 
 
+def test_baseline_relation_models_vs_reference_golden(cuda, golden_dir):
+    """HandcraftedFilter / Learnable1DConv forward on the device (pvsg_temporal_fir; pvsg_temporal_unfold + one GEMM)
+    against outputs of the reference's own classes (tests/golden/rel_baselines.npz), plus a full-size (100 pairs x 128
+    frames) comparison with the oracle, state_dict layout as the reference's."""
+    from openpvsg_b200 import relation_head as rh
+    from oracle import relation as orel
+    g = np.load(os.path.join(golden_dir, 'rel_baselines.npz'))
+    bsd = syn.relation_baseline_state_dicts(seed=int(g['weights_seed']))
+    filt, conv = rh.HandcraftedFilter(512, 57), rh.Learnable1DConv(512, 57)
+    assert not filt.load_state_dict(bsd['filter'], strict=True).missing_keys
+    assert not conv.load_state_dict(bsd['conv'], strict=True).missing_keys
+    filt.to(cuda), conv.to(cuda)
+    x = torch.randn(int(g['P']), int(g['T']), 512, generator=torch.Generator().manual_seed(int(g['x_seed'])))
+    x[2, 7:] = 0.0
+    fs, fp = filt(x.to(cuda))
+    cs, cp = conv(x.to(cuda))
+    close(fs, g['fspan'], 2e-4, 'filter span')
+    close(fp, g['fprob'], 2e-4, 'filter prob')
+    close(cs, g['cspan'], 5e-4, 'conv span')
+    close(cp, g['cprob'], 5e-4, 'conv prob')
+    xl = torch.randn(100, 128, 512, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        rfs, rfp = orel.handcrafted_filter(bsd['filter'], xl)
+        rcs, rcp = orel.learnable_conv(bsd['conv'], xl)
+    fs, fp = filt(xl.to(cuda))
+    cs, cp = conv(xl.to(cuda))
+    close(fs, rfs, 2e-4, 'filter span (full size)')
+    close(fp, rfp, 2e-4, 'filter prob (full size)')
+    close(cs, rcs, TOL, 'conv span (full size)')
+    close(cp, rcp, TOL, 'conv prob (full size)')
+
+
 def test_relation_full_size_vs_oracle(cuda):
     """BASELINE config 4: 200 tubes x 128 frames, 100 pairs."""
     from openpvsg_b200 import relation_head as rh
@@ -620,3 +652,35 @@ def test_relation_full_size_vs_oracle(cuda):
     b = orel.generate_pairwise_results(ref['span_pred'], ref['prob'], ref['pairs'])
     assert [(r['subject_index'], r['object_index'], r['relation']) for r in a[:50]] == \
         [(r['subject_index'], r['object_index'], r['relation']) for r in b[:50]]
+
+
+def test_compat_single_gpu_test_loop(detectors, cuda):
+    """The import floor for the reference's tools (openpvsg_b200/compat; tests/test_compat_tools_cpu.py runs the
+    reference's tools/test.py through it on CPU with a recorder): here the same loop -- compat build_dataset /
+    build_dataloader / build_dp / mmdet.apis.single_gpu_test -- drives the real detector on the GPU, and must return
+    what direct calls return."""
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'openpvsg_b200', 'compat')
+    sys.path.insert(0, compat)
+    try:
+        from datasets.datasets.builder import build_dataset
+        from mmdet.apis import single_gpu_test
+        from mmdet.datasets import build_dataloader
+        from mmdet.utils import build_dp
+        dets, sd = detectors
+        det = dets[True]
+        ds = build_dataset(dict(type='SyntheticVPSDataset', num_frames=4, height=96, width=160, seed=300, split='val',
+                                video_name='x', pipeline=[]))
+        for spg in (1, 2):
+            loader = build_dataloader(ds, samples_per_gpu=spg, workers_per_gpu=0, dist=False, shuffle=False)
+            outputs = single_gpu_test(build_dp(det, 'cuda', device_ids=[0]), loader)
+            assert len(outputs) == 4 and all(len(o) == 1 for o in outputs)
+            for i, o in enumerate(outputs):
+                want = det.simple_test(None, None, ref_img=syn.synthetic_frame(300 + i, 96, 160)[None, None].to(cuda),
+                                       ref_img_metas=[[syn.frame_meta(96, 160)]], rescale=True)[0][0]
+                assert np.array_equal(o[0]['pan_results'], want['pan_results'])
+                assert sorted(o[0]['query_feats']) == sorted(want['query_feats'])
+    finally:
+        sys.path.remove(compat)
+        for name in [m for m in sys.modules if m.split('.')[0] in ('mmdet', 'datasets', 'mmcv')]:
+            del sys.modules[name]

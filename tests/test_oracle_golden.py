@@ -291,3 +291,19 @@ def test_assembled_decoder_layer_vs_hf_mask2former():
                                encoder_hidden_states=[key], encoder_attention_mask=mask)[0]
         got = om.decoder_layer(sd, p, query, key, key, qpos, kpos, mask)
     _close(got, want, 5e-5)
+
+
+def test_baseline_relation_models_golden(golden_dir):
+    """HandcraftedFilter / Learnable1DConv (models/relation_head/convolution.py, `--model-name filter | conv` of
+    tools/rel_test.py:167-175): oracle restatement vs outputs of the reference's own classes (rel_baselines.npz)."""
+    g = _load(golden_dir, 'rel_baselines.npz')
+    bsd = syn.relation_baseline_state_dicts(seed=int(g['weights_seed']))
+    x = _randn(int(g['x_seed']), int(g['P']), int(g['T']), 512)
+    x[2, 7:] = 0.0
+    assert abs(_checksum(x, *[v for sd in bsd.values() for v in sd.values()]) - float(g['in_checksum'])) < 1e-3
+    fs, fp = orel.handcrafted_filter(bsd['filter'], x)
+    cs, cp = orel.learnable_conv(bsd['conv'], x)
+    _close(fs, g['fspan'])
+    _close(fp, g['fprob'])
+    _close(cs, g['cspan'])
+    _close(cp, g['cprob'])
