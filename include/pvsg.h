@@ -400,6 +400,28 @@ int pvsg_top_pairs(const float* pair, int N, int k, int32_t* pairs, int32_t* n_o
 int pvsg_gather_pairs(const float* sub, const float* obj, const int32_t* pairs, const float* pe,
                       float* out, int P, int T, int F, void* stream);
 
+/* ------------------------------------------------------------ IPS tracker path ----- */
+
+/* F.interpolate(x, scale_factor=s, mode='bilinear') as models/unitrack/mask.py:36 calls it: the source coordinate of an
+ * output pixel is (dst + 0.5) * scale - 0.5 with the CALLER's scale = 1 / s (ATen uses the given scale factor, not
+ * in / out, when recompute_scale_factor is unset), output size floor(in * s).  Token-major [B,H,W,C], C % 4 == 0. */
+int pvsg_bilinear_resize_scaled(const float* src, float* dst, int B, int IH, int IW, int OH, int OW, int C,
+                                float scale_h, float scale_w, void* stream);
+
+/* UniTrack reconstruction-similarity distance (models/unitrack/core/association/matching.py:194-238
+ * `reconsdot_distance`, called from multitracker.py:27 `class_aware_distance`).  trk [ntrk,nst,d], det [ndet,nsd,d]:
+ * mask-pooled appearance embeddings, position-major, zero padded to the longest (`get_track_feat`, :170-191).
+ * cost [ntrk,ndet] = 1 - (cos(recons_trk, trk) + cos(recons_det, det)) / 2 with softmax temperature tmp (100). */
+int64_t pvsg_reconsdot_workspace_bytes(int ntrk, int nst, int ndet, int nsd, int d);
+int pvsg_reconsdot(const float* trk, const float* det, float* cost, void* workspace, int ntrk, int nst, int ndet,
+                   int nsd, int d, float tmp, void* stream);
+
+/* lap.lapjv(cost, extend_cost=True, cost_limit=thresh) as called by matching.py:29-40 `linear_assignment` (lap is a
+ * third-party dependency of the reference, not vendored): exact assignment on the (n+m)-square extension whose extra
+ * entries cost cost_limit / 2; x[i] = column of row i or -1, y[j] = row of column j or -1; +inf entries are never
+ * matched.  n + m <= 256. */
+int pvsg_lap_assign(const float* cost, int n, int m, double cost_limit, int32_t* x, int32_t* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

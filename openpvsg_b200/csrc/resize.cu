@@ -165,6 +165,15 @@ extern "C" int pvsg_bilinear_resize_nhwc_ex(const float* src, int64_t src_batch_
     return pvsg_launch_status();
 }
 
+extern "C" int pvsg_bilinear_resize_scaled(const float* src, float* dst, int B, int IH, int IW, int OH, int OW, int C,
+                                           float scale_h, float scale_w, void* stream) {
+    PVSG_CHECK_ARG(src && dst && B > 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && C > 0 && C % 4 == 0 && scale_h > 0.f && scale_w > 0.f);
+    const int64_t total = (int64_t)B * OH * OW * (C / 4);
+    bilinear_nhwc_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(src, dst, IH, IW, OH, OW, C / 4, scale_h, scale_w, 0, total,
+                                                                         (int64_t)IH * IW * (C / 4));
+    return pvsg_launch_status();
+}
+
 extern "C" int pvsg_maxpool3x3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, void* stream) {
     PVSG_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0);
     const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;

@@ -43,6 +43,7 @@ SIGNATURES = {
     'pvsg_add_rowvec': (I, [P, P, P, L, I, P]),
     'pvsg_bilinear_resize_nhwc': (I, [P, P, I, I, I, I, I, I, I, P]),
     'pvsg_bilinear_resize_nhwc_ex': (I, [P, L, P, P, P, I, I, I, I, I, I, I, P]),
+    'pvsg_bilinear_resize_scaled': (I, [P, P, I, I, I, I, I, I, F, F, P]),
     'pvsg_sine_pe': (I, [P, P, P, P, I, I, I, I, F, F, P]),
     'pvsg_msda_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
     'pvsg_msda_fused_forward': (I, [P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
@@ -65,6 +66,9 @@ SIGNATURES = {
     'pvsg_window_attention': (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
     'pvsg_patch_merge_ln': (I, [P, P, P, P, I, I, I, I, F, P]),
     'pvsg_tube_overlap': (I, [P, P, P, I, I, I, I, I, P, P]),
+    'pvsg_reconsdot_workspace_bytes': (L, [I, I, I, I, I]),
+    'pvsg_reconsdot': (I, [P, P, P, P, I, I, I, I, I, F, P]),
+    'pvsg_lap_assign': (I, [P, I, I, D, P, P, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
     'pvsg_temporal_fir': (I, [P, P, P, I, I, I, I, P]),
     'pvsg_temporal_unfold': (I, [P, P, I, I, I, I, P]),
@@ -113,7 +117,7 @@ def load():
 
 # kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)
 KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_groupnorm_nhwc_split': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3,
-                    'pvsg_panoptic_fuse_batched': 4, 'pvsg_instance_masks_batched': 3, 'pvsg_rle_events': 3, 'pvsg_tube_overlap': 1}
+                    'pvsg_panoptic_fuse_batched': 4, 'pvsg_instance_masks_batched': 3, 'pvsg_rle_events': 3, 'pvsg_tube_overlap': 1, 'pvsg_reconsdot': 7}
 launch_count = [0]
 
 

@@ -492,6 +492,16 @@ def bilinear_resize_nhwc(src, out_hw, out=None, accumulate=False, out_split=Fals
     return out
 
 
+def bilinear_resize_scaled(src, out_hw, scale):
+    """F.interpolate(scale_factor=1/scale, mode='bilinear') on token-major [B,H,W,C]: explicit source-coordinate scale."""
+    lib = _l.load()
+    B, IH, IW, C = _f32(src).shape
+    out = torch.empty(B, out_hw[0], out_hw[1], C, device=src.device, dtype=torch.float32)
+    _l.check(lib.pvsg_bilinear_resize_scaled(_ptr(src.contiguous()), _ptr(out), B, IH, IW, out_hw[0], out_hw[1], C, float(scale),
+                                             float(scale), _stream()), 'pvsg_bilinear_resize_scaled')
+    return out
+
+
 def sine_pe(h, w, device, t=0, num_feats=128, temperature=10000, scale=6.283185307179586, eps=1e-6,
             add_vec=None):
     """Token-major sine positional encoding [max(t,1)*h*w, 2*num_feats]."""
@@ -847,6 +857,30 @@ def tube_overlap(gt, pan, seg_info, num_gt):
     _l.check(lib.pvsg_tube_overlap(_ptr(gt.contiguous()), _ptr(pan.contiguous()), _ptr(seg_info.contiguous()), B, Q, H, W,
                                    int(num_gt), _ptr(counts), _stream()), 'pvsg_tube_overlap')
     return counts
+
+
+def reconsdot(trk, det, tmp=100.0):
+    """trk [ntrk,nst,d], det [ndet,nsd,d] zero-padded position-major embeddings -> cost [ntrk,ndet] (pvsg_reconsdot)."""
+    lib = _l.load()
+    ntrk, nst, d = _f32(trk, 'trk').shape
+    ndet, nsd, d2 = _f32(det, 'det').shape
+    if d2 != d:
+        raise _l.PvsgError('reconsdot: feature widths differ')
+    cost = torch.empty(ntrk, ndet, device=trk.device, dtype=torch.float32)
+    ws = torch.empty(lib.pvsg_reconsdot_workspace_bytes(ntrk, nst, ndet, nsd, d), device=trk.device, dtype=torch.uint8)
+    _l.check(lib.pvsg_reconsdot(_ptr(trk.contiguous()), _ptr(det.contiguous()), _ptr(cost), _ptr(ws), ntrk, nst, ndet, nsd, d,
+                                float(tmp), _stream()), 'pvsg_reconsdot')
+    return cost
+
+
+def lap_assign(cost, cost_limit):
+    """cost [n,m] fp32 (+inf = forbidden) -> (x int32 [n], y int32 [m]) of lap.lapjv(cost, extend_cost=True, cost_limit)."""
+    lib = _l.load()
+    n, m = _f32(cost, 'cost').shape
+    x = torch.empty(n, device=cost.device, dtype=torch.int32)
+    y = torch.empty(m, device=cost.device, dtype=torch.int32)
+    _l.check(lib.pvsg_lap_assign(_ptr(cost.contiguous()), n, m, float(cost_limit), _ptr(x), _ptr(y), _stream()), 'pvsg_lap_assign')
+    return x, y
 
 
 def max_over_time(x):
