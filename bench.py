@@ -192,6 +192,20 @@ def relation_bench(dev, with_cpu):
         ts.append(e0.elapsed_time(e1))
     out = dict(workload='relation head forward, 200 tubes x 128 frames, top-100 pairs (BASELINE configs[3])',
                ms=round(float(np.median(ts)), 3), forwards_per_s=round(1e3 / float(np.median(ts)), 1))
+    for _ in range(3):
+        rh.relation_forward(*mods, fd, 100, graph=True)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rh.relation_forward(*mods, fd, 100, graph=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    out['ms_cuda_graph'] = round(float(np.median(ts)), 3)
+    out['gflop'] = round(2 * 64.2 + 0.33 + 48.2, 1)
+    out['tflops_cuda_graph'] = round(out['gflop'] / out['ms_cuda_graph'], 1)
     if with_cpu:
         from oracle import relation as orel
         torch.set_num_threads(os.cpu_count())

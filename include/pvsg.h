@@ -422,6 +422,44 @@ int pvsg_reconsdot(const float* trk, const float* det, float* cost, void* worksp
  * matched.  n + m <= 256. */
 int pvsg_lap_assign(const float* cost, int n, int m, double cost_limit, int32_t* x, int32_t* y, void* stream);
 
+/* ------------------------------------------------------------ training slice ----- */
+
+/* mmcv.ops.point_sample as used by loss_single / _get_target_single (mask2former_video_head.py:175-178,262-267):
+ * out[n,k] = bilinear sample (align_corners=False, zero padding) of maps[n] [H,W] at points [n,K,2] (x, y in [0,1];
+ * points_per_map = 0: ONE [K,2] set shared by all maps).  _backward: grad_maps[n] = scatter of grad_out (zeroed first). */
+int pvsg_point_sample(const float* maps, const float* points, float* out, int n, int H, int W, int K, int points_per_map,
+                      void* stream);
+int pvsg_point_sample_backward(const float* grad_out, const float* points, float* grad_maps, int n, int H, int W, int K,
+                               int points_per_map, void* stream);
+
+/* loss_mask + loss_dice of loss_single (:270-289) on sampled logits / targets [n,K]: sums[0] = sum of
+ * binary_cross_entropy_with_logits terms (mmdet CrossEntropyLoss(use_sigmoid=True)), sums[1] = sum over rows of the
+ * naive dice loss 1 - (2 sum(s t) + eps) / (sum s + sum t + eps) (mmdet DiceLoss(naive_dice=True)); grad (optional)
+ * = bce_grad_scale * dBCE/dlogit + dice_grad_scale * ddice/dlogit. */
+int pvsg_mask_point_losses(const float* logits, const float* targets, int n, int K, float dice_eps, float bce_grad_scale,
+                           float dice_grad_scale, float* sums, float* grad, void* stream);
+
+/* loss_cls of loss_single (:236-244): mmdet CrossEntropyLoss with class_weight [C] and per-row label_weight (may be
+ * NULL): sums[0] = sum_r w[y_r] lw_r (logsumexp(x_r) - x_r[y_r]), sums[1] = sum_r w[y_r] (the avg_factor);
+ * grad (optional) = grad_scale * w lw (softmax(x) - onehot). */
+int pvsg_weighted_ce(const float* logits, const int64_t* labels, const float* class_weight, const float* label_weight,
+                     int rows, int C, float grad_scale, float* sums, float* grad, void* stream);
+
+/* mmdet MaskHungarianAssigner cost matrix (called from _get_target_single :181): cost[q,g] = -w_cls softmax(cls[q])[label_g]
+ * + w_mask mean_k BCE cost (CrossEntropyLossCost, use_sigmoid) + w_dice DiceCost(pred_act, naive_dice, eps) over the
+ * K sampled points; the assignment itself is scipy's linear_sum_assignment on the host, as in mmdet. */
+int pvsg_mask_match_cost(const float* cls_logits, const int64_t* gt_labels, const float* pred_points, const float* gt_points,
+                         int Q, int G, int C, int K, float w_cls, float w_mask, float w_dice, float dice_eps, float* cost,
+                         void* stream);
+
+/* mmcv MultiScaleDeformableAttnFunction.backward (the pixel decoder's attention, cfg :38-47): gradients of
+ * pvsg_msda_forward w.r.t. value [B,N,H,32] (atomics, zeroed first), sampling_locations [B,Nq,H,L,P,2] and
+ * attention_weights [B,Nq,H,L,P]. */
+int pvsg_msda_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const float* sampling_locations, const float* attention_weights, const float* grad_out,
+                       float* grad_value, float* grad_loc, float* grad_attn, int B, int64_t N, int64_t Nq, int H, int D,
+                       int L, int P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,12 @@ SIGNATURES = {
     'pvsg_reconsdot_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_reconsdot': (I, [P, P, P, P, I, I, I, I, I, F, P]),
     'pvsg_lap_assign': (I, [P, I, I, D, P, P, P]),
+    'pvsg_point_sample': (I, [P, P, P, I, I, I, I, I, P]),
+    'pvsg_point_sample_backward': (I, [P, P, P, I, I, I, I, I, P]),
+    'pvsg_mask_point_losses': (I, [P, P, I, I, F, F, F, P, P, P]),
+    'pvsg_weighted_ce': (I, [P, P, P, P, I, I, F, P, P, P]),
+    'pvsg_mask_match_cost': (I, [P, P, P, P, I, I, I, I, F, F, F, F, P, P]),
+    'pvsg_msda_backward': (I, [P, P, P, P, P, P, P, P, P, I, L, L, I, I, I, I, P]),
     'pvsg_max_over_time': (I, [P, P, I, I, I, P]),
     'pvsg_temporal_fir': (I, [P, P, P, I, I, I, I, P]),
     'pvsg_temporal_unfold': (I, [P, P, I, I, I, I, P]),

@@ -688,9 +688,31 @@ class _Mask2FormerHeadBase(_Prepared):
         pass
 
     def forward_train(self, *a, **k):
-        raise NotImplementedError('training is out of scope of the B200 inference backend')
+        raise NotImplementedError('forward_train: the losses (loss / loss_single, openpvsg_b200/losses.py) and the deformable '
+                                  "attention backward are built; the backward of the GEMM / attention engine is not "
+                                  '(SURVEY.md 8f rank 4, DESIGN.md section 7)')
 
-    loss = forward_train
+    def loss_single(self, cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas=None, **point_sets):
+        """mask2former_video_head.py:196-293 (mask_preds [B,T,Q,h,w]) / mask2former_head.py:233-318 ([B,Q,h,w]):
+        -> (loss_cls, loss_mask, loss_dice), differentiable w.r.t. cls_scores / mask_preds."""
+        from . import losses
+        if mask_preds.dim() == 4:                       # image head: one frame
+            mask_preds = mask_preds[:, None]
+            gt_masks_list = [g[:, None] for g in gt_masks_list]
+        tc = dict(self.train_cfg or {})
+        return losses.loss_single(cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas, num_classes=self.num_classes,
+                                  num_points=tc.get('num_points', 12544), oversample_ratio=tc.get('oversample_ratio', 3.0),
+                                  importance_sample_ratio=tc.get('importance_sample_ratio', 0.75), **point_sets)
+
+    def loss(self, all_cls_scores, all_mask_preds, gt_labels_list, gt_masks_list, img_metas=None):
+        """mask2former_video_head.py:524-634, the default (loss_split_th_st=False) branch: loss_single per decoder layer,
+        the last layer under the plain names, earlier ones as d{i}.loss_*."""
+        per_layer = [self.loss_single(c, m, gt_labels_list, gt_masks_list, img_metas)
+                     for c, m in zip(all_cls_scores, all_mask_preds)]
+        out = dict(loss_cls=per_layer[-1][0], loss_mask=per_layer[-1][1], loss_dice=per_layer[-1][2])
+        for i, (lc, lm, ld) in enumerate(per_layer[:-1]):
+            out[f'd{i}.loss_cls'], out[f'd{i}.loss_mask'], out[f'd{i}.loss_dice'] = lc, lm, ld
+        return out
 
     # ---- per-layer prediction heads (mask2former_head.py:355-395 / video :337-359) ----
     @torch.no_grad()

@@ -570,6 +570,88 @@ def msda_fused_forward(value, spatial_shapes, proj, ref, num_heads=8, num_points
     return out
 
 
+def msda_backward(value, spatial_shapes, sampling_locations, attention_weights, grad_out):
+    """mmcv MultiScaleDeformableAttnFunction.backward: value [B,N,H,D], grad_out [B,Nq,H*D] ->
+    (grad_value, grad_sampling_locations, grad_attention_weights)."""
+    lib = _l.load()
+    B, N, H, D = _f32(value).shape
+    _, Nq, _, L, P, _ = _f32(sampling_locations).shape
+    ss, ls, L2, tot = _levels(spatial_shapes)
+    if L2 != L or tot != N or tuple(_f32(grad_out).shape) != (B, Nq, H * D):
+        raise _l.PvsgError('msda_backward: shape mismatch')
+    gv = torch.empty_like(value, memory_format=torch.contiguous_format)
+    gl = torch.empty(sampling_locations.shape, device=value.device, dtype=torch.float32)
+    ga = torch.empty(attention_weights.shape, device=value.device, dtype=torch.float32)
+    _l.check(lib.pvsg_msda_backward(_ptr(value.contiguous()), ss, ls, _ptr(sampling_locations.contiguous()),
+                                    _ptr(_f32(attention_weights).contiguous()), _ptr(grad_out.contiguous()), _ptr(gv), _ptr(gl),
+                                    _ptr(ga), B, N, Nq, H, D, L, P, _stream()), 'pvsg_msda_backward')
+    return gv, gl, ga
+
+
+def point_sample(maps, points):
+    """maps [n,H,W], points [n,K,2] or [K,2] (x, y in [0,1]) -> [n,K] (mmcv.ops.point_sample, align_corners=False)."""
+    lib = _l.load()
+    n, H, W = _f32(maps).shape
+    shared = points.dim() == 2
+    K = points.shape[-2]
+    if _f32(points).shape[-1] != 2 or (not shared and points.shape[0] != n):
+        raise _l.PvsgError('point_sample: points must be [n,K,2] or [K,2]')
+    out = torch.empty(n, K, device=maps.device, dtype=torch.float32)
+    if n:
+        _l.check(lib.pvsg_point_sample(_ptr(maps.contiguous()), _ptr(points.contiguous()), _ptr(out), n, H, W, K, 0 if shared else 1,
+                                       _stream()), 'pvsg_point_sample')
+    return out
+
+
+def point_sample_backward(grad_out, points, hw):
+    lib = _l.load()
+    n, K = _f32(grad_out).shape
+    gm = torch.empty(n, hw[0], hw[1], device=grad_out.device, dtype=torch.float32)
+    if n:
+        _l.check(lib.pvsg_point_sample_backward(_ptr(grad_out.contiguous()), _ptr(_f32(points).contiguous()), _ptr(gm), n, hw[0], hw[1],
+                                                K, 0 if points.dim() == 2 else 1, _stream()), 'pvsg_point_sample_backward')
+    return gm
+
+
+def mask_point_losses(logits, targets, dice_eps=1.0, bce_grad_scale=0.0, dice_grad_scale=0.0, want_grad=False):
+    """logits / targets [n,K] -> (sums fp32 [2] = (sum of BCE terms, sum of dice losses), grad or None)."""
+    lib = _l.load()
+    n, K = _f32(logits).shape
+    sums = torch.empty(2, device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits, memory_format=torch.contiguous_format) if want_grad else None
+    _l.check(lib.pvsg_mask_point_losses(_ptr(logits.contiguous()), _ptr(_f32(targets).contiguous()), n, K, float(dice_eps),
+                                        float(bce_grad_scale), float(dice_grad_scale), _ptr(sums), _ptr(grad), _stream()),
+             'pvsg_mask_point_losses')
+    return sums, grad
+
+
+def weighted_ce(logits, labels, class_weight, label_weight=None, grad_scale=0.0, want_grad=False):
+    """logits [R,C], labels int64 [R] -> (sums fp32 [2] = (weighted loss sum, sum of class_weight[labels]), grad or None)."""
+    lib = _l.load()
+    R, C = _f32(logits).shape
+    if labels.dtype != torch.int64 or labels.numel() != R or _f32(class_weight).numel() != C:
+        raise _l.PvsgError('weighted_ce: int64 labels [R] and class_weight [C] expected')
+    sums = torch.empty(2, device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits, memory_format=torch.contiguous_format) if want_grad else None
+    _l.check(lib.pvsg_weighted_ce(_ptr(logits.contiguous()), _ptr(labels.contiguous()), _ptr(class_weight.contiguous()),
+                                  _ptr(_f32(label_weight)), R, C, float(grad_scale), _ptr(sums), _ptr(grad), _stream()),
+             'pvsg_weighted_ce')
+    return sums, grad
+
+
+def mask_match_cost(cls_logits, gt_labels, pred_points, gt_points, w_cls=2.0, w_mask=5.0, w_dice=5.0, dice_eps=1.0):
+    """cls_logits [Q,C], gt_labels int64 [G], pred_points [Q,K], gt_points [G,K] -> cost [Q,G] (MaskHungarianAssigner)."""
+    lib = _l.load()
+    Q, C = _f32(cls_logits).shape
+    G, K = _f32(gt_points).shape
+    cost = torch.empty(Q, G, device=cls_logits.device, dtype=torch.float32)
+    if G:
+        _l.check(lib.pvsg_mask_match_cost(_ptr(cls_logits.contiguous()), _ptr(gt_labels.contiguous()), _ptr(_f32(pred_points).contiguous()),
+                                          _ptr(gt_points.contiguous()), Q, G, C, K, float(w_cls), float(w_mask), float(w_dice),
+                                          float(dice_eps), _ptr(cost), _stream()), 'pvsg_mask_match_cost')
+    return cost
+
+
 def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None):
     """q [B,Lq,E], k/v [B,Lk,E] (any batch / token strides, unit inner stride) -> [B,Lq,E].
     mask uint8 [B,Lq,Lk] (non-zero = blocked), row_open int32 [B,Lq].

@@ -586,6 +586,13 @@ def test_relation_head_vs_reference_golden(cuda, golden_dir):
     out = rh.relation_forward(sub_enc, obj_enc, ppn, rel, feats, P)
     assert out['pairs'].cpu().tolist() == g['pairs'].tolist()
     close(out['span_pred'], g['span'], TOL, 'fused span_pred')
+    # ... and so does its CUDA-graph replay (twice: the second call reuses the captured graph on new input values)
+    for scale in (1.0, 1.0):
+        out2 = rh.relation_forward(sub_enc, obj_enc, ppn, rel, feats * scale, P, graph=True)
+        assert out2['pairs'].cpu().tolist() == g['pairs'].tolist()
+        assert torch.equal(out2['span_pred'], out['span_pred']) and torch.equal(out2['prob'], out['prob'])
+    few = rh.relation_forward(sub_enc, obj_enc, ppn, rel, feats[:3], P)       # N^2 = 9 < P: all 9 entries, diagonal last
+    assert few['pairs'].shape[0] == 9 and few['span_pred'].shape[0] == 9
 
 
 def test_baseline_relation_models_vs_reference_golden(cuda, golden_dir):
