@@ -400,6 +400,18 @@ int pvsg_top_pairs(const float* pair, int N, int k, int32_t* pairs, int32_t* n_o
 int pvsg_gather_pairs(const float* sub, const float* obj, const int32_t* pairs, const float* pe,
                       float* out, int P, int T, int F, void* stream);
 
+/* Attention on the 5th-generation tensor cores: same contract as pvsg_attention_tc (K / V as split-bf16 operand planes,
+ * head dim 32 or 128, byte mask + open-row rule, key splits merged through the workspace), but S = Q K^T and O = P V are
+ * tcgen05.mma instructions with TMEM accumulators, K / V tiles arrive by TMA and V is consumed as an MN-major operand
+ * (csrc/attention_t5.cu).  The K and V planes must share their strides (slices of one projection).  Replaces
+ * models/relation_head/base.py:26-40 and transformer.py:35-56 (nn.TransformerEncoderLayer self-attention) and the
+ * decoder cross-attention of models/mask2former/mask2former_head.py:457-468. */
+int64_t pvsg_attention_t5_workspace_bytes(int B, int H, int Lq, int Lk, int D);
+int pvsg_attention_t5(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
+                      const uint8_t* mask, const int32_t* row_open, float* out, void* workspace, int B, int H, int Lq,
+                      int Lk, int D, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts,
+                      int64_t o_bs, int64_t o_ts, float scale, void* stream);
+
 /* ------------------------------------------------------------ IPS tracker path ----- */
 
 /* F.interpolate(x, scale_factor=s, mode='bilinear') as models/unitrack/mask.py:36 calls it: the source coordinate of an

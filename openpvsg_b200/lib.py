@@ -52,6 +52,8 @@ SIGNATURES = {
     'pvsg_attention': (I, [P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_attention_tc_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_attention_tc': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
+    'pvsg_attention_t5_workspace_bytes': (L, [I, I, I, I, I]),
+    'pvsg_attention_t5': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_mask_logits': (I, [P, P, P, P, P, I, I, L, I, P]),
     'pvsg_panoptic_fuse': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),
     'pvsg_instance_masks': (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, P, P]),
@@ -124,6 +126,7 @@ def load():
 # kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)
 KERNELS_PER_CALL = {'pvsg_groupnorm_nhwc': 2, 'pvsg_groupnorm_nhwc_split': 2, 'pvsg_panoptic_fuse': 4, 'pvsg_instance_masks': 3,
                     'pvsg_panoptic_fuse_batched': 4, 'pvsg_instance_masks_batched': 3, 'pvsg_rle_events': 3, 'pvsg_tube_overlap': 1, 'pvsg_reconsdot': 7}
+ATTN_IMPL = [os.environ.get('PVSG_ATTN_IMPL', 't5')]   # 't5' = tcgen05 / TMEM kernel, 'mma' = mma.sync kernel (debug switch)
 launch_count = [0]
 
 

@@ -680,6 +680,16 @@ def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None
             raise _l.PvsgError('attention: row_open must be contiguous int32')
         if (k.hi.stride() != k.lo.stride()) or (v.hi.stride() != v.lo.stride()):
             raise _l.PvsgError('attention: hi / lo planes must share their layout')
+        t5 = (_l.ATTN_IMPL[0] == 't5' and k.hi.stride() == v.hi.stride() and q.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
+              and q.stride(0) % 4 == 0 and q.stride(1) % 4 == 0 and out.stride(0) % 4 == 0 and out.stride(1) % 4 == 0
+              and all(t.data_ptr() % 16 == 0 for t in (k.hi, k.lo, v.hi, v.lo)) and B * num_heads <= 65535)
+        if t5:      # tcgen05 / TMEM kernel (csrc/attention_t5.cu)
+            ws = torch.empty(lib.pvsg_attention_t5_workspace_bytes(B, num_heads, Lq, Lk, D), device=q.device, dtype=torch.uint8)
+            _l.check(lib.pvsg_attention_t5(_ptr(q), _ptr(k.hi), _ptr(k.lo), _ptr(v.hi), _ptr(v.lo), _ptr(mask), _ptr(row_open),
+                                           _ptr(out), _ptr(ws), B, num_heads, Lq, Lk, D, q.stride(0), q.stride(1),
+                                           k.hi.stride(0), k.hi.stride(1), v.hi.stride(0), v.hi.stride(1), out.stride(0),
+                                           out.stride(1), scale, _stream()), 'pvsg_attention_t5')
+            return out
         ws = torch.empty(lib.pvsg_attention_tc_workspace_bytes(B, num_heads, Lq, Lk, D), device=q.device,
                          dtype=torch.uint8)
         _l.check(lib.pvsg_attention_tc(_ptr(q), _ptr(k.hi), _ptr(k.lo), _ptr(v.hi), _ptr(v.lo), _ptr(mask),
