@@ -434,6 +434,17 @@ int pvsg_reconsdot(const float* trk, const float* det, float* cost, void* worksp
  * matched.  n + m <= 256. */
 int pvsg_lap_assign(const float* cost, int n, int m, double cost_limit, int32_t* x, int32_t* y, void* stream);
 
+/* MinVIS tube linking, all frame pairs at once (models/mask2former_vps/mask2former_min_vis.py:244-258
+ * `match_from_embds`: cosine cost + scipy linear_sum_assignment, one frame after the other).  The cost matrix of step t
+ * depends only on the RAW query embeddings of frames t-1 and t (re-ordering the target permutes rows), so all T-1
+ * problems are independent: pvsg_cosine_chain_cost -> cost [T-1,Q,Q] (rows: queries of frame t, columns: frame t+1),
+ * pvsg_lap_square_batched -> x[t,i] = column assigned to row i (one warp per problem, exact, n <= 256); the clip's
+ * permutations are then the running composition of the x[t] (host, T small integer gathers). */
+int pvsg_cosine_chain_cost(const float* embeds, float* cost, int T, int Q, int C, void* stream);
+int pvsg_lap_square_batched(const float* cost, int batch, int n, int32_t* x, int32_t* y, void* stream);
+/* perms[0] = identity, perms[t][i] = x[t-1][perms[t-1][i]]: position i of the clip-long ordering holds query perms[t][i] of frame t. */
+int pvsg_perm_chain(const int32_t* sigma, int32_t* perms, int T, int Q, void* stream);
+
 /* ------------------------------------------------------------ training slice ----- */
 
 /* mmcv.ops.point_sample as used by loss_single / _get_target_single (mask2former_video_head.py:175-178,262-267):

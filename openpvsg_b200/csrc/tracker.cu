@@ -105,12 +105,16 @@ __device__ __forceinline__ double lap_cost(const float* __restrict__ c, int n, i
     return (i > n && j > m) ? 0.0 : half;
 }
 
-__global__ void __launch_bounds__(32) lap_kernel(const float* __restrict__ c, int n, int m, double cost_limit, int32_t* __restrict__ x,
-                                                 int32_t* __restrict__ y) {
+// one warp = one problem (blockIdx.x); extend = 0: plain square problem (n == m), no unmatched option
+__global__ void __launch_bounds__(32) lap_kernel(const float* __restrict__ c_all, int n, int m, double cost_limit, int extend,
+                                                 int32_t* __restrict__ x_all, int32_t* __restrict__ y_all) {
     __shared__ double u[LAP_MAX + 1], v[LAP_MAX + 1], minv[LAP_MAX + 1];
     __shared__ int p[LAP_MAX + 1], way[LAP_MAX + 1];
     __shared__ unsigned char used[LAP_MAX + 1];
-    const int lane = threadIdx.x, N = n + m;
+    const float* c = c_all + (int64_t)blockIdx.x * n * m;
+    int32_t* x = x_all + (int64_t)blockIdx.x * n;
+    int32_t* y = y_all + (int64_t)blockIdx.x * m;
+    const int lane = threadIdx.x, N = extend ? n + m : n;
     const double half = isfinite(cost_limit) ? cost_limit * 0.5 : 0.0;
     for (int j = lane; j <= N; j += 32) { u[j] = 0.0; v[j] = 0.0; p[j] = 0; way[j] = 0; }
     __syncwarp();
@@ -192,6 +196,56 @@ extern "C" int pvsg_reconsdot(const float* trk, const float* det, float* cost, v
 extern "C" int pvsg_lap_assign(const float* cost, int n, int m, double cost_limit, int32_t* x, int32_t* y, void* stream) {
     PVSG_CHECK_ARG(cost && x && y && n > 0 && m > 0);
     if (n + m > LAP_MAX) return PVSG_ERR_UNSUPPORTED;
-    lap_kernel<<<1, 32, 0, as_stream(stream)>>>(cost, n, m, cost_limit, x, y);
+    lap_kernel<<<1, 32, 0, as_stream(stream)>>>(cost, n, m, cost_limit, 1, x, y);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_lap_square_batched(const float* cost, int batch, int n, int32_t* x, int32_t* y, void* stream) {
+    PVSG_CHECK_ARG(cost && x && y && batch > 0 && n > 0);
+    if (n > LAP_MAX) return PVSG_ERR_UNSUPPORTED;
+    lap_kernel<<<batch, 32, 0, as_stream(stream)>>>(cost, n, n, INFINITY, 0, x, y);
+    return pvsg_launch_status();
+}
+
+// cost[t, i, j] = 1 - <a_t[i] / |a_t[i]|, b_t[j] / |b_t[j]|>, a_t = E[t], b_t = E[t + 1]  (one warp per (t, i, j))
+namespace {
+__global__ void __launch_bounds__(256) cosine_chain_kernel(const float* __restrict__ E, float* __restrict__ cost, int Q, int C,
+                                                           int64_t total) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= total) return;
+    const int j = (int)(w % Q);
+    const int i = (int)((w / Q) % Q);
+    const int64_t t = w / ((int64_t)Q * Q);
+    const float* a = E + (t * Q + i) * C;
+    const float* b = E + ((t + 1) * Q + j) * C;
+    float ab = 0.f, aa = 0.f, bb = 0.f;
+    for (int k = lane; k < C; k += 32) { const float x = a[k], y = b[k]; ab = fmaf(x, y, ab); aa = fmaf(x, x, aa); bb = fmaf(y, y, bb); }
+    ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (lane == 0) cost[w] = 1.f - ab / (sqrtf(aa) * sqrtf(bb));
+}
+}  // namespace
+
+namespace {
+// perms[0] = identity, perms[t][i] = sigma[t-1][perms[t-1][i]]  (one CTA, Q threads, T-1 dependent steps)
+__global__ void perm_chain_kernel(const int32_t* __restrict__ sigma, int32_t* __restrict__ perms, int T, int Q) {
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        int p = i;
+        perms[i] = p;
+        for (int t = 1; t < T; ++t) { p = sigma[(int64_t)(t - 1) * Q + p]; perms[(int64_t)t * Q + i] = p; }
+    }
+}
+}  // namespace
+
+extern "C" int pvsg_perm_chain(const int32_t* sigma, int32_t* perms, int T, int Q, void* stream) {
+    PVSG_CHECK_ARG(perms && T > 0 && Q > 0 && (sigma || T == 1));
+    perm_chain_kernel<<<1, 128, 0, as_stream(stream)>>>(sigma, perms, T, Q);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_cosine_chain_cost(const float* embeds, float* cost, int T, int Q, int C, void* stream) {
+    PVSG_CHECK_ARG(embeds && cost && T > 1 && Q > 0 && C > 0);
+    const int64_t total = (int64_t)(T - 1) * Q * Q;
+    cosine_chain_kernel<<<(unsigned)((total + 7) / 8), 256, 0, as_stream(stream)>>>(embeds, cost, Q, C, total);
     return pvsg_launch_status();
 }

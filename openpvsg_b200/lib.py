@@ -71,6 +71,9 @@ SIGNATURES = {
     'pvsg_reconsdot_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_reconsdot': (I, [P, P, P, P, I, I, I, I, I, F, P]),
     'pvsg_lap_assign': (I, [P, I, I, D, P, P, P]),
+    'pvsg_cosine_chain_cost': (I, [P, P, I, I, I, P]),
+    'pvsg_lap_square_batched': (I, [P, I, I, P, P, P]),
+    'pvsg_perm_chain': (I, [P, P, I, I, P]),
     'pvsg_point_sample': (I, [P, P, P, I, I, I, I, I, P]),
     'pvsg_point_sample_backward': (I, [P, P, P, I, I, I, I, I, P]),
     'pvsg_mask_point_losses': (I, [P, P, I, I, F, F, F, P, P, P]),

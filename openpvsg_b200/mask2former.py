@@ -1186,15 +1186,21 @@ class Mask2FormerVideoCustomMinVIS(Mask2FormerVideoCustom):
 
     @torch.no_grad()
     def match_from_embds(self, tgt_embds, cur_embds):
-        """mask2former_min_vis.py:244-258: cosine cost on the device (one 100x256x100 GEMM through
-        pvsg_linear), Hungarian assignment on the host with scipy exactly as the reference."""
-        from scipy.optimize import linear_sum_assignment
-        cur = (cur_embds / cur_embds.norm(dim=1)[:, None]).contiguous()
-        tgt = (tgt_embds / tgt_embds.norm(dim=1)[:, None]).contiguous()
-        cos_sim = ops.linear(cur, tgt)                 # cur @ tgt^T
-        C = (1.0 - cos_sim).cpu()
-        indices = linear_sum_assignment(C.transpose(0, 1))
-        return torch.as_tensor(indices[1], device=cur_embds.device)
+        """mask2former_min_vis.py:244-258: cosine cost and exact linear assignment (rows: target queries, columns:
+        current queries), both on the device; returns for every target row the matched current query."""
+        sigma = ops.minvis_chain(torch.stack([tgt_embds, cur_embds]))
+        return sigma[0].long()
+
+    @torch.no_grad()
+    def link_clip(self, query_list):
+        """The whole clip's matching at once.  The reference matches frame t against the RE-ORDERED queries
+        of frame t-1 (mask2former_min_vis.py:176-181); re-ordering the target only permutes the rows of the cost
+        matrix, so the T-1 assignment problems are independent on the raw embeddings: they are solved concurrently
+        (one warp each) and the clip's orderings are the running composition of the per-pair matchings."""
+        embeds = torch.stack(list(query_list))                  # [T, Q, C]
+        T, Q = embeds.shape[:2]
+        sigma = ops.minvis_chain(embeds) if T > 1 else torch.empty(0, Q, device=embeds.device, dtype=torch.int32)
+        return ops.perm_chain(sigma, Q).long()                  # [T, Q]
 
     @torch.no_grad()
     def simple_test(self, img, img_metas, ref_img, ref_img_metas, **kwargs):
@@ -1210,12 +1216,9 @@ class Mask2FormerVideoCustomMinVIS(Mask2FormerVideoCustom):
             pred_logits.append(cls[0])
             mask_lr_list.append(mask_lr[0, 0])
             query_list.append(query[:, 0])
-        out_logits, out_masks, out_embds = [pred_logits[0]], [mask_lr_list[0]], [query_list[0]]
-        for i in range(1, num_frame):
-            idx = self.match_from_embds(out_embds[-1], query_list[i])
-            out_logits.append(pred_logits[i][idx, :])
-            out_masks.append(mask_lr_list[i][idx, :, :])
-            out_embds.append(query_list[i][idx, :])
+        perms = self.link_clip(query_list)
+        out_logits = [pred_logits[i][perms[i], :] for i in range(num_frame)]
+        out_masks = [mask_lr_list[i][perms[i], :, :] for i in range(num_frame)]
         logits = (sum(out_logits) / len(out_logits)).unsqueeze(0)
         results = [[]]
         for frame_id in range(num_frame):

@@ -975,6 +975,28 @@ def lap_assign(cost, cost_limit):
     return x, y
 
 
+def minvis_chain(embeds):
+    """embeds [T,Q,C] raw per-frame query embeddings -> sigma int32 [T-1,Q]: sigma[t][i] = query of frame t+1 matched to
+    query i of frame t (cosine cost, exact assignment; all T-1 problems solved concurrently)."""
+    lib = _l.load()
+    T, Q, C = _f32(embeds, 'embeds').shape
+    cost = torch.empty(T - 1, Q, Q, device=embeds.device, dtype=torch.float32)
+    _l.check(lib.pvsg_cosine_chain_cost(_ptr(embeds.contiguous()), _ptr(cost), T, Q, C, _stream()), 'pvsg_cosine_chain_cost')
+    x = torch.empty(T - 1, Q, device=embeds.device, dtype=torch.int32)
+    y = torch.empty(T - 1, Q, device=embeds.device, dtype=torch.int32)
+    _l.check(lib.pvsg_lap_square_batched(_ptr(cost), T - 1, Q, _ptr(x), _ptr(y), _stream()), 'pvsg_lap_square_batched')
+    return x
+
+
+def perm_chain(sigma, Q):
+    """sigma int32 [T-1,Q] (may be empty) -> perms int32 [T,Q]: perms[0] = identity, perms[t] = sigma[t-1][perms[t-1]]."""
+    lib = _l.load()
+    T = sigma.shape[0] + 1
+    perms = torch.empty(T, Q, device=sigma.device, dtype=torch.int32)
+    _l.check(lib.pvsg_perm_chain(_ptr(sigma.contiguous()) if T > 1 else None, _ptr(perms), T, Q, _stream()), 'pvsg_perm_chain')
+    return perms
+
+
 def max_over_time(x):
     lib = _l.load()
     N, T, C = _f32(x).shape

@@ -295,3 +295,49 @@ def gather_and_link(frame_entries, num_frames, max_segments=100, device='cpu', f
         linker.add_frames_bulk(c, g[r, per:per + m].astype(np.int64),
                                g[r, per + n_max:per + n_max + m * feature_dim].reshape(m, feature_dim))
     return linker
+
+
+def minvis_link_sharded(local_embeds, num_frames, solve_pairs=None, compose=None):
+    """MinVIS query matching of a clip whose frames are sharded across ranks (reference
+    mask2former_min_vis.py:176-181 + 244-258 run sequentially on one GPU).
+
+    ``local_embeds`` [F_local, Q, C]: the raw query embeddings of this rank's contiguous frame block
+    (``shard_frames``).  Exchange 1: all-gather of the blocks (Q*C*4 = 100 KB per frame).  Each rank then solves the
+    assignment problems of the frame pairs (t-1, t) with t in ITS block -- the pair that crosses into the previous block
+    uses the gathered halo frame -- and exchange 2 all-gathers the matchings (Q int32 per pair).  Every rank returns the
+    same perms int64 [T, Q]: position i of the clip-long ordering holds query perms[t][i] of frame t.
+
+    ``solve_pairs(embeds [n+1, Q, C]) -> int32 [n, Q]`` defaults to the device kernels (ops.minvis_chain);
+    ``compose(sigma [T-1, Q], Q) -> [T, Q]`` to ops.perm_chain.  The CPU tests inject host versions of both."""
+    import torch.distributed as dist
+    if solve_pairs is None or compose is None:
+        from . import ops
+        solve_pairs = solve_pairs or ops.minvis_chain
+        compose = compose or ops.perm_chain
+    ws = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if ws > 1 else 0
+    per = (num_frames + ws - 1) // ws
+    lo, hi = shard_frames(num_frames, ws, rank)
+    if local_embeds.shape[0] != hi - lo:
+        raise ValueError(f'minvis_link_sharded: rank {rank} holds {local_embeds.shape[0]} frames, its block has {hi - lo}')
+    Q, C = local_embeds.shape[1:]
+    dev = local_embeds.device
+    if ws == 1:
+        everything = local_embeds
+    else:
+        pad = torch.zeros(per, Q, C, device=dev, dtype=torch.float32)
+        pad[:hi - lo] = local_embeds
+        gathered = torch.empty(ws * per, Q, C, device=dev, dtype=torch.float32)
+        dist.all_gather(list(gathered.view(ws, per, Q, C).unbind(0)), pad)
+        everything = gathered[:num_frames]          # blocks are contiguous and only the last may be short
+    first = max(lo, 1)                              # pairs (t-1, t), t in [first, hi)
+    sigma_local = torch.zeros(per, Q, device=dev, dtype=torch.int32)
+    if hi > first:
+        sigma_local[first - lo:hi - lo] = solve_pairs(everything[first - 1:hi].contiguous()).to(torch.int32)
+    if ws == 1:
+        sigma = sigma_local[1:num_frames]
+    else:
+        allsig = torch.empty(ws * per, Q, device=dev, dtype=torch.int32)
+        dist.all_gather(list(allsig.view(ws, per, Q).unbind(0)), sigma_local)
+        sigma = allsig[1:num_frames]                # row t-1 = matching of the pair (t-1, t)
+    return compose(sigma.contiguous(), Q).long()

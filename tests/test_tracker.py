@@ -180,6 +180,34 @@ def test_lap_kernel_vs_oracle(golden):
 
 
 @pytest.mark.gpu
+def test_minvis_chain_kernels_vs_scipy():
+    """All T-1 MinVIS matchings at once (pvsg_cosine_chain_cost + pvsg_lap_square_batched + pvsg_perm_chain) against the
+    reference's sequential order of operations (mask2former_min_vis.py:176-181, 244-258) with scipy on the host."""
+    from scipy.optimize import linear_sum_assignment
+    from openpvsg_b200 import ops, tubes
+    g = torch.Generator().manual_seed(5)
+    for T, Q, C in ((9, 100, 256), (2, 100, 256), (5, 7, 16), (3, 256, 32)):
+        base = torch.randn(Q, C, generator=g)
+        embeds = torch.stack([base[torch.randperm(Q, generator=g)] * (1 + 0.3 * torch.rand(Q, 1, generator=g))
+                              + 0.3 * torch.randn(Q, C, generator=g) for _ in range(T)])
+        out, want = [embeds[0]], [torch.arange(Q)]
+        for t in range(1, T):
+            cur = embeds[t] / embeds[t].norm(dim=1)[:, None]
+            tgt = out[-1] / out[-1].norm(dim=1)[:, None]
+            idx = torch.as_tensor(linear_sum_assignment((1 - cur @ tgt.T).T.numpy())[1])
+            want.append(idx)
+            out.append(embeds[t][idx])
+        dev = embeds.cuda()
+        sigma = ops.minvis_chain(dev)
+        assert sigma.shape == (T - 1, Q) and all(sorted(r.tolist()) == list(range(Q)) for r in sigma)
+        perms = ops.perm_chain(sigma, Q)
+        assert torch.equal(perms.cpu().long(), torch.stack(want)), (T, Q, C)
+        assert torch.equal(tubes.minvis_link_sharded(dev, T).cpu(), torch.stack(want))
+    one = ops.perm_chain(torch.empty(0, 11, dtype=torch.int32, device='cuda'), 11)
+    assert one.cpu().tolist() == [list(range(11))]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('use_kalman', [True, False])
 def test_tracker_on_device_matches_reference(golden, use_kalman):
     _check_clip(golden, use_kalman)

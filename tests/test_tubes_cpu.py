@@ -134,6 +134,79 @@ def test_gather_and_link_world2_gloo():
         assert np.array_equal(feats, ref.tube_features())
 
 
+def _host_solve(embeds):
+    """scipy stand-in for ops.minvis_chain (host logic tests only)."""
+    from scipy.optimize import linear_sum_assignment
+    e = embeds.numpy().astype(np.float64)
+    e = e / np.linalg.norm(e, axis=2, keepdims=True)
+    return torch.from_numpy(np.stack([linear_sum_assignment(1.0 - e[t] @ e[t + 1].T)[1] for t in range(len(e) - 1)]).astype(np.int32))
+
+
+def _host_compose(sigma, Q):
+    perms = [torch.arange(Q)]
+    for s in sigma.long():
+        perms.append(s[perms[-1]])
+    return torch.stack(perms)
+
+
+def _sequential_minvis(embeds):
+    """The reference's order of operations: frame t is matched against the RE-ORDERED queries of frame t-1."""
+    from scipy.optimize import linear_sum_assignment
+    out = [embeds[0]]
+    perms = [torch.arange(embeds.shape[1])]
+    for t in range(1, embeds.shape[0]):
+        cur = embeds[t] / embeds[t].norm(dim=1)[:, None]
+        tgt = out[-1] / out[-1].norm(dim=1)[:, None]
+        C = 1 - cur @ tgt.T
+        idx = torch.as_tensor(linear_sum_assignment(C.T.numpy())[1])
+        perms.append(idx)
+        out.append(embeds[t][idx])
+    return torch.stack(perms)
+
+
+def _minvis_embeds(T, Q=12, C=16, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(Q, C, generator=g)
+    return torch.stack([base[torch.randperm(Q, generator=g)] + 0.05 * torch.randn(Q, C, generator=g) for _ in range(T)])
+
+
+def test_minvis_parallel_linking_equals_sequential_chain():
+    for T in (1, 2, 7):
+        e = _minvis_embeds(T, seed=T)
+        got = tubes.minvis_link_sharded(e, T, _host_solve, _host_compose)
+        assert torch.equal(got, _sequential_minvis(e))
+
+
+def _minvis_worker(rank, world, port, embeds, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = tubes.shard_frames(len(embeds), world, rank)
+    perms = tubes.minvis_link_sharded(embeds[lo:hi], len(embeds), _host_solve, _host_compose)
+    q.put((rank, perms.numpy()))
+    dist.destroy_process_group()
+
+
+def test_minvis_link_sharded_world2_gloo():
+    for T in (7, 2):                        # 2 frames: rank 1 owns the only pair, through the halo
+        embeds = _minvis_embeds(T, seed=11 + T)
+        ref = _sequential_minvis(embeds).numpy()
+        s = socket.socket()
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+        s.close()
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_minvis_worker, args=(r, 2, port, embeds, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        for rank, perms in got:
+            assert np.array_equal(perms, ref), rank
+
+
 def test_rle_events_host_side_matches_scalar_encoder():
     """tubes.rle_from_events / rle_string_np (host side of the device RLE encoder, pvsg_rle_events)
     against the scalar pycocotools-style encoder, including a segment that owns pixel 0, an absent
