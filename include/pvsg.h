@@ -39,6 +39,21 @@ const char* pvsg_error_string(int code);
 /* SM count / compute capability of `device`; PVSG_ERR_NO_DEVICE when no CUDA device. */
 int pvsg_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Handle ("handle + workspace").  The op entry points below are stateless and need no handle; a handle is
+ * the create-time half of the contract for a host that wants it:
+ *   pvsg_create   checks that `device` is compute capability 10.x (PVSG_ERR_UNSUPPORTED otherwise), and sets every
+ *                 kernel's opt-in attributes (dynamic shared memory, carve-out) on it, so that no op call made later --
+ *                 for instance the first one, inside a stream capture -- has a first-use side effect;
+ *   pvsg_workspace returns a device scratch pointer of at least `bytes` owned by the handle (grow-only; growing frees
+ *                 the old block, i.e. synchronises -- size it before capturing), for the `ws` arguments sized by the
+ *                 pvsg_<op>_workspace_bytes companions (attention, attention_tc, attention_t5, reconsdot);
+ *   pvsg_destroy  frees it.  Replaces nothing in the reference (torch's caching allocator plays this part there). */
+typedef struct pvsg_handle pvsg_handle;
+int pvsg_create(int device, pvsg_handle** out);
+int pvsg_destroy(pvsg_handle* handle);
+int pvsg_handle_info(const pvsg_handle* handle, int* device, int* sm_count, int64_t* smem_optin_bytes, int64_t* workspace_bytes);
+int pvsg_workspace(pvsg_handle* handle, int64_t bytes, void** ptr);
+
 /* ---------------------------------------------------------------- dense layers --- */
 
 /* C[b] = act(A[b] (+A2[b]) . W[b]^T + bias + R[b]);  A [M,K] (row stride lda), W [N,K]

@@ -318,17 +318,30 @@ int pick_splits_tc(int B, int H, int qtiles, int Lk) {
 }
 
 template <int D>
-int launch_attn(const AttnArgs& a, dim3 grid, int nwarp, cudaStream_t st) {
-    constexpr size_t smem = 2ull * 4 * Tile<D>::KT * Tile<D>::PITCH * sizeof(__nv_bfloat16);
+constexpr size_t attn_smem() { return 2ull * 4 * Tile<D>::KT * Tile<D>::PITCH * sizeof(__nv_bfloat16); }
+
+template <int D>
+int configure_attn() {
     static bool configured[PVSG_MAX_DEVICES];
     if (pvsg_first_use_on_device(configured) &&
-        cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem<D>()) != cudaSuccess)
         return PVSG_ERR_LAUNCH;
-    attn_mma_kernel<D><<<grid, 32 * nwarp, smem, st>>>(a);
+    return PVSG_OK;
+}
+
+template <int D>
+int launch_attn(const AttnArgs& a, dim3 grid, int nwarp, cudaStream_t st) {
+    if (const int rc = configure_attn<D>()) return rc;
+    attn_mma_kernel<D><<<grid, 32 * nwarp, attn_smem<D>(), st>>>(a);
     return PVSG_OK;
 }
 
 }  // namespace
+
+int pvsg_internal::configure_attention_mma() {
+    const int rc = configure_attn<32>();
+    return rc ? rc : configure_attn<128>();
+}
 
 extern "C" int64_t pvsg_attention_tc_workspace_bytes(int B, int H, int Lq, int Lk, int D) {
     const int qtiles = (Lq + 16 * MAXWARP - 1) / (16 * MAXWARP);

@@ -484,17 +484,28 @@ int pick_splits(int B, int H, int qtiles, int ntiles, int D) {
 }
 
 template <int D>
-int launch(const CUtensorMap* maps, const T5Args& a, dim3 grid, cudaStream_t st) {
+int configure() {
     static bool configured[PVSG_MAX_DEVICES];
     if (pvsg_first_use_on_device(configured) &&
         (cudaFuncSetAttribute(attn_t5_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM) != cudaSuccess ||
          cudaFuncSetAttribute(attn_t5_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess))
         return PVSG_ERR_LAUNCH;
+    return PVSG_OK;
+}
+
+template <int D>
+int launch(const CUtensorMap* maps, const T5Args& a, dim3 grid, cudaStream_t st) {
+    if (const int rc = configure<D>()) return rc;
     attn_t5_kernel<D><<<grid, NTHR, Cfg<D>::SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], a);
     return PVSG_OK;
 }
 
 }  // namespace
+
+int pvsg_internal::configure_attention_t5() {
+    const int rc = configure<32>();
+    return rc ? rc : configure<128>();
+}
 
 extern "C" int64_t pvsg_attention_t5_workspace_bytes(int B, int H, int Lq, int Lk, int D) {
     const int ns = pick_splits(B, H, (Lq + BM - 1) / BM, (Lk + BN - 1) / BN, D);

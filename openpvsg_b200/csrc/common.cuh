@@ -25,6 +25,21 @@ static inline bool pvsg_first_use_on_device(bool (&flags)[PVSG_MAX_DEVICES]) {
     return first;
 }
 
+// Every translation unit with opt-in kernel attributes exposes configure_<unit>(): sets them for the CURRENT device
+// (idempotent).  Launchers call them lazily; pvsg_create calls all of them up front so that the first launch of a
+// kernel may happen inside a stream capture (cudaFuncSetAttribute is not a stream operation, but doing it eagerly keeps
+// captures free of first-use side effects and surfaces an unsupported device at create time).
+namespace pvsg_internal {
+int configure_attention_mma();
+int configure_attention_t5();
+int configure_gemm_tc();
+int configure_gemm_skinny();
+int configure_msda_tile();
+int configure_overlap();
+int configure_panoptic();
+int configure_swin();
+}  // namespace pvsg_internal
+
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

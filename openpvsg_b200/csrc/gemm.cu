@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(256) skinny_kernel(GemmParams p) {
     }
 }
 
+// opt in to `smem` bytes of dynamic shared memory on the current device (grow-only, per device)
 template <int NB>
-int launch_skinny(const GemmParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)NB * p.K + 128 * NB);
-    static size_t configured[PVSG_MAX_DEVICES];   // per device (function attributes are)
+int configure_skinny(size_t smem) {
+    static size_t configured[PVSG_MAX_DEVICES];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PVSG_MAX_DEVICES) dev = 0;
     if (smem > 48 * 1024 && smem > configured[dev]) {
@@ -388,11 +388,23 @@ int launch_skinny(const GemmParams& p, cudaStream_t st) {
             return PVSG_ERR_LAUNCH;
         configured[dev] = smem;
     }
+    return PVSG_OK;
+}
+
+template <int NB>
+int launch_skinny(const GemmParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)NB * p.K + 128 * NB);
+    if (const int rc = configure_skinny<NB>(smem)) return rc;
     skinny_kernel<NB><<<(unsigned)((p.N + NB - 1) / NB), 256, smem, st>>>(p);
     return pvsg_launch_status();
 }
 
 }  // namespace
+
+int pvsg_internal::configure_gemm_skinny() {
+    const int rc = configure_skinny<8>(204 * 1024);
+    return rc ? rc : configure_skinny<4>(204 * 1024);
+}
 
 extern "C" int pvsg_linear(const float* A, const float* A2, const float* W, const float* bias,
                            const float* R, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,

@@ -866,12 +866,18 @@ bool make_out_map_3d(CUtensorMap* m, const void* ptr, int64_t M, int64_t N, int6
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN>
-int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-              const TcParams& p, int B, cudaStream_t st) {
+int configure_tc() {
     static bool configured[PVSG_MAX_DEVICES];
     if (pvsg_first_use_on_device(configured) &&
         cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_TOTAL) != cudaSuccess)
         return PVSG_ERR_LAUNCH;
+    return PVSG_OK;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+              const TcParams& p, int B, cudaStream_t st) {
+    if (const int rc = configure_tc<BN>()) return rc;
     const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
     const unsigned grid = (unsigned)imin64(tiles, sm_count());
     TcParams q = p;
@@ -908,6 +914,11 @@ int pick_bn(int64_t tiles_m, int64_t N) {
 }
 
 }  // namespace
+
+int pvsg_internal::configure_gemm_tc() {
+    const int rc = configure_tc<128>();
+    return rc ? rc : configure_tc<256>();
+}
 
 extern "C" int pvsg_im2col_split(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int R, int S,
                                  int stride, int pad, int Kpad, void* stream) {

@@ -341,6 +341,16 @@ constexpr int kHX = 4, kHY = 3;
 
 }  // namespace
 
+int pvsg_internal::configure_msda_tile() {
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        (cudaFuncSetAttribute(msda_tile_kernel<kHX, kHY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Win<kHX, kHY>::SMEM) != cudaSuccess ||
+         cudaFuncSetAttribute(msda_tile_kernel<kHX, kHY>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared) != cudaSuccess))
+        return PVSG_ERR_LAUNCH;
+    return PVSG_OK;
+}
+
 // Region-tiled fused MSDeformAttn (queries = pyramid tokens, 3 levels x 4 points, 8 heads x 32 channels, levels
 // forming an exact 2x pyramid).  Returns PVSG_ERR_UNSUPPORTED when the shape does not qualify (the caller then
 // uses the lane-group kernel of msda.cu).
@@ -352,13 +362,7 @@ int pvsg_msda_tile_launch(const float* value, const int* hs, const int* ws, cons
     CUtensorMap maps[3];
     for (int l = 0; l < 3; ++l)
         if (!make_level_map(&maps[l], value, B, N, starts[l], hs[l], ws[l], W::wx(l), W::wy(l))) return PVSG_ERR_UNSUPPORTED;
-    static bool configured[PVSG_MAX_DEVICES];
-    if (pvsg_first_use_on_device(configured)) {
-        if (cudaFuncSetAttribute(msda_tile_kernel<kHX, kHY>, cudaFuncAttributeMaxDynamicSharedMemorySize, W::SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(msda_tile_kernel<kHX, kHY>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared) != cudaSuccess)
-            return PVSG_ERR_LAUNCH;
-    }
+    if (const int rc = pvsg_internal::configure_msda_tile()) return rc;
     TileLevels lv;
     for (int l = 0; l < 3; ++l) { lv.h[l] = hs[l]; lv.w[l] = ws[l]; lv.start[l] = starts[l]; }
     const int regions_x = (ws[2] + RW - 1) / RW, regions_y = (hs[2] + RH - 1) / RH;

@@ -124,6 +124,14 @@ __global__ void __launch_bounds__(256) overlap_kernel(const int32_t* __restrict_
 
 }  // namespace
 
+int pvsg_internal::configure_overlap() {
+    static bool configured[PVSG_MAX_DEVICES];   // idempotent, value-independent of the call
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
+    return PVSG_OK;
+}
+
 extern "C" int pvsg_tube_overlap(const int32_t* gt, const int32_t* pan, const int32_t* seg_info, int B, int Q,
                                  int H, int W, int G, int32_t* counts, void* stream) {
     PVSG_CHECK_ARG(gt && pan && seg_info && counts);
@@ -132,10 +140,7 @@ extern "C" int pvsg_tube_overlap(const int32_t* gt, const int32_t* pan, const in
     const size_t smem = (size_t)cells * sizeof(int32_t);
     PVSG_CHECK_ARG(smem <= 200 * 1024);
     cudaStream_t st = as_stream(stream);
-    static bool configured[PVSG_MAX_DEVICES];   // idempotent, value-independent of the call
-    if (pvsg_first_use_on_device(configured) &&
-        cudaFuncSetAttribute(overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-        return PVSG_ERR_LAUNCH;
+    if (const int rc = pvsg_internal::configure_overlap()) return rc;
     if (cudaMemsetAsync(counts, 0, (size_t)B * cells * sizeof(int32_t), st) != cudaSuccess) return PVSG_ERR_LAUNCH;
     const int64_t HW = (int64_t)H * W;
     const int64_t strips = (HW + kStrip - 1) / kStrip;

@@ -637,6 +637,14 @@ int make_geom(UpGeom& g, int h, int w, int in_h, int in_w, int img_h, int img_w,
 
 }  // namespace
 
+int pvsg_internal::configure_panoptic() {
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(ins_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
+    return PVSG_OK;
+}
+
 extern "C" int pvsg_panoptic_fuse_batched(const float* cls_logits, const float* mask_logits, int B, int Q, int NC,
                                           int num_things, int h, int w, int in_h, int in_w, int img_h, int img_w,
                                           int out_h, int out_w, float object_mask_thr, double iou_thr,
@@ -715,10 +723,7 @@ extern "C" int pvsg_instance_select_batched(const float* cls_logits, int B, int 
     PVSG_CHECK_ARG((int64_t)k <= (int64_t)Q * NC);
     const size_t smem = sizeof(float) * (size_t)Q * NC;
     if (smem > 200 * 1024) return PVSG_ERR_UNSUPPORTED;
-    static bool configured[PVSG_MAX_DEVICES];
-    if (pvsg_first_use_on_device(configured) &&
-        cudaFuncSetAttribute(ins_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-        return PVSG_ERR_LAUNCH;
+    if (const int rc = pvsg_internal::configure_panoptic()) return rc;
     ins_select_kernel<<<B, 1024, smem, as_stream(stream)>>>(cls_logits, Q, NC, k, top_scores, top_labels, top_query);
     return pvsg_launch_status();
 }

@@ -450,13 +450,15 @@ __global__ void __launch_bounds__(32 * KS16, CH16 == 1 ? 3 : 2) window_attention
     }
 }
 
+template <int KS16>
+constexpr size_t window_smem() {
+    return sizeof(__nv_bfloat16) * 4 * (16 * KS16) * kPitch + sizeof(float) * ((2 * kMaxWs - 1) * (2 * kMaxWs - 1) + 1) +
+           sizeof(int64_t) * (16 * KS16) + sizeof(int) * (16 * KS16);
+}
+
 template <int KS16, int CH16>
-static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv, const float* qkv_bias, const float* bias_table,
-                             float* out, __nv_bfloat16* oh, __nv_bfloat16* ol, int H, int W, int C, int heads, int window,
-                             int shift, int nwy, int nwx, float scale) {
-    constexpr int NK = 16 * KS16;
-    constexpr size_t smem = sizeof(__nv_bfloat16) * 4 * NK * kPitch + sizeof(float) * ((2 * kMaxWs - 1) * (2 * kMaxWs - 1) + 1) +
-                            sizeof(int64_t) * NK + sizeof(int) * NK;
+static int configure_window_mma() {
+    constexpr size_t smem = window_smem<KS16>();
     static bool configured[PVSG_MAX_DEVICES];
     if (pvsg_first_use_on_device(configured)) {
         // 50 KB per CTA: ask for the large shared-memory carve-out so that three CTAs fit an SM (ncu showed the default
@@ -467,6 +469,15 @@ static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv
                                  cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return PVSG_ERR_LAUNCH;
     }
+    return PVSG_OK;
+}
+
+template <int KS16, int CH16>
+static int launch_window_mma(dim3 grid, int N, cudaStream_t st, const float* qkv, const float* qkv_bias, const float* bias_table,
+                             float* out, __nv_bfloat16* oh, __nv_bfloat16* ol, int H, int W, int C, int heads, int window,
+                             int shift, int nwy, int nwx, float scale) {
+    constexpr size_t smem = window_smem<KS16>();
+    if (const int rc = configure_window_mma<KS16, CH16>()) return rc;
     const int warps = (N + 15) / 16;
     window_attention_mma_kernel<KS16, CH16><<<grid, 32 * warps, smem, st>>>(qkv, qkv_bias, bias_table, out, oh, ol, H, W, C, heads,
                                                                       window, shift, nwy, nwx, scale);
@@ -519,7 +530,22 @@ __global__ void __launch_bounds__(128) patch_merge_ln_kernel(const float* __rest
     }
 }
 
+int configure_patch_merge() {
+    static bool configured[PVSG_MAX_DEVICES];
+    if (pvsg_first_use_on_device(configured) &&
+        cudaFuncSetAttribute(patch_merge_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * 4) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
+    return PVSG_OK;
+}
+
 }  // namespace
+
+int pvsg_internal::configure_swin() {
+    int rc = configure_window_mma<4, 2>();
+    if (!rc) rc = configure_window_mma<9, 1>();
+    if (!rc) rc = configure_window_mma<9, 3>();
+    return rc ? rc : configure_patch_merge();
+}
 
 extern "C" int pvsg_window_attention(const float* qkv, const float* qkv_bias, const float* bias_table, float* out,
                                      void* out_hi, void* out_lo, int B, int H, int W, int C, int heads, int window,
@@ -567,10 +593,7 @@ extern "C" int pvsg_patch_merge_ln(const float* x, const float* gamma, const flo
     const int OH = (H + 1) / 2, OW = (W + 1) / 2;
     const int64_t total = (int64_t)B * OH * OW;
     const size_t smem = (size_t)4 * 4 * C * sizeof(float);
-    static bool configured[PVSG_MAX_DEVICES];
-    if (pvsg_first_use_on_device(configured) &&
-        cudaFuncSetAttribute(patch_merge_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * 4) != cudaSuccess)
-        return PVSG_ERR_LAUNCH;
+    if (const int rc = configure_patch_merge()) return rc;
     const unsigned grid = (unsigned)imin64((total + 3) / 4, 148 * 16);
     patch_merge_ln_kernel<<<grid, 128, smem, as_stream(stream)>>>(x, gamma, beta, y, B, H, W, C, OH, OW, eps);
     return pvsg_launch_status();

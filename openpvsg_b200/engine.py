@@ -136,6 +136,7 @@ class FrameRunner:
         return out
 
     def _capture(self, first=True):
+        _l.handle(torch.cuda.current_device())      # kernel attributes configured before anything is captured
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -24,6 +24,10 @@ SIGNATURES = {
     'pvsg_version': (I, []),
     'pvsg_error_string': (c_char_p, [I]),
     'pvsg_device_info': (I, [I, P, P, P]),
+    'pvsg_create': (I, [I, P]),
+    'pvsg_destroy': (I, [P]),
+    'pvsg_handle_info': (I, [P, P, P, P, P]),
+    'pvsg_workspace': (I, [P, L, P]),
     'pvsg_linear': (I, [P, P, P, P, P, P, L, L, L, L, L, L, L, I, L, L, L, L, P]),
     'pvsg_conv2d_nhwc': (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     'pvsg_split_bf16': (I, [P, P, P, P, L, P]),
@@ -124,6 +128,54 @@ def load():
         raise PvsgError('libpvsg_sm100.so version mismatch')
     _lib = lib
     return lib
+
+
+class Handle:
+    """pvsg_create / pvsg_destroy (include/pvsg.h): pins a device, configures every kernel's opt-in attributes on it
+    before any capture, owns a grow-only scratch block."""
+
+    def __init__(self, device):
+        self._h = ctypes.c_void_p()
+        code = load().pvsg_create(int(device), ctypes.byref(self._h))
+        if code != 0:
+            raise PvsgError(f'pvsg_create({device}) failed: {load().pvsg_error_string(code).decode()} ({code})')
+
+    def info(self):
+        dev, sms, smem, ws = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+        code = load().pvsg_handle_info(self._h, ctypes.byref(dev), ctypes.byref(sms), ctypes.byref(smem), ctypes.byref(ws))
+        if code != 0:
+            raise PvsgError(f'pvsg_handle_info failed ({code})')
+        return {'device': dev.value, 'sm_count': sms.value, 'smem_optin_bytes': smem.value, 'workspace_bytes': ws.value}
+
+    def workspace(self, nbytes):
+        ptr = ctypes.c_void_p()
+        code = load().pvsg_workspace(self._h, int(nbytes), ctypes.byref(ptr))
+        if code != 0:
+            raise PvsgError(f'pvsg_workspace({nbytes}) failed: {load().pvsg_error_string(code).decode()} ({code})')
+        return ptr.value
+
+    def close(self):
+        if self._h:
+            load().pvsg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def handle(device):
+    """The process-wide handle of a device index (created on first use; engine.FrameRunner and the relation head's
+    graph capture call this before capturing)."""
+    device = int(device)
+    if device not in _handles:
+        _handles[device] = Handle(device)
+    return _handles[device]
 
 
 # kernels launched per successful C-ABI call (lower bounds; used for bench.py's gpu_launches)

@@ -10,6 +10,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import lib as _l
 from . import ops
 
 
@@ -325,6 +326,7 @@ def _graphed_forward(models, feats, num_top_pairs):
     cache = holder.__dict__.setdefault('_pvsg_graphs', {})
     hit = cache.get(key)
     if hit is None:
+        _l.handle(feats.device.index if feats.device.index is not None else torch.cuda.current_device())
         cache.clear()                      # one shape at a time: a changed clip length / weights epoch drops the old graph
         static_in = torch.empty_like(feats)
         static_in.copy_(feats)

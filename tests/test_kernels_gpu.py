@@ -520,3 +520,24 @@ def test_error_codes(ops):
     with pytest.raises(lib.PvsgError):
         ops.msda_forward(torch.zeros(1, 10, 8, 32, device='cuda'), [(2, 3)],
                          torch.zeros(1, 10, 8, 1, 4, 2, device='cuda'), torch.zeros(1, 10, 8, 1, 4, device='cuda'))
+
+
+@pytest.mark.gpu
+def test_handle_create_workspace_destroy():
+    """include/pvsg.h handle API: create on a device, grow-only workspace, info, destroy; bad device is refused."""
+    from openpvsg_b200 import lib as l
+    h = l.Handle(0)
+    info = h.info()
+    assert info['device'] == 0 and info['sm_count'] >= 100 and info['smem_optin_bytes'] >= 200 * 1024 and info['workspace_bytes'] == 0
+    p1 = h.workspace(1000)
+    assert p1 and h.info()['workspace_bytes'] == 1024
+    assert h.workspace(512) == p1 and h.workspace(0) == p1            # never shrinks, same block
+    p2 = h.workspace(1 << 20)
+    assert p2 and h.info()['workspace_bytes'] == 1 << 20
+    t = torch.zeros(4, device='cuda')                                  # the device still works after a grow
+    assert float((t + 1).sum()) == 4.0
+    h.close()
+    h.close()                                                          # idempotent
+    with pytest.raises(l.PvsgError):
+        l.Handle(torch.cuda.device_count() + 3)
+    assert l.handle(0) is l.handle(0)
