@@ -498,6 +498,30 @@ int pvsg_msda_backward(const float* value, const int64_t* spatial_shapes, const 
                        float* grad_value, float* grad_loc, float* grad_attn, int B, int64_t N, int64_t Nq, int H, int D,
                        int L, int P, void* stream);
 
+/* ---- second training slice: backward of the decoder head (forward_train, mask2former_video_head.py:464-522).  Every
+ * dense product of the backward pass is pvsg_linear again (dX = dY W, dW^T = X^T dY on transposed copies). ---- */
+
+/* nn.LayerNorm backward over the last axis of x [M,C]: dx [M,C]; dgamma / dbeta [C] = sums over the rows (zeroed here). */
+int pvsg_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma, float* dbeta,
+                            int64_t M, int C, float eps, void* stream);
+/* dx = dy where the forward OUTPUT y of a ReLU-fused layer was positive, else 0. */
+int pvsg_relu_backward(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* out[n] = sum_m x[m*ld + n]: bias gradients, d level_embed, gradient of a batch broadcast (out zeroed here). */
+int pvsg_colsum(const float* x, float* out, int64_t M, int N, int64_t ld, void* stream);
+/* nn.MultiheadAttention core as the decoder calls it (mask2former_head.py:457-468) in training: out = softmax(scale q k^T
+ * + mask) v per head, exact fp32, also returning the row log-sum-exp lse [B,H,Lq] for the backward.  q [B,Lq,H*D],
+ * k / v [B,Lk,H*D] with batch / row strides in floats (multiples of 4), D = 32; mask uint8 [B,Lq,Lk] (non-zero = blocked,
+ * shared by the heads) with row_open [B,Lq] = open keys per row (a row with none ignores the mask, :451-452); both may be
+ * NULL.  _backward: dq [B,Lq,H*D], dk / dv [B,Lk,H*D] contiguous; `dout` laid out like `out`; delta [B,H,Lq] scratch. */
+int pvsg_attention_train_forward(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_open,
+                                 float* out, float* lse, int B, int H, int Lq, int Lk, int D, int64_t q_bs, int64_t q_rs,
+                                 int64_t k_bs, int64_t k_rs, int64_t v_bs, int64_t v_rs, int64_t o_bs, int64_t o_rs, float scale,
+                                 void* stream);
+int pvsg_attention_train_backward(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_open,
+                                  const float* out, const float* dout, const float* lse, float* delta, float* dq, float* dk,
+                                  float* dv, int B, int H, int Lq, int Lk, int D, int64_t q_bs, int64_t q_rs, int64_t k_bs,
+                                  int64_t k_rs, int64_t v_bs, int64_t v_rs, int64_t o_bs, int64_t o_rs, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

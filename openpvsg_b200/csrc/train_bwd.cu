@@ -1,0 +1,340 @@
+// Training of the transformer decoder head (second slice): the backward kernels that, together with
+// the forward engine (pvsg_linear for every dense product, forward AND backward), make
+// Mask2FormerVideoHead.forward_train (models/mask2former_vps/mask2former_video_head.py:464-522) run on the device:
+//
+//   pvsg_layernorm_backward      nn.LayerNorm backward: dx, and dgamma / dbeta accumulated over the rows
+//   pvsg_relu_backward           dx = dy where the forward output was positive (FFN / mask-embed MLP)
+//   pvsg_colsum                  out[n] = sum_m x[m, n]: bias gradients, level_embed, the broadcast of the query embeddings
+//   pvsg_attention_train_forward masked multi-head attention that also returns the row log-sum-exp (exact fp32, SIMT)
+//   pvsg_attention_train_backward dq, dk, dv from (q, k, v, o, do, lse) with the same mask -- nn.MultiheadAttention's
+//                                softmax(q k^T / sqrt(d) + mask) v as mmcv's MultiheadAttention wrapper calls it
+//                                (mask2former_head.py:457-468); recomputes the probabilities, never stores them
+//
+// First cut, sized for correctness at training shapes (batch 1-4, 100 queries, <= 15 k keys, head dim 32): exact fp32
+// SIMT, deterministic (no atomics except the column sums).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ LayerNorm backward
+// One warp per row (rows strided over the grid); lane owns columns lane, lane + 32, ...  CPL = C / 32 columns per lane.
+template <int CPL>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ dy, float* __restrict__ dx,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, float eps) {
+    constexpr int C = 32 * CPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float g[CPL], dg[CPL], db[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { g[i] = gamma[lane + 32 * i]; dg[i] = 0.f; db[i] = 0.f; }
+    for (int64_t r = (int64_t)blockIdx.x * nwarp + warp; r < M; r += (int64_t)gridDim.x * nwarp) {
+        float xv[CPL], dv[CPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { xv[i] = x[r * C + lane + 32 * i]; dv[i] = dy[r * C + lane + 32 * i]; s += xv[i]; }
+        const float mean = warp_sum(s) * (1.f / C);
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { xv[i] -= mean; v = fmaf(xv[i], xv[i], v); }
+        const float rstd = rsqrtf(warp_sum(v) * (1.f / C) + eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            xv[i] *= rstd;                         // xhat
+            const float gi = dv[i] * g[i];
+            sg += gi;
+            sgx = fmaf(gi, xv[i], sgx);
+            dg[i] = fmaf(dv[i], xv[i], dg[i]);
+            db[i] += dv[i];
+        }
+        sg = warp_sum(sg) * (1.f / C);
+        sgx = warp_sum(sgx) * (1.f / C);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) dx[r * C + lane + 32 * i] = rstd * (dv[i] * g[i] - sg - xv[i] * sgx);
+    }
+    // CTA reduction of the parameter gradients, then one atomic per column and CTA
+    __shared__ float sh[2][8][C];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { sh[0][warp][lane + 32 * i] = dg[i]; sh[1][warp][lane + 32 * i] = db[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < nwarp; ++w) { a += sh[0][w][c]; b += sh[1][w][c]; }
+        atomicAdd(dgamma + c, a);
+        atomicAdd(dbeta + c, b);
+    }
+}
+
+// any C: one warp per row, parameter gradients by direct atomics (slow path, small tensors only)
+__global__ void __launch_bounds__(256) ln_bwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ dy, float* __restrict__ dx,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M,
+                                                             int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* xr = x + r * C;
+    const float* dr = dy + r * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    float sg = 0.f, sgx = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float xh = (xr[c] - mean) * rstd, gi = dr[c] * gamma[c];
+        sg += gi;
+        sgx = fmaf(gi, xh, sgx);
+    }
+    sg = warp_sum(sg) / (float)C;
+    sgx = warp_sum(sgx) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+        const float xh = (xr[c] - mean) * rstd;
+        dx[r * C + c] = rstd * (dr[c] * gamma[c] - sg - xh * sgx);
+        atomicAdd(dgamma + c, dr[c] * xh);
+        atomicAdd(dbeta + c, dr[c]);
+    }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                       float* __restrict__ dx, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+// out[n] (+)= sum over a slab of rows; block (32, 8), grid (ceil(N/32), row slabs)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t M, int N,
+                                                     int64_t ld, int64_t rows_per_slab) {
+    __shared__ float sh[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+    const int64_t r1 = r0 + rows_per_slab < M ? r0 + rows_per_slab : M;
+    float s = 0.f;
+    if (col < N)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + col];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+        atomicAdd(out + col, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ attention (training)
+constexpr int AD = 32;      // head dim
+
+struct AttnT {
+    const float *q, *k, *v;
+    const uint8_t* mask;        // [B, Lq, Lk], non-zero = blocked (shared by the heads), or null
+    const int32_t* row_open;    // [B, Lq]: number of open keys of the row (0 -> the row ignores the mask), or null
+    int B, H, Lq, Lk;
+    int64_t qb, qr, kb, kr, vb, vr;   // batch / row strides (floats)
+    float scale;
+};
+
+__device__ __forceinline__ void load_row(const float* p, float (&r)[AD]) {
+#pragma unroll
+    for (int i = 0; i < AD / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+        r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ float dot_row(const float* p, const float (&r)[AD]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < AD / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+        s = fmaf(t.x, r[4 * i], s); s = fmaf(t.y, r[4 * i + 1], s); s = fmaf(t.z, r[4 * i + 2], s); s = fmaf(t.w, r[4 * i + 3], s);
+    }
+    return s;
+}
+// after the call lane d holds the warp-wide sum of acc[d]
+__device__ __forceinline__ float reduce_rows(float (&acc)[AD], int lane) {
+    float mine = 0.f;
+#pragma unroll
+    for (int d = 0; d < AD; ++d) {
+        const float t = warp_sum(acc[d]);
+        if (lane == d) mine = t;
+    }
+    return mine;
+}
+
+// one warp per (b, h, query): lanes stride over the keys
+__global__ void __launch_bounds__(128) attn_train_fwd_kernel(AttnT a, float* __restrict__ out, int64_t ob, int64_t orow,
+                                                             float* __restrict__ lse) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)a.B * a.H * a.Lq) return;
+    const int qi = (int)(w % a.Lq), h = (int)((w / a.Lq) % a.H), b = (int)(w / ((int64_t)a.Lq * a.H));
+    float q[AD];
+    load_row(a.q + b * a.qb + qi * a.qr + h * AD, q);
+    const uint8_t* m = a.mask ? a.mask + ((int64_t)b * a.Lq + qi) * a.Lk : nullptr;
+    if (m && a.row_open && a.row_open[b * a.Lq + qi] == 0) m = nullptr;
+    const float* kp = a.k + b * a.kb + h * AD;
+    const float* vp = a.v + b * a.vb + h * AD;
+    float mx = -INFINITY;
+    for (int j = lane; j < a.Lk; j += 32)
+        if (!m || !m[j]) mx = fmaxf(mx, a.scale * dot_row(kp + j * a.kr, q));
+    mx = warp_max(mx);
+    float l = 0.f, acc[AD];
+#pragma unroll
+    for (int d = 0; d < AD; ++d) acc[d] = 0.f;
+    for (int j = lane; j < a.Lk; j += 32) {
+        if (m && m[j]) continue;
+        const float p = expf(a.scale * dot_row(kp + j * a.kr, q) - mx);
+        l += p;
+        const float* vr = vp + j * a.vr;
+#pragma unroll
+        for (int i = 0; i < AD / 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(vr + 4 * i);
+            acc[4 * i] = fmaf(p, t.x, acc[4 * i]); acc[4 * i + 1] = fmaf(p, t.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(p, t.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(p, t.w, acc[4 * i + 3]);
+        }
+    }
+    l = warp_sum(l);
+    const float o = reduce_rows(acc, lane);
+    out[b * ob + qi * orow + h * AD + lane] = o / l;
+    if (lane == 0) lse[w] = mx + logf(l);
+}
+
+// dq: one warp per (b, h, query); also writes delta = <do, o> for the dk / dv pass
+__global__ void __launch_bounds__(128) attn_train_dq_kernel(AttnT a, const float* __restrict__ o, int64_t ob, int64_t orow,
+                                                            const float* __restrict__ dout, int64_t dob, int64_t dor,
+                                                            const float* __restrict__ lse, float* __restrict__ delta,
+                                                            float* __restrict__ dq, int64_t dqb, int64_t dqr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)a.B * a.H * a.Lq) return;
+    const int qi = (int)(w % a.Lq), h = (int)((w / a.Lq) % a.H), b = (int)(w / ((int64_t)a.Lq * a.H));
+    float q[AD], g[AD], acc[AD];
+    load_row(a.q + b * a.qb + qi * a.qr + h * AD, q);
+    load_row(dout + b * dob + qi * dor + h * AD, g);
+    const float dl = dot_row(o + b * ob + qi * orow + h * AD, g);
+    if (lane == 0) delta[w] = dl;
+    const float ls = lse[w];
+    const uint8_t* m = a.mask ? a.mask + ((int64_t)b * a.Lq + qi) * a.Lk : nullptr;
+    if (m && a.row_open && a.row_open[b * a.Lq + qi] == 0) m = nullptr;
+    const float* kp = a.k + b * a.kb + h * AD;
+    const float* vp = a.v + b * a.vb + h * AD;
+#pragma unroll
+    for (int d = 0; d < AD; ++d) acc[d] = 0.f;
+    for (int j = lane; j < a.Lk; j += 32) {
+        if (m && m[j]) continue;
+        const float* kr = kp + j * a.kr;
+        const float p = expf(a.scale * dot_row(kr, q) - ls);
+        const float ds = p * (dot_row(vp + j * a.vr, g) - dl) * a.scale;
+#pragma unroll
+        for (int i = 0; i < AD / 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(kr + 4 * i);
+            acc[4 * i] = fmaf(ds, t.x, acc[4 * i]); acc[4 * i + 1] = fmaf(ds, t.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(ds, t.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(ds, t.w, acc[4 * i + 3]);
+        }
+    }
+    dq[b * dqb + qi * dqr + h * AD + lane] = reduce_rows(acc, lane);
+}
+
+// dk, dv: one warp per (b, h, key), lane = channel; loops over the queries
+__global__ void __launch_bounds__(128) attn_train_dkv_kernel(AttnT a, const float* __restrict__ dout, int64_t dob, int64_t dor,
+                                                             const float* __restrict__ lse, const float* __restrict__ delta,
+                                                             float* __restrict__ dk, int64_t dkb, int64_t dkr,
+                                                             float* __restrict__ dv, int64_t dvb, int64_t dvr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)a.B * a.H * a.Lk) return;
+    const int j = (int)(w % a.Lk), h = (int)((w / a.Lk) % a.H), b = (int)(w / ((int64_t)a.Lk * a.H));
+    const float kc = a.k[b * a.kb + j * a.kr + h * AD + lane];
+    const float vc = a.v[b * a.vb + j * a.vr + h * AD + lane];
+    float gk = 0.f, gv = 0.f;
+    const float* qp = a.q + b * a.qb + h * AD + lane;
+    const float* gp = dout + b * dob + h * AD + lane;
+    const float* lp = lse + ((int64_t)b * a.H + h) * a.Lq;
+    const float* dp = delta + ((int64_t)b * a.H + h) * a.Lq;
+    for (int qi = 0; qi < a.Lq; ++qi) {
+        if (a.mask && a.mask[((int64_t)b * a.Lq + qi) * a.Lk + j] && !(a.row_open && a.row_open[b * a.Lq + qi] == 0)) continue;
+        const float qc = qp[qi * a.qr], gc = gp[qi * dor];
+        const float s = warp_sum(qc * kc), dpv = warp_sum(gc * vc);
+        const float p = expf(a.scale * s - lp[qi]);
+        gv = fmaf(p, gc, gv);
+        gk = fmaf(p * (dpv - dp[qi]) * a.scale, qc, gk);
+    }
+    dk[b * dkb + j * dkr + h * AD + lane] = gk;
+    dv[b * dvb + j * dvr + h * AD + lane] = gv;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline bool attn_args_ok(const AttnT& a) {
+    return a.q && a.k && a.v && a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0 && al16(a.q) && al16(a.k) && al16(a.v) &&
+           a.qb % 4 == 0 && a.qr % 4 == 0 && a.kb % 4 == 0 && a.kr % 4 == 0 && a.vb % 4 == 0 && a.vr % 4 == 0;
+}
+
+}  // namespace
+
+extern "C" int pvsg_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
+                                       float* dbeta, int64_t M, int C, float eps, void* stream) {
+    PVSG_CHECK_ARG(x && gamma && dy && dx && dgamma && dbeta && M > 0 && C > 0);
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st) != cudaSuccess || cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
+    if (C == 256) {
+        const unsigned grid = (unsigned)imin64((M + 7) / 8, 148 * 4);
+        ln_bwd_kernel<8><<<grid, 256, 0, st>>>(x, gamma, dy, dx, dgamma, dbeta, M, eps);
+    } else {
+        ln_bwd_generic_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, gamma, dy, dx, dgamma, dbeta, M, C, eps);
+    }
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_relu_backward(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+    PVSG_CHECK_ARG(dy && y && dx && n > 0);
+    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dy, y, dx, n);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_colsum(const float* x, float* out, int64_t M, int N, int64_t ld, void* stream) {
+    PVSG_CHECK_ARG(x && out && M > 0 && N > 0 && ld >= N);
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(out, 0, sizeof(float) * N, st) != cudaSuccess) return PVSG_ERR_LAUNCH;
+    const int64_t col_blocks = (N + 31) / 32;
+    int64_t slabs = imin64((M + 63) / 64, (148 * 8 + col_blocks - 1) / col_blocks);
+    if (slabs < 1) slabs = 1;
+    if (slabs > 65535) slabs = 65535;
+    const int64_t rows_per_slab = (M + slabs - 1) / slabs;
+    colsum_kernel<<<dim3((unsigned)col_blocks, (unsigned)slabs), dim3(32, 8), 0, st>>>(x, out, M, N, ld, rows_per_slab);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_attention_train_forward(const float* q, const float* k, const float* v, const uint8_t* mask,
+                                            const int32_t* row_open, float* out, float* lse, int B, int H, int Lq, int Lk,
+                                            int D, int64_t q_bs, int64_t q_rs, int64_t k_bs, int64_t k_rs, int64_t v_bs,
+                                            int64_t v_rs, int64_t o_bs, int64_t o_rs, float scale, void* stream) {
+    AttnT a{q, k, v, mask, row_open, B, H, Lq, Lk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, scale};
+    PVSG_CHECK_ARG(out && lse && attn_args_ok(a));
+    if (D != AD) return PVSG_ERR_UNSUPPORTED;
+    const int64_t warps = (int64_t)B * H * Lq;
+    attn_train_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, as_stream(stream)>>>(a, out, o_bs, o_rs, lse);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_attention_train_backward(const float* q, const float* k, const float* v, const uint8_t* mask,
+                                             const int32_t* row_open, const float* out, const float* dout, const float* lse,
+                                             float* delta, float* dq, float* dk, float* dv, int B, int H, int Lq, int Lk, int D,
+                                             int64_t q_bs, int64_t q_rs, int64_t k_bs, int64_t k_rs, int64_t v_bs, int64_t v_rs,
+                                             int64_t o_bs, int64_t o_rs, float scale, void* stream) {
+    AttnT a{q, k, v, mask, row_open, B, H, Lq, Lk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, scale};
+    PVSG_CHECK_ARG(out && dout && lse && delta && dq && dk && dv && attn_args_ok(a) && al16(out) && al16(dout) &&
+                   o_bs % 4 == 0 && o_rs % 4 == 0);
+    if (D != AD) return PVSG_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    const int E = H * AD;
+    // gradients are written contiguous: dq [B, Lq, E], dk / dv [B, Lk, E]; dout shares the layout of out
+    const int64_t wq = (int64_t)B * H * Lq, wk = (int64_t)B * H * Lk;
+    attn_train_dq_kernel<<<(unsigned)((wq + 3) / 4), 128, 0, st>>>(a, out, o_bs, o_rs, dout, o_bs, o_rs, lse, delta, dq,
+                                                                   (int64_t)Lq * E, E);
+    attn_train_dkv_kernel<<<(unsigned)((wk + 3) / 4), 128, 0, st>>>(a, dout, o_bs, o_rs, lse, delta, dk, (int64_t)Lk * E, E, dv,
+                                                                    (int64_t)Lk * E, E);
+    return pvsg_launch_status();
+}

@@ -75,6 +75,11 @@ SIGNATURES = {
     'pvsg_reconsdot_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_reconsdot': (I, [P, P, P, P, I, I, I, I, I, F, P]),
     'pvsg_lap_assign': (I, [P, I, I, D, P, P, P]),
+    'pvsg_layernorm_backward': (I, [P, P, P, P, P, P, L, I, F, P]),
+    'pvsg_relu_backward': (I, [P, P, P, L, P]),
+    'pvsg_colsum': (I, [P, P, L, I, L, P]),
+    'pvsg_attention_train_forward': (I, [P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
+    'pvsg_attention_train_backward': (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_cosine_chain_cost': (I, [P, P, I, I, I, P]),
     'pvsg_lap_square_batched': (I, [P, I, I, P, P, P]),
     'pvsg_perm_chain': (I, [P, P, I, I, P]),

@@ -652,6 +652,84 @@ def mask_match_cost(cls_logits, gt_labels, pred_points, gt_points, w_cls=2.0, w_
     return cost
 
 
+def layernorm_backward(x, gamma, dy, eps=1e-5):
+    """nn.LayerNorm backward over the last axis -> (dx, dgamma, dbeta)."""
+    lib = _l.load()
+    C = _f32(x).shape[-1]
+    x, dy = x.contiguous(), _f32(dy).contiguous()
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32)
+    db = torch.empty(C, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_layernorm_backward(_ptr(x), _ptr(_f32(gamma).contiguous()), _ptr(dy), _ptr(dx), _ptr(dg), _ptr(db),
+                                         x.numel() // C, C, eps, _stream()), 'pvsg_layernorm_backward')
+    return dx, dg, db
+
+
+def relu_backward(dy, y):
+    lib = _l.load()
+    dy, y = _f32(dy).contiguous(), _f32(y).contiguous()
+    dx = torch.empty_like(dy)
+    _l.check(lib.pvsg_relu_backward(_ptr(dy), _ptr(y), _ptr(dx), dy.numel(), _stream()), 'pvsg_relu_backward')
+    return dx
+
+
+def colsum(x):
+    """x [M,N] (row stride >= N) -> [N] column sums."""
+    lib = _l.load()
+    x2, M, N, ld = _rows(x, 'x')
+    out = torch.empty(N, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_colsum(_ptr(x2), _ptr(out), M, N, ld, _stream()), 'pvsg_colsum')
+    return out
+
+
+def _attn_train_args(q, k, v, num_heads, mask, row_open):
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _f32(t, n)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise _l.PvsgError(f'attention_train: {n} must be [B,L,E] with unit inner stride')
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    if E // num_heads != 32 or E % num_heads:
+        raise _l.PvsgError('attention_train: head dim 32 only')
+    if mask is not None and not (mask.dtype == torch.uint8 and mask.is_contiguous() and tuple(mask.shape) == (B, Lq, Lk)):
+        raise _l.PvsgError('attention_train: mask must be contiguous uint8 [B,Lq,Lk]')
+    if row_open is not None and not (row_open.dtype == torch.int32 and row_open.is_contiguous()):
+        raise _l.PvsgError('attention_train: row_open must be contiguous int32')
+    return B, Lq, Lk, E
+
+
+def attention_train_forward(q, k, v, num_heads, mask=None, row_open=None):
+    """Training-time attention: -> (out [B,Lq,E], lse [B,H,Lq])."""
+    lib = _l.load()
+    B, Lq, Lk, E = _attn_train_args(q, k, v, num_heads, mask, row_open)
+    out = torch.empty(B, Lq, E, device=q.device, dtype=torch.float32)
+    lse = torch.empty(B, num_heads, Lq, device=q.device, dtype=torch.float32)
+    _l.check(lib.pvsg_attention_train_forward(_ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(row_open), _ptr(out), _ptr(lse), B,
+                                              num_heads, Lq, Lk, 32, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
+                                              v.stride(0), v.stride(1), out.stride(0), out.stride(1), 32 ** -0.5, _stream()),
+             'pvsg_attention_train_forward')
+    return out, lse
+
+
+def attention_train_backward(q, k, v, num_heads, mask, row_open, out, dout, lse):
+    """-> (dq [B,Lq,E], dk [B,Lk,E], dv [B,Lk,E])."""
+    lib = _l.load()
+    B, Lq, Lk, E = _attn_train_args(q, k, v, num_heads, mask, row_open)
+    dout = _f32(dout).contiguous()
+    if not out.is_contiguous():
+        raise _l.PvsgError('attention_train_backward: contiguous forward output required')
+    dq = torch.empty(B, Lq, E, device=q.device, dtype=torch.float32)
+    dk = torch.empty(B, Lk, E, device=q.device, dtype=torch.float32)
+    dv = torch.empty(B, Lk, E, device=q.device, dtype=torch.float32)
+    delta = torch.empty(B, num_heads, Lq, device=q.device, dtype=torch.float32)
+    _l.check(lib.pvsg_attention_train_backward(_ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(row_open), _ptr(out), _ptr(dout),
+                                               _ptr(lse), _ptr(delta), _ptr(dq), _ptr(dk), _ptr(dv), B, num_heads, Lq, Lk, 32,
+                                               q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                               out.stride(0), out.stride(1), 32 ** -0.5, _stream()),
+             'pvsg_attention_train_backward')
+    return dq, dk, dv
+
+
 def attention(q, k, v, num_heads, mask=None, row_open=None, scale=None, out=None):
     """q [B,Lq,E], k/v [B,Lk,E] (any batch / token strides, unit inner stride) -> [B,Lq,E].
     mask uint8 [B,Lq,Lk] (non-zero = blocked), row_open int32 [B,Lq].
