@@ -610,6 +610,26 @@ class DetrTransformerDecoderLayer(nn.Module):
         x, _, xq = ops.layernorm(x, n2.weight, n2.bias, n2.eps, out_split=True, add=query_pos)
         return x, xq
 
+    def forward_tokens_train(self, query, query_pos, kproj, vproj, mask, row_open):
+        """``forward_tokens`` on the autograd tape (train_ops): same operation order, fp32 tensors, every forward and
+        backward step a library kernel.  Dropout rates of the reference config are all 0 (base cfg :70-83)."""
+        from . import train_ops as T
+        ca, sa, ffn = self.attentions[0], self.attentions[1], self.ffns[0]
+        n0, n1, n2 = self.norms
+        E = self.embed_dims
+        w, b = ca.attn.in_proj_weight, ca.attn.in_proj_bias
+        q = T.linear(query, w[:E], b[:E], add_input=query_pos)
+        o = T.attention(q, kproj, vproj, ca.num_heads, mask, row_open)
+        x = T.layernorm(T.linear(o, ca.attn.out_proj.weight, ca.attn.out_proj.bias, residual=query), n0)
+        w, b = sa.attn.in_proj_weight, sa.attn.in_proj_bias
+        qk = T.linear(x, w[:2 * E], b[:2 * E], add_input=query_pos)
+        v = T.linear(x, w[2 * E:], b[2 * E:])
+        o = T.attention(qk[..., :E], qk[..., E:], v, sa.num_heads)
+        x = T.layernorm(T.linear(o, sa.attn.out_proj.weight, sa.attn.out_proj.bias, residual=x), n1)
+        h = T.linear(x, ffn.layers[0][0].weight, ffn.layers[0][0].bias, act=ops.ACT_RELU)
+        x = T.linear(h, ffn.layers[1].weight, ffn.layers[1].bias, residual=x if ffn.add_identity else None)
+        return T.layernorm(x, n2)
+
     @torch.no_grad()
     def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
                 query_key_padding_mask=None, key_padding_mask=None, **kwargs):
@@ -687,10 +707,117 @@ class _Mask2FormerHeadBase(_Prepared):
     def init_weights(self):
         pass
 
-    def forward_train(self, *a, **k):
-        raise NotImplementedError('forward_train: the losses (loss / loss_single, openpvsg_b200/losses.py) and the deformable '
-                                  "attention backward are built; the backward of the GEMM / attention engine is not "
-                                  '(SURVEY.md 8f rank 4, DESIGN.md section 7)')
+    # ---- training: decoder head on the autograd tape, pixel decoder / backbone frozen ----
+    def _embeds_train(self, query):
+        from . import train_ops as T
+        x = T.layernorm(query, self.transformer_decoder.post_norm)
+        cls_pred = T.linear(x, self.cls_embed.weight, self.cls_embed.bias)
+        me = T.linear(x, self.mask_embed[0].weight, self.mask_embed[0].bias, act=ops.ACT_RELU)
+        me = T.linear(me, self.mask_embed[2].weight, self.mask_embed[2].bias, act=ops.ACT_RELU)
+        return cls_pred, T.linear(me, self.mask_embed[4].weight, self.mask_embed[4].bias)
+
+    def forward_train_outputs(self, feats, num_frames=1):
+        """The training-mode ``forward`` (mask2former_video_head.py:361-462 / mask2former_head.py:397-479): ->
+        (all_cls_scores [L+1] x [B,Q,NC+1], all_mask_preds [L+1] x [B,T,Q,h,w] (video) / [B,Q,h,w] (image)), differentiable
+        w.r.t. every parameter of the transformer decoder, the prediction heads, the query / level embeddings.  The pixel
+        decoder and the backbone run under no_grad (their GEMM / conv backward is not built: DESIGN.md section 7)."""
+        from . import train_ops as T
+        with torch.no_grad():
+            mask_features, memories = self.pixel_decoder(feats)
+            BT = mask_features.shape[0]
+            Tn = num_frames
+            B = BT // Tn
+            assert B * Tn == BT
+            mf = _tokens(mask_features)
+            _, h4, w4, C = mf.shape
+            mf_flat = mf.view(B, Tn * h4 * w4, C)
+            lvl_shapes = [tuple(m.shape[-2:]) for m in memories]
+            pooled = [ops.bilinear_resize_nhwc(mf, s).view(B, -1, C) for s in lvl_shapes]
+            toks = [_tokens(m) for m in memories]
+            dec_pe = [self._batched(self._decoder_pe((Tn, h, w), mf.device), B) for h, w in lvl_shapes]
+        dec_in = [T.add_rowvec(tok, self.level_embed.weight[i]).view(B, -1, C) for i, tok in enumerate(toks)]
+        Q = self.num_queries
+        query = T.expand_batch(self.query_feat.weight, B)
+        qpos = T.expand_batch(self.query_embed.weight, B)
+        layers = self.transformer_decoder.layers
+        nl = self.num_transformer_decoder_layers
+        E = self.decoder_embed_dims
+
+        def predict(query, nxt):
+            cls_pred, me = self._embeds_train(query)
+            mask_pred = T.mask_logits(me, mf_flat).view(B, Q, Tn, h4, w4).transpose(1, 2)
+            with torch.no_grad():          # attn_mask = (interpolate(mask_pred).sigmoid() < 0.5).detach(), :346-357
+                _, mask, row_open = ops.mask_logits(me.detach(), pooled[nxt], False, True)
+            return cls_pred, mask_pred, mask, row_open
+
+        cls_list, mask_list = [], []
+        cls_pred, mask_pred, mask, row_open = predict(query, 0)
+        cls_list.append(cls_pred)
+        mask_list.append(mask_pred)
+        for i in range(nl):
+            lvl = i % self.num_transformer_feat_level
+            ca = layers[i].attentions[0]
+            w, b = ca.attn.in_proj_weight, ca.attn.in_proj_bias
+            kproj = T.linear(dec_in[lvl], w[E:2 * E], b[E:2 * E], add_input=dec_pe[lvl])
+            vproj = T.linear(dec_in[lvl], w[2 * E:], b[2 * E:])
+            if self._capture_masks is not None:
+                self._capture_masks.append(mask)
+            query = layers[i].forward_tokens_train(query, qpos, kproj, vproj, mask, row_open)
+            cls_pred, mask_pred, mask, row_open = predict(query, (i + 1) % self.num_transformer_feat_level)
+            cls_list.append(cls_pred)
+            mask_list.append(mask_pred)
+        if not self.video:
+            mask_list = [m[:, 0] for m in mask_list]
+        return cls_list, mask_list
+
+    def preprocess_gt(self, gt_labels_list, gt_masks_list, gt_semantic_seg, gt_instance_ids, img_metas):
+        """maskformer_video_head.py:138-180 + utils.py:94-140 (``preprocess_video_panoptic_gt``): per clip, one label and
+        one [T,H,W] mask stack per instance id; frames without the instance get an empty mask.  ``gt_labels`` /
+        ``gt_instance_ids`` [n,2] = (frame, value); ``gt_masks``: per frame a [n_f,H,W] tensor or a BitmapMasks-like object
+        (``.pad(shape, pad_val).to_tensor(dtype, device)``).  Index bookkeeping only."""
+        labels_out, masks_out = [], []
+        for gt_labels, gt_masks, ids, metas in zip(gt_labels_list, gt_masks_list, gt_instance_ids, img_metas):
+            dev = gt_labels.device
+            frames = []
+            for f, meta in enumerate(metas):
+                m = gt_masks[f]
+                if hasattr(m, 'pad'):
+                    m = m.pad(meta['pad_shape'][:2], pad_val=0).to_tensor(dtype=torch.bool, device=dev)
+                else:
+                    ph, pw = meta['pad_shape'][:2]
+                    m = torch.nn.functional.pad(m.to(dev).bool(), (0, pw - m.shape[-1], 0, ph - m.shape[-2]))
+                frames.append(m)
+            labels, things = [], []
+            for inst in torch.unique(ids[:, 1]):
+                pos = torch.nonzero(ids[:, 1] == inst, as_tuple=True)[0]
+                lab = gt_labels[:, 1][pos]
+                assert bool((lab == lab[0]).all())
+                labels.append(lab[0])
+                in_frames = ids[:, 0][pos].to(torch.int32).tolist()
+                stack = []
+                for f, meta in enumerate(metas):
+                    if f not in in_frames:
+                        stack.append(torch.zeros(tuple(meta['pad_shape'][:2]), dtype=torch.bool, device=dev))
+                    else:
+                        frame_ids = ids[ids[:, 0] == f, 1]
+                        stack.append(frames[f][int(torch.nonzero(frame_ids == inst, as_tuple=True)[0].item())])
+                things.append(torch.stack(stack))
+            labels_out.append(torch.stack(labels).long())
+            masks_out.append(torch.stack(things).long())
+        return labels_out, masks_out
+
+    def forward_train(self, feats, img_metas, gt_bboxes, gt_labels, gt_masks, gt_semantic_seg=None, gt_instance_ids=None,
+                      gt_bboxes_ignore=None):
+        """mask2former_video_head.py:464-522 (``loss_sem_seg=None``, the shipped configs): forward -> preprocess_gt ->
+        loss.  Returns the reference's loss dict; ``.backward()`` on its sum fills the gradients of the decoder head."""
+        assert gt_bboxes_ignore is None
+        if not self.video:
+            raise NotImplementedError('forward_train of the image head: preprocess_panoptic_gt (things + stuff from the '
+                                      'semantic map) is not built; use forward_train_outputs + loss with prepared targets')
+        num_frames = len(img_metas[0])
+        all_cls_scores, all_mask_preds = self.forward_train_outputs(feats, num_frames)
+        labels, masks = self.preprocess_gt(gt_labels, gt_masks, gt_semantic_seg, gt_instance_ids, img_metas)
+        return self.loss(all_cls_scores, all_mask_preds, labels, masks, img_metas)
 
     def loss_single(self, cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas=None, **point_sets):
         """mask2former_video_head.py:196-293 (mask_preds [B,T,Q,h,w]) / mask2former_head.py:233-318 ([B,Q,h,w]):
@@ -700,9 +827,10 @@ class _Mask2FormerHeadBase(_Prepared):
             mask_preds = mask_preds[:, None]
             gt_masks_list = [g[:, None] for g in gt_masks_list]
         tc = dict(self.train_cfg or {})
-        return losses.loss_single(cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas, num_classes=self.num_classes,
-                                  num_points=tc.get('num_points', 12544), oversample_ratio=tc.get('oversample_ratio', 3.0),
-                                  importance_sample_ratio=tc.get('importance_sample_ratio', 0.75), **point_sets)
+        kw = dict(num_points=tc.get('num_points', 12544), oversample_ratio=tc.get('oversample_ratio', 3.0),
+                  importance_sample_ratio=tc.get('importance_sample_ratio', 0.75))
+        kw.update(point_sets)
+        return losses.loss_single(cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas, num_classes=self.num_classes, **kw)
 
     def loss(self, all_cls_scores, all_mask_preds, gt_labels_list, gt_masks_list, img_metas=None):
         """mask2former_video_head.py:524-634, the default (loss_split_th_st=False) branch: loss_single per decoder layer,
@@ -1041,7 +1169,22 @@ class _DetectorBase(nn.Module):
         return self.backbone(img)
 
     def forward_train(self, *a, **k):
-        raise NotImplementedError('training is out of scope of the B200 inference backend')
+        raise NotImplementedError('forward_train is built for the video (VPS) detector only: Mask2FormerVideoCustom')
+
+    def _parse_losses(self, losses):
+        """mmdet BaseDetector._parse_losses (single process: no all_reduce): -> (total loss, log_vars)."""
+        log_vars = {}
+        for name, value in losses.items():
+            log_vars[name] = value.mean() if torch.is_tensor(value) else sum(v.mean() for v in value)
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        return loss, {k: float(v) for k, v in log_vars.items()}
+
+    def train_step(self, data, optimizer=None):
+        """mmdet BaseDetector.train_step: the runner's entry point (``tools/train.py`` -> ``EpochBasedRunner``)."""
+        losses = self(**data)
+        loss, log_vars = self._parse_losses(losses)
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
 
     def aug_test(self, imgs, img_metas, **kwargs):
         raise NotImplementedError  # as the reference: mask2former.py:193-194
@@ -1096,6 +1239,21 @@ class Mask2FormerVideoCustom(_DetectorBase):
     def __init__(self, *args, dataset='kitti-step', **kwargs):
         super().__init__(*args, **kwargs)
         self.dataset = dataset
+
+    def forward_train(self, img, img_metas, gt_bboxes=None, gt_labels=None, gt_masks=None, gt_semantic_seg=None,
+                      gt_bboxes_ignore=None, *, ref_img=None, ref_img_metas=None, ref_gt_bboxes=None, ref_gt_labels=None,
+                      ref_gt_bboxes_ignore=None, ref_gt_masks=None, ref_gt_semantic_seg=None, ref_gt_instance_ids=None,
+                      **kwargs):
+        """models/mask2former_vps/mask2former.py:85-123.  Backbone and pixel decoder are frozen feature extractors in
+        this build (no_grad): the loss dict trains the transformer decoder head."""
+        bs, num_frame, three, h, w = ref_img.size()
+        for metas in ref_img_metas:
+            for m in metas:
+                m['batch_input_shape'] = (h, w)
+        with torch.no_grad():
+            video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
+        return self.panoptic_head.forward_train(video_x, ref_img_metas, ref_gt_bboxes, ref_gt_labels, ref_gt_masks,
+                                                ref_gt_semantic_seg, ref_gt_instance_ids, gt_bboxes_ignore=None)
 
     def forward_test(self, imgs, img_metas, **kwargs):
         """mask2former.py:225-240."""
