@@ -522,6 +522,24 @@ int pvsg_attention_train_backward(const float* q, const float* k, const float* v
                                   float* dv, int B, int H, int Lq, int Lk, int D, int64_t q_bs, int64_t q_rs, int64_t k_bs,
                                   int64_t k_rs, int64_t v_bs, int64_t v_rs, int64_t o_bs, int64_t o_rs, float scale, void* stream);
 
+/* ---- third training slice: backward of the pixel decoder (mmdet MSDeformAttnPixelDecoder, cfg :27-59).  Convolutions
+ * go backward through the forward engine: dX of a 3x3 conv = pvsg_conv2d_nhwc of dY with the flipped, transposed filter;
+ * dW = one pvsg_linear per filter tap on shifted copies of the input. ---- */
+
+/* nn.GroupNorm backward on token-major x [B,HW,C] (mmcv ConvModule norm, optionally followed by ReLU: relu != 0 masks dy
+ * where the forward output was <= 0): dx, dgamma / dbeta [C] (zeroed here); stats: scratch [B*G*4] floats. */
+int pvsg_groupnorm_nhwc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx, float* dgamma,
+                                 float* dbeta, float* stats, int B, int64_t HW, int C, int G, float eps, int relu, void* stream);
+/* adjoint of pvsg_bilinear_resize_nhwc (F.interpolate bilinear, align_corners=False, the FPN top-down step
+ * msdeformattn_pixel_decoder.py L0): dsrc [B,IH,IW,C] (zeroed here) += scatter of dout [B,OH,OW,C]. */
+int pvsg_bilinear_resize_nhwc_backward(const float* dout, float* dsrc, int B, int IH, int IW, int OH, int OW, int C, void* stream);
+/* proj [B,Nq,H*L*P*3] (see pvsg_msda_fused_forward) -> sampling locations [B,Nq,H,L,P,2] and attention weights [B,Nq,H,L,P],
+ * the explicit tensors pvsg_msda_backward wants; _backward maps their gradients back to dproj. */
+int pvsg_msda_proj_expand(const float* proj, const float* ref, const int64_t* spatial_shapes, float* loc, float* aw, int B,
+                          int64_t Nq, int H, int L, int P, void* stream);
+int pvsg_msda_proj_backward(const float* aw, const float* dloc, const float* daw, const int64_t* spatial_shapes, float* dproj,
+                            int B, int64_t Nq, int H, int L, int P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

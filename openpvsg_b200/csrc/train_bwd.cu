@@ -264,6 +264,164 @@ __global__ void __launch_bounds__(128) attn_train_dkv_kernel(AttnT a, const floa
     dv[b * dvb + j * dvr + h * AD + lane] = gv;
 }
 
+
+// ------------------------------------------------------------------------------------------ GroupNorm backward (NHWC)
+// x, dy [B, HW, C], G groups of cpg = C / G channels.  Kernel A: one CTA per (b, g) recomputes mean / rstd, then the two
+// group sums of the backward formula and this group's share of dgamma / dbeta (atomics over b).  Kernel B: dx.
+// relu != 0: the forward applied ReLU after the affine map; dy is masked where y = xhat * gamma + beta <= 0.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += sh[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ dy,
+                                                           float* __restrict__ stats, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int64_t HW, int C, int G, float eps, int relu) {
+    __shared__ float sh[8];
+    __shared__ float chan[2][32];       // cpg <= 32
+    const int b = blockIdx.x / G, g = blockIdx.x % G, cpg = C / G;
+    const int64_t n = HW * cpg;
+    const float* xb = x + (int64_t)b * HW * C + g * cpg;
+    const float* db = dy + (int64_t)b * HW * C + g * cpg;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += xb[(i / cpg) * C + (i % cpg)];
+    const float mean = block_sum(s, sh) / (float)n;
+    float v = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float d = xb[(i / cpg) * C + (i % cpg)] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(block_sum(v, sh) / (float)n + eps);
+    if (threadIdx.x < 64) chan[threadIdx.x >> 5][threadIdx.x & 31] = 0.f;
+    __syncthreads();
+    float sg = 0.f, sgx = 0.f, pg = 0.f, pb = 0.f;
+    // when cpg divides the block size a thread only ever visits channel threadIdx.x % cpg: register partials, one
+    // shared-memory atomic per thread at the end
+    const bool fixed = blockDim.x % cpg == 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = (int)(i % cpg);
+        const int64_t off = (i / cpg) * C + c;
+        const float xh = (xb[off] - mean) * rstd;
+        const float ga = gamma[g * cpg + c];
+        float d = db[off];
+        if (relu && fmaf(xh, ga, beta[g * cpg + c]) <= 0.f) d = 0.f;
+        const float gi = d * ga;
+        sg += gi;
+        sgx = fmaf(gi, xh, sgx);
+        if (fixed) {
+            pg = fmaf(d, xh, pg);
+            pb += d;
+        } else {
+            atomicAdd(&chan[0][c], d * xh);
+            atomicAdd(&chan[1][c], d);
+        }
+    }
+    if (fixed) {
+        atomicAdd(&chan[0][threadIdx.x % cpg], pg);
+        atomicAdd(&chan[1][threadIdx.x % cpg], pb);
+    }
+    sg = block_sum(sg, sh);
+    sgx = block_sum(sgx, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float* st = stats + (int64_t)blockIdx.x * 4;
+        st[0] = mean; st[1] = rstd; st[2] = sg / (float)n; st[3] = sgx / (float)n;
+    }
+    if (threadIdx.x < cpg) {
+        atomicAdd(dgamma + g * cpg + threadIdx.x, chan[0][threadIdx.x]);
+        atomicAdd(dbeta + g * cpg + threadIdx.x, chan[1][threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ dy,
+                                                        const float* __restrict__ stats, float* __restrict__ dx, int64_t HW,
+                                                        int C, int G, int relu, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const int64_t b = i / (HW * C);
+    const int cpg = C / G;
+    const float* st = stats + (b * G + c / cpg) * 4;
+    const float xh = (x[i] - st[0]) * st[1];
+    float d = dy[i];
+    if (relu && fmaf(xh, gamma[c], beta[c]) <= 0.f) d = 0.f;
+    dx[i] = st[1] * (d * gamma[c] - st[2] - xh * st[3]);
+}
+
+// ------------------------------------------------------------------------------------------ bilinear resize backward
+// adjoint of bilinear_nhwc (align_corners=False): every output pixel scatters its gradient to its 4 source taps
+__global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int B, int IH,
+                                                         int IW, int OH, int OW, int C, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const int ox = (int)((i / C) % OW), oy = (int)((i / ((int64_t)C * OW)) % OH);
+    const int64_t b = i / ((int64_t)C * OW * OH);
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    bilinear_coord(oy, (float)IH / (float)OH, IH, y0, y1, wy0, wy1);
+    bilinear_coord(ox, (float)IW / (float)OW, IW, x0, x1, wx0, wx1);
+    const float g = dout[i];
+    float* base = dsrc + b * (int64_t)IH * IW * C + c;
+    atomicAdd(base + ((int64_t)y0 * IW + x0) * C, g * wy0 * wx0);
+    atomicAdd(base + ((int64_t)y0 * IW + x1) * C, g * wy0 * wx1);
+    atomicAdd(base + ((int64_t)y1 * IW + x0) * C, g * wy1 * wx0);
+    atomicAdd(base + ((int64_t)y1 * IW + x1) * C, g * wy1 * wx1);
+}
+
+// ------------------------------------------------------------------------------------------ MSDeformAttn projections
+// proj [B*Nq, H*L*P*3] = offsets (H, L, P, 2) | logits (H, L, P)  <->  sampling locations [.., H, L, P, 2] and
+// attention weights [.., H, L, P] (softmax over L*P), as MultiScaleDeformableAttention.forward computes them.
+struct LevelWH { float w[8], h[8]; };
+
+__global__ void __launch_bounds__(256) msda_expand_kernel(const float* __restrict__ proj, const float* __restrict__ ref,
+                                                          float* __restrict__ loc, float* __restrict__ aw, int64_t rows, int64_t Nq,
+                                                          int H, int L, int P, LevelWH lv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * H) return;
+    const int h = (int)(i % H);
+    const int64_t r = i / H;
+    const int LP = L * P;
+    const float* off = proj + r * (int64_t)H * LP * 3 + (int64_t)h * LP * 2;
+    const float* lg = proj + r * (int64_t)H * LP * 3 + (int64_t)H * LP * 2 + (int64_t)h * LP;
+    const float rx = ref[(r % Nq) * 2], ry = ref[(r % Nq) * 2 + 1];
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+    for (int k = 0; k < LP; ++k) sum += expf(lg[k] - mx);
+    for (int k = 0; k < LP; ++k) {
+        const int l = k / P;
+        loc[(i * LP + k) * 2] = rx + off[2 * k] / lv.w[l];
+        loc[(i * LP + k) * 2 + 1] = ry + off[2 * k + 1] / lv.h[l];
+        aw[i * LP + k] = expf(lg[k] - mx) / sum;
+    }
+}
+
+__global__ void __launch_bounds__(256) msda_proj_bwd_kernel(const float* __restrict__ aw, const float* __restrict__ dloc,
+                                                            const float* __restrict__ daw, float* __restrict__ dproj,
+                                                            int64_t rows, int H, int L, int P, LevelWH lv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * H) return;
+    const int h = (int)(i % H);
+    const int64_t r = i / H;
+    const int LP = L * P;
+    float* doff = dproj + r * (int64_t)H * LP * 3 + (int64_t)h * LP * 2;
+    float* dlg = dproj + r * (int64_t)H * LP * 3 + (int64_t)H * LP * 2 + (int64_t)h * LP;
+    float dot = 0.f;
+    for (int k = 0; k < LP; ++k) dot = fmaf(aw[i * LP + k], daw[i * LP + k], dot);
+    for (int k = 0; k < LP; ++k) {
+        const int l = k / P;
+        doff[2 * k] = dloc[(i * LP + k) * 2] / lv.w[l];
+        doff[2 * k + 1] = dloc[(i * LP + k) * 2 + 1] / lv.h[l];
+        dlg[k] = aw[i * LP + k] * (daw[i * LP + k] - dot);
+    }
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 inline bool attn_args_ok(const AttnT& a) {
@@ -336,5 +494,57 @@ extern "C" int pvsg_attention_train_backward(const float* q, const float* k, con
                                                                    (int64_t)Lq * E, E);
     attn_train_dkv_kernel<<<(unsigned)((wk + 3) / 4), 128, 0, st>>>(a, dout, o_bs, o_rs, lse, delta, dk, (int64_t)Lk * E, E, dv,
                                                                     (int64_t)Lk * E, E);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_groupnorm_nhwc_backward(const float* x, const float* gamma, const float* beta, const float* dy, float* dx,
+                                            float* dgamma, float* dbeta, float* stats, int B, int64_t HW, int C, int G, float eps,
+                                            int relu, void* stream) {
+    PVSG_CHECK_ARG(x && gamma && beta && dy && dx && dgamma && dbeta && stats && B > 0 && HW > 0 && C > 0 && G > 0 && C % G == 0);
+    if (C / G > 32) return PVSG_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st) != cudaSuccess || cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st) != cudaSuccess)
+        return PVSG_ERR_LAUNCH;
+    gn_bwd_stats_kernel<<<(unsigned)(B * G), 256, 0, st>>>(x, gamma, beta, dy, stats, dgamma, dbeta, HW, C, G, eps, relu);
+    const int64_t total = (int64_t)B * HW * C;
+    gn_bwd_dx_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, gamma, beta, dy, stats, dx, HW, C, G, relu, total);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_bilinear_resize_nhwc_backward(const float* dout, float* dsrc, int B, int IH, int IW, int OH, int OW, int C,
+                                                  void* stream) {
+    PVSG_CHECK_ARG(dout && dsrc && B > 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && C > 0);
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(dsrc, 0, sizeof(float) * (size_t)B * IH * IW * C, st) != cudaSuccess) return PVSG_ERR_LAUNCH;
+    const int64_t total = (int64_t)B * OH * OW * C;
+    resize_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dout, dsrc, B, IH, IW, OH, OW, C, total);
+    return pvsg_launch_status();
+}
+
+static bool level_wh(const int64_t* spatial_shapes, int L, LevelWH& lv) {
+    if (!spatial_shapes || L < 1 || L > 8) return false;
+    for (int l = 0; l < L; ++l) {
+        lv.h[l] = (float)spatial_shapes[2 * l];
+        lv.w[l] = (float)spatial_shapes[2 * l + 1];
+        if (lv.h[l] <= 0.f || lv.w[l] <= 0.f) return false;
+    }
+    return true;
+}
+
+extern "C" int pvsg_msda_proj_expand(const float* proj, const float* ref, const int64_t* spatial_shapes, float* loc, float* aw,
+                                     int B, int64_t Nq, int H, int L, int P, void* stream) {
+    LevelWH lv;
+    PVSG_CHECK_ARG(proj && ref && loc && aw && B > 0 && Nq > 0 && H > 0 && P > 0 && level_wh(spatial_shapes, L, lv));
+    const int64_t n = (int64_t)B * Nq * H;
+    msda_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(proj, ref, loc, aw, (int64_t)B * Nq, Nq, H, L, P, lv);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_msda_proj_backward(const float* aw, const float* dloc, const float* daw, const int64_t* spatial_shapes,
+                                       float* dproj, int B, int64_t Nq, int H, int L, int P, void* stream) {
+    LevelWH lv;
+    PVSG_CHECK_ARG(aw && dloc && daw && dproj && B > 0 && Nq > 0 && H > 0 && P > 0 && level_wh(spatial_shapes, L, lv));
+    const int64_t n = (int64_t)B * Nq * H;
+    msda_proj_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(aw, dloc, daw, dproj, (int64_t)B * Nq, H, L, P, lv);
     return pvsg_launch_status();
 }

@@ -77,6 +77,10 @@ SIGNATURES = {
     'pvsg_lap_assign': (I, [P, I, I, D, P, P, P]),
     'pvsg_layernorm_backward': (I, [P, P, P, P, P, P, L, I, F, P]),
     'pvsg_relu_backward': (I, [P, P, P, L, P]),
+    'pvsg_groupnorm_nhwc_backward': (I, [P, P, P, P, P, P, P, P, I, L, I, I, F, I, P]),
+    'pvsg_bilinear_resize_nhwc_backward': (I, [P, P, I, I, I, I, I, I, P]),
+    'pvsg_msda_proj_expand': (I, [P, P, P, P, P, I, L, I, I, I, P]),
+    'pvsg_msda_proj_backward': (I, [P, P, P, P, P, I, L, I, I, I, P]),
     'pvsg_colsum': (I, [P, P, L, I, L, P]),
     'pvsg_attention_train_forward': (I, [P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_attention_train_backward': (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),

@@ -250,6 +250,16 @@ class MultiScaleDeformableAttention(_Prepared):
                                       out_mode='split')   # planes for the output projection
         return ops.linear(samp, self.output_proj.weight, self.output_proj.bias, residual=x)
 
+    def forward_tokens_train(self, x, pos, ref, spatial_shapes):
+        """``forward_tokens`` on the autograd tape (train_ops)."""
+        from . import train_ops as T
+        w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+        b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+        proj = T.linear(x, w, b, add_input=pos)
+        value = T.linear(x, self.value_proj.weight, self.value_proj.bias)
+        samp = T.msda_fused(value, proj, ref, spatial_shapes, self.num_heads, self.num_points)
+        return T.linear(samp, self.output_proj.weight, self.output_proj.bias, residual=x)
+
     @torch.no_grad()
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
@@ -344,6 +354,18 @@ class BaseTransformerLayer(nn.Module):
         return ops.layernorm(x, n1.weight, n1.bias, n1.eps, out_split=True) + (None,)
 
 
+    def _forward_tokens_train(self, x, pos, ref, spatial_shapes):
+        from . import train_ops as T
+        n0, n1, ffn = self.norms[0], self.norms[1], self.ffns[0]
+        x = T.layernorm(self.attentions[0].forward_tokens_train(x, pos, ref, spatial_shapes), n0)
+        h = T.linear(x, ffn.layers[0][0].weight, ffn.layers[0][0].bias, act=ops.ACT_RELU)
+        x = T.linear(h, ffn.layers[1].weight, ffn.layers[1].bias, residual=x if ffn.add_identity else None)
+        return T.layernorm(x, n1)
+
+
+BaseTransformerLayer.forward_tokens_train = BaseTransformerLayer._forward_tokens_train
+
+
 @TRANSFORMER_LAYER_SEQUENCE.register_module()
 class DetrTransformerEncoder(nn.Module):
     def __init__(self, transformerlayers=None, num_layers=6, post_norm_cfg=None, init_cfg=None, **kwargs):
@@ -373,6 +395,16 @@ class _ConvModule(nn.Module):
             planes = ops.recall_split(x)   # e.g. backbone stage outputs already carry operand planes
         y = ops.conv2d_nhwc(planes if planes is not None else x, self._w, self.conv.bias, pad=self.pad)
         return y
+
+    def forward_tokens_train(self, x):
+        """conv -> GN (-> ReLU) on the autograd tape; x [B,H,W,Cin] token-major."""
+        from . import train_ops as T
+        if self.conv.kernel_size == (1, 1):
+            y = T.linear(x, self.conv.weight.view(self.conv.out_channels, -1), self.conv.bias)
+        else:
+            assert self.conv.kernel_size == (3, 3) and self.conv.bias is None
+            y = T.conv3x3(x, self.conv.weight)
+        return T.groupnorm(y, self.gn, relu=self.act)
 
     def norm_tokens(self, y, out_mode='f32'):
         return ops.groupnorm_nhwc(y, self.gn.weight, self.gn.bias, self.gn.num_groups, self.gn.eps,
@@ -440,6 +472,36 @@ class MSDeformAttnPixelDecoder(_Prepared):
             if not (pos.is_cuda and torch.cuda.is_current_stream_capturing()):
                 self._shape_cache[key] = hit   # tensors created during graph capture belong to the graph
         return hit
+
+    def forward_train(self, feats):
+        """``forward`` on the autograd tape: same outputs (token-major views, logical NCHW), differentiable w.r.t. every
+        parameter of the pixel decoder (the backbone maps ``feats`` are constants)."""
+        from . import train_ops as T
+        B = feats[0].shape[0]
+        toks, shapes = [], []
+        for i in range(self.num_encoder_levels):
+            y = self.input_convs[i].forward_tokens_train(_tokens(feats[self.num_input_levels - i - 1]))
+            shapes.append((y.shape[1], y.shape[2]))
+            toks.append(y.view(B, -1, y.shape[-1]))
+        x = torch.cat(toks, 1)
+        ref = self._shape_consts(shapes, x.device)[1]
+        with torch.no_grad():
+            sine = [self.postional_encoding.tokens(h, w, x.device) for h, w in shapes]
+        pos = torch.cat([T.add_rowvec(pe, self.level_encoding.weight[i]) for i, pe in enumerate(sine)], 0)
+        posb = pos[None].expand(B, -1, -1).contiguous() if B > 1 else pos[None]
+        for layer in self.encoder.layers:
+            x = layer.forward_tokens_train(x, posb, ref, shapes)
+        outs, start = [], 0
+        for (h, w) in shapes:
+            outs.append(x[:, start:start + h * w].reshape(B, h, w, -1))
+            start += h * w
+        for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
+            j = self.num_input_levels - self.num_encoder_levels - 1 - i
+            cur = T.resize_add(self.lateral_convs[j].forward_tokens_train(_tokens(feats[i])), outs[-1])
+            outs.append(self.output_convs[j].forward_tokens_train(cur))
+        wmf = self.mask_feature.weight.view(self.mask_feature.out_channels, -1)
+        mf = T.linear(outs[-1], wmf, self.mask_feature.bias)
+        return _as_nchw(mf), [_as_nchw(o) for o in outs[:self.num_outs]]
 
     @torch.no_grad()
     def forward(self, feats):
@@ -703,6 +765,7 @@ class _Mask2FormerHeadBase(_Prepared):
         # debug / parity hook: when set to a list, ``_run`` appends the raw sign masks (uint8 [B,Q,hw], non-zero =
         # blocked) it computes for decoder layers 0..L-1, so a test can resolve near-threshold ties the same way
         self._capture_masks = None
+        self.train_pixel_decoder = True     # forward_train: False freezes the pixel decoder (it then runs the inference kernels)
 
     def init_weights(self):
         pass
@@ -719,21 +782,25 @@ class _Mask2FormerHeadBase(_Prepared):
     def forward_train_outputs(self, feats, num_frames=1):
         """The training-mode ``forward`` (mask2former_video_head.py:361-462 / mask2former_head.py:397-479): ->
         (all_cls_scores [L+1] x [B,Q,NC+1], all_mask_preds [L+1] x [B,T,Q,h,w] (video) / [B,Q,h,w] (image)), differentiable
-        w.r.t. every parameter of the transformer decoder, the prediction heads, the query / level embeddings.  The pixel
-        decoder and the backbone run under no_grad (their GEMM / conv backward is not built: DESIGN.md section 7)."""
+        w.r.t. every parameter of the head: pixel decoder (``train_pixel_decoder``, default on), transformer decoder,
+        prediction heads, query / level embeddings.  The backbone maps ``feats`` are constants."""
         from . import train_ops as T
+        if self.train_pixel_decoder:
+            mask_features, memories = self.pixel_decoder.forward_train(feats)
+        else:
+            with torch.no_grad():
+                mask_features, memories = self.pixel_decoder(feats)
+        BT = mask_features.shape[0]
+        Tn = num_frames
+        B = BT // Tn
+        assert B * Tn == BT
+        mf = _tokens(mask_features)
+        _, h4, w4, C = mf.shape
+        mf_flat = mf.view(B, Tn * h4 * w4, C)
+        lvl_shapes = [tuple(m.shape[-2:]) for m in memories]
+        toks = [_tokens(m) for m in memories]
         with torch.no_grad():
-            mask_features, memories = self.pixel_decoder(feats)
-            BT = mask_features.shape[0]
-            Tn = num_frames
-            B = BT // Tn
-            assert B * Tn == BT
-            mf = _tokens(mask_features)
-            _, h4, w4, C = mf.shape
-            mf_flat = mf.view(B, Tn * h4 * w4, C)
-            lvl_shapes = [tuple(m.shape[-2:]) for m in memories]
-            pooled = [ops.bilinear_resize_nhwc(mf, s).view(B, -1, C) for s in lvl_shapes]
-            toks = [_tokens(m) for m in memories]
+            pooled = [ops.bilinear_resize_nhwc(mf.detach(), s).view(B, -1, C) for s in lvl_shapes]
             dec_pe = [self._batched(self._decoder_pe((Tn, h, w), mf.device), B) for h, w in lvl_shapes]
         dec_in = [T.add_rowvec(tok, self.level_embed.weight[i]).view(B, -1, C) for i, tok in enumerate(toks)]
         Q = self.num_queries

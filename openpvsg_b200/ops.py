@@ -652,6 +652,55 @@ def mask_match_cost(cls_logits, gt_labels, pred_points, gt_points, w_cls=2.0, w_
     return cost
 
 
+def groupnorm_nhwc_backward(x, gamma, beta, dy, groups=32, eps=1e-5, relu=False):
+    """nn.GroupNorm (+ ReLU) backward on token-major x [B,...,C] -> (dx, dgamma, dbeta)."""
+    lib = _l.load()
+    x, dy = _f32(x).contiguous(), _f32(dy).contiguous()
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32)
+    db = torch.empty(C, device=x.device, dtype=torch.float32)
+    stats = torch.empty(B * groups * 4, device=x.device, dtype=torch.float32)
+    _l.check(lib.pvsg_groupnorm_nhwc_backward(_ptr(x), _ptr(_f32(gamma).contiguous()), _ptr(_f32(beta).contiguous()), _ptr(dy), _ptr(dx),
+                                              _ptr(dg), _ptr(db), _ptr(stats), B, HW, C, groups, eps, 1 if relu else 0, _stream()),
+             'pvsg_groupnorm_nhwc_backward')
+    return dx, dg, db
+
+
+def bilinear_resize_nhwc_backward(dout, in_hw):
+    """Adjoint of bilinear_resize_nhwc: dout [B,OH,OW,C] -> dsrc [B,IH,IW,C]."""
+    lib = _l.load()
+    dout = _f32(dout).contiguous()
+    B, OH, OW, C = dout.shape
+    dsrc = torch.empty(B, in_hw[0], in_hw[1], C, device=dout.device, dtype=torch.float32)
+    _l.check(lib.pvsg_bilinear_resize_nhwc_backward(_ptr(dout), _ptr(dsrc), B, in_hw[0], in_hw[1], OH, OW, C, _stream()),
+             'pvsg_bilinear_resize_nhwc_backward')
+    return dsrc
+
+
+def msda_proj_expand(proj, ref, spatial_shapes, num_heads=8, num_points=4):
+    """raw projections [B,Nq,H*L*P*3] -> (sampling_locations [B,Nq,H,L,P,2], attention_weights [B,Nq,H,L,P])."""
+    lib = _l.load()
+    ss, ls, L, tot = _levels(spatial_shapes)
+    B, Nq = _f32(proj).shape[:2]
+    loc = torch.empty(B, Nq, num_heads, L, num_points, 2, device=proj.device, dtype=torch.float32)
+    aw = torch.empty(B, Nq, num_heads, L, num_points, device=proj.device, dtype=torch.float32)
+    _l.check(lib.pvsg_msda_proj_expand(_ptr(proj.contiguous()), _ptr(_f32(ref).contiguous()), ss, _ptr(loc), _ptr(aw), B, Nq,
+                                       num_heads, L, num_points, _stream()), 'pvsg_msda_proj_expand')
+    return loc, aw
+
+
+def msda_proj_backward(aw, dloc, daw, spatial_shapes):
+    lib = _l.load()
+    ss, ls, L, tot = _levels(spatial_shapes)
+    B, Nq, H, _, P = aw.shape
+    dproj = torch.empty(B, Nq, H * L * P * 3, device=aw.device, dtype=torch.float32)
+    _l.check(lib.pvsg_msda_proj_backward(_ptr(aw.contiguous()), _ptr(_f32(dloc).contiguous()), _ptr(_f32(daw).contiguous()), ss,
+                                         _ptr(dproj), B, Nq, H, L, P, _stream()), 'pvsg_msda_proj_backward')
+    return dproj
+
+
 def layernorm_backward(x, gamma, dy, eps=1e-5):
     """nn.LayerNorm backward over the last axis -> (dx, dgamma, dbeta)."""
     lib = _l.load()

@@ -154,3 +154,109 @@ class _ExpandBatch(torch.autograd.Function):
 
 def expand_batch(w, B):
     return _ExpandBatch.apply(w, B)
+
+
+# ---------------------------------------------------------------------------------------------- pixel decoder pieces
+class _GroupNorm(torch.autograd.Function):
+    """mmcv ConvModule norm (+ ReLU) on token-major maps [B,H,W,C]."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, relu):
+        x = x.contiguous()
+        ctx.cfg = (groups, eps, relu)
+        ctx.save_for_backward(x, gamma, beta)
+        return ops.groupnorm_nhwc(x, gamma, beta, groups, eps, ops.ACT_RELU if relu else ops.ACT_NONE)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta = ctx.saved_tensors
+        groups, eps, relu = ctx.cfg
+        dx, dg, db = ops.groupnorm_nhwc_backward(x, gamma, beta, dy, groups, eps, relu)
+        return dx, dg, db, None, None, None
+
+
+def groupnorm(x, gn, relu=False):
+    return _GroupNorm.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps, relu)
+
+
+class _Conv3x3(torch.autograd.Function):
+    """3x3, stride 1, pad 1 convolution on token-major maps; weight in the module's layout [Cout,Cin,3,3].
+    Backward through the forward engine: dX = conv(dY, flipped / transposed filter); dW[:, :, r, s] = dY^T X_shift(r, s),
+    one GEMM per tap on a shifted copy of the input (zero padding = zero rows)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        return ops.conv2d_nhwc(x, weight.permute(0, 2, 3, 1).contiguous(), None, pad=1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin, 3, 3, Cout], taps mirrored
+            dx = ops.conv2d_nhwc(dy, wt, None, pad=1)
+        if ctx.needs_input_grad[1]:
+            dyt = _t(dy.view(-1, Cout))                                      # [Cout, tokens]
+            xp = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))              # zero border (data movement)
+            dw = torch.empty_like(weight)
+            for r in range(3):
+                for s in range(3):
+                    xs = xp[:, r:r + H, s:s + W].reshape(-1, Cin)
+                    dw[:, :, r, s] = ops.linear(dyt, _t(xs))                 # [Cout, Cin]
+        return dx, dw
+
+
+def conv3x3(x, weight):
+    return _Conv3x3.apply(x, weight)
+
+
+class _ResizeAdd(torch.autograd.Function):
+    """base + bilinear_resize(src -> base's size) (the FPN top-down step; F.interpolate bilinear, align_corners=False)."""
+
+    @staticmethod
+    def forward(ctx, base, src):
+        ctx.in_hw = tuple(src.shape[1:3])
+        out = base.contiguous().clone()
+        ops.bilinear_resize_nhwc(src.contiguous(), out.shape[1:3], out=out, accumulate=True)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dsrc = ops.bilinear_resize_nhwc_backward(dy, ctx.in_hw) if ctx.needs_input_grad[1] else None
+        return (dy if ctx.needs_input_grad[0] else None), dsrc
+
+
+def resize_add(base, src):
+    return _ResizeAdd.apply(base, src)
+
+
+class _MSDAFused(torch.autograd.Function):
+    """MultiScaleDeformableAttention core from the raw projections (ops.msda_fused_forward); the backward expands the
+    projections into explicit sampling locations / attention weights, runs pvsg_msda_backward and maps their gradients
+    back (softmax over L*P, division by the level sizes)."""
+
+    @staticmethod
+    def forward(ctx, value, proj, ref, shapes, num_heads, num_points):
+        value, proj = value.contiguous(), proj.contiguous()
+        ctx.cfg = (shapes, num_heads, num_points)
+        ctx.save_for_backward(value, proj, ref)
+        return ops.msda_fused_forward(value, shapes, proj, ref, num_heads, num_points)
+
+    @staticmethod
+    def backward(ctx, dout):
+        value, proj, ref = ctx.saved_tensors
+        shapes, H, P = ctx.cfg
+        B, N, C = value.shape
+        loc, aw = ops.msda_proj_expand(proj, ref, shapes, H, P)
+        gv, gl, ga = ops.msda_backward(value.view(B, N, H, C // H), shapes, loc, aw, dout.contiguous())
+        dproj = ops.msda_proj_backward(aw, gl, ga, shapes)
+        return gv.view(B, N, C), dproj, None, None, None, None
+
+
+def msda_fused(value, proj, ref, shapes, num_heads, num_points):
+    return _MSDAFused.apply(value, proj, ref, tuple(shapes), num_heads, num_points)

@@ -219,6 +219,74 @@ def test_backward_kernels_vs_autograd():
     assert torch.allclose(vv.grad, torch.full_like(vv, 20.0)) and torch.equal(xv.grad, torch.ones_like(xv))
 
 
+def test_pixel_decoder_backward_kernels_vs_autograd():
+    """GroupNorm(+ReLU) / bilinear-resize / 3x3-conv / fused-MSDeformAttn backward against torch autograd on the CPU."""
+    from openpvsg_b200 import train_ops as T
+    from oracle import m2f as om
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(33)
+    # GroupNorm on token-major maps, with and without the ReLU
+    for relu, C in ((False, 256), (True, 256), (True, 128)):
+        x = torch.randn(2, 11, 13, C, generator=g) * 1.5 + 0.3
+        dy = torch.randn(2, 11, 13, C, generator=g)
+        gn = torch.nn.GroupNorm(32, C)
+        gn.weight.data = torch.rand(C, generator=g) + 0.5
+        gn.bias.data = torch.randn(C, generator=g) * 0.3
+        xc = x.clone().requires_grad_(True)
+        yc = gn(xc.permute(0, 3, 1, 2))
+        yc = (torch.relu(yc) if relu else yc).permute(0, 2, 3, 1)
+        yc.backward(dy)
+        gd = torch.nn.GroupNorm(32, C).cuda()
+        gd.load_state_dict(gn.state_dict())
+        xd = x.cuda().requires_grad_(True)
+        yd = T.groupnorm(xd, gd, relu=relu)
+        yd.backward(dy.cuda())
+        _close(yd, yc, 2e-5, 'gn forward')
+        _close(xd.grad, xc.grad, 5e-5, 'gn dx')
+        _close(gd.weight.grad, gn.weight.grad, 5e-5, 'gn dgamma')
+        _close(gd.bias.grad, gn.bias.grad, 5e-5, 'gn dbeta')
+    # base + upsample(src)
+    base, src, dy = torch.randn(2, 12, 20, 8, generator=g), torch.randn(2, 6, 10, 8, generator=g), torch.randn(2, 12, 20, 8, generator=g)
+    bc, sc = base.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    (bc + F.interpolate(sc.permute(0, 3, 1, 2), size=(12, 20), mode='bilinear', align_corners=False).permute(0, 2, 3, 1)).backward(dy)
+    bd, sdv = base.cuda().requires_grad_(True), src.cuda().requires_grad_(True)
+    out = T.resize_add(bd, sdv)
+    out.backward(dy.cuda())
+    _close(sdv.grad, sc.grad, 2e-5, 'resize d src')
+    _close(bd.grad, bc.grad, 1e-6, 'resize d base')
+    # 3x3 convolution
+    x, w, dy = torch.randn(2, 8, 16, 64, generator=g), torch.randn(128, 64, 3, 3, generator=g) * 0.1, torch.randn(2, 8, 16, 128, generator=g)
+    xc, wc = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yc = F.conv2d(xc.permute(0, 3, 1, 2), wc, padding=1).permute(0, 2, 3, 1)
+    yc.backward(dy)
+    xd, wd = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    yd = T.conv3x3(xd, wd)
+    yd.backward(dy.cuda())
+    _close(yd, yc, 2e-5, 'conv3x3 forward')
+    _close(xd.grad, xc.grad, 5e-5, 'conv3x3 dx')
+    _close(wd.grad, wc.grad, 5e-5, 'conv3x3 dw')
+    # fused MSDeformAttn from raw projections
+    shapes = [(3, 5), (6, 10), (12, 20)]
+    n = sum(h * w for h, w in shapes)
+    value, proj = torch.randn(2, n, 256, generator=g), torch.randn(2, n, 288, generator=g) * 2
+    ref = torch.cat([torch.stack(((torch.arange(w).float().repeat(h) + 0.5) / w, (torch.arange(h).float().repeat_interleave(w) + 0.5) / h), -1)
+                     for h, w in shapes])
+    gout = torch.randn(2, n, 256, generator=g)
+    vc, pc = value.clone().requires_grad_(True), proj.clone().requires_grad_(True)
+    off = pc[..., :192].view(2, n, 8, 3, 4, 2)
+    norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
+    loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
+    aw = pc[..., 192:].view(2, n, 8, 12).softmax(-1).view(2, n, 8, 3, 4)
+    want = om.msda_core(vc.view(2, n, 8, 32), shapes, loc, aw)
+    want.backward(gout)
+    vd, pd = value.cuda().requires_grad_(True), proj.cuda().requires_grad_(True)
+    got = T.msda_fused(vd, pd, ref.cuda(), shapes, 8, 4)
+    got.backward(gout.cuda())
+    _close(got, want, 1e-4, 'msda fused forward')
+    _close(vd.grad, vc.grad, 2e-4, 'msda fused d value')
+    _close(pd.grad, pc.grad, 5e-4, 'msda fused d proj')
+
+
 def _train_setup(H=96, W=160, T=2, seed=3):
     import openpvsg_b200 as pv
     from openpvsg_b200 import configs, synthetic as syn
@@ -244,7 +312,7 @@ def test_decoder_head_training_step_vs_oracle():
     """forward_train_outputs -> loss_single per decoder layer -> backward, against torch autograd through the CPU oracle
     (oracle/m2f.py::head_forward + oracle/losses.py::loss_single) on the same backbone features, with the same random
     point sets and the product's attention-mask decisions adopted at ties: loss terms and the gradient of EVERY
-    parameter of the decoder head."""
+    parameter of the head (pixel decoder included)."""
     from oracle import losses as ol
     from oracle import m2f as om
     det, sd, frames, metas = _train_setup()
@@ -276,7 +344,7 @@ def test_decoder_head_training_step_vs_oracle():
     finally:
         captured, head._capture_masks = head._capture_masks, None
         T.linear = real_linear
-    assert len(tie_units) == 9 + 2 and all(float(v.float().mean()) <= 0.05 for v in tie_units.values()), \
+    assert len(tie_units) == 9 + 2 + 6 and all(float(v.float().mean()) <= 0.05 for v in tie_units.values()), \
         {k: int(v.sum()) for k, v in tie_units.items()}
     assert len(cls_list) == 10 and mask_list[0].shape[:3] == (1, Tn, 100) and cls_list[-1].requires_grad
     picks, gt_masks, gt_labels = _planted_gt(mask_list[-1].detach().cpu())
@@ -294,7 +362,7 @@ def test_decoder_head_training_step_vs_oracle():
     total.backward()
     # ---- oracle
     osd = {k: v.clone().float() for k, v in sd.items()}
-    trainable = [k for k in osd if k.startswith('panoptic_head.') and not k.startswith('panoptic_head.pixel_decoder.')]
+    trainable = [k for k in osd if k.startswith('panoptic_head.')]
     for k in trainable:
         osd[k].requires_grad_(True)
     ofeats = [f.detach().cpu().contiguous() for f in feats]
@@ -326,8 +394,8 @@ def test_decoder_head_training_step_vs_oracle():
         worst[k] = err / scale
     bad = {k: round(v, 5) for k, v in worst.items() if v > 2e-3}
     assert not bad, bad
-    assert len(worst) > 150                                   # 9 layers x 18 tensors + heads + embeddings
-    assert all(params[k].grad is None for k in params if k.startswith('backbone.') or '.pixel_decoder.' in k)
+    assert len(worst) > 280                                   # decoder 9 x 18, encoder 6 x 16, convs / norms, heads, embeddings
+    assert all(params[k].grad is None for k in params if k.startswith('backbone.'))
     import json
     import os
     os.makedirs('gpurun_out', exist_ok=True)
@@ -357,7 +425,7 @@ def test_forward_train_and_optimizer_steps():
     data = dict(img=frames[:, 0].cuda(), img_metas=[metas[0][0]], return_loss=True, ref_img=frames.cuda(), ref_img_metas=metas,
                 ref_gt_bboxes=None, ref_gt_labels=gt_labels, ref_gt_masks=gt_masks, ref_gt_semantic_seg=None,
                 ref_gt_instance_ids=gt_ids)
-    opt = torch.optim.AdamW([p for n, p in det.named_parameters() if n.startswith('panoptic_head.') and '.pixel_decoder.' not in n],
+    opt = torch.optim.AdamW([p for n, p in det.named_parameters() if n.startswith('panoptic_head.')],
                             lr=1e-4, weight_decay=0.05)
     history = []
     for step in range(6):
