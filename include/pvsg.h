@@ -533,6 +533,9 @@ int pvsg_groupnorm_nhwc_backward(const float* x, const float* gamma, const float
 /* adjoint of pvsg_bilinear_resize_nhwc (F.interpolate bilinear, align_corners=False, the FPN top-down step
  * msdeformattn_pixel_decoder.py L0): dsrc [B,IH,IW,C] (zeroed here) += scatter of dout [B,OH,OW,C]. */
 int pvsg_bilinear_resize_nhwc_backward(const float* dout, float* dsrc, int B, int IH, int IW, int OH, int OW, int C, void* stream);
+/* backward of pvsg_maxpool3x3s2_nhwc (ResNet stem max pooling): dx [B,H,W,C] (zeroed here); the gradient of a window goes to
+ * its first maximum in scan order (ATen max_pool2d_with_indices_backward). */
+int pvsg_maxpool3x3s2_nhwc_backward(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream);
 /* proj [B,Nq,H*L*P*3] (see pvsg_msda_fused_forward) -> sampling locations [B,Nq,H,L,P,2] and attention weights [B,Nq,H,L,P],
  * the explicit tensors pvsg_msda_backward wants; _backward maps their gradients back to dproj. */
 int pvsg_msda_proj_expand(const float* proj, const float* ref, const int64_t* spatial_shapes, float* loc, float* aw, int B,

@@ -374,6 +374,31 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
     atomicAdd(base + ((int64_t)y1 * IW + x1) * C, g * wy1 * wx1);
 }
 
+// ------------------------------------------------------------------------------------------ max pooling backward
+// 3x3 / stride 2 / pad 1: every output routes its gradient to the FIRST maximum of its window in (row, column) scan order
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, int H, int W, int OH, int OW, int C, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const int ox = (int)((i / C) % OW), oy = (int)((i / ((int64_t)C * OW)) % OH);
+    const int64_t b = i / ((int64_t)C * OW * OH);
+    const float* xb = x + b * (int64_t)H * W * C + c;
+    float best = -INFINITY;
+    int64_t arg = -1;
+    for (int r = 0; r < 3; ++r) {
+        const int y = 2 * oy - 1 + r;
+        if (y < 0 || y >= H) continue;
+        for (int s = 0; s < 3; ++s) {
+            const int xx = 2 * ox - 1 + s;
+            if (xx < 0 || xx >= W) continue;
+            const float v = xb[((int64_t)y * W + xx) * C];
+            if (v > best || arg < 0) { best = v; arg = (int64_t)y * W + xx; }
+        }
+    }
+    atomicAdd(dx + b * (int64_t)H * W * C + arg * C + c, dy[i]);
+}
+
 // ------------------------------------------------------------------------------------------ MSDeformAttn projections
 // proj [B*Nq, H*L*P*3] = offsets (H, L, P, 2) | logits (H, L, P)  <->  sampling locations [.., H, L, P, 2] and
 // attention weights [.., H, L, P] (softmax over L*P), as MultiScaleDeformableAttention.forward computes them.
@@ -546,5 +571,15 @@ extern "C" int pvsg_msda_proj_backward(const float* aw, const float* dloc, const
     PVSG_CHECK_ARG(aw && dloc && daw && dproj && B > 0 && Nq > 0 && H > 0 && P > 0 && level_wh(spatial_shapes, L, lv));
     const int64_t n = (int64_t)B * Nq * H;
     msda_proj_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(aw, dloc, daw, dproj, (int64_t)B * Nq, H, L, P, lv);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_maxpool3x3s2_nhwc_backward(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+    PVSG_CHECK_ARG(x && dy && dx && B > 0 && H > 0 && W > 0 && C > 0);
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st) != cudaSuccess) return PVSG_ERR_LAUNCH;
+    const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+    const int64_t total = (int64_t)B * OH * OW * C;
+    maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, dx, H, W, OH, OW, C, total);
     return pvsg_launch_status();
 }

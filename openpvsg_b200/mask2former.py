@@ -136,6 +136,35 @@ class ResNet(_Prepared):
                 p['blocks'].append(d)
         self._prep = p
 
+    def forward_train(self, x):
+        """``forward`` on the autograd tape (train_ops): eval-mode BatchNorm folded into every convolution as in
+        inference (norm_eval=True, BN parameters frozen: base cfg :7-16), so the trainable tensors are the convolution
+        weights; fp32 maps instead of operand planes."""
+        from . import train_ops as T
+
+        def fold(conv, bn):
+            with torch.no_grad():
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                shift = (bn.bias - bn.running_mean * scale).contiguous()
+            return (conv.weight * scale[:, None, None, None]).permute(0, 2, 3, 1), shift    # weight prep, on the tape
+
+        x = T.conv(_tokens(x), *fold(self.conv1, self.bn1), stride=2, pad=3, act=ops.ACT_RELU)
+        x = T.maxpool3x3s2(x)
+        outs = []
+        for i in range(4):
+            for blk in getattr(self, f'layer{i + 1}'):
+                o = T.conv(x, *fold(blk.conv1, blk.bn1), act=ops.ACT_RELU)
+                o = T.conv(o, *fold(blk.conv2, blk.bn2), stride=blk.stride, pad=1, act=ops.ACT_RELU)
+                if blk.downsample is None:
+                    idt = x
+                else:
+                    sub = x[:, ::blk.stride, ::blk.stride].contiguous() if blk.stride > 1 else x
+                    idt = T.conv(sub, *fold(blk.downsample[0], blk.downsample[1]))
+                x = T.conv(o, *fold(blk.conv3, blk.bn3), residual=idt, act=ops.ACT_RELU)
+            if i in self.out_indices:
+                outs.append(_as_nchw(x))
+        return tuple(outs)
+
     @torch.no_grad()
     def forward(self, x):
         if self._prep is None:
@@ -1306,19 +1335,24 @@ class Mask2FormerVideoCustom(_DetectorBase):
     def __init__(self, *args, dataset='kitti-step', **kwargs):
         super().__init__(*args, **kwargs)
         self.dataset = dataset
+        self.train_backbone = True
 
     def forward_train(self, img, img_metas, gt_bboxes=None, gt_labels=None, gt_masks=None, gt_semantic_seg=None,
                       gt_bboxes_ignore=None, *, ref_img=None, ref_img_metas=None, ref_gt_bboxes=None, ref_gt_labels=None,
                       ref_gt_bboxes_ignore=None, ref_gt_masks=None, ref_gt_semantic_seg=None, ref_gt_instance_ids=None,
                       **kwargs):
-        """models/mask2former_vps/mask2former.py:85-123.  Backbone and pixel decoder are frozen feature extractors in
-        this build (no_grad): the loss dict trains the transformer decoder head."""
+        """models/mask2former_vps/mask2former.py:85-123.  ``self.train_backbone`` (default True) puts the ResNet on the
+        autograd tape too (BatchNorm frozen as the reference config has it); a Swin backbone runs frozen."""
         bs, num_frame, three, h, w = ref_img.size()
         for metas in ref_img_metas:
             for m in metas:
                 m['batch_input_shape'] = (h, w)
-        with torch.no_grad():
-            video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
+        frames = ref_img.reshape(bs * num_frame, three, h, w)
+        if self.train_backbone and hasattr(self.backbone, 'forward_train'):
+            video_x = self.backbone.forward_train(frames)
+        else:
+            with torch.no_grad():
+                video_x = self.extract_feat(frames)
         return self.panoptic_head.forward_train(video_x, ref_img_metas, ref_gt_bboxes, ref_gt_labels, ref_gt_masks,
                                                 ref_gt_semantic_seg, ref_gt_instance_ids, gt_bboxes_ignore=None)
 

@@ -381,6 +381,15 @@ def maxpool3x3s2_nhwc(x):
     return out
 
 
+def maxpool3x3s2_nhwc_backward(x, dy):
+    lib = _l.load()
+    B, H, W, C = _f32(x).shape
+    dx = torch.empty_like(x)
+    _l.check(lib.pvsg_maxpool3x3s2_nhwc_backward(_ptr(x.contiguous()), _ptr(_f32(dy).contiguous()), _ptr(dx), B, H, W, C, _stream()),
+             'pvsg_maxpool_backward')
+    return dx
+
+
 def nchw_to_nhwc(x):
     lib = _l.load()
     B, C, H, W = _f32(x).shape

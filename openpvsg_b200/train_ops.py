@@ -36,11 +36,9 @@ class _Linear(torch.autograd.Function):
         has_bias, has_add, has_res = ctx.has
         N, K = weight.shape
         dz = dy.contiguous()
-        d_res = dz if has_res and ctx.needs_input_grad[4] else None      # the residual bypasses the activation only
-        if ctx.act == ops.ACT_RELU:                                      # when act is none (the head never mixes them)
-            if has_res:
-                raise ops._l.PvsgError('linear backward: residual with a fused ReLU is not used by the head')
+        if ctx.act == ops.ACT_RELU:                                      # y = relu(z + residual): the mask applies to both
             dz = ops.relu_backward(dz, y)
+        d_res = dz if has_res and ctx.needs_input_grad[4] else None
         dz2 = dz.reshape(-1, N)
         dx = dw = db = None
         if ctx.needs_input_grad[0] or (has_add and ctx.needs_input_grad[3]):
@@ -179,40 +177,83 @@ def groupnorm(x, gn, relu=False):
     return _GroupNorm.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps, relu)
 
 
-class _Conv3x3(torch.autograd.Function):
-    """3x3, stride 1, pad 1 convolution on token-major maps; weight in the module's layout [Cout,Cin,3,3].
-    Backward through the forward engine: dX = conv(dY, flipped / transposed filter); dW[:, :, r, s] = dY^T X_shift(r, s),
-    one GEMM per tap on a shifted copy of the input (zero padding = zero rows)."""
+class _Conv(torch.autograd.Function):
+    """act(conv(x, w) + bias + residual) on token-major maps; x [B,H,W,Cin], w [Cout,R,S,Cin] (the kernel layout), square
+    filters, stride 1 or 2.  Backward through the forward engine:
+      dX = stride-1 convolution of dZ (zero-inserted for stride 2) with the mirrored, transposed filter, pad R-1-pad;
+      dW[:, r, s, :] = dZ^T X_shift(r, s): one GEMM per filter tap on a (strided) shifted copy of the padded input."""
 
     @staticmethod
-    def forward(ctx, x, weight):
-        x = x.contiguous()
-        ctx.save_for_backward(x, weight)
-        return ops.conv2d_nhwc(x, weight.permute(0, 2, 3, 1).contiguous(), None, pad=1)
+    def forward(ctx, x, w, bias, residual, stride, pad, act):
+        x, w = x.contiguous(), w.contiguous()
+        y = ops.conv2d_nhwc(x, w, bias, residual=residual, stride=stride, pad=pad, act=act)
+        ctx.cfg = (stride, pad, act, bias is not None, residual is not None)
+        ctx.save_for_backward(x, w, y if act == ops.ACT_RELU else None)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
-        dy = dy.contiguous()
+        x, w, y = ctx.saved_tensors
+        stride, pad, act, has_bias, has_res = ctx.cfg
         B, H, W, Cin = x.shape
-        Cout = weight.shape[0]
-        dx = dw = None
+        Cout, R, S, _ = w.shape
+        dz = dy.contiguous()
+        if act == ops.ACT_RELU:
+            dz = ops.relu_backward(dz, y)
+        OH, OW = dz.shape[1:3]
+        dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = weight.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin, 3, 3, Cout], taps mirrored
-            dx = ops.conv2d_nhwc(dy, wt, None, pad=1)
+            if stride == 1:
+                z = dz
+            else:                                        # zero insertion (data movement)
+                z = dz.new_zeros(B, H - R + 1 + 2 * pad, W - S + 1 + 2 * pad, Cout)
+                z[:, 0:stride * OH:stride, 0:stride * OW:stride] = dz
+            if R == 1 and S == 1:
+                dx = ops.linear(z.view(-1, Cout), _t(w.view(Cout, Cin))).view(B, H, W, Cin)
+            else:
+                dx = ops.conv2d_nhwc(z, w.flip(1, 2).permute(3, 1, 2, 0).contiguous(), None, pad=R - 1 - pad)
         if ctx.needs_input_grad[1]:
-            dyt = _t(dy.view(-1, Cout))                                      # [Cout, tokens]
-            xp = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))              # zero border (data movement)
-            dw = torch.empty_like(weight)
-            for r in range(3):
-                for s in range(3):
-                    xs = xp[:, r:r + H, s:s + W].reshape(-1, Cin)
-                    dw[:, :, r, s] = ops.linear(dyt, _t(xs))                 # [Cout, Cin]
-        return dx, dw
+            dzt = _t(dz.view(-1, Cout))                  # [Cout, tokens]
+            xp = torch.nn.functional.pad(x, (0, 0, pad, pad, pad, pad)) if pad else x
+            taps = [xp[:, r:r + stride * OH:stride, q:q + stride * OW:stride].reshape(-1, Cin) for r in range(R) for q in range(S)]
+            if Cin < 16:                                 # RGB stem: one GEMM over the gathered patches [tokens, R*S*Cin]
+                dw = ops.linear(dzt, _t(torch.cat(taps, 1))).view(Cout, R, S, Cin)
+            else:
+                dw = torch.empty_like(w)
+                for i, xs in enumerate(taps):
+                    dw[:, i // S, i % S, :] = ops.linear(dzt, _t(xs))
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dz.view(-1, Cout))
+        return dx, dw, db, (dz if has_res and ctx.needs_input_grad[3] else None), None, None, None
+
+
+def conv(x, w, bias=None, residual=None, stride=1, pad=0, act=ops.ACT_NONE):
+    return _Conv.apply(x, w, bias, residual, stride, pad, act)
 
 
 def conv3x3(x, weight):
-    return _Conv3x3.apply(x, weight)
+    """weight in the nn.Conv2d layout [Cout,Cin,3,3] (the permute is on the tape)."""
+    return _Conv.apply(x, weight.permute(0, 2, 3, 1), None, None, 1, 1, ops.ACT_NONE)
+
+
+class _MaxPool(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 max pooling (ResNet stem); the gradient goes to the first maximum of each window in scan
+    order, as ATen's max_pool2d backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.maxpool3x3s2_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool3x3s2_nhwc_backward(x, dy)
+
+
+def maxpool3x3s2(x):
+    return _MaxPool.apply(x)
 
 
 class _ResizeAdd(torch.autograd.Function):

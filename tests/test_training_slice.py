@@ -221,7 +221,7 @@ def test_backward_kernels_vs_autograd():
 
 def test_pixel_decoder_backward_kernels_vs_autograd():
     """GroupNorm(+ReLU) / bilinear-resize / 3x3-conv / fused-MSDeformAttn backward against torch autograd on the CPU."""
-    from openpvsg_b200 import train_ops as T
+    from openpvsg_b200 import ops, train_ops as T
     from oracle import m2f as om
     F = torch.nn.functional
     g = torch.Generator().manual_seed(33)
@@ -265,6 +265,34 @@ def test_pixel_decoder_backward_kernels_vs_autograd():
     _close(yd, yc, 2e-5, 'conv3x3 forward')
     _close(xd.grad, xc.grad, 5e-5, 'conv3x3 dx')
     _close(wd.grad, wc.grad, 5e-5, 'conv3x3 dw')
+    # general convolution: 3x3 stride 2 with bias + ReLU, 1x1 with residual + ReLU, 7x7 stride 2 stem on 3 channels
+    for (Cin, Cout, R, stride, pad, H, W, res) in ((64, 128, 3, 2, 1, 10, 16, False), (64, 128, 3, 2, 1, 9, 15, False),
+                                                   (128, 64, 1, 1, 0, 6, 8, True), (3, 64, 7, 2, 3, 20, 32, False)):
+        x, w = torch.randn(2, H, W, Cin, generator=g), torch.randn(Cout, R, R, Cin, generator=g) * (0.5 / R)
+        bias = torch.randn(Cout, generator=g)
+        OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+        resid, dy = torch.randn(2, OH, OW, Cout, generator=g), torch.randn(2, OH, OW, Cout, generator=g)
+        c = [t.clone().requires_grad_(True) for t in (x, w, bias, resid)]
+        yc = F.conv2d(c[0].permute(0, 3, 1, 2), c[1].permute(0, 3, 1, 2), c[2], stride=stride, padding=pad).permute(0, 2, 3, 1)
+        yc = torch.relu(yc + c[3] if res else yc)
+        yc.backward(dy)
+        d = [t.cuda().requires_grad_(True) for t in (x, w, bias, resid)]
+        yd = T.conv(d[0], d[1], d[2], residual=d[3] if res else None, stride=stride, pad=pad, act=ops.ACT_RELU)
+        yd.backward(dy.cuda())
+        tag = f'conv {R}x{R}/{stride} {Cin}->{Cout}'
+        _close(yd, yc, 2e-5, tag)
+        for a, b, n in zip(d, c, ('dx', 'dw', 'dbias', 'dresidual')):
+            if n == 'dresidual' and not res:
+                continue
+            _close(a.grad, b.grad, 5e-5, f'{tag} {n}')
+    # max pooling with ties (post-ReLU zeros): gradient to the first maximum in scan order
+    x = torch.relu(torch.randn(2, 9, 14, 64, generator=g))
+    dy = torch.randn(2, 5, 7, 64, generator=g)
+    xc = x.clone().requires_grad_(True)
+    F.max_pool2d(xc.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).backward(dy)
+    xd = x.cuda().requires_grad_(True)
+    T.maxpool3x3s2(xd).backward(dy.cuda())
+    _close(xd.grad, xc.grad, 1e-6, 'maxpool backward')
     # fused MSDeformAttn from raw projections
     shapes = [(3, 5), (6, 10), (12, 20)]
     n = sum(h * w for h, w in shapes)
@@ -318,8 +346,6 @@ def test_decoder_head_training_step_vs_oracle():
     det, sd, frames, metas = _train_setup()
     head = det.panoptic_head
     Tn = frames.shape[1]
-    with torch.no_grad():
-        feats = det.extract_feat(frames[0].cuda())
     # ReLU'd layers: remember which hidden units sit on the kink for some row (|pre-activation| < 5e-5, the forward
     # agrees to ~4e-5 there).  The derivative of ReLU is a discrete decision like the attention-mask sign test: two
     # correct fp32 forwards may take different sides, which changes that unit's weight / bias gradient by a whole row's
@@ -337,13 +363,31 @@ def test_decoder_head_training_step_vs_oracle():
             tie_units[n] = tie_units.get(n, False) | (pre.abs() < 5e-5).any(0).cpu()
         return y
 
+    conv_names = ['backbone.conv1.weight']
+    for li, nblk in enumerate((3, 4, 6, 3)):
+        conv_names += [f'backbone.layer{li + 1}.{b}.conv{c}.weight' for b in range(nblk) for c in (1, 2, 3)]
+    real_conv = T.conv
+    conv_calls = []
+
+    def spy_conv(x, w, bias=None, residual=None, stride=1, pad=0, act=ops.ACT_NONE):
+        if act == ops.ACT_RELU:      # the same convolution without the ReLU: output channels with a token on the kink
+            with torch.no_grad():
+                pre = ops.conv2d_nhwc(x.detach().contiguous(), w.detach().contiguous(), bias, residual=None if residual is None else residual.detach(),
+                                      stride=stride, pad=pad)
+            thr = 5e-5 * max(1.0, float(pre.abs().mean()))
+            conv_calls.append((pre.abs() < thr).flatten(0, 2).any(0).cpu())
+        return real_conv(x, w, bias, residual, stride, pad, act)
+
     head._capture_masks = []
-    T.linear = spy
+    T.linear, T.conv = spy, spy_conv
     try:
+        feats = det.backbone.forward_train(frames[0].cuda())
         cls_list, mask_list = head.forward_train_outputs(feats, Tn)
     finally:
         captured, head._capture_masks = head._capture_masks, None
-        T.linear = real_linear
+        T.linear, T.conv = real_linear, real_conv
+    assert len(conv_calls) == len(conv_names) == 49
+    conv_ties = dict(zip(conv_names, conv_calls))
     assert len(tie_units) == 9 + 2 + 6 and all(float(v.float().mean()) <= 0.05 for v in tie_units.values()), \
         {k: int(v.sum()) for k, v in tie_units.items()}
     assert len(cls_list) == 10 and mask_list[0].shape[:3] == (1, Tn, 100) and cls_list[-1].requires_grad
@@ -362,10 +406,13 @@ def test_decoder_head_training_step_vs_oracle():
     total.backward()
     # ---- oracle
     osd = {k: v.clone().float() for k, v in sd.items()}
-    trainable = [k for k in osd if k.startswith('panoptic_head.')]
+    bb = {n for n, p in det.named_parameters() if n.startswith('backbone.') and ('conv' in n or 'downsample.0' in n)}
+    trainable = [k for k in osd if k.startswith('panoptic_head.') or k in bb]
     for k in trainable:
         osd[k].requires_grad_(True)
-    ofeats = [f.detach().cpu().contiguous() for f in feats]
+    ofeats = om.resnet50(osd, frames[0])
+    for a, b in zip(feats, ofeats):
+        _close(a, b, 1e-4, 'backbone features')
     ocls, omask, _, extras = om.head_forward(osd, ofeats, video=True, num_frames=Tn, return_all=True,
                                              tie_masks=[m.cpu() for m in captured])
     assert not [s for s in extras['tie_stats'] if s['flipped_non_ties']], extras['tie_stats']
@@ -377,7 +424,7 @@ def test_decoder_head_training_step_vs_oracle():
         ototal = ototal + wc + wm + wd
     ototal.backward()
     params = dict(det.named_parameters())
-    worst = {}
+    worst, excused = {}, {}
     for k in trainable:
         p = params[k]
         og = osd[k].grad
@@ -386,20 +433,32 @@ def test_decoder_head_training_step_vs_oracle():
             continue
         assert p.grad is not None, k
         diff = (p.grad.cpu() - og).abs()
-        ties = tie_units.get(k if k.endswith('.weight') else k[:-len('bias')] + 'weight')
-        if ties is not None and ties.any():          # units on the ReLU kink: excluded here, counted in tie_units
-            diff = diff[~ties]
-        err = float(diff.max())
         scale = max(float(og.abs().max()), 1e-3)
-        worst[k] = err / scale
-    bad = {k: round(v, 5) for k, v in worst.items() if v > 2e-3}
+        ties = tie_units.get(k if k.endswith('.weight') else k[:-len('bias')] + 'weight')
+        if ties is None:
+            ties = conv_ties.get(k)
+        if ties is not None and ties.any():          # output units with a ReLU kink tie: a difference there is excused,
+            tol = 2e-2 if k.startswith('backbone.') else 2e-3       # and counted; everywhere else it is an error
+            excused[k] = int(((diff.flatten(1).max(1)[0] if diff.dim() > 1 else diff) > tol * scale)[ties].sum())
+            diff = diff[~ties]
+        worst[k] = float(diff.max()) / scale if diff.numel() else 0.0
+    # tolerances: 2e-3 of the tensor maximum for the head; 2e-2 plus a cosine of 0.999 for the backbone convolutions,
+    # whose gradients pass ~1.5 M ReLU kinks and the max-pooling ties -- the CPU oracle differs from ITSELF by up to 7e-3
+    # there between fp32 and fp64 (tools/grad_noise_floor.py; head tensors: 3e-6)
+    bad = {k: round(v, 5) for k, v in worst.items() if v > (2e-2 if k.startswith('backbone.') else 2e-3)}
     assert not bad, bad
-    assert len(worst) > 280                                   # decoder 9 x 18, encoder 6 x 16, convs / norms, heads, embeddings
-    assert all(params[k].grad is None for k in params if k.startswith('backbone.'))
+    cos = {k: float(torch.nn.functional.cosine_similarity(params[k].grad.cpu().flatten(), osd[k].grad.flatten(), dim=0))
+           for k in trainable if k.startswith('backbone.')}
+    assert min(cos.values()) > 0.999, min(cos.items(), key=lambda kv: kv[1])
+    assert len(worst) > 330                                   # + 53 backbone convolutions
+    assert all(params[k].grad is None for k in params if k.startswith('backbone.') and k not in bb)     # BatchNorm frozen
     import json
     import os
     os.makedirs('gpurun_out', exist_ok=True)
-    json.dump(dict(loss_terms=terms, worst_rel_grad_err=max(worst.values()), tensors=len(worst),
+    json.dump(dict(loss_terms=terms, worst_rel_grad_err_head=max(v for k, v in worst.items() if not k.startswith('backbone.')),
+                   worst_rel_grad_err_backbone=max(v for k, v in worst.items() if k.startswith('backbone.')),
+                   min_cosine_backbone=min(cos.values()), tensors=len(worst),
+                   rows_excused_as_relu_kink_ties={k: v for k, v in excused.items() if v},
                    tie_bits=sum(s['flipped_ties'] for s in extras['tie_stats']),
                    relu_kink_units={k: int(v.sum()) for k, v in tie_units.items() if v.any()}), open('gpurun_out/train_parity.json', 'w'))
 
@@ -425,7 +484,7 @@ def test_forward_train_and_optimizer_steps():
     data = dict(img=frames[:, 0].cuda(), img_metas=[metas[0][0]], return_loss=True, ref_img=frames.cuda(), ref_img_metas=metas,
                 ref_gt_bboxes=None, ref_gt_labels=gt_labels, ref_gt_masks=gt_masks, ref_gt_semantic_seg=None,
                 ref_gt_instance_ids=gt_ids)
-    opt = torch.optim.AdamW([p for n, p in det.named_parameters() if n.startswith('panoptic_head.')],
+    opt = torch.optim.AdamW([p for n, p in det.named_parameters() if n.startswith('panoptic_head.') or 'conv' in n or 'downsample.0' in n],
                             lr=1e-4, weight_decay=0.05)
     history = []
     for step in range(6):
