@@ -294,6 +294,76 @@ def tube_dump_bench(det, meta, frames, batch):
                      'host path: numpy RLE of pan == id per segment (the reference uses pycocotools per segment)')
 
 
+def training_bench(dev, with_cpu, clips=16, steps=3):
+    """one optimisation step of the VPS detector at the reference's training configuration
+    (configs/mask2former_vps/mask2former_video_r50.py: samples_per_gpu = 16 clips of 2 frames, 360 x 480 padded to
+    384 x 480, 12544 loss points; _base_/schedules/m2f_schedules.py: AdamW lr 1e-4, weight decay 0.05, gradient clipping at
+    0.01): detector.train_step (forward_train + the 30 loss terms) -> backward -> clip -> AdamW step, every forward and
+    backward op a library kernel; device time per step.  CPU: the oracle's forward + torch autograd backward of ONE clip."""
+    import openpvsg_b200 as pv
+    from openpvsg_b200 import configs, synthetic as syn
+    det = pv.build_detector(configs.mask2former_r50(True))
+    det.load_state_dict(syn.mask2former_state_dict(seed=3))
+    det.to(dev)
+    det.panoptic_head.train_cfg = dict(num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75)
+    data = syn.training_batch(clips, device=dev)
+    params = [p for n, p in det.named_parameters() if n.startswith('panoptic_head.') or 'conv' in n or 'downsample.0' in n]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = det.train_step(data, opt)
+        out['loss'].backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.01)
+        opt.step()
+        return out
+
+    from openpvsg_b200 import lib as _l
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    n0 = _l.launch_count[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.reset_peak_memory_stats()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = dict(workload=f'VPS training step: {clips} clips x 2 frames @384x480 (reference training config), forward_train + '
+                        'backward + grad clip + AdamW, backbone convolutions + whole head trainable (BatchNorm frozen as in the '
+                        'reference config)', ms_per_step=round(ms, 1), clips_per_s=round(clips / ms * 1e3, 2),
+               frames_per_s=round(2 * clips / ms * 1e3, 2), trainable_tensors=len(params), loss=round(float(out['loss']), 3),
+               library_calls_per_step=int((_l.launch_count[0] - n0) / steps),
+               peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 1))
+    del det, opt, params, data, out
+    torch.cuda.empty_cache()
+    if with_cpu:
+        from oracle import losses as ol, m2f as om
+        torch.set_num_threads(os.cpu_count())
+        sd = {k: v.clone().float() for k, v in syn.mask2former_state_dict(seed=3).items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and (k.startswith('panoptic_head.') or 'conv' in k or 'downsample.0' in k):
+                v.requires_grad_(True)
+        one = syn.training_batch(1)
+        gt = torch.stack(one['ref_gt_masks'][0], 1).float()                       # [G,T,H,W]
+        labels = one['ref_gt_labels'][0][:gt.shape[0], 1]
+        g = torch.Generator().manual_seed(0)
+        t0 = time.perf_counter()
+        cls, masks, _ = om.head_forward(sd, om.resnet50(sd, one['ref_img'][0]), video=True, num_frames=2)
+        total = 0
+        for c, m in zip(cls, masks):
+            lc, lm, ld, _, _ = ol.loss_single(c, m, [labels], [gt], torch.rand(1, 12544, 2, generator=g),
+                                              lambda n: torch.rand(n, 12544, 2, generator=g))
+            total = total + lc + lm + ld
+        total.backward()
+        sec = time.perf_counter() - t0
+        res.update(cpu_clips_per_s=round(1.0 / sec, 4), cpu_cores=os.cpu_count(),
+                   cpu_sample='1 clip of 2 frames through the CPU oracle forward + torch autograd backward (no optimizer step)')
+    return res
+
+
 def _relation_models(dev):
     from openpvsg_b200 import relation_head as rh, synthetic as syn
     sds = syn.relation_state_dicts(seed=1)
@@ -769,6 +839,11 @@ def main():
         extra['relation_head'] = relation_bench(dev, not args.no_cpu_baseline)
     except Exception as ex:
         extra['relation_head'] = dict(error=repr(ex))
+    try:
+        if not swin and world == 1:
+            extra['training_step'] = training_bench(dev, not args.no_cpu_baseline)
+    except Exception as ex:
+        extra['training_step'] = dict(error=repr(ex))
     try:
         extra['relation_set'] = relset_bench(dev, not args.no_cpu_baseline)
         extra['relation_set']['frac_hbm'] = round(extra['relation_set']['achieved_GBps'] / peaks['hbm_gbs'], 4)

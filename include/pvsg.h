@@ -533,6 +533,11 @@ int pvsg_groupnorm_nhwc_backward(const float* x, const float* gamma, const float
 /* adjoint of pvsg_bilinear_resize_nhwc (F.interpolate bilinear, align_corners=False, the FPN top-down step
  * msdeformattn_pixel_decoder.py L0): dsrc [B,IH,IW,C] (zeroed here) += scatter of dout [B,OH,OW,C]. */
 int pvsg_bilinear_resize_nhwc_backward(const float* dout, float* dsrc, int B, int IH, int IW, int OH, int OW, int C, void* stream);
+/* Operand preparation of the weight-gradient GEMMs (dW = dZ^T X, reduction over the tokens): rows r = (b, oh, ow) of a
+ * token-major view (element strides sb, sh, sw; channels contiguous; optional `add` with the same layout) -> bf16 (hi, lo)
+ * planes [C, ldt], column r.  The planes feed pvsg_linear_tc_batched as K-chunk views (split-K), summed by pvsg_colsum. */
+int pvsg_transpose_split(const float* x, const float* add, void* hi, void* lo, int64_t T, int C, int OH, int OW, int64_t sb,
+                         int64_t sh, int64_t sw, int64_t ldt, void* stream);
 /* backward of pvsg_maxpool3x3s2_nhwc (ResNet stem max pooling): dx [B,H,W,C] (zeroed here); the gradient of a window goes to
  * its first maximum in scan order (ATen max_pool2d_with_indices_backward). */
 int pvsg_maxpool3x3s2_nhwc_backward(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream);

@@ -18,6 +18,19 @@ class Config(ConfigDict):
         cfg['filename'] = filename
         return cfg
 
+    @property
+    def pretty_text(self):
+        import pprint
+        return pprint.pformat(_plain(self), width=120)
+
+    def dump(self, file=None):
+        """mmcv.Config.dump: the merged config as a python file of top-level assignments."""
+        text = ''.join(f'{k} = {_plain(v)!r}\n' for k, v in self.items() if k != 'filename')
+        if file is None:
+            return text
+        with open(file, 'w') as f:
+            f.write(text)
+
     def merge_from_dict(self, options):
         for dotted, value in options.items():
             node = self
@@ -27,6 +40,14 @@ class Config(ConfigDict):
                     node[k] = ConfigDict()
                 node = node[k]
             node[keys[-1]] = to_cfg(value)
+
+
+def _plain(v):
+    if isinstance(v, dict):
+        return {k: _plain(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return type(v)(_plain(x) for x in v) if not isinstance(v, range) else list(v)
+    return v
 
 
 class DictAction(argparse.Action):

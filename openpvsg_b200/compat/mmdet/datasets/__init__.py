@@ -21,9 +21,25 @@ def _collate(batch):
     return out
 
 
+def _collate_train(batch):
+    """Training samples (SeqDefaultFormatBundle + Collect of the train pipeline): image tensors are stacked (img [B,3,H,W],
+    ref_img [B,T,3,H,W]); metas and every ground-truth field stay lists over the batch -- the keyword arguments of
+    Mask2FormerVideoCustom.forward_train."""
+    out = {}
+    for key in batch[0]:
+        vals = [b[key] for b in batch]
+        out[key] = torch.stack(vals) if key in ('img', 'ref_img') else vals
+    return out
+
+
 def build_dataloader(dataset, samples_per_gpu=1, workers_per_gpu=0, num_gpus=1, dist=False, shuffle=False, seed=None,
-                     persistent_workers=False, **kwargs):
+                     persistent_workers=False, train=False, **kwargs):
     sampler = DistributedSampler(dataset, shuffle=False) if dist else None
+    if train:
+        gen = torch.Generator()
+        gen.manual_seed(int(seed) if seed is not None else 0)
+        return DataLoader(dataset, batch_size=samples_per_gpu, shuffle=shuffle, generator=gen, num_workers=workers_per_gpu,
+                          collate_fn=_collate_train, drop_last=False)
     return DataLoader(dataset, batch_size=samples_per_gpu, sampler=sampler, shuffle=False, num_workers=workers_per_gpu,
                       collate_fn=_collate, pin_memory=torch.cuda.is_available(),
                       persistent_workers=persistent_workers and workers_per_gpu > 0)

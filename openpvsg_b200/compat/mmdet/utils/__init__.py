@@ -57,3 +57,23 @@ def build_ddp(model, device='cuda', device_ids=None, **kwargs):
     """Inference needs no gradient synchronisation: one replica per rank on its own GPU."""
     index = (device_ids or [0])[0]
     return _SingleDevice(model, f'cuda:{index}' if device == 'cuda' else device)
+
+
+def collect_env():
+    import sys
+    return {'sys.platform': sys.platform, 'Python': sys.version.replace('\n', ''), 'PyTorch': torch.__version__,
+            'CUDA available': torch.cuda.is_available(),
+            'GPU 0': torch.cuda.get_device_name(0) if torch.cuda.is_available() else None, 'backend': 'openpvsg_b200'}
+
+
+def get_root_logger(log_file=None, log_level='INFO'):
+    import logging
+    logger = logging.getLogger('mmdet')
+    if not logger.handlers:
+        logger.addHandler(logging.StreamHandler())
+    if log_file is not None and not any(getattr(h, 'baseFilename', None) == log_file for h in logger.handlers):
+        logger.addHandler(logging.FileHandler(log_file, 'w'))
+    for h in logger.handlers:
+        h.setFormatter(logging.Formatter('%(asctime)s - %(name)s - %(levelname)s - %(message)s'))
+    logger.setLevel(getattr(logging, log_level) if isinstance(log_level, str) else log_level)
+    return logger

@@ -987,7 +987,8 @@ extern "C" int pvsg_linear_tc_batched(const void* A_hi, const void* A_lo, int64_
                                       int32_t* row_open, int64_t ldc, int batch, int64_t M, int64_t N, int64_t K,
                                       void* stream) {
     PVSG_CHECK_ARG(A_hi && A_lo && W_hi && W_lo && (C || mask) && batch > 0 && M > 0 && N > 0 && K > 0);
-    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && a_bs >= M * lda && w_bs >= N * ldw);
+    // batch strides: whole matrices ([batch, M, lda]) or K-chunks of ONE matrix (split-K views: stride = chunk length)
+    PVSG_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (a_bs >= M * lda || a_bs >= K) && (w_bs >= N * ldw || w_bs >= K));
     if (K % BK != 0 || (lda | ldw | a_bs | w_bs) % 8 != 0 || !al16(A_hi) || !al16(A_lo) || !al16(W_hi) || !al16(W_lo))
         return PVSG_ERR_UNSUPPORTED;
     const int64_t tiles_mb = (M + BM - 1) / BM;

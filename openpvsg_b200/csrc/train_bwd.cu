@@ -12,6 +12,8 @@
 //
 // First cut, sized for correctness at training shapes (batch 1-4, 100 queries, <= 15 k keys, head dim 32): exact fp32
 // SIMT, deterministic (no atomics except the column sums).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -374,6 +376,50 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
     atomicAdd(base + ((int64_t)y1 * IW + x1) * C, g * wy1 * wx1);
 }
 
+// ------------------------------------------------------------------------------------------ transpose + split
+// Operand preparation of the weight-gradient GEMMs (dW = dZ^T X: the reduction runs over the tokens, so both operands
+// are needed token-minor): source rows r = (b, oh, ow) of a (possibly strided / shifted) token-major view [.., C] ->
+// bf16 (hi, lo) planes [C, ldt] with column r; one pass instead of transpose + split (+ the optional add of a second
+// source with the same layout).
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                              int64_t T, int C, int OH, int OW, int64_t sb, int64_t sh, int64_t sw,
+                                                              int64_t ldt) {
+    // tile: 64 source rows x 32 channels.  Loads: a warp reads the 32 channels of one row (128 B).  Stores: a warp writes
+    // 64 consecutive columns of one channel row as bf16x2 (128 B); rows beyond T are written as zeros (ldt >= ceil64(T)).
+    __shared__ float tile[64][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 32;
+    const int64_t hw = (int64_t)OH * OW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = warp + 8 * i;
+        const int64_t r = r0 + row;
+        float v = 0.f;
+        if (r < T && c0 + lane < C) {
+            const int64_t b = r / hw, rem = r - b * hw;
+            const int64_t off = b * sb + (rem / OW) * sh + (rem % OW) * sw + c0 + lane;
+            v = x[off];
+            if (add) v += add[off];
+        }
+        tile[row][lane] = v;
+    }
+    __syncthreads();
+    if (r0 + 2 * lane >= ldt) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = warp + 8 * i;
+        if (c0 + c >= C) continue;
+        const float v0 = tile[2 * lane][c], v1 = tile[2 * lane + 1][c];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        const int64_t o = (int64_t)(c0 + c) * ldt + r0 + 2 * lane;
+        *reinterpret_cast<__nv_bfloat162*>(hi + o) = __nv_bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162*>(lo + o) = __nv_bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
+                                                                    __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ max pooling backward
 // 3x3 / stride 2 / pad 1: every output routes its gradient to the FIRST maximum of its window in (row, column) scan order
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
@@ -581,5 +627,16 @@ extern "C" int pvsg_maxpool3x3s2_nhwc_backward(const float* x, const float* dy, 
     const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
     const int64_t total = (int64_t)B * OH * OW * C;
     maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, dx, H, W, OH, OW, C, total);
+    return pvsg_launch_status();
+}
+
+extern "C" int pvsg_transpose_split(const float* x, const float* add, void* hi, void* lo, int64_t T, int C, int OH, int OW,
+                                    int64_t sb, int64_t sh, int64_t sw, int64_t ldt, void* stream) {
+    PVSG_CHECK_ARG(x && hi && lo && T > 0 && C > 0 && OH > 0 && OW > 0 && ldt >= T && ldt % 2 == 0);
+    PVSG_CHECK_ARG(((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 3) == 0);
+    dim3 grid((unsigned)((T + 63) / 64), (unsigned)((C + 31) / 32));
+    if (grid.y > 65535) return PVSG_ERR_UNSUPPORTED;
+    transpose_split_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, add, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                        reinterpret_cast<__nv_bfloat16*>(lo), T, C, OH, OW, sb, sh, sw, ldt);
     return pvsg_launch_status();
 }

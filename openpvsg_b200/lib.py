@@ -77,6 +77,7 @@ SIGNATURES = {
     'pvsg_lap_assign': (I, [P, I, I, D, P, P, P]),
     'pvsg_layernorm_backward': (I, [P, P, P, P, P, P, L, I, F, P]),
     'pvsg_relu_backward': (I, [P, P, P, L, P]),
+    'pvsg_transpose_split': (I, [P, P, P, P, L, I, I, I, L, L, L, L, P]),
     'pvsg_maxpool3x3s2_nhwc_backward': (I, [P, P, P, I, I, I, I, P]),
     'pvsg_groupnorm_nhwc_backward': (I, [P, P, P, P, P, P, P, P, I, L, I, I, F, I, P]),
     'pvsg_bilinear_resize_nhwc_backward': (I, [P, P, I, I, I, I, I, I, P]),

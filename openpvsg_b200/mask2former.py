@@ -120,6 +120,11 @@ class ResNet(_Prepared):
                 blocks.append(_Bottleneck(inpl, planes, stride, b == 0))
                 inpl = planes * 4
             setattr(self, f'layer{i + 1}', nn.Sequential(*blocks))
+        if norm_cfg is not None and dict(norm_cfg).get('requires_grad', True) is False:     # base cfg :12 (BN frozen)
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad_(False)
         self.eval()
 
     def init_weights(self):
@@ -1243,9 +1248,12 @@ class _DetectorBase(nn.Module):
         self.eval()
 
     def train(self, mode=True):
-        if mode:
-            raise NotImplementedError('inference backend only')
-        return super().train(False)
+        """Training mode only changes the flag: every normalisation layer of the model is batch-independent (LayerNorm,
+        GroupNorm, eval-mode BatchNorm folded into the convolutions: norm_eval=True) and all dropout rates are 0."""
+        return super().train(mode)
+
+    def init_weights(self):
+        """mmcv BaseModule.init_weights: pretrained weights come from ``load_state_dict`` / ``load_checkpoint`` here."""
 
     # Captured CUDA graphs (engine.FrameRunner) hold raw pointers to kernel-layout copies of the weights:
     # reloading, moving or casting the detector starts a new weights epoch and drops them (engine.get_runner).
@@ -1285,8 +1293,8 @@ class _DetectorBase(nn.Module):
     def aug_test(self, imgs, img_metas, **kwargs):
         raise NotImplementedError  # as the reference: mask2former.py:193-194
 
-    def forward(self, img=None, img_metas=None, return_loss=False, **kwargs):
-        """mmdet BaseDetector.forward."""
+    def forward(self, img=None, img_metas=None, return_loss=True, **kwargs):
+        """mmdet BaseDetector.forward (return_loss defaults to True there: train_step calls self(**data))."""
         if return_loss:
             return self.forward_train(img, img_metas, **kwargs)
         return self.forward_test(img, img_metas, **kwargs)

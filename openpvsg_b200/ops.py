@@ -710,6 +710,68 @@ def msda_proj_backward(aw, dloc, daw, spatial_shapes):
     return dproj
 
 
+def splitk_plan(T, M, N):
+    """Split-K plan of a token-reduction GEMM [M,T] x [N,T]^T: (chunks S, chunk length Kc, padded T = S * Kc).  Enough
+    chunks that S * tiles covers the SMs twice, chunk length a multiple of the 64-column k-block."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    S = max(1, min((296 + tiles - 1) // tiles, (T + 255) // 256))
+    Kc = ((T + S - 1) // S + 63) // 64 * 64
+    S = (T + Kc - 1) // Kc
+    return S, Kc, S * Kc
+
+
+def alloc_planes(rows, T, ldt, device):
+    """(hi, lo) bf16 [rows, ldt] for transpose_split: the kernel writes (zeros included) up to the 64-column tile that holds
+    column T - 1, so only the columns beyond it are cleared here."""
+    hi = torch.empty(rows, ldt, device=device, dtype=torch.bfloat16)
+    lo = torch.empty(rows, ldt, device=device, dtype=torch.bfloat16)
+    t64 = (T + 63) // 64 * 64
+    if t64 < ldt:
+        hi[:, t64:].zero_()
+        lo[:, t64:].zero_()
+    return hi, lo
+
+
+def transpose_split(x, ldt, add=None, hi=None, lo=None, row0=0):
+    """Token-major view x [.., C] (2-D [T,C] with any row stride, or 4-D [B,OH,OW,C] with any strides; unit channel
+    stride) -> planes [C, ldt] (zero beyond T).  hi / lo + row0: write into rows row0.. of existing [R, ldt] planes."""
+    lib = _l.load()
+    _f32(x)
+    if x.stride(-1) != 1 or x.dim() not in (2, 4):
+        raise _l.PvsgError('transpose_split: 2-D or 4-D token-major view with unit channel stride required')
+    C = x.shape[-1]
+    if x.dim() == 2:
+        T, OH, OW, sb, sh, sw = x.shape[0], 1, x.shape[0], 0, 0, x.stride(0)
+    else:
+        B, OH, OW, _ = x.shape
+        T, sb, sh, sw = B * OH * OW, x.stride(0), x.stride(1), x.stride(2)
+    if add is not None and (add.shape != x.shape or add.stride() != x.stride()):
+        raise _l.PvsgError('transpose_split: add must share the layout of x')
+    if hi is None:
+        hi, lo = alloc_planes(C, T, ldt, x.device)
+    if hi.shape[1] != ldt or row0 + C > hi.shape[0] or not hi.is_contiguous() or not lo.is_contiguous():
+        raise _l.PvsgError('transpose_split: bad destination planes')
+    _l.check(lib.pvsg_transpose_split(_ptr(x), _ptr(add), hi.data_ptr() + 2 * row0 * ldt, lo.data_ptr() + 2 * row0 * ldt, T, C,
+                                      OH, OW, sb, sh, sw, ldt, _stream()), 'pvsg_transpose_split')
+    return hi, lo
+
+
+def splitk_gemm(a, w, S, Kc):
+    """a = (hi, lo) [M, S*Kc], w = (hi, lo) [N, S*Kc] bf16 planes -> fp32 [M, N] = a w^T, reduced over S K-chunks: one
+    batched tcgen05 launch over the chunk views, then a column sum over the partial results."""
+    lib = _l.load()
+    (a_hi, a_lo), (w_hi, w_lo) = a, w
+    M, Tp = a_hi.shape
+    N = w_hi.shape[0]
+    if Tp != S * Kc or w_hi.shape[1] != Tp:
+        raise _l.PvsgError('splitk_gemm: plane widths do not match the plan')
+    part = torch.empty(S, M, N, device=a_hi.device, dtype=torch.float32)
+    _l.check(lib.pvsg_linear_tc_batched(_ptr(a_hi), _ptr(a_lo), Tp, Kc if S > 1 else M * Tp, _ptr(w_hi), _ptr(w_lo), Tp,
+                                        Kc if S > 1 else N * Tp, _ptr(part), None, None, N, S, M, N, Kc, _stream()),
+             'pvsg_linear_tc_batched')
+    return part[0] if S == 1 else colsum(part.view(S, M * N)).view(M, N)
+
+
 def layernorm_backward(x, gamma, dy, eps=1e-5):
     """nn.LayerNorm backward over the last axis -> (dx, dgamma, dbeta)."""
     lib = _l.load()

@@ -246,3 +246,25 @@ def frame_meta(height=720, width=1280, size_divisor=32):
     wp = (width + size_divisor - 1) // size_divisor * size_divisor
     return dict(img_shape=(height, width, 3), ori_shape=(height, width, 3),
                 pad_shape=(hp, wp, 3), batch_input_shape=(hp, wp))
+
+
+def training_batch(clips=16, height=384, width=480, num_frames=2, num_gt=4, device='cpu', seed=0):
+    """A synthetic training batch in the reference's format (configs/_base_/datasets/pvsg_vps.py: 2-frame clips resized to
+    360 x 480 and padded to a multiple of 32; mask2former_video_r50.py: samples_per_gpu = 16): the keyword arguments of
+    ``Mask2FormerVideoCustom.forward_train`` -- ref_img [B,T,3,H,W], per clip the (frame, label) / (frame, instance id) pairs
+    and per frame the instance masks [n,H,W].  ``num_gt`` box-shaped instances per clip, present in every frame."""
+    frames = torch.stack([torch.stack([synthetic_frame(seed + 7 * c + t, height, width) for t in range(num_frames)])
+                          for c in range(clips)]).to(device)
+    metas = [[dict(frame_meta(height, width), pad_shape=(height, width, 3)) for _ in range(num_frames)] for _ in range(clips)]
+    gt_masks, gt_labels, gt_ids = [], [], []
+    for c in range(clips):
+        m = torch.zeros(num_gt, num_frames, height, width, dtype=torch.bool)
+        for k in range(num_gt):
+            y0, x0 = (37 * k + 11 * c) % (height // 2), (53 * k + 29 * c) % (width // 2)
+            m[k, :, y0:y0 + height // 3, x0:x0 + width // 3] = True
+        gt_masks.append([m[:, t].to(device) for t in range(num_frames)])
+        gt_labels.append(torch.tensor([[t, (10 * k + 3 + c) % 126] for t in range(num_frames) for k in range(num_gt)], device=device))
+        gt_ids.append(torch.tensor([[t, 100 + k] for t in range(num_frames) for k in range(num_gt)], device=device))
+    return dict(img=frames[:, 0], img_metas=[m[0] for m in metas], return_loss=True, ref_img=frames, ref_img_metas=metas,
+                ref_gt_bboxes=None, ref_gt_labels=gt_labels, ref_gt_masks=gt_masks, ref_gt_semantic_seg=None,
+                ref_gt_instance_ids=gt_ids)

@@ -19,6 +19,27 @@ def _t(x):
     return x.t().contiguous()
 
 
+def _grad_weight(dz2, sources):
+    """dW [N, sum C_i] = dz2^T [N,T] . concat_i(src_i) [T, C_i]: both operands are transposed into token-minor bf16 planes
+    in one pass each (ops.transpose_split), the GEMM runs split-K over token chunks on the tcgen05 engine
+    (ops.splitk_gemm).  sources: list of (view [T,C] or [B,OH,OW,C], add or None)."""
+    N = dz2.shape[1]
+    T = dz2.shape[0]
+    widths = [src.shape[-1] for src, _ in sources]
+    S, Kc, Tp = ops.splitk_plan(T, N, sum(widths))
+    dzp = ops.transpose_split(dz2, Tp)
+    if len(sources) == 1:
+        wp = ops.transpose_split(sources[0][0], Tp, add=sources[0][1])
+    else:
+        hi, lo = ops.alloc_planes(sum(widths), T, Tp, dz2.device)
+        row = 0
+        for (src, add), c in zip(sources, widths):
+            ops.transpose_split(src, Tp, add=add, hi=hi, lo=lo, row0=row)
+            row += c
+        wp = (hi, lo)
+    return ops.splitk_gemm(dzp, wp, S, Kc)
+
+
 class _Linear(torch.autograd.Function):
     """y = act((x + add_input) W^T + bias + residual); act in {none, relu}."""
 
@@ -43,10 +64,10 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0] or (has_add and ctx.needs_input_grad[3]):
             dx = ops.linear(dz2, _t(weight)).reshape(x.shape)           # dy W
-        if ctx.needs_input_grad[1]:
-            x2 = x.reshape(-1, K)
-            a2 = _t(add_input.reshape(-1, K)) if has_add else None
-            dw = _t(ops.linear(_t(x2), _t(dz2), add_input=a2))           # (x + add)^T dy, transposed back -> [N, K]
+        if ctx.needs_input_grad[1]:                                      # dW = dz^T (x + add): reduction over the tokens
+            x2 = x.reshape(-1, K).contiguous()
+            a2 = add_input.reshape(-1, K).contiguous() if has_add else None
+            dw = _grad_weight(dz2, [(x2, a2)])
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dz2)
         return (dx if ctx.needs_input_grad[0] else None, dw, db, dx if has_add and ctx.needs_input_grad[3] else None, d_res, None)
@@ -109,10 +130,19 @@ class _MaskLogits(torch.autograd.Function):
         embed, feat = ctx.saved_tensors
         dl = dl.contiguous()
         d_embed = d_feat = None
-        if ctx.needs_input_grad[0]:
-            d_embed = torch.stack([ops.linear(dl[b], _t(feat[b])) for b in range(embed.shape[0])])        # dL F
-        if ctx.needs_input_grad[1]:
-            d_feat = torch.stack([ops.linear(_t(dl[b]), _t(embed[b])) for b in range(embed.shape[0])])    # dL^T E
+        B, Q, C = embed.shape
+        P = feat.shape[1]
+        if ctx.needs_input_grad[0]:                      # dL F: reduction over the pixels, split-K
+            S, Kc, Tp = ops.splitk_plan(P, Q, C)
+            rows = []
+            for b in range(B):
+                a = ops.split_bf16(torch.nn.functional.pad(dl[b], (0, Tp - P)).contiguous())
+                rows.append(ops.splitk_gemm(a, ops.transpose_split(feat[b], Tp), S, Kc))
+            d_embed = torch.stack(rows)
+        if ctx.needs_input_grad[1]:                      # dL^T E: reduction over the queries (padded to one k-block pair)
+            Qp = (Q + 63) // 64 * 64
+            d_feat = torch.stack([ops.splitk_gemm(ops.transpose_split(dl[b], Qp), ops.transpose_split(embed[b], Qp), 1, Qp)
+                                  for b in range(B)])
         return d_embed, d_feat
 
 
@@ -212,16 +242,10 @@ class _Conv(torch.autograd.Function):
                 dx = ops.linear(z.view(-1, Cout), _t(w.view(Cout, Cin))).view(B, H, W, Cin)
             else:
                 dx = ops.conv2d_nhwc(z, w.flip(1, 2).permute(3, 1, 2, 0).contiguous(), None, pad=R - 1 - pad)
-        if ctx.needs_input_grad[1]:
-            dzt = _t(dz.view(-1, Cout))                  # [Cout, tokens]
+        if ctx.needs_input_grad[1]:                      # all filter taps in ONE token-reduction GEMM: N = R * S * Cin
             xp = torch.nn.functional.pad(x, (0, 0, pad, pad, pad, pad)) if pad else x
-            taps = [xp[:, r:r + stride * OH:stride, q:q + stride * OW:stride].reshape(-1, Cin) for r in range(R) for q in range(S)]
-            if Cin < 16:                                 # RGB stem: one GEMM over the gathered patches [tokens, R*S*Cin]
-                dw = ops.linear(dzt, _t(torch.cat(taps, 1))).view(Cout, R, S, Cin)
-            else:
-                dw = torch.empty_like(w)
-                for i, xs in enumerate(taps):
-                    dw[:, i // S, i % S, :] = ops.linear(dzt, _t(xs))
+            taps = [(xp[:, r:r + stride * OH:stride, q:q + stride * OW:stride], None) for r in range(R) for q in range(S)]
+            dw = _grad_weight(dz.view(-1, Cout), taps).view(Cout, R, S, Cin)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dz.view(-1, Cout))
         return dx, dw, db, (dz if has_res and ctx.needs_input_grad[3] else None), None, None, None

@@ -500,3 +500,56 @@ def test_forward_train_and_optimizer_steps():
     with torch.no_grad():
         cls_after, _ = head.forward(det.extract_feat(frames[0].cuda()), metas)
     assert float((cls_after[-1] - cls_list[-1]).abs().max()) > 1e-4
+
+
+def test_compat_train_detector_runs_the_reference_schedule(tmp_path):
+    """openpvsg_b200/compat mmdet.apis.train_detector (what tools/train.py calls) on the synthetic training set: the
+    optimizer groups follow _base_/schedules/m2f_schedules.py (backbone lr x0.1, embeddings / norms without weight decay,
+    frozen BatchNorm left out), warm-up scales the lr, gradients are clipped, a checkpoint is written, the loss falls."""
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'openpvsg_b200', 'compat')
+    saved_path, saved = list(sys.path), {k: v for k, v in sys.modules.items() if k.split('.')[0] in ('mmcv', 'mmdet', 'datasets', 'models', 'utils')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, compat)
+    try:
+        from mmcv import Config
+        from mmdet.apis import build_optimizer, set_random_seed, train_detector
+        from datasets.datasets.builder import build_dataset
+        import openpvsg_b200 as pv
+        from openpvsg_b200 import configs, synthetic as syn
+        set_random_seed(3)
+        embed_multi = dict(lr_mult=1.0, decay_mult=0.0)
+        cfg = Config(dict(
+            data=dict(samples_per_gpu=2, workers_per_gpu=0,
+                      train=dict(type='SyntheticVPSDataset', num_frames=6, height=96, width=160, test_mode=False, ref_seq_index=[0, 1])),
+            optimizer=dict(type='AdamW', lr=1e-4, weight_decay=0.05, eps=1e-8, betas=(0.9, 0.999),
+                           paramwise_cfg=dict(custom_keys={'backbone': dict(lr_mult=0.1, decay_mult=1.0), 'query_embed': embed_multi,
+                                                           'query_feat': embed_multi, 'level_embed': embed_multi}, norm_decay_mult=0.0)),
+            optimizer_config=dict(grad_clip=dict(max_norm=0.01, norm_type=2)),
+            lr_config=dict(policy='step', warmup='linear', warmup_iters=4, warmup_ratio=0.001, step=[2]),
+            runner=dict(type='EpochBasedRunner', max_epochs=3), log_config=dict(interval=1), checkpoint_config=dict(interval=3),
+            work_dir=str(tmp_path), device='cuda', seed=3))
+        det = pv.build_detector(configs.mask2former_r50(True))
+        det.load_state_dict(syn.mask2former_state_dict(seed=4))
+        det.panoptic_head.train_cfg = dict(num_points=400, oversample_ratio=3.0, importance_sample_ratio=0.75)
+        assert not any(p.requires_grad for n, p in det.named_parameters() if '.bn' in n or 'downsample.1' in n)
+        opt = build_optimizer(det, cfg.optimizer)
+        by_name = {g['name']: g for g in opt.param_groups}
+        assert abs(by_name['backbone.layer1.0.conv1.weight']['lr'] - 1e-5) < 1e-12 and by_name['backbone.conv1.weight']['weight_decay'] == 0.05
+        assert by_name['panoptic_head.query_embed.weight']['weight_decay'] == 0.0 and by_name['panoptic_head.query_embed.weight']['lr'] == 1e-4
+        assert by_name['panoptic_head.transformer_decoder.layers.0.norms.0.weight']['weight_decay'] == 0.0
+        assert by_name['panoptic_head.pixel_decoder.input_convs.0.gn.weight']['weight_decay'] == 0.0
+        assert by_name['panoptic_head.cls_embed.weight']['weight_decay'] == 0.05 and not any('.bn' in n for n in by_name)
+        out = train_detector(det, [build_dataset(cfg.data.train)], cfg, distributed=False, validate=False, meta=dict(seed=3))
+        assert out['iters'] == 9 and all(np.isfinite(out['loss_history']))
+        assert np.mean(out['loss_history'][-3:]) < np.mean(out['loss_history'][:3])
+        ck = torch.load(os.path.join(str(tmp_path), 'epoch_3.pth'), map_location='cpu', weights_only=False)
+        assert ck['meta']['epoch'] == 3 and ck['meta']['iter'] == 9 and 'panoptic_head.query_feat.weight' in ck['state_dict']
+        assert abs(out['optimizer'].param_groups[0]['lr'] - out['optimizer'].param_groups[0]['initial_lr'] * 0.1) < 1e-12   # epoch 2: step
+    finally:
+        sys.path[:] = saved_path
+        for k in [m for m in sys.modules if m.split('.')[0] in ('mmcv', 'mmdet', 'datasets', 'models', 'utils')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
