@@ -12,6 +12,9 @@ __version__ = '1.4.0+openpvsg_b200.compat'
 class Config(ConfigDict):
     """mmcv.Config subset: python config files with `_base_` inheritance, attribute access, merge_from_dict."""
 
+    def __init__(self, cfg_dict=None, **kwargs):
+        super().__init__(to_cfg(dict(cfg_dict or {}, **kwargs)))      # nested dicts get attribute access too
+
     @staticmethod
     def fromfile(filename, **kwargs):
         cfg = Config(load_config(filename))

@@ -63,11 +63,14 @@ class _Prepared(nn.Module):
         self._prep = None
         return super()._apply(fn, *a, **k)
 
-    def train(self, mode=True):
-        if mode:
-            raise NotImplementedError('openpvsg_b200 implements the inference path only '
-                                      '(SURVEY.md 8f rank 4: training forward/backward is a "next" row)')
-        return super().train(False)
+    def _stale(self):
+        """True when a parameter changed in place since the kernel-layout copies were made (an optimizer step bumps the
+        version counters; load_state_dict / .to() are caught by the hooks above)."""
+        sig = tuple(p._version for p in self.parameters())
+        if sig != self.__dict__.get('_prep_sig'):
+            self.__dict__['_prep_sig'] = sig
+            return True
+        return False
 
 
 # ======================================================================================
@@ -143,15 +146,15 @@ class ResNet(_Prepared):
 
     def forward_train(self, x):
         """``forward`` on the autograd tape (train_ops): eval-mode BatchNorm folded into every convolution as in
-        inference (norm_eval=True, BN parameters frozen: base cfg :7-16), so the trainable tensors are the convolution
-        weights; fp32 maps instead of operand planes."""
+        inference (norm_eval=True: running statistics, base cfg :7-16); the convolution weights and -- when
+        norm_cfg.requires_grad, as in the VPS config -- the BN affine parameters receive gradients through the fold; fp32
+        maps instead of operand planes."""
         from . import train_ops as T
 
-        def fold(conv, bn):
-            with torch.no_grad():
-                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-                shift = (bn.bias - bn.running_mean * scale).contiguous()
-            return (conv.weight * scale[:, None, None, None]).permute(0, 2, 3, 1), shift    # weight prep, on the tape
+        def fold(conv, bn):       # weight prep on the tape: the BN affine parameters train when norm_cfg.requires_grad (VPS cfg :13)
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            shift = bn.bias - bn.running_mean * scale
+            return (conv.weight * scale[:, None, None, None]).permute(0, 2, 3, 1), shift
 
         x = T.conv(_tokens(x), *fold(self.conv1, self.bn1), stride=2, pad=3, act=ops.ACT_RELU)
         x = T.maxpool3x3s2(x)
@@ -172,7 +175,7 @@ class ResNet(_Prepared):
 
     @torch.no_grad()
     def forward(self, x):
-        if self._prep is None:
+        if self._prep is None or self._stale():
             self._prepare()
         p = self._prep
         ops.clear_split_cache()
@@ -275,7 +278,7 @@ class MultiScaleDeformableAttention(_Prepared):
     def forward_tokens(self, x, pos, ref, spatial_shapes, x_planes=None, q_planes=None):
         """x, pos [B,N,C]; ref [N,2] -> output_proj(msda) + x.  x_planes / q_planes: operand planes of
         x and of x + pos when the producer (the previous LayerNorm) already emitted them."""
-        if self._prep is None:
+        if self._prep is None or self._stale():
             self._prepare()
         proj = ops.linear(q_planes, self._prep['w'], self._prep['b']) if q_planes is not None else \
             ops.linear(x, self._prep['w'], self._prep['b'], add_input=pos)
@@ -423,8 +426,9 @@ class _ConvModule(nn.Module):
 
     @torch.no_grad()
     def forward_tokens(self, x, planes=None):
-        if self._w is None or self._w.device != self.conv.weight.device:
+        if self._w is None or self._w.device != self.conv.weight.device or self._w_ver != self.conv.weight._version:
             self._w = self.conv.weight.permute(0, 2, 3, 1).contiguous()
+            self._w_ver = self.conv.weight._version
         if planes is None:
             planes = ops.recall_split(x)   # e.g. backbone stage outputs already carry operand planes
         y = ops.conv2d_nhwc(planes if planes is not None else x, self._w, self.conv.bias, pad=self.pad)
@@ -484,7 +488,7 @@ class MSDeformAttnPixelDecoder(_Prepared):
     def _shape_consts(self, shapes, device):
         """level positional encodings + reference points; depend on the shapes only."""
         key = (tuple(shapes), str(device))
-        if key not in self._shape_cache or self._prep is None:
+        if key not in self._shape_cache or self._prep is None or self._stale():
             pos, refs = [], []
             for i, (h, w) in enumerate(shapes):
                 pos.append(self.postional_encoding.tokens(h, w, device, add_vec=self.level_encoding.weight[i].contiguous()))

@@ -406,7 +406,7 @@ def test_decoder_head_training_step_vs_oracle():
     total.backward()
     # ---- oracle
     osd = {k: v.clone().float() for k, v in sd.items()}
-    bb = {n for n, p in det.named_parameters() if n.startswith('backbone.') and ('conv' in n or 'downsample.0' in n)}
+    bb = {n for n, p in det.named_parameters() if n.startswith('backbone.') and p.requires_grad}     # convs + BN affine (VPS cfg)
     trainable = [k for k in osd if k.startswith('panoptic_head.') or k in bb]
     for k in trainable:
         osd[k].requires_grad_(True)
@@ -437,21 +437,24 @@ def test_decoder_head_training_step_vs_oracle():
         ties = tie_units.get(k if k.endswith('.weight') else k[:-len('bias')] + 'weight')
         if ties is None:
             ties = conv_ties.get(k)
+        if ties is None and '.bn' in k:           # BN affine of a ReLU'd convolution: same output units as its conv
+            ties = conv_ties.get(k.replace('.bn', '.conv').rsplit('.', 1)[0] + '.weight')
         if ties is not None and ties.any():          # output units with a ReLU kink tie: a difference there is excused,
-            tol = 2e-2 if k.startswith('backbone.') else 2e-3       # and counted; everywhere else it is an error
+            tol = 3e-2 if k.startswith('backbone.') else 2e-3       # and counted; everywhere else it is an error
             excused[k] = int(((diff.flatten(1).max(1)[0] if diff.dim() > 1 else diff) > tol * scale)[ties].sum())
             diff = diff[~ties]
         worst[k] = float(diff.max()) / scale if diff.numel() else 0.0
-    # tolerances: 2e-3 of the tensor maximum for the head; 2e-2 plus a cosine of 0.999 for the backbone convolutions,
+    # tolerances: 2e-3 of the tensor maximum for the head; 3e-2 plus a cosine of 0.999 for the backbone tensors (one
+    # excused kink on the 3 x 5 layer4 maps of this test moves the upstream gradients of its block by ~1/30 of a token sum),
     # whose gradients pass ~1.5 M ReLU kinks and the max-pooling ties -- the CPU oracle differs from ITSELF by up to 7e-3
     # there between fp32 and fp64 (tools/grad_noise_floor.py; head tensors: 3e-6)
-    bad = {k: round(v, 5) for k, v in worst.items() if v > (2e-2 if k.startswith('backbone.') else 2e-3)}
+    bad = {k: round(v, 5) for k, v in worst.items() if v > (3e-2 if k.startswith('backbone.') else 2e-3)}
     assert not bad, bad
     cos = {k: float(torch.nn.functional.cosine_similarity(params[k].grad.cpu().flatten(), osd[k].grad.flatten(), dim=0))
            for k in trainable if k.startswith('backbone.')}
     assert min(cos.values()) > 0.999, min(cos.items(), key=lambda kv: kv[1])
-    assert len(worst) > 330                                   # + 53 backbone convolutions
-    assert all(params[k].grad is None for k in params if k.startswith('backbone.') and k not in bb)     # BatchNorm frozen
+    assert len(worst) > 430                                   # + 53 backbone convolutions and their BN affine pairs
+    assert len(bb) == 53 + 2 * 53
     import json
     import os
     os.makedirs('gpurun_out', exist_ok=True)
@@ -484,7 +487,7 @@ def test_forward_train_and_optimizer_steps():
     data = dict(img=frames[:, 0].cuda(), img_metas=[metas[0][0]], return_loss=True, ref_img=frames.cuda(), ref_img_metas=metas,
                 ref_gt_bboxes=None, ref_gt_labels=gt_labels, ref_gt_masks=gt_masks, ref_gt_semantic_seg=None,
                 ref_gt_instance_ids=gt_ids)
-    opt = torch.optim.AdamW([p for n, p in det.named_parameters() if n.startswith('panoptic_head.') or 'conv' in n or 'downsample.0' in n],
+    opt = torch.optim.AdamW([p for p in det.parameters() if p.requires_grad],
                             lr=1e-4, weight_decay=0.05)
     history = []
     for step in range(6):
@@ -500,6 +503,17 @@ def test_forward_train_and_optimizer_steps():
     with torch.no_grad():
         cls_after, _ = head.forward(det.extract_feat(frames[0].cuda()), metas)
     assert float((cls_after[-1] - cls_list[-1]).abs().max()) > 1e-4
+    # ... all of them: a fresh detector loaded with the trained state dict gives bit-identical inference results, i.e. no
+    # kernel-layout copy of a parameter (folded BN, concatenated projections, conv layouts, operand planes) went stale
+    import openpvsg_b200 as pv
+    from openpvsg_b200 import configs
+    fresh = pv.build_detector(configs.mask2former_r50(True))
+    fresh.load_state_dict(det.state_dict())
+    fresh.cuda()
+    with torch.no_grad():
+        cls_fresh, mask_fresh = fresh.panoptic_head.forward(fresh.extract_feat(frames[0].cuda()), metas)
+        _, mask_after = head.forward(det.extract_feat(frames[0].cuda()), metas)
+    assert torch.equal(cls_fresh[-1], cls_after[-1]) and torch.equal(mask_fresh[-1], mask_after[-1])
 
 
 def test_compat_train_detector_runs_the_reference_schedule(tmp_path):
@@ -534,14 +548,15 @@ def test_compat_train_detector_runs_the_reference_schedule(tmp_path):
         det = pv.build_detector(configs.mask2former_r50(True))
         det.load_state_dict(syn.mask2former_state_dict(seed=4))
         det.panoptic_head.train_cfg = dict(num_points=400, oversample_ratio=3.0, importance_sample_ratio=0.75)
-        assert not any(p.requires_grad for n, p in det.named_parameters() if '.bn' in n or 'downsample.1' in n)
+        assert all(p.requires_grad for n, p in det.named_parameters())         # VPS cfg: norm_cfg.requires_grad=True, norm_eval
         opt = build_optimizer(det, cfg.optimizer)
         by_name = {g['name']: g for g in opt.param_groups}
         assert abs(by_name['backbone.layer1.0.conv1.weight']['lr'] - 1e-5) < 1e-12 and by_name['backbone.conv1.weight']['weight_decay'] == 0.05
         assert by_name['panoptic_head.query_embed.weight']['weight_decay'] == 0.0 and by_name['panoptic_head.query_embed.weight']['lr'] == 1e-4
         assert by_name['panoptic_head.transformer_decoder.layers.0.norms.0.weight']['weight_decay'] == 0.0
         assert by_name['panoptic_head.pixel_decoder.input_convs.0.gn.weight']['weight_decay'] == 0.0
-        assert by_name['panoptic_head.cls_embed.weight']['weight_decay'] == 0.05 and not any('.bn' in n for n in by_name)
+        assert by_name['panoptic_head.cls_embed.weight']['weight_decay'] == 0.05
+        assert abs(by_name['backbone.bn1.weight']['lr'] - 1e-5) < 1e-12 and by_name['backbone.bn1.weight']['weight_decay'] == 0.05   # custom key wins
         out = train_detector(det, [build_dataset(cfg.data.train)], cfg, distributed=False, validate=False, meta=dict(seed=3))
         assert out['iters'] == 9 and all(np.isfinite(out['loss_history']))
         assert np.mean(out['loss_history'][-3:]) < np.mean(out['loss_history'][:3])

@@ -12,7 +12,7 @@ det.load_state_dict(syn.mask2former_state_dict(seed=3))
 det.cuda()
 det.panoptic_head.train_cfg = dict(num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75)
 data = syn.training_batch(clips, H, W, T, device='cuda')
-params = [p for n, p in det.named_parameters() if n.startswith('panoptic_head.') or 'conv' in n or 'downsample.0' in n]
+params = [p for p in det.parameters() if p.requires_grad]
 opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
 def step():
     opt.zero_grad(set_to_none=True)
