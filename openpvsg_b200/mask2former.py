@@ -1286,7 +1286,7 @@ class _DetectorBase(nn.Module):
             log_vars[name] = value.mean() if torch.is_tensor(value) else sum(v.mean() for v in value)
         loss = sum(v for k, v in log_vars.items() if 'loss' in k)
         log_vars['loss'] = loss
-        return loss, {k: float(v) for k, v in log_vars.items()}
+        return loss, {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in log_vars.items()}
 
     def train_step(self, data, optimizer=None):
         """mmdet BaseDetector.train_step: the runner's entry point (``tools/train.py`` -> ``EpochBasedRunner``)."""

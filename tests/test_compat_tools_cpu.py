@@ -125,3 +125,35 @@ def test_test_tool_imports_and_plumbing(compat_path, tmp_path, monkeypatch):
     args = tool.parse_args.__globals__['argparse'].Namespace()      # DictAction parses --cfg-options like mmcv's
     tool.DictAction(['--cfg-options'], 'cfg_options')(None, args, ['a.b=1', 'c=[1,2]', 'd=true', 'e=x'])
     assert args.cfg_options == {'a.b': 1, 'c': [1, 2], 'd': True, 'e': 'x'}
+
+
+@needs_ref
+def test_train_tool_main_runs_unmodified(compat_path, tmp_path, monkeypatch):
+    """tools/train.py main(), unmodified, on the reference's own VPS training config: every import resolves in compat, the
+    config builds the B200 detector and the synthetic training set, and the tool reaches train_detector with them.  The
+    model's train_step is replaced by a recorder (no GPU in this container); train_detector itself -- loader, optimizer
+    groups, schedule, clipping, checkpoint -- is the real compat code (its GPU run: tests/test_training_slice.py)."""
+    tool = _load_tool('train')
+    calls = []
+
+    def fake_train_step(self, data, optimizer=None):
+        assert data['ref_img'].dim() == 5 and data['ref_img'].shape[:2] == (2, 2) and len(data['ref_gt_masks']) == 2
+        assert data['ref_gt_labels'][0].shape[1] == 2 and data['ref_gt_instance_ids'][0].shape == data['ref_gt_labels'][0].shape
+        loss = sum((p ** 2).sum() for n, p in self.named_parameters() if n.endswith('query_feat.weight'))
+        calls.append(float(loss.detach()))
+        return dict(loss=loss, log_vars=dict(loss=float(loss.detach())), num_samples=len(data['img_metas']))
+
+    from openpvsg_b200.mask2former import Mask2FormerVideoCustom
+    monkeypatch.setattr(Mask2FormerVideoCustom, 'train_step', fake_train_step)
+    work = str(tmp_path / 'work')
+    argv = ['train.py', os.path.join(REF, 'configs/mask2former_vps/mask2former_video_r50.py'), '--work-dir', work, '--no-validate',
+            '--seed', '5', '--cfg-options', 'data.train.type=SyntheticVPSDataset', 'data.train.num_frames=4', 'data.train.test_mode=False',
+            'data.samples_per_gpu=2', 'data.workers_per_gpu=0', 'runner.max_epochs=1', 'log_config.interval=1', 'device=cpu',
+            'load_from=None']
+    monkeypatch.setattr(sys, 'argv', argv)
+    monkeypatch.setattr(tool, 'get_device', lambda: 'cpu')
+    tool.main()
+    assert len(calls) == 2                                     # 4 clips / 2 per batch, 1 epoch
+    assert os.path.exists(os.path.join(work, 'epoch_1.pth')) and os.path.exists(os.path.join(work, 'mask2former_video_r50.py'))
+    ck = torch.load(os.path.join(work, 'epoch_1.pth'), map_location='cpu', weights_only=False)
+    assert ck['meta']['seed'] == 5 and len(ck['meta']['CLASSES']) == 126 and ck['meta']['iter'] == 2

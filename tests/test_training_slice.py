@@ -401,7 +401,7 @@ def test_decoder_head_training_step_vs_oracle():
     for c, m, a, l in zip(cls_list, mask_list, apts, lpts):
         lc, lm, ld = head.loss_single(c, m, [gt_labels.cuda()], [gt_masks.cuda()], None, assign_points=a.cuda(),
                                       loss_points=l.cuda(), num_points=K)
-        terms.append((float(lc), float(lm), float(ld)))
+        terms.append((float(lc.detach()), float(lm.detach()), float(ld.detach())))
         total = total + lc + lm + ld
     total.backward()
     # ---- oracle
