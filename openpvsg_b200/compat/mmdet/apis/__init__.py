@@ -109,23 +109,28 @@ def train_detector(model, dataset, cfg, distributed=False, validate=False, times
     """mmdet.apis.train_detector, single process: data loader -> optimizer (build_optimizer) -> EpochBasedRunner /
     IterBasedRunner loop of ``model.train_step`` -> backward -> gradient clipping (``optimizer_config.grad_clip``) ->
     optimizer step, with the step lr policy + linear warm-up, text logging every ``log_config.interval`` iterations and a
-    checkpoint per ``checkpoint_config.interval`` epochs in ``cfg.work_dir``.  Evaluation hooks (``validate``), wandb and
-    multi-process training are outside this floor."""
+    checkpoint per ``checkpoint_config.interval`` epochs in ``cfg.work_dir``.  ``distributed=True``: one process per GPU (the
+    launcher has initialised torch.distributed), a DistributedSampler shards the clips, the weights are broadcast once and the
+    gradients averaged by ``openpvsg_b200.dist_train.allreduce_gradients`` after every backward.  Evaluation hooks
+    (``validate``) and wandb are outside this floor."""
     from mmdet.datasets import build_dataloader
     from mmdet.utils import get_root_logger
-    if distributed:
-        raise NotImplementedError('compat train_detector: single-process training only')
+    from openpvsg_b200 import dist_train
     logger = get_root_logger(log_level=cfg.get('log_level', 'INFO'))
     if validate:
         logger.warning('compat train_detector: evaluation during training is not part of this floor; continuing without it')
     dataset = dataset[0] if isinstance(dataset, (list, tuple)) else dataset
     data_cfg = cfg.get('data', {})
     loader = build_dataloader(dataset, samples_per_gpu=data_cfg.get('samples_per_gpu', 1),
-                              workers_per_gpu=data_cfg.get('workers_per_gpu', 0), shuffle=True, seed=cfg.get('seed'), train=True)
+                              workers_per_gpu=data_cfg.get('workers_per_gpu', 0), shuffle=True, seed=cfg.get('seed'), train=True,
+                              dist=distributed)
     device = cfg.get('device', 'cuda')
     model.to(device)
     model.train()
+    if distributed:                          # one process per GPU: same start, clips sharded by the sampler, gradients averaged
+        dist_train.broadcast_parameters(model)
     optimizer = build_optimizer(model, cfg.optimizer)
+    bucket = None
     clip = (cfg.get('optimizer_config') or {}).get('grad_clip')
     runner_cfg = cfg.get('runner') or dict(type='EpochBasedRunner', max_epochs=cfg.get('total_epochs', 1))
     by_epoch = runner_cfg.get('type', 'EpochBasedRunner') == 'EpochBasedRunner'
@@ -137,6 +142,8 @@ def train_detector(model, dataset, cfg, distributed=False, validate=False, times
     it, history = 0, []
     t0 = time.time()
     for epoch in range(max_epochs):
+        if distributed and hasattr(loader.sampler, 'set_epoch'):
+            loader.sampler.set_epoch(epoch)
         for data in loader:
             factor = _lr_factor(cfg.get('lr_config'), epoch, it)
             for g in optimizer.param_groups:
@@ -145,6 +152,8 @@ def train_detector(model, dataset, cfg, distributed=False, validate=False, times
             optimizer.zero_grad(set_to_none=True)
             out = model.train_step(data, optimizer)
             out['loss'].backward()
+            if distributed:
+                bucket = dist_train.allreduce_gradients(params, bucket)
             grad_norm = None
             if clip:
                 grad_norm = float(torch.nn.utils.clip_grad_norm_(params, clip['max_norm'], clip.get('norm_type', 2)))
@@ -156,7 +165,8 @@ def train_detector(model, dataset, cfg, distributed=False, validate=False, times
                             f'grad_norm: {grad_norm}, time: {(time.time() - t0) / it:.3f} s/iter')
             if it >= max_iters:
                 break
-        if ckpt is not None and by_epoch and (epoch + 1) % ckpt.get('interval', 1) == 0 and cfg.get('work_dir'):
+        if ckpt is not None and by_epoch and (epoch + 1) % ckpt.get('interval', 1) == 0 and cfg.get('work_dir') and \
+                (not distributed or dist_train.dist.get_rank() == 0):
             os.makedirs(cfg.work_dir, exist_ok=True)
             torch.save(dict(meta=dict(ckpt.get('meta', {}) or {}, epoch=epoch + 1, iter=it, **(meta or {})),
                             state_dict=model.state_dict(), optimizer=optimizer.state_dict()),

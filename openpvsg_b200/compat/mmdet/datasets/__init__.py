@@ -34,12 +34,15 @@ def _collate_train(batch):
 
 def build_dataloader(dataset, samples_per_gpu=1, workers_per_gpu=0, num_gpus=1, dist=False, shuffle=False, seed=None,
                      persistent_workers=False, train=False, **kwargs):
-    sampler = DistributedSampler(dataset, shuffle=False) if dist else None
     if train:
         gen = torch.Generator()
         gen.manual_seed(int(seed) if seed is not None else 0)
+        if dist:
+            return DataLoader(dataset, batch_size=samples_per_gpu, sampler=DistributedSampler(dataset, shuffle=shuffle, seed=int(seed or 0)),
+                              num_workers=workers_per_gpu, collate_fn=_collate_train, drop_last=False)
         return DataLoader(dataset, batch_size=samples_per_gpu, shuffle=shuffle, generator=gen, num_workers=workers_per_gpu,
                           collate_fn=_collate_train, drop_last=False)
+    sampler = DistributedSampler(dataset, shuffle=False) if dist else None
     return DataLoader(dataset, batch_size=samples_per_gpu, sampler=sampler, shuffle=False, num_workers=workers_per_gpu,
                       collate_fn=_collate, pin_memory=torch.cuda.is_available(),
                       persistent_workers=persistent_workers and workers_per_gpu > 0)

@@ -118,6 +118,17 @@ def get_uncertain_point_coords_with_randomness(mask_pred, labels, num_points, ov
     return picked
 
 
+def reduce_mean(value, device):
+    """mmdet.core.reduce_mean (mask2former_video_head.py:246): the positive count averaged over the ranks, so that every
+    rank normalises its mask losses by the same factor; the identity in a single process."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float32, device=device)
+    dist.all_reduce(t)
+    return float(t.item()) / dist.get_world_size()
+
+
 def hungarian_assign(cls_score, mask_points_pred, gt_labels, gt_points_masks, w_cls=2.0, w_mask=5.0, w_dice=5.0, eps=1.0):
     """mmdet MaskHungarianAssigner.assign + MaskPseudoSampler: -> (pos_inds, pos_assigned_gt_inds) int64, sorted by query."""
     from scipy.optimize import linear_sum_assignment
@@ -158,7 +169,7 @@ def loss_single(cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas
     loss_cls = _WeightedCE.apply(cls_scores.flatten(0, 1), labels.flatten(), class_weight, None, loss_weights[0])
     mask_pos = torch.cat(pos_pred, 0)
     mask_targets = torch.cat(pos_tgt, 0)
-    num_total_masks = max(float(mask_pos.shape[0]), 1.0)
+    num_total_masks = max(reduce_mean(float(mask_pos.shape[0]), dev), 1.0)
     if mask_targets.shape[0] == 0:
         zero = mask_pos.sum()
         return loss_cls, zero, zero

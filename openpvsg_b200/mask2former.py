@@ -911,14 +911,39 @@ class _Mask2FormerHeadBase(_Prepared):
             masks_out.append(torch.stack(things).long())
         return labels_out, masks_out
 
+    def preprocess_gt_image(self, gt_labels_list, gt_masks_list, gt_semantic_segs, img_metas):
+        """mmdet MaskFormerHead.preprocess_gt -> ``preprocess_panoptic_gt`` (mmdet 2.25 models/utils/panoptic_gt_processing.py,
+        called from mask2former_head.py:519): per image, the instance masks padded to pad_shape, followed by one mask per
+        stuff class present in the semantic map (labels in [num_things, num_classes); 255 = void).  Index bookkeeping."""
+        if gt_semantic_segs is None:
+            gt_semantic_segs = [None] * len(gt_labels_list)
+        labels_out, masks_out = [], []
+        for labels, gm, sem, meta in zip(gt_labels_list, gt_masks_list, gt_semantic_segs, img_metas):
+            dev = labels.device
+            ph, pw = meta['pad_shape'][:2]
+            if hasattr(gm, 'pad'):
+                things = gm.pad((ph, pw), pad_val=0).to_tensor(dtype=torch.bool, device=dev)
+            else:
+                things = torch.nn.functional.pad(gm.to(dev).bool(), (0, pw - gm.shape[-1], 0, ph - gm.shape[-2]))
+            if sem is not None:
+                sem = sem.to(dev).squeeze(0)
+                stuff = [c for c in torch.unique(sem).tolist() if self.num_things_classes <= c < self.num_classes]
+                if stuff:
+                    things = torch.cat([things, torch.stack([sem == c for c in stuff])], 0)
+                    labels = torch.cat([labels, torch.tensor(stuff, dtype=labels.dtype, device=dev)], 0)
+            labels_out.append(labels.long())
+            masks_out.append(things.long())
+        return labels_out, masks_out
+
     def forward_train(self, feats, img_metas, gt_bboxes, gt_labels, gt_masks, gt_semantic_seg=None, gt_instance_ids=None,
                       gt_bboxes_ignore=None):
         """mask2former_video_head.py:464-522 (``loss_sem_seg=None``, the shipped configs): forward -> preprocess_gt ->
         loss.  Returns the reference's loss dict; ``.backward()`` on its sum fills the gradients of the decoder head."""
         assert gt_bboxes_ignore is None
-        if not self.video:
-            raise NotImplementedError('forward_train of the image head: preprocess_panoptic_gt (things + stuff from the '
-                                      'semantic map) is not built; use forward_train_outputs + loss with prepared targets')
+        if not self.video:         # mask2former_head.py:481-523: (feats, img_metas, gt_bboxes, gt_labels, gt_masks, gt_semantic_seg)
+            all_cls_scores, all_mask_preds = self.forward_train_outputs(feats, 1)
+            labels, masks = self.preprocess_gt_image(gt_labels, gt_masks, gt_semantic_seg, img_metas)
+            return self.loss(all_cls_scores, all_mask_preds, labels, masks, img_metas)
         num_frames = len(img_metas[0])
         all_cls_scores, all_mask_preds = self.forward_train_outputs(feats, num_frames)
         labels, masks = self.preprocess_gt(gt_labels, gt_masks, gt_semantic_seg, gt_instance_ids, img_metas)
@@ -1277,7 +1302,7 @@ class _DetectorBase(nn.Module):
         return self.backbone(img)
 
     def forward_train(self, *a, **k):
-        raise NotImplementedError('forward_train is built for the video (VPS) detector only: Mask2FormerVideoCustom')
+        raise NotImplementedError('forward_train: Mask2FormerCustom (image) and Mask2FormerVideoCustom (video) implement it')
 
     def _parse_losses(self, losses):
         """mmdet BaseDetector._parse_losses (single process: no all_reduce): -> (total loss, log_vars)."""
@@ -1307,6 +1332,20 @@ class _DetectorBase(nn.Module):
 @DETECTORS.register_module()
 class Mask2FormerCustom(_DetectorBase):
     """models/mask2former/mask2former.py:14 (image panoptic segmentation)."""
+    train_backbone = True
+
+    def forward_train(self, img, img_metas, gt_bboxes=None, gt_labels=None, gt_masks=None, gt_semantic_seg=None,
+                      gt_bboxes_ignore=None, **kwargs):
+        """models/mask2former/mask2former.py:75-116."""
+        for m in img_metas:
+            m['batch_input_shape'] = tuple(img.shape[-2:])
+        if self.train_backbone and hasattr(self.backbone, 'forward_train'):
+            x = self.backbone.forward_train(img)
+        else:
+            with torch.no_grad():
+                x = self.extract_feat(img)
+        return self.panoptic_head.forward_train(x, img_metas, gt_bboxes, gt_labels, gt_masks, gt_semantic_seg,
+                                                gt_bboxes_ignore=gt_bboxes_ignore)
 
     def forward_test(self, imgs, img_metas, **kwargs):
         """mmdet BaseDetector.forward_test (single augmentation): adds batch_input_shape."""

@@ -30,9 +30,6 @@ def test_build_and_strict_load(video):
     assert not res.missing_keys and not res.unexpected_keys
     assert not det.training
     assert det.train().training and not det.eval().training     # mode flag only: no batch statistics, no dropout
-    if not video:
-        with pytest.raises(NotImplementedError):
-            det.forward_train(None, None)                       # training is built for the VPS detector
     with pytest.raises(NotImplementedError):
         det.aug_test(None, None)
     with pytest.raises(KeyError):

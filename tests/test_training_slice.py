@@ -568,3 +568,61 @@ def test_compat_train_detector_runs_the_reference_schedule(tmp_path):
         for k in [m for m in sys.modules if m.split('.')[0] in ('mmcv', 'mmdet', 'datasets', 'models', 'utils')]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_image_detector_forward_train():
+    """Mask2FormerCustom.forward_train (models/mask2former/mask2former.py:75-116): instance masks + the stuff classes of the
+    semantic map become the targets (preprocess_panoptic_gt), the 30-term loss dict comes back, every parameter receives a
+    gradient, and the image head's outputs / losses equal the oracle's (non-video head_forward + loss_single)."""
+    import openpvsg_b200 as pv
+    from openpvsg_b200 import configs, synthetic as syn
+    from oracle import losses as ol, m2f as om
+    det = pv.build_detector(configs.mask2former_r50(False))
+    sd = syn.mask2former_state_dict(seed=6)
+    det.load_state_dict(sd)
+    det.cuda()
+    H, W = 96, 160
+    img = torch.stack([syn.synthetic_frame(s, H, W) for s in (1, 2)]).cuda()
+    metas = [dict(syn.frame_meta(H, W), pad_shape=(H, W, 3)) for _ in range(2)]
+    head = det.panoptic_head
+    head.train_cfg = dict(num_points=300, oversample_ratio=3.0, importance_sample_ratio=0.75)
+    things = torch.zeros(2, 2, H, W, dtype=torch.bool)
+    things[:, 0, 10:50, 20:90] = True
+    things[:, 1, 40:90, 70:150] = True
+    sem = torch.full((2, 1, H, W), 255, dtype=torch.int64)
+    sem[:, :, :, :40] = 120                                 # a stuff class (>= num_things = 115)
+    sem[:, :, 60:, 100:] = 3                                # a thing class in the semantic map: ignored
+    labels, masks = head.preprocess_gt_image([torch.tensor([4, 9]).cuda()] * 2, list(things.cuda()), list(sem.cuda()), metas)
+    assert labels[0].tolist() == [4, 9, 120] and masks[0].shape == (3, H, W) and int(masks[0][2].sum()) == H * 40
+    assert not any(p.requires_grad for n, p in det.named_parameters() if '.bn' in n or 'downsample.1' in n)   # image cfg: BN frozen
+    torch.manual_seed(1)
+    losses = det(img=img, img_metas=metas, gt_bboxes=None, gt_labels=[torch.tensor([4, 9]).cuda()] * 2, gt_masks=list(things.cuda()),
+                 gt_semantic_seg=list(sem.cuda()))
+    assert len(losses) == 30 and all(torch.isfinite(v) for v in losses.values())
+    loss, log_vars = det._parse_losses(losses)
+    loss.backward()
+    missing = [n for n, p in det.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:5]
+    # forward outputs + one loss_single vs the oracle (fixed point sets)
+    with torch.no_grad():
+        feats = det.extract_feat(img)
+    head._capture_masks = []
+    try:
+        cls_list, mask_list = head.forward_train_outputs(feats, 1)
+    finally:
+        captured, head._capture_masks = head._capture_masks, None
+    assert mask_list[-1].dim() == 4
+    osd = {k: v.float() for k, v in sd.items()}
+    with torch.no_grad():
+        ocls, omask, _, ex = om.head_forward(osd, om.resnet50(osd, img.cpu()), video=False, return_all=True,
+                                             tie_masks=[m.cpu() for m in captured])
+    assert not [s for s in ex['tie_stats'] if s['flipped_non_ties']]
+    _close(cls_list[-1], ocls[-1], 1e-3, 'image head cls')
+    _close(mask_list[-1], omask[-1], 1e-3, 'image head masks')
+    g = torch.Generator().manual_seed(2)
+    a, l = torch.rand(1, 300, 2, generator=g), torch.rand(6, 300, 2, generator=g)
+    got = head.loss_single(cls_list[-1], mask_list[-1], labels, [m.float() for m in masks], None, assign_points=a.cuda(), loss_points=l.cuda(),
+                           num_points=300)
+    want = ol.loss_single(ocls[-1], omask[-1][:, None], [t.cpu() for t in labels], [m.cpu().float()[:, None] for m in masks], a, lambda n: l[:n])
+    for x, y, n in zip(got, want[:3], ('loss_cls', 'loss_mask', 'loss_dice')):
+        _close(x, y, 5e-4, n)

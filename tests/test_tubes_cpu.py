@@ -207,6 +207,64 @@ def test_minvis_link_sharded_world2_gloo():
             assert np.array_equal(perms, ref), rank
 
 
+def _grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from openpvsg_b200 import dist_train
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(rank)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    model[1].bias.requires_grad_(False)
+    dist_train.broadcast_parameters(model)                         # every rank now holds rank 0's weights
+    start = [p.detach().clone() for p in model.parameters()]
+    x = torch.full((4, 5), float(rank + 1))
+    if rank == 0:
+        model(x).sum().backward()
+    else:                                                          # this rank's batch does not touch layer 1
+        model[0](x).sum().backward()
+    bucket = dist_train.allreduce_gradients(list(model.parameters()))
+    bucket2 = dist_train.allreduce_gradients(list(model.parameters()), bucket)     # reusable buffer, idempotent on equal grads
+    q.put((rank, [t.numpy() for t in start], [None if p.grad is None else p.grad.numpy() for p in model.parameters()],
+           bucket2.data_ptr() == bucket.data_ptr()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    """dist_train: weights broadcast from rank 0, gradients averaged over the ranks through one flat bucket; a parameter
+    without a gradient on one rank contributes zeros, frozen parameters are left alone."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, w0, g0, same0), (_, w1, g1, same1) = got
+    assert same0 and same1
+    for a, b in zip(w0, w1):
+        assert np.array_equal(a, b)
+    assert g0[3] is None and g1[3] is None                         # frozen bias: untouched
+    for a, b in zip(g0[:3], g1[:3]):
+        assert np.array_equal(a, b)                                # both ranks hold the same averaged gradients
+    # reference: the mean of the two ranks' gradients computed in one process
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    with torch.no_grad():
+        for p, w in zip(model.parameters(), w0):
+            p.copy_(torch.from_numpy(w))
+    model(torch.full((4, 5), 1.0)).sum().backward()
+    ga = [p.grad.clone() for p in list(model.parameters())[:3]]
+    model.zero_grad()
+    model[0](torch.full((4, 5), 2.0)).sum().backward()
+    gb = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in list(model.parameters())[:3]]
+    for a, b, got_g in zip(ga, gb, g0[:3]):
+        assert np.allclose((a + b).numpy() / 2, got_g, atol=1e-6)
+
+
 def test_rle_events_host_side_matches_scalar_encoder():
     """tubes.rle_from_events / rle_string_np (host side of the device RLE encoder, pvsg_rle_events)
     against the scalar pycocotools-style encoder, including a segment that owns pixel 0, an absent
