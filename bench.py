@@ -650,7 +650,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=240))   # fail fast on a lost rank
 
     import openpvsg_b200 as pv
     from openpvsg_b200 import configs, engine, lib, synthetic as syn, tubes
@@ -781,6 +782,15 @@ def main():
         except Exception as ex:
             extra['swin_b_clip'] = dict(error=repr(ex))
 
+    # ---- SURVEY 8f rank 4 at this N: data-parallel training step (every rank takes part: gradient all-reduce)
+    if not swin:
+        try:
+            extra['training_step'] = training_bench(dev, not args.no_cpu_baseline and world == 1, world=world, rank=rank)
+        except Exception as ex:
+            if world > 1:
+                raise                      # a rank that drops out of a collective would hang the others
+            extra['training_step'] = dict(error=repr(ex))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -852,11 +862,6 @@ def main():
         extra['relation_head'] = relation_bench(dev, not args.no_cpu_baseline)
     except Exception as ex:
         extra['relation_head'] = dict(error=repr(ex))
-    try:
-        if not swin:
-            extra['training_step'] = training_bench(dev, not args.no_cpu_baseline and world == 1, world=world, rank=rank)
-    except Exception as ex:
-        extra['training_step'] = dict(error=repr(ex))
     try:
         extra['relation_set'] = relset_bench(dev, not args.no_cpu_baseline)
         extra['relation_set']['frac_hbm'] = round(extra['relation_set']['achieved_GBps'] / peaks['hbm_gbs'], 4)
