@@ -68,3 +68,28 @@ def test_reference_config_file_builds_unmodified():
     ips = pv.load_config('/root/reference/configs/mask2former/'
                          'mask2former_r50_lsj_8x2_50e_coco-panoptic_custom_single_video_test.py')
     assert type(pv.build_detector(ips['model'])).__name__ == 'Mask2FormerCustom'
+
+
+def test_preprocess_gt_matches_reference_golden():
+    """Mask2FormerVideoHead.preprocess_gt against the reference's own preprocess_video_panoptic_gt (golden vectors written
+    by tests/golden/make_golden_train_gt.py from models/mask2former_vps/utils.py:94-140): instance order, labels, per-frame
+    masks, empty masks for frames without the instance, padding to pad_shape.  Pure index work: runs on the CPU."""
+    import json
+    import os
+    import torch
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'train_gt.json')))
+    head = pv.build_detector(configs.mask2former_r50(True)).panoptic_head
+    for c in golden:
+        metas = [dict(pad_shape=(c['pad'][0], c['pad'][1], 3)) for _ in c['masks']]
+        labels, masks = head.preprocess_gt([torch.tensor(c['labels'])], [[torch.tensor(m, dtype=torch.uint8) for m in c['masks']]], None,
+                                           [torch.tensor(c['ids'])], [metas])
+        assert labels[0].tolist() == c['out_labels'] and labels[0].dtype == torch.int64
+        assert masks[0].tolist() == c['out_masks'] and masks[0].dtype == torch.int64
+    # a clip batch of two: one result per clip, in order
+    a, b = golden[0], golden[1]
+    labels, masks = head.preprocess_gt([torch.tensor(a['labels']), torch.tensor(b['labels'])],
+                                       [[torch.tensor(m, dtype=torch.uint8) for m in a['masks']], [torch.tensor(m, dtype=torch.uint8) for m in b['masks']]],
+                                       None, [torch.tensor(a['ids']), torch.tensor(b['ids'])],
+                                       [[dict(pad_shape=(a['pad'][0], a['pad'][1], 3))] * len(a['masks']),
+                                        [dict(pad_shape=(b['pad'][0], b['pad'][1], 3))] * len(b['masks'])])
+    assert labels[1].tolist() == b['out_labels'] and masks[0].tolist() == a['out_masks']
