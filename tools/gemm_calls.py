@@ -105,3 +105,10 @@ tot = sum(r[0] for r in rows)
 print(f'batch {B}: {len(calls)} calls, {len(rows)} shapes, total {tot:.0f} us = {tot / B:.0f} us/frame')
 for t, n, us, tf, gbs, s in rows[:40]:
     print(f'{t:8.0f} us  x{n:<3d} {us:7.1f} us/call {tf:6.0f} TF {gbs:6.0f} GB/s  {s}')
+if len(sys.argv) > 1:
+    json.dump(dict(source=f'tools/gemm_calls.py, PROBE_BATCH={B}: every distinct dense call of one {B}-frame 720p forward replayed alone in '
+                          'a CUDA graph (warm L2); TF = algorithmic 2MNK flops / time (split-bf16 ceiling 469 TF), GB/s = operand '
+                          'planes + outputs + residual bytes / time (HBM peak 6539 GB/s)',
+                   total_us=round(tot, 1), us_per_frame=round(tot / B, 1),
+                   shapes=[dict(total_us=round(t, 1), calls=n, us_per_call=round(us, 1), tflops=round(tf, 1), gbps=round(gbs, 1), shape=s)
+                           for t, n, us, tf, gbs, s in rows]), open(sys.argv[1], 'w'), indent=1)
