@@ -63,7 +63,8 @@ extern "C" int pvsg_create(int device, pvsg_handle** out) {
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     using namespace pvsg_internal;
     int (*const units[])() = {configure_gemm_tc,  configure_gemm_skinny, configure_attention_t5, configure_attention_mma,
-                              configure_msda_tile, configure_panoptic,   configure_overlap,      configure_swin};
+                              configure_msda_tile, configure_panoptic,   configure_overlap,      configure_swin,
+                              configure_relation};
     for (auto f : units)
         if (const int rc = f()) return rc;
     auto* h = new (std::nothrow) pvsg_handle{device, sms, (int64_t)optin, nullptr, 0};

@@ -37,6 +37,7 @@ int configure_gemm_skinny();
 int configure_msda_tile();
 int configure_overlap();
 int configure_panoptic();
+int configure_relation();
 int configure_swin();
 }  // namespace pvsg_internal
 

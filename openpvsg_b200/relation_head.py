@@ -28,18 +28,21 @@ class _EncoderLayer(nn.Module):
         self.nhead = nhead
 
     @torch.no_grad()
-    def forward_tokens(self, x, seq_axis):
+    def forward_tokens(self, x, seq_axis, x_planes=None, want_planes=False):
         """x [A, B, E] contiguous; attention runs over axis ``seq_axis`` independently for every
         index of the other axis.  All row-wise layers work on the flat [A*B, E] view, and the
         attention kernel takes the (batch, sequence) structure through strides, so neither
-        orientation needs a transpose."""
+        orientation needs a transpose.  x_planes: operand planes of x when the producer emitted them;
+        want_planes: also return the planes of the result (-> (y, planes)).  The LayerNorms and the FFN
+        hand planes to their consumers, so the only split pass left in a layer is the attention output."""
         A, Bx, E = x.shape
         a = self.self_attn
         if not x.is_contiguous():
             raise ops._l.PvsgError('encoder layer: contiguous [A,B,E] expected')
         o = torch.empty(A, Bx, E, device=x.device, dtype=torch.float32)
         tc = E // self.nhead in (32, 128)  # tensor-core attention on the projection's planes
-        res = ops.linear(x.view(A * Bx, E), a.in_proj_weight, a.in_proj_bias, out_mode='both' if tc else 'f32')
+        res = ops.linear(x_planes.view(A * Bx, E) if x_planes is not None else x.view(A * Bx, E), a.in_proj_weight, a.in_proj_bias,
+                         out_mode='both' if tc else 'f32')
         qkv, planes = res if tc else (res, None)
         qkv = qkv.view(A, Bx, 3 * E)
         qv, ov = (qkv.permute(1, 0, 2), o.permute(1, 0, 2)) if seq_axis == 0 else (qkv, o)
@@ -52,10 +55,11 @@ class _EncoderLayer(nn.Module):
         else:
             ops.attention(qv[..., :E], qv[..., E:2 * E], qv[..., 2 * E:], self.nhead, out=ov)
         y = ops.linear(o, a.out_proj.weight, a.out_proj.bias, residual=x)
-        y = ops.layernorm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        h = ops.linear(y, self.linear1.weight, self.linear1.bias, act=ops.ACT_RELU)
+        y, ys = ops.layernorm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, out_split=True)
+        h = ops.linear(ys if ys is not None else y, self.linear1.weight, self.linear1.bias, act=ops.ACT_RELU, out_mode='split')
         z = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=y)
-        return ops.layernorm(z, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        z, zs = ops.layernorm(z, self.norm2.weight, self.norm2.bias, self.norm2.eps, out_split=True)
+        return (z, zs) if want_planes else z
 
 
 class _Encoder(nn.Module):
@@ -82,9 +86,9 @@ class ObjectEncoder(_Inference):
 
     @torch.no_grad()
     def forward(self, x):
-        y = x.contiguous()
+        y, ys = x.contiguous(), None
         for layer in self.transformer_encoder.layers:
-            y = layer.forward_tokens(y, seq_axis=0)   # sequence = tubes, batch = frames
+            y, ys = layer.forward_tokens(y, 0, ys, want_planes=True)   # sequence = tubes, batch = frames
         return y
 
 
@@ -127,8 +131,8 @@ class PositionalEncoding(nn.Module):
 def _heads(mod, x):
     """fc1/fc2/span_head/pred_head tail shared by all relation models (base.py:16-23)."""
     P, T, _ = x.shape
-    h = ops.linear(x, mod.fc1.weight, mod.fc1.bias, act=ops.ACT_RELU)
-    h = ops.linear(h, mod.fc2.weight, mod.fc2.bias, act=ops.ACT_RELU)
+    h = ops.linear(x, mod.fc1.weight, mod.fc1.bias, act=ops.ACT_RELU, out_mode='split')     # hidden layers as planes only
+    h = ops.linear(h, mod.fc2.weight, mod.fc2.bias, act=ops.ACT_RELU, out_mode='split')
     span_pred = ops.linear(h, mod.span_head.weight, mod.span_head.bias)
     rel = ops.linear(h, mod.pred_head.weight, mod.pred_head.bias)
     return span_pred, ops.max_over_time(rel)
@@ -152,10 +156,11 @@ class TemporalTransformer(_Inference):
 
     @torch.no_grad()
     def _encode(self, x):
+        xs = None
         for layer in self.transformer_encoder.layers:
-            x = layer.forward_tokens(x, seq_axis=1)   # sequence = frames, batch = pairs
-        x = ops.layernorm(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
-        return _heads(self, x)
+            x, xs = layer.forward_tokens(x, 1, xs, want_planes=True)   # sequence = frames, batch = pairs
+        x, xs = ops.layernorm(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, out_split=True)
+        return _heads(self, xs if xs is not None else x)
 
     @torch.no_grad()
     def forward(self, x):
