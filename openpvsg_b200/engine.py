@@ -17,6 +17,7 @@ an event record.  ``submit`` returns immediately; ``collect`` waits for that bat
 and builds the reference's result dicts, so the host-side work of batch i overlaps the
 device work of batch i+1 (``Mask2FormerVideoCustom.simple_test`` = submit + collect, batch 1).
 """
+import os
 import numpy as np
 import torch
 
@@ -25,6 +26,7 @@ from . import ops
 from .mask2former import INSTANCE_OFFSET, bbox2result
 
 RING = 3
+SYNC_CHUNKS = int(os.environ.get('PVSG_SYNC_CHUNKS', '2'))   # pieces a synchronous multi-sample call is pipelined in (simple_test)
 DEBUG_MASKS = False   # parity tests: every runner also returns the decoder's sign masks and class logits
 _copy_pool = None
 

@@ -1437,8 +1437,21 @@ class Mask2FormerVideoCustom(_DetectorBase):
                 runner = get_runner(self, metas[0], kwargs.get('rescale', False))
                 return [[runner.run(ref_img)]]
             if all(key(d) == key(metas[0]) for d in metas):
-                runner = get_runner(self, metas[0], kwargs.get('rescale', False), batch=bs)
-                return [[r] for r in runner.collect(runner.submit([ref_img[i, 0] for i in range(bs)]))]
+                # one synchronous call, pipelined inside: the batch goes through the runner in SYNC_CHUNKS pieces, so the
+                # host->device copy of piece i+1 and the device->host copy + result building of piece i-1 overlap the
+                # graph replay of piece i (the call still returns only when every result is on the host)
+                from . import engine
+                chunks = engine.SYNC_CHUNKS if bs >= 4 * engine.SYNC_CHUNKS and bs % engine.SYNC_CHUNKS == 0 else 1
+                per = bs // chunks
+                runner = get_runner(self, metas[0], kwargs.get('rescale', False), batch=per)
+                out, queue = [], []
+                for c in range(chunks):
+                    queue.append(runner.submit([ref_img[i, 0] for i in range(c * per, (c + 1) * per)]))
+                    if len(queue) == 2:
+                        out += runner.collect(queue.pop(0))
+                while queue:
+                    out += runner.collect(queue.pop(0))
+                return [[r] for r in out]
         video_x = self.extract_feat(ref_img.reshape(bs * num_frame, three, h, w))
         results = [[] for _ in range(bs)]
         for i in range(bs):
