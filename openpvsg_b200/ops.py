@@ -17,7 +17,16 @@ from . import lib as _l
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_raw_device = getattr(torch._C, '_cuda_getDevice', None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device.  torch.cuda.current_stream() costs ~15 us of Python
+    per call (device-index resolution, Stream object): 4400 library calls of a training step paid 65 ms for it; the raw
+    accessor is ~0.3 us."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -39,3 +39,12 @@ if os.environ.get('PROFILE'):
         step()
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=28, max_name_column_width=60))
+if os.environ.get('CPROFILE'):
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
