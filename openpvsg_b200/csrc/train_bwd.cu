@@ -410,20 +410,33 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
     // tile: 64 source rows x 32 channels.  Loads: a warp reads the 32 channels of one row (128 B).  Stores: a warp writes
     // 64 consecutive columns of one channel row as bf16x2 (128 B); rows beyond T are written as zeros (ldt >= ceil64(T)).
     __shared__ float tile[64][33];
+    __shared__ int64_t row_off[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * 64;
     const int c0 = blockIdx.y * 32;
-    const int64_t hw = (int64_t)OH * OW;
+    if (threadIdx.x < 64) {            // one (b, oh, ow) decomposition per source row, 32-bit when it fits
+        const int64_t r = r0 + threadIdx.x;
+        int64_t off = -1;
+        if (r < T) {
+            if (T < (1LL << 31)) {
+                const unsigned ru = (unsigned)r, hw = (unsigned)(OH * OW), b = ru / hw, rem = ru - b * hw, oh = rem / (unsigned)OW;
+                off = (int64_t)b * sb + (int64_t)oh * sh + (int64_t)(rem - oh * (unsigned)OW) * sw;
+            } else {
+                const int64_t hw = (int64_t)OH * OW, b = r / hw, rem = r - b * hw;
+                off = b * sb + (rem / OW) * sh + (rem % OW) * sw;
+            }
+        }
+        row_off[threadIdx.x] = off;
+    }
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = warp + 8 * i;
-        const int64_t r = r0 + row;
+        const int64_t off = row_off[row];
         float v = 0.f;
-        if (r < T && c0 + lane < C) {
-            const int64_t b = r / hw, rem = r - b * hw;
-            const int64_t off = b * sb + (rem / OW) * sh + (rem % OW) * sw + c0 + lane;
-            v = x[off];
-            if (add) v += add[off];
+        if (off >= 0 && c0 + lane < C) {
+            v = x[off + c0 + lane];
+            if (add) v += add[off + c0 + lane];
         }
         tile[row][lane] = v;
     }
