@@ -153,22 +153,49 @@ def loss_single(cls_scores, mask_preds, gt_labels_list, gt_masks_list, img_metas
     if class_weight is None:
         class_weight = torch.ones(num_classes + 1, device=dev)
         class_weight[-1] = 0.1
+    from scipy.optimize import linear_sum_assignment
     labels = torch.full((B, Q), num_classes, dtype=torch.int64, device=dev)
-    pos_pred, pos_tgt = [], []
+    # phase 1 (device, no host round trip): sampled points and the assignment cost matrix of every clip
+    all_pred = mask_preds.transpose(2, 1).flatten(2, 3)                         # [B, Q, T*h, w] (one copy, on the tape)
+    preds, gts, costs = [], [], []
     for b in range(B):
-        gt_masks = gt_masks_list[b].float().flatten(1, 2)                       # [G, T*h, w]: frames as one long image
-        mask_pred = mask_preds[b].transpose(1, 0).flatten(1, 2)                 # [Q, T*h, w]
+        g = gt_masks_list[b]
+        gt_masks = (g if g.is_floating_point() else g.float()).flatten(1, 2)    # [G, T*h, w]: frames as one long image
+        mask_pred = all_pred[b]                                                 # [Q, T*h, w]
+        preds.append(mask_pred)
+        gts.append(gt_masks)
+        if gt_masks.shape[0] == 0:
+            costs.append(None)
+            continue
         pts = assign_points if assign_points is not None else torch.rand(1, num_points, 2, device=dev, generator=generator)
         pred_pts = ops.point_sample(mask_pred.detach().contiguous(), pts[0])
-        gt_pts = ops.point_sample(gt_masks.contiguous(), pts[0]) if gt_masks.shape[0] else gt_masks.new_zeros(0, pts.shape[1])
-        pos_inds, gt_inds = hungarian_assign(cls_scores[b].detach(), pred_pts, gt_labels_list[b], gt_pts,
-                                             loss_weights[0], loss_weights[1], loss_weights[2])
-        labels[b, pos_inds] = gt_labels_list[b][gt_inds]
-        pos_pred.append(mask_pred[pos_inds])
-        pos_tgt.append(gt_masks[gt_inds])
+        gt_pts = ops.point_sample(gt_masks.contiguous(), pts[0])
+        costs.append(ops.mask_match_cost(cls_scores[b].detach(), gt_labels_list[b], pred_pts, gt_pts, *loss_weights, 1.0))
+    # phase 2: ONE device->host transfer of all cost matrices, the assignments on the host (scipy, as mmdet's
+    # MaskHungarianAssigner + MaskPseudoSampler), ONE transfer of the index lists back
+    pos_flat, gt_flat, n_gt = [], [], 0
+    if any(c is not None for c in costs):
+        host = torch.cat([c.reshape(-1) for c in costs if c is not None]).cpu().numpy()
+        off = 0
+        for b in range(B):
+            G = gts[b].shape[0]
+            if costs[b] is not None:
+                rows, cols = linear_sum_assignment(host[off:off + Q * G].reshape(Q, G))
+                off += Q * G
+                order = np.argsort(rows)
+                pos_flat.append(b * Q + rows[order])
+                gt_flat.append(n_gt + cols[order])
+            n_gt += G
+    if pos_flat:
+        idx = torch.as_tensor(np.stack([np.concatenate(pos_flat), np.concatenate(gt_flat)]), device=dev)
+        pos_idx, gt_idx = idx[0], idx[1]
+        labels.view(-1)[pos_idx] = torch.cat(list(gt_labels_list))[gt_idx]
+        mask_pos = all_pred.flatten(0, 1)[pos_idx]                              # [n_pos, T*h, w]
+        mask_targets = torch.cat(gts, 0)[gt_idx] if len(gts) > 1 else gts[0][gt_idx]
+    else:
+        mask_pos = preds[0][:0]
+        mask_targets = gts[0][:0]
     loss_cls = _WeightedCE.apply(cls_scores.flatten(0, 1), labels.flatten(), class_weight, None, loss_weights[0])
-    mask_pos = torch.cat(pos_pred, 0)
-    mask_targets = torch.cat(pos_tgt, 0)
     num_total_masks = max(reduce_mean(float(mask_pos.shape[0]), dev), 1.0)
     if mask_targets.shape[0] == 0:
         zero = mask_pos.sum()

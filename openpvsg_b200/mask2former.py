@@ -965,6 +965,7 @@ class _Mask2FormerHeadBase(_Prepared):
     def loss(self, all_cls_scores, all_mask_preds, gt_labels_list, gt_masks_list, img_metas=None):
         """mask2former_video_head.py:524-634, the default (loss_split_th_st=False) branch: loss_single per decoder layer,
         the last layer under the plain names, earlier ones as d{i}.loss_*."""
+        gt_masks_list = [g if g.is_floating_point() else g.float() for g in gt_masks_list]     # once, not per decoder layer
         per_layer = [self.loss_single(c, m, gt_labels_list, gt_masks_list, img_metas)
                      for c, m in zip(all_cls_scores, all_mask_preds)]
         out = dict(loss_cls=per_layer[-1][0], loss_mask=per_layer[-1][1], loss_dice=per_layer[-1][2])
