@@ -619,3 +619,58 @@ class MaskAssociationTracker(AssociationTracker):
         boxes = mask2box(masks)
         keep_idx = remove_duplicated_box(boxes, iou_th=0.7)
         return [STrack(tlbr_to_tlwh(boxes[k]), 1, embs[k], self.buffer_size, obs[k], ac=True) for k in keep_idx]
+
+
+# ======================================================================================
+# clip driver: data/single_video.py::LoadOutputsFromMask2Former + test_mots_from_mask2former.py::eval_seq
+# ======================================================================================
+def frame_observations(pan_mask, query_feat_dict, num_classes):
+    """single_video.py:49-85: one binary mask per panoptic id of the frame (void = ``num_classes`` dropped, ids in the
+    sorted order of ``np.unique``), with its query feature (the mean over the merged queries of a stuff segment) and
+    class id (``id % INSTANCE_OFFSET``).  -> (obs int array [n,H,W] or empty, [dict(query_feat, cls_id)])."""
+    from .mask2former import INSTANCE_OFFSET
+    object_ids = [i for i in np.unique(pan_mask).tolist() if i != num_classes]
+    if not object_ids:
+        return np.array([]), []
+    assert len(query_feat_dict) == len(object_ids), 'Masks and query feats should match!'
+    masks, feats = [], []
+    for oid in object_ids:
+        masks.append((pan_mask == oid).astype(np.int64))
+        qf = [np.asarray(x).squeeze() for x in query_feat_dict[oid]]
+        feats.append(dict(query_feat=qf[0] if len(qf) == 1 else np.stack(qf).mean(axis=0), cls_id=oid % INSTANCE_OFFSET))
+    return np.stack(masks), feats
+
+
+def track_clip(outputs, frames, tracker_cfg, num_classes, app_model):
+    """eval_seq (test_mots_from_mask2former.py:29-95) without the file / plotting side effects: per-frame IPS results
+    (``pan_results``, ``query_feats``) -> MaskAssociationTracker.update -> (results, query_feat_tubes).
+
+    ``frames``: the normalised frames the appearance network sees ([3,H,W] tensors, ``tracker_cfg.common.im_mean/std``
+    already applied), one per output.  ``results`` rows: (frame id (1-based), tlwhs * down_factor, masks as dicts
+    ``{size, counts (COCO RLE string), class_id}``, track ids) -- what ``write_mots_results`` writes to masks.txt."""
+    from . import tubes
+    BaseTrack.reset_count()
+    tracker = MaskAssociationTracker(tracker_cfg, app_model)
+    results = []
+    frame_id = -1
+    for frame_id, (out, img) in enumerate(zip(outputs, frames)):
+        obs, query_feats = frame_observations(np.asarray(out['pan_results']), out['query_feats'], num_classes)
+        if len(obs) == 0:
+            results.append((frame_id + 1, [], [], []))
+            continue
+        targets, _ = tracker.update(img, None, obs, query_feats, 0)
+        tlwhs, ids, masks = [], [], []
+        for t in targets:
+            m = np.asarray(t.mask).astype(np.uint8)
+            masks.append(dict(size=list(m.shape), counts=tubes.rle_string(tubes.rle_counts(m)), class_id=t.cls_id))
+            tlwhs.append(t.tlwh * tracker_cfg.common.down_factor)
+            ids.append(t.track_id)
+        results.append((frame_id + 1, tlwhs, masks, ids))
+    tubes_out = [t.complete_empty_postfix(frame_id) for t in tracker.query_feat_tubes]
+    return results, tubes_out
+
+
+def mots_rows(results):
+    """write_mots_results (utils/io.py:14-37): the lines of quantitive/masks.txt."""
+    return [f'{fid} {tid} {rle["class_id"]} {rle["size"][0]} {rle["size"][1]} {rle["counts"]}'
+            for fid, _, rles, tids in results for rle, tid in zip(rles, tids) if tid >= 0]

@@ -68,3 +68,47 @@ if __name__ == '__main__':
         golden.append(dict(c, out_labels=lab.tolist(), out_masks=msk.tolist()))
     json.dump(golden, open(os.path.join(HERE, 'train_gt.json'), 'w'))
     print('wrote', len(golden), 'cases', [np.asarray(g['out_masks']).shape for g in golden])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# frame unpacking of the IPS tracker driver: LoadOutputsFromMask2Former._get_binary_masks_and_query_feats /
+# _unify_query_feat_dim (models/unitrack/data/single_video.py:49-85), executed from the reference file (two methods only: the
+# module imports cv2 / torchvision at module scope; `np.int` no longer exists in numpy 2, so the namespace maps it to int)
+def load_single_video_methods():
+    src = '/root/reference/models/unitrack/data/single_video.py'
+    tree = ast.parse(open(src).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'LoadOutputsFromMask2Former')
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ('_get_binary_masks_and_query_feats', '_unify_query_feat_dim')]
+
+    class NP:
+        int = int
+
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+    ns = {'np': NP(), 'INSTANCE_OFFSET': 1000}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), src, 'exec'), ns)
+    return type('Loader', (), {'num_classes': 126, '_get_binary_masks_and_query_feats': ns['_get_binary_masks_and_query_feats'],
+                               '_unify_query_feat_dim': ns['_unify_query_feat_dim']})()
+
+
+def frame_cases():
+    rng = np.random.default_rng(3)
+    out = []
+    for ids in ([126, 1005, 2005, 120], [126], [3007, 121, 1003], [120, 121, 122]):
+        pan = rng.choice(ids, size=(6, 9)).astype(np.int32)
+        present = [i for i in np.unique(pan).tolist() if i != 126]
+        qf = {i: [rng.standard_normal((1, 8)).astype(np.float32) for _ in range(1 if i >= 1000 else int(rng.integers(1, 4)))] for i in present}
+        out.append((pan, qf))
+    return out
+
+
+if __name__ == '__main__':
+    loader = load_single_video_methods()
+    golden = []
+    for pan, qf in frame_cases():
+        masks, feats = loader._get_binary_masks_and_query_feats(pan, qf)
+        golden.append(dict(pan=pan.tolist(), query_feats={str(k): [x.tolist() for x in v] for k, v in qf.items()},
+                           masks=np.asarray(masks).tolist(), feats=[dict(query_feat=np.asarray(f['query_feat']).tolist(), cls_id=int(f['cls_id'])) for f in feats]))
+    json.dump(golden, open(os.path.join(HERE, 'tracker_frames.json'), 'w'))
+    print('wrote', len(golden), 'frame cases', [np.asarray(g['masks']).shape for g in golden])

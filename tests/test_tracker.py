@@ -235,3 +235,74 @@ def test_mask_tracker_extract_emb_vs_oracle():
     assert embs[2].shape == (32, 40)      # empty mask: random template, as the reference
     dets = tracker.prepare_obs(torch.zeros(3, H, W), None, obs)
     assert len(dets) == 3 and all(d.curr_feat.shape[1] == 32 for d in dets)
+
+
+def test_frame_observations_match_reference_golden():
+    """tracker.frame_observations against the reference's own LoadOutputsFromMask2Former._get_binary_masks_and_query_feats
+    (golden vectors from tests/golden/make_golden_train_gt.py): id order, void dropped, binary masks, class ids, the mean
+    query feature of merged stuff segments, the empty frame."""
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'tracker_frames.json')))
+    for c in golden:
+        qf = {int(k): [np.asarray(x, np.float32) for x in v] for k, v in c['query_feats'].items()}
+        masks, feats = trk.frame_observations(np.asarray(c['pan'], np.int32), qf, 126)
+        assert np.asarray(masks).tolist() == c['masks']
+        assert [f['cls_id'] for f in feats] == [f['cls_id'] for f in c['feats']]
+        for a, b in zip(feats, c['feats']):
+            assert np.allclose(a['query_feat'], np.asarray(b['query_feat'], np.float32), atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_track_clip_links_moving_segments():
+    """tracker.track_clip (eval_seq of test_mots_from_mask2former.py:29-95) on a synthetic IPS clip: three segments drift
+    across 8 frames (one frame is all void, one segment is missing for two frames).  Every segment keeps ONE track id, the
+    masks.txt rows decode back to the panoptic segments, and the query-feature tubes are complete with None where the
+    track was not seen (positions follow the reference's quirk for void frames, see the end of the test)."""
+    from openpvsg_b200 import tubes
+    H, W, T = 96, 160, 8
+    rng = np.random.default_rng(0)
+    protos = rng.standard_normal((3, 32)).astype(np.float32)
+    ids = [1005, 2005, 120]                                   # two instances of thing class 5, one stuff segment
+
+    def boxes(t):
+        return [(10 + 4 * t, 10, 30, 30), (60, 20 + 3 * t, 36, 28), (100 - 3 * t, 50, 40, 36)]
+
+    outputs, frames, feats_per_frame = [], [], []
+    for t in range(T):
+        pan = np.full((H, W), 126, np.int32)
+        qf = {}
+        for k, (x, y, w, h) in enumerate(boxes(t)):
+            if t == 4 or (k == 1 and t in (2, 3)):
+                continue
+            pan[y:y + h, x:x + w] = ids[k]
+            qf[ids[k]] = [np.full((1, 256), float(k + 1), np.float32)]
+        qf = {i: v for i, v in qf.items() if (pan == i).any()}
+        # appearance map consistent with the panoptic map: the cell whose top-left pixel belongs to segment k carries proto k
+        cell = pan[::8, ::8]
+        fmap = np.zeros((32, H // 8, W // 8), np.float32)
+        for k, i in enumerate(ids):
+            fmap[:, cell == i] = protos[k][:, None]
+        outputs.append(dict(pan_results=pan, query_feats=qf))
+        frames.append(torch.zeros(3, H, W))
+        feats_per_frame.append(torch.from_numpy(fmap)[None])
+    it = iter(f for t, f in enumerate(feats_per_frame) if t != 4)      # the void frame never reaches the appearance network
+    app = lambda img: next(it).cuda()                         # noqa: E731  the appearance map of the frame being tracked
+    cfg = to_cfg(fx.tracker_cfg())
+    results, qtubes = trk.track_clip(outputs, frames, cfg, 126, app)
+    assert len(results) == T and results[4] == (5, [], [], [])
+    seen = {}
+    for fid, tlwhs, masks, tids in results:
+        pan = outputs[fid - 1]['pan_results']
+        for m, tid in zip(masks, tids):
+            dec = tubes.rle_decode(m['counts'], H, W).astype(bool)
+            seg = [i for i in ids if np.array_equal(dec, pan == i)]
+            assert len(seg) == 1, (fid, tid)
+            assert m['class_id'] == seg[0] % 1000
+            seen.setdefault(seg[0], set()).add(tid)
+    assert all(len(v) == 1 for v in seen.values()) and len({next(iter(v)) for v in seen.values()}) == 3, seen
+    rows = trk.mots_rows(results)
+    assert len(rows) == sum(len(r[3]) for r in results) and rows[0].split()[0] == '1' and rows[0].split()[3:5] == [str(H), str(W)]
+    assert len(qtubes) == 3 and all(len(q.qf_tube) == T for q in qtubes)
+    missing = {tuple(i for i, x in enumerate(q.qf_tube) if x is None) for q in qtubes}
+    # as in the reference, an all-void frame never reaches tracker.update, so the tubes index TRACKER frames: the void
+    # frame shows up as one missing entry at the end (complete_empty_postfix), not at position 4
+    assert missing == {(7,), (2, 3, 7)}
