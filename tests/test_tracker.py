@@ -306,3 +306,15 @@ def test_track_clip_links_moving_segments():
     # as in the reference, an all-void frame never reaches tracker.update, so the tubes index TRACKER frames: the void
     # frame shows up as one missing entry at the end (complete_empty_postfix), not at position 4
     assert missing == {(7,), (2, 3, 7)}
+
+
+def test_track_clip_all_void_clip():
+    """No segment in any frame: the tracker is never called, every result row is empty, there are no tubes (CPU: the
+    appearance network is never reached)."""
+    outputs = [dict(pan_results=np.full((8, 12), 126, np.int32), query_feats={}) for _ in range(3)]
+
+    def never(img):
+        raise AssertionError('appearance network called on a void clip')
+
+    results, qtubes = trk.track_clip(outputs, [None] * 3, to_cfg(fx.tracker_cfg()), 126, never)
+    assert results == [(1, [], [], []), (2, [], [], []), (3, [], [], [])] and qtubes == [] and trk.mots_rows(results) == []

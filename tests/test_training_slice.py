@@ -626,3 +626,31 @@ def test_image_detector_forward_train():
     want = ol.loss_single(ocls[-1], omask[-1][:, None], [t.cpu() for t in labels], [m.cpu().float()[:, None] for m in masks], a, lambda n: l[:n])
     for x, y, n in zip(got, want[:3], ('loss_cls', 'loss_mask', 'loss_dice')):
         _close(x, y, 5e-4, n)
+
+
+def test_loss_single_mixed_empty_and_ragged_targets():
+    """Edge cases of the batched assignment: a clip without ground truth between clips with 1 and 5 targets (ragged cost
+    matrices in one host round trip); labels of unmatched queries stay background; the empty clip contributes only to the class loss; gradients flow to every clip."""
+    from openpvsg_b200 import losses
+    from oracle import losses as ol
+    g = torch.Generator().manual_seed(4)
+    B, T, Q, h, w, K = 3, 1, 12, 16, 24, 200
+    cls = torch.randn(B, Q, 127, generator=g)
+    masks = torch.randn(B, T, Q, h, w, generator=g)
+    gts = [torch.rand(1, T, h, w, generator=g) > 0.5, torch.zeros(0, T, h, w, dtype=torch.bool), torch.rand(5, T, h, w, generator=g) > 0.5]
+    labels = [torch.tensor([7]), torch.zeros(0, dtype=torch.int64), torch.tensor([1, 2, 3, 120, 125])]
+    apts = torch.rand(1, K, 2, generator=g)
+    lpts = torch.rand(6, K, 2, generator=g)
+    cc, mc = cls.clone().requires_grad_(True), masks.clone().requires_grad_(True)
+    wc, wm, wd, wlabels, wpos = ol.loss_single(cc, mc, labels, [m.float() for m in gts], apts, lambda n: lpts[:n])
+    (wc + wm + wd).backward()
+    cd, md = cls.cuda().requires_grad_(True), masks.cuda().requires_grad_(True)
+    lc, lm, ld = losses.loss_single(cd, md, [t.cuda() for t in labels], [m.cuda() for m in gts], assign_points=apts.cuda(),
+                                    loss_points=lpts.cuda(), num_points=K)
+    (lc + lm + ld).backward()
+    for a, b, n in ((lc, wc, 'loss_cls'), (lm, wm, 'loss_mask'), (ld, wd, 'loss_dice')):
+        _close(a, b, 2e-5, n)
+    _close(cd.grad, cc.grad, 1e-6, 'grad cls_scores')
+    _close(md.grad, mc.grad, 1e-6, 'grad mask_preds')
+    assert float(md.grad[1].abs().max()) == 0.0 and float(md.grad[0].abs().max()) > 0 and float(md.grad[2].abs().max()) > 0
+    assert int((wlabels[1] != 126).sum()) == 0 and int((wlabels[2] != 126).sum()) == 5

@@ -177,6 +177,20 @@ def test_minvis_parallel_linking_equals_sequential_chain():
         assert torch.equal(got, _sequential_minvis(e))
 
 
+def test_single_process_collectives_are_noops():
+    """world size 1 (no process group): the gradient exchange and the parameter broadcast do nothing, the MinVIS linking of a
+    one-frame clip is the identity."""
+    from openpvsg_b200 import dist_train
+    model = torch.nn.Linear(3, 2)
+    model(torch.ones(1, 3)).sum().backward()
+    before = [p.grad.clone() for p in model.parameters()]
+    assert dist_train.allreduce_gradients(list(model.parameters())) is None and dist_train.world() == 1
+    dist_train.broadcast_parameters(model)
+    assert all(torch.equal(a, p.grad) for a, p in zip(before, model.parameters()))
+    e = _minvis_embeds(1, Q=5)
+    assert tubes.minvis_link_sharded(e, 1, _host_solve, _host_compose).tolist() == [[0, 1, 2, 3, 4]]
+
+
 def _minvis_worker(rank, world, port, embeds, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
