@@ -422,6 +422,12 @@ int pvsg_gather_pairs(const float* sub, const float* obj, const int32_t* pairs, 
  * models/relation_head/base.py:26-40 and transformer.py:35-56 (nn.TransformerEncoderLayer self-attention) and the
  * decoder cross-attention of models/mask2former/mask2former_head.py:457-468. */
 int64_t pvsg_attention_t5_workspace_bytes(int B, int H, int Lq, int Lk, int D);
+/* same, also returning lse [B,H,Lq] = log sum_k exp(scale q.k + mask) per row: what pvsg_attention_train_backward needs, so the
+ * training forward of the decoder's attention runs on the tcgen05 kernel too. */
+int pvsg_attention_t5_lse(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
+                          const uint8_t* mask, const int32_t* row_open, float* out, float* lse, void* ws, int B, int H, int Lq,
+                          int Lk, int Dh, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts,
+                          int64_t o_bs, int64_t o_ts, float scale, void* stream);
 int pvsg_attention_t5(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
                       const uint8_t* mask, const int32_t* row_open, float* out, void* workspace, int B, int H, int Lq,
                       int Lk, int D, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts,

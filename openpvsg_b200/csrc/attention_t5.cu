@@ -60,6 +60,7 @@ struct T5Args {
     float* out;
     float* part_o;
     float* part_ml;
+    float* lse;           // optional [B, H, Lq]: natural-log sum-exp of the scaled, masked scores (training backward)
     int H, Lq, Lk;
     int64_t q_bs, q_ts, o_bs, o_ts;
     float scale;
@@ -390,6 +391,7 @@ attn_t5_kernel(const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < OD; i += 4)
                     *reinterpret_cast<float4*>(op + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+                if (part == 0 && a.lse) a.lse[(int64_t)bh * a.Lq + row] = l > 0.f ? m / kLog2e + logf(l) : -INFINITY;
             } else {
                 const int64_t prow = ((int64_t)bh * a.Lq + row) * a.nsplit + split;
                 float* op = a.part_o + prow * D + part * OD;
@@ -412,8 +414,8 @@ attn_t5_kernel(const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant
 
 // one thread per (bh, q, d): out = sum_s o_s exp(m_s - M) / sum_s l_s exp(m_s - M)
 __global__ void __launch_bounds__(256) attn_t5_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
-                                                              float* __restrict__ out, int H, int Lq, int nsplit, int64_t o_bs,
-                                                              int64_t o_ts, int64_t total, int D) {
+                                                              float* __restrict__ out, float* __restrict__ lse, int H, int Lq,
+                                                              int nsplit, int64_t o_bs, int64_t o_ts, int64_t total, int D) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int d = (int)(i % D);
@@ -432,6 +434,7 @@ __global__ void __launch_bounds__(256) attn_t5_combine_kernel(const float* __res
         den = fmaf(part_ml[(row * nsplit + s) * 2 + 1], c, den);
     }
     out[b * o_bs + (int64_t)qi * o_ts + h * D + d] = den > 0.f ? num / den : 0.f;
+    if (lse && d == 0) lse[row] = den > 0.f ? M + logf(den) : -INFINITY;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -513,10 +516,10 @@ extern "C" int64_t pvsg_attention_t5_workspace_bytes(int B, int H, int Lq, int L
     return (int64_t)B * H * Lq * ns * (D + 2) * sizeof(float) + 16;
 }
 
-extern "C" int pvsg_attention_t5(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
-                                 const uint8_t* mask, const int32_t* row_open, float* out, void* ws, int B, int H, int Lq, int Lk,
-                                 int Dh, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts,
-                                 int64_t o_bs, int64_t o_ts, float scale, void* stream) {
+static int attention_t5_impl(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
+                             const uint8_t* mask, const int32_t* row_open, float* out, float* lse, void* ws, int B, int H, int Lq, int Lk,
+                             int Dh, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts,
+                             int64_t o_bs, int64_t o_ts, float scale, void* stream) {
     PVSG_CHECK_ARG(Q && K_hi && K_lo && V_hi && V_lo && out && B > 0 && H > 0 && Lq > 0 && Lk > 0);
     if (Dh != 32 && Dh != 128) return PVSG_ERR_UNSUPPORTED;
     PVSG_CHECK_ARG((k_bs | k_ts | v_bs | v_ts) % 8 == 0 && (q_bs | q_ts | o_bs | o_ts) % 4 == 0);
@@ -534,7 +537,7 @@ extern "C" int pvsg_attention_t5(const float* Q, const void* K_hi, const void* K
         tok_dim = td;
     }
     T5Args a;
-    a.Q = Q; a.mask = mask; a.row_open = row_open; a.out = out;
+    a.Q = Q; a.mask = mask; a.row_open = row_open; a.out = out; a.lse = lse;
     a.part_o = reinterpret_cast<float*>(ws);
     a.part_ml = a.part_o ? a.part_o + (int64_t)B * H * Lq * ns * Dh : nullptr;
     a.H = H; a.Lq = Lq; a.Lk = Lk;
@@ -547,7 +550,24 @@ extern "C" int pvsg_attention_t5(const float* Q, const void* K_hi, const void* K
     if (rc != PVSG_OK) return rc;
     if (ns > 1) {
         const int64_t total = (int64_t)B * H * Lq * Dh;
-        attn_t5_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.part_o, a.part_ml, out, H, Lq, ns, o_bs, o_ts, total, Dh);
+        attn_t5_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.part_o, a.part_ml, out, lse, H, Lq, ns, o_bs, o_ts, total, Dh);
     }
     return pvsg_launch_status();
+}
+
+extern "C" int pvsg_attention_t5(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
+                                 const uint8_t* mask, const int32_t* row_open, float* out, void* ws, int B, int H, int Lq, int Lk,
+                                 int Dh, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts,
+                                 int64_t o_bs, int64_t o_ts, float scale, void* stream) {
+    return attention_t5_impl(Q, K_hi, K_lo, V_hi, V_lo, mask, row_open, out, nullptr, ws, B, H, Lq, Lk, Dh, q_bs, q_ts, k_bs, k_ts, v_bs,
+                             v_ts, o_bs, o_ts, scale, stream);
+}
+
+extern "C" int pvsg_attention_t5_lse(const float* Q, const void* K_hi, const void* K_lo, const void* V_hi, const void* V_lo,
+                                     const uint8_t* mask, const int32_t* row_open, float* out, float* lse, void* ws, int B, int H,
+                                     int Lq, int Lk, int Dh, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
+                                     int64_t v_ts, int64_t o_bs, int64_t o_ts, float scale, void* stream) {
+    PVSG_CHECK_ARG(lse);
+    return attention_t5_impl(Q, K_hi, K_lo, V_hi, V_lo, mask, row_open, out, lse, ws, B, H, Lq, Lk, Dh, q_bs, q_ts, k_bs, k_ts, v_bs,
+                             v_ts, o_bs, o_ts, scale, stream);
 }

@@ -58,6 +58,7 @@ SIGNATURES = {
     'pvsg_attention_tc': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_attention_t5_workspace_bytes': (L, [I, I, I, I, I]),
     'pvsg_attention_t5': (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
+    'pvsg_attention_t5_lse': (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, L, F, P]),
     'pvsg_mask_logits': (I, [P, P, P, P, P, I, I, L, I, P]),
     'pvsg_panoptic_fuse': (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, F, D, I, I, P, P, P, P, P, P]),
     'pvsg_instance_masks': (I, [P, P, I, I, I, I, I, I, I, I, I, P, P, P, P]),

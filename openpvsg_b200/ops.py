@@ -828,11 +828,23 @@ def _attn_train_args(q, k, v, num_heads, mask, row_open):
 
 
 def attention_train_forward(q, k, v, num_heads, mask=None, row_open=None):
-    """Training-time attention: -> (out [B,Lq,E], lse [B,H,Lq])."""
+    """Training-time attention: -> (out [B,Lq,E], lse [B,H,Lq]).  On the tcgen05 engine the forward is the inference kernel
+    (csrc/attention_t5.cu) on freshly split K / V planes, with the row log-sum-exp as a second output; the exact-fp32 SIMT
+    kernel (PVSG_ENGINE=simt, or layouts the tensor-map path does not take) computes the same pair."""
     lib = _l.load()
     B, Lq, Lk, E = _attn_train_args(q, k, v, num_heads, mask, row_open)
     out = torch.empty(B, Lq, E, device=q.device, dtype=torch.float32)
     lse = torch.empty(B, num_heads, Lq, device=q.device, dtype=torch.float32)
+    if (ENGINE[0] == 'tc' and _l.ATTN_IMPL[0] == 't5' and B * num_heads <= 65535 and q.data_ptr() % 16 == 0
+            and q.stride(0) % 4 == 0 and q.stride(1) % 4 == 0):
+        k_hi, k_lo = split_bf16(k.contiguous())
+        v_hi, v_lo = split_bf16(v.contiguous())
+        ws = torch.empty(lib.pvsg_attention_t5_workspace_bytes(B, num_heads, Lq, Lk, 32), device=q.device, dtype=torch.uint8)
+        _l.check(lib.pvsg_attention_t5_lse(_ptr(q), _ptr(k_hi), _ptr(k_lo), _ptr(v_hi), _ptr(v_lo), _ptr(mask), _ptr(row_open),
+                                           _ptr(out), _ptr(lse), _ptr(ws), B, num_heads, Lq, Lk, 32, q.stride(0), q.stride(1),
+                                           k_hi.stride(0), k_hi.stride(1), v_hi.stride(0), v_hi.stride(1), out.stride(0),
+                                           out.stride(1), 32 ** -0.5, _stream()), 'pvsg_attention_t5_lse')
+        return out, lse
     _l.check(lib.pvsg_attention_train_forward(_ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(row_open), _ptr(out), _ptr(lse), B,
                                               num_heads, Lq, Lk, 32, q.stride(0), q.stride(1), k.stride(0), k.stride(1),
                                               v.stride(0), v.stride(1), out.stride(0), out.stride(1), 32 ** -0.5, _stream()),
