@@ -127,16 +127,17 @@ __global__ void __launch_bounds__(128) weighted_ce_kernel(const float* __restric
 }
 
 // ---- Hungarian matching cost (mmdet MaskHungarianAssigner: ClassificationCost + CrossEntropyLossCost + DiceCost) ------
-// one CTA per query: the per-point terms of the prediction (softplus, sigmoid) are computed once and shared by all ground
+// one CTA (32 warps: the loop is a chain of transcendentals, latency-bound with fewer) per query: the per-point terms of the prediction (softplus, sigmoid) are computed once and shared by all ground
 // truths; threads stride over the K points, ground truths in chunks of MC_G register accumulators.  (First version: one warp
 // per (query, gt) pair = 50 CTAs recomputing the transcendental terms per pair: 139 us per call, 22 ms per training step.)
 constexpr int MC_G = 8;
-__global__ void __launch_bounds__(256) match_cost_kernel(const float* __restrict__ cls, const int64_t* __restrict__ labels,
+__global__ void __launch_bounds__(1024) match_cost_kernel(const float* __restrict__ cls, const int64_t* __restrict__ labels,
                                                          const float* __restrict__ pred, const float* __restrict__ gt, int Q, int G,
                                                          int C, int K, float w_cls, float w_mask, float w_dice, float eps,
                                                          float* __restrict__ cost) {
-    __shared__ float sh[8][3 * MC_G + 1];
+    __shared__ float sh[32][3 * MC_G + 1];
     __shared__ float s_mx, s_se;
+    const int nwarp = blockDim.x >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x;
     // classification cost: -softmax(cls[q])[label_g]   (warp 0)
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) match_cost_kernel(const float* __restrict
         if (threadIdx.x < ng) {
             const int j = threadIdx.x;
             float tb = 0.f, ta = 0.f, tc = 0.f, tbs = 0.f;
-            for (int w = 0; w < 8; ++w) { tb += sh[w][3 * j]; ta += sh[w][3 * j + 1]; tc += sh[w][3 * j + 2]; tbs += sh[w][3 * MC_G]; }
+            for (int w = 0; w < nwarp; ++w) { tb += sh[w][3 * j]; ta += sh[w][3 * j + 1]; tc += sh[w][3 * j + 2]; tbs += sh[w][3 * MC_G]; }
             const float prob = expf(xr[labels[g0 + j]] - s_mx) / s_se;
             cost[(int64_t)q * G + g0 + j] = -w_cls * prob + w_mask * tb / (float)K + w_dice * (1.f - (2.f * ta + eps) / (tbs + tc + eps));
         }
@@ -285,7 +286,7 @@ extern "C" int pvsg_mask_match_cost(const float* cls_logits, const int64_t* gt_l
                                     int Q, int G, int C, int K, float w_cls, float w_mask, float w_dice, float dice_eps, float* cost,
                                     void* stream) {
     PVSG_CHECK_ARG(cls_logits && gt_labels && pred_points && gt_points && cost && Q > 0 && G > 0 && C > 0 && K > 0);
-    match_cost_kernel<<<Q, 256, 0, as_stream(stream)>>>(cls_logits, gt_labels, pred_points, gt_points, Q, G, C, K, w_cls,
+    match_cost_kernel<<<Q, 1024, 0, as_stream(stream)>>>(cls_logits, gt_labels, pred_points, gt_points, Q, G, C, K, w_cls,
                                                                       w_mask, w_dice, dice_eps, cost);
     return pvsg_launch_status();
 }
