@@ -286,3 +286,45 @@ def get_runner(detector, meta, rescale=True, batch=1, rle=False, debug_masks=Fal
     if key not in runners:
         runners[key] = FrameRunner(detector, meta, rescale, batch, rle=rle, debug_masks=debug_masks)
     return runners[key]
+
+
+def batch_schedule(n, batch, ramp=True):
+    """Batch sizes for n frames through runners of ``batch`` and ``batch // 2`` frames: a half batch first and last, so
+    that the pipeline's fill (the first host->device copy, which nothing overlaps) and drain (the last device->host copy
+    and result building) cost half a batch each.  n = 100, batch = 20 -> [10, 20, 20, 20, 20, 10]."""
+    half = batch // 2
+    if not ramp or half < 1 or n < 2 * batch:
+        return [batch] * (n // batch) + ([n % batch] if n % batch else [])
+    sched = [half]
+    left = n - half
+    while left > batch + half:
+        sched.append(batch)
+        left -= batch
+    if left > batch:                      # batch < left <= batch + half
+        sched += [left - half, half] if left - half <= batch else [batch, left - batch]
+    else:
+        sched.append(left)
+    return [b for b in sched if b > 0]
+
+
+@torch.no_grad()
+def stream_frames(detector, meta, frames, batch, consume, rescale=True, rle=False, ramp=True):
+    """Software-pipelined inference of a list of frames (pinned host or device tensors [3,H,W]) through the CUDA-graph
+    runners: batch i+1 is submitted before batch i is collected; ``consume(result)`` is called per frame, in order, with
+    views of the runner's pinned ring.  With ``ramp`` the first and last batch are half-sized (``batch_schedule``)."""
+    if getattr(detector, '_runners', None) is None:
+        enable_cuda_graph(detector)
+    pend = None
+    i = 0
+    for b in batch_schedule(len(frames), batch, ramp):
+        size = batch if b > batch // 2 else max(batch // 2, 1)        # the runner whose capacity fits this batch
+        runner = get_runner(detector, meta, rescale, batch=size, rle=rle)
+        nxt = (runner, runner.submit(frames[i:i + b]))
+        i += b
+        if pend is not None:
+            for r in pend[0].collect(pend[1], copy=False):
+                consume(r)
+        pend = nxt
+    if pend is not None:
+        for r in pend[0].collect(pend[1], copy=False):
+            consume(r)
