@@ -177,6 +177,20 @@ def test_minvis_parallel_linking_equals_sequential_chain():
         assert torch.equal(got, _sequential_minvis(e))
 
 
+def test_batch_schedule_ramps_and_covers_every_frame():
+    """engine.batch_schedule: half-sized first / last batch, every batch within the runner capacity, all frames covered."""
+    from openpvsg_b200 import engine
+    assert engine.batch_schedule(100, 20) == [10, 20, 20, 20, 20, 10]
+    assert engine.batch_schedule(100, 20, ramp=False) == [20] * 5
+    assert engine.batch_schedule(39, 20) == [20, 19] and engine.batch_schedule(7, 20) == [7] and engine.batch_schedule(0, 20) == []
+    for n in range(1, 130):
+        for b in (1, 2, 8, 20):
+            s = engine.batch_schedule(n, b)
+            assert sum(s) == n and all(0 < x <= b for x in s), (n, b, s)
+            if n >= 2 * b and b >= 2:
+                assert s[0] == b // 2
+
+
 def test_single_process_collectives_are_noops():
     """world size 1 (no process group): the gradient exchange and the parameter broadcast do nothing, the MinVIS linking of a
     one-frame clip is the identity."""
