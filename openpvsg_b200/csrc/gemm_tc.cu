@@ -36,12 +36,13 @@ constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_STAGE_BYTES = 4096;      // per epilogue warp: 32 x 32 fp32, or 32 x 32 bf16 hi | lo
 constexpr int PATCH_H = 8, PATCH_W = 16;   // conv M tile = 8 x 16 output pixels
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-// Tile width BN = 128 (3-stage ring) or 256 (2-stage ring).  The wide tile reads each A k-block
+// Tile width BN = 64 (4-stage ring; N <= 64: the 64-channel convolutions of layer1 / the stem, where a 128-wide tile spends
+// half of every MMA on padding), 128 (3-stage ring) or 256 (2-stage ring).  The wide tile reads each A k-block
 // once per 256 output columns instead of once per 128: the engine is L2->SM bandwidth bound
 // (four bf16 planes per k-block), so operand bytes per flop, not MMA issue, set its speed.
 template <int BN>
 struct Cfg {
-    static constexpr int STAGES = BN == 128 ? 3 : 2;
+    static constexpr int STAGES = BN == 64 ? 4 : (BN == 128 ? 3 : 2);
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int DATA_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
@@ -908,6 +909,8 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
 int pick_bn(int64_t tiles_m, int64_t N) {
     static const int forced = [] { const char* e = getenv("PVSG_TC_BN"); return e ? atoi(e) : 0; }();
     if (forced == 128 || forced == 256) return forced;
+    static const bool narrow = getenv("PVSG_TC_NO_BN64") == nullptr;
+    if (narrow && N <= 64) return 64;
     const int64_t t256 = (N + 255) / 256;
     if (t256 * 256 != ((N + 127) / 128) * 128) return 128;
     return tiles_m * t256 >= 4 * (int64_t)sm_count() ? 256 : 128;
@@ -916,7 +919,8 @@ int pick_bn(int64_t tiles_m, int64_t N) {
 }  // namespace
 
 int pvsg_internal::configure_gemm_tc() {
-    const int rc = configure_tc<128>();
+    int rc = configure_tc<64>();
+    if (!rc) rc = configure_tc<128>();
     return rc ? rc : configure_tc<256>();
 }
 
@@ -978,6 +982,7 @@ extern "C" int pvsg_linear_tc(const void* A_hi, const void* A_lo, int64_t lda, c
     p.mask = mask; p.row_open = row_open;
     p.M = M; p.N = N; p.ldc = ldc; p.ldr = ldr; p.num_kb = (int)(K / BK); p.act = act; p.conv = 0;
     p.tiles_m = (int)((M + BM - 1) / BM); p.tiles_n = (int)((N + bn - 1) / bn);
+    if (bn == 64) return launch_tc<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
     return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream))
                      : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
 }
@@ -1010,6 +1015,7 @@ extern "C" int pvsg_linear_tc_batched(const void* A_hi, const void* A_lo, int64_
     p.M = M; p.N = N; p.ldc = ldc; p.num_kb = (int)(K / BK); p.act = PVSG_ACT_NONE; p.conv = 0;
     p.batch = batch; p.tiles_mb = (int)tiles_mb;
     p.tiles_m = (int)(batch * tiles_mb); p.tiles_n = (int)((N + bn - 1) / bn);
+    if (bn == 64) return launch_tc<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
     return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream))
                      : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, 1, as_stream(stream));
 }
@@ -1042,6 +1048,7 @@ extern "C" int pvsg_conv2d_tc(const void* x_hi, const void* x_lo, const void* w_
     p.tiles_h = tiles_h; p.tiles_w = tiles_w;
     if (tiles_m * ((Cout + 127) / 128) > 0x7fffffffLL) return PVSG_ERR_UNSUPPORTED;
     p.tiles_m = (int)tiles_m; p.tiles_n = (Cout + bn - 1) / bn;
+    if (bn == 64) return launch_tc<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, B, as_stream(stream));
     return bn == 256 ? launch_tc<256>(ta_hi, ta_lo, tb_hi, tb_lo, p, B, as_stream(stream))
                      : launch_tc<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, B, as_stream(stream));
 }
