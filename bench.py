@@ -712,10 +712,9 @@ def main():
         elif api == 'pipelined':
             # the public streaming call: software-pipelined batches, half-sized first / last batch so that the host->device
             # fill and the device->host drain of a clip cost half a batch each (engine.batch_schedule)
-            # (ramp only when one process owns the host: A/B with tools/e2e_ab.py -- 1 GPU 277 vs 280 ms per step with / without,
-            #  8 ranks on one host 317 vs 292 ms: the extra submit / collect round of the ramp costs more than the shorter fill there)
-            engine.stream_frames(det, meta, [frames[i % len(frames)] for i in range(args.frames)], args.batch, consume,
-                                 ramp=world == 1)
+            # (the graphs of the two runners are ordered by an event: left to run concurrently on their own streams they contend
+            #  for the SMs -- tools/e2e_ab.py at 8 GPUs: ramp 274 ms, plain 287 ms, ramp with unordered runners 313 ms per step)
+            engine.stream_frames(det, meta, [frames[i % len(frames)] for i in range(args.frames)], args.batch, consume)
         else:
             # same kernels, software-pipelined: frame i+1 is submitted before frame i is collected
             runner = engine.get_runner(det, meta, True, batch=args.batch)
@@ -887,7 +886,7 @@ def main():
                 config=workload_config(args, world), tubes=len(linker.object_list),
                 e2e=dict(value=round(e2e, 3), unit='frames/s', h2d_bytes_per_step=in_bytes * args.frames * world,
                          d2h_bytes_per_step=out_bytes * args.frames * world, ms_per_step=round(ms_e2e / args.steps, 3),
-                         api='engine.stream_frames (FrameRunner.submit/collect pipelined; half-sized first / last batch when one process owns the host) on pinned host frames',
+                         api='engine.stream_frames (FrameRunner.submit/collect pipelined, half-sized first / last batch) on pinned host frames',
                          sync_api_value=round(e2e_sync, 3),
                          sync_api=f'model(return_loss=False, rescale=True, img=..., ref_img=...) with {args.batch} samples per call, synchronous',
                          latency_ms_batch1=None if lat1 is None else round(lat1, 3),

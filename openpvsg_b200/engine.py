@@ -26,6 +26,7 @@ from . import ops
 from .mask2former import INSTANCE_OFFSET, bbox2result
 
 RING = 3
+SERIALISE_RUNNERS = os.environ.get('PVSG_SERIALISE_RUNNERS', '1') != '0'   # stream_frames: order the graphs of different runners
 SYNC_CHUNKS = int(os.environ.get('PVSG_SYNC_CHUNKS', '2'))   # pieces a synchronous multi-sample call is pipelined in (simple_test)
 DEBUG_MASKS = False   # parity tests: every runner also returns the decoder's sign masks and class logits
 _copy_pool = None
@@ -153,10 +154,12 @@ class FrameRunner:
         self.launches_per_frame = (_l.launch_count[0] - n0) / self.batch
 
     @torch.no_grad()
-    def submit(self, imgs):
+    def submit(self, imgs, after=None):
         """imgs: one frame ([1,3,H,W] / [3,H,W]) or a list of up to ``batch`` frames, device or
         pinned host tensors.  Enqueues H2D, the graph and the D2H of its outputs; returns a handle
-        for ``collect``.  A short final batch is padded by repeating its last frame."""
+        for ``collect``.  A short final batch is padded by repeating its last frame.
+        after: optional CUDA event the graph replay waits for (the compute of ANOTHER runner: graphs of
+        two runners live on different streams and would otherwise run concurrently, contending for the SMs)."""
         if torch.is_tensor(imgs):
             imgs = [imgs]
         n = len(imgs)
@@ -189,7 +192,11 @@ class FrameRunner:
             else:
                 for b in range(self.batch):
                     static_in[b].copy_(imgs[min(b, n - 1)].reshape(shape), non_blocking=True)
+            if after is not None:
+                main.wait_event(after)
             self.lane_graph[lane].replay()
+            self.last_compute = torch.cuda.Event()
+            self.last_compute.record(main)
             if self.busy[slot]:
                 main.wait_event(self.events[slot])                   # this slot's previous D2H has finished
             for k, v in out.items():
@@ -319,7 +326,8 @@ def stream_frames(detector, meta, frames, batch, consume, rescale=True, rle=Fals
     for b in batch_schedule(len(frames), batch, ramp):
         size = batch if b > batch // 2 else max(batch // 2, 1)        # the runner whose capacity fits this batch
         runner = get_runner(detector, meta, rescale, batch=size, rle=rle)
-        nxt = (runner, runner.submit(frames[i:i + b]))
+        after = pend[0].last_compute if (pend is not None and pend[0] is not runner and SERIALISE_RUNNERS) else None
+        nxt = (runner, runner.submit(frames[i:i + b], after=after))
         i += b
         if pend is not None:
             for r in pend[0].collect(pend[1], copy=False):

@@ -22,14 +22,16 @@ def step(ramp):
     sink.clear()
 for ramp in (True, False):
     step(ramp)
-res = {True: [], False: []}
+res = {True: [], False: [], 'ramp, runners not ordered': []}
 for rep in range(4):
-    for ramp in (True, False):
+    for ramp in (True, False, 'ramp, runners not ordered'):
+        engine.SERIALISE_RUNNERS = ramp is not 'ramp, runners not ordered'
+        ramp_flag = bool(ramp)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        step(ramp)
+        step(ramp_flag)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device='cuda')
         if world > 1:
@@ -38,5 +40,6 @@ for rep in range(4):
 if rank == 0:
     print('ramp  ', [round(x, 1) for x in res[True]])
     print('plain ', [round(x, 1) for x in res[False]])
+    print('ramp, runners not ordered', [round(x, 1) for x in res['ramp, runners not ordered']])
 if world > 1:
     dist.destroy_process_group()
