@@ -709,8 +709,8 @@ def main():
                     res = det.simple_test(None, None, ref_img=xs[0][None, None], ref_img_metas=[[meta]],
                                           rescale=True)[0][0]
                     consume(res)
-        elif api == 'pipelined':
-            # the public streaming call: software-pipelined batches, half-sized first / last batch so that the host->device
+        elif api in ('pipelined', 'device'):
+            # the public streaming call (pinned host frames: 'pipelined'; frames resident in HBM: 'device'): software-pipelined batches, half-sized first / last batch so that the host->device
             # fill and the device->host drain of a clip cost half a batch each (engine.batch_schedule)
             # (the graphs of the two runners are ordered by an event: left to run concurrently on their own streams they contend
             #  for the SMs -- tools/e2e_ab.py at 8 GPUs: ramp 274 ms, plain 287 ms, ramp with unordered runners 313 ms per step)
