@@ -191,6 +191,20 @@ def test_batch_schedule_ramps_and_covers_every_frame():
                 assert s[0] == b // 2
 
 
+def test_splitk_plan_covers_the_reduction():
+    """ops.splitk_plan (weight-gradient GEMMs): chunk length a multiple of the 64-column k-block, chunks x length covers the
+    token count with less than one chunk of padding, enough chunks to fill the SMs when the output has few tiles."""
+    from openpvsg_b200 import ops
+    for T in (1, 30, 100, 960, 3840, 23040, 368640, 2949120):
+        for M, N in ((64, 64), (256, 576), (2048, 512), (100, 256), (64, 147)):
+            S, Kc, Tp = ops.splitk_plan(T, M, N)
+            assert Kc % 64 == 0 and Tp == S * Kc and Tp >= T and Tp - T < Kc + 64, (T, M, N, S, Kc)
+            tiles = ((M + 127) // 128) * ((N + 127) // 128)
+            if T >= 256 * 296:
+                assert S * tiles >= 148, (T, M, N, S)
+    assert ops.splitk_plan(100, 256, 256) == (1, 128, 128)
+
+
 def test_single_process_collectives_are_noops():
     """world size 1 (no process group): the gradient exchange and the parameter broadcast do nothing, the MinVIS linking of a
     one-frame clip is the identity."""
