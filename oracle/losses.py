@@ -4,6 +4,9 @@ Restates, in plain torch with autograd, ``Mask2FormerVideoHead.loss_single`` / `
 (models/mask2former_vps/mask2former_video_head.py:162-293) together with the mmcv 1.4 / mmdet 2.25 pieces it calls
 (absent from /root/reference: **parity unpinned by the reference**, restated from the pinned versions' published
 algorithm; ``point_sample`` = ``F.grid_sample(2p - 1, align_corners=False)``).  Gradients come from torch autograd.
+Independent pin: dice / sigmoid-BCE losses, the three assignment costs and the point sampling equal the implementation of
+the same published losses in HF transformers' Mask2Former, values and gradients
+(tests/test_oracle_golden.py::test_training_losses_vs_hf_mask2former).
 """
 import torch
 import torch.nn.functional as F

@@ -307,3 +307,37 @@ def test_baseline_relation_models_golden(golden_dir):
     _close(fp, g['fprob'])
     _close(cs, g['cspan'])
     _close(cp, g['cprob'])
+
+
+def test_training_losses_vs_hf_mask2former():
+    """The training-loss restatements (oracle/losses.py: mmdet DiceLoss(naive_dice, eps=1) / sigmoid CrossEntropyLoss /
+    MaskHungarianAssigner costs, mmcv point_sample) against the independent implementation of the same published
+    losses in HF transformers (both port Detectron2's Mask2Former): values AND gradients.  mmdet / mmcv are not in the
+    reference tree, so this is the available pin for the formulas the oracle's training side rests on."""
+    mm, _ = _hf()
+    from oracle import losses as ol
+    g = torch.Generator().manual_seed(2)
+    n, K, Q, G = 5, 300, 12, 4
+    pred = (torch.randn(n, K, generator=g) * 3).requires_grad_(True)
+    tgt = (torch.rand(n, K, generator=g) > 0.6).float()
+    ours = ol.dice_loss(pred, tgt, avg_factor=float(n), eps=1.0, loss_weight=1.0)
+    (g1,) = torch.autograd.grad(ours, pred)
+    p2 = pred.detach().clone().requires_grad_(True)
+    theirs = mm.dice_loss(p2, tgt, n)
+    (g2,) = torch.autograd.grad(theirs, p2)
+    assert torch.allclose(ours, theirs, atol=1e-6) and torch.allclose(g1, g2, atol=1e-7)
+    ours = ol.mask_bce_loss(pred.reshape(-1), tgt.reshape(-1), avg_factor=float(n * K), loss_weight=1.0)
+    theirs = mm.sigmoid_cross_entropy_loss(p2, tgt, n)
+    assert torch.allclose(ours, theirs, atol=1e-6)
+    # assignment costs: class + mask (BCE against ones / zeros) + dice, weights 2 / 5 / 5
+    cls = torch.randn(Q, 127, generator=g)
+    labels = torch.tensor([3, 40, 120, 7])
+    pp = torch.randn(Q, K, generator=g) * 2
+    gp = (torch.rand(G, K, generator=g) > 0.5).float()
+    want = (-2.0 * cls.softmax(-1)[:, labels] + 5.0 * mm.pair_wise_sigmoid_cross_entropy_loss(pp, gp)
+            + 5.0 * mm.pair_wise_dice_loss(pp, gp))
+    assert torch.allclose(ol.match_cost(cls, labels, pp, gp), want, atol=1e-5)
+    # point sampling
+    maps = torch.randn(3, 1, 20, 28, generator=g)
+    pts = torch.rand(3, 50, 2, generator=g)
+    assert torch.allclose(ol.point_sample(maps, pts), mm.sample_point(maps, pts, align_corners=False), atol=1e-6)
