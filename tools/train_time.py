@@ -48,3 +48,9 @@ if os.environ.get('CPROFILE'):
     torch.cuda.synchronize()
     pr.disable()
     pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
+if os.environ.get('NCU'):
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
